@@ -1,0 +1,179 @@
+/*
+ * libmmlst -- B200-native (sm_100a) kernels for MetaMLST's post-alignment allele-calling hot path.
+ *
+ * C ABI: plain pointers and sizes only.  The reference (SegataLab/metamlst, pure Python) has no FFI of its own;
+ * each entry point below names the reference lines it replaces (paths relative to the reference root) and
+ * INTEGRATION.md shows the ctypes binding a maintainer adds at the four Python seams.
+ *
+ * Conventions
+ *   - every call returns 0 on success or a negative MMLST_E_* code; mmlst_last_error() gives the thread-local text;
+ *   - "*_dev" entry points take DEVICE pointers and a cudaStream_t (as void*), launch asynchronously and own nothing;
+ *   - the other entry points take HOST pointers (pinned memory from mmlst_pinned_alloc gives async copies), stage
+ *     through device memory owned by the mmlst_ctx and return after the results are back on the host;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with MMLST_E_CUDA.
+ *
+ * Record streams (structure-of-arrays, produced once per BAM by mmlst_bam_unpack or metamlst_b200.packing)
+ *   score stream   : every BAM record, any order (coordinate-sorted gives run-length aggregation):
+ *                      tid u32 (BAM reference index == allele row), as0 i16 (1st aux field by POSITION),
+ *                      xm3 u8 (4th aux field by POSITION, saturated at 255), qlen u16 (len(SEQ) as SAM prints it),
+ *                      optional orig_idx u32 (index in file order; NULL = identity + idx_base).        9 B / record
+ *   pileup stream  : records ADMITTED by the htslib depth cap, coordinate-sorted, CIGAR already projected on the
+ *                    reference: pos i32, row_off u32 (word offset into planes, row_off[P] = end), reflen u16,
+ *                    as_named i16 / xm_named u8 (AS, XM by NAME), and per record a row of 3 bit-planes x nw words
+ *                    (nw = ceil(reflen/32)), word-interleaved [V_j, B1_j, B0_j], bit i of word j = reference offset
+ *                    32 j + i:  V=1 -> ACGT base with quality >= minqual and code B1B0 (A=0,C=1,G=2,T=3);
+ *                    V=0,B0=1 -> counted non-ACGT base (bin N); V=0,B0=0 -> not in the column (deletion, refskip,
+ *                    quality < minqual, beyond the read).  Rows are padded to an odd number of words.
+ *   count tensor   : u32 [total_columns][5], bins A,C,G,T,N.
+ */
+#ifndef MMLST_H
+#define MMLST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMLST_VERSION 100
+
+enum {
+    MMLST_OK = 0,
+    MMLST_E_ARG = -1,        /* bad argument */
+    MMLST_E_CUDA = -2,       /* CUDA runtime error / no device */
+    MMLST_E_IO = -3,         /* file cannot be read */
+    MMLST_E_BAM = -4,        /* malformed BAM / aux fields the reference would crash on (metamlst.py:107-110) */
+    MMLST_E_UNSORTED = -5,   /* pileup needs coordinate order (htslib "The input is not sorted") */
+    MMLST_E_PAIRED = -6,     /* BAM_FPROPER_PAIR record: htslib overlap handling (H2) refused, never silently differs */
+    MMLST_E_RANGE = -7,      /* value does not fit the packed field (AS outside int16, reflen > 65535, ...) */
+    MMLST_E_NOMEM = -8
+};
+
+typedef struct mmlst_ctx mmlst_ctx;
+
+const char* mmlst_last_error(void);
+int mmlst_version(void);
+int mmlst_device_count(void);
+
+int mmlst_create(int device, mmlst_ctx** out);
+void mmlst_destroy(mmlst_ctx* ctx);
+/* stream owned by the context (cudaStream_t) */
+void* mmlst_stream(mmlst_ctx* ctx);
+int mmlst_sync(mmlst_ctx* ctx);
+
+void* mmlst_pinned_alloc(size_t bytes);
+void mmlst_pinned_free(void* p);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Stage 1 -- per-allele scoring.  Replaces metamlst.py:101-130 (filter + append) and the integer half of :133-151
+ * (sum, hit count).  Per-locus max hit count, penalty, division and round(.,1) stay on the host (H6).
+ *   allow[tid]    : 1 if the record's species passes --filter (metamlst.py:114), else the record is not counted at all
+ *   locus_of[tid] : global locus index of the allele row
+ *   sum_as[tid] += as0, n_hit[tid] += 1 for records with as0 >= minscore && qlen >= min_read_len && xm3 <= max_xm
+ *   first_idx[locus] = min(orig index) over passing records (H5: dict insertion order); caller presets 0xFFFFFFFF
+ *   counters[0] += allowed records (totalReads), counters[1] += allowed but failing (ignoredReads)
+ * Outputs are ACCUMULATED (caller zeroes them), so shards / GPUs can be summed.
+ * --------------------------------------------------------------------------------------------------------------- */
+int mmlst_score_dev(const uint32_t* tid, const int16_t* as0, const uint8_t* xm3, const uint16_t* qlen,
+                    const uint32_t* orig_idx, uint64_t n_rec, uint64_t idx_base,
+                    const uint8_t* allow, const uint32_t* locus_of, uint32_t n_ref,
+                    int minscore, int max_xm, int min_read_len,
+                    int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, uint64_t* counters, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Stage 2 -- pileup base counts.  Replaces cmseq/cmseq.py:527-548 (+ htslib pileup rules H1-H3 applied at unpack).
+ *   chunks[c]: a run of consecutive pileup-stream records of ONE chosen contig; its columns live at
+ *   counts[col_base .. col_base+contig_len); plane_delta is added (mod 2^32) to row_off of its records so that a
+ *   caller may upload only the chosen contigs' plane ranges.  A base counts as its letter when V=1 and the record
+ *   passes as_named >= minscore && xm_named <= max_xm (metaMLST_functions.py:259), else as N.
+ *   counts are ACCUMULATED (caller zeroes).  impl: 0 = best available, 1 = per-base atomics (v1), 2 = bit-sliced
+ *   carry-save counters (v2).  max_row_words = largest row (3*nw, padded odd) in the stream.
+ * --------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    uint32_t rec_begin, rec_end;   /* pileup-stream record range */
+    uint32_t col_base, contig_len; /* column range in the count tensor */
+    uint32_t plane_delta;          /* added to row_off[] */
+    uint32_t reserved[3];
+} mmlst_chunk;
+
+int mmlst_pileup_dev(const int32_t* pos, const uint32_t* row_off, const uint16_t* reflen,
+                     const int16_t* as_named, const uint8_t* xm_named, const uint32_t* planes,
+                     const mmlst_chunk* chunks, uint32_t n_chunks, uint32_t max_row_words,
+                     int minscore, int max_xm, uint32_t* counts, uint32_t total_cols, int impl, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * H1 -- htslib pileup depth cap (pysam `pileup(max_depth=8000)` default reaches cmseq/cmseq.py:527 unchanged).
+ * HOST function, sequential per contig: records coordinate-sorted (tid, pos), unmapped ones already removed.
+ * bam_plp_push drops a record when its start equals the iterator's current column and the mempool holds more than
+ * maxcnt nodes; the first record of every start position is pushed while the iterator is still behind it and is
+ * always kept, so per start position B the first min(n_B, max(1, maxcnt - live(B) - sentinel_nodes + 1)) records are
+ * admitted, live(B) = admitted records with start < B and end >= B.  sentinel_nodes = 1 (htslib >= 1.10).
+ * --------------------------------------------------------------------------------------------------------------- */
+int mmlst_depth_cap(const uint32_t* tid, const int32_t* pos, const uint32_t* reflen, uint64_t n, uint32_t maxcnt,
+                    uint32_t sentinel_nodes, uint8_t* admitted);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Stage 2b -- consensus call + comparison with the chosen DB allele.  Replaces cmseq/cmseq.py:551-554 (column
+ * recorded iff A+C+G+T >= mincov), :202-209 (majority, ties A>C>G>N>T, N competes: H8), :234-237 (fill with 'N')
+ * and metaMLST_functions.py:260-276 (N -> lower-case DB base + hole; mismatch -> SNP).
+ *   col_off[n_loci+1] : column range of each chosen locus in counts / dbseq / cons
+ *   dbseq             : ASCII DB sequence of the chosen allele per column (host checks len >= BAM LN, H10)
+ * --------------------------------------------------------------------------------------------------------------- */
+int mmlst_consensus_dev(const uint32_t* counts, const uint8_t* dbseq, const uint32_t* col_off, uint32_t n_loci,
+                        uint32_t mincov, uint8_t* cons, uint32_t* holes, uint32_t* snps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Stage 3 -- closest known allele by zip-truncated Hamming distance.  Replaces metaMLST_functions.py:230-234
+ * (stringDiff) driven by metamlst-merge.py:174-181 over sequencesGetAll (:224-228).
+ *   DB rows   : bit-planes hi/lo of the 2-bit code, tiles of 32 rows, word-major inside a tile:
+ *               db_hi[(tile*W + w)*32 + r], same for db_lo; row_len u16; zero padded.  W = words per plane.
+ *   queries   : q_hi/q_lo [Q][W] row-major, q_len u16.
+ *   blocks[b] = { q_begin, q_end, row_begin, row_end }: every query of the range is compared with every row of the
+ *               range (locus-restricted mode = one block per locus; all-pairs = one block).
+ *   best[q]   = min over rows of (distance << 32 | row) as u64 -- ties resolve to the lowest row; caller presets
+ *               ~0ull; results from row shards / GPUs combine with min.
+ * Sequences holding non-ACGT letters are refused by the host packer in this version (H9 exception path TODO).
+ * --------------------------------------------------------------------------------------------------------------- */
+int mmlst_hamming_min_dev(const uint32_t* db_hi, const uint32_t* db_lo, const uint16_t* row_len, uint32_t n_rows,
+                          uint32_t W, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
+                          const uint32_t* blocks, uint32_t n_blocks, uint32_t row_index_base,
+                          unsigned long long* best, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Host-buffer entry points (what the Python seams call; host<->device copies inside).
+ * --------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    /* score stream */
+    const uint32_t* tid; const int16_t* as0; const uint8_t* xm3; const uint16_t* qlen; const uint32_t* orig_idx;
+    uint64_t n_rec;
+    /* pileup stream */
+    const int32_t* p_pos; const uint32_t* p_row_off; const uint16_t* p_reflen; const int16_t* p_as; const uint8_t* p_xm;
+    const uint32_t* planes; uint64_t n_prec; uint64_t n_plane_words; uint32_t max_row_words;
+    /* per reference (allele row) */
+    const uint64_t* contig_start; /* [n_ref+1] first pileup-stream record of each contig */
+    uint32_t n_ref;
+} mmlst_soa;
+
+typedef struct { int minscore, max_xm, min_read_len; } mmlst_score_params;
+
+/* seam S1 (metamlst.py:96-151): uploads the score stream, runs the kernel, returns the integer tables. */
+int mmlst_score(mmlst_ctx* ctx, const mmlst_soa* soa, const uint8_t* allow, const uint32_t* locus_of, uint32_t n_loci,
+                const mmlst_score_params* prm, int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, uint64_t* counters);
+
+/* seam S2 (metaMLST_functions.py:249-281): uploads the chosen contigs' pileup records, runs pileup + consensus.
+ *   chosen_tid[n_loci], dbseq/col_off as in mmlst_consensus_dev; counts may be NULL. */
+int mmlst_pileup_consensus(mmlst_ctx* ctx, const mmlst_soa* soa, const uint32_t* chosen_tid, uint32_t n_loci,
+                           const uint8_t* dbseq, const uint32_t* col_off, int minscore, int max_xm, uint32_t mincov,
+                           int impl, uint32_t* counts, uint8_t* cons, uint32_t* holes, uint32_t* snps);
+
+/* seam S3 (metamlst-merge.py:177-181): DB planes stay resident in the context across calls / samples. */
+int mmlst_db_upload(mmlst_ctx* ctx, const uint32_t* db_hi, const uint32_t* db_lo, const uint16_t* row_len,
+                    uint32_t n_rows, uint32_t W);
+int mmlst_hamming_min(mmlst_ctx* ctx, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
+                      const uint32_t* blocks, uint32_t n_blocks, uint32_t* min_dist, uint32_t* argmin_row);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMLST_H */

@@ -1,0 +1,352 @@
+// C-ABI plumbing: error text, context (stream + grow-only device buffers), host-buffer entry points.
+#include <stdarg.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "pileup.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mmlst_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int mmlst_cuda_fail(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return MMLST_OK;
+    mmlst_set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
+    return MMLST_E_CUDA;
+}
+
+int mmlst_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaDeviceProp p;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess) n = p.multiProcessorCount;
+        else n = MMLST_NUM_SMS_DEFAULT;
+    }
+    return n;
+}
+
+extern "C" const char* mmlst_last_error(void) { return g_err; }
+extern "C" int mmlst_version(void) { return MMLST_VERSION; }
+extern "C" int mmlst_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" void* mmlst_pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        mmlst_set_error("cudaHostAlloc(%zu) failed", bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void mmlst_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---------------------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return MMLST_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); mmlst_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); return MMLST_E_NOMEM; }
+        cap = want;
+        return MMLST_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+struct mmlst_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // score stream
+    DevBuf tid, as0, xm3, qlen, oidx, allow, locus_of, sum_as, n_hit, first_idx, counters;
+    // pileup stream (chosen contigs only)
+    DevBuf p_pos, p_off, p_reflen, p_as, p_xm, planes, chunks, counts, dbseq, col_off, cons, holes, snps;
+    // hamming
+    DevBuf db_hi, db_lo, db_len, q_hi, q_lo, q_len, blocks, best;
+    uint32_t db_rows = 0, db_W = 0;
+    DevBuf* all[35];
+    int n_all = 0;
+    mmlst_ctx() {
+        DevBuf* l[] = {&tid, &as0, &xm3, &qlen, &oidx, &allow, &locus_of, &sum_as, &n_hit, &first_idx, &counters, &p_pos, &p_off,
+                       &p_reflen, &p_as, &p_xm, &planes, &chunks, &counts, &dbseq, &col_off, &cons, &holes, &snps, &db_hi,
+                       &db_lo, &db_len, &q_hi, &q_lo, &q_len, &blocks, &best};
+        for (DevBuf* b : l) all[n_all++] = b;
+    }
+};
+
+#define CTX_ENTER(ctx)                                                        \
+    if (!(ctx)) { mmlst_set_error("null context"); return MMLST_E_ARG; }      \
+    CUDA_TRY(cudaSetDevice((ctx)->device))
+#define TRY(expr) do { int _r = (expr); if (_r != MMLST_OK) return _r; } while (0)
+
+extern "C" int mmlst_create(int device, mmlst_ctx** out) {
+    if (!out) { mmlst_set_error("mmlst_create: null out"); return MMLST_E_ARG; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        mmlst_set_error("no CUDA device available (%s); libmmlst has no CPU fallback", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+        return MMLST_E_CUDA;
+    }
+    if (device < 0 || device >= n) { mmlst_set_error("device %d out of range (0..%d)", device, n - 1); return MMLST_E_ARG; }
+    CUDA_TRY(cudaSetDevice(device));
+    mmlst_ctx* c = new mmlst_ctx();
+    c->device = device;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return mmlst_cuda_fail(e, "cudaStreamCreate"); }
+    *out = c;
+    return MMLST_OK;
+}
+
+extern "C" void mmlst_destroy(mmlst_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < c->n_all; ++i) c->all[i]->release();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+extern "C" void* mmlst_stream(mmlst_ctx* c) { return c ? c->stream : nullptr; }
+extern "C" int mmlst_sync(mmlst_ctx* c) {
+    CTX_ENTER(c);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return MMLST_OK;
+}
+
+template <class T>
+static int h2d(DevBuf& b, const T* src, size_t n, cudaStream_t s) {
+    TRY(b.reserve(n * sizeof(T)));
+    if (n) CUDA_TRY(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    return MMLST_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* allow, const uint32_t* locus_of,
+                           uint32_t n_loci, const mmlst_score_params* prm, int64_t* sum_as, uint32_t* n_hit,
+                           uint32_t* first_idx, uint64_t* counters) {
+    CTX_ENTER(c);
+    if (!soa || !allow || !locus_of || !prm || !sum_as || !n_hit || !first_idx || !counters) { mmlst_set_error("mmlst_score: null pointer"); return MMLST_E_ARG; }
+    cudaStream_t s = c->stream;
+    const size_t n = soa->n_rec, nr = soa->n_ref;
+    TRY(h2d(c->tid, soa->tid, n, s));
+    TRY(h2d(c->as0, soa->as0, n, s));
+    TRY(h2d(c->xm3, soa->xm3, n, s));
+    TRY(h2d(c->qlen, soa->qlen, n, s));
+    if (soa->orig_idx) TRY(h2d(c->oidx, soa->orig_idx, n, s));
+    TRY(h2d(c->allow, allow, nr, s));
+    TRY(h2d(c->locus_of, locus_of, nr, s));
+    TRY(c->sum_as.reserve(nr * 8)); TRY(c->n_hit.reserve(nr * 4)); TRY(c->first_idx.reserve((size_t)n_loci * 4 + 4)); TRY(c->counters.reserve(16));
+    CUDA_TRY(cudaMemsetAsync(c->sum_as.p, 0, nr * 8, s));
+    CUDA_TRY(cudaMemsetAsync(c->n_hit.p, 0, nr * 4, s));
+    CUDA_TRY(cudaMemsetAsync(c->first_idx.p, 0xff, (size_t)n_loci * 4, s));
+    CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, 16, s));
+    TRY(mmlst_score_dev(c->tid.as<uint32_t>(), c->as0.as<int16_t>(), c->xm3.as<uint8_t>(), c->qlen.as<uint16_t>(),
+                        soa->orig_idx ? c->oidx.as<uint32_t>() : nullptr, n, 0, c->allow.as<uint8_t>(),
+                        c->locus_of.as<uint32_t>(), (uint32_t)nr, prm->minscore, prm->max_xm, prm->min_read_len,
+                        c->sum_as.as<int64_t>(), c->n_hit.as<uint32_t>(), c->first_idx.as<uint32_t>(),
+                        c->counters.as<uint64_t>(), s));
+    CUDA_TRY(cudaMemcpyAsync(sum_as, c->sum_as.p, nr * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(n_hit, c->n_hit.p, nr * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(first_idx, c->first_idx.p, (size_t)n_loci * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(counters, c->counters.p, 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return MMLST_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static const uint32_t kChunkRecords = 63 * 512;  // bit-sliced counters hold < 2^10 records per lane (pileup_bitsliced.cu)
+
+extern "C" int mmlst_pileup_dev(const int32_t* pos, const uint32_t* row_off, const uint16_t* reflen, const int16_t* as_named,
+                                const uint8_t* xm_named, const uint32_t* planes, const mmlst_chunk* chunks, uint32_t n_chunks,
+                                uint32_t max_row_words, int minscore, int max_xm, uint32_t* counts, uint32_t total_cols,
+                                int impl, void* stream) {
+    if (n_chunks == 0) return MMLST_OK;
+    if (!pos || !row_off || !reflen || !as_named || !xm_named || !planes || !chunks || !counts) { mmlst_set_error("mmlst_pileup_dev: null pointer"); return MMLST_E_ARG; }
+    PileupArgs a{pos, row_off, reflen, as_named, xm_named, planes, chunks, n_chunks, max_row_words, minscore, max_xm, counts, total_cols};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (impl == 1) return launch_pileup_atomic(a, s);
+    if (impl == 0 || impl == 2) return launch_pileup_bitsliced(a, s);
+    mmlst_set_error("mmlst_pileup_dev: impl %d unknown", impl);
+    return MMLST_E_ARG;
+}
+
+extern "C" int mmlst_pileup_consensus(mmlst_ctx* c, const mmlst_soa* soa, const uint32_t* chosen_tid, uint32_t n_loci,
+                                      const uint8_t* dbseq, const uint32_t* col_off, int minscore, int max_xm,
+                                      uint32_t mincov, int impl, uint32_t* counts, uint8_t* cons, uint32_t* holes,
+                                      uint32_t* snps) {
+    CTX_ENTER(c);
+    if (!soa || !chosen_tid || !dbseq || !col_off || !cons || !holes || !snps) { mmlst_set_error("mmlst_pileup_consensus: null pointer"); return MMLST_E_ARG; }
+    if (n_loci == 0) return MMLST_OK;
+    cudaStream_t s = c->stream;
+    // gather the chosen contigs' record / plane ranges (contiguous in the coordinate-sorted stream)
+    size_t n_rec = 0, n_words = 0;
+    for (uint32_t l = 0; l < n_loci; ++l) {
+        const uint32_t t = chosen_tid[l];
+        if (t >= soa->n_ref) { mmlst_set_error("chosen_tid[%u]=%u out of range", l, t); return MMLST_E_ARG; }
+        const uint64_t r0 = soa->contig_start[t], r1 = soa->contig_start[t + 1];
+        n_rec += r1 - r0;
+        n_words += (size_t)soa->p_row_off[r1] - soa->p_row_off[r0];
+    }
+    const uint32_t total_cols = col_off[n_loci];
+    TRY(c->p_pos.reserve(n_rec * 4 + 16)); TRY(c->p_off.reserve(n_rec * 4 + 16)); TRY(c->p_reflen.reserve(n_rec * 2 + 16));
+    TRY(c->p_as.reserve(n_rec * 2 + 16)); TRY(c->p_xm.reserve(n_rec + 16)); TRY(c->planes.reserve(n_words * 4 + 64));
+    std::vector<mmlst_chunk> chunks;
+    size_t rbase = 0, wbase = 0;
+    for (uint32_t l = 0; l < n_loci; ++l) {
+        const uint32_t t = chosen_tid[l];
+        const uint64_t r0 = soa->contig_start[t], r1 = soa->contig_start[t + 1];
+        const size_t nr = r1 - r0;
+        if (nr == 0) continue;
+        const uint32_t w0 = soa->p_row_off[r0], w1 = soa->p_row_off[r1];
+        CUDA_TRY(cudaMemcpyAsync(c->p_pos.as<int32_t>() + rbase, soa->p_pos + r0, nr * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->p_off.as<uint32_t>() + rbase, soa->p_row_off + r0, nr * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->p_reflen.as<uint16_t>() + rbase, soa->p_reflen + r0, nr * 2, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->p_as.as<int16_t>() + rbase, soa->p_as + r0, nr * 2, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->p_xm.as<uint8_t>() + rbase, soa->p_xm + r0, nr, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->planes.as<uint32_t>() + wbase, soa->planes + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, s));
+        for (size_t b = 0; b < nr; b += kChunkRecords) {
+            mmlst_chunk ck{};
+            ck.rec_begin = (uint32_t)(rbase + b);
+            ck.rec_end = (uint32_t)(rbase + std::min(nr, b + kChunkRecords));
+            ck.col_base = col_off[l];
+            ck.contig_len = col_off[l + 1] - col_off[l];
+            ck.plane_delta = (uint32_t)wbase - w0;
+            chunks.push_back(ck);
+        }
+        rbase += nr;
+        wbase += w1 - w0;
+    }
+    TRY(h2d(c->chunks, chunks.data(), chunks.size(), s));
+    TRY(h2d(c->dbseq, dbseq, total_cols, s));
+    TRY(h2d(c->col_off, col_off, (size_t)n_loci + 1, s));
+    TRY(c->counts.reserve((size_t)total_cols * 20 + 16)); TRY(c->cons.reserve(total_cols + 16));
+    TRY(c->holes.reserve(n_loci * 4)); TRY(c->snps.reserve(n_loci * 4));
+    CUDA_TRY(cudaMemsetAsync(c->counts.p, 0, (size_t)total_cols * 20, s));
+    TRY(mmlst_pileup_dev(c->p_pos.as<int32_t>(), c->p_off.as<uint32_t>(), c->p_reflen.as<uint16_t>(), c->p_as.as<int16_t>(),
+                         c->p_xm.as<uint8_t>(), c->planes.as<uint32_t>(), c->chunks.as<mmlst_chunk>(), (uint32_t)chunks.size(),
+                         soa->max_row_words, minscore, max_xm, c->counts.as<uint32_t>(), total_cols, impl, s));
+    TRY(mmlst_consensus_dev(c->counts.as<uint32_t>(), c->dbseq.as<uint8_t>(), c->col_off.as<uint32_t>(), n_loci, mincov,
+                            c->cons.as<uint8_t>(), c->holes.as<uint32_t>(), c->snps.as<uint32_t>(), s));
+    if (counts) CUDA_TRY(cudaMemcpyAsync(counts, c->counts.p, (size_t)total_cols * 20, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(cons, c->cons.p, total_cols, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(holes, c->holes.p, n_loci * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(snps, c->snps.p, n_loci * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return MMLST_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int mmlst_hamming_min_dev2(const uint32_t*, const uint32_t*, const uint16_t*, uint32_t, uint32_t, const uint32_t*,
+                                      const uint32_t*, const uint16_t*, uint32_t, const uint32_t*, uint32_t, uint32_t, uint32_t,
+                                      uint32_t, unsigned long long*, void*);
+
+extern "C" int mmlst_db_upload(mmlst_ctx* c, const uint32_t* db_hi, const uint32_t* db_lo, const uint16_t* row_len,
+                               uint32_t n_rows, uint32_t W) {
+    CTX_ENTER(c);
+    if (!db_hi || !db_lo || !row_len) { mmlst_set_error("mmlst_db_upload: null pointer"); return MMLST_E_ARG; }
+    const size_t words = (size_t)((n_rows + 31) / 32) * 32 * W;
+    TRY(h2d(c->db_hi, db_hi, words, c->stream));
+    TRY(h2d(c->db_lo, db_lo, words, c->stream));
+    TRY(h2d(c->db_len, row_len, n_rows, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->db_rows = n_rows; c->db_W = W;
+    return MMLST_OK;
+}
+
+extern "C" int mmlst_hamming_min(mmlst_ctx* c, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
+                                 const uint32_t* blocks, uint32_t n_blocks, uint32_t* min_dist, uint32_t* argmin_row) {
+    CTX_ENTER(c);
+    if (!c->db_rows) { mmlst_set_error("mmlst_hamming_min: no DB uploaded"); return MMLST_E_ARG; }
+    if (!q_hi || !q_lo || !q_len || !blocks || !min_dist || !argmin_row) { mmlst_set_error("mmlst_hamming_min: null pointer"); return MMLST_E_ARG; }
+    if (n_q == 0) return MMLST_OK;
+    cudaStream_t s = c->stream;
+    const uint32_t W = c->db_W;
+    TRY(h2d(c->q_hi, q_hi, (size_t)n_q * W, s));
+    TRY(h2d(c->q_lo, q_lo, (size_t)n_q * W, s));
+    TRY(h2d(c->q_len, q_len, n_q, s));
+    TRY(h2d(c->blocks, blocks, (size_t)n_blocks * 4, s));
+    TRY(c->best.reserve((size_t)n_q * 8));
+    CUDA_TRY(cudaMemsetAsync(c->best.p, 0xff, (size_t)n_q * 8, s));
+    uint32_t max_rows = 0, max_q = 0;
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        if (blocks[4 * b + 1] < blocks[4 * b] || blocks[4 * b + 3] < blocks[4 * b + 2] || blocks[4 * b + 1] > n_q || blocks[4 * b + 3] > c->db_rows) {
+            mmlst_set_error("mmlst_hamming_min: block %u out of range", b);
+            return MMLST_E_ARG;
+        }
+        max_q = std::max(max_q, blocks[4 * b + 1] - blocks[4 * b]);
+        max_rows = std::max(max_rows, blocks[4 * b + 3] - blocks[4 * b + 2]);
+    }
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += 65535) {
+        const uint32_t nb = std::min(65535u, n_blocks - b0);
+        TRY(mmlst_hamming_min_dev2(c->db_hi.as<uint32_t>(), c->db_lo.as<uint32_t>(), c->db_len.as<uint16_t>(), c->db_rows, W,
+                                   c->q_hi.as<uint32_t>(), c->q_lo.as<uint32_t>(), c->q_len.as<uint16_t>(), n_q,
+                                   c->blocks.as<uint32_t>() + 4 * (size_t)b0, nb, max_rows, max_q, 0,
+                                   c->best.as<unsigned long long>(), s));
+    }
+    std::vector<unsigned long long> best(n_q);
+    CUDA_TRY(cudaMemcpyAsync(best.data(), c->best.p, (size_t)n_q * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (uint32_t q = 0; q < n_q; ++q) {
+        min_dist[q] = (uint32_t)(best[q] >> 32);
+        argmin_row[q] = (uint32_t)(best[q] & 0xffffffffu);
+    }
+    return MMLST_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host-side (sequential) htslib depth-cap admission, H1.  See include/mmlst.h.
+extern "C" int mmlst_depth_cap(const uint32_t* tid, const int32_t* pos, const uint32_t* reflen, uint64_t n, uint32_t maxcnt,
+                               uint32_t sentinel_nodes, uint8_t* admitted) {
+    if (n == 0) return MMLST_OK;
+    if (!tid || !pos || !reflen || !admitted) { mmlst_set_error("mmlst_depth_cap: null pointer"); return MMLST_E_ARG; }
+    std::vector<uint32_t> endhist;
+    uint64_t i = 0;
+    while (i < n) {
+        uint64_t j = i;
+        int64_t maxend = 0;
+        while (j < n && tid[j] == tid[i]) {
+            if (j > i && pos[j] < pos[j - 1]) { mmlst_set_error("mmlst_depth_cap: records not coordinate-sorted at %llu", (unsigned long long)j); return MMLST_E_UNSORTED; }
+            maxend = std::max<int64_t>(maxend, (int64_t)pos[j] + reflen[j]);
+            ++j;
+        }
+        if (j < n && tid[j] < tid[i]) { mmlst_set_error("mmlst_depth_cap: contigs out of order at %llu", (unsigned long long)j); return MMLST_E_UNSORTED; }
+        if ((j - i) + sentinel_nodes <= (uint64_t)maxcnt) {  // the mempool can never exceed the cap
+            memset(admitted + i, 1, j - i);
+            i = j;
+            continue;
+        }
+        endhist.assign((size_t)maxend + 2, 0);
+        uint64_t live = 0;
+        int64_t cursor = 0;  // ends < cursor already removed
+        uint64_t k = i;
+        while (k < j) {
+            const int32_t B = pos[k];
+            for (; cursor <= (int64_t)B - 1; ++cursor) live -= endhist[(size_t)cursor];  // freed while emitting columns < B
+            bool first = true;
+            for (; k < j && pos[k] == B; ++k) {
+                if (!first && (uint64_t)sentinel_nodes + live > (uint64_t)maxcnt) { admitted[k] = 0; continue; }
+                admitted[k] = 1;
+                const int64_t end = (int64_t)B + reflen[k];
+                if (first || end > B) { ++live; ++endhist[(size_t)end]; }  // linked into the buffer (mp_alloc)
+                first = false;
+            }
+        }
+        i = j;
+    }
+    return MMLST_OK;
+}

@@ -1,0 +1,51 @@
+// Stage 2b: majority consensus + comparison with the chosen DB allele, one CTA per locus.
+// Replaces cmseq/cmseq.py:202-209,234-237,551-554 and metaMLST_functions.py:260-276.  20 B/column in, 1 B out.
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(128) consensus_kernel(const uint32_t* __restrict__ counts, const uint8_t* __restrict__ dbseq,
+                                                        const uint32_t* __restrict__ col_off, uint32_t mincov,
+                                                        uint8_t* __restrict__ cons, uint32_t* __restrict__ holes,
+                                                        uint32_t* __restrict__ snps) {
+    const uint32_t locus = blockIdx.x;
+    const uint32_t c0 = col_off[locus], c1 = col_off[locus + 1];
+    uint32_t h = 0, s = 0;
+    for (uint32_t col = c0 + threadIdx.x; col < c1; col += blockDim.x) {
+        const uint32_t* c = counts + static_cast<size_t>(col) * 5;
+        const uint32_t A = c[0], C = c[1], G = c[2], T = c[3], N = c[4];
+        uint8_t call = 'N';
+        if (A + C + G + T >= mincov && (A | C | G | T | N)) {
+            // max(sorted(freq), key=freq.get): first maximum in the order A, C, G, N, T (H8)
+            uint32_t best = A; call = 'A';
+            if (C > best) { best = C; call = 'C'; }
+            if (G > best) { best = G; call = 'G'; }
+            if (N > best) { best = N; call = 'N'; }
+            if (T > best) { best = T; call = 'T'; }
+        }
+        const uint8_t db = dbseq[col];
+        uint8_t out;
+        if (call == 'N') { out = (db >= 'A' && db <= 'Z') ? db + 32 : db; ++h; }
+        else { out = call; if (call != db) ++s; }
+        cons[col] = out;
+    }
+    __shared__ uint32_t sh[2];
+    if (threadIdx.x < 2) sh[threadIdx.x] = 0;
+    __syncthreads();
+    h = __reduce_add_sync(0xffffffffu, h);
+    s = __reduce_add_sync(0xffffffffu, s);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[0], h); atomicAdd(&sh[1], s); }
+    __syncthreads();
+    if (threadIdx.x == 0) { holes[locus] = sh[0]; snps[locus] = sh[1]; }
+}
+
+}  // namespace
+
+extern "C" int mmlst_consensus_dev(const uint32_t* counts, const uint8_t* dbseq, const uint32_t* col_off, uint32_t n_loci,
+                                   uint32_t mincov, uint8_t* cons, uint32_t* holes, uint32_t* snps, void* stream) {
+    if (n_loci == 0) return MMLST_OK;
+    if (!counts || !dbseq || !col_off || !cons || !holes || !snps) { mmlst_set_error("mmlst_consensus_dev: null pointer"); return MMLST_E_ARG; }
+    consensus_kernel<<<n_loci, 128, 0, static_cast<cudaStream_t>(stream)>>>(counts, dbseq, col_off, mincov, cons, holes, snps);
+    CUDA_TRY(cudaGetLastError());
+    return MMLST_OK;
+}

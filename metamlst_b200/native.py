@@ -1,0 +1,120 @@
+"""ctypes binding of libmmlst.so (include/mmlst.h).  No fallback: a missing library or device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmlst.so")
+
+
+class MmlstError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("libmmlst error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Chunk(C.Structure):
+    _fields_ = [("rec_begin", C.c_uint32), ("rec_end", C.c_uint32), ("col_base", C.c_uint32), ("contig_len", C.c_uint32),
+                ("plane_delta", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+
+
+class Soa(C.Structure):
+    _fields_ = [("tid", C.c_void_p), ("as0", C.c_void_p), ("xm3", C.c_void_p), ("qlen", C.c_void_p), ("orig_idx", C.c_void_p),
+                ("n_rec", C.c_uint64),
+                ("p_pos", C.c_void_p), ("p_row_off", C.c_void_p), ("p_reflen", C.c_void_p), ("p_as", C.c_void_p), ("p_xm", C.c_void_p),
+                ("planes", C.c_void_p), ("n_prec", C.c_uint64), ("n_plane_words", C.c_uint64), ("max_row_words", C.c_uint32),
+                ("contig_start", C.c_void_p), ("n_ref", C.c_uint32)]
+
+
+class ScoreParams(C.Structure):
+    _fields_ = [("minscore", C.c_int), ("max_xm", C.c_int), ("min_read_len", C.c_int)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "mmlst_last_error": (C.c_char_p, []),
+    "mmlst_version": (C.c_int, []),
+    "mmlst_device_count": (C.c_int, []),
+    "mmlst_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "mmlst_destroy": (None, [C.c_void_p]),
+    "mmlst_stream": (C.c_void_p, [C.c_void_p]),
+    "mmlst_sync": (C.c_int, [C.c_void_p]),
+    "mmlst_pinned_alloc": (C.c_void_p, [C.c_size_t]),
+    "mmlst_pinned_free": (None, [C.c_void_p]),
+    "mmlst_score_dev": (C.c_int, [C.c_void_p] * 5 + [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
+                                  C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmlst_pileup_dev": (C.c_int, [C.c_void_p] * 7 + [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_uint32,
+                                   C.c_int, C.c_void_p]),
+    "mmlst_consensus_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "mmlst_hamming_min_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "mmlst_hamming_min_dev2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                         C.c_void_p, C.c_void_p]),
+    "mmlst_depth_cap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "mmlst_score": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(ScoreParams),
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmlst_pileup_consensus": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmlst_db_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "mmlst_hamming_min": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                    C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libmmlst.so (built in-tree by metamlst_b200/csrc/build.sh or __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(metamlst_b200 has no CPU fallback)" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            f = getattr(l, name)  # AttributeError if the symbol is not exported
+            f.restype = res
+            f.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise MmlstError(rc, lib().mmlst_last_error().decode(errors="replace"))
+
+
+def ptr(x) -> int:
+    """Address of a numpy array / torch tensor / None."""
+    if x is None:
+        return 0
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    return x.ctypes.data
+
+
+class Context:
+    """mmlst_ctx: one per GPU; owns a stream and the staging device memory of the host-buffer entry points."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib().mmlst_create(device, C.byref(self._h)))
+        self.device = device
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            lib().mmlst_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,275 @@
+"""Host-side packing of alignment records / allele sequences into the HBM layouts of include/mmlst.h.
+
+`pack_table` is the numpy route used for synthetic tables (tests, bench); BAM files go through the C++ unpacker
+(`metamlst_b200.bam.unpack_bam`), which emits the same structure.  Everything here is layout work: no result of the
+reference is computed on the host except the sequential depth-cap admission (H1), done by the native host function
+`mmlst_depth_cap`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import native
+
+BAM_FUNMAP = 0x4
+BAM_FPROPER_PAIR = 0x2
+DEFAULT_MAX_DEPTH = 8000  # pysam pileup() default reaching cmseq/cmseq.py:527 (H1)
+DEFAULT_MINQUAL = 20  # metaMLST_functions.py:258
+PLANE_SLACK_WORDS = 8
+
+
+@dataclass
+class SoaHost:
+    """Score stream + pileup stream on the host (numpy; pin() moves them to page-locked memory)."""
+
+    ref_names: List[str]
+    ref_lens: np.ndarray
+    # score stream (all records, coordinate-sorted)
+    tid: np.ndarray
+    as0: np.ndarray
+    xm3: np.ndarray
+    qlen: np.ndarray
+    orig_idx: Optional[np.ndarray]
+    # pileup stream (mapped + admitted records, coordinate-sorted)
+    p_pos: np.ndarray
+    p_row_off: np.ndarray  # [P+1]
+    p_reflen: np.ndarray
+    p_as: np.ndarray
+    p_xm: np.ndarray
+    planes: np.ndarray
+    max_row_words: int
+    contig_start: np.ndarray  # uint64 [n_ref+1]
+    minqual: int = DEFAULT_MINQUAL
+    max_depth: int = DEFAULT_MAX_DEPTH
+    n_dropped_by_cap: int = 0
+    _keep: tuple = ()
+
+    @property
+    def n_rec(self) -> int:
+        return int(self.tid.shape[0])
+
+    @property
+    def n_prec(self) -> int:
+        return int(self.p_pos.shape[0])
+
+    def c_struct(self) -> native.Soa:
+        s = native.Soa()
+        s.tid, s.as0, s.xm3, s.qlen = native.ptr(self.tid), native.ptr(self.as0), native.ptr(self.xm3), native.ptr(self.qlen)
+        s.orig_idx = native.ptr(self.orig_idx)
+        s.n_rec = self.n_rec
+        s.p_pos, s.p_row_off, s.p_reflen = native.ptr(self.p_pos), native.ptr(self.p_row_off), native.ptr(self.p_reflen)
+        s.p_as, s.p_xm, s.planes = native.ptr(self.p_as), native.ptr(self.p_xm), native.ptr(self.planes)
+        s.n_prec = self.n_prec
+        s.n_plane_words = int(self.planes.shape[0])
+        s.max_row_words = int(self.max_row_words)
+        s.contig_start = native.ptr(self.contig_start)
+        s.n_ref = len(self.ref_names)
+        return s
+
+    def pin(self) -> "SoaHost":
+        """Copy the streams into page-locked memory (torch pinned tensors) so uploads are asynchronous DMA."""
+        import torch
+
+        keep = []
+        for name in ("tid", "as0", "xm3", "qlen", "orig_idx", "p_pos", "p_row_off", "p_reflen", "p_as", "p_xm", "planes"):
+            arr = getattr(self, name)
+            if arr is None:
+                continue
+            t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).pin_memory()
+            keep.append(t)
+            setattr(self, name, t.numpy().view(arr.dtype).reshape(arr.shape))
+        self._keep = tuple(keep)
+        return self
+
+
+def row_words(reflen: np.ndarray) -> np.ndarray:
+    """3 planes x ceil(reflen/32) words, padded to an odd word count (bank-conflict-free row stride)."""
+    rw = 3 * ((reflen.astype(np.int64) + 31) >> 5)
+    return rw + ((rw > 0) & ((rw & 1) == 0))
+
+
+def project_cigars(cig_off: np.ndarray, cig_ops: np.ndarray, n: int):
+    """CIGAR -> reference projection: per record reflen and, for every reference offset, the query index of the
+    base aligned there (-1 for D/N).  M,=,X consume both; I,S query only; D,N reference only; H,P nothing (htslib
+    resolve_cigar2 as restated in oracle/mlst_oracle.py).  Returns (reflen[n], rec_of_seg, ref_start, q_start, seg_len)."""
+    ncig = (cig_off[1:] - cig_off[:-1]).astype(np.int64)
+    rec = np.repeat(np.arange(n, dtype=np.int64), ncig)
+    op = (cig_ops & 0xF).astype(np.int64)
+    ln = (cig_ops >> 4).astype(np.int64)
+    cons_ref = np.isin(op, (0, 2, 3, 7, 8))
+    cons_q = np.isin(op, (0, 1, 4, 7, 8))
+    # exclusive prefix sums inside each record
+    def seg_excl_cumsum(v):
+        c = np.cumsum(v)
+        start = c - v
+        base = np.zeros(n + 1, dtype=np.int64)
+        np.add.at(base, rec + 1, v)  # totals per record
+        tot = base[1:]
+        first = np.cumsum(tot) - tot
+        return start - first[rec], tot
+    ref_start, reflen = seg_excl_cumsum(ln * cons_ref)
+    q_start, _ = seg_excl_cumsum(ln * cons_q)
+    is_m = np.isin(op, (0, 7, 8))
+    return reflen, rec[is_m], ref_start[is_m], q_start[is_m], ln[is_m]
+
+
+def _pack_bits_u32(bits: np.ndarray) -> np.ndarray:
+    """bool [n, 32*k] -> uint32 [n, k], bit i of word j = column 32 j + i."""
+    return np.packbits(bits, axis=1, bitorder="little").view(np.uint32)
+
+
+def pack_table(tab, minqual: int = DEFAULT_MINQUAL, max_depth: Optional[int] = DEFAULT_MAX_DEPTH, sentinel_nodes: int = 1,
+               chunk: int = 1 << 18) -> SoaHost:
+    """AlnTable (fixed read length, ASCII seq + phred qual) -> SoaHost.  max_depth=None disables the htslib cap."""
+    n = tab.n
+    if n and np.any(tab.flag & BAM_FPROPER_PAIR):
+        raise native.MmlstError(-6, "proper-pair records: htslib overlap handling (H2) is not implemented -- refusing")
+    if n and np.any(tab.tid < 0):
+        raise native.MmlstError(-4, "unmapped record (RNAME '*'): the reference crashes at metamlst.py:107")
+    if n and (tab.AS.min() < -32768 or tab.AS.max() > 32767):
+        raise native.MmlstError(-7, "AS outside int16")
+    order = tab.coord_order()
+    presorted = bool(np.all(order == np.arange(n)))
+    L = tab.read_len
+    # positional aux fields (H4): field 0 is AS; field 3 is XM when XS:i is present, else XO
+    aux3 = np.where(tab.has_xs, tab.XM, tab.XO)
+    tid = tab.tid[order].astype(np.uint32)
+    as0 = tab.AS[order].astype(np.int16)
+    xm3 = np.clip(aux3[order], 0, 255).astype(np.uint8)
+    if np.any(aux3 < 0):
+        raise native.MmlstError(-7, "negative 4th aux field")
+    qlen = np.full(n, max(L, 1), dtype=np.uint16)
+    orig_idx = None if presorted else order.astype(np.uint32)
+
+    # ---- pileup stream
+    reflen_all, seg_rec, seg_ref, seg_q, seg_len = project_cigars(tab.cig_off, tab.cig_ops, n)
+    if n and reflen_all.max() > 65535:
+        raise native.MmlstError(-7, "reference span > 65535")
+    mapped = (tab.flag[order] & BAM_FUNMAP) == 0
+    s_idx = order[mapped]  # table indices of pileup candidates, coordinate-sorted
+    p_tid = tab.tid[s_idx].astype(np.uint32)
+    p_pos_all = tab.pos[s_idx].astype(np.int32)
+    p_reflen_all = reflen_all[s_idx].astype(np.uint32)
+    admitted = np.ones(s_idx.shape[0], dtype=np.uint8)
+    if max_depth is not None and s_idx.shape[0]:
+        native.check(native.lib().mmlst_depth_cap(native.ptr(p_tid), native.ptr(p_pos_all), native.ptr(p_reflen_all),
+                                                   s_idx.shape[0], int(max_depth), int(sentinel_nodes), native.ptr(admitted)))
+    adm = admitted.astype(bool)
+    sel = s_idx[adm]
+    P = sel.shape[0]
+    p_pos = p_pos_all[adm]
+    p_reflen = p_reflen_all[adm].astype(np.uint16)
+    p_as = tab.AS[sel].astype(np.int16)  # by NAME
+    p_xm = np.clip(tab.XM[sel], 0, 255).astype(np.uint8)
+    rw = row_words(p_reflen)
+    p_row_off = np.zeros(P + 1, dtype=np.int64)
+    p_row_off[1:] = np.cumsum(rw)
+    if p_row_off[-1] + PLANE_SLACK_WORDS >= (1 << 32):
+        raise native.MmlstError(-7, "plane array exceeds 2^32 words")
+    planes = np.zeros(int(p_row_off[-1]) + PLANE_SLACK_WORDS, dtype=np.uint32)
+    # segments grouped by table record for fast lookup
+    seg_order = np.argsort(seg_rec, kind="stable")
+    seg_rec, seg_ref, seg_q, seg_len = seg_rec[seg_order], seg_ref[seg_order], seg_q[seg_order], seg_len[seg_order]
+    seg_first = np.searchsorted(seg_rec, np.arange(n + 1))
+    code_lut = np.full(256, 255, dtype=np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        code_lut[ch] = i
+        code_lut[ch + 32] = i  # query_sequence[..].upper() (cmseq/cmseq.py:537)
+    for c0 in range(0, P, chunk):
+        idx = sel[c0:c0 + chunk]
+        m = idx.shape[0]
+        maxref = int(p_reflen[c0:c0 + m].max()) if m else 0
+        wmax = (maxref + 31) >> 5
+        if wmax == 0:
+            continue
+        qidx = np.full((m, wmax * 32), -1, dtype=np.int64)
+        # expand the M segments of these records
+        s0, s1 = seg_first[idx], seg_first[idx + 1]
+        nseg = s1 - s0
+        sid = np.repeat(s0, nseg) + (np.arange(int(nseg.sum())) - np.repeat(np.cumsum(nseg) - nseg, nseg))
+        row = np.repeat(np.arange(m), nseg)
+        sl = seg_len[sid]
+        tot = int(sl.sum())
+        within = np.arange(tot) - np.repeat(np.cumsum(sl) - sl, sl)
+        rr = np.repeat(row, sl)
+        qidx[rr, np.repeat(seg_ref[sid], sl) + within] = np.repeat(seg_q[sid], sl) + within
+        has = qidx >= 0
+        qi = np.where(has, qidx, 0)
+        base = tab.seq[idx][np.arange(m)[:, None], qi]
+        ql = tab.qual[idx][np.arange(m)[:, None], qi]
+        code = code_lut[base]
+        qok = has & (ql >= minqual)  # H3: bases under minqual are not in the column at all
+        V = qok & (code != 255)
+        Nn = qok & (code == 255)
+        B1 = V & ((code & 2) != 0)
+        B0 = (V & ((code & 1) != 0)) | Nn
+        Vw, B1w, B0w = _pack_bits_u32(V), _pack_bits_u32(B1), _pack_bits_u32(B0)
+        nw = (p_reflen[c0:c0 + m].astype(np.int64) + 31) >> 5
+        off = p_row_off[c0:c0 + m]
+        for j in range(wmax):
+            msk = nw > j
+            o = off[msk] + 3 * j
+            planes[o] = Vw[msk, j]
+            planes[o + 1] = B1w[msk, j]
+            planes[o + 2] = B0w[msk, j]
+    n_ref = len(tab.ref_names)
+    contig_start = np.searchsorted(tab.tid[sel], np.arange(n_ref + 1)).astype(np.uint64)
+    return SoaHost(list(tab.ref_names), np.asarray(tab.ref_lens, dtype=np.int32), tid, as0, xm3, qlen, orig_idx,
+                   p_pos, p_row_off.astype(np.uint32), p_reflen, p_as, p_xm, planes, int(rw.max()) if P else 0, contig_start,
+                   minqual, max_depth if max_depth is not None else 0, int((~adm).sum()))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Allele database for the Hamming search
+# ----------------------------------------------------------------------------------------------------------------
+
+def _w_for(max_len: int) -> int:
+    w = (max_len + 31) // 32
+    for cand in (8, 16, 24, 32):
+        if w <= cand:
+            return cand
+    raise native.MmlstError(-7, "sequence of %d bases exceeds 1024 (W > 32 words per plane)" % max_len)
+
+
+def encode_2bit(seqs: Sequence[bytes], W: int):
+    """ASCII sequences -> (hi[n, W], lo[n, W], len[n]) uint32 bit-planes of the code A=0 C=1 G=2 T=3 (upper case
+    only: stringDiff compares characters, metaMLST_functions.py:230-234).  Non-ACGT letters are refused (H9 exception
+    path not implemented in this version)."""
+    n = len(seqs)
+    lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=n)
+    if n and lens.max() > 65535:
+        raise native.MmlstError(-7, "sequence longer than 65535")
+    lut = np.full(256, 255, dtype=np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        lut[ch] = i
+    mat = np.zeros((n, W * 32), dtype=np.uint8)
+    valid = np.zeros((n, W * 32), dtype=bool)
+    flat = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    rows = np.repeat(np.arange(n), lens)
+    cols = np.arange(flat.shape[0]) - np.repeat(np.cumsum(lens) - lens, lens)
+    if n and lens.max() > W * 32:
+        raise native.MmlstError(-7, "sequence longer than W*32")
+    codes = lut[flat]
+    if np.any(codes == 255):
+        bad = int(np.argmax(codes == 255))
+        raise native.MmlstError(-7, "non-ACGT letter %r in sequence %d: exact-character path (H9) not implemented" % (chr(flat[bad]), int(rows[bad])))
+    mat[rows, cols] = codes
+    valid[rows, cols] = True
+    hi = _pack_bits_u32((mat & 2) != 0)
+    lo = _pack_bits_u32((mat & 1) != 0)
+    return np.ascontiguousarray(hi), np.ascontiguousarray(lo), lens.astype(np.uint16)
+
+
+def tile_db(hi: np.ndarray, lo: np.ndarray):
+    """[n, W] row-major planes -> 32-row word-major tiles: out[(tile*W + w)*32 + r]."""
+    n, W = hi.shape
+    nt = (n + 31) // 32
+    def t(x):
+        p = np.zeros((nt * 32, W), dtype=np.uint32)
+        p[:n] = x
+        return np.ascontiguousarray(p.reshape(nt, 32, W).transpose(0, 2, 1)).reshape(-1)
+    return t(hi), t(lo)

@@ -1,0 +1,90 @@
+"""Host packer (CIGAR projection, 3-plane rows, closed-form depth cap) against the oracles -- no GPU needed."""
+import numpy as np
+import pytest
+
+from helpers import planes_to_counts, small_case
+from metamlst_b200 import native, packing
+from oracle import corc
+
+
+def test_library_exports_every_declared_symbol():
+    import re, os
+    hdr = open(os.path.join(os.path.dirname(native.__file__), "..", "include", "mmlst.h")).read()
+    declared = set(re.findall(r"\b(mmlst_[a-z0-9_]+)\s*\(", hdr))
+    l = native.lib()
+    for name in declared:
+        assert hasattr(l, name), name
+    assert declared <= set(native.EXPORTS) | {"mmlst_hamming_min_dev2"}
+    assert l.mmlst_version() == 100
+
+
+def test_no_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(native.MmlstError) as e:
+        native.Context(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.parametrize("maxcnt", [1, 2, 7, 33, 200, 8000])
+def test_closed_form_depth_cap_equals_htslib_simulation(maxcnt):
+    db, tab = small_case(seed=21, n_reads=1500, L=50, K=2, schemes={"ecoli": [("adk", 90), ("fumC", 70)]}, apl=3,
+                         frac_clip=0.2, frac_indel=0.3)
+    tab = tab.sorted_by_coord()
+    rl = corc.ref_lengths(tab).astype(np.uint32)
+    tid = tab.tid.astype(np.uint32)
+    pos = tab.pos.astype(np.int32)
+    adm = np.zeros(tab.n, np.uint8)
+    native.check(native.lib().mmlst_depth_cap(native.ptr(tid), native.ptr(pos), native.ptr(rl), tab.n, maxcnt, 1, native.ptr(adm)))
+    for t in sorted(set(int(x) for x in tab.tid)):
+        _, sim = corc.contig_counts(tab, t, max_depth=maxcnt)
+        assert np.array_equal(adm[tab.tid == t], sim), t
+
+
+def test_depth_cap_rejects_unsorted():
+    db, tab = small_case(seed=22, n_reads=200, L=50, K=1)
+    rl = corc.ref_lengths(tab).astype(np.uint32)
+    tid = tab.tid.astype(np.uint32); pos = tab.pos.astype(np.int32); adm = np.zeros(tab.n, np.uint8)
+    with pytest.raises(native.MmlstError) as e:
+        native.check(native.lib().mmlst_depth_cap(native.ptr(tid), native.ptr(pos), native.ptr(rl), tab.n, 8000, 1, native.ptr(adm)))
+    assert e.value.code == -5
+
+
+@pytest.mark.parametrize("order,maxd", [("name", 8000), ("coord", 8000), ("coord", 25), ("name", None)])
+def test_packed_planes_reproduce_oracle_counts(order, maxd):
+    db, tab = small_case(seed=23, n_reads=500, L=70, K=2, schemes={"ecoli": [("adk", 200), ("fumC", 131)]}, apl=3,
+                         frac_clip=0.2, frac_indel=0.3, sub_err=0.03, n_frac=0.05)
+    if order == "coord":
+        tab = tab.sorted_by_coord()
+    soa = packing.pack_table(tab, minqual=20, max_depth=maxd)
+    st = tab.sorted_by_coord()
+    assert (soa.orig_idx is None) == (order == "coord")
+    assert soa.max_row_words % 2 == 1
+    for t in sorted(set(int(x) for x in tab.tid)):
+        want, adm = corc.contig_counts(st, t, 20, 110, 3, maxd)
+        got = planes_to_counts(soa, t, int(tab.ref_lens[t]), 110, 3)
+        assert np.array_equal(got, want.astype(np.int64)), t
+        assert int(soa.contig_start[t + 1] - soa.contig_start[t]) == int(adm.sum())
+
+
+def test_packer_refuses_proper_pairs_and_unmapped():
+    db, tab = small_case(seed=24, n_reads=50, L=60, K=1)
+    tab.flag = tab.flag | 0x3
+    with pytest.raises(native.MmlstError) as e:
+        packing.pack_table(tab)
+    assert e.value.code == -6
+
+
+def test_hamming_encoding_roundtrip_and_refusal():
+    seqs = [b"ACGTACGTAA", b"TTTT", b"G" * 70]
+    hi, lo, ln = packing.encode_2bit(seqs, 8)
+    assert list(ln) == [10, 4, 70]
+    for r, s in enumerate(seqs):
+        for i, ch in enumerate(s):
+            code = ((int(hi[r, i // 32]) >> (i % 32)) & 1) * 2 + ((int(lo[r, i // 32]) >> (i % 32)) & 1)
+            assert b"ACGT"[code] == ch
+    th, tl = packing.tile_db(hi, lo)
+    assert th.shape[0] == 32 * 8 and int(th[(0 * 8 + 2) * 32 + 2]) == int(hi[2, 2])
+    with pytest.raises(native.MmlstError):
+        packing.encode_2bit([b"ACGN"], 8)
