@@ -1,0 +1,428 @@
+#!/usr/bin/env python3
+"""bench.py -- aligned reads/s through score + pileup + consensus (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--reads R --alleles A]
+
+Workload (N=1): BASELINE.json configs[1] -- one sample of 10 M x 150 bp reads, K=4 alignments per read (40 M BAM
+records, coordinate-sorted), against the synthetic E. coli + S. aureus + K. pneumoniae schemes (21 loci x 1024
+alleles).  A "step" is one full pass of the hot path over that sample.  For N>1 every rank owns the records of a
+disjoint set of loci (contig-aligned shards, 10 M reads each: weak scaling) and the integer tables are all-reduced.
+
+  value     : records/s with the packed streams already resident in HBM (CUDA events, max over ranks)
+  e2e       : the same pass through the host-buffer C-ABI (mmlst_score + mmlst_pileup_consensus) from pinned host
+              memory, host<->device copies inside the timed region
+  roofline  : dominant kernel of the step against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference : the C port of the oracle on the host cores, on a bounded sample
+The headline mode is the reference's own semantics (pysam max_depth = 8000, "parity mode"); the same sample without
+the htslib depth cap (full 1.5 G-increment histogram) is reported under "uncapped".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU")
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--alleles", type=int, default=1024, help="alleles per locus")
+    ap.add_argument("--k", type=int, default=4, help="alignments per read")
+    ap.add_argument("--pileup-impl", type=int, default=0)
+    ap.add_argument("--no-extras", action="store_true", help="skip uncapped / hamming / cpu baseline extras")
+    ap.add_argument("--cpu-sample-reads", type=int, default=400_000)
+    return ap.parse_args()
+
+
+ORGS = ("ecoli", "saureus", "kpneumoniae")
+PROPS = (0.5, 0.3, 0.2)
+PARAMS = dict(minscore=80, max_xM=5, min_read_len=50, penalty=100)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.p = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_db(args):
+    from metamlst_b200 import synth
+    return synth.make_db(ORGS, alleles_per_locus=args.alleles, n_profiles=2048, seed=1002)
+
+
+def gen_streams(db, args, device, max_depth, locus_subset=None, seed=1002, n_reads=None, chunk=1_000_000):
+    from metamlst_b200 import devpack, synth
+    import torch
+    n_reads = n_reads or args.reads
+    cores = []
+    for i, c0 in enumerate(range(0, n_reads, chunk)):
+        core = synth.gen_core(db, min(chunk, n_reads - c0), args.read_len, seed=seed * 1000 + i, K=args.k, org_props=PROPS,
+                              device=device, strain_seed=1002, locus_subset=locus_subset)
+        # keep only what the packer needs
+        cores.append({k: core[k] for k in ("L", "K", "bases", "qual", "rtype", "a_split", "rows", "start", "flag", "AS", "xm")})
+        del core
+    st = devpack.pack_cores(db, cores, 20, max_depth)
+    n_ops = sum(int((c["rtype"] != 0).sum()) * 2 for c in cores) * args.k  # extra CIGAR ops beyond 1 per record
+    del cores
+    if device != "cpu":
+        torch.cuda.empty_cache()
+    return st, n_ops
+
+
+def pileup_alg_bytes(st, tids, L):
+    """per admitted record on a chosen contig 8 + 4 n_ops + L/2 bytes; + 21.25 B per column."""
+    recs = sum(int(st.contig_start[t + 1] - st.contig_start[t]) for t in tids)
+    cols = sum(int(st.ref_lens[t]) for t in tids)
+    return recs * (8 + 4 * 1.22 + L / 2.0) + cols * 21.25, recs  # 1.22 = mean CIGAR ops of the generator (89 % 1 op, 11 % 3)
+
+
+def event_ms(pairs):
+    return [a.elapsed_time(b) for a, b in pairs]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_port_run(db, args, n_reads, threads, steps=1, warmup=0):
+    """The oracle's C port (oracle/c) on the host: score + depth-cap simulation + pileup + consensus on a sample of
+    the same workload.  Returns (records/s, description)."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from metamlst_b200 import api, synth
+    from oracle import corc
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    tab = synth.make_sample(db, n_reads, args.read_len, seed=1002001, K=args.k, org_props=PROPS, device=dev, strain_seed=1002)
+    tab = tab.sorted_by_coord()
+    index = api.AlleleIndex(tab.ref_names)
+    allow = np.ones(db.n_rows, np.uint8)
+    locus_of = db.row_locus.astype(np.uint32)
+    n = tab.n
+    bounds = np.linspace(0, n, threads + 1).astype(np.int64)
+    parts = [tab.take(np.arange(bounds[i], bounds[i + 1])) for i in range(threads)]
+    pool = ThreadPoolExecutor(threads)
+
+    def one_step():
+        res = list(pool.map(lambda p: corc.score(p, allow, locus_of, len(db.locus_names), PARAMS["minscore"], PARAMS["max_xM"], PARAMS["min_read_len"]), parts))
+        s = sum(r[0] for r in res); c = sum(r[1].astype(np.int64) for r in res).astype(np.uint32)
+        f = np.minimum.reduce([r[2] for r in res])
+        chosen = api.fast_select(index, s, c, f, PARAMS["penalty"])
+        tids = [t for _sp, ts in chosen for t in ts]
+
+        def contig(t):
+            counts, _ = corc.contig_counts(tab, t, 20, PARAMS["minscore"], PARAMS["max_xM"], 8000)
+            return corc.consensus(counts, db.row_seq(t).encode(), 1)
+        return list(pool.map(contig, tids))
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = (time.perf_counter() - t0) / steps
+    return n / dt, dt, "%d reads x K=%d = %d records of the same generator (1/%d of the workload), C port of the oracle, %d threads" % (
+        n_reads, args.k, n, max(1, args.reads // n_reads), threads)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    db = make_db(args)
+    threads = os.cpu_count() or 1
+    rate, dt, sample = cpu_port_run(db, args, args.cpu_sample_reads, threads, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "aligned reads/s (score+pileup+consensus)", "value": rate, "unit": "records/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32/u8", "data": "synthetic",
+            "config": workload_config(args, 1), "gpu_launches": 0,
+            "cpu_baseline": {"value": rate, "unit": "records/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference itself (pure Python over pysam/samtools) cannot run on this box; this is the C port of its restatement (oracle/c), a faster stand-in"}
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": "configs[1]: single sample, %d x %d bp reads, K=%d alignments/read (%d BAM records per GPU), coordinate-sorted; "
+                        "E. coli + S. aureus + K. pneumoniae synthetic schemes, 21 loci x %d alleles" % (args.reads, args.read_len, args.k, args.reads * args.k, args.alleles),
+            "mode": "parity (htslib max_depth 8000, minqual 20, minscore 80, max_xM 5)",
+            "sharding": "replica" if world == 1 else "contig-aligned: each rank owns the records of a disjoint locus set; all-reduce SUM(sum_as,n_hit,counts) MIN(first_idx)",
+            "l2": "the 360 MB score stream exceeds the 126 MB L2 and is re-streamed every step (no flush needed)"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    from metamlst_b200 import api, native, pipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = "cuda:%d" % local
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device(device))
+    native.lib()  # fail loudly if the CUDA library is missing
+    peak, peak_src = peaks()
+
+    db = make_db(args)
+    index = api.AlleleIndex(db.ref_names())
+    n_loci = len(db.locus_names)
+    subset = None if world == 1 else [l for l in range(n_loci) if l % world == rank]
+    st, _ = gen_streams(db, args, device, 8000, subset, seed=1002 + rank)
+    R_local = int(st.tid.shape[0])
+    pipe = pipeline.DevicePipeline(st, index, db.row_seq, impl=args.pileup_impl, idx_base=rank * R_local, **PARAMS)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    result = None
+    for _ in range(max(args.warmup, 3)):
+        result = pipe.step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    pipe.timers = {}
+    pipe.launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = pipe.step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    assert out == result, "results changed between steps"
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
+    R_total = R_local * world
+    kms = {k: float(np.mean(event_ms(v))) for k, v in pipe.timers.items()}
+    launches = pipe.launches
+    pipe.timers = None
+    tids = [index.name_to_tid[c] for sp in out for (c, _s, _h, _n) in out[sp]]
+    score_bytes = 9.0 * R_local
+    pb, precs = pileup_alg_bytes(st, [t for t in tids if st.contig_start[t + 1] > st.contig_start[t]], args.read_len)
+    rooflines = {
+        "score": {"bound": "hbm", "achieved": score_bytes / kms["score"] / 1e6, "peak": peak, "unit": "GB/s", "frac": score_bytes / kms["score"] / 1e6 / peak,
+                  "traffic": None, "ms": kms["score"], "algorithmic_bytes": score_bytes},
+        "pileup_parity": {"bound": "hbm", "achieved": pb / kms.get("pileup", float("inf")) / 1e6, "peak": peak, "unit": "GB/s",
+                          "frac": pb / kms.get("pileup", float("inf")) / 1e6 / peak, "traffic": None, "ms": kms.get("pileup"),
+                          "algorithmic_bytes": pb, "records": precs},
+        "consensus": {"ms": kms.get("consensus")},
+    }
+    dominant = max(("score", "pileup_parity"), key=lambda k: rooflines[k]["ms"] or 0)
+    line = {"metric": "aligned reads/s (score+pileup+consensus)", "value": R_total / (ms / 1e3), "unit": "records/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32/u8 (integer bit-plane arithmetic)", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks, "gpu_launches": launches,
+            "roofline": dict(rooflines[dominant], kernel=dominant, peak_source=peak_src), "rooflines": rooflines,
+            "kernel_ms_per_step": kms, "records_per_gpu": R_local,
+            "host_gap_ms_per_step": ms - sum(kms.values())}
+
+    # ---- end to end through the host-buffer C-ABI (pinned host memory -> results on the host)
+    soa = st.to_host(pinned=True)
+    ctx = native.Context(local)
+    def e2e_step():
+        cel_raw = api.score_soa_raw(ctx, soa, index, **{k: PARAMS[k] for k in ("minscore", "max_xM", "min_read_len")})
+        chosen = api.fast_select(index, cel_raw[0], cel_raw[1], cel_raw[2], PARAMS["penalty"])
+        ts = [t for _sp, tt in chosen for t in tt]
+        seqs, holes, snps, _, _ = api.pileup_consensus(ctx, soa, ts, [db.row_seq(t) for t in ts], PARAMS["minscore"], PARAMS["max_xM"], 1, args.pileup_impl)
+        return ts, seqs, holes, snps
+    if world == 1:
+        for _ in range(2):
+            r0 = e2e_step()
+        assert [s for s in r0[1]] == [s for sp in out for (_c, s, _h, _n) in out[sp]], "e2e result differs from the device-resident result"
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_e2e = max(3, min(args.steps, 10))
+        for _ in range(n_e2e):
+            e2e_step()
+        dt = (time.perf_counter() - t0) / n_e2e
+        h2d = 9 * R_local + db.n_rows * 5 + int(sum((st.contig_start[t + 1] - st.contig_start[t]) * 13 + 0 for t in tids))
+        h2d += int(sum(int(soa.p_row_off[int(st.contig_start[t + 1])]) - int(soa.p_row_off[int(st.contig_start[t])]) for t in tids)) * 4
+        d2h = db.n_rows * 16 + 16 + sum(int(st.ref_lens[t]) for t in tids) + 8 * len(tids)
+        line["e2e"] = {"value": R_local / dt, "unit": "records/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3}
+    else:
+        line["e2e"] = None
+    ctx.close()
+    del soa
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        line["uncapped"] = extra_uncapped(db, args, device, index, peak)
+        line["hamming"] = extra_hamming(device, peak)
+        rate, dt, sample = cpu_port_run(db, args, args.cpu_sample_reads, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": "records/s", "cores": 1, "kind": "port", "sample": sample, "host_cpus": os.cpu_count()}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def extra_uncapped(db, args, device, index, peak):
+    """Same sample with the htslib depth cap disabled: the full histogram work (SURVEY.md 8 H1 'uncapped mode')."""
+    import torch
+    from metamlst_b200 import pipeline
+    st, _ = gen_streams(db, args, device, None)
+    out = {}
+    for impl, name in ((2, "bitsliced"), (1, "atomic")):
+        pipe = pipeline.DevicePipeline(st, index, db.row_seq, impl=impl, **PARAMS)
+        for _ in range(2):
+            res = pipe.step()
+        pipe.timers = {}
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = 5 if impl == 2 else 2
+        for _ in range(n):
+            res2 = pipe.step()
+        e1.record()
+        torch.cuda.synchronize()
+        assert res2 == res
+        out.setdefault("_res", res)
+        assert res == out["_res"], "atomic and bit-sliced pileup disagree"
+        tids = [index.name_to_tid[c] for sp in res for (c, _s, _h, _n) in res[sp]]
+        pb, precs = pileup_alg_bytes(st, tids, args.read_len)
+        pms = float(np.mean(event_ms(pipe.timers["pileup"])))
+        out[name] = {"ms_per_step": e0.elapsed_time(e1) / n, "value": int(st.tid.shape[0]) / (e0.elapsed_time(e1) / n / 1e3), "unit": "records/s",
+                     "pileup_ms": pms, "pileup_records": precs, "algorithmic_bytes": pb,
+                     "roofline": {"bound": "hbm", "achieved": pb / pms / 1e6, "peak": peak, "unit": "GB/s", "frac": pb / pms / 1e6 / peak, "traffic": None},
+                     "increments_per_s": precs * args.read_len * 0.94 / (pms / 1e3)}
+        del pipe
+    del out["_res"]
+    del st
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_hamming(device, peak, n_rows=1_000_000, n_q=10_000):
+    """configs[4]: 10 k reconstructed loci vs 1 M DB alleles (length 480 +- 60), all-pairs and locus-restricted."""
+    import torch
+    from metamlst_b200 import devpack, native
+    g = torch.Generator(device=device); g.manual_seed(1005)
+    W = 24
+    lens = (480 + torch.randint(-60, 61, (n_rows,), generator=g, device=device)).to(torch.int64)
+    n_loci = 1000
+    hi = torch.zeros((n_rows, W), dtype=torch.int32, device=device)
+    lo = torch.zeros((n_rows, W), dtype=torch.int32, device=device)
+    base = torch.randint(0, 4, (n_loci, W * 32), generator=g, device=device, dtype=torch.uint8)
+    per = n_rows // n_loci
+    col = torch.arange(W * 32, device=device)[None, :]
+    for c0 in range(0, n_rows, 100_000):
+        c1 = min(n_rows, c0 + 100_000)
+        codes = base[(torch.arange(c0, c1, device=device) // per).clamp(max=n_loci - 1)].clone()
+        mut = torch.rand(codes.shape, generator=g, device=device) < (5.0 / 480)
+        codes = torch.where(mut, (codes + torch.randint(1, 4, codes.shape, generator=g, device=device, dtype=torch.uint8)) % 4, codes)
+        valid = col < lens[c0:c1, None]
+        hi[c0:c1] = devpack._pack_words(((codes & 2) != 0) & valid)
+        lo[c0:c1] = devpack._pack_words(((codes & 1) != 0) & valid)
+    qsrc = torch.randint(0, n_rows, (n_q,), generator=g, device=device)
+    qsrc = torch.sort(qsrc).values
+    q_hi, q_lo, q_len = hi[qsrc].contiguous(), lo[qsrc].contiguous(), lens[qsrc].to(torch.int16)
+    flip = torch.randint(0, 2 ** 31 - 1, (n_q, W), generator=g, device=device, dtype=torch.int32) & torch.randint(0, 2 ** 31 - 1, (n_q, W), generator=g, device=device, dtype=torch.int32) \
+        & torch.randint(0, 2 ** 31 - 1, (n_q, W), generator=g, device=device, dtype=torch.int32) & torch.randint(0, 2 ** 31 - 1, (n_q, W), generator=g, device=device, dtype=torch.int32) \
+        & torch.randint(0, 2 ** 31 - 1, (n_q, W), generator=g, device=device, dtype=torch.int32) & torch.randint(0, 2 ** 31 - 1, (n_q, W), generator=g, device=device, dtype=torch.int32)
+    qvalid = devpack._pack_words(col < lens[qsrc][:, None])
+    q_hi = (q_hi ^ (flip & qvalid)).contiguous()  # ~1/64 of the bases substituted
+    nt = (n_rows + 31) // 32
+    def tile(x):
+        p = torch.zeros((nt * 32, W), dtype=torch.int32, device=device)
+        p[:n_rows] = x
+        return p.view(nt, 32, W).transpose(1, 2).contiguous().view(-1)
+    db_hi, db_lo = tile(hi), tile(lo)
+    row_len = lens.to(torch.int16)
+    best = torch.empty(n_q, dtype=torch.int64, device=device)
+    lib = native.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    out = {}
+    # locus-restricted blocks: queries are sorted by source row => by locus
+    qloc = (qsrc // per).clamp(max=n_loci - 1).cpu().numpy()
+    blocks = []
+    i = 0
+    while i < n_q:
+        j = i
+        while j < n_q and qloc[j] == qloc[i]:
+            j += 1
+        l = int(qloc[i])
+        blocks.append((i, j, l * per, n_rows if l == n_loci - 1 else (l + 1) * per))
+        i = j
+    modes = {"all_pairs": (np.asarray([[0, n_q, 0, n_rows]], np.uint32), n_rows, n_q),
+             "locus_restricted": (np.asarray(blocks, np.uint32), max(b[3] - b[2] for b in blocks), max(b[1] - b[0] for b in blocks))}
+    S = 2 * W * 4
+    for name, (blk, mr, mq) in modes.items():
+        blk_d = torch.from_numpy(blk.view(np.int32).reshape(-1)).to(device)
+        def run():
+            best.fill_(-1)
+            native.check(lib.mmlst_hamming_min_dev2(native.ptr(db_hi), native.ptr(db_lo), native.ptr(row_len), n_rows, W, native.ptr(q_hi), native.ptr(q_lo),
+                                                    native.ptr(q_len), n_q, native.ptr(blk_d), int(blk.shape[0]), int(mr), int(mq), 0, native.ptr(best), stream))
+        run(); run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        pairs = float(sum((int(b[1]) - int(b[0])) * (int(b[3]) - int(b[2])) for b in blk))
+        comp = n_rows * S + n_q * S + 8 * n_q
+        words = pairs * W
+        res = best.cpu().numpy().view(np.uint64)
+        out[name] = {"ms": ms, "pairs": pairs, "pairs_per_s": pairs / (ms / 1e3), "compulsory_bytes": comp,
+                     "compulsory_GBps": comp / ms / 1e6, "hbm_frac": comp / ms / 1e6 / peak,
+                     "word_ops_per_s": words / (ms / 1e3), "effective_GBps_labelled_effective": pairs * S / ms / 1e6,
+                     "mean_min_dist": float((res >> np.uint64(32)).astype(np.float64).mean())}
+    return out
+
+
+if __name__ == "__main__":
+    main()

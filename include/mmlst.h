@@ -71,7 +71,8 @@ void mmlst_pinned_free(void* p);
  *   allow[tid]    : 1 if the record's species passes --filter (metamlst.py:114), else the record is not counted at all
  *   locus_of[tid] : global locus index of the allele row
  *   sum_as[tid] += as0, n_hit[tid] += 1 for records with as0 >= minscore && qlen >= min_read_len && xm3 <= max_xm
- *   first_idx[locus] = min(orig index) over passing records (H5: dict insertion order); caller presets 0xFFFFFFFF
+ *   first_idx[tid] = min(orig index) over the allele's passing records (H5: dict insertion order of species, loci
+ *                    and alleles all follow from it); caller presets 0xFFFFFFFF
  *   counters[0] += allowed records (totalReads), counters[1] += allowed but failing (ignoredReads)
  * Outputs are ACCUMULATED (caller zeroes them), so shards / GPUs can be summed.
  * --------------------------------------------------------------------------------------------------------------- */

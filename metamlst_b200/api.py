@@ -1,0 +1,304 @@
+"""Host-side mirror of the reference's four Python seams on top of libmmlst.
+
+    S1  score_soa          <-> metamlst.py:96-151          (cel / totalReads / ignoredReads)
+    S2  build_consensus    <-> metaMLST_functions.py:249-281 (same name, argument meaning and return shape)
+    S3  HammingIndex       <-> metamlst-merge.py:174-181 + metaMLST_functions.py:224-234
+    S4  define_profile     <-> metaMLST_functions.py:205-216 (SQL kept: ms-scale, H11 quirks preserved verbatim)
+
+All per-record / per-base / per-pair arithmetic runs in the CUDA kernels; what stays here is what the reference
+also does once per allele or per locus in Python floats and strings (penalty, round(.,1), dict ordering, formatting),
+so that those are bit-identical by construction (H5, H6).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import native, packing
+
+NO_IDX = 0xFFFFFFFF
+
+
+class AlleleIndex:
+    """BAM reference names `organism_gene_allele` (metamlst.py:107) -> species / locus / allele tables."""
+
+    def __init__(self, ref_names: Sequence[str]):
+        self.ref_names = list(ref_names)
+        self.species: List[str] = []
+        self.gene: List[str] = []
+        self.allele: List[str] = []
+        self.locus_names: List[Tuple[str, str]] = []
+        loc: Dict[Tuple[str, str], int] = {}
+        locus_of = np.zeros(len(self.ref_names), dtype=np.uint32)
+        for i, name in enumerate(self.ref_names):
+            parts = name.split("_")
+            if len(parts) != 3:
+                # the reference dies with "ValueError: not enough/too many values to unpack" at metamlst.py:107 as soon
+                # as a record on this reference is read; we refuse the header up front
+                raise ValueError("reference name %r is not organism_gene_allele (metamlst.py:107)" % name)
+            s, g, a = parts
+            self.species.append(s)
+            self.gene.append(g)
+            self.allele.append(a)
+            key = (s, g)
+            if key not in loc:
+                loc[key] = len(self.locus_names)
+                self.locus_names.append(key)
+            locus_of[i] = loc[key]
+        self.locus_of = locus_of
+        self.n_loci = len(self.locus_names)
+        self.name_to_tid = {n: i for i, n in enumerate(self.ref_names)}
+
+    def allow_mask(self, species_filter: Optional[str]) -> np.ndarray:
+        """metamlst.py:114: `(args.filter and species in args.filter.split(',')) or not args.filter`."""
+        if not species_filter:
+            return np.ones(len(self.ref_names), dtype=np.uint8)
+        keep = set(species_filter.split(","))
+        return np.fromiter((1 if s in keep else 0 for s in self.species), dtype=np.uint8, count=len(self.species))
+
+
+def finish_scores(index: AlleleIndex, sum_as: np.ndarray, n_hit: np.ndarray, first_idx: np.ndarray, penalty: int):
+    """Integer tables -> `cel` exactly as metamlst.py holds it after line 151.
+    Dict insertion order (H5) = ascending first passing record index of species, locus, allele."""
+    hit = np.nonzero(n_hit)[0]
+    hit = hit[np.argsort(first_idx[hit], kind="stable")]
+    cel: Dict[str, Dict[str, Dict[str, tuple]]] = {}
+    raw: Dict[Tuple[str, str], List[Tuple[str, int, int]]] = {}
+    for t in hit:
+        t = int(t)
+        s, g, a = index.species[t], index.gene[t], index.allele[t]
+        cel.setdefault(s, {}).setdefault(g, {})
+        raw.setdefault((s, g), []).append((a, int(sum_as[t]), int(n_hit[t])))
+    for (s, g), lst in raw.items():
+        maxLen = max(n for (_a, _s, n) in lst)  # metamlst.py:137
+        for a, localScore, geneLen in lst:
+            if geneLen != maxLen:
+                localScore = localScore - (maxLen - geneLen) * penalty  # :146-147
+            averageScore = float(localScore) / float(geneLen)
+            cel[s][g][a] = (localScore, geneLen, round(averageScore, 1))  # :151 (H6: Python float rounding)
+    return cel
+
+
+def score_soa_raw(ctx: native.Context, soa: packing.SoaHost, index: AlleleIndex, minscore: int = 80, max_xM: int = 5,
+                  min_read_len: int = 50, species_filter: Optional[str] = None):
+    """Seam S1, integer half: (sum_as, n_hit, first_idx, totalReads, ignoredReads) straight from mmlst_score."""
+    n_ref = len(index.ref_names)
+    allow = index.allow_mask(species_filter)
+    sum_as = np.zeros(n_ref, np.int64)
+    n_hit = np.zeros(n_ref, np.uint32)
+    first_idx = np.full(n_ref, NO_IDX, np.uint32)
+    counters = np.zeros(2, np.uint64)
+    cs = soa.c_struct()
+    prm = native.ScoreParams(int(minscore), int(max_xM), int(min_read_len))
+    native.check(native.lib().mmlst_score(ctx.handle, C.byref(cs), native.ptr(allow), native.ptr(index.locus_of), index.n_loci,
+                                          C.byref(prm), native.ptr(sum_as), native.ptr(n_hit), native.ptr(first_idx),
+                                          native.ptr(counters)))
+    return sum_as, n_hit, first_idx, int(counters[0]), int(counters[1])
+
+
+def score_soa(ctx: native.Context, soa: packing.SoaHost, index: AlleleIndex, minscore: int = 80, max_xM: int = 5,
+              min_read_len: int = 50, species_filter: Optional[str] = None, penalty: int = 100):
+    """Seam S1.  Returns (cel, totalReads, ignoredReads, raw) with raw = (sum_as, n_hit, first_idx) numpy tables."""
+    sum_as, n_hit, first_idx, total, ignored = score_soa_raw(ctx, soa, index, minscore, max_xM, min_read_len, species_filter)
+    cel = finish_scores(index, sum_as, n_hit, first_idx, penalty)
+    return cel, total, ignored, (sum_as, n_hit, first_idx)
+
+
+def select_alleles(species_cel: Dict[str, Dict[str, tuple]]) -> List[Tuple[str, str]]:
+    """metamlst.py:244: per locus (dict order) the lowest-numbered allele among those whose rounded average equals
+    the locus maximum."""
+    out = []
+    for g1, g2 in species_cel.items():
+        best = max(avg for (_v, _l, avg) in g2.values())
+        out.append((g1, sorted((k for k, (_v, _l, avg) in g2.items() if avg == best), key=lambda x: int(x))[0]))
+    return out
+
+
+class ConsRecord:
+    """What buildConsensus' callers touch on a Bio.SeqRecord (metamlst.py:254-285): id, seq (mutable), description."""
+
+    def __init__(self, seq: str, id: str, description: str):
+        self.seq = seq
+        self.id = id
+        self.description = description
+
+    def __repr__(self):
+        return "ConsRecord(id=%r, %s, len=%d)" % (self.id, self.description, len(self.seq))
+
+
+def pileup_consensus(ctx: native.Context, soa: packing.SoaHost, chosen_tid: Sequence[int], dbseqs: Sequence[str],
+                     minscore: int, max_xM: int, mincov: int = 1, impl: int = 0, want_counts: bool = False):
+    """Counts + consensus for the chosen contigs.  Returns (cons strings, holes, snps, counts or None, col_off)."""
+    n = len(chosen_tid)
+    lens = [int(soa.ref_lens[t]) for t in chosen_tid]
+    col_off = np.zeros(n + 1, dtype=np.uint32)
+    col_off[1:] = np.cumsum(lens)
+    total = int(col_off[-1])
+    db = np.zeros(max(total, 1), dtype=np.uint8)
+    for i, (t, s) in enumerate(zip(chosen_tid, dbseqs)):
+        if len(s) < lens[i]:
+            # metaMLST_functions.py:267/269 index dbSequen[i] for i < BAM LN (H10)
+            raise IndexError("string index out of range: BAM LN %d > DB sequence length %d for %s" % (lens[i], len(s), soa.ref_names[t]))
+        db[col_off[i]:col_off[i + 1]] = np.frombuffer(s[:lens[i]].encode("latin-1"), dtype=np.uint8)
+    tid_arr = np.asarray(chosen_tid, dtype=np.uint32)
+    counts = np.zeros((max(total, 1), 5), dtype=np.uint32) if want_counts else None
+    cons = np.zeros(max(total, 1), dtype=np.uint8)
+    holes = np.zeros(max(n, 1), dtype=np.uint32)
+    snps = np.zeros(max(n, 1), dtype=np.uint32)
+    cs = soa.c_struct()
+    native.check(native.lib().mmlst_pileup_consensus(ctx.handle, C.byref(cs), native.ptr(tid_arr), n, native.ptr(db),
+                                                     native.ptr(col_off), int(minscore), int(max_xM), int(mincov), int(impl),
+                                                     native.ptr(counts), native.ptr(cons), native.ptr(holes), native.ptr(snps)))
+    seqs = [cons[col_off[i]:col_off[i + 1]].tobytes().decode("latin-1") for i in range(n)]
+    return seqs, holes[:n].copy(), snps[:n].copy(), (counts[:total] if want_counts else None), col_off
+
+
+def build_consensus(ctx: native.Context, soa: packing.SoaHost, chromosomeList: Dict[str, str], filterScore: int, max_xM: int,
+                    debugMode: bool = False, impl: int = 0) -> List[ConsRecord]:
+    """Seam S2 -- same contract as metaMLST_functions.buildConsensus(bamFile, chromosomeList, filterScore, max_xM,
+    debugMode): list order = chromosomeList order, rec.description == 'CI::<holes>_SP::<snps>'.  The BAM is replaced by
+    its unpacked SoaHost (consensus rule hard-wired upstream: dominant 0.4 (output-dead), mincov 1, minqual 20)."""
+    if soa.minqual != 20:
+        raise ValueError("buildConsensus needs a stream unpacked with minqual=20 (metaMLST_functions.py:258)")
+    name2tid = {n: i for i, n in enumerate(soa.ref_names)}
+    contigs = list(chromosomeList.keys())
+    for c in contigs:
+        if c not in name2tid:
+            # cmseq get_contig_by_label returns None -> AttributeError upstream (cmseq/cmseq.py:88)
+            raise AttributeError("'NoneType' object has no attribute 'reference_free_consensus' (contig %s not in BAM)" % c)
+    tids = [name2tid[c] for c in contigs]
+    seqs, holes, snps, _, _ = pileup_consensus(ctx, soa, tids, [chromosomeList[c] for c in contigs], filterScore, max_xM, 1, impl)
+    return [ConsRecord(seqs[i], contigs[i], "CI::" + str(int(holes[i])) + "_SP::" + str(int(snps[i]))) for i in range(len(contigs))]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Seam S3
+# ----------------------------------------------------------------------------------------------------------------
+
+class HammingIndex:
+    """Known alleles resident on the GPU as 2-bit planes; rows grouped by (bacterium, gene) in sequencesGetAll order
+    (metaMLST_functions.py:224-228: rows of `alleles` by rowid)."""
+
+    def __init__(self, ctx: native.Context, rows: Sequence[Tuple[str, str, int, str]]):
+        """rows: (bacterium, gene, alleleVariant, sequence) in table order."""
+        self.ctx = ctx
+        order = sorted(range(len(rows)), key=lambda i: (rows[i][0], rows[i][1]))  # stable: keeps table order inside a locus
+        self.rows = [rows[i] for i in order]
+        self.block: Dict[Tuple[str, str], Tuple[int, int]] = {}
+        for i, (b, g, _v, _s) in enumerate(self.rows):
+            lo, hi = self.block.get((b, g), (i, i))
+            self.block[(b, g)] = (lo, i + 1)
+        seqs = [r[3].encode("latin-1") for r in self.rows]
+        self.W = packing._w_for(max((len(s) for s in seqs), default=1))
+        hi, lo, ln = packing.encode_2bit(seqs, self.W)
+        self._hi, self._lo = packing.tile_db(hi, lo)
+        self._len = ln
+        native.check(native.lib().mmlst_db_upload(ctx.handle, native.ptr(self._hi), native.ptr(self._lo), native.ptr(self._len),
+                                                  len(self.rows), self.W))
+
+    @classmethod
+    def from_sqlite(cls, ctx, conn, bacterium: Optional[str] = None):
+        q = "SELECT bacterium, gene, alleleVariant, sequence FROM alleles"
+        args = ()
+        if bacterium is not None:
+            q += " WHERE bacterium = ?"
+            args = (bacterium,)
+        return cls(ctx, [(r[0], r[1], r[2], r[3]) for r in conn.execute(q + " ORDER BY recID", args)])
+
+    def search(self, queries: Sequence[str], ranges: Sequence[Tuple[int, int]]):
+        """min/argmin of stringDiff(query, row) over rows[ranges[i]] for every query; ties -> lowest row."""
+        nq = len(queries)
+        if nq == 0:
+            return np.zeros(0, np.uint32), np.zeros(0, np.uint32)
+        # group queries with identical row ranges into blocks (queries of a block must be contiguous)
+        order = sorted(range(nq), key=lambda i: ranges[i])
+        qs = [queries[i].encode("latin-1") for i in order]
+        hi, lo, ln = packing.encode_2bit(qs, self.W)
+        blocks = []
+        i = 0
+        while i < nq:
+            j = i
+            while j < nq and ranges[order[j]] == ranges[order[i]]:
+                j += 1
+            blocks.append((i, j, ranges[order[i]][0], ranges[order[i]][1]))
+            i = j
+        blk = np.asarray(blocks, dtype=np.uint32).reshape(-1)
+        md = np.zeros(nq, np.uint32)
+        am = np.zeros(nq, np.uint32)
+        native.check(native.lib().mmlst_hamming_min(self.ctx.handle, native.ptr(hi), native.ptr(lo), native.ptr(ln), nq,
+                                                    native.ptr(blk), len(blocks), native.ptr(md), native.ptr(am)))
+        out_d = np.zeros(nq, np.uint32)
+        out_a = np.zeros(nq, np.uint32)
+        out_d[order] = md
+        out_a[order] = am
+        return out_d, out_a
+
+    def closest_allele(self, bacterium: str, gene: str, seq: str) -> Tuple[int, int]:
+        """(min distance, alleleVariant) over the rows of (bacterium, gene); flag of metamlst-merge.py:178 = d <= z."""
+        rng = self.block.get((bacterium, gene))
+        if rng is None:
+            return (1 << 30, -1)
+        d, a = self.search([seq], [rng])
+        return int(d[0]), int(self.rows[int(a[0])][2])
+
+
+def stringDiff(s1: str, s2: str, ctx: Optional[native.Context] = None) -> int:
+    """metaMLST_functions.py:230-234, kept as a name; one pair through the same kernel."""
+    ctx = ctx or native.Context(0)
+    idx = HammingIndex(ctx, [("x", "x", 1, s2)])
+    return int(idx.search([s1], [(0, 1)])[0][0])
+
+
+def define_profile(conn, geneList: Sequence[str]):
+    """Seam S4 -- metaMLST_functions.py:205-216 including H11: unknown labels shrink the denominator, [(0,0)] only
+    when the LAST lookup failed.  Stays SQL (ms-scale)."""
+    recs = []
+    result = None
+    for allele in geneList:
+        result = conn.execute("SELECT recID FROM alleles WHERE bacterium||'_'||gene||'_'||alleleVariant = ?", (allele,)).fetchone()
+        if result:
+            recs.append(str(result[0]))
+    if not result:
+        return [(0, 0)]
+    inl = ",".join(recs)
+    q = ("SELECT profileCode, COUNT(*) as T FROM profiles WHERE alleleCode IN (" + inl + ") GROUP BY profileCode HAVING T = "
+         "(SELECT COUNT(*) FROM profiles WHERE alleleCode IN (" + inl + ") GROUP BY profileCode ORDER BY COUNT(*) DESC LIMIT 1) ORDER BY T DESC")
+    return [(row[0], int((float(row[1]) / float(len(recs))) * 100)) for row in conn.execute(q)]
+
+
+def fast_select(index: AlleleIndex, sum_as: np.ndarray, n_hit: np.ndarray, first_idx: np.ndarray, penalty: int = 100):
+    """Vectorised equivalent of finish_scores + select_alleles for the hot loop (bench, cohort driver): per detected
+    locus the chosen allele row, in the reference's dict order (species by first record, loci by first record).
+
+    Exactness: Python's round(x, 1) is monotone in x, so the alleles whose rounded average equals the locus maximum
+    all lie within 0.11 of the best raw average; only those few candidates go through Python round() (H6).
+    Returns [(species, [tid per locus in dict order])] in species dict order."""
+    hit = n_hit > 0
+    loc = index.locus_of.astype(np.int64)
+    nl = index.n_loci
+    maxlen = np.zeros(nl, dtype=np.int64)
+    np.maximum.at(maxlen, loc[hit], n_hit[hit].astype(np.int64))
+    n = n_hit.astype(np.int64)
+    score = sum_as - (maxlen[loc] - n) * penalty
+    avg = np.full(n.shape[0], -np.inf)
+    avg[hit] = score[hit].astype(np.float64) / n[hit].astype(np.float64)
+    best = np.full(nl, -np.inf)
+    np.maximum.at(best, loc[hit], avg[hit])
+    cand = np.nonzero(hit & (avg >= best[loc] - 0.11))[0]
+    chosen: Dict[int, Tuple[float, int, int]] = {}
+    for t in cand:
+        t = int(t)
+        r = round(float(score[t]) / float(n[t]), 1)
+        l = int(loc[t])
+        a = int(index.allele[t])
+        cur = chosen.get(l)
+        if cur is None or r > cur[0] or (r == cur[0] and a < cur[1]):
+            chosen[l] = (r, a, t)
+    lfirst = np.full(nl, NO_IDX, dtype=np.uint32)
+    np.minimum.at(lfirst, loc[hit], first_idx[hit])
+    out: Dict[str, List[Tuple[int, int]]] = {}
+    for l in sorted(chosen, key=lambda l: int(lfirst[l])):
+        out.setdefault(index.locus_names[l][0], []).append(chosen[l][2])
+    return list(out.items())

@@ -150,10 +150,10 @@ extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* al
     if (soa->orig_idx) TRY(h2d(c->oidx, soa->orig_idx, n, s));
     TRY(h2d(c->allow, allow, nr, s));
     TRY(h2d(c->locus_of, locus_of, nr, s));
-    TRY(c->sum_as.reserve(nr * 8)); TRY(c->n_hit.reserve(nr * 4)); TRY(c->first_idx.reserve((size_t)n_loci * 4 + 4)); TRY(c->counters.reserve(16));
+    TRY(c->sum_as.reserve(nr * 8)); TRY(c->n_hit.reserve(nr * 4)); TRY(c->first_idx.reserve(nr * 4 + 4)); TRY(c->counters.reserve(16));
     CUDA_TRY(cudaMemsetAsync(c->sum_as.p, 0, nr * 8, s));
     CUDA_TRY(cudaMemsetAsync(c->n_hit.p, 0, nr * 4, s));
-    CUDA_TRY(cudaMemsetAsync(c->first_idx.p, 0xff, (size_t)n_loci * 4, s));
+    CUDA_TRY(cudaMemsetAsync(c->first_idx.p, 0xff, nr * 4, s));
     CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, 16, s));
     TRY(mmlst_score_dev(c->tid.as<uint32_t>(), c->as0.as<int16_t>(), c->xm3.as<uint8_t>(), c->qlen.as<uint16_t>(),
                         soa->orig_idx ? c->oidx.as<uint32_t>() : nullptr, n, 0, c->allow.as<uint8_t>(),
@@ -162,7 +162,7 @@ extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* al
                         c->counters.as<uint64_t>(), s));
     CUDA_TRY(cudaMemcpyAsync(sum_as, c->sum_as.p, nr * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(n_hit, c->n_hit.p, nr * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(first_idx, c->first_idx.p, (size_t)n_loci * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(first_idx, c->first_idx.p, nr * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(counters, c->counters.p, 16, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return MMLST_OK;

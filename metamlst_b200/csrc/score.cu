@@ -23,7 +23,7 @@ __device__ __forceinline__ void flush_run(const ScoreArgs& a, uint32_t key, long
     if (c) {
         atomicAdd(reinterpret_cast<unsigned long long*>(a.sum_as + key), static_cast<unsigned long long>(s));
         atomicAdd(a.n_hit + key, c);
-        atomicMin(a.first_idx + a.locus_of[key], mn);
+        atomicMin(a.first_idx + key, mn);
     }
 }
 

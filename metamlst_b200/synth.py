@@ -217,34 +217,46 @@ class AlnTable:
         return self.take(self.coord_order())
 
 
-def _nearest_alleles(db: SynthDB, k: int) -> np.ndarray:
+def _nearest_alleles(db: SynthDB, k: int, device: str = "cpu") -> np.ndarray:
     """For every row the k nearest other rows of its locus by Hamming distance (ties -> lower row)."""
     out = np.zeros((db.n_rows, k), dtype=np.int32)
+    dev = torch.device(device)
     for li in range(len(db.locus_names)):
         r0, r1 = int(db.locus_row0[li]), int(db.locus_row0[li + 1])
         ln = int(db.seq_off[r0 + 1] - db.seq_off[r0])
-        m = db.seq[db.seq_off[r0]:db.seq_off[r1]].reshape(r1 - r0, ln)
+        m = torch.from_numpy(db.seq[db.seq_off[r0]:db.seq_off[r1]].reshape(r1 - r0, ln)).to(dev)
         a = r1 - r0
-        d = np.zeros((a, a), dtype=np.int32)
+        d = torch.zeros((a, a), dtype=torch.int32, device=dev)
         for c in range(0, a, 64):
-            d[c:c + 64] = (m[c:c + 64, None, :] != m[None, :, :]).sum(-1)
-        d[np.arange(a), np.arange(a)] = 1 << 30
+            d[c:c + 64] = (m[c:c + 64, None, :] != m[None, :, :]).sum(-1).to(torch.int32)
+        d.fill_diagonal_(1 << 30)
         kk = min(k, a - 1)
-        nn = np.argsort(d, axis=1, kind="stable")[:, :kk]
+        nn = torch.sort(d, dim=1, stable=True).indices[:, :kk].cpu().numpy()
         out[r0:r1, :kk] = nn + r0
         if kk < k:
             out[r0:r1, kk:] = out[r0:r1, :1] if kk else np.arange(r0, r1)[:, None]
     return out
 
 
-def make_sample(db: SynthDB, n_reads: int, read_len: int = 100, seed: int = 1001, K: int = 4,
-                org_props: Optional[Sequence[float]] = None, sub_err: float = 0.005, n_frac: float = 0.01,
-                novel_loci: int = 2, frac_clip: float = 0.10, frac_indel: float = 0.01,
-                device: str = "cpu") -> AlnTable:
+def _cached_nearest(db: SynthDB, k: int, device: str) -> np.ndarray:
+    cache = db.__dict__.setdefault("_nearest_cache", {})
+    if k not in cache:
+        cache[k] = _nearest_alleles(db, k, device)
+    return cache[k]
+
+
+def gen_core(db: SynthDB, n_reads: int, read_len: int = 100, seed: int = 1001, K: int = 4,
+             org_props: Optional[Sequence[float]] = None, sub_err: float = 0.005, n_frac: float = 0.01,
+             novel_loci: int = 2, frac_clip: float = 0.10, frac_indel: float = 0.01,
+             device: str = "cpu", strain_seed: Optional[int] = None,
+             locus_subset: Optional[Sequence[int]] = None) -> dict:
     """Reads drawn uniformly from one sample strain per organism (one ST, `novel_loci` loci carrying 1-3 novel
     SNPs); K records per read (true allele flag 0/16, K-1 nearest alleles flag 256/272); AS = 2*#M - 6*XM -
-    sum(5+3*gaplen); aux order AS,XS,XN,XM,XO,XG,NM,YT.  Records are emitted name-grouped (bowtie2 order)."""
-    rng = np.random.Generator(np.random.PCG64(seed))
+    sum(5+3*gaplen).  Returns torch tensors on `device`: per read (bases, qual, start, rtype, a_split) and per
+    record [n_reads, K] (rows, AS, XS, xm, flag).  `make_sample` turns them into an AlnTable (host),
+    `metamlst_b200.devpack.pack_core` into the packed streams directly on the GPU (bench)."""
+    # the sample strain depends on strain_seed only, so a big sample can be generated in chunks of reads
+    rng = np.random.Generator(np.random.PCG64(seed if strain_seed is None else strain_seed))
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -283,7 +295,7 @@ def make_sample(db: SynthDB, n_reads: int, read_len: int = 100, seed: int = 1001
     genome = torch.from_numpy(np.concatenate(strain_seqs)).to(dev)
     allseq = torch.from_numpy(db.seq).to(dev)
     row_off_t = torch.from_numpy(db.seq_off).to(dev)
-    nearest = torch.from_numpy(_nearest_alleles(db, max(K - 1, 1))).to(dev)
+    nearest = torch.from_numpy(_cached_nearest(db, max(K - 1, 1), device)).to(dev)
 
     # --- per read: locus (organism by props, locus by length), type, start
     w = np.zeros(n_loci, dtype=np.float64)
@@ -293,7 +305,11 @@ def make_sample(db: SynthDB, n_reads: int, read_len: int = 100, seed: int = 1001
         ll = locus_len[li0:li0 + nl].astype(np.float64)
         w[li0:li0 + nl] = props[oi] * ll / ll.sum()
         li0 += nl
-    wt = torch.from_numpy(w).to(dev)
+    if locus_subset is not None:  # multi-GPU shards own disjoint locus sets (contig-aligned shards)
+        keep = np.zeros(n_loci, dtype=bool)
+        keep[np.asarray(list(locus_subset), dtype=np.int64)] = True
+        w = np.where(keep, w, 0.0)
+    wt = torch.from_numpy(w / w.sum()).to(dev)
     locus = torch.multinomial(wt, n_reads, replacement=True, generator=g)
     u = torch.rand(n_reads, generator=g, device=dev)
     # type 0 simple LM, 1 clipped 5S(L-10)M5S, 2 insertion aM1IbM, 3 deletion aM1DbM
@@ -363,6 +379,22 @@ def make_sample(db: SynthDB, n_reads: int, read_len: int = 100, seed: int = 1001
         XS = torch.where(AS == top2[:, :1], top2[:, 1:2].expand(-1, K), top2[:, :1].expand(-1, K))
     else:
         XS = AS.clone()
+
+    return dict(L=L, K=K, n_reads=n_reads, bases=bases, qual=qual, start=start, rtype=rtype, a_split=a_split,
+                rows=rows, AS=AS, XS=XS, xm=xm, flag=flag, gap=gap, truth=truth, strain_row=strain_row,
+                strain_seqs=strain_seqs, lens_all=lens_all)
+
+
+def make_sample(db: SynthDB, n_reads: int, read_len: int = 100, seed: int = 1001, K: int = 4, device: str = "cpu",
+                **kw) -> AlnTable:
+    """AlnTable (host, BAM-equivalent, name-grouped = bowtie2 order) of gen_core's reads; aux order
+    AS,XS,XN,XM,XO,XG,NM,YT."""
+    core = gen_core(db, n_reads, read_len, seed, K, device=device, **kw)
+    L, K = core["L"], core["K"]
+    dev = core["bases"].device
+    bases, qual, start, rtype, a_split = core["bases"], core["qual"], core["start"], core["rtype"], core["a_split"]
+    rows, AS, XS, xm, flag, gap, truth = core["rows"], core["AS"], core["XS"], core["xm"], core["flag"], core["gap"], core["truth"]
+    strain_row, strain_seqs, lens_all = core["strain_row"], core["strain_seqs"], core["lens_all"]
 
     def rep(x):  # [n_reads] -> [n_reads*K]
         return x[:, None].expand(-1, K).reshape(-1)

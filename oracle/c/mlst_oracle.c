@@ -23,7 +23,7 @@ void orc_score(uint64_t n, const int32_t* tid, const int32_t* aux0, const int32_
             sum_as[t] += aux0[i];
             n_hit[t] += 1;
             const uint32_t oi = orig_idx ? orig_idx[i] : (uint32_t)i;
-            if (oi < first_idx[locus_of[t]]) first_idx[locus_of[t]] = oi;
+            if (oi < first_idx[t]) first_idx[t] = oi;
         } else {
             counters[1] += 1;                                      /* :129 */
         }

@@ -40,7 +40,7 @@ def score(tab, allow, locus_of, n_loci, minscore=80, max_xm=5, min_read_len=50, 
     qlen = np.full(tab.n, max(tab.read_len, 1), dtype=np.int32)
     sum_as = np.zeros(n_ref, np.int64)
     n_hit = np.zeros(n_ref, np.uint32)
-    first = np.full(n_loci, 0xFFFFFFFF, np.uint32)
+    first = np.full(n_ref, 0xFFFFFFFF, np.uint32)
     counters = np.zeros(2, np.uint64)
     tid = np.ascontiguousarray(tab.tid, dtype=np.int32)
     oi = None if orig_idx is None else np.ascontiguousarray(orig_idx, dtype=np.uint32)

@@ -44,3 +44,35 @@ def planes_to_counts(soa, tid, contig_len, minscore, max_xm):
                 if 0 <= col < contig_len:
                     counts[col, (2 * h + l) if (vb and ok) else 4] += 1
     return counts
+
+
+def records_to_table(h, recs):
+    """oracle.bamio records -> AlnTable (test side: lets GPU tests consume the committed golden BAMs)."""
+    from metamlst_b200.synth import AlnTable
+    n = len(recs)
+    L = max((len(r.seq) for r in recs), default=1)
+    seq = np.full((n, L), ord("N"), np.uint8)
+    qual = np.zeros((n, L), np.uint8)
+    cig_off = np.zeros(n + 1, np.int64)
+    ops = []
+    def tag(r, t, default=0):
+        for k, _ty, v in r.aux:
+            if k == t:
+                return int(v)
+        return default
+    AS = np.zeros(n, np.int32); XS = np.zeros(n, np.int32); has_xs = np.zeros(n, bool)
+    XN = np.zeros(n, np.int32); XM = np.zeros(n, np.int32); XO = np.zeros(n, np.int32); XG = np.zeros(n, np.int32); NM = np.zeros(n, np.int32)
+    for i, r in enumerate(recs):
+        assert len(r.seq) == L, "helper handles fixed-length reads"
+        seq[i] = np.frombuffer(r.seq.encode(), np.uint8)
+        qual[i] = np.frombuffer(bytes(r.qual), np.uint8)
+        ops.extend((l << 4) | op for op, l in r.cigar)
+        cig_off[i + 1] = len(ops)
+        AS[i] = tag(r, "AS"); XM[i] = tag(r, "XM"); XO[i] = tag(r, "XO"); XG[i] = tag(r, "XG"); NM[i] = tag(r, "NM"); XN[i] = tag(r, "XN")
+        has_xs[i] = any(k == "XS" for k, _t, _v in r.aux)
+        XS[i] = tag(r, "XS")
+        assert [k for k, _t, _v in r.aux][0] == "AS"
+    return AlnTable(list(h.ref_names), np.asarray(h.ref_lens, np.int32), np.array([r.tid for r in recs], np.int32),
+                    np.array([r.pos for r in recs], np.int32), np.array([r.flag for r in recs], np.uint16),
+                    np.array([int(r.qname[1:]) for r in recs], np.int64), cig_off, np.asarray(ops, np.uint32), L, seq, qual,
+                    AS, XS, has_xs, XN, XM, XO, XG, NM)

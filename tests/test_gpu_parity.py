@@ -1,0 +1,216 @@
+"""Parity of the CUDA path (through the C-ABI) against the oracles.  Needs a B200: `pytest -m gpu`."""
+import json
+import os
+import sqlite3
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from helpers import lut_from_db, records_to_table, small_case, table_to_records
+from metamlst_b200 import api, native, packing
+from oracle import bamio, corc, mlst_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = native.Context(0)
+    yield c
+    c.close()
+
+
+# ------------------------------------------------------------------------------------------------ stage 1
+@pytest.mark.parametrize("order", ["name", "coord"])
+@pytest.mark.parametrize("n_reads,species_filter", [(37, None), (3000, None), (3000, "saureus"), (60000, "ecoli,saureus")])
+def test_score_bit_exact(ctx, order, n_reads, species_filter):
+    db, tab = small_case(seed=31, n_reads=n_reads, orgs=("ecoli", "saureus"), apl=8, sub_err=0.02)
+    if order == "coord":
+        tab = tab.sorted_by_coord()
+    tab.has_xs = (np.arange(tab.n) % 7) != 0  # H4
+    soa = packing.pack_table(tab)
+    index = api.AlleleIndex(tab.ref_names)
+    cel, total, ignored, (s, c, f) = api.score_soa(ctx, soa, index, 176, 3, 50, species_filter, 100)
+    allow, locus_of, n_loci = lut_from_db(db, species_filter)
+    ws, wc, wf, wcnt = corc.score(tab, allow, locus_of, n_loci, 176, 3, 50)
+    assert np.array_equal(s, ws) and np.array_equal(c, wc) and np.array_equal(f, wf)
+    assert (total, ignored) == (int(wcnt[0]), int(wcnt[1]))
+    if n_reads <= 3000:  # the whole dict, including insertion order (H5) and rounded floats (H6)
+        h, recs = table_to_records(tab)
+        want, _bank, wt, wi = orc.stage1(h, recs, 176, 3, 50, species_filter, 100)
+        assert json.dumps(cel) == json.dumps(want)
+        assert "".join(orc.out_log_rows(cel)) == "".join(orc.out_log_rows(want))
+
+
+def test_score_empty_and_thresholds(ctx):
+    db, tab = small_case(seed=32, n_reads=300)
+    soa = packing.pack_table(tab)
+    index = api.AlleleIndex(tab.ref_names)
+    cel, total, ignored, _ = api.score_soa(ctx, soa, index, 10000, 5, 50)
+    assert cel == {} and total == tab.n and ignored == tab.n
+    cel, total, ignored, _ = api.score_soa(ctx, soa, index, 80, 5, 101)  # min_read_len above the read length
+    assert cel == {} and ignored == tab.n
+    cel, total, ignored, _ = api.score_soa(ctx, soa, index, 80, 5, 50, "nosuch")
+    assert cel == {} and total == 0
+
+
+# ------------------------------------------------------------------------------------------------ stage 2
+CASES = [
+    dict(seed=41, n_reads=400, L=100, K=4, maxd=8000),
+    dict(seed=42, n_reads=5000, L=150, K=4, maxd=8000),
+    dict(seed=43, n_reads=5000, L=70, K=2, maxd=8000, frac_clip=0.3, frac_indel=0.3, n_frac=0.05, sub_err=0.03),
+    dict(seed=44, n_reads=40000, L=100, K=1, maxd=300),   # cap active
+    dict(seed=45, n_reads=40000, L=150, K=2, maxd=None),  # uncapped, deep
+    dict(seed=46, n_reads=3, L=100, K=1, maxd=8000),
+    dict(seed=47, n_reads=20000, L=50, K=1, maxd=8000, schemes={"ecoli": [("adk", 80), ("fumC", 70)]}),  # H1 at the real cap
+    dict(seed=48, n_reads=2000, L=100, K=4, maxd=8000, orgs=("ecoli", "saureus", "kpneumoniae")),
+]
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("case", CASES, ids=[str(c["seed"]) for c in CASES])
+def test_pileup_counts_and_consensus_bit_exact(ctx, case, impl):
+    kw = dict(case)
+    maxd = kw.pop("maxd")
+    db, tab = small_case(apl=4, **kw)
+    soa = packing.pack_table(tab, 20, maxd)
+    st = tab.sorted_by_coord()
+    minscore, max_xm = 2 * tab.read_len - 24, 3
+    tids = sorted(set(int(t) for t in tab.tid))
+    dbs = [db.row_seq(t) for t in tids]
+    seqs, holes, snps, counts, col_off = api.pileup_consensus(ctx, soa, tids, dbs, minscore, max_xm, 1, impl, want_counts=True)
+    for i, t in enumerate(tids):
+        want, _ = corc.contig_counts(st, t, 20, minscore, max_xm, maxd)
+        got = counts[col_off[i]:col_off[i + 1]]
+        assert np.array_equal(got, want), (t, np.argwhere(got != want)[:5])
+        wseq, wh, ws = corc.consensus(want, dbs[i].encode(), 1)
+        assert (seqs[i], int(holes[i]), int(snps[i])) == (wseq, wh, ws)
+
+
+def test_pileup_linearity_shards_sum_to_whole(ctx):
+    """counts(A) + counts(B) == counts(A u B): what the multi-GPU allreduce relies on."""
+    db, tab = small_case(seed=51, n_reads=20000, L=100, K=1, apl=3)
+    st = tab.sorted_by_coord()
+    half = st.n // 2
+    tids = sorted(set(int(t) for t in tab.tid))
+    dbs = [db.row_seq(t) for t in tids]
+    tot = None
+    for part in (st.take(np.arange(half)), st.take(np.arange(half, st.n))):
+        soa = packing.pack_table(part, 20, None)
+        _, _, _, counts, _ = api.pileup_consensus(ctx, soa, tids, dbs, 170, 3, 1, 2, want_counts=True)
+        tot = counts.astype(np.int64) if tot is None else tot + counts
+    soa = packing.pack_table(st, 20, None)
+    _, _, _, whole, _ = api.pileup_consensus(ctx, soa, tids, dbs, 170, 3, 1, 2, want_counts=True)
+    assert np.array_equal(tot, whole.astype(np.int64))
+    assert int(whole.sum()) == int(((st.qual >= 20) & (st.seq != 0)).sum()) - _unaligned_qok(st)
+
+
+def _unaligned_qok(st):
+    """quality-passing bases that are soft-clipped or inserted (not in any column)."""
+    n = 0
+    for i in range(st.n):
+        q = 0
+        for c in st.cig_ops[st.cig_off[i]:st.cig_off[i + 1]]:
+            op, ln = int(c) & 15, int(c) >> 4
+            if op in (1, 4):
+                n += int((st.qual[i, q:q + ln] >= 20).sum())
+            if op in (0, 1, 4, 7, 8):
+                q += ln
+    return n
+
+
+def test_build_consensus_seam_on_golden_bams(ctx):
+    """Seam S2 against the reference's own .nfo (committed golden, produced by the unmodified scripts over shims)."""
+    man = json.load(open(os.path.join(GOLDEN, "manifest.json")))
+    for name in ("basic", "two_org", "no_xs", "lowcov", "deep", "strict"):
+        d = os.path.join(GOLDEN, name)
+        h, recs = bamio.read_bam(os.path.join(d, "sample.bam"))
+        tab = records_to_table(h, recs)
+        args = man[name]["args"]
+        minscore = int(args[args.index("--minscore") + 1]) if "--minscore" in args else 80
+        max_xm = int(args[args.index("--max_xM") + 1]) if "--max_xM" in args else 5
+        min_acc = float(args[args.index("--min_accuracy") + 1]) if "--min_accuracy" in args else 0.9
+        soa = packing.pack_table(tab)
+        index = api.AlleleIndex(tab.ref_names)
+        cel, total, ignored, _ = api.score_soa(ctx, soa, index, minscore, max_xm, 50, None, 100)
+        odb = orc.OracleDB(os.path.join(d, "db.sqlite"))
+        lines = []
+        for sp, species in cel.items():
+            chosen = dict((sp + "_" + g + "_" + a, odb.unal_sequence(sp, g, a)) for g, a in api.select_alleles(species))
+            cons = api.build_consensus(ctx, soa, chosen, minscore, max_xm)
+            line, _rows = orc.nfo_line(sp, "sample", cons, min_acc, "-a" in args, odb.sequence_find)
+            if line:
+                lines.append(line)
+        gold = open(os.path.join(d, "sample.nfo"), newline="").read() if os.path.exists(os.path.join(d, "sample.nfo")) else ""
+        assert "".join(lines) == gold, name
+        out = open(os.path.join(d, "sample.out"), newline="").read()
+        assert "".join(orc.out_log_rows(cel)) == out.split("RESULTS ------------------------------\r\n")[1], name
+
+
+def test_consensus_len_mismatch_raises_like_reference(ctx):
+    db, tab = small_case(seed=52, n_reads=200)
+    soa = packing.pack_table(tab)
+    t = int(tab.tid[0])
+    with pytest.raises(IndexError):
+        api.build_consensus(ctx, soa, {tab.ref_names[t]: db.row_seq(t)[:-3]}, 80, 5)
+    with pytest.raises(AttributeError):
+        api.build_consensus(ctx, soa, {"ecoli_nosuch_1": "ACGT"}, 80, 5)
+
+
+# ------------------------------------------------------------------------------------------------ stage 3
+def _rand_rows(rng, n, lo, hi):
+    return ["".join(rng.choice(list("ACGT"), size=int(l))) for l in rng.integers(lo, hi + 1, size=n)]
+
+
+@pytest.mark.parametrize("n_rows,lo,hi", [(1, 30, 30), (33, 400, 540), (700, 470, 520), (3000, 60, 250), (1000, 600, 1000)])
+def test_hamming_min_bit_exact(ctx, n_rows, lo, hi):
+    rng = np.random.default_rng(n_rows)
+    base = _rand_rows(rng, 1, hi, hi)[0]
+    rows = []
+    for l in rng.integers(lo, hi + 1, size=n_rows):  # near-identical alleles: realistic small distances + ties
+        s = list(base[:int(l)])
+        for p in rng.integers(0, len(s), size=int(rng.integers(0, 8))):
+            s[int(p)] = "ACGT"[int(rng.integers(0, 4))]
+        rows.append("".join(s))
+    rows[min(5, n_rows - 1)] = rows[0]  # exact duplicate -> tie must resolve to the lowest row
+    loci = [("org", "g%d" % (i * 3 // max(n_rows, 1))) for i in range(n_rows)]
+    idx = api.HammingIndex(ctx, [(o, g, i + 1, s) for i, ((o, g), s) in enumerate(zip(loci, rows))])
+    qs, ranges = [], []
+    for k in range(40):
+        r = int(rng.integers(0, n_rows))
+        s = list(rows[r])
+        for p in rng.integers(0, len(s), size=int(rng.integers(0, 6))):
+            s[int(p)] = "ACGT"[int(rng.integers(0, 4))]
+        if k % 5 == 0:
+            s = s[:max(1, len(s) - int(rng.integers(0, 40)))]  # shorter query: zip truncation (H9)
+        if k % 7 == 0:
+            s = s + list("ACGT" * 5)  # longer than its rows
+        qs.append("".join(s)[:idx.W * 32])
+        ranges.append(idx.block[("org", loci[r][1])] if k % 2 else (0, n_rows))
+    flat = np.frombuffer("".join(r[3] for r in idx.rows).encode(), np.uint8)
+    off = np.zeros(n_rows + 1, np.int64)
+    off[1:] = np.cumsum([len(r[3]) for r in idx.rows])
+    wd, wa = corc.hamming_min([q.encode() for q in qs], flat, off, ranges)
+    d, a = idx.search(qs, ranges)
+    assert np.array_equal(d, wd) and np.array_equal(a, wa)
+
+
+def test_closest_allele_seam_matches_oracle_on_golden_cohort(ctx):
+    d = os.path.join(GOLDEN, "cohort")
+    odb = orc.OracleDB(os.path.join(d, "db.sqlite"))
+    idx = api.HammingIndex.from_sqlite(ctx, sqlite3.connect(os.path.join(d, "db.sqlite")))
+    cel = orc.parse_nfo_folder(os.path.join(d, "nfo"))
+    n = 0
+    for line, _sample in cel["ecoli"]:
+        for label, (seq, _acc, _snp) in line.items():
+            if not seq:
+                continue
+            _o, g, _a = label.split("_")
+            assert idx.closest_allele("ecoli", g, seq) == orc.closest_allele(odb, "ecoli", g, seq)
+            n += 1
+    assert n >= 4
+    # the merge classification driven by the GPU search reproduces the reference's ST table byte for byte
+    st = orc.merge_bacterium(odb, "ecoli", cel["ecoli"], 5, closest=idx.closest_allele)
+    assert orc.st_table_text(st) == open(os.path.join(d, "nfo", "merged", "ecoli_ST.txt"), newline="").read()
+    assert api.define_profile(odb.conn, ["ecoli_adk_1", "ecoli_nosuch_1"]) == [(0, 0)]

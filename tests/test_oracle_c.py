@@ -29,8 +29,11 @@ def test_score_matches_python_oracle(order):
                 seen += 1
     assert seen == int((c > 0).sum())
     # H5: gene order inside a species == ascending first passing record index
-    order_idx = [int(first[[i for i, (o, gg) in enumerate(db.locus_names) if gg == g][0]]) for g in cel["ecoli"]]
+    order_idx = [min(int(first[names.index("ecoli_%s_%s" % (g, a))]) for a in cel["ecoli"][g]) for g in cel["ecoli"]]
     assert order_idx == sorted(order_idx)
+    for g, alleles in cel["ecoli"].items():  # allele insertion order too
+        ai = [int(first[names.index("ecoli_%s_%s" % (g, a))]) for a in alleles]
+        assert ai == sorted(ai)
 
 
 @pytest.mark.parametrize("maxcnt", [1, 3, 17, 60, 8000])
