@@ -59,35 +59,52 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons sampled through NVML (nvidia_ml_py) every 10 ms while the GPU is under load:
+    started before the warm-up, stopped after the timed region (B200_PROFILING.md recipe, same counters)."""
 
     def __init__(self, gpu_index):
-        self.rows = []
-        self.p = None
         self.gpu = gpu_index
+        self.sm, self.reasons, self.max_sm = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.p = None
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            return
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:  # noqa: BLE001
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:  # noqa: BLE001
+                    pass
+                time.sleep(0.01)
+        self._t = threading.Thread(target=loop, daemon=True)
+        self._t.start()
 
     def stop(self):
-        if self.p:
-            self.p.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=1)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "how": "NVML every 10 ms from warm-up start to end of the timed region"}
 
 
 def make_db(args):
@@ -222,12 +239,12 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     result = None
     for _ in range(max(args.warmup, 3)):
         result = pipe.step()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     pipe.timers = {}
     pipe.launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

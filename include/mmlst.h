@@ -98,6 +98,9 @@ typedef struct {
     uint32_t reserved[3];
 } mmlst_chunk;
 
+/* records per chunk that fills the chip for a launch over n_rec records (multiple of 512, <= 63*512) */
+uint32_t mmlst_chunk_records(uint64_t n_rec);
+
 int mmlst_pileup_dev(const int32_t* pos, const uint32_t* row_off, const uint16_t* reflen,
                      const int16_t* as_named, const uint8_t* xm_named, const uint32_t* planes,
                      const mmlst_chunk* chunks, uint32_t n_chunks, uint32_t max_row_words,

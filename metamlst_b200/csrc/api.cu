@@ -169,7 +169,17 @@ extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* al
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-static const uint32_t kChunkRecords = 63 * 512;  // bit-sliced counters hold < 2^10 records per lane (pileup_bitsliced.cu)
+static const uint32_t kMaxChunkRecords = 63 * 512;  // bit-sliced counters hold < 2^10 records per lane (pileup_bitsliced.cu)
+
+// Chunk length (records) for a launch over n_rec records: enough chunks to fill the chip (4 per SM), whole 512-record tiles.
+extern "C" uint32_t mmlst_chunk_records(uint64_t n_rec) {
+    const uint64_t target = (uint64_t)mmlst_num_sms() * 4;
+    uint64_t c = (n_rec + target - 1) / target;
+    c = ((c + 511) / 512) * 512;
+    if (c < 512) c = 512;
+    if (c > kMaxChunkRecords) c = kMaxChunkRecords;
+    return (uint32_t)c;
+}
 
 extern "C" int mmlst_pileup_dev(const int32_t* pos, const uint32_t* row_off, const uint16_t* reflen, const int16_t* as_named,
                                 const uint8_t* xm_named, const uint32_t* planes, const mmlst_chunk* chunks, uint32_t n_chunks,
@@ -206,6 +216,7 @@ extern "C" int mmlst_pileup_consensus(mmlst_ctx* c, const mmlst_soa* soa, const 
     TRY(c->p_pos.reserve(n_rec * 4 + 16)); TRY(c->p_off.reserve(n_rec * 4 + 16)); TRY(c->p_reflen.reserve(n_rec * 2 + 16));
     TRY(c->p_as.reserve(n_rec * 2 + 16)); TRY(c->p_xm.reserve(n_rec + 16)); TRY(c->planes.reserve(n_words * 4 + 64));
     std::vector<mmlst_chunk> chunks;
+    const uint32_t kChunkRecords = mmlst_chunk_records(n_rec);
     size_t rbase = 0, wbase = 0;
     for (uint32_t l = 0; l < n_loci; ++l) {
         const uint32_t t = chosen_tid[l];

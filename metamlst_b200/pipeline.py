@@ -14,12 +14,11 @@ import torch
 
 from . import api, native
 
-CHUNK_RECORDS = 63 * 512  # must match kChunkRecords in csrc/api.cu (bit-sliced counters: < 1024 records per lane)
-
-
 def build_chunks(contig_start: np.ndarray, chosen_tid: Sequence[int], col_off: np.ndarray) -> np.ndarray:
     """mmlst_chunk descriptors (8 x u32 each) for the chosen contigs of a device-resident pileup stream."""
     out = []
+    total = sum(int(contig_start[t + 1]) - int(contig_start[t]) for t in chosen_tid)
+    CHUNK_RECORDS = int(native.lib().mmlst_chunk_records(total))  # whole tiles, <= 63 tiles, >= 4 chunks per SM
     for l, t in enumerate(chosen_tid):
         r0, r1 = int(contig_start[t]), int(contig_start[t + 1])
         for b in range(r0, r1, CHUNK_RECORDS):
