@@ -128,6 +128,30 @@ int mmlst_consensus_dev(const uint32_t* counts, const uint8_t* dbseq, const uint
                         uint32_t mincov, uint8_t* cons, uint32_t* holes, uint32_t* snps, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Best-allele selection on the device: no host round trip between stage 1 and stage 2.  Replaces metamlst.py:133-151
+ * (maxLen, penalty, round(avg,1) -- computed exactly as integer tenths from the IEEE double quotient, H6), :184-206
+ * (--nloci gate), :213-220 + :244 (alleles whose rounded average equals the locus maximum, lowest int(allele)), and the
+ * dict-order bookkeeping of H5 (species by first passing record, loci inside a species by first passing record).
+ *   allele_num[tid] = int(alleleVariant); species_of_locus[locus]; genes_in_db[species] = rows of `genes` (metamlst.py:184)
+ *   contig_start / ref_len / db_off: pileup-stream record range, BAM LN and DB-sequence offset of every allele row
+ *   scratch: >= 24*n_loci + 8 bytes.  Outputs: header[0]=n_chosen [1]=n_chunks [2]=total columns [3]=error bits
+ *   (1: "Database is broken", 2: chunk list overflow) [4]=records per chunk; chosen_tid / chosen_species / col_off /
+ *   db_start per chosen locus in output order; chunks for mmlst_pileup_indirect_dev.
+ * --------------------------------------------------------------------------------------------------------------- */
+int mmlst_select_dev(const int64_t* sum_as, const uint32_t* n_hit, const uint32_t* first_idx, const uint32_t* locus_of,
+                     const uint32_t* allele_num, uint32_t n_ref, const uint32_t* species_of_locus, const uint32_t* genes_in_db,
+                     uint32_t n_loci, uint32_t n_species, int penalty, int nloci_pct, const uint64_t* contig_start,
+                     const uint32_t* ref_len, const uint64_t* db_off, uint32_t chunk_records, void* scratch, size_t scratch_bytes,
+                     uint32_t* header, uint32_t* chosen_tid, uint32_t* chosen_species, uint32_t* col_off, uint64_t* db_start,
+                     mmlst_chunk* chunks, uint32_t max_chunks, void* stream);
+int mmlst_pileup_indirect_dev(const int32_t* pos, const uint32_t* row_off, const uint16_t* reflen, const int16_t* as_named,
+                              const uint8_t* xm_named, const uint32_t* planes, const mmlst_chunk* chunks, const uint32_t* header,
+                              uint32_t max_row_words, int minscore, int max_xm, uint32_t* counts, int impl, void* stream);
+int mmlst_consensus_indirect_dev(const uint32_t* counts, const uint8_t* db_ascii, const uint64_t* db_start, const uint32_t* col_off,
+                                 uint32_t max_loci, const uint32_t* header, uint32_t mincov, uint8_t* cons, uint32_t* holes,
+                                 uint32_t* snps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Stage 3 -- closest known allele by zip-truncated Hamming distance.  Replaces metaMLST_functions.py:230-234
  * (stringDiff) driven by metamlst-merge.py:174-181 over sequencesGetAll (:224-228).
  *   DB rows   : bit-planes hi/lo of the 2-bit code, tiles of 32 rows, word-major inside a tile:

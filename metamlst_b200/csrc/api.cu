@@ -187,11 +187,25 @@ extern "C" int mmlst_pileup_dev(const int32_t* pos, const uint32_t* row_off, con
                                 int impl, void* stream) {
     if (n_chunks == 0) return MMLST_OK;
     if (!pos || !row_off || !reflen || !as_named || !xm_named || !planes || !chunks || !counts) { mmlst_set_error("mmlst_pileup_dev: null pointer"); return MMLST_E_ARG; }
-    PileupArgs a{pos, row_off, reflen, as_named, xm_named, planes, chunks, n_chunks, max_row_words, minscore, max_xm, counts, total_cols};
+    PileupArgs a{pos, row_off, reflen, as_named, xm_named, planes, chunks, n_chunks, max_row_words, minscore, max_xm, counts, total_cols, nullptr};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (impl == 1) return launch_pileup_atomic(a, s);
     if (impl == 0 || impl == 2) return launch_pileup_bitsliced(a, s);
     mmlst_set_error("mmlst_pileup_dev: impl %d unknown", impl);
+    return MMLST_E_ARG;
+}
+
+// chunk list and count produced on the device by mmlst_select_dev (header[1] = n_chunks)
+extern "C" int mmlst_pileup_indirect_dev(const int32_t* pos, const uint32_t* row_off, const uint16_t* reflen, const int16_t* as_named,
+                                         const uint8_t* xm_named, const uint32_t* planes, const mmlst_chunk* chunks,
+                                         const uint32_t* header, uint32_t max_row_words, int minscore, int max_xm, uint32_t* counts,
+                                         int impl, void* stream) {
+    if (!pos || !row_off || !reflen || !as_named || !xm_named || !planes || !chunks || !header || !counts) { mmlst_set_error("mmlst_pileup_indirect_dev: null pointer"); return MMLST_E_ARG; }
+    PileupArgs a{pos, row_off, reflen, as_named, xm_named, planes, chunks, 0, max_row_words, minscore, max_xm, counts, 0, header + 1};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (impl == 1) return launch_pileup_atomic(a, s);
+    if (impl == 0 || impl == 2) return launch_pileup_bitsliced(a, s);
+    mmlst_set_error("mmlst_pileup_indirect_dev: impl %d unknown", impl);
     return MMLST_E_ARG;
 }
 

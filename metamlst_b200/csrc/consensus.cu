@@ -5,11 +5,15 @@
 namespace {
 
 __global__ void __launch_bounds__(128) consensus_kernel(const uint32_t* __restrict__ counts, const uint8_t* __restrict__ dbseq,
-                                                        const uint32_t* __restrict__ col_off, uint32_t mincov,
-                                                        uint8_t* __restrict__ cons, uint32_t* __restrict__ holes,
-                                                        uint32_t* __restrict__ snps) {
+                                                        const unsigned long long* __restrict__ db_start,
+                                                        const uint32_t* __restrict__ col_off, const uint32_t* __restrict__ n_loci_dev,
+                                                        uint32_t mincov, uint8_t* __restrict__ cons,
+                                                        uint32_t* __restrict__ holes, uint32_t* __restrict__ snps) {
     const uint32_t locus = blockIdx.x;
+    if (n_loci_dev && locus >= *n_loci_dev) return;
     const uint32_t c0 = col_off[locus], c1 = col_off[locus + 1];
+    // DB sequence of the chosen allele: either pre-concatenated (column-aligned) or addressed through db_start[locus]
+    const uint8_t* db_base = db_start ? dbseq + db_start[locus] - c0 : dbseq;
     uint32_t h = 0, s = 0;
     for (uint32_t col = c0 + threadIdx.x; col < c1; col += blockDim.x) {
         const uint32_t* c = counts + static_cast<size_t>(col) * 5;
@@ -23,7 +27,7 @@ __global__ void __launch_bounds__(128) consensus_kernel(const uint32_t* __restri
             if (N > best) { best = N; call = 'N'; }
             if (T > best) { best = T; call = 'T'; }
         }
-        const uint8_t db = dbseq[col];
+        const uint8_t db = db_base[col];
         uint8_t out;
         if (call == 'N') { out = (db >= 'A' && db <= 'Z') ? db + 32 : db; ++h; }
         else { out = call; if (call != db) ++s; }
@@ -45,7 +49,19 @@ extern "C" int mmlst_consensus_dev(const uint32_t* counts, const uint8_t* dbseq,
                                    uint32_t mincov, uint8_t* cons, uint32_t* holes, uint32_t* snps, void* stream) {
     if (n_loci == 0) return MMLST_OK;
     if (!counts || !dbseq || !col_off || !cons || !holes || !snps) { mmlst_set_error("mmlst_consensus_dev: null pointer"); return MMLST_E_ARG; }
-    consensus_kernel<<<n_loci, 128, 0, static_cast<cudaStream_t>(stream)>>>(counts, dbseq, col_off, mincov, cons, holes, snps);
+    consensus_kernel<<<n_loci, 128, 0, static_cast<cudaStream_t>(stream)>>>(counts, dbseq, nullptr, col_off, nullptr, mincov, cons, holes, snps);
+    CUDA_TRY(cudaGetLastError());
+    return MMLST_OK;
+}
+
+// device-driven variant: n_loci and the DB offsets come from mmlst_select_dev (header[0], db_start)
+extern "C" int mmlst_consensus_indirect_dev(const uint32_t* counts, const uint8_t* db_ascii, const uint64_t* db_start,
+                                            const uint32_t* col_off, uint32_t max_loci, const uint32_t* header, uint32_t mincov,
+                                            uint8_t* cons, uint32_t* holes, uint32_t* snps, void* stream) {
+    if (max_loci == 0) return MMLST_OK;
+    if (!counts || !db_ascii || !db_start || !col_off || !header || !cons || !holes || !snps) { mmlst_set_error("mmlst_consensus_indirect_dev: null pointer"); return MMLST_E_ARG; }
+    consensus_kernel<<<max_loci, 128, 0, static_cast<cudaStream_t>(stream)>>>(counts, db_ascii, reinterpret_cast<const unsigned long long*>(db_start),
+                                                                            col_off, header, mincov, cons, holes, snps);
     CUDA_TRY(cudaGetLastError());
     return MMLST_OK;
 }

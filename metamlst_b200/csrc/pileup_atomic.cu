@@ -7,10 +7,12 @@
 namespace {
 
 __global__ void __launch_bounds__(256) pileup_atomic_kernel(const PileupArgs a) {
-    const mmlst_chunk ck = a.chunks[blockIdx.x];
+    const uint32_t n_chunks = pileup_n_chunks(a);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t wib = threadIdx.x >> 5;
     const uint32_t wpb = blockDim.x >> 5;
+    for (uint32_t ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
+    const mmlst_chunk ck = a.chunks[ci];
     for (uint32_t rec = ck.rec_begin + wib; rec < ck.rec_end; rec += wpb) {
         const int p = a.pos[rec];
         const uint32_t off = a.row_off[rec] + ck.plane_delta;
@@ -29,11 +31,13 @@ __global__ void __launch_bounds__(256) pileup_atomic_kernel(const PileupArgs a) 
             atomicAdd(a.counts + (static_cast<size_t>(ck.col_base) + col) * 5 + bin, 1u);
         }
     }
+    }
 }
 
 }  // namespace
 
 int launch_pileup_atomic(const PileupArgs& a, cudaStream_t stream) {
-    pileup_atomic_kernel<<<a.n_chunks, 256, 0, stream>>>(a);
+    const uint32_t grid = a.n_chunks_dev ? uint32_t(mmlst_num_sms() * 8) : min(a.n_chunks, uint32_t(mmlst_num_sms() * 8));
+    pileup_atomic_kernel<<<grid, 256, 0, stream>>>(a);
     return mmlst_cuda_fail(cudaGetLastError(), "pileup_atomic_kernel");
 }

@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
     __syncthreads();
     uint32_t phase_bits = 0;  // parity per stage
 
-    for (uint32_t ci = blockIdx.x; ci < a.n_chunks; ci += gridDim.x) {
+    const uint32_t n_chunks = pileup_n_chunks(a);
+    for (uint32_t ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
         const mmlst_chunk ck = a.chunks[ci];
         const uint32_t nrec = ck.rec_end - ck.rec_begin;
         const uint32_t ntiles = (nrec + TR - 1) / TR;
@@ -323,12 +324,12 @@ int launch_pileup_bitsliced(const PileupArgs& a, cudaStream_t stream) {
     if (s3 <= 110 * 1024) {
         static bool set3 = false;
         if (!set3) { cudaFuncSetAttribute(pileup_bitsliced_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); set3 = true; }
-        const uint32_t grid = min(a.n_chunks, uint32_t(sms * 2));
+        const uint32_t grid = a.n_chunks_dev ? uint32_t(sms * 2) : min(a.n_chunks, uint32_t(sms * 2));
         pileup_bitsliced_kernel<3><<<grid, NTHREADS, s3, stream>>>(a, stage_words);
     } else {
         static bool set2 = false;
         if (!set2) { cudaFuncSetAttribute(pileup_bitsliced_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); set2 = true; }
-        const uint32_t grid = min(a.n_chunks, uint32_t(sms));
+        const uint32_t grid = a.n_chunks_dev ? uint32_t(sms) : min(a.n_chunks, uint32_t(sms));
         pileup_bitsliced_kernel<2><<<grid, NTHREADS, s2, stream>>>(a, stage_words);
     }
     return mmlst_cuda_fail(cudaGetLastError(), "pileup_bitsliced_kernel");

@@ -29,7 +29,8 @@ def build_chunks(contig_start: np.ndarray, chosen_tid: Sequence[int], col_off: n
 class DevicePipeline:
     def __init__(self, streams, index: api.AlleleIndex, dbseq_of: Callable[[int], str], minscore: int = 80, max_xM: int = 5,
                  min_read_len: int = 50, penalty: int = 100, species_filter: Optional[str] = None, mincov: int = 1,
-                 impl: int = 0, idx_base: int = 0, group=None):
+                 impl: int = 0, idx_base: int = 0, group=None, nloci: int = 100, genes_in_db: Optional[Dict[str, int]] = None,
+                 db_ascii: Optional[np.ndarray] = None, db_off: Optional[np.ndarray] = None):
         self.s = streams
         self.index = index
         self.dbseq_of = dbseq_of
@@ -55,6 +56,45 @@ class DevicePipeline:
         self.snps = torch.zeros(index.n_loci + 1, dtype=torch.int32, device=dev)
         self._db_cache: Dict[Tuple[int, ...], tuple] = {}
         self.lib = native.lib()
+        # ---- device-side selection (mmlst_select_dev): look-up tables + output block
+        self.nloci = int(nloci)
+        species_names: List[str] = []
+        sp_id: Dict[str, int] = {}
+        sol = np.zeros(index.n_loci, dtype=np.int32)
+        for l, (sp, _g) in enumerate(index.locus_names):
+            if sp not in sp_id:
+                sp_id[sp] = len(species_names)
+                species_names.append(sp)
+            sol[l] = sp_id[sp]
+        self.species_names = species_names
+        gdb = np.zeros(len(species_names), dtype=np.int32)
+        for sp, i in sp_id.items():
+            gdb[i] = (genes_in_db or {}).get(sp, int((sol == i).sum()))  # rows of `genes` for the organism (metamlst.py:184)
+        if db_ascii is None:
+            seqs = [dbseq_of(t).encode("latin-1") for t in range(n_ref)]
+            db_off = np.zeros(n_ref + 1, dtype=np.int64)
+            db_off[1:] = np.cumsum([len(x) for x in seqs])
+            db_ascii = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+        self.bad_len = np.asarray(streams.ref_lens, dtype=np.int64) > (db_off[1:] - db_off[:-1])  # H10
+        t32 = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self.allele_num = t32(np.asarray([int(a) for a in index.allele], dtype=np.int64).astype(np.uint32).view(np.int32))
+        self.species_of_locus = t32(sol)
+        self.genes_in_db = t32(gdb)
+        self.contig_start_d = t32(np.asarray(streams.contig_start, dtype=np.uint64).view(np.int64))
+        self.ref_len_d = t32(np.asarray(streams.ref_lens, dtype=np.int32))
+        self.db_ascii_d = t32(np.concatenate([db_ascii, np.zeros(8, np.uint8)]))
+        self.db_off_d = t32(np.asarray(db_off, dtype=np.int64))
+        nl = index.n_loci
+        self.scratch = torch.zeros(nl * 24 + 64, dtype=torch.uint8, device=dev)
+        self.max_chunks = int(streams.p_pos.shape[0]) // 512 + nl + 8
+        self.chunks_d = torch.zeros(self.max_chunks * 8, dtype=torch.int32, device=dev)
+        # one int32 block for every small output: header[8] | chosen_tid[nl] | chosen_species[nl] | col_off[nl+1] | holes[nl] | snps[nl]
+        self.o_hdr, self.o_tid, self.o_sp, self.o_col, self.o_holes, self.o_snps = 0, 8, 8 + nl, 8 + 2 * nl, 9 + 3 * nl, 9 + 4 * nl
+        self.small = torch.zeros(9 + 5 * nl + 7, dtype=torch.int32, device=dev)
+        self.db_start_d = torch.zeros(nl + 1, dtype=torch.int64, device=dev)
+        self.small_h = torch.zeros(self.small.shape[0], dtype=torch.int32).pin_memory()
+        self.cons_h = torch.zeros(self.cons.shape[0], dtype=torch.uint8).pin_memory()
+        self.counters_h = torch.zeros(2, dtype=torch.int64).pin_memory()
         self.timers: Optional[Dict[str, list]] = None  # name -> [(start_event, end_event)]
         self.launches = 0
 
@@ -145,7 +185,61 @@ class DevicePipeline:
         return [cons[col_off[i]:col_off[i + 1]].tobytes().decode("latin-1") for i in range(len(tids))], holes, snps, col_off
 
     def step(self):
-        """One pass of the hot path over the resident sample.  Returns {species: [(contig, consensus, holes, snps)]}."""
+        """One pass of the hot path, no host round trip between the stages: score -> [all-reduce] -> select (device) ->
+        pileup -> [all-reduce] -> consensus -> one D2H.  Returns {species: [(contig, consensus, holes, snps)]}."""
+        self.run_score()
+        sm, nl = self.small, self.index.n_loci
+        base = sm.data_ptr()
+        def k():
+            native.check(self.lib.mmlst_select_dev(native.ptr(self.sum_as), native.ptr(self.n_hit), native.ptr(self.first_idx), native.ptr(self.locus_of),
+                                                   native.ptr(self.allele_num), self.n_ref, native.ptr(self.species_of_locus), native.ptr(self.genes_in_db),
+                                                   nl, len(self.species_names), self.penalty, self.nloci, native.ptr(self.contig_start_d),
+                                                   native.ptr(self.ref_len_d), native.ptr(self.db_off_d), 0, native.ptr(self.scratch),
+                                                   int(self.scratch.shape[0]), base + 4 * self.o_hdr, base + 4 * self.o_tid, base + 4 * self.o_sp,
+                                                   base + 4 * self.o_col, native.ptr(self.db_start_d), native.ptr(self.chunks_d), self.max_chunks,
+                                                   self._stream()))
+        self._timed("select", k)
+        self.launches += 4
+        s = self.s
+        self.counts.zero_()
+        def k1():
+            native.check(self.lib.mmlst_pileup_indirect_dev(native.ptr(s.p_pos), native.ptr(s.p_row_off), native.ptr(s.p_reflen), native.ptr(s.p_as),
+                                                            native.ptr(s.p_xm), native.ptr(s.planes), native.ptr(self.chunks_d), base + 4 * self.o_hdr,
+                                                            int(s.max_row_words), self.minscore, self.max_xM, native.ptr(self.counts), self.impl,
+                                                            self._stream()))
+        self._timed("pileup", k1)
+        self.launches += 1
+        if self.dist:
+            torch.distributed.all_reduce(self.counts, op=torch.distributed.ReduceOp.SUM, group=self.group)
+        def k2():
+            native.check(self.lib.mmlst_consensus_indirect_dev(native.ptr(self.counts), native.ptr(self.db_ascii_d), native.ptr(self.db_start_d),
+                                                               base + 4 * self.o_col, nl, base + 4 * self.o_hdr, self.mincov, native.ptr(self.cons),
+                                                               base + 4 * self.o_holes, base + 4 * self.o_snps, self._stream()))
+        self._timed("consensus", k2)
+        self.launches += 1
+        self.small_h.copy_(sm, non_blocking=True)
+        self.cons_h.copy_(self.cons, non_blocking=True)
+        self.counters_h.copy_(self.counters, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        h = self.small_h.numpy()
+        n = int(h[0])
+        if h[3] & 1:
+            raise RuntimeError("Database is broken: a species has more detected loci than the genes table lists (metamlst.py:188)")
+        if h[3] & 2:
+            raise RuntimeError("chunk list overflow")
+        tids = h[self.o_tid:self.o_tid + n]
+        if self.bad_len[tids].any():
+            raise IndexError("string index out of range: BAM LN > DB sequence length (metaMLST_functions.py:267)")
+        col = h[self.o_col:self.o_col + n + 1]
+        cons = self.cons_h.numpy()
+        out: Dict[str, list] = {}
+        for i in range(n):
+            out.setdefault(self.species_names[int(h[self.o_sp + i])], []).append(
+                (self.index.ref_names[int(tids[i])], cons[col[i]:col[i + 1]].tobytes().decode("latin-1"), int(h[self.o_holes + i]), int(h[self.o_snps + i])))
+        return out
+
+    def step_host_select(self):
+        """Same pass with the selection done on the host in Python floats (cross-check of the device selection)."""
         self.run_score()
         chosen, _raw = self.select()
         tids = [t for _sp, ts in chosen for t in ts]
@@ -158,3 +252,42 @@ class DevicePipeline:
                     out.setdefault(sp, []).append((self.index.ref_names[t], seqs[i], int(holes[i]), int(snps[i])))
                     i += 1
         return out
+
+
+def device_select(index: api.AlleleIndex, sum_as: np.ndarray, n_hit: np.ndarray, first_idx: np.ndarray, penalty: int = 100,
+                  nloci: int = 100, genes_in_db: Optional[Dict[str, int]] = None, device: str = "cuda:0"):
+    """mmlst_select_dev on given score tables -> [(species, [tid per locus])] in the reference's dict order
+    (same shape as api.fast_select; used by the parity tests of the device-side rounding / ordering)."""
+    lib = native.lib()
+    dev = torch.device(device)
+    n_ref, nl = len(index.ref_names), index.n_loci
+    names: List[str] = []
+    sid: Dict[str, int] = {}
+    sol = np.zeros(nl, np.int32)
+    for l, (sp, _g) in enumerate(index.locus_names):
+        if sp not in sid:
+            sid[sp] = len(names)
+            names.append(sp)
+        sol[l] = sid[sp]
+    gdb = np.asarray([(genes_in_db or {}).get(sp, int((sol == i).sum())) for i, sp in enumerate(names)], np.int32)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    t_sum, t_n, t_f = d(sum_as.astype(np.int64)), d(n_hit.astype(np.uint32).view(np.int32)), d(first_idx.astype(np.uint32).view(np.int32))
+    t_loc, t_an = d(index.locus_of.view(np.int32)), d(np.asarray([int(a) for a in index.allele], np.int64).astype(np.uint32).view(np.int32))
+    t_sol, t_gdb = d(sol), d(gdb)
+    t_cs, t_rl, t_dbo = d(np.zeros(n_ref + 1, np.int64)), d(np.ones(n_ref, np.int32)), d(np.zeros(n_ref + 1, np.int64))
+    scratch = torch.zeros(nl * 24 + 64, dtype=torch.uint8, device=dev)
+    small = torch.zeros(16 + 3 * nl, dtype=torch.int32, device=dev)
+    dbs = torch.zeros(nl + 1, dtype=torch.int64, device=dev)
+    chunks = torch.zeros(8 * (nl + 8), dtype=torch.int32, device=dev)
+    base = small.data_ptr()
+    native.check(lib.mmlst_select_dev(native.ptr(t_sum), native.ptr(t_n), native.ptr(t_f), native.ptr(t_loc), native.ptr(t_an), n_ref,
+                                      native.ptr(t_sol), native.ptr(t_gdb), nl, len(names), int(penalty), int(nloci), native.ptr(t_cs),
+                                      native.ptr(t_rl), native.ptr(t_dbo), 0, native.ptr(scratch), int(scratch.shape[0]), base,
+                                      base + 4 * 8, base + 4 * (8 + nl), base + 4 * (8 + 2 * nl), native.ptr(dbs), native.ptr(chunks), nl + 8,
+                                      torch.cuda.current_stream(dev).cuda_stream))
+    h = small.cpu().numpy()
+    n = int(h[0])
+    out: Dict[str, List[int]] = {}
+    for i in range(n):
+        out.setdefault(names[int(h[8 + nl + i])], []).append(int(h[8 + i]))
+    return list(out.items()), int(h[3])

@@ -214,3 +214,65 @@ def test_closest_allele_seam_matches_oracle_on_golden_cohort(ctx):
     st = orc.merge_bacterium(odb, "ecoli", cel["ecoli"], 5, closest=idx.closest_allele)
     assert orc.st_table_text(st) == open(os.path.join(d, "nfo", "merged", "ecoli_ST.txt"), newline="").read()
     assert api.define_profile(odb.conn, ["ecoli_adk_1", "ecoli_nosuch_1"]) == [(0, 0)]
+
+
+# ------------------------------------------------------------------------------------------------ device-side selection
+def test_device_selection_rounding_and_order_match_python(ctx):
+    """H5/H6 on the device: exact Python round(x, 1) as integer tenths, lowest int(allele) among ties, dict order."""
+    from metamlst_b200 import pipeline
+    rng = np.random.default_rng(7)
+    names = ["s%d_g%d_%d" % (sp, g, a) for sp in range(3) for g in range(4) for a in (7, 3, 12, 1, 25, 2)]
+    index = api.AlleleIndex(names)
+    for trial in range(60):
+        n = rng.integers(0, 40, size=len(names)).astype(np.uint32)
+        n[rng.random(len(names)) < 0.3] = 0
+        # sums chosen so that many quotients land on / next to x.x5 ties
+        s = (n.astype(np.int64) * rng.integers(100, 140, size=len(names))) + rng.integers(0, 3, size=len(names)) * (n.astype(np.int64) // 20 + 1)
+        s = np.where(rng.random(len(names)) < 0.3, (n.astype(np.int64) * 27 + n.astype(np.int64) // 20), s)  # x.05-type ties
+        f = rng.permutation(len(names)).astype(np.uint32)
+        f[n == 0] = 0xFFFFFFFF
+        nloci = int(rng.choice([100, 75, 50, 0]))
+        want_all = api.fast_select(index, s, n, f, 100)
+        # --nloci gate (metamlst.py:194-206) applied on the host side of the comparison
+        want = [(sp, t) for sp, t in want_all if int((float(len(t)) / 4.0) * 100) >= nloci]
+        got, err = pipeline.device_select(index, s, n, f, 100, nloci)
+        assert err == 0 and got == want, (trial, got, want)
+    # hand-made ties: 2705/20 = 135.25 -> 135.2 and 2704/20 = 135.2 tie; lowest allele number (3) must win over 7
+    idx2 = api.AlleleIndex(["o_g_7", "o_g_3", "o_g_5"])
+    got, _ = pipeline.device_select(idx2, np.array([2705, 2704, 2690], np.int64), np.array([20, 20, 20], np.uint32), np.array([0, 1, 2], np.uint32))
+    assert got == [("o", [1])]
+    # penalty path: fewer hits than the locus maximum
+    got, _ = pipeline.device_select(idx2, np.array([1000, 2704, 100], np.int64), np.array([7, 20, 1], np.uint32), np.array([0, 1, 2], np.uint32))
+    assert got == api.fast_select(idx2, np.array([1000, 2704, 100], np.int64), np.array([7, 20, 1], np.uint32), np.array([0, 1, 2], np.uint32), 100)
+
+
+@pytest.mark.parametrize("case", [dict(seed=81, n_reads=3000, L=100, K=4, orgs=("ecoli", "saureus")),
+                                  dict(seed=82, n_reads=30000, L=150, K=4, orgs=("ecoli",)),
+                                  dict(seed=83, n_reads=60, L=100, K=2, orgs=("ecoli", "saureus", "kpneumoniae"))])
+def test_device_pipeline_equals_host_selected_path_and_oracle(ctx, case):
+    from metamlst_b200 import devpack, pipeline, synth
+    kw = dict(case)
+    orgs = kw.pop("orgs")
+    db = synth.make_db(orgs, alleles_per_locus=6, n_profiles=10, seed=kw["seed"])
+    gk = dict(read_len=kw["L"], seed=kw["seed"], K=kw["K"], sub_err=0.02)
+    core = synth.gen_core(db, kw["n_reads"], device="cuda:0", **gk)
+    st = devpack.pack_cores(db, [core], 20, 8000)
+    tab = synth.make_sample(db, kw["n_reads"], device="cuda:0", **gk)
+    index = api.AlleleIndex(db.ref_names())
+    for nloci in (100, 50):
+        pipe = pipeline.DevicePipeline(st, index, db.row_seq, minscore=2 * kw["L"] - 30, max_xM=4, nloci=nloci)
+        a = pipe.step()
+        b = pipe.step_host_select()
+        if nloci == 100:
+            b = {sp: v for sp, v in b.items() if len(v) == 7}
+        else:
+            b = {sp: v for sp, v in b.items() if int(len(v) / 7.0 * 100) >= nloci}
+        assert a == b
+        assert a == pipe.step()  # idempotent
+    # oracle: consensus of every chosen contig
+    stab = tab.sorted_by_coord()
+    for sp, lst in a.items():
+        for contig, seq, holes, snps in lst:
+            t = index.name_to_tid[contig]
+            want, _ = corc.contig_counts(stab, t, 20, 2 * kw["L"] - 30, 4, 8000)
+            assert (seq, holes, snps) == corc.consensus(want, db.row_seq(t).encode(), 1)
