@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--k", type=int, default=4, help="alignments per read")
     ap.add_argument("--pileup-impl", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true", help="skip uncapped / hamming / cpu baseline extras")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay of the pass")
     ap.add_argument("--cpu-sample-reads", type=int, default=400_000)
     return ap.parse_args()
 
@@ -244,8 +245,16 @@ def main():
     result = None
     for _ in range(max(args.warmup, 3)):
         result = pipe.step()
+    use_graph = not args.no_graph
+    if use_graph:
+        try:
+            pipe.capture()
+            assert pipe.step_graph() == result, "graph replay differs from the eager pass"
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write("CUDA graph capture unavailable (%r): timing the eager pass\n" % (e,))
+            use_graph = False
+    stepfn = pipe.step_graph if use_graph else pipe.step
     barrier()
-    pipe.timers = {}
     pipe.launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -254,13 +263,19 @@ def main():
         torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
-        out = pipe.step()
+        out = stepfn()
     e1.record()
     barrier()
     if prof:
         torch.cuda.profiler.stop()
     clocks = sampler.stop()
     assert out == result, "results changed between steps"
+    launches = pipe.launches
+    # per-kernel durations: CUDA events around each launch of the same pass, eager (events are not graph-capturable)
+    pipe.timers = {}
+    for _ in range(min(args.steps, 20)):
+        pipe.step()
+    torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms], dtype=torch.float64, device=device)
     if world > 1:
@@ -268,7 +283,6 @@ def main():
     ms = float(t.item())
     R_total = R_local * world
     kms = {k: float(np.mean(event_ms(v))) for k, v in pipe.timers.items()}
-    launches = pipe.launches
     pipe.timers = None
     tids = [index.name_to_tid[c] for sp in out for (c, _s, _h, _n) in out[sp]]
     score_bytes = 9.0 * R_local
@@ -287,8 +301,8 @@ def main():
             "vs_baseline": None, "dtype": "int32/u8 (integer bit-plane arithmetic)", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks, "gpu_launches": launches,
             "roofline": dict(rooflines[dominant], kernel=dominant, peak_source=peak_src), "rooflines": rooflines,
-            "kernel_ms_per_step": kms, "records_per_gpu": R_local,
-            "host_gap_ms_per_step": ms - sum(kms.values())}
+            "kernel_ms_per_step": kms, "records_per_gpu": R_local, "cuda_graph": use_graph,
+            "non_kernel_ms_per_step": ms - sum(kms.values())}
 
     # ---- end to end through the host-buffer C-ABI (pinned host memory -> results on the host)
     soa = st.to_host(pinned=True)
@@ -309,8 +323,9 @@ def main():
         for _ in range(n_e2e):
             e2e_step()
         dt = (time.perf_counter() - t0) / n_e2e
-        h2d = 9 * R_local + db.n_rows * 5 + int(sum((st.contig_start[t + 1] - st.contig_start[t]) * 13 + 0 for t in tids))
-        h2d += int(sum(int(soa.p_row_off[int(st.contig_start[t + 1])]) - int(soa.p_row_off[int(st.contig_start[t])]) for t in tids)) * 4
+        h2d = 9 * R_local + db.n_rows * 5 + int(sum((st.contig_start[t + 1] - st.contig_start[t]) * 16 for t in tids))
+        proff = soa.p_row_off
+        h2d += int(sum(int(proff[int(st.contig_start[t + 1])]) - int(proff[int(st.contig_start[t])]) for t in tids)) * 4
         d2h = db.n_rows * 16 + 16 + sum(int(st.ref_lens[t]) for t in tids) + 8 * len(tids)
         line["e2e"] = {"value": R_local / dt, "unit": "records/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3}
     else:

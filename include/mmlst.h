@@ -18,8 +18,10 @@
  *                      xm3 u8 (4th aux field by POSITION, saturated at 255), qlen u16 (len(SEQ) as SAM prints it),
  *                      optional orig_idx u32 (index in file order; NULL = identity + idx_base).        9 B / record
  *   pileup stream  : records ADMITTED by the htslib depth cap, coordinate-sorted, CIGAR already projected on the
- *                    reference: pos i32, row_off u32 (word offset into planes, row_off[P] = end), reflen u16,
- *                    as_named i16 / xm_named u8 (AS, XM by NAME), and per record a row of 3 bit-planes x nw words
+ *                    reference: one 16-byte mmlst_prec per record {pos i32, row_off u32 (word offset into planes),
+ *                    reflen u16, as_named i16, xm_named u8 (AS, XM by NAME)} -- array-of-16-byte-structs so that the
+ *                    metadata of a 512-record tile is ONE contiguous 8 KB bulk copy -- and per record a row of 3
+ *                    bit-planes x nw words
  *                    (nw = ceil(reflen/32)), word-interleaved [V_j, B1_j, B0_j], bit i of word j = reference offset
  *                    32 j + i:  V=1 -> ACGT base with quality >= minqual and code B1B0 (A=0,C=1,G=2,T=3);
  *                    V=0,B0=1 -> counted non-ACGT base (bin N); V=0,B0=0 -> not in the column (deletion, refskip,
@@ -92,6 +94,15 @@ int mmlst_score_dev(const uint32_t* tid, const int16_t* as0, const uint8_t* xm3,
  *   carry-save counters (v2).  max_row_words = largest row (3*nw, padded odd) in the stream.
  * --------------------------------------------------------------------------------------------------------------- */
 typedef struct {
+    int32_t pos;        /* 0-based leftmost reference position */
+    uint32_t row_off;   /* word offset of the record's plane row */
+    uint16_t reflen;    /* reference span */
+    int16_t as_named;   /* AS:i by NAME (cmseq tag filter, metaMLST_functions.py:259) */
+    uint8_t xm_named;   /* XM:i by NAME, saturated at 255 */
+    uint8_t pad[3];
+} mmlst_prec;
+
+typedef struct {
     uint32_t rec_begin, rec_end;   /* pileup-stream record range */
     uint32_t col_base, contig_len; /* column range in the count tensor */
     uint32_t plane_delta;          /* added to row_off[] */
@@ -101,8 +112,7 @@ typedef struct {
 /* records per chunk that fills the chip for a launch over n_rec records (multiple of 512, <= 63*512) */
 uint32_t mmlst_chunk_records(uint64_t n_rec);
 
-int mmlst_pileup_dev(const int32_t* pos, const uint32_t* row_off, const uint16_t* reflen,
-                     const int16_t* as_named, const uint8_t* xm_named, const uint32_t* planes,
+int mmlst_pileup_dev(const mmlst_prec* recs, const uint32_t* planes,
                      const mmlst_chunk* chunks, uint32_t n_chunks, uint32_t max_row_words,
                      int minscore, int max_xm, uint32_t* counts, uint32_t total_cols, int impl, void* stream);
 
@@ -144,8 +154,7 @@ int mmlst_select_dev(const int64_t* sum_as, const uint32_t* n_hit, const uint32_
                      const uint32_t* ref_len, const uint64_t* db_off, uint32_t chunk_records, void* scratch, size_t scratch_bytes,
                      uint32_t* header, uint32_t* chosen_tid, uint32_t* chosen_species, uint32_t* col_off, uint64_t* db_start,
                      mmlst_chunk* chunks, uint32_t max_chunks, void* stream);
-int mmlst_pileup_indirect_dev(const int32_t* pos, const uint32_t* row_off, const uint16_t* reflen, const int16_t* as_named,
-                              const uint8_t* xm_named, const uint32_t* planes, const mmlst_chunk* chunks, const uint32_t* header,
+int mmlst_pileup_indirect_dev(const mmlst_prec* recs, const uint32_t* planes, const mmlst_chunk* chunks, const uint32_t* header,
                               uint32_t max_row_words, int minscore, int max_xm, uint32_t* counts, int impl, void* stream);
 int mmlst_consensus_indirect_dev(const uint32_t* counts, const uint8_t* db_ascii, const uint64_t* db_start, const uint32_t* col_off,
                                  uint32_t max_loci, const uint32_t* header, uint32_t mincov, uint8_t* cons, uint32_t* holes,
@@ -176,7 +185,7 @@ typedef struct {
     const uint32_t* tid; const int16_t* as0; const uint8_t* xm3; const uint16_t* qlen; const uint32_t* orig_idx;
     uint64_t n_rec;
     /* pileup stream */
-    const int32_t* p_pos; const uint32_t* p_row_off; const uint16_t* p_reflen; const int16_t* p_as; const uint8_t* p_xm;
+    const mmlst_prec* p_recs;
     const uint32_t* planes; uint64_t n_prec; uint64_t n_plane_words; uint32_t max_row_words;
     /* per reference (allele row) */
     const uint64_t* contig_start; /* [n_ref+1] first pileup-stream record of each contig */

@@ -76,15 +76,15 @@ struct mmlst_ctx {
     // score stream
     DevBuf tid, as0, xm3, qlen, oidx, allow, locus_of, sum_as, n_hit, first_idx, counters;
     // pileup stream (chosen contigs only)
-    DevBuf p_pos, p_off, p_reflen, p_as, p_xm, planes, chunks, counts, dbseq, col_off, cons, holes, snps;
+    DevBuf p_recs, planes, chunks, counts, dbseq, col_off, cons, holes, snps;
     // hamming
     DevBuf db_hi, db_lo, db_len, q_hi, q_lo, q_len, blocks, best;
     uint32_t db_rows = 0, db_W = 0;
     DevBuf* all[35];
     int n_all = 0;
     mmlst_ctx() {
-        DevBuf* l[] = {&tid, &as0, &xm3, &qlen, &oidx, &allow, &locus_of, &sum_as, &n_hit, &first_idx, &counters, &p_pos, &p_off,
-                       &p_reflen, &p_as, &p_xm, &planes, &chunks, &counts, &dbseq, &col_off, &cons, &holes, &snps, &db_hi,
+        DevBuf* l[] = {&tid, &as0, &xm3, &qlen, &oidx, &allow, &locus_of, &sum_as, &n_hit, &first_idx, &counters, &p_recs,
+                       &planes, &chunks, &counts, &dbseq, &col_off, &cons, &holes, &snps, &db_hi,
                        &db_lo, &db_len, &q_hi, &q_lo, &q_len, &blocks, &best};
         for (DevBuf* b : l) all[n_all++] = b;
     }
@@ -181,13 +181,13 @@ extern "C" uint32_t mmlst_chunk_records(uint64_t n_rec) {
     return (uint32_t)c;
 }
 
-extern "C" int mmlst_pileup_dev(const int32_t* pos, const uint32_t* row_off, const uint16_t* reflen, const int16_t* as_named,
-                                const uint8_t* xm_named, const uint32_t* planes, const mmlst_chunk* chunks, uint32_t n_chunks,
+extern "C" int mmlst_pileup_dev(const mmlst_prec* recs, const uint32_t* planes, const mmlst_chunk* chunks, uint32_t n_chunks,
                                 uint32_t max_row_words, int minscore, int max_xm, uint32_t* counts, uint32_t total_cols,
                                 int impl, void* stream) {
     if (n_chunks == 0) return MMLST_OK;
-    if (!pos || !row_off || !reflen || !as_named || !xm_named || !planes || !chunks || !counts) { mmlst_set_error("mmlst_pileup_dev: null pointer"); return MMLST_E_ARG; }
-    PileupArgs a{pos, row_off, reflen, as_named, xm_named, planes, chunks, n_chunks, max_row_words, minscore, max_xm, counts, total_cols, nullptr};
+    if (!recs || !planes || !chunks || !counts) { mmlst_set_error("mmlst_pileup_dev: null pointer"); return MMLST_E_ARG; }
+    if ((reinterpret_cast<uintptr_t>(recs) & 15) || (reinterpret_cast<uintptr_t>(planes) & 15)) { mmlst_set_error("mmlst_pileup_dev: recs and planes must be 16-byte aligned"); return MMLST_E_ARG; }
+    PileupArgs a{recs, planes, chunks, n_chunks, max_row_words, minscore, max_xm, counts, total_cols, nullptr};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (impl == 1) return launch_pileup_atomic(a, s);
     if (impl == 0 || impl == 2) return launch_pileup_bitsliced(a, s);
@@ -196,12 +196,12 @@ extern "C" int mmlst_pileup_dev(const int32_t* pos, const uint32_t* row_off, con
 }
 
 // chunk list and count produced on the device by mmlst_select_dev (header[1] = n_chunks)
-extern "C" int mmlst_pileup_indirect_dev(const int32_t* pos, const uint32_t* row_off, const uint16_t* reflen, const int16_t* as_named,
-                                         const uint8_t* xm_named, const uint32_t* planes, const mmlst_chunk* chunks,
+extern "C" int mmlst_pileup_indirect_dev(const mmlst_prec* recs, const uint32_t* planes, const mmlst_chunk* chunks,
                                          const uint32_t* header, uint32_t max_row_words, int minscore, int max_xm, uint32_t* counts,
                                          int impl, void* stream) {
-    if (!pos || !row_off || !reflen || !as_named || !xm_named || !planes || !chunks || !header || !counts) { mmlst_set_error("mmlst_pileup_indirect_dev: null pointer"); return MMLST_E_ARG; }
-    PileupArgs a{pos, row_off, reflen, as_named, xm_named, planes, chunks, 0, max_row_words, minscore, max_xm, counts, 0, header + 1};
+    if (!recs || !planes || !chunks || !header || !counts) { mmlst_set_error("mmlst_pileup_indirect_dev: null pointer"); return MMLST_E_ARG; }
+    if ((reinterpret_cast<uintptr_t>(recs) & 15) || (reinterpret_cast<uintptr_t>(planes) & 15)) { mmlst_set_error("mmlst_pileup_indirect_dev: recs and planes must be 16-byte aligned"); return MMLST_E_ARG; }
+    PileupArgs a{recs, planes, chunks, 0, max_row_words, minscore, max_xm, counts, 0, header + 1};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (impl == 1) return launch_pileup_atomic(a, s);
     if (impl == 0 || impl == 2) return launch_pileup_bitsliced(a, s);
@@ -218,17 +218,18 @@ extern "C" int mmlst_pileup_consensus(mmlst_ctx* c, const mmlst_soa* soa, const 
     if (n_loci == 0) return MMLST_OK;
     cudaStream_t s = c->stream;
     // gather the chosen contigs' record / plane ranges (contiguous in the coordinate-sorted stream)
+    auto row_end = [&](uint64_t r) { return soa->p_recs[r].row_off + mmlst_row_words(soa->p_recs[r].reflen); };
     size_t n_rec = 0, n_words = 0;
     for (uint32_t l = 0; l < n_loci; ++l) {
         const uint32_t t = chosen_tid[l];
         if (t >= soa->n_ref) { mmlst_set_error("chosen_tid[%u]=%u out of range", l, t); return MMLST_E_ARG; }
         const uint64_t r0 = soa->contig_start[t], r1 = soa->contig_start[t + 1];
+        if (r1 <= r0) continue;
         n_rec += r1 - r0;
-        n_words += (size_t)soa->p_row_off[r1] - soa->p_row_off[r0];
+        n_words += (size_t)row_end(r1 - 1) - soa->p_recs[r0].row_off + 4;  // +4: every range starts 16-byte aligned on the device
     }
     const uint32_t total_cols = col_off[n_loci];
-    TRY(c->p_pos.reserve(n_rec * 4 + 16)); TRY(c->p_off.reserve(n_rec * 4 + 16)); TRY(c->p_reflen.reserve(n_rec * 2 + 16));
-    TRY(c->p_as.reserve(n_rec * 2 + 16)); TRY(c->p_xm.reserve(n_rec + 16)); TRY(c->planes.reserve(n_words * 4 + 64));
+    TRY(c->p_recs.reserve(n_rec * sizeof(mmlst_prec) + 64)); TRY(c->planes.reserve(n_words * 4 + 64));
     std::vector<mmlst_chunk> chunks;
     const uint32_t kChunkRecords = mmlst_chunk_records(n_rec);
     size_t rbase = 0, wbase = 0;
@@ -237,12 +238,8 @@ extern "C" int mmlst_pileup_consensus(mmlst_ctx* c, const mmlst_soa* soa, const 
         const uint64_t r0 = soa->contig_start[t], r1 = soa->contig_start[t + 1];
         const size_t nr = r1 - r0;
         if (nr == 0) continue;
-        const uint32_t w0 = soa->p_row_off[r0], w1 = soa->p_row_off[r1];
-        CUDA_TRY(cudaMemcpyAsync(c->p_pos.as<int32_t>() + rbase, soa->p_pos + r0, nr * 4, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(c->p_off.as<uint32_t>() + rbase, soa->p_row_off + r0, nr * 4, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(c->p_reflen.as<uint16_t>() + rbase, soa->p_reflen + r0, nr * 2, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(c->p_as.as<int16_t>() + rbase, soa->p_as + r0, nr * 2, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(c->p_xm.as<uint8_t>() + rbase, soa->p_xm + r0, nr, cudaMemcpyHostToDevice, s));
+        const uint32_t w0 = soa->p_recs[r0].row_off, w1 = row_end(r1 - 1);
+        CUDA_TRY(cudaMemcpyAsync(c->p_recs.as<mmlst_prec>() + rbase, soa->p_recs + r0, nr * sizeof(mmlst_prec), cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(c->planes.as<uint32_t>() + wbase, soa->planes + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, s));
         for (size_t b = 0; b < nr; b += kChunkRecords) {
             mmlst_chunk ck{};
@@ -254,7 +251,8 @@ extern "C" int mmlst_pileup_consensus(mmlst_ctx* c, const mmlst_soa* soa, const 
             chunks.push_back(ck);
         }
         rbase += nr;
-        wbase += w1 - w0;
+        wbase += (size_t)(w1 - w0);
+        wbase = (wbase + 3) & ~(size_t)3;
     }
     TRY(h2d(c->chunks, chunks.data(), chunks.size(), s));
     TRY(h2d(c->dbseq, dbseq, total_cols, s));
@@ -262,8 +260,7 @@ extern "C" int mmlst_pileup_consensus(mmlst_ctx* c, const mmlst_soa* soa, const 
     TRY(c->counts.reserve((size_t)total_cols * 20 + 16)); TRY(c->cons.reserve(total_cols + 16));
     TRY(c->holes.reserve(n_loci * 4)); TRY(c->snps.reserve(n_loci * 4));
     CUDA_TRY(cudaMemsetAsync(c->counts.p, 0, (size_t)total_cols * 20, s));
-    TRY(mmlst_pileup_dev(c->p_pos.as<int32_t>(), c->p_off.as<uint32_t>(), c->p_reflen.as<uint16_t>(), c->p_as.as<int16_t>(),
-                         c->p_xm.as<uint8_t>(), c->planes.as<uint32_t>(), c->chunks.as<mmlst_chunk>(), (uint32_t)chunks.size(),
+    TRY(mmlst_pileup_dev(c->p_recs.as<mmlst_prec>(), c->planes.as<uint32_t>(), c->chunks.as<mmlst_chunk>(), (uint32_t)chunks.size(),
                          soa->max_row_words, minscore, max_xm, c->counts.as<uint32_t>(), total_cols, impl, s));
     TRY(mmlst_consensus_dev(c->counts.as<uint32_t>(), c->dbseq.as<uint8_t>(), c->col_off.as<uint32_t>(), n_loci, mincov,
                             c->cons.as<uint8_t>(), c->holes.as<uint32_t>(), c->snps.as<uint32_t>(), s));

@@ -3,7 +3,7 @@
 #include "common.cuh"
 
 struct PileupArgs {
-    const int32_t* pos; const uint32_t* row_off; const uint16_t* reflen; const int16_t* as_named; const uint8_t* xm_named;
+    const mmlst_prec* recs;
     const uint32_t* planes; const mmlst_chunk* chunks; uint32_t n_chunks; uint32_t max_row_words;
     int minscore, max_xm; uint32_t* counts; uint32_t total_cols;
     const uint32_t* n_chunks_dev;  // when non-null the chunk count is read on the device (written by mmlst_select_dev)
@@ -12,3 +12,8 @@ struct PileupArgs {
 int launch_pileup_atomic(const PileupArgs& a, cudaStream_t stream);
 int launch_pileup_bitsliced(const PileupArgs& a, cudaStream_t stream);
 __device__ __forceinline__ uint32_t pileup_n_chunks(const PileupArgs& a) { return a.n_chunks_dev ? *a.n_chunks_dev : a.n_chunks; }
+
+__host__ __device__ __forceinline__ uint32_t mmlst_row_words(uint32_t reflen) {
+    const uint32_t rw = 3u * ((reflen + 31u) >> 5);
+    return rw + ((rw != 0u && (rw & 1u) == 0u) ? 1u : 0u);  // padded to an odd word count (0 stays 0)
+}

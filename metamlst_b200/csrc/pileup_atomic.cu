@@ -14,10 +14,11 @@ __global__ void __launch_bounds__(256) pileup_atomic_kernel(const PileupArgs a) 
     for (uint32_t ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
     const mmlst_chunk ck = a.chunks[ci];
     for (uint32_t rec = ck.rec_begin + wib; rec < ck.rec_end; rec += wpb) {
-        const int p = a.pos[rec];
-        const uint32_t off = a.row_off[rec] + ck.plane_delta;
-        const uint32_t rl = a.reflen[rec];
-        const bool pass = (int(a.as_named[rec]) >= a.minscore) && (int(a.xm_named[rec]) <= a.max_xm);
+        const mmlst_prec pr = a.recs[rec];
+        const int p = pr.pos;
+        const uint32_t off = pr.row_off + ck.plane_delta;
+        const uint32_t rl = pr.reflen;
+        const bool pass = (int(pr.as_named) >= a.minscore) && (int(pr.xm_named) <= a.max_xm);
         const uint32_t nw = (rl + 31u) >> 5;
         for (uint32_t j = 0; j < nw; ++j) {
             const uint32_t v = a.planes[off + 3 * j + 0];

@@ -7,9 +7,10 @@
 // are counted per LOP3 with carry-save adders (Harley-Seal), the same trick as a vertical popcount.
 //
 // Mapping
-//   CTA      : persistent over chunks (<= 63 tiles of one contig); tile = 512 consecutive coordinate-sorted records
-//              whose plane rows are ONE contiguous global range -> a single cp.async.bulk (TMA 1-D, UBLKCP) per tile
-//              into a 3-stage shared-memory ring, completion on an mbarrier.
+//   CTA      : persistent over chunks (<= 63 tiles of one contig); tile = 512 consecutive coordinate-sorted records.
+//              Their plane rows are ONE contiguous global range and their 16-byte records another, so a tile is two
+//              cp.async.bulk (TMA 1-D, SASS UBLKCP) into a double-buffered shared-memory stage, completion on one
+//              mbarrier; thread 0 issues tile t+1 before tile t is counted.  No per-thread global loads at all.
 //   warp     : owns one 32-column word w of the contig (w mod 8 == warp id inside the sliding 8-word window).
 //   lane     : takes records lane, lane+32, ... of the tile (16 per tile), funnel-shifts the record's planes to the
 //              word's alignment and adds five 1-bit planes (counted, ok, ok&B0, ok&B1, ok&B0&B1) into private
@@ -78,19 +79,28 @@ __device__ __forceinline__ void ripple16(Counter& c, uint32_t x) {  // add the "
 
 struct Contrib { uint32_t x[5]; };  // counted, ok, ok&B0, ok&B1, ok&B0&B1
 
-// planes of tile-record (meta) shifted to the alignment of column word starting at column w32
-__device__ __forceinline__ Contrib load_contrib(const uint32_t* __restrict__ stage, int2 meta, int w32) {
-    const int pos = meta.x;
-    const uint32_t m = static_cast<uint32_t>(meta.y);
-    const uint32_t soff = m & 0xffffu;
-    const int nw = int((m >> 16) & 63u);
-    const uint32_t pm = ((m >> 22) & 1u) ? FULL : 0u;
+struct TileCtx {
+    const uint32_t* planes;  // stage planes
+    uint32_t soff_base;      // plane_delta - a0 (mod 2^32): row_off + soff_base = word offset inside the stage
+    uint32_t cnt;            // records in the tile
+    int minscore, max_xm;
+};
+
+// planes of tile record i (16-byte mmlst_prec in shared memory) shifted to the alignment of the column word at w32
+__device__ __forceinline__ Contrib load_contrib(const TileCtx& tc, const uint4* __restrict__ meta, uint32_t i, int w32) {
+    const uint4 m = meta[i];
+    const int pos = static_cast<int>(m.x);
+    const uint32_t nw = ((m.z & 0xffffu) + 31u) >> 5;
+    const int as = static_cast<int>(m.z) >> 16;
+    const int xm = static_cast<int>(m.w & 0xffu);
+    const uint32_t pm = (as >= tc.minscore && xm <= tc.max_xm) ? FULL : 0u;
     const int d = w32 - pos;
     const int j0 = d >> 5;
     const uint32_t s = static_cast<uint32_t>(d) & 31u;
-    const bool lo_ok = (j0 >= 0) && (j0 < nw);
-    const bool hi_ok = (j0 + 1 >= 0) && (j0 + 1 < nw);
-    const uint32_t* r = stage + soff + 3 * j0;
+    const bool valid = i < tc.cnt;
+    const bool lo_ok = valid && (static_cast<uint32_t>(j0) < nw);
+    const bool hi_ok = valid && (static_cast<uint32_t>(j0 + 1) < nw);
+    const uint32_t* r = tc.planes + (m.y + tc.soff_base) + 3 * j0;
     uint32_t vl = 0, hl = 0, ll = 0, vh = 0, hh = 0, lh = 0;
     if (lo_ok) { vl = r[0]; hl = r[1]; ll = r[2]; }
     if (hi_ok) { vh = r[3]; hh = r[4]; lh = r[5]; }
@@ -164,26 +174,12 @@ __device__ __forceinline__ void flush_word(const WarpAcc& acc, int w, const mmls
     if (nN) atomicAdd(c + 4, nN);
 }
 
-struct TileInfo {
-    int min_pos;    // pos of the first record
-    int max_end;    // max(pos + reflen) over the tile
-    uint32_t a0;    // first (16-byte aligned) plane word of the tile
-    uint32_t nwords;  // words copied (multiple of 4)
-};
-
-__device__ __forceinline__ uint32_t row_words(uint32_t reflen) {
-    const uint32_t rw = 3u * ((reflen + 31u) >> 5);
-    return rw + ((rw & 1u) ^ 1u) * (rw ? 1u : 0u);  // padded to an odd word count (0 stays 0)
-}
-
 template <int NS>
 __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const PileupArgs a, const uint32_t stage_words) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint32_t* stages = reinterpret_cast<uint32_t*>(smem_raw);                            // NS x stage_words
-    int2* meta = reinterpret_cast<int2*>(stages + static_cast<size_t>(NS) * stage_words);  // 2 x TR
-    TileInfo* tinfo = reinterpret_cast<TileInfo*>(meta + 2 * TR);                       // 2
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tinfo + 2);                            // NS
-    int* red = reinterpret_cast<int*>(bars + NS);                                       // NWARP
+    // stage s: planes [stage_words] u32, then TR x 16-byte records
+    const size_t stage_bytes = static_cast<size_t>(stage_words) * 4 + TR * sizeof(mmlst_prec);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + NS * stage_bytes);
 
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
@@ -193,86 +189,62 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
     }
     __syncthreads();
     uint32_t phase_bits = 0;  // parity per stage
+    const int maxspan = int(a.max_row_words / 3u) * 32;  // upper bound of any record's reference span
 
     const uint32_t n_chunks = pileup_n_chunks(a);
     for (uint32_t ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
         const mmlst_chunk ck = a.chunks[ci];
         const uint32_t nrec = ck.rec_end - ck.rec_begin;
         const uint32_t ntiles = (nrec + TR - 1) / TR;
+        uint4 g_first = make_uint4(0, 0, 0, 0), g_last = g_first;  // thread 0: first / last record of the next tile to copy
 
-        // tile geometry + metadata builder (two records per thread); returns nothing, writes meta[buf] and tinfo[buf]
-        auto build_meta = [&](uint32_t t, int buf) {
+        auto load_geo = [&](uint32_t t) {  // thread 0: two 16-byte loads, consumed one tile later
+            const uint32_t r0 = ck.rec_begin + t * TR;
+            const uint32_t last = min(r0 + uint32_t(TR), ck.rec_end) - 1u;
+            g_first = __ldg(reinterpret_cast<const uint4*>(a.recs + r0));
+            g_last = __ldg(reinterpret_cast<const uint4*>(a.recs + last));
+        };
+        auto issue_copy = [&](uint32_t t, int stage) {  // thread 0
             const uint32_t r0 = ck.rec_begin + t * TR;
             const uint32_t cnt = min(uint32_t(TR), ck.rec_end - r0);
-            const uint32_t w_first = a.row_off[r0] + ck.plane_delta;
-            const uint32_t a0 = w_first & ~3u;
-            int mx = INT_MIN;
-#pragma unroll
-            for (int k = 0; k < TR / NTHREADS; ++k) {
-                const uint32_t i = threadIdx.x + k * NTHREADS;
-                int2 m = make_int2(0, 0);
-                if (i < cnt) {
-                    const uint32_t rec = r0 + i;
-                    const int p = a.pos[rec];
-                    const uint32_t rl = a.reflen[rec];
-                    const uint32_t soff = a.row_off[rec] + ck.plane_delta - a0;
-                    const uint32_t pass = (int(a.as_named[rec]) >= a.minscore) && (int(a.xm_named[rec]) <= a.max_xm);
-                    m.x = p;
-                    m.y = int(soff | (((rl + 31u) >> 5) << 16) | (pass << 22));
-                    mx = max(mx, p + int(rl));
-                }
-                meta[buf * TR + i] = m;
-            }
-            mx = __reduce_max_sync(FULL, mx);
-            if (lane == 0) red[wid] = mx;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                int m2 = red[0];
-#pragma unroll
-                for (int k = 1; k < NWARP; ++k) m2 = max(m2, red[k]);
-                const uint32_t last = r0 + cnt - 1;
-                const uint32_t w_end = a.row_off[last] + ck.plane_delta + row_words(a.reflen[last]);
-                TileInfo ti;
-                ti.min_pos = a.pos[r0];
-                ti.max_end = m2;
-                ti.a0 = a0;
-                ti.nwords = ((w_end + 3u) & ~3u) - a0;
-                tinfo[buf] = ti;
-            }
-            __syncthreads();
-        };
-        auto issue_copy = [&](int buf, int stage) {  // thread 0 only
-            const TileInfo ti = tinfo[buf];
-            const uint32_t bytes = ti.nwords * 4u;
-            mbar_expect_tx(bars + stage, bytes);
-            bulk_g2s(stages + static_cast<size_t>(stage) * stage_words, a.planes + ti.a0, bytes, bars + stage);
+            const uint32_t a0 = (g_first.y + ck.plane_delta) & ~3u;
+            const uint32_t w_end = g_last.y + ck.plane_delta + mmlst_row_words(g_last.z & 0xffffu);
+            const uint32_t pbytes = (((w_end + 3u) & ~3u) - a0) * 4u;
+            const uint32_t mbytes = cnt * uint32_t(sizeof(mmlst_prec));
+            uint8_t* st = smem_raw + stage * stage_bytes;
+            mbar_expect_tx(bars + stage, pbytes + mbytes);
+            if (pbytes) bulk_g2s(st, a.planes + a0, pbytes, bars + stage);
+            bulk_g2s(st + static_cast<size_t>(stage_words) * 4, a.recs + r0, mbytes, bars + stage);
         };
 
         WarpAcc acc;
         acc.clear();
         int cur_w = INT_MIN;
 
-        // prologue: metadata of tile 0, copy of tile 0
-        build_meta(0, 0);
-        if (threadIdx.x == 0) issue_copy(0, 0);
+        if (threadIdx.x == 0) load_geo(0);
+        __syncthreads();  // every warp is done with the previous chunk's stages
+        if (threadIdx.x == 0) { issue_copy(0, 0); if (ntiles > 1) load_geo(1); }
 
         for (uint32_t t = 0; t < ntiles; ++t) {
-            const int buf = t & 1;
             const int stage = t % NS;
-            // metadata + copy of the next tile overlap this tile's arithmetic (meta[buf^1] was last read in iteration
-            // t-1, stage (t+1)%NS in iteration t+1-NS; both are behind the __syncthreads that ended iteration t-1)
-            if (t + 1 < ntiles) {
-                build_meta(t + 1, buf ^ 1);
-                if (threadIdx.x == 0) issue_copy(buf ^ 1, (t + 1) % NS);
+            if (threadIdx.x == 0 && t + 1 < ntiles) {  // stage (t+1)%NS was last read for tile t+1-NS: behind a barrier
+                issue_copy(t + 1, (t + 1) % NS);
+                if (t + 2 < ntiles) load_geo(t + 2);
             }
             mbar_wait(bars + stage, (phase_bits >> stage) & 1u);
             phase_bits ^= 1u << stage;
 
-            const TileInfo ti = tinfo[buf];
-            const uint32_t* st = stages + static_cast<size_t>(stage) * stage_words;
-            const int2* mt = meta + buf * TR;
-            const int wlo0 = ti.min_pos >> 5;
-            const int whi = (ti.max_end - 1) >> 5;  // last word touched
+            const uint8_t* st = smem_raw + stage * stage_bytes;
+            const uint4* mt = reinterpret_cast<const uint4*>(st + static_cast<size_t>(stage_words) * 4);
+            TileCtx tc;
+            tc.planes = reinterpret_cast<const uint32_t*>(st);
+            tc.cnt = min(uint32_t(TR), ck.rec_end - (ck.rec_begin + t * TR));
+            const uint4 first = mt[0], last = mt[tc.cnt - 1];
+            tc.soff_base = ck.plane_delta - ((first.y + ck.plane_delta) & ~3u);
+            tc.minscore = a.minscore; tc.max_xm = a.max_xm;
+            const int wlo0 = static_cast<int>(first.x) >> 5;  // sorted: the first record has the smallest pos
+            // last word any record of the tile can touch (span bound), clipped to the contig
+            const int whi = min((static_cast<int>(last.x) + maxspan - 1) >> 5, (int(ck.contig_len) - 1) >> 5);
             for (int wlo = wlo0; wlo <= whi; wlo += NWARP) {
                 // the word of this window that this warp owns: w == wid (mod NWARP)
                 const int w = wlo + ((int(wid) - wlo) & (NWARP - 1));
@@ -286,8 +258,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
                 uint32_t t2[5][2], t4[5][2], t8[5][2];
 #pragma unroll
                 for (int pr = 0; pr < 8; ++pr) {
-                    const Contrib xa = load_contrib(st, mt[(2 * pr) * 32 + lane], w32);
-                    const Contrib xb = load_contrib(st, mt[(2 * pr + 1) * 32 + lane], w32);
+                    const Contrib xa = load_contrib(tc, mt, (2 * pr) * 32 + lane, w32);
+                    const Contrib xb = load_contrib(tc, mt, (2 * pr + 1) * 32 + lane, w32);
 #pragma unroll
                     for (int k = 0; k < 5; ++k) {
                         Counter& c = acc.c[k];
@@ -306,7 +278,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
                     }
                 }
             }
-            __syncthreads();  // stage + meta[buf] free for reuse
+            __syncthreads();  // the stage may be overwritten by the copy issued at the top of the next iteration
         }
         if (cur_w != INT_MIN) flush_word(acc, cur_w, ck, a.counts);
     }
@@ -315,22 +287,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
 }  // namespace
 
 int launch_pileup_bitsliced(const PileupArgs& a, cudaStream_t stream) {
-    // stage capacity: TR rows of the largest row + alignment slack; rows too long for shared memory take the atomic path
+    // stage = TR rows of the largest row (+ alignment slack) + TR 16-byte records; rows too long for shared memory
+    // take the atomic path
     const uint32_t stage_words = ((TR * a.max_row_words + 8u) + 31u) & ~31u;
-    const size_t fixed = 2 * TR * sizeof(int2) + 2 * sizeof(TileInfo) + 4 * sizeof(uint64_t) + NWARP * sizeof(int) + 128;
-    const size_t s3 = 3 * size_t(stage_words) * 4 + fixed, s2 = 2 * size_t(stage_words) * 4 + fixed;
-    if (a.max_row_words >= 64 || (TR * a.max_row_words) > 0xffffu || s2 > 220 * 1024) return launch_pileup_atomic(a, stream);
+    const size_t stage_bytes = size_t(stage_words) * 4 + TR * sizeof(mmlst_prec);
+    const size_t smem = 2 * stage_bytes + 2 * sizeof(uint64_t) + 128;
+    if (a.max_row_words < 3 || smem > 220 * 1024) return launch_pileup_atomic(a, stream);
     const int sms = mmlst_num_sms();
-    if (s3 <= 110 * 1024) {
-        static bool set3 = false;
-        if (!set3) { cudaFuncSetAttribute(pileup_bitsliced_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); set3 = true; }
-        const uint32_t grid = a.n_chunks_dev ? uint32_t(sms * 2) : min(a.n_chunks, uint32_t(sms * 2));
-        pileup_bitsliced_kernel<3><<<grid, NTHREADS, s3, stream>>>(a, stage_words);
-    } else {
-        static bool set2 = false;
-        if (!set2) { cudaFuncSetAttribute(pileup_bitsliced_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); set2 = true; }
-        const uint32_t grid = a.n_chunks_dev ? uint32_t(sms) : min(a.n_chunks, uint32_t(sms));
-        pileup_bitsliced_kernel<2><<<grid, NTHREADS, s2, stream>>>(a, stage_words);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(pileup_bitsliced_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return mmlst_cuda_fail(e, "cudaFuncSetAttribute(pileup_bitsliced_kernel)");
+        configured = smem;
     }
+    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const uint32_t grid = a.n_chunks_dev ? uint32_t(sms * per_sm) : min(a.n_chunks, uint32_t(sms * per_sm));
+    pileup_bitsliced_kernel<2><<<grid, NTHREADS, smem, stream>>>(a, stage_words);
     return mmlst_cuda_fail(cudaGetLastError(), "pileup_bitsliced_kernel");
 }

@@ -142,6 +142,9 @@ __global__ void __launch_bounds__(1024) sel_finalize(const SelArgs a) {
         atomicAdd(&s_totrec, a.contig_start[tid + 1] - a.contig_start[tid]);
     }
     __syncthreads();
+    // per-locus chunk counts -> exclusive prefix (serial over <= 8192 loci), then all threads write the descriptors
+    uint32_t* s_cbase = sm + 3 * a.n_species;  // [n_loci + 1]
+    __shared__ uint32_t s_cr, s_nch, s_col;
     if (threadIdx.x == 0) {
         uint32_t cr = a.chunk_records;
         if (cr == 0) {  // same rule as mmlst_chunk_records(): >= 4 chunks per SM, whole 512-record tiles, <= 63 tiles
@@ -156,26 +159,32 @@ __global__ void __launch_bounds__(1024) sel_finalize(const SelArgs a) {
         for (uint32_t i = 0; i < s_n; ++i) {
             const uint32_t tid = a.chosen_tid[i];
             a.col_off[i] = col;
-            const unsigned long long r0 = a.contig_start[tid], r1 = a.contig_start[tid + 1];
-            const uint32_t len = a.ref_len[tid];
-            for (unsigned long long b = r0; b < r1; b += cr) {
-                if (nch < a.max_chunks) {
-                    mmlst_chunk ck;
-                    ck.rec_begin = static_cast<uint32_t>(b);
-                    ck.rec_end = static_cast<uint32_t>(b + cr < r1 ? b + cr : r1);
-                    ck.col_base = col; ck.contig_len = len; ck.plane_delta = 0;
-                    ck.reserved[0] = ck.reserved[1] = ck.reserved[2] = 0;
-                    a.chunks[nch] = ck;
-                } else {
-                    s_err |= 2u;
-                }
-                ++nch;
-            }
-            col += len;
+            s_cbase[i] = nch;
+            const unsigned long long nrec = a.contig_start[tid + 1] - a.contig_start[tid];
+            nch += static_cast<uint32_t>((nrec + cr - 1) / cr);
+            col += a.ref_len[tid];
         }
         a.col_off[s_n] = col;
-        a.header[0] = s_n; a.header[1] = nch < a.max_chunks ? nch : a.max_chunks; a.header[2] = col; a.header[3] = s_err; a.header[4] = cr;
+        s_cbase[s_n] = nch;
+        s_cr = cr; s_nch = nch; s_col = col;
+        if (nch > a.max_chunks) s_err |= 2u;
     }
+    __syncthreads();
+    const uint32_t nch = min(s_nch, a.max_chunks), cr = s_cr, nsel = s_n;
+    for (uint32_t c = threadIdx.x; c < nch; c += blockDim.x) {
+        uint32_t lo = 0, hi = nsel;  // last i with s_cbase[i] <= c
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_cbase[mid] <= c) lo = mid; else hi = mid; }
+        const uint32_t tid = a.chosen_tid[lo];
+        const unsigned long long r0 = a.contig_start[tid], r1 = a.contig_start[tid + 1];
+        const unsigned long long b = r0 + static_cast<unsigned long long>(c - s_cbase[lo]) * cr;
+        mmlst_chunk ck;
+        ck.rec_begin = static_cast<uint32_t>(b);
+        ck.rec_end = static_cast<uint32_t>(b + cr < r1 ? b + cr : r1);
+        ck.col_base = a.col_off[lo]; ck.contig_len = a.ref_len[tid]; ck.plane_delta = 0;
+        ck.reserved[0] = ck.reserved[1] = ck.reserved[2] = 0;
+        a.chunks[c] = ck;
+    }
+    if (threadIdx.x == 0) { a.header[0] = nsel; a.header[1] = nch; a.header[2] = s_col; a.header[3] = s_err; a.header[4] = cr; }
 }
 
 }  // namespace
@@ -222,7 +231,7 @@ extern "C" int mmlst_select_dev(const int64_t* sum_as, const uint32_t* n_hit, co
     sel_pass_a<<<grid, 256, 0, s>>>(a);
     sel_pass_b<<<grid, 256, 0, s>>>(a);
     sel_pass_c<<<grid, 256, 0, s>>>(a);
-    sel_finalize<<<1, 1024, 3 * sizeof(uint32_t) * n_species, s>>>(a);
+    sel_finalize<<<1, 1024, sizeof(uint32_t) * (3 * n_species + n_loci + 2), s>>>(a);
     CUDA_TRY(cudaGetLastError());
     return MMLST_OK;
 }

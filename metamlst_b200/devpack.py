@@ -74,9 +74,9 @@ class DeviceStreams:
         def h(t, dt):
             a = t.detach().cpu().numpy()
             return a.view(dt) if a.dtype != dt else a
+        recs = self.p_recs.detach().cpu().numpy().reshape(-1).view(packing.PREC_DTYPE)
         soa = packing.SoaHost(self.ref_names, self.ref_lens, h(self.tid, np.uint32), h(self.as0, np.int16), h(self.xm3, np.uint8),
-                              h(self.qlen, np.uint16), None, h(self.p_pos, np.int32), h(self.p_row_off, np.uint32),
-                              h(self.p_reflen, np.uint16), h(self.p_as, np.int16), h(self.p_xm, np.uint8), h(self.planes, np.uint32),
+                              h(self.qlen, np.uint16), None, recs, h(self.planes, np.uint32),
                               int(self.max_row_words), self.contig_start.copy(), self.minqual, self.max_depth, self.n_dropped)
         return soa.pin() if pinned else soa
 
@@ -126,15 +126,13 @@ def pack_cores(db, cores: List[dict], minqual: int = 20, max_depth: Optional[int
     s.n_dropped = int(n - int(adm.sum()))
     sel = order[adm]
     rd = read_of[sel]
-    s.p_pos = pos[sel].to(torch.int32)
-    s.p_reflen = reflen_r[rd].to(torch.int16)
-    s.p_as = AS[sel].to(torch.int16)
-    s.p_xm = xm[sel].clamp(0, 255).to(torch.uint8)
     rw = rw_r[rd]
     off = torch.zeros(sel.shape[0] + 1, dtype=torch.int64, device=dev)
     off[1:] = torch.cumsum(rw, 0)
     assert int(off[-1]) + packing.PLANE_SLACK_WORDS < (1 << 32)
-    s.p_row_off = off.to(torch.int32)  # bit pattern of uint32
+    # 16-byte mmlst_prec records as int32 [P, 4]: pos | row_off | reflen + (as_named << 16) | xm_named
+    s.p_recs = torch.stack([pos[sel], off[:-1], reflen_r[rd] | ((AS[sel] & 0xffff) << 16), xm[sel].clamp(0, 255)], dim=1).to(torch.int32).contiguous()
+    s.n_prec = int(sel.shape[0])
     rwmax = rows_r.shape[1]
     if bool((rw == rwmax).all()):
         body = rows_r[rd].reshape(-1)

@@ -22,7 +22,7 @@ class Chunk(C.Structure):
 class Soa(C.Structure):
     _fields_ = [("tid", C.c_void_p), ("as0", C.c_void_p), ("xm3", C.c_void_p), ("qlen", C.c_void_p), ("orig_idx", C.c_void_p),
                 ("n_rec", C.c_uint64),
-                ("p_pos", C.c_void_p), ("p_row_off", C.c_void_p), ("p_reflen", C.c_void_p), ("p_as", C.c_void_p), ("p_xm", C.c_void_p),
+                ("p_recs", C.c_void_p),
                 ("planes", C.c_void_p), ("n_prec", C.c_uint64), ("n_plane_words", C.c_uint64), ("max_row_words", C.c_uint32),
                 ("contig_start", C.c_void_p), ("n_ref", C.c_uint32)]
 
@@ -44,7 +44,7 @@ EXPORTS = {
     "mmlst_pinned_free": (None, [C.c_void_p]),
     "mmlst_score_dev": (C.c_int, [C.c_void_p] * 5 + [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "mmlst_pileup_dev": (C.c_int, [C.c_void_p] * 7 + [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_uint32,
+    "mmlst_pileup_dev": (C.c_int, [C.c_void_p] * 3 + [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_uint32,
                                    C.c_int, C.c_void_p]),
     "mmlst_consensus_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
@@ -56,7 +56,7 @@ EXPORTS = {
     "mmlst_select_dev": (C.c_int, [C.c_void_p] * 5 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t] + [C.c_void_p] * 6 +
                          [C.c_uint32, C.c_void_p]),
-    "mmlst_pileup_indirect_dev": (C.c_int, [C.c_void_p] * 8 + [C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "mmlst_pileup_indirect_dev": (C.c_int, [C.c_void_p] * 4 + [C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "mmlst_consensus_indirect_dev": (C.c_int, [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p]),
     "mmlst_chunk_records": (C.c_uint32, [C.c_uint64]),

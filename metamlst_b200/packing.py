@@ -20,6 +20,9 @@ BAM_FPROPER_PAIR = 0x2
 DEFAULT_MAX_DEPTH = 8000  # pysam pileup() default reaching cmseq/cmseq.py:527 (H1)
 DEFAULT_MINQUAL = 20  # metaMLST_functions.py:258
 PLANE_SLACK_WORDS = 8
+# mmlst_prec (include/mmlst.h): 16 bytes per pileup-stream record
+PREC_DTYPE = np.dtype([("pos", "<i4"), ("row_off", "<u4"), ("reflen", "<u2"), ("as_named", "<i2"), ("xm_named", "u1"), ("pad", "u1", (3,))])
+assert PREC_DTYPE.itemsize == 16
 
 
 @dataclass
@@ -34,12 +37,8 @@ class SoaHost:
     xm3: np.ndarray
     qlen: np.ndarray
     orig_idx: Optional[np.ndarray]
-    # pileup stream (mapped + admitted records, coordinate-sorted)
-    p_pos: np.ndarray
-    p_row_off: np.ndarray  # [P+1]
-    p_reflen: np.ndarray
-    p_as: np.ndarray
-    p_xm: np.ndarray
+    # pileup stream (mapped + admitted records, coordinate-sorted): 16-byte records + plane rows
+    p_recs: np.ndarray  # PREC_DTYPE [P]
     planes: np.ndarray
     max_row_words: int
     contig_start: np.ndarray  # uint64 [n_ref+1]
@@ -54,15 +53,29 @@ class SoaHost:
 
     @property
     def n_prec(self) -> int:
-        return int(self.p_pos.shape[0])
+        return int(self.p_recs.shape[0])
+
+    # column views of the records (tests / tools)
+    p_pos = property(lambda self: self.p_recs["pos"])
+    p_reflen = property(lambda self: self.p_recs["reflen"])
+    p_as = property(lambda self: self.p_recs["as_named"])
+    p_xm = property(lambda self: self.p_recs["xm_named"])
+
+    @property
+    def p_row_off(self) -> np.ndarray:
+        """[P+1] word offsets (last entry = end of the last row)."""
+        off = np.zeros(self.n_prec + 1, dtype=np.int64)
+        off[:-1] = self.p_recs["row_off"]
+        if self.n_prec:
+            off[-1] = int(off[-2]) + int(row_words(self.p_recs["reflen"][-1:])[0])
+        return off
 
     def c_struct(self) -> native.Soa:
         s = native.Soa()
         s.tid, s.as0, s.xm3, s.qlen = native.ptr(self.tid), native.ptr(self.as0), native.ptr(self.xm3), native.ptr(self.qlen)
         s.orig_idx = native.ptr(self.orig_idx)
         s.n_rec = self.n_rec
-        s.p_pos, s.p_row_off, s.p_reflen = native.ptr(self.p_pos), native.ptr(self.p_row_off), native.ptr(self.p_reflen)
-        s.p_as, s.p_xm, s.planes = native.ptr(self.p_as), native.ptr(self.p_xm), native.ptr(self.planes)
+        s.p_recs, s.planes = native.ptr(self.p_recs), native.ptr(self.planes)
         s.n_prec = self.n_prec
         s.n_plane_words = int(self.planes.shape[0])
         s.max_row_words = int(self.max_row_words)
@@ -75,7 +88,7 @@ class SoaHost:
         import torch
 
         keep = []
-        for name in ("tid", "as0", "xm3", "qlen", "orig_idx", "p_pos", "p_row_off", "p_reflen", "p_as", "p_xm", "planes"):
+        for name in ("tid", "as0", "xm3", "qlen", "orig_idx", "p_recs", "planes"):
             arr = getattr(self, name)
             if arr is None:
                 continue
@@ -218,8 +231,10 @@ def pack_table(tab, minqual: int = DEFAULT_MINQUAL, max_depth: Optional[int] = D
             planes[o + 2] = B0w[msk, j]
     n_ref = len(tab.ref_names)
     contig_start = np.searchsorted(tab.tid[sel], np.arange(n_ref + 1)).astype(np.uint64)
+    recs = np.zeros(P, dtype=PREC_DTYPE)
+    recs["pos"], recs["row_off"], recs["reflen"], recs["as_named"], recs["xm_named"] = p_pos, p_row_off[:-1], p_reflen, p_as, p_xm
     return SoaHost(list(tab.ref_names), np.asarray(tab.ref_lens, dtype=np.int32), tid, as0, xm3, qlen, orig_idx,
-                   p_pos, p_row_off.astype(np.uint32), p_reflen, p_as, p_xm, planes, int(rw.max()) if P else 0, contig_start,
+                   recs, planes, int(rw.max()) if P else 0, contig_start,
                    minqual, max_depth if max_depth is not None else 0, int((~adm).sum()))
 
 

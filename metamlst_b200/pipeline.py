@@ -86,7 +86,7 @@ class DevicePipeline:
         self.db_off_d = t32(np.asarray(db_off, dtype=np.int64))
         nl = index.n_loci
         self.scratch = torch.zeros(nl * 24 + 64, dtype=torch.uint8, device=dev)
-        self.max_chunks = int(streams.p_pos.shape[0]) // 512 + nl + 8
+        self.max_chunks = int(streams.n_prec) // 512 + nl + 8
         self.chunks_d = torch.zeros(self.max_chunks * 8, dtype=torch.int32, device=dev)
         # one int32 block for every small output: header[8] | chosen_tid[nl] | chosen_species[nl] | col_off[nl+1] | holes[nl] | snps[nl]
         self.o_hdr, self.o_tid, self.o_sp, self.o_col, self.o_holes, self.o_snps = 0, 8, 8 + nl, 8 + 2 * nl, 9 + 3 * nl, 9 + 4 * nl
@@ -166,8 +166,7 @@ class DevicePipeline:
         if chunks.shape[0]:
             chunks_d = torch.from_numpy(chunks.view(np.int32)).to(self.dev, non_blocking=True)
             def k():
-                native.check(self.lib.mmlst_pileup_dev(native.ptr(s.p_pos), native.ptr(s.p_row_off), native.ptr(s.p_reflen), native.ptr(s.p_as),
-                                                       native.ptr(s.p_xm), native.ptr(s.planes), native.ptr(chunks_d), int(chunks.shape[0]),
+                native.check(self.lib.mmlst_pileup_dev(native.ptr(s.p_recs), native.ptr(s.planes), native.ptr(chunks_d), int(chunks.shape[0]),
                                                        int(s.max_row_words), self.minscore, self.max_xM, native.ptr(self.counts), total,
                                                        self.impl, self._stream()))
             self._timed("pileup", k)
@@ -184,9 +183,9 @@ class DevicePipeline:
         snps = self.snps[: len(tids)].cpu().numpy()
         return [cons[col_off[i]:col_off[i + 1]].tobytes().decode("latin-1") for i in range(len(tids))], holes, snps, col_off
 
-    def step(self):
-        """One pass of the hot path, no host round trip between the stages: score -> [all-reduce] -> select (device) ->
-        pileup -> [all-reduce] -> consensus -> one D2H.  Returns {species: [(contig, consensus, holes, snps)]}."""
+    def _enqueue(self):
+        """Everything of one pass on the current stream, no host synchronisation: score -> [all-reduce] -> select ->
+        pileup -> [all-reduce] -> consensus -> D2H into pinned buffers."""
         self.run_score()
         sm, nl = self.small, self.index.n_loci
         base = sm.data_ptr()
@@ -203,8 +202,7 @@ class DevicePipeline:
         s = self.s
         self.counts.zero_()
         def k1():
-            native.check(self.lib.mmlst_pileup_indirect_dev(native.ptr(s.p_pos), native.ptr(s.p_row_off), native.ptr(s.p_reflen), native.ptr(s.p_as),
-                                                            native.ptr(s.p_xm), native.ptr(s.planes), native.ptr(self.chunks_d), base + 4 * self.o_hdr,
+            native.check(self.lib.mmlst_pileup_indirect_dev(native.ptr(s.p_recs), native.ptr(s.planes), native.ptr(self.chunks_d), base + 4 * self.o_hdr,
                                                             int(s.max_row_words), self.minscore, self.max_xM, native.ptr(self.counts), self.impl,
                                                             self._stream()))
         self._timed("pileup", k1)
@@ -220,7 +218,8 @@ class DevicePipeline:
         self.small_h.copy_(sm, non_blocking=True)
         self.cons_h.copy_(self.cons, non_blocking=True)
         self.counters_h.copy_(self.counters, non_blocking=True)
-        torch.cuda.current_stream(self.dev).synchronize()
+
+    def _finish(self):
         h = self.small_h.numpy()
         n = int(h[0])
         if h[3] & 1:
@@ -237,6 +236,32 @@ class DevicePipeline:
             out.setdefault(self.species_names[int(h[self.o_sp + i])], []).append(
                 (self.index.ref_names[int(tids[i])], cons[col[i]:col[i + 1]].tobytes().decode("latin-1"), int(h[self.o_holes + i]), int(h[self.o_snps + i])))
         return out
+
+    def step(self):
+        """One pass of the hot path, no host round trip between the stages.
+        Returns {species: [(contig, consensus, holes, snps)]} in the reference's dict order."""
+        self._enqueue()
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self._finish()
+
+    def capture(self):
+        """Record the pass once into a CUDA graph (one launch per step afterwards; kernels, memsets, NCCL calls and
+        the D2H copies are all graph nodes)."""
+        assert self.timers is None, "per-kernel timers are not capturable"
+        self._enqueue()  # warm-up outside capture (lazy attribute setting, NCCL channels)
+        torch.cuda.synchronize(self.dev)
+        n0 = self.launches
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue()
+        self.launches_per_step = self.launches - n0
+        self.launches = n0
+
+    def step_graph(self):
+        self.graph.replay()
+        self.launches += self.launches_per_step
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self._finish()
 
     def step_host_select(self):
         """Same pass with the selection done on the host in Python floats (cross-check of the device selection)."""

@@ -14,6 +14,7 @@ def test_devpack_equals_host_packer(L, maxd):
     want = packing.pack_table(tab, 20, maxd)
     got = devpack.pack_cores(db, [core], 20, maxd).to_host(pinned=False)
     assert want.orig_idx is None
+    assert got.p_recs.tobytes() == want.p_recs.tobytes()
     for f in ("tid", "as0", "xm3", "qlen", "p_pos", "p_row_off", "p_reflen", "p_as", "p_xm", "planes", "contig_start"):
         assert np.array_equal(getattr(got, f), getattr(want, f)), f
     assert got.max_row_words == want.max_row_words and got.n_dropped_by_cap == want.n_dropped_by_cap
