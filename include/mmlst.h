@@ -210,6 +210,39 @@ int mmlst_db_upload(mmlst_ctx* ctx, const uint32_t* db_hi, const uint32_t* db_lo
 int mmlst_hamming_min(mmlst_ctx* ctx, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
                       const uint32_t* blocks, uint32_t n_blocks, uint32_t* min_dist, uint32_t* argmin_row);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * BAM ingest (HOST, C++ threads + zlib).  Replaces the `samtools view -h -` text pipe of stage 1 (metamlst.py:96-110),
+ * pysam's record access of stage 2 (cmseq/cmseq.py:54,527-545) and `samtools sort` + `samtools index`
+ * (metaMLST_functions.py:237-247; the input file is never overwritten).  One pass: BGZF blocks inflated in
+ * parallel, records walked once, streams emitted in `samtools sort` order (stable by tid, pos, reverse strand) with
+ * the htslib depth cap applied.  Everything the reference would crash on is refused with MMLST_E_BAM and the
+ * reference line named in mmlst_last_error(): RNAME '*' (metamlst.py:107), 1st/4th aux field missing or not an
+ * integer (:109-110), a pileup record without integer AS/XM tags or without qualities (cmseq/cmseq.py:538,545);
+ * proper-pair mates are refused with MMLST_E_PAIRED (H2).
+ *   minqual       : pysam min_base_quality (20 at the only call site, metaMLST_functions.py:258)
+ *   max_depth     : pysam pileup max_depth (8000 default reaches cmseq unchanged); 0 = no cap
+ *   assume_sorted : metamlst.py --presorted -- keep the file order, MMLST_E_UNSORTED if it is not coordinate order
+ *   want_qhash    : also emit a 64-bit hash of QNAME per score-stream record (coverage column, H7)
+ * --------------------------------------------------------------------------------------------------------------- */
+typedef struct mmlst_bam mmlst_bam;
+typedef struct {
+    int minqual; uint32_t max_depth; uint32_t sentinel_nodes; int n_threads; int pinned; int assume_sorted;
+    int want_qhash; int check_crc;
+} mmlst_unpack_opts;
+typedef struct {
+    mmlst_soa soa;              /* pointers into memory owned by the mmlst_bam (page-locked when opts.pinned) */
+    const uint64_t* qhash;      /* [n_rec] or NULL */
+    const uint32_t* ref_len;    /* [n_ref] BAM header LN */
+    const char* ref_names;      /* n_ref names joined by '\n' */
+    const char* header_text;
+    uint64_t n_dropped_by_cap, n_unmapped_flag;
+    int presorted, minqual; uint32_t max_depth;
+    double seconds[5];          /* read, inflate, parse, sort, pack */
+} mmlst_bam_info_t;
+int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts /* NULL = defaults */, mmlst_bam** out);
+int mmlst_bam_info(const mmlst_bam* bam, mmlst_bam_info_t* info);
+void mmlst_bam_free(mmlst_bam* bam);
+
 #ifdef __cplusplus
 }
 #endif

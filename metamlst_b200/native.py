@@ -66,6 +66,9 @@ EXPORTS = {
     "mmlst_pileup_consensus": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmlst_db_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "mmlst_bam_unpack": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mmlst_bam_info": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mmlst_bam_free": (None, [C.c_void_p]),
     "mmlst_hamming_min": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                     C.c_void_p, C.c_void_p]),
 }

@@ -46,6 +46,9 @@ class SoaHost:
     max_depth: int = DEFAULT_MAX_DEPTH
     n_dropped_by_cap: int = 0
     _keep: tuple = ()
+    qhash: Optional[np.ndarray] = None  # u64 [n_rec] QNAME hash (coverage column, H7); None when not unpacked
+    header_text: str = ""
+    unpack_seconds: Optional[dict] = None
 
     @property
     def n_rec(self) -> int:
