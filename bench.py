@@ -44,12 +44,22 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip uncapped / hamming / cpu baseline extras")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay of the pass")
     ap.add_argument("--cpu-sample-reads", type=int, default=400_000)
+    ap.add_argument("--only-hamming", action="store_true", help="run only the configs[4] Hamming sweep (profiling aid)")
+    ap.add_argument("--max-depth", type=int, default=8000, help="htslib pileup depth cap of the main workload (0 = uncapped; profiling aid)")
     return ap.parse_args()
 
 
 ORGS = ("ecoli", "saureus", "kpneumoniae")
 PROPS = (0.5, 0.3, 0.2)
 PARAMS = dict(minscore=80, max_xM=5, min_read_len=50, penalty=100)
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
 
 
 def peaks():
@@ -204,7 +214,7 @@ def run_reference(args):
 def workload_config(args, world):
     return {"workload": "configs[1]: single sample, %d x %d bp reads, K=%d alignments/read (%d BAM records per GPU), coordinate-sorted; "
                         "E. coli + S. aureus + K. pneumoniae synthetic schemes, 21 loci x %d alleles" % (args.reads, args.read_len, args.k, args.reads * args.k, args.alleles),
-            "mode": "parity (htslib max_depth 8000, minqual 20, minscore 80, max_xM 5)",
+            "mode": ("parity (htslib max_depth %d, minqual 20, minscore 80, max_xM 5)" % args.max_depth) if args.max_depth else "uncapped (no depth cap; NOT the reference's semantics)",
             "sharding": "replica" if world == 1 else "contig-aligned: each rank owns the records of a disjoint locus set; all-reduce SUM(sum_as,n_hit,counts) MIN(first_idx)",
             "l2": "the 360 MB score stream exceeds the 126 MB L2 and is re-streamed every step (no flush needed)"}
 
@@ -226,12 +236,15 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
     native.lib()  # fail loudly if the CUDA library is missing
     peak, peak_src = peaks()
+    if args.only_hamming:
+        print(json.dumps({"hamming": extra_hamming(device, peak)}))
+        return
 
     db = make_db(args)
     index = api.AlleleIndex(db.ref_names())
     n_loci = len(db.locus_names)
     subset = None if world == 1 else [l for l in range(n_loci) if l % world == rank]
-    st, _ = gen_streams(db, args, device, 8000, subset, seed=1002 + rank)
+    st, _ = gen_streams(db, args, device, args.max_depth or None, subset, seed=1002 + rank)
     R_local = int(st.tid.shape[0])
     pipe = pipeline.DevicePipeline(st, index, db.row_seq, impl=args.pileup_impl, idx_base=rank * R_local, **PARAMS)
 
@@ -253,7 +266,8 @@ def main():
         except Exception as e:  # noqa: BLE001
             sys.stderr.write("CUDA graph capture unavailable (%r): timing the eager pass\n" % (e,))
             use_graph = False
-    stepfn = pipe.step_graph if use_graph else pipe.step
+    if not use_graph:
+        pipe.graph = None
     barrier()
     pipe.launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -261,35 +275,39 @@ def main():
     prof = bool(os.environ.get("MMLST_CUDA_PROFILER"))  # `ncu --profile-from-start off`: capture the timed steps only
     if prof:
         torch.cuda.profiler.start()
+    # K passes queued back to back (each one ends with its D2H into the pinned output block); the host parses the
+    # result after the timed region -- the way a cohort is typed.  Per-pass latency WITH a host sync is reported too.
     e0.record()
     for _ in range(args.steps):
-        out = stepfn()
+        pipe.enqueue_step()
     e1.record()
     barrier()
+    out = pipe.collect()
     if prof:
         torch.cuda.profiler.stop()
     clocks = sampler.stop()
     assert out == result, "results changed between steps"
     launches = pipe.launches
-    # per-kernel durations: CUDA events around each launch of the same pass, eager (events are not graph-capturable)
-    pipe.timers = {}
-    for _ in range(min(args.steps, 20)):
-        pipe.step()
+    # per-kernel durations: 20 back-to-back launches of each kernel of the same pass between two CUDA events on the
+    # launching stream (events are not graph-capturable; a single launch would carry the event/launch gap)
+    kms = pipe.time_kernels(20)
     torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        assert (pipe.step_graph() if use_graph else pipe.step()) == result
+    lat_ms = (time.perf_counter() - t0) / 10 * 1e3
     ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms], dtype=torch.float64, device=device)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms = float(t.item())
     R_total = R_local * world
-    kms = {k: float(np.mean(event_ms(v))) for k, v in pipe.timers.items()}
-    pipe.timers = None
     tids = [index.name_to_tid[c] for sp in out for (c, _s, _h, _n) in out[sp]]
     score_bytes = 9.0 * R_local
     pb, precs = pileup_alg_bytes(st, [t for t in tids if st.contig_start[t + 1] > st.contig_start[t]], args.read_len)
     rooflines = {
         "score": {"bound": "hbm", "achieved": score_bytes / kms["score"] / 1e6, "peak": peak, "unit": "GB/s", "frac": score_bytes / kms["score"] / 1e6 / peak,
-                  "traffic": None, "ms": kms["score"], "algorithmic_bytes": score_bytes},
+                  "traffic": ncu_traffic("score") if args.reads == 10_000_000 and args.k == 4 else None, "ms": kms["score"], "algorithmic_bytes": score_bytes},
         "pileup_parity": {"bound": "hbm", "achieved": pb / kms.get("pileup", float("inf")) / 1e6, "peak": peak, "unit": "GB/s",
                           "frac": pb / kms.get("pileup", float("inf")) / 1e6 / peak, "traffic": None, "ms": kms.get("pileup"),
                           "algorithmic_bytes": pb, "records": precs},
@@ -302,7 +320,7 @@ def main():
             "config": workload_config(args, world), "clocks": clocks, "gpu_launches": launches,
             "roofline": dict(rooflines[dominant], kernel=dominant, peak_source=peak_src), "rooflines": rooflines,
             "kernel_ms_per_step": kms, "records_per_gpu": R_local, "cuda_graph": use_graph,
-            "non_kernel_ms_per_step": ms - sum(kms.values())}
+            "non_kernel_ms_per_step": ms - sum(kms.values()), "latency_ms_per_step_with_host_sync": lat_ms}
 
     # ---- end to end through the host-buffer C-ABI (pinned host memory -> results on the host)
     soa = st.to_host(pinned=True)
@@ -354,7 +372,6 @@ def extra_uncapped(db, args, device, index, peak):
         pipe = pipeline.DevicePipeline(st, index, db.row_seq, impl=impl, **PARAMS)
         for _ in range(2):
             res = pipe.step()
-        pipe.timers = {}
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -368,10 +385,11 @@ def extra_uncapped(db, args, device, index, peak):
         assert res == out["_res"], "atomic and bit-sliced pileup disagree"
         tids = [index.name_to_tid[c] for sp in res for (c, _s, _h, _n) in res[sp]]
         pb, precs = pileup_alg_bytes(st, tids, args.read_len)
-        pms = float(np.mean(event_ms(pipe.timers["pileup"])))
+        pms = pipe.time_kernels(10 if impl == 2 else 2)["pileup"]
         out[name] = {"ms_per_step": e0.elapsed_time(e1) / n, "value": int(st.tid.shape[0]) / (e0.elapsed_time(e1) / n / 1e3), "unit": "records/s",
                      "pileup_ms": pms, "pileup_records": precs, "algorithmic_bytes": pb,
-                     "roofline": {"bound": "hbm", "achieved": pb / pms / 1e6, "peak": peak, "unit": "GB/s", "frac": pb / pms / 1e6 / peak, "traffic": None},
+                     "roofline": {"bound": "hbm", "achieved": pb / pms / 1e6, "peak": peak, "unit": "GB/s", "frac": pb / pms / 1e6 / peak,
+                                  "traffic": ncu_traffic("pileup_uncapped_" + name) if args.reads == 10_000_000 and args.k == 4 else None},
                      "increments_per_s": precs * args.read_len * 0.94 / (pms / 1e3)}
         del pipe
     del out["_res"]

@@ -19,13 +19,15 @@
  *                      optional orig_idx u32 (index in file order; NULL = identity + idx_base).        9 B / record
  *   pileup stream  : records ADMITTED by the htslib depth cap, coordinate-sorted, CIGAR already projected on the
  *                    reference: one 16-byte mmlst_prec per record {pos i32, row_off u32 (word offset into planes),
- *                    reflen u16, as_named i16, xm_named u8 (AS, XM by NAME)} -- array-of-16-byte-structs so that the
- *                    metadata of a 512-record tile is ONE contiguous 8 KB bulk copy -- and per record a row of 3
- *                    bit-planes x nw words
- *                    (nw = ceil(reflen/32)), word-interleaved [V_j, B1_j, B0_j], bit i of word j = reference offset
- *                    32 j + i:  V=1 -> ACGT base with quality >= minqual and code B1B0 (A=0,C=1,G=2,T=3);
+ *                    reflen u16, as_named i16, xm_named u8 (AS, XM by NAME), nw u16} -- array-of-16-byte-structs so
+ *                    that the metadata of a 512-record tile is ONE contiguous 8 KB bulk copy -- and per record a row
+ *                    of 3 bit-planes x nw words, ALIGNED TO THE CONTIG'S 32-COLUMN WORDS: nw = number of words the
+ *                    record touches = ((pos & 31) + reflen + 31) >> 5 (0 when reflen == 0); word-interleaved
+ *                    [V_j, B1_j, B0_j], bit i of word j = contig column 32 ((pos >> 5) + j) + i:
+ *                    V=1 -> ACGT base with quality >= minqual and code B1B0 (A=0,C=1,G=2,T=3);
  *                    V=0,B0=1 -> counted non-ACGT base (bin N); V=0,B0=0 -> not in the column (deletion, refskip,
- *                    quality < minqual, beyond the read).  Rows are padded to an odd number of words.
+ *                    quality < minqual, outside the read).  Rows are padded to an odd number of words (bank-conflict-
+ *                    free stride in shared memory).  Aligning at unpack time removes every shift from the kernel.
  *   count tensor   : u32 [total_columns][5], bins A,C,G,T,N.
  */
 #ifndef MMLST_H
@@ -38,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MMLST_VERSION 100
+#define MMLST_VERSION 101
 
 enum {
     MMLST_OK = 0,
@@ -99,7 +101,8 @@ typedef struct {
     uint16_t reflen;    /* reference span */
     int16_t as_named;   /* AS:i by NAME (cmseq tag filter, metaMLST_functions.py:259) */
     uint8_t xm_named;   /* XM:i by NAME, saturated at 255 */
-    uint8_t pad[3];
+    uint8_t pad;
+    uint16_t nw;        /* 32-column contig words touched by the record = plane words per plane in its row */
 } mmlst_prec;
 
 typedef struct {
@@ -142,23 +145,34 @@ int mmlst_consensus_dev(const uint32_t* counts, const uint8_t* dbseq, const uint
  * (maxLen, penalty, round(avg,1) -- computed exactly as integer tenths from the IEEE double quotient, H6), :184-206
  * (--nloci gate), :213-220 + :244 (alleles whose rounded average equals the locus maximum, lowest int(allele)), and the
  * dict-order bookkeeping of H5 (species by first passing record, loci inside a species by first passing record).
+ * ONE launch: CTA = locus (three in-CTA reductions, no global atomics), the last CTA to finish finalizes.
+ *   locus_rows[n_ref] = allele rows grouped by locus, locus_start[n_loci+1] = range of each locus in locus_rows
  *   allele_num[tid] = int(alleleVariant); species_of_locus[locus]; genes_in_db[species] = rows of `genes` (metamlst.py:184)
  *   contig_start / ref_len / db_off: pileup-stream record range, BAM LN and DB-sequence offset of every allele row
- *   scratch: >= 24*n_loci + 8 bytes.  Outputs: header[0]=n_chosen [1]=n_chunks [2]=total columns [3]=error bits
- *   (1: "Database is broken", 2: chunk list overflow) [4]=records per chunk; chosen_tid / chosen_species / col_off /
- *   db_start per chosen locus in output order; chunks for mmlst_pileup_indirect_dev.
+ *   scratch: >= 12*n_loci + 16 bytes, 8-byte aligned.  flags: MMLST_SELECT_CONSUME = the call resets what it has read
+ *   (sum_as / n_hit / first_idx of every hit row, counters) so the next pass needs no memset of the score tables;
+ *   MMLST_SELECT_SCRATCH_CLEAN = the caller zeroed the scratch once and every call since ran to completion (the
+ *   call leaves it zeroed), so the 4-byte ticket memset is skipped.
+ *   Outputs: header[0]=n_chosen [1]=n_chunks [2]=total columns [3]=error bits (1: "Database is broken", 2: chunk list
+ *   overflow) [4]=records per chunk [6,7]=counters[0] (totalReads) [8,9]=counters[1] (ignoredReads) when `counters` is
+ *   given; chosen_tid / chosen_species / col_off / db_start per chosen locus in output order; chunks for
+ *   mmlst_pileup_indirect_dev.  header needs 16 words.
  * --------------------------------------------------------------------------------------------------------------- */
-int mmlst_select_dev(const int64_t* sum_as, const uint32_t* n_hit, const uint32_t* first_idx, const uint32_t* locus_of,
+#define MMLST_SELECT_CONSUME 1u
+#define MMLST_SELECT_SCRATCH_CLEAN 2u
+int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, const uint32_t* locus_rows, const uint32_t* locus_start,
                      const uint32_t* allele_num, uint32_t n_ref, const uint32_t* species_of_locus, const uint32_t* genes_in_db,
                      uint32_t n_loci, uint32_t n_species, int penalty, int nloci_pct, const uint64_t* contig_start,
                      const uint32_t* ref_len, const uint64_t* db_off, uint32_t chunk_records, void* scratch, size_t scratch_bytes,
                      uint32_t* header, uint32_t* chosen_tid, uint32_t* chosen_species, uint32_t* col_off, uint64_t* db_start,
-                     mmlst_chunk* chunks, uint32_t max_chunks, void* stream);
+                     mmlst_chunk* chunks, uint32_t max_chunks, uint32_t flags, uint64_t* counters, void* stream);
 int mmlst_pileup_indirect_dev(const mmlst_prec* recs, const uint32_t* planes, const mmlst_chunk* chunks, const uint32_t* header,
                               uint32_t max_row_words, int minscore, int max_xm, uint32_t* counts, int impl, void* stream);
-int mmlst_consensus_indirect_dev(const uint32_t* counts, const uint8_t* db_ascii, const uint64_t* db_start, const uint32_t* col_off,
+/* flags: MMLST_CONSENSUS_CONSUME = zero every count that was read (the next pass accumulates from zero, no memset) */
+#define MMLST_CONSENSUS_CONSUME 1u
+int mmlst_consensus_indirect_dev(uint32_t* counts, const uint8_t* db_ascii, const uint64_t* db_start, const uint32_t* col_off,
                                  uint32_t max_loci, const uint32_t* header, uint32_t mincov, uint8_t* cons, uint32_t* holes,
-                                 uint32_t* snps, void* stream);
+                                 uint32_t* snps, uint32_t flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Stage 3 -- closest known allele by zip-truncated Hamming distance.  Replaces metaMLST_functions.py:230-234
@@ -230,7 +244,7 @@ typedef struct {
     int want_qhash; int check_crc;
 } mmlst_unpack_opts;
 typedef struct {
-    mmlst_soa soa;              /* pointers into memory owned by the mmlst_bam (page-locked when opts.pinned) */
+    mmlst_soa soa;              /* pointers into memory owned by the mmlst_bam handle, page-locked when opts.pinned */
     const uint64_t* qhash;      /* [n_rec] or NULL */
     const uint32_t* ref_len;    /* [n_ref] BAM header LN */
     const char* ref_names;      /* n_ref names joined by '\n' */

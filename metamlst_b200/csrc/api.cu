@@ -171,14 +171,11 @@ extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* al
 // ---------------------------------------------------------------------------------------------------------------
 static const uint32_t kMaxChunkRecords = 63 * 512;  // bit-sliced counters hold < 2^10 records per lane (pileup_bitsliced.cu)
 
-// Chunk length (records) for a launch over n_rec records: enough chunks to fill the chip (4 per SM), whole 512-record tiles.
+// Chunk length (records) for a launch over n_rec records: two chunks per SM (one resident wave of the bit-sliced kernel --
+// every (chunk, column word) pair costs one cross-lane flush, so chunks are as long as a full wave allows), whole
+// 512-record tiles.
 extern "C" uint32_t mmlst_chunk_records(uint64_t n_rec) {
-    const uint64_t target = (uint64_t)mmlst_num_sms() * 4;
-    uint64_t c = (n_rec + target - 1) / target;
-    c = ((c + 511) / 512) * 512;
-    if (c < 512) c = 512;
-    if (c > kMaxChunkRecords) c = kMaxChunkRecords;
-    return (uint32_t)c;
+    return 512u * mmlst_chunk_tiles(n_rec, (uint32_t)mmlst_num_sms() * MMLST_CHUNKS_PER_SM);
 }
 
 extern "C" int mmlst_pileup_dev(const mmlst_prec* recs, const uint32_t* planes, const mmlst_chunk* chunks, uint32_t n_chunks,
@@ -218,7 +215,7 @@ extern "C" int mmlst_pileup_consensus(mmlst_ctx* c, const mmlst_soa* soa, const 
     if (n_loci == 0) return MMLST_OK;
     cudaStream_t s = c->stream;
     // gather the chosen contigs' record / plane ranges (contiguous in the coordinate-sorted stream)
-    auto row_end = [&](uint64_t r) { return soa->p_recs[r].row_off + mmlst_row_words(soa->p_recs[r].reflen); };
+    auto row_end = [&](uint64_t r) { return soa->p_recs[r].row_off + mmlst_row_words(soa->p_recs[r].nw); };
     size_t n_rec = 0, n_words = 0;
     for (uint32_t l = 0; l < n_loci; ++l) {
         const uint32_t t = chosen_tid[l];

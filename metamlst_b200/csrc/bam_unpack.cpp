@@ -139,8 +139,9 @@ inline uint64_t hash64(const uint8_t* s, size_t n) {  // FNV-1a folded through a
     return h;
 }
 
-inline uint32_t row_words(uint32_t reflen) {
-    const uint32_t rw = 3u * ((reflen + 31u) >> 5);
+inline uint32_t touched_words(uint32_t pos, uint32_t reflen) { return reflen ? (((pos & 31u) + reflen + 31u) >> 5) : 0u; }
+inline uint32_t row_words(uint32_t nw) {  // 3 planes, padded to an odd word count
+    const uint32_t rw = 3u * nw;
     return rw + ((rw != 0u && (rw & 1u) == 0u) ? 1u : 0u);
 }
 
@@ -420,7 +421,8 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
     std::vector<uint64_t> rowoff(P + 1, 0);
     uint32_t maxrw = 0;
     for (size_t j = 0; j < P; ++j) {
-        const uint32_t rw = row_words(core[src(adm[j])].reflen);
+        const Core& cj = core[src(adm[j])];
+        const uint32_t rw = row_words(touched_words((uint32_t)cj.pos, cj.reflen));
         rowoff[j + 1] = rowoff[j] + rw;
         maxrw = std::max(maxrw, rw);
     }
@@ -453,10 +455,12 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
             const uint8_t* qual = seq + (l_seq + 1) / 2;
             mmlst_prec m;
             memset(&m, 0, sizeof(m));
+            const uint32_t nw = touched_words((uint32_t)c.pos, c.reflen);
             m.pos = c.pos; m.row_off = (uint32_t)rowoff[j]; m.reflen = (uint16_t)c.reflen; m.as_named = c.asn; m.xm_named = c.xmn;
+            m.nw = (uint16_t)nw;
             pr[j] = m;
             uint32_t* row = planes + rowoff[j];
-            const uint32_t rw = row_words(c.reflen);
+            const uint32_t rw = row_words(nw);
             for (uint32_t w = 0; w < rw; ++w) row[w] = 0;
             if (c.reflen == 0) continue;
             if (!c.named_ok) {
@@ -468,7 +472,7 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
                 err.set(MMLST_E_BAM, "%s: record %zu has no base qualities: query_qualities is None (TypeError at cmseq/cmseq.py:538)", path, i);
                 return;
             }
-            uint32_t x = 0, y = 0;  // reference offset, query index
+            uint32_t x = (uint32_t)c.pos & 31u, y = 0;  // column inside the row (rows are aligned to the contig's words), query index
             for (uint32_t k = 0; k < n_cig; ++k) {
                 const uint32_t cw = rd32(cig + 4 * k), op = cw & 15u, ln = cw >> 4;
                 if (op == 0 || op == 7 || op == 8) {

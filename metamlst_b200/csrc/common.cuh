@@ -8,6 +8,27 @@
 #include "../../include/mmlst.h"
 
 #define MMLST_NUM_SMS_DEFAULT 148
+#define MMLST_CHUNKS_PER_SM 2u  // resident CTAs per SM of the bit-sliced pileup kernel ("slots" = SMs x this)
+
+// Tiles (512 records) per pileup chunk for a launch over n_rec records on `slots` resident CTAs.  Every (chunk, column
+// word) pair costs one cross-lane flush, so chunks should be long; the static round-robin over slots wants the chunk
+// count to be a whole number of waves.  Pick the number of waves k (fewest first) whose chunk length
+// ceil(tiles / (k slots)) <= 8 tiles wastes the least of the last wave; short inputs get exactly one wave.
+__host__ __device__ inline uint32_t mmlst_chunk_tiles(unsigned long long n_rec, uint32_t slots) {
+    const unsigned long long tiles64 = (n_rec + 511ull) / 512ull;
+    if (tiles64 == 0 || slots == 0) return 1u;
+    if (tiles64 > 0x7fffffffull / 64ull) return 63u;
+    const uint32_t tiles = static_cast<uint32_t>(tiles64);  // 32-bit from here on: 64-bit division is a subroutine on the GPU
+    uint32_t kmin = (tiles + 8u * slots - 1u) / (8u * slots);  // fewest waves with chunks of <= 8 tiles
+    if (kmin == 0) kmin = 1;
+    uint32_t best_cr = (tiles + kmin * slots - 1u) / (kmin * slots), best_cost = kmin * best_cr;
+    for (uint32_t k = kmin + 1; k < kmin + 12; ++k) {
+        const uint32_t cr = (tiles + k * slots - 1u) / (k * slots);
+        if (cr < 2u) break;
+        if (k * cr < best_cost) { best_cost = k * cr; best_cr = cr; }  // makespan in tiles
+    }
+    return best_cr > 63u ? 63u : best_cr;
+}
 
 void mmlst_set_error(const char* fmt, ...);
 int mmlst_cuda_fail(cudaError_t e, const char* what);

@@ -4,7 +4,10 @@
 
 namespace {
 
-__global__ void __launch_bounds__(128) consensus_kernel(const uint32_t* __restrict__ counts, const uint8_t* __restrict__ dbseq,
+constexpr int CONS_THREADS = 512;  // one column per thread for MLST-sized loci: all loads of a locus in flight at once
+
+template <bool CONSUME>
+__global__ void __launch_bounds__(CONS_THREADS) consensus_kernel(uint32_t* __restrict__ counts, const uint8_t* __restrict__ dbseq,
                                                         const unsigned long long* __restrict__ db_start,
                                                         const uint32_t* __restrict__ col_off, const uint32_t* __restrict__ n_loci_dev,
                                                         uint32_t mincov, uint8_t* __restrict__ cons,
@@ -16,8 +19,9 @@ __global__ void __launch_bounds__(128) consensus_kernel(const uint32_t* __restri
     const uint8_t* db_base = db_start ? dbseq + db_start[locus] - c0 : dbseq;
     uint32_t h = 0, s = 0;
     for (uint32_t col = c0 + threadIdx.x; col < c1; col += blockDim.x) {
-        const uint32_t* c = counts + static_cast<size_t>(col) * 5;
+        uint32_t* c = counts + static_cast<size_t>(col) * 5;
         const uint32_t A = c[0], C = c[1], G = c[2], T = c[3], N = c[4];
+        if (CONSUME) { c[0] = 0; c[1] = 0; c[2] = 0; c[3] = 0; c[4] = 0; }  // the next pass accumulates from zero without a memset
         uint8_t call = 'N';
         if (A + C + G + T >= mincov && (A | C | G | T | N)) {
             // max(sorted(freq), key=freq.get): first maximum in the order A, C, G, N, T (H8)
@@ -49,19 +53,21 @@ extern "C" int mmlst_consensus_dev(const uint32_t* counts, const uint8_t* dbseq,
                                    uint32_t mincov, uint8_t* cons, uint32_t* holes, uint32_t* snps, void* stream) {
     if (n_loci == 0) return MMLST_OK;
     if (!counts || !dbseq || !col_off || !cons || !holes || !snps) { mmlst_set_error("mmlst_consensus_dev: null pointer"); return MMLST_E_ARG; }
-    consensus_kernel<<<n_loci, 128, 0, static_cast<cudaStream_t>(stream)>>>(counts, dbseq, nullptr, col_off, nullptr, mincov, cons, holes, snps);
+    consensus_kernel<false><<<n_loci, CONS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(const_cast<uint32_t*>(counts), dbseq, nullptr, col_off, nullptr, mincov, cons, holes, snps);
     CUDA_TRY(cudaGetLastError());
     return MMLST_OK;
 }
 
 // device-driven variant: n_loci and the DB offsets come from mmlst_select_dev (header[0], db_start)
-extern "C" int mmlst_consensus_indirect_dev(const uint32_t* counts, const uint8_t* db_ascii, const uint64_t* db_start,
+extern "C" int mmlst_consensus_indirect_dev(uint32_t* counts, const uint8_t* db_ascii, const uint64_t* db_start,
                                             const uint32_t* col_off, uint32_t max_loci, const uint32_t* header, uint32_t mincov,
-                                            uint8_t* cons, uint32_t* holes, uint32_t* snps, void* stream) {
+                                            uint8_t* cons, uint32_t* holes, uint32_t* snps, uint32_t flags, void* stream) {
     if (max_loci == 0) return MMLST_OK;
     if (!counts || !db_ascii || !db_start || !col_off || !header || !cons || !holes || !snps) { mmlst_set_error("mmlst_consensus_indirect_dev: null pointer"); return MMLST_E_ARG; }
-    consensus_kernel<<<max_loci, 128, 0, static_cast<cudaStream_t>(stream)>>>(counts, db_ascii, reinterpret_cast<const unsigned long long*>(db_start),
-                                                                            col_off, header, mincov, cons, holes, snps);
+    const unsigned long long* dbs = reinterpret_cast<const unsigned long long*>(db_start);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (flags & MMLST_CONSENSUS_CONSUME) consensus_kernel<true><<<max_loci, CONS_THREADS, 0, s>>>(counts, db_ascii, dbs, col_off, header, mincov, cons, holes, snps);
+    else consensus_kernel<false><<<max_loci, CONS_THREADS, 0, s>>>(counts, db_ascii, dbs, col_off, header, mincov, cons, holes, snps);
     CUDA_TRY(cudaGetLastError());
     return MMLST_OK;
 }

@@ -13,7 +13,11 @@ int launch_pileup_atomic(const PileupArgs& a, cudaStream_t stream);
 int launch_pileup_bitsliced(const PileupArgs& a, cudaStream_t stream);
 __device__ __forceinline__ uint32_t pileup_n_chunks(const PileupArgs& a) { return a.n_chunks_dev ? *a.n_chunks_dev : a.n_chunks; }
 
-__host__ __device__ __forceinline__ uint32_t mmlst_row_words(uint32_t reflen) {
-    const uint32_t rw = 3u * ((reflen + 31u) >> 5);
-    return rw + ((rw != 0u && (rw & 1u) == 0u) ? 1u : 0u);  // padded to an odd word count (0 stays 0)
+// words of a plane row for a record touching nw contig words: 3 planes, padded to an odd count (0 stays 0)
+__host__ __device__ __forceinline__ uint32_t mmlst_row_words(uint32_t nw) {
+    const uint32_t rw = 3u * nw;
+    return rw + ((rw != 0u && (rw & 1u) == 0u) ? 1u : 0u);
+}
+__host__ __device__ __forceinline__ uint32_t mmlst_touched_words(uint32_t pos, uint32_t reflen) {
+    return reflen ? (((pos & 31u) + reflen + 31u) >> 5) : 0u;
 }

@@ -19,14 +19,16 @@ __global__ void __launch_bounds__(256) pileup_atomic_kernel(const PileupArgs a) 
         const uint32_t off = pr.row_off + ck.plane_delta;
         const uint32_t rl = pr.reflen;
         const bool pass = (int(pr.as_named) >= a.minscore) && (int(pr.xm_named) <= a.max_xm);
-        const uint32_t nw = (rl + 31u) >> 5;
+        const uint32_t nw = pr.nw;  // contig words touched; rows are aligned to the contig's 32-column words
+        const long long col0 = static_cast<long long>(p >> 5) * 32;
+        (void)rl;
         for (uint32_t j = 0; j < nw; ++j) {
             const uint32_t v = a.planes[off + 3 * j + 0];
             const uint32_t b1 = a.planes[off + 3 * j + 1];
             const uint32_t b0 = a.planes[off + 3 * j + 2];
             const uint32_t vb = (v >> lane) & 1u, h = (b1 >> lane) & 1u, l = (b0 >> lane) & 1u;
             if (!(vb | l)) continue;  // not in the column
-            const long long col = static_cast<long long>(p) + 32 * j + lane;
+            const long long col = col0 + 32 * j + lane;
             if (col < 0 || col >= static_cast<long long>(ck.contig_len)) continue;
             const uint32_t bin = (vb && pass) ? (h * 2u + l) : 4u;
             atomicAdd(a.counts + (static_cast<size_t>(ck.col_base) + col) * 5 + bin, 1u);

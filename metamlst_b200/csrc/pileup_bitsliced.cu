@@ -11,13 +11,17 @@
 //              Their plane rows are ONE contiguous global range and their 16-byte records another, so a tile is two
 //              cp.async.bulk (TMA 1-D, SASS UBLKCP) into a double-buffered shared-memory stage, completion on one
 //              mbarrier; thread 0 issues tile t+1 before tile t is counted.  No per-thread global loads at all.
+//   prepass  : once per tile the 16-byte records are rewritten in place to what the inner loop needs
+//              {first contig word, row offset inside the stage, words touched, tag-filter mask}.
 //   warp     : owns one 32-column word w of the contig (w mod 8 == warp id inside the sliding 8-word window).
-//   lane     : takes records lane, lane+32, ... of the tile (16 per tile), funnel-shifts the record's planes to the
-//              word's alignment and adds five 1-bit planes (counted, ok, ok&B0, ok&B1, ok&B0&B1) into private
-//              bit-sliced counters: ones/twos/fours/eights by a 16-input Harley-Seal block (30 LOP3 per 16 inputs),
-//              the sixteens plane rippled into 6 upper planes once per tile.
-//   flush    : when the warp's word changes or the chunk ends: bit-sliced add across the 32 lanes (shuffle butterfly),
-//              lane i extracts column i, converts to A/C/G/T/N and issues 5 coalesced RED.ADD.
+//   lane     : takes records lane, lane+32, ... of the tile (16 per tile).  Rows are already aligned to the contig's
+//              words (include/mmlst.h), so a (record, word) pair costs 1 LDS.128 + 3 LDS, ~9 integer ops to form
+//              five 1-bit planes (counted, ok, ok&B0, ok&B1, ok&B0&B1) and a 16-input Harley-Seal block (30 LOP3
+//              per 16 inputs per counter) into private bit-sliced counters ones/twos/fours/eights, the sixteens
+//              plane rippled into 6 upper planes once per tile.
+//   flush    : when the warp's word changes or the chunk ends: bit-sliced add across the 32 lanes (shuffle butterfly
+//              over only as many planes as the tiles accumulated so far can have set), lane i extracts column i,
+//              converts to A/C/G/T/N and issues 5 coalesced RED.ADD.
 #include "common.cuh"
 #include "pileup.cuh"
 
@@ -79,53 +83,35 @@ __device__ __forceinline__ void ripple16(Counter& c, uint32_t x) {  // add the "
 
 struct Contrib { uint32_t x[5]; };  // counted, ok, ok&B0, ok&B1, ok&B0&B1
 
-struct TileCtx {
-    const uint32_t* planes;  // stage planes
-    uint32_t soff_base;      // plane_delta - a0 (mod 2^32): row_off + soff_base = word offset inside the stage
-    uint32_t cnt;            // records in the tile
-    int minscore, max_xm;
-};
-
-// planes of tile record i (16-byte mmlst_prec in shared memory) shifted to the alignment of the column word at w32
-__device__ __forceinline__ Contrib load_contrib(const TileCtx& tc, const uint4* __restrict__ meta, uint32_t i, int w32) {
+// planes of tile record i (rewritten 16-byte record in shared memory: {w0, stage row offset, nw, pm}) for contig word w
+__device__ __forceinline__ Contrib load_contrib(const uint32_t* __restrict__ planes, const uint4* __restrict__ meta, uint32_t i, int w) {
     const uint4 m = meta[i];
-    const int pos = static_cast<int>(m.x);
-    const uint32_t nw = ((m.z & 0xffffu) + 31u) >> 5;
-    const int as = static_cast<int>(m.z) >> 16;
-    const int xm = static_cast<int>(m.w & 0xffu);
-    const uint32_t pm = (as >= tc.minscore && xm <= tc.max_xm) ? FULL : 0u;
-    const int d = w32 - pos;
-    const int j0 = d >> 5;
-    const uint32_t s = static_cast<uint32_t>(d) & 31u;
-    const bool valid = i < tc.cnt;
-    const bool lo_ok = valid && (static_cast<uint32_t>(j0) < nw);
-    const bool hi_ok = valid && (static_cast<uint32_t>(j0 + 1) < nw);
-    const uint32_t* r = tc.planes + (m.y + tc.soff_base) + 3 * j0;
-    uint32_t vl = 0, hl = 0, ll = 0, vh = 0, hh = 0, lh = 0;
-    if (lo_ok) { vl = r[0]; hl = r[1]; ll = r[2]; }
-    if (hi_ok) { vh = r[3]; hh = r[4]; lh = r[5]; }
-    const uint32_t v = __funnelshift_r(vl, vh, s);
-    const uint32_t b1 = __funnelshift_r(hl, hh, s);
-    const uint32_t b0 = __funnelshift_r(ll, lh, s);
+    const uint32_t j = static_cast<uint32_t>(w - static_cast<int>(m.x));
+    const bool valid = j < m.z;                       // the record touches word w (records past the tile end have nw = 0)
+    const uint32_t* r = planes + (valid ? m.y + 3u * j : 0u);
+    const uint32_t vm = valid ? FULL : 0u;
+    const uint32_t v = r[0], b1 = r[1], b0 = r[2];
     Contrib c;
-    c.x[0] = v | b0;
-    c.x[1] = v & pm;
+    c.x[0] = (v | b0) & vm;
+    c.x[1] = v & m.w & vm;
     c.x[2] = c.x[1] & b0;
     c.x[3] = c.x[1] & b1;
     c.x[4] = c.x[2] & b1;
     return c;
 }
 
-// bit-sliced sum over the 32 lanes: every lane ends with the warp total in NPR planes
-__device__ __forceinline__ void reduce_lanes(const Counter& c, uint32_t (&t)[NPR]) {
+// bit-sliced sum over the 32 lanes of a counter whose planes >= P are still zero: every lane ends with the warp
+// total in P + 5 planes
+template <int P>
+__device__ __forceinline__ void reduce_lanes(const Counter& c, uint32_t (&t)[P + 5]) {
 #pragma unroll
-    for (int i = 0; i < NPR; ++i) t[i] = (i < NP) ? c.p[i] : 0u;
+    for (int i = 0; i < P + 5; ++i) t[i] = (i < P) ? c.p[i] : 0u;
 #pragma unroll
     for (int step = 0; step < 5; ++step) {
         uint32_t carry = 0;
 #pragma unroll
-        for (int i = 0; i < NPR; ++i) {
-            if (i <= NP + step) {  // planes that can be non-zero after this step
+        for (int i = 0; i < P + 5; ++i) {
+            if (i <= P + step) {  // planes that can be non-zero after this step
                 const uint32_t o = __shfl_xor_sync(FULL, t[i], 1 << step);
                 uint32_t hi, lo;
                 csa(hi, lo, t[i], o, carry);
@@ -136,10 +122,11 @@ __device__ __forceinline__ void reduce_lanes(const Counter& c, uint32_t (&t)[NPR
     }
 }
 
-__device__ __forceinline__ uint32_t extract(const uint32_t (&t)[NPR], uint32_t lane) {
+template <int N>
+__device__ __forceinline__ uint32_t extract(const uint32_t (&t)[N], uint32_t lane) {
     uint32_t v = 0;
 #pragma unroll
-    for (int i = 0; i < NPR; ++i) v |= ((t[i] >> lane) & 1u) << i;
+    for (int i = 0; i < N; ++i) v |= ((t[i] >> lane) & 1u) << i;
     return v;
 }
 
@@ -153,14 +140,15 @@ struct WarpAcc {
     }
 };
 
-__device__ __forceinline__ void flush_word(const WarpAcc& acc, int w, const mmlst_chunk& ck, uint32_t* __restrict__ counts) {
+template <int P>
+__device__ __forceinline__ void flush_word_p(const WarpAcc& acc, int w, const mmlst_chunk& ck, uint32_t* __restrict__ counts) {
     const uint32_t lane = threadIdx.x & 31u;
-    uint32_t t[NPR];
+    uint32_t t[P + 5];
     uint32_t n[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-        reduce_lanes(acc.c[k], t);
-        n[k] = extract(t, lane);
+        reduce_lanes<P>(acc.c[k], t);
+        n[k] = extract<P + 5>(t, lane);
     }
     const uint32_t n_cnt = n[0], n_ok = n[1], n_p0 = n[2], n_p1 = n[3], n_p01 = n[4];
     const long long col = static_cast<long long>(w) * 32 + lane;
@@ -174,12 +162,20 @@ __device__ __forceinline__ void flush_word(const WarpAcc& acc, int w, const mmls
     if (nN) atomicAdd(c + 4, nN);
 }
 
+// tiles = tiles accumulated since the counters were cleared: a lane counted <= 16 * tiles records
+__device__ __forceinline__ void flush_word(const WarpAcc& acc, int w, const mmlst_chunk& ck, uint32_t* __restrict__ counts, uint32_t tiles) {
+    if (tiles <= 3) flush_word_p<6>(acc, w, ck, counts);        // <= 48  < 2^6
+    else if (tiles <= 15) flush_word_p<8>(acc, w, ck, counts);  // <= 240 < 2^8
+    else flush_word_p<NP>(acc, w, ck, counts);                  // <= 1008 < 2^10
+}
+
 template <int NS>
 __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const PileupArgs a, const uint32_t stage_words) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // stage s: planes [stage_words] u32, then TR x 16-byte records
     const size_t stage_bytes = static_cast<size_t>(stage_words) * 4 + TR * sizeof(mmlst_prec);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + NS * stage_bytes);
+    uint4* loop_recs = reinterpret_cast<uint4*>(smem_raw + NS * stage_bytes);  // [2][TR], by tile parity
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + NS * stage_bytes + 2 * TR * sizeof(uint4));
 
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
@@ -189,7 +185,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
     }
     __syncthreads();
     uint32_t phase_bits = 0;  // parity per stage
-    const int maxspan = int(a.max_row_words / 3u) * 32;  // upper bound of any record's reference span
+    const int max_nw = int(a.max_row_words / 3u);  // upper bound of the contig words any record touches
 
     const uint32_t n_chunks = pileup_n_chunks(a);
     for (uint32_t ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
@@ -208,7 +204,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
             const uint32_t r0 = ck.rec_begin + t * TR;
             const uint32_t cnt = min(uint32_t(TR), ck.rec_end - r0);
             const uint32_t a0 = (g_first.y + ck.plane_delta) & ~3u;
-            const uint32_t w_end = g_last.y + ck.plane_delta + mmlst_row_words(g_last.z & 0xffffu);
+            const uint32_t w_end = g_last.y + ck.plane_delta + mmlst_row_words(g_last.w >> 16);
             const uint32_t pbytes = (((w_end + 3u) & ~3u) - a0) * 4u;
             const uint32_t mbytes = cnt * uint32_t(sizeof(mmlst_prec));
             uint8_t* st = smem_raw + stage * stage_bytes;
@@ -220,46 +216,67 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
         WarpAcc acc;
         acc.clear();
         int cur_w = INT_MIN;
+        uint32_t acc_tiles = 0;  // tiles folded into acc since the last clear
 
         if (threadIdx.x == 0) load_geo(0);
-        __syncthreads();  // every warp is done with the previous chunk's stages
+        __syncthreads();  // every warp is done with the previous chunk's stages and loop records
         if (threadIdx.x == 0) { issue_copy(0, 0); if (ntiles > 1) load_geo(1); }
 
         for (uint32_t t = 0; t < ntiles; ++t) {
             const int stage = t % NS;
-            if (threadIdx.x == 0 && t + 1 < ntiles) {  // stage (t+1)%NS was last read for tile t+1-NS: behind a barrier
-                issue_copy(t + 1, (t + 1) % NS);
-                if (t + 2 < ntiles) load_geo(t + 2);
-            }
             mbar_wait(bars + stage, (phase_bits >> stage) & 1u);
             phase_bits ^= 1u << stage;
 
             const uint8_t* st = smem_raw + stage * stage_bytes;
-            const uint4* mt = reinterpret_cast<const uint4*>(st + static_cast<size_t>(stage_words) * 4);
-            TileCtx tc;
-            tc.planes = reinterpret_cast<const uint32_t*>(st);
-            tc.cnt = min(uint32_t(TR), ck.rec_end - (ck.rec_begin + t * TR));
-            const uint4 first = mt[0], last = mt[tc.cnt - 1];
-            tc.soff_base = ck.plane_delta - ((first.y + ck.plane_delta) & ~3u);
-            tc.minscore = a.minscore; tc.max_xm = a.max_xm;
-            const int wlo0 = static_cast<int>(first.x) >> 5;  // sorted: the first record has the smallest pos
+            const uint4* raw = reinterpret_cast<const uint4*>(st + static_cast<size_t>(stage_words) * 4);
+            const uint32_t* planes = reinterpret_cast<const uint32_t*>(st);
+            uint4* mt = loop_recs + (t & 1u) * TR;
+            const uint32_t cnt = min(uint32_t(TR), ck.rec_end - (ck.rec_begin + t * TR));
+            // prepass: the tile's records in the form the inner loop wants, into the loop-record buffer of this parity
+            // {first contig word, row offset inside the stage, words touched, tag-filter mask}; nw = 0 past the tile end
+            {
+                const uint32_t soff_base = ck.plane_delta - ((raw[0].y + ck.plane_delta) & ~3u);
+#pragma unroll
+                for (uint32_t i = threadIdx.x; i < uint32_t(TR); i += NTHREADS) {
+                    uint4 m = make_uint4(0u, 0u, 0u, 0u);
+                    if (i < cnt) {
+                        const uint4 r = raw[i];
+                        const int as = static_cast<int>(r.z) >> 16;
+                        const int xm = static_cast<int>(r.w & 0xffu);
+                        m.x = static_cast<uint32_t>(static_cast<int>(r.x) >> 5);
+                        m.y = r.y + soff_base;
+                        m.z = r.w >> 16;
+                        m.w = (as >= a.minscore && xm <= a.max_xm) ? FULL : 0u;
+                    }
+                    mt[i] = m;
+                }
+            }
+            // the ONLY CTA-wide barrier of a tile: loop records visible, and every warp has finished tile t-1, so its
+            // stage and the other loop-record buffer may be overwritten
+            __syncthreads();
+            if (threadIdx.x == 0 && t + 1 < ntiles) {
+                issue_copy(t + 1, (t + 1) % NS);
+                if (t + 2 < ntiles) load_geo(t + 2);
+            }
+            const int wlo0 = static_cast<int>(mt[0].x);  // sorted: the first record has the smallest first word
             // last word any record of the tile can touch (span bound), clipped to the contig
-            const int whi = min((static_cast<int>(last.x) + maxspan - 1) >> 5, (int(ck.contig_len) - 1) >> 5);
+            const int whi = min(static_cast<int>(mt[cnt - 1].x) + max_nw - 1, (int(ck.contig_len) - 1) >> 5);
             for (int wlo = wlo0; wlo <= whi; wlo += NWARP) {
                 // the word of this window that this warp owns: w == wid (mod NWARP)
                 const int w = wlo + ((int(wid) - wlo) & (NWARP - 1));
                 if (w > whi) continue;
                 if (w != cur_w) {
-                    if (cur_w != INT_MIN) flush_word(acc, cur_w, ck, a.counts);
+                    if (cur_w != INT_MIN) flush_word(acc, cur_w, ck, a.counts, acc_tiles);
                     acc.clear();
                     cur_w = w;
+                    acc_tiles = 0;
                 }
-                const int w32 = w * 32;
+                ++acc_tiles;
                 uint32_t t2[5][2], t4[5][2], t8[5][2];
 #pragma unroll
                 for (int pr = 0; pr < 8; ++pr) {
-                    const Contrib xa = load_contrib(tc, mt, (2 * pr) * 32 + lane, w32);
-                    const Contrib xb = load_contrib(tc, mt, (2 * pr + 1) * 32 + lane, w32);
+                    const Contrib xa = load_contrib(planes, mt, (2 * pr) * 32 + lane, w);
+                    const Contrib xb = load_contrib(planes, mt, (2 * pr + 1) * 32 + lane, w);
 #pragma unroll
                     for (int k = 0; k < 5; ++k) {
                         Counter& c = acc.c[k];
@@ -278,9 +295,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
                     }
                 }
             }
-            __syncthreads();  // the stage may be overwritten by the copy issued at the top of the next iteration
         }
-        if (cur_w != INT_MIN) flush_word(acc, cur_w, ck, a.counts);
+        if (cur_w != INT_MIN) flush_word(acc, cur_w, ck, a.counts, acc_tiles);
     }
 }
 
@@ -291,7 +307,7 @@ int launch_pileup_bitsliced(const PileupArgs& a, cudaStream_t stream) {
     // take the atomic path
     const uint32_t stage_words = ((TR * a.max_row_words + 8u) + 31u) & ~31u;
     const size_t stage_bytes = size_t(stage_words) * 4 + TR * sizeof(mmlst_prec);
-    const size_t smem = 2 * stage_bytes + 2 * sizeof(uint64_t) + 128;
+    const size_t smem = 2 * stage_bytes + 2 * TR * sizeof(uint4) + 2 * sizeof(uint64_t) + 16;
     if (a.max_row_words < 3 || smem > 220 * 1024) return launch_pileup_atomic(a, stream);
     const int sms = mmlst_num_sms();
     static size_t configured = 0;
@@ -300,7 +316,7 @@ int launch_pileup_bitsliced(const PileupArgs& a, cudaStream_t stream) {
         if (e != cudaSuccess) return mmlst_cuda_fail(e, "cudaFuncSetAttribute(pileup_bitsliced_kernel)");
         configured = smem;
     }
-    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const int per_sm = smem <= 113 * 1024 ? int(MMLST_CHUNKS_PER_SM) : 1;  // 227 KB per SM, 1 KB reserved per CTA
     const uint32_t grid = a.n_chunks_dev ? uint32_t(sms * per_sm) : min(a.n_chunks, uint32_t(sms * per_sm));
     pileup_bitsliced_kernel<2><<<grid, NTHREADS, smem, stream>>>(a, stage_words);
     return mmlst_cuda_fail(cudaGetLastError(), "pileup_bitsliced_kernel");

@@ -41,72 +41,174 @@ __device__ __forceinline__ long long round_tenths(double x) {
 }
 
 struct SelArgs {
-    const long long* sum_as; const uint32_t* n_hit; const uint32_t* first_idx;
-    const uint32_t* locus_of; const uint32_t* allele_num; uint32_t n_ref;
+    long long* sum_as; uint32_t* n_hit; uint32_t* first_idx;
+    const uint32_t* locus_rows; const uint32_t* locus_start; const uint32_t* allele_num; uint32_t n_ref;
     const uint32_t* species_of_locus; const uint32_t* genes_in_db; uint32_t n_loci, n_species;
     int penalty, nloci_pct;
     const unsigned long long* contig_start; const uint32_t* ref_len; const unsigned long long* db_off;
-    uint32_t chunk_records, target_chunks;
-    // scratch
-    uint32_t* maxlen; unsigned long long* best_t; uint32_t* lfirst; unsigned long long* chosen_key;
+    uint32_t chunk_records, slots, flags;
+    unsigned long long* counters;
+    // scratch: per-locus results + the "CTAs done" ticket (left at zero by every call)
+    unsigned long long* res_key;  // (allele_num << 32 | row) of the chosen allele, ~0 = locus not detected
+    uint32_t* res_first;          // first passing record of the locus
+    uint32_t* done;
     // outputs
-    uint32_t* header;  // [0]=n_chosen [1]=n_chunks [2]=total_cols [3]=error flags [4]=chunk_records used
+    uint32_t* header;  // [0]=n_chosen [1]=n_chunks [2]=total_cols [3]=error flags [4]=chunk_records used [6..9]=counters
     uint32_t* chosen_tid; uint32_t* chosen_species; uint32_t* col_off; unsigned long long* db_start;
     mmlst_chunk* chunks; uint32_t max_chunks;
 };
 
-__global__ void sel_pass_a(const SelArgs a) {
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_ref; t += gridDim.x * blockDim.x) {
-        const uint32_t n = a.n_hit[t];
-        if (!n) continue;
-        const uint32_t l = a.locus_of[t];
-        atomicMax(a.maxlen + l, n);
-        atomicMin(a.lfirst + l, a.first_idx[t]);
-    }
-}
-
-__device__ __forceinline__ long long tenths_of(const SelArgs& a, uint32_t t, uint32_t n, uint32_t l) {
-    long long score = a.sum_as[t];
-    const uint32_t mx = a.maxlen[l];
-    if (n != mx) score -= static_cast<long long>(mx - n) * a.penalty;
+__device__ __forceinline__ long long tenths_of(long long score, uint32_t n, uint32_t mx, int penalty) {
+    if (n != mx) score -= static_cast<long long>(mx - n) * penalty;
     return round_tenths(__ddiv_rn(static_cast<double>(score), static_cast<double>(n)));
 }
 
-__global__ void sel_pass_b(const SelArgs a) {
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_ref; t += gridDim.x * blockDim.x) {
-        const uint32_t n = a.n_hit[t];
-        if (!n) continue;
-        const uint32_t l = a.locus_of[t];
-        atomicMax(a.best_t + l, static_cast<unsigned long long>(tenths_of(a, t, n, l)) + T_BIAS);
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_R = 4;  // rows per thread held in registers (1024 alleles per locus without a second trip to memory)
+
+// block-wide reductions over 256 threads (8 warps): warp REDUX / shuffles, then one shared-memory round
+__device__ __forceinline__ uint32_t block_max_u32(uint32_t v, uint32_t* sh) {
+    v = __reduce_max_sync(0xffffffffu, v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t r = sh[0];
+#pragma unroll
+    for (int i = 1; i < SEL_THREADS / 32; ++i) r = max(r, sh[i]);
+    return r;
+}
+__device__ __forceinline__ unsigned long long block_reduce_u64(unsigned long long v, unsigned long long* sh, bool want_max) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long x = __shfl_xor_sync(0xffffffffu, v, o);
+        v = want_max ? (x > v ? x : v) : (x < v ? x : v);
     }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long r = sh[0];
+#pragma unroll
+    for (int i = 1; i < SEL_THREADS / 32; ++i) { const unsigned long long x = sh[i]; r = want_max ? (x > r ? x : r) : (x < r ? x : r); }
+    return r;
 }
 
-__global__ void sel_pass_c(const SelArgs a) {
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_ref; t += gridDim.x * blockDim.x) {
-        const uint32_t n = a.n_hit[t];
-        if (!n) continue;
-        const uint32_t l = a.locus_of[t];
-        if (static_cast<unsigned long long>(tenths_of(a, t, n, l)) + T_BIAS == a.best_t[l])
-            atomicMin(a.chosen_key + l, (static_cast<unsigned long long>(a.allele_num[t]) << 32) | t);
+// ONE launch for the whole selection.  CTA = one locus: its allele rows (locus_rows[locus_start[l] .. locus_start[l+1]))
+// are reduced three times inside the CTA (max hit count -> max rounded average -> lowest allele number), no global
+// atomics and no grid barrier.  The last CTA to finish (ticket counter) applies the --nloci gate, orders species and
+// loci (H5), lays out the columns and writes the pileup chunk descriptors.
+__global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
+    extern __shared__ __align__(8) uint32_t sm[];
+    __shared__ unsigned long long sh64[SEL_THREADS / 32];
+    __shared__ uint32_t sh32[SEL_THREADS / 32];
+    __shared__ uint32_t s_last;
+    const uint32_t l = blockIdx.x;
+    const uint32_t r0 = a.locus_start[l], r1 = a.locus_start[l + 1];
+    // The first SEL_R x 256 rows of the locus live in registers: ONE round of independent loads (row id, then hit count /
+    // score sum / first index / allele number together), after which the three passes are register arithmetic.  Loci
+    // with more rows run the same passes over the remainder from global memory.
+    uint32_t tt[SEL_R], nn[SEL_R], an[SEL_R], ff[SEL_R];
+    long long ss[SEL_R];
+#pragma unroll
+    for (int k = 0; k < SEL_R; ++k) {
+        const uint32_t i = r0 + k * SEL_THREADS + threadIdx.x;
+        tt[k] = (i < r1) ? a.locus_rows[i] : 0xffffffffu;
     }
-}
+#pragma unroll
+    for (int k = 0; k < SEL_R; ++k) {
+        const bool v = tt[k] != 0xffffffffu;
+        nn[k] = v ? a.n_hit[tt[k]] : 0u;
+        ss[k] = v ? a.sum_as[tt[k]] : 0ll;
+        ff[k] = v ? a.first_idx[tt[k]] : 0xffffffffu;
+        an[k] = v ? a.allele_num[tt[k]] : 0u;
+    }
+    const uint32_t rest0 = r0 + SEL_R * SEL_THREADS + threadIdx.x;  // rows beyond the register window
+    // pass 1: per-locus max hit count and first passing record
+    uint32_t mx = 0, fmin = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < SEL_R; ++k)
+        if (nn[k]) { mx = max(mx, nn[k]); fmin = min(fmin, ff[k]); }
+    for (uint32_t i = rest0; i < r1; i += SEL_THREADS) {
+        const uint32_t t = a.locus_rows[i];
+        const uint32_t n = a.n_hit[t];
+        if (n) { mx = max(mx, n); fmin = min(fmin, a.first_idx[t]); }
+    }
+    mx = block_max_u32(mx, sh32);
+    if (mx) {  // CTA-uniform
+        const uint32_t nfmax = block_max_u32(~fmin, sh32);
+        // pass 2: maximum rounded average (integer tenths)
+        unsigned long long best = 0, tk[SEL_R];
+#pragma unroll
+        for (int k = 0; k < SEL_R; ++k) {
+            tk[k] = nn[k] ? static_cast<unsigned long long>(tenths_of(ss[k], nn[k], mx, a.penalty)) + T_BIAS : 0ull;
+            best = tk[k] > best ? tk[k] : best;
+        }
+        for (uint32_t i = rest0; i < r1; i += SEL_THREADS) {
+            const uint32_t t = a.locus_rows[i];
+            const uint32_t n = a.n_hit[t];
+            if (n) { const unsigned long long v = static_cast<unsigned long long>(tenths_of(a.sum_as[t], n, mx, a.penalty)) + T_BIAS; best = v > best ? v : best; }
+        }
+        best = block_reduce_u64(best, sh64, true);
+        // pass 3: lowest allele number among the alleles that reach it (then lowest row)
+        unsigned long long key = ~0ull;
+#pragma unroll
+        for (int k = 0; k < SEL_R; ++k) {
+            if (!nn[k]) continue;
+            if (tk[k] == best) {
+                const unsigned long long kk = (static_cast<unsigned long long>(an[k]) << 32) | tt[k];
+                key = kk < key ? kk : key;
+            }
+            if (a.flags & MMLST_SELECT_CONSUME) { a.sum_as[tt[k]] = 0; a.n_hit[tt[k]] = 0; a.first_idx[tt[k]] = 0xffffffffu; }
+        }
+        for (uint32_t i = rest0; i < r1; i += SEL_THREADS) {
+            const uint32_t t = a.locus_rows[i];
+            const uint32_t n = a.n_hit[t];
+            if (!n) continue;
+            if (static_cast<unsigned long long>(tenths_of(a.sum_as[t], n, mx, a.penalty)) + T_BIAS == best) {
+                const unsigned long long k = (static_cast<unsigned long long>(a.allele_num[t]) << 32) | t;
+                key = k < key ? k : key;
+            }
+            if (a.flags & MMLST_SELECT_CONSUME) { a.sum_as[t] = 0; a.n_hit[t] = 0; a.first_idx[t] = 0xffffffffu; }
+        }
+        key = block_reduce_u64(key, sh64, false);
+        if (threadIdx.x == 0) { a.res_key[l] = key; a.res_first[l] = ~nfmax; }
+    } else if (threadIdx.x == 0) {
+        a.res_key[l] = ~0ull; a.res_first[l] = 0xffffffffu;
+    }
+    // ticket: the last CTA finalizes
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(a.done, 1u) == gridDim.x - 1u);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
 
-// one CTA: nloci gate, H5 ordering, column offsets, chunk descriptors
-__global__ void __launch_bounds__(1024) sel_finalize(const SelArgs a) {
-    extern __shared__ uint32_t sm[];
-    uint32_t* s_detected = sm;                       // [n_species]
-    uint32_t* s_first = sm + a.n_species;            // [n_species]
-    uint32_t* s_pass = sm + 2 * a.n_species;         // [n_species]
-    __shared__ uint32_t s_n, s_err;
+    // ---- last CTA: finalize
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(sm);   // [n_loci] order key of kept loci, 0 = not kept
+    uint32_t* s_tid = sm + 2 * a.n_loci;                                     // [n_loci] chosen row of the locus
+    uint32_t* s_cbase = s_tid + a.n_loci;                                    // [n_loci + 1]
+    uint32_t* s_len = s_cbase + a.n_loci + 1;                                // [n_loci] BAM LN of chosen rows, output order
+    uint32_t* s_nch = s_len + a.n_loci;                                      // [n_loci] chunks of chosen rows, output order
+    uint32_t* s_lfirst = s_nch + a.n_loci;                                   // [n_loci]
+    uint32_t* s_detected = s_lfirst + a.n_loci;                              // [n_species]
+    uint32_t* s_first = s_detected + a.n_species;                            // [n_species]
+    uint32_t* s_pass = s_first + a.n_species;                                // [n_species]
+    __shared__ uint32_t s_n, s_err, s_cr, s_totch, s_col;
     __shared__ unsigned long long s_totrec;
     for (uint32_t i = threadIdx.x; i < a.n_species; i += blockDim.x) { s_detected[i] = 0; s_first[i] = 0xffffffffu; }
-    if (threadIdx.x == 0) { s_n = 0; s_err = 0; s_totrec = 0; }
+    if (threadIdx.x == 0) { s_n = 0; s_err = 0; s_totrec = 0; *a.done = 0; }
     __syncthreads();
-    for (uint32_t l = threadIdx.x; l < a.n_loci; l += blockDim.x) {
-        if (a.chosen_key[l] != ~0ull) {
-            const uint32_t sp = a.species_of_locus[l];
+    for (uint32_t m = threadIdx.x; m < a.n_loci; m += blockDim.x) {
+        const unsigned long long ck = __ldcg(a.res_key + m);
+        const uint32_t lf = __ldcg(a.res_first + m);
+        s_tid[m] = static_cast<uint32_t>(ck & 0xffffffffull);
+        s_lfirst[m] = lf;
+        s_key[m] = (ck != ~0ull) ? 1ull : 0ull;  // provisional: detected
+        if (ck != ~0ull) {
+            const uint32_t sp = a.species_of_locus[m];
             atomicAdd(s_detected + sp, 1u);
-            atomicMin(s_first + sp, a.lfirst[l]);
+            atomicMin(s_first + sp, lf);
         }
     }
     __syncthreads();
@@ -120,118 +222,132 @@ __global__ void __launch_bounds__(1024) sel_finalize(const SelArgs a) {
         s_pass[sp] = pass;
     }
     __syncthreads();
-    // rank of every kept locus by (species first record, locus first record)
-    for (uint32_t l = threadIdx.x; l < a.n_loci; l += blockDim.x) {
-        if (a.chosen_key[l] == ~0ull) continue;
-        const uint32_t sp = a.species_of_locus[l];
-        if (!s_pass[sp]) continue;
-        const unsigned long long key = (static_cast<unsigned long long>(s_first[sp]) << 32) | a.lfirst[l];
-        uint32_t rank = 0;
-        for (uint32_t m = 0; m < a.n_loci; ++m) {
-            if (a.chosen_key[m] == ~0ull) continue;
-            const uint32_t sp2 = a.species_of_locus[m];
-            if (!s_pass[sp2]) continue;
-            const unsigned long long k2 = (static_cast<unsigned long long>(s_first[sp2]) << 32) | a.lfirst[m];
-            rank += (k2 < key) || (k2 == key && m < l);
+    // order key of every kept locus: (species first record, locus first record) + 1 so that 0 means "not kept"
+    for (uint32_t m = threadIdx.x; m < a.n_loci; m += blockDim.x) {
+        unsigned long long key = 0;
+        if (s_key[m]) {
+            const uint32_t sp = a.species_of_locus[m];
+            if (s_pass[sp]) { key = ((static_cast<unsigned long long>(s_first[sp]) << 32) | s_lfirst[m]) + 1ull; atomicAdd(&s_n, 1u); }
         }
-        const uint32_t tid = static_cast<uint32_t>(a.chosen_key[l] & 0xffffffffu);
-        a.chosen_tid[rank] = tid;
-        a.chosen_species[rank] = sp;
-        a.db_start[rank] = a.db_off[tid];
-        atomicAdd(&s_n, 1u);
-        atomicAdd(&s_totrec, a.contig_start[tid + 1] - a.contig_start[tid]);
+        s_key[m] = key;
     }
     __syncthreads();
-    // per-locus chunk counts -> exclusive prefix (serial over <= 8192 loci), then all threads write the descriptors
-    uint32_t* s_cbase = sm + 3 * a.n_species;  // [n_loci + 1]
-    __shared__ uint32_t s_cr, s_nch, s_col;
+    for (uint32_t m = threadIdx.x; m < a.n_loci; m += blockDim.x) {
+        const unsigned long long key = s_key[m];
+        if (!key) continue;
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < a.n_loci; ++j) {
+            const unsigned long long k2 = s_key[j];
+            rank += (k2 != 0ull) && ((k2 < key) || (k2 == key && j < m));
+        }
+        const uint32_t tid = s_tid[m];
+        const unsigned long long nrec = a.contig_start[tid + 1] - a.contig_start[tid];
+        a.chosen_tid[rank] = tid;
+        a.chosen_species[rank] = a.species_of_locus[m];
+        a.db_start[rank] = a.db_off[tid];
+        s_len[rank] = a.ref_len[tid];
+        s_cbase[rank] = tid;  // parked here until the chunk size is known
+        atomicAdd(&s_totrec, nrec);
+    }
+    __syncthreads();
+    const uint32_t nsel = s_n;
     if (threadIdx.x == 0) {
         uint32_t cr = a.chunk_records;
-        if (cr == 0) {  // same rule as mmlst_chunk_records(): >= 4 chunks per SM, whole 512-record tiles, <= 63 tiles
-            const unsigned long long target = a.target_chunks;
-            unsigned long long c = (s_totrec + target - 1) / target;
-            c = ((c + 511ull) / 512ull) * 512ull;
-            if (c < 512ull) c = 512ull;
-            if (c > 63ull * 512ull) c = 63ull * 512ull;
-            cr = static_cast<uint32_t>(c);
-        }
-        uint32_t col = 0, nch = 0;
-        for (uint32_t i = 0; i < s_n; ++i) {
-            const uint32_t tid = a.chosen_tid[i];
-            a.col_off[i] = col;
-            s_cbase[i] = nch;
-            const unsigned long long nrec = a.contig_start[tid + 1] - a.contig_start[tid];
-            nch += static_cast<uint32_t>((nrec + cr - 1) / cr);
-            col += a.ref_len[tid];
-        }
-        a.col_off[s_n] = col;
-        s_cbase[s_n] = nch;
-        s_cr = cr; s_nch = nch; s_col = col;
-        if (nch > a.max_chunks) s_err |= 2u;
+        if (cr == 0) cr = 512u * mmlst_chunk_tiles(s_totrec, a.slots);  // same rule as mmlst_chunk_records()
+        s_cr = cr;
     }
     __syncthreads();
-    const uint32_t nch = min(s_nch, a.max_chunks), cr = s_cr, nsel = s_n;
+    const uint32_t cr = s_cr;
+    for (uint32_t i = threadIdx.x; i < nsel; i += blockDim.x) {
+        const uint32_t tid = s_cbase[i];
+        const unsigned long long nrec = a.contig_start[tid + 1] - a.contig_start[tid];
+        s_nch[i] = static_cast<uint32_t>((nrec + cr - 1) / cr);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // exclusive prefixes over shared memory (no dependent global loads)
+        uint32_t col = 0, nch = 0;
+        for (uint32_t i = 0; i < nsel; ++i) {
+            a.col_off[i] = col;
+            const uint32_t k = s_nch[i];
+            s_nch[i] = s_cbase[i];  // keep the row id
+            s_cbase[i] = nch;
+            nch += k;
+            col += s_len[i];
+        }
+        a.col_off[nsel] = col;
+        s_cbase[nsel] = nch;
+        s_totch = nch; s_col = col;
+        if (nch > a.max_chunks) s_err |= 2u;
+        a.header[0] = nsel; a.header[1] = min(nch, a.max_chunks); a.header[2] = col; a.header[3] = s_err; a.header[4] = cr;
+        if (a.counters) {  // totalReads / ignoredReads travel with the header; consumed like the tables
+            const unsigned long long c0 = a.counters[0], c1 = a.counters[1];
+            a.header[6] = static_cast<uint32_t>(c0); a.header[7] = static_cast<uint32_t>(c0 >> 32);
+            a.header[8] = static_cast<uint32_t>(c1); a.header[9] = static_cast<uint32_t>(c1 >> 32);
+            if (a.flags & MMLST_SELECT_CONSUME) { a.counters[0] = 0; a.counters[1] = 0; }
+        }
+    }
+    __syncthreads();
+    const uint32_t nch = min(s_totch, a.max_chunks);
     for (uint32_t c = threadIdx.x; c < nch; c += blockDim.x) {
         uint32_t lo = 0, hi = nsel;  // last i with s_cbase[i] <= c
         while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_cbase[mid] <= c) lo = mid; else hi = mid; }
-        const uint32_t tid = a.chosen_tid[lo];
-        const unsigned long long r0 = a.contig_start[tid], r1 = a.contig_start[tid + 1];
-        const unsigned long long b = r0 + static_cast<unsigned long long>(c - s_cbase[lo]) * cr;
+        const uint32_t tid = s_nch[lo];
+        const unsigned long long q0 = a.contig_start[tid], q1 = a.contig_start[tid + 1];
+        const unsigned long long b = q0 + static_cast<unsigned long long>(c - s_cbase[lo]) * cr;
         mmlst_chunk ck;
         ck.rec_begin = static_cast<uint32_t>(b);
-        ck.rec_end = static_cast<uint32_t>(b + cr < r1 ? b + cr : r1);
-        ck.col_base = a.col_off[lo]; ck.contig_len = a.ref_len[tid]; ck.plane_delta = 0;
+        ck.rec_end = static_cast<uint32_t>(b + cr < q1 ? b + cr : q1);
+        ck.col_base = a.col_off[lo]; ck.contig_len = s_len[lo]; ck.plane_delta = 0;
         ck.reserved[0] = ck.reserved[1] = ck.reserved[2] = 0;
         a.chunks[c] = ck;
     }
-    if (threadIdx.x == 0) { a.header[0] = nsel; a.header[1] = nch; a.header[2] = s_col; a.header[3] = s_err; a.header[4] = cr; }
 }
 
 }  // namespace
 
 // see include/mmlst.h
-extern "C" int mmlst_select_dev(const int64_t* sum_as, const uint32_t* n_hit, const uint32_t* first_idx, const uint32_t* locus_of,
-                                const uint32_t* allele_num, uint32_t n_ref, const uint32_t* species_of_locus,
-                                const uint32_t* genes_in_db, uint32_t n_loci, uint32_t n_species, int penalty, int nloci_pct,
-                                const uint64_t* contig_start, const uint32_t* ref_len, const uint64_t* db_off,
-                                uint32_t chunk_records, void* scratch, size_t scratch_bytes, uint32_t* header,
-                                uint32_t* chosen_tid, uint32_t* chosen_species, uint32_t* col_off, uint64_t* db_start,
-                                mmlst_chunk* chunks, uint32_t max_chunks, void* stream) {
-    if (!sum_as || !n_hit || !first_idx || !locus_of || !allele_num || !species_of_locus || !genes_in_db || !contig_start || !ref_len ||
-        !db_off || !scratch || !header || !chosen_tid || !chosen_species || !col_off || !db_start || !chunks) {
+extern "C" int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, const uint32_t* locus_rows,
+                                const uint32_t* locus_start, const uint32_t* allele_num, uint32_t n_ref,
+                                const uint32_t* species_of_locus, const uint32_t* genes_in_db, uint32_t n_loci, uint32_t n_species,
+                                int penalty, int nloci_pct, const uint64_t* contig_start, const uint32_t* ref_len,
+                                const uint64_t* db_off, uint32_t chunk_records, void* scratch, size_t scratch_bytes,
+                                uint32_t* header, uint32_t* chosen_tid, uint32_t* chosen_species, uint32_t* col_off,
+                                uint64_t* db_start, mmlst_chunk* chunks, uint32_t max_chunks, uint32_t flags,
+                                uint64_t* counters, void* stream) {
+    if (!sum_as || !n_hit || !first_idx || !locus_rows || !locus_start || !allele_num || !species_of_locus || !genes_in_db ||
+        !contig_start || !ref_len || !db_off || !scratch || !header || !chosen_tid || !chosen_species || !col_off || !db_start || !chunks) {
         mmlst_set_error("mmlst_select_dev: null pointer");
         return MMLST_E_ARG;
     }
+    if (n_loci == 0) { mmlst_set_error("mmlst_select_dev: no loci"); return MMLST_E_ARG; }
     if (n_loci > 8192 || n_species > 4096) { mmlst_set_error("mmlst_select_dev: more than 8192 loci / 4096 species"); return MMLST_E_RANGE; }
-    const size_t need = static_cast<size_t>(n_loci) * 24 + 8;
+    const size_t need = static_cast<size_t>(n_loci) * 12 + 16;
     if (scratch_bytes < need || (reinterpret_cast<uintptr_t>(scratch) & 7)) { mmlst_set_error("mmlst_select_dev: scratch needs %zu bytes, 8-byte aligned", need); return MMLST_E_ARG; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    // scratch layout: best_t u64[n_loci] | maxlen u32[n_loci]  (zeroed)  ||  chosen_key u64[n_loci] | lfirst u32[n_loci] (0xff)
+    // scratch layout: res_key u64[n_loci] | res_first u32[n_loci] | (pad to 8) done u32
     uint8_t* p = static_cast<uint8_t*>(scratch);
     SelArgs a;
-    a.sum_as = reinterpret_cast<const long long*>(sum_as); a.n_hit = n_hit; a.first_idx = first_idx; a.locus_of = locus_of;
+    a.sum_as = reinterpret_cast<long long*>(sum_as); a.n_hit = n_hit; a.first_idx = first_idx;
+    a.locus_rows = locus_rows; a.locus_start = locus_start;
     a.allele_num = allele_num; a.n_ref = n_ref; a.species_of_locus = species_of_locus; a.genes_in_db = genes_in_db;
     a.n_loci = n_loci; a.n_species = n_species; a.penalty = penalty; a.nloci_pct = nloci_pct;
     a.contig_start = reinterpret_cast<const unsigned long long*>(contig_start); a.ref_len = ref_len;
     a.db_off = reinterpret_cast<const unsigned long long*>(db_off); a.chunk_records = chunk_records;
-    a.best_t = reinterpret_cast<unsigned long long*>(p);
-    a.maxlen = reinterpret_cast<uint32_t*>(p + static_cast<size_t>(n_loci) * 8);
-    a.chosen_key = reinterpret_cast<unsigned long long*>(p + static_cast<size_t>(n_loci) * 12 + ((n_loci & 1) ? 4 : 0));
-    a.lfirst = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a.chosen_key) + static_cast<size_t>(n_loci) * 8);
-    a.target_chunks = static_cast<uint32_t>(mmlst_num_sms()) * 4u;
+    a.flags = flags; a.counters = reinterpret_cast<unsigned long long*>(counters);
+    a.res_key = reinterpret_cast<unsigned long long*>(p);
+    a.res_first = reinterpret_cast<uint32_t*>(a.res_key + n_loci);
+    a.done = reinterpret_cast<uint32_t*>(p + ((static_cast<size_t>(n_loci) * 12 + 7) & ~static_cast<size_t>(7)));
+    a.slots = static_cast<uint32_t>(mmlst_num_sms()) * MMLST_CHUNKS_PER_SM;
     a.header = header; a.chosen_tid = chosen_tid; a.chosen_species = chosen_species; a.col_off = col_off;
     a.db_start = reinterpret_cast<unsigned long long*>(db_start); a.chunks = chunks; a.max_chunks = max_chunks;
-    CUDA_TRY(cudaMemsetAsync(a.best_t, 0, static_cast<size_t>(n_loci) * 12, s));
-    CUDA_TRY(cudaMemsetAsync(a.chosen_key, 0xff, static_cast<size_t>(n_loci) * 12, s));
-    size_t gsz = (static_cast<size_t>(n_ref) + 255) / 256;
-    const size_t gcap = static_cast<size_t>(mmlst_num_sms()) * 4;
-    if (gsz > gcap) gsz = gcap;
-    if (gsz < 1) gsz = 1;
-    const unsigned grid = static_cast<unsigned>(gsz);
-    sel_pass_a<<<grid, 256, 0, s>>>(a);
-    sel_pass_b<<<grid, 256, 0, s>>>(a);
-    sel_pass_c<<<grid, 256, 0, s>>>(a);
-    sel_finalize<<<1, 1024, sizeof(uint32_t) * (3 * n_species + n_loci + 2), s>>>(a);
+    if (!(flags & MMLST_SELECT_SCRATCH_CLEAN)) CUDA_TRY(cudaMemsetAsync(a.done, 0, 4, s));
+    const size_t smem = sizeof(uint32_t) * (static_cast<size_t>(n_loci) * 7 + 1 + 3 * static_cast<size_t>(n_species)) + 16;
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        CUDA_TRY(cudaFuncSetAttribute(sel_locus, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = smem;
+    }
+    sel_locus<<<n_loci, SEL_THREADS, smem, s>>>(a);
     CUDA_TRY(cudaGetLastError());
     return MMLST_OK;
 }

@@ -24,23 +24,26 @@ def _pack_words(bits: torch.Tensor) -> torch.Tensor:
 
 
 def read_planes(core: dict, minqual: int = 20):
-    """Per READ: (reflen int64 [n], rw int64 [n], rows int32 [n, RWmax]) -- 3 interleaved planes, odd-padded."""
+    """Per READ: (reflen int64 [n], nw int64 [n], rw int64 [n], rows int32 [n, RWmax]) -- 3 interleaved planes aligned to
+    the contig's 32-column words (bit i of word j = contig column 32 ((start >> 5) + j) + i), odd-padded."""
     L = core["L"]
-    bases, qual, rtype, a = core["bases"], core["qual"], core["rtype"], core["a_split"]
+    bases, qual, rtype, a, start = core["bases"], core["qual"], core["rtype"], core["a_split"], core["start"]
     dev = bases.device
     n = bases.shape[0]
     reflen = torch.full((n,), L, dtype=torch.int64, device=dev)
     reflen[rtype == 1] = L - 10
     reflen[rtype == 2] = L - 1
     reflen[rtype == 3] = L + 1
-    nwmax = (L + 1 + 31) // 32
-    r = torch.arange(nwmax * 32, device=dev)[None, :]
+    shift = (start.to(torch.int64) & 31)[:, None]
+    nwmax = (31 + L + 1 + 31) // 32
+    c = torch.arange(nwmax * 32, device=dev)[None, :]
+    r = c - shift  # reference offset of row column c
     t, a_ = rtype[:, None], a[:, None]
-    q = r.expand(n, -1).clone()
+    q = r.clone()
     q = torch.where(t == 1, r + 5, q)
     q = torch.where(t == 2, torch.where(r < a_, r, r + 1), q)
     q = torch.where(t == 3, torch.where(r < a_, r, torch.where(r == a_, torch.full_like(q, -1), r - 1)), q)
-    valid = (r < reflen[:, None]) & (q >= 0)
+    valid = (r >= 0) & (r < reflen[:, None]) & (q >= 0)
     qc = q.clamp(0, L - 1)
     b = torch.gather(bases, 1, qc)
     ql = torch.gather(qual, 1, qc)
@@ -53,14 +56,14 @@ def read_planes(core: dict, minqual: int = 20):
     B1 = V & ((code & 2) != 0)
     B0 = (V & ((code & 1) != 0)) | Nn
     planes = torch.stack([_pack_words(V), _pack_words(B1), _pack_words(B0)], dim=2).reshape(n, 3 * nwmax)
-    nw = (reflen + 31) // 32
+    nw = (shift[:, 0] + reflen + 31) // 32
     rw = 3 * nw
     rw = rw + ((rw & 1) == 0).long()
     rwmax = 3 * nwmax + (1 if (3 * nwmax) % 2 == 0 else 0)
     rows = torch.zeros((n, rwmax), dtype=torch.int32, device=dev)
     rows[:, :3 * nwmax] = planes
-    # words beyond 3*nw must be zero (they are: bits beyond reflen are invalid); pad word is zero
-    return reflen, rw, rows
+    # words beyond 3*nw are zero (columns beyond the span are invalid); the pad word is zero
+    return reflen, nw, rw, rows
 
 
 class DeviceStreams:
@@ -86,19 +89,20 @@ def pack_cores(db, cores: List[dict], minqual: int = 20, max_depth: Optional[int
     dev = cores[0]["bases"].device
     K = cores[0]["K"]
     L = cores[0]["L"]
-    tids, poss, revs, ASs, xms, reflens, rws, rowss = [], [], [], [], [], [], [], []
+    tids, poss, revs, ASs, xms, reflens, nws, rws, rowss = [], [], [], [], [], [], [], [], []
     for c in cores:
-        reflen, rw, rows = read_planes(c, minqual)
+        reflen, nw, rw, rows = read_planes(c, minqual)
         tids.append(c["rows"].reshape(-1))
         poss.append(c["start"][:, None].expand(-1, K).reshape(-1))
         revs.append(((c["flag"] >> 4) & 1).reshape(-1))
         ASs.append(c["AS"].reshape(-1))
         xms.append(c["xm"].reshape(-1))
         reflens.append(reflen)
+        nws.append(nw)
         rws.append(rw)
         rowss.append(rows)
     tid = torch.cat(tids); pos = torch.cat(poss); rev = torch.cat(revs); AS = torch.cat(ASs); xm = torch.cat(xms)
-    reflen_r = torch.cat(reflens); rw_r = torch.cat(rws); rows_r = torch.cat(rowss)
+    reflen_r = torch.cat(reflens); nw_r = torch.cat(nws); rw_r = torch.cat(rws); rows_r = torch.cat(rowss)
     n = tid.shape[0]
     read_of = torch.arange(n, device=dev) // K
     key = (tid << 33) | ((pos + 1) << 1) | rev
@@ -130,8 +134,8 @@ def pack_cores(db, cores: List[dict], minqual: int = 20, max_depth: Optional[int
     off = torch.zeros(sel.shape[0] + 1, dtype=torch.int64, device=dev)
     off[1:] = torch.cumsum(rw, 0)
     assert int(off[-1]) + packing.PLANE_SLACK_WORDS < (1 << 32)
-    # 16-byte mmlst_prec records as int32 [P, 4]: pos | row_off | reflen + (as_named << 16) | xm_named
-    s.p_recs = torch.stack([pos[sel], off[:-1], reflen_r[rd] | ((AS[sel] & 0xffff) << 16), xm[sel].clamp(0, 255)], dim=1).to(torch.int32).contiguous()
+    # 16-byte mmlst_prec records as int32 [P, 4]: pos | row_off | reflen + (as_named << 16) | xm_named + (nw << 16)
+    s.p_recs = torch.stack([pos[sel], off[:-1], reflen_r[rd] | ((AS[sel] & 0xffff) << 16), xm[sel].clamp(0, 255) | (nw_r[rd] << 16)], dim=1).to(torch.int32).contiguous()
     s.n_prec = int(sel.shape[0])
     rwmax = rows_r.shape[1]
     if bool((rw == rwmax).all()):

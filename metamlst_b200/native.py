@@ -53,12 +53,12 @@ EXPORTS = {
     "mmlst_hamming_min_dev2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                          C.c_void_p, C.c_void_p]),
-    "mmlst_select_dev": (C.c_int, [C.c_void_p] * 5 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+    "mmlst_select_dev": (C.c_int, [C.c_void_p] * 6 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t] + [C.c_void_p] * 6 +
-                         [C.c_uint32, C.c_void_p]),
+                         [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "mmlst_pileup_indirect_dev": (C.c_int, [C.c_void_p] * 4 + [C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "mmlst_consensus_indirect_dev": (C.c_int, [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                                C.c_void_p]),
+                                                C.c_uint32, C.c_void_p]),
     "mmlst_chunk_records": (C.c_uint32, [C.c_uint64]),
     "mmlst_depth_cap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]),
     "mmlst_score": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(ScoreParams),
@@ -74,6 +74,7 @@ EXPORTS = {
 }
 
 _lib = None
+SELECT_CONSUME, SELECT_SCRATCH_CLEAN, CONSENSUS_CONSUME = 1, 2, 1  # include/mmlst.h flags
 
 
 def lib() -> C.CDLL:

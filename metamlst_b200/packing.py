@@ -21,7 +21,7 @@ DEFAULT_MAX_DEPTH = 8000  # pysam pileup() default reaching cmseq/cmseq.py:527 (
 DEFAULT_MINQUAL = 20  # metaMLST_functions.py:258
 PLANE_SLACK_WORDS = 8
 # mmlst_prec (include/mmlst.h): 16 bytes per pileup-stream record
-PREC_DTYPE = np.dtype([("pos", "<i4"), ("row_off", "<u4"), ("reflen", "<u2"), ("as_named", "<i2"), ("xm_named", "u1"), ("pad", "u1", (3,))])
+PREC_DTYPE = np.dtype([("pos", "<i4"), ("row_off", "<u4"), ("reflen", "<u2"), ("as_named", "<i2"), ("xm_named", "u1"), ("pad", "u1"), ("nw", "<u2")])
 assert PREC_DTYPE.itemsize == 16
 
 
@@ -70,7 +70,7 @@ class SoaHost:
         off = np.zeros(self.n_prec + 1, dtype=np.int64)
         off[:-1] = self.p_recs["row_off"]
         if self.n_prec:
-            off[-1] = int(off[-2]) + int(row_words(self.p_recs["reflen"][-1:])[0])
+            off[-1] = int(off[-2]) + int(row_words(self.p_recs["nw"][-1:])[0])
         return off
 
     def c_struct(self) -> native.Soa:
@@ -102,9 +102,16 @@ class SoaHost:
         return self
 
 
-def row_words(reflen: np.ndarray) -> np.ndarray:
-    """3 planes x ceil(reflen/32) words, padded to an odd word count (bank-conflict-free row stride)."""
-    rw = 3 * ((reflen.astype(np.int64) + 31) >> 5)
+def touched_words(pos: np.ndarray, reflen: np.ndarray) -> np.ndarray:
+    """32-column contig words a record touches: ((pos & 31) + reflen + 31) >> 5, 0 for an empty span."""
+    pos = pos.astype(np.int64)
+    reflen = reflen.astype(np.int64)
+    return np.where(reflen > 0, ((pos & 31) + reflen + 31) >> 5, 0)
+
+
+def row_words(nw: np.ndarray) -> np.ndarray:
+    """3 planes x nw words, padded to an odd word count (bank-conflict-free row stride)."""
+    rw = 3 * nw.astype(np.int64)
     return rw + ((rw > 0) & ((rw & 1) == 0))
 
 
@@ -181,7 +188,11 @@ def pack_table(tab, minqual: int = DEFAULT_MINQUAL, max_depth: Optional[int] = D
     p_reflen = p_reflen_all[adm].astype(np.uint16)
     p_as = tab.AS[sel].astype(np.int16)  # by NAME
     p_xm = np.clip(tab.XM[sel], 0, 255).astype(np.uint8)
-    rw = row_words(p_reflen)
+    p_nw = touched_words(p_pos, p_reflen)
+    if P and p_nw.max() > 65535:
+        raise native.MmlstError(-7, "record touches more than 65535 words")
+    p_shift = p_pos.astype(np.int64) & 31  # rows are aligned to the contig's 32-column words
+    rw = row_words(p_nw)
     p_row_off = np.zeros(P + 1, dtype=np.int64)
     p_row_off[1:] = np.cumsum(rw)
     if p_row_off[-1] + PLANE_SLACK_WORDS >= (1 << 32):
@@ -198,8 +209,7 @@ def pack_table(tab, minqual: int = DEFAULT_MINQUAL, max_depth: Optional[int] = D
     for c0 in range(0, P, chunk):
         idx = sel[c0:c0 + chunk]
         m = idx.shape[0]
-        maxref = int(p_reflen[c0:c0 + m].max()) if m else 0
-        wmax = (maxref + 31) >> 5
+        wmax = int(p_nw[c0:c0 + m].max()) if m else 0
         if wmax == 0:
             continue
         qidx = np.full((m, wmax * 32), -1, dtype=np.int64)
@@ -212,7 +222,7 @@ def pack_table(tab, minqual: int = DEFAULT_MINQUAL, max_depth: Optional[int] = D
         tot = int(sl.sum())
         within = np.arange(tot) - np.repeat(np.cumsum(sl) - sl, sl)
         rr = np.repeat(row, sl)
-        qidx[rr, np.repeat(seg_ref[sid], sl) + within] = np.repeat(seg_q[sid], sl) + within
+        qidx[rr, np.repeat(seg_ref[sid], sl) + within + p_shift[c0:c0 + m][rr]] = np.repeat(seg_q[sid], sl) + within
         has = qidx >= 0
         qi = np.where(has, qidx, 0)
         base = tab.seq[idx][np.arange(m)[:, None], qi]
@@ -224,7 +234,7 @@ def pack_table(tab, minqual: int = DEFAULT_MINQUAL, max_depth: Optional[int] = D
         B1 = V & ((code & 2) != 0)
         B0 = (V & ((code & 1) != 0)) | Nn
         Vw, B1w, B0w = _pack_bits_u32(V), _pack_bits_u32(B1), _pack_bits_u32(B0)
-        nw = (p_reflen[c0:c0 + m].astype(np.int64) + 31) >> 5
+        nw = p_nw[c0:c0 + m]
         off = p_row_off[c0:c0 + m]
         for j in range(wmax):
             msk = nw > j
@@ -236,6 +246,7 @@ def pack_table(tab, minqual: int = DEFAULT_MINQUAL, max_depth: Optional[int] = D
     contig_start = np.searchsorted(tab.tid[sel], np.arange(n_ref + 1)).astype(np.uint64)
     recs = np.zeros(P, dtype=PREC_DTYPE)
     recs["pos"], recs["row_off"], recs["reflen"], recs["as_named"], recs["xm_named"] = p_pos, p_row_off[:-1], p_reflen, p_as, p_xm
+    recs["nw"] = p_nw
     return SoaHost(list(tab.ref_names), np.asarray(tab.ref_lens, dtype=np.int32), tid, as0, xm3, qlen, orig_idx,
                    recs, planes, int(rw.max()) if P else 0, contig_start,
                    minqual, max_depth if max_depth is not None else 0, int((~adm).sum()))

@@ -12,7 +12,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from . import api, native
+from . import api, dist, native
 
 def build_chunks(contig_start: np.ndarray, chosen_tid: Sequence[int], col_off: np.ndarray) -> np.ndarray:
     """mmlst_chunk descriptors (8 x u32 each) for the chosen contigs of a device-resident pileup stream."""
@@ -44,16 +44,15 @@ class DevicePipeline:
         self.n_ref = n_ref
         self.allow = torch.from_numpy(index.allow_mask(species_filter)).to(dev)
         self.locus_of = torch.from_numpy(index.locus_of.astype(np.int32)).to(dev)
-        # one int64 block so a single D2H / all-reduce moves the three score tables
-        self.sum_as = torch.zeros(n_ref, dtype=torch.int64, device=dev)
-        self.n_hit = torch.zeros(n_ref, dtype=torch.int32, device=dev)
-        self.first_idx = torch.zeros(n_ref, dtype=torch.int32, device=dev)
-        self.counters = torch.zeros(2, dtype=torch.int64, device=dev)
+        # every accumulator that must start at zero lives in ONE int64 block => one memset node per pass
         self.max_cols = int(np.sort(np.asarray(streams.ref_lens))[::-1][: index.n_loci].sum())
-        self.counts = torch.zeros(self.max_cols * 5 + 8, dtype=torch.int32, device=dev)
-        self.cons = torch.zeros(self.max_cols + 8, dtype=torch.uint8, device=dev)
-        self.holes = torch.zeros(index.n_loci + 1, dtype=torch.int32, device=dev)
-        self.snps = torch.zeros(index.n_loci + 1, dtype=torch.int32, device=dev)
+        w_hit, w_cnt = (n_ref + 1) // 2, (self.max_cols * 5 + 8 + 1) // 2
+        self.zblock = torch.zeros(n_ref + 2 + w_hit + w_cnt, dtype=torch.int64, device=dev)
+        self.sum_as = self.zblock[:n_ref]
+        self.counters = self.zblock[n_ref:n_ref + 2]
+        self.n_hit = self.zblock[n_ref + 2:n_ref + 2 + w_hit].view(torch.int32)[:n_ref]
+        self.counts = self.zblock[n_ref + 2 + w_hit:].view(torch.int32)[: self.max_cols * 5 + 8]
+        self.first_idx = torch.zeros(n_ref, dtype=torch.int32, device=dev)
         self._db_cache: Dict[Tuple[int, ...], tuple] = {}
         self.lib = native.lib()
         # ---- device-side selection (mmlst_select_dev): look-up tables + output block
@@ -85,16 +84,26 @@ class DevicePipeline:
         self.db_ascii_d = t32(np.concatenate([db_ascii, np.zeros(8, np.uint8)]))
         self.db_off_d = t32(np.asarray(db_off, dtype=np.int64))
         nl = index.n_loci
-        self.scratch = torch.zeros(nl * 24 + 64, dtype=torch.uint8, device=dev)
+        self.scratch = torch.zeros(nl * 12 + 64, dtype=torch.uint8, device=dev)
+        order = np.argsort(index.locus_of, kind="stable").astype(np.uint32)  # allele rows grouped by locus
+        self.locus_rows = t32(order.view(np.int32))
+        self.locus_start = t32(np.searchsorted(index.locus_of[order], np.arange(nl + 1)).astype(np.int32))
         self.max_chunks = int(streams.n_prec) // 512 + nl + 8
         self.chunks_d = torch.zeros(self.max_chunks * 8, dtype=torch.int32, device=dev)
-        # one int32 block for every small output: header[8] | chosen_tid[nl] | chosen_species[nl] | col_off[nl+1] | holes[nl] | snps[nl]
-        self.o_hdr, self.o_tid, self.o_sp, self.o_col, self.o_holes, self.o_snps = 0, 8, 8 + nl, 8 + 2 * nl, 9 + 3 * nl, 9 + 4 * nl
-        self.small = torch.zeros(9 + 5 * nl + 7, dtype=torch.int32, device=dev)
+        # ONE output block => one D2H node per pass: int32 header[16] | chosen_tid[nl] | chosen_species[nl] | col_off[nl+1] |
+        # holes[nl] | snps[nl] | pad, then the consensus bytes
+        self.o_hdr, self.o_tid, self.o_sp, self.o_col, self.o_holes, self.o_snps = 0, 16, 16 + nl, 16 + 2 * nl, 17 + 3 * nl, 17 + 4 * nl
+        self.n_small = (17 + 5 * nl + 7) // 4 * 4
+        self.out = torch.zeros(self.n_small * 4 + self.max_cols + 16, dtype=torch.uint8, device=dev)
+        self.small = self.out[: self.n_small * 4].view(torch.int32)
+        self.cons = self.out[self.n_small * 4:]
+        self.holes = self.small[self.o_holes:self.o_holes + nl]
+        self.snps = self.small[self.o_snps:self.o_snps + nl]
         self.db_start_d = torch.zeros(nl + 1, dtype=torch.int64, device=dev)
-        self.small_h = torch.zeros(self.small.shape[0], dtype=torch.int32).pin_memory()
-        self.cons_h = torch.zeros(self.cons.shape[0], dtype=torch.uint8).pin_memory()
-        self.counters_h = torch.zeros(2, dtype=torch.int64).pin_memory()
+        self.out_h = torch.zeros(self.out.shape[0], dtype=torch.uint8).pin_memory()
+        self.small_h = self.out_h[: self.n_small * 4].view(torch.int32)
+        self.cons_h = self.out_h[self.n_small * 4:]
+        self._clean = False  # score tables / counts / scratch hold the "nothing accumulated" state
         self.timers: Optional[Dict[str, list]] = None  # name -> [(start_event, end_event)]
         self.launches = 0
 
@@ -112,9 +121,17 @@ class DevicePipeline:
     def _stream(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 
-    def run_score(self):
+    def reset_tables(self):
+        """Score tables, counters, count tensor and the selection ticket back to the empty state.  The device-driven
+        pass (`_enqueue`) leaves them that way itself (MMLST_SELECT_CONSUME / MMLST_CONSENSUS_CONSUME)."""
+        self.zblock.zero_(); self.first_idx.fill_(-1); self.scratch.zero_()
+        self._clean = True
+
+    def run_score(self, reset: bool = True):
         s = self.s
-        self.sum_as.zero_(); self.n_hit.zero_(); self.first_idx.fill_(-1); self.counters.zero_()
+        if reset:
+            self.reset_tables()
+        self._clean = False
         def k():
             native.check(self.lib.mmlst_score_dev(native.ptr(s.tid), native.ptr(s.as0), native.ptr(s.xm3), native.ptr(s.qlen), 0,
                                                   int(s.tid.shape[0]), self.idx_base, native.ptr(self.allow), native.ptr(self.locus_of),
@@ -124,13 +141,7 @@ class DevicePipeline:
         self._timed("score", k)
         self.launches += 1
         if self.dist:
-            d = torch.distributed
-            d.all_reduce(self.sum_as, op=d.ReduceOp.SUM, group=self.group)
-            d.all_reduce(self.n_hit, op=d.ReduceOp.SUM, group=self.group)
-            self.first_idx.bitwise_xor_(-2147483648)  # u32 order -> i32 order
-            d.all_reduce(self.first_idx, op=d.ReduceOp.MIN, group=self.group)
-            self.first_idx.bitwise_xor_(-2147483648)
-            d.all_reduce(self.counters, op=d.ReduceOp.SUM, group=self.group)
+            dist.allreduce_score_tables(self.sum_as, self.n_hit, self.first_idx, self.counters, self.group)
 
     def select(self):
         sum_as = self.sum_as.cpu().numpy()
@@ -172,7 +183,7 @@ class DevicePipeline:
             self._timed("pileup", k)
             self.launches += 1
         if self.dist:
-            torch.distributed.all_reduce(self.counts[: total * 5], op=torch.distributed.ReduceOp.SUM, group=self.group)
+            dist.allreduce_counts(self.counts[: total * 5], self.group)
         def k2():
             native.check(self.lib.mmlst_consensus_dev(native.ptr(self.counts), native.ptr(db_d), native.ptr(col_off_d), len(tids), self.mincov,
                                                       native.ptr(self.cons), native.ptr(self.holes), native.ptr(self.snps), self._stream()))
@@ -183,45 +194,95 @@ class DevicePipeline:
         snps = self.snps[: len(tids)].cpu().numpy()
         return [cons[col_off[i]:col_off[i + 1]].tobytes().decode("latin-1") for i in range(len(tids))], holes, snps, col_off
 
-    def _enqueue(self):
-        """Everything of one pass on the current stream, no host synchronisation: score -> [all-reduce] -> select ->
-        pileup -> [all-reduce] -> consensus -> D2H into pinned buffers."""
-        self.run_score()
+    def _select_call(self, flags: int):
         sm, nl = self.small, self.index.n_loci
         base = sm.data_ptr()
-        def k():
-            native.check(self.lib.mmlst_select_dev(native.ptr(self.sum_as), native.ptr(self.n_hit), native.ptr(self.first_idx), native.ptr(self.locus_of),
-                                                   native.ptr(self.allele_num), self.n_ref, native.ptr(self.species_of_locus), native.ptr(self.genes_in_db),
-                                                   nl, len(self.species_names), self.penalty, self.nloci, native.ptr(self.contig_start_d),
-                                                   native.ptr(self.ref_len_d), native.ptr(self.db_off_d), 0, native.ptr(self.scratch),
-                                                   int(self.scratch.shape[0]), base + 4 * self.o_hdr, base + 4 * self.o_tid, base + 4 * self.o_sp,
-                                                   base + 4 * self.o_col, native.ptr(self.db_start_d), native.ptr(self.chunks_d), self.max_chunks,
-                                                   self._stream()))
-        self._timed("select", k)
-        self.launches += 4
+        native.check(self.lib.mmlst_select_dev(native.ptr(self.sum_as), native.ptr(self.n_hit), native.ptr(self.first_idx), native.ptr(self.locus_rows),
+                                               native.ptr(self.locus_start), native.ptr(self.allele_num), self.n_ref, native.ptr(self.species_of_locus),
+                                               native.ptr(self.genes_in_db), nl, len(self.species_names), self.penalty, self.nloci,
+                                               native.ptr(self.contig_start_d), native.ptr(self.ref_len_d), native.ptr(self.db_off_d), 0,
+                                               native.ptr(self.scratch), int(self.scratch.shape[0]), base + 4 * self.o_hdr, base + 4 * self.o_tid,
+                                               base + 4 * self.o_sp, base + 4 * self.o_col, native.ptr(self.db_start_d), native.ptr(self.chunks_d),
+                                               self.max_chunks, flags, native.ptr(self.counters), self._stream()))
+
+    def _consensus_call(self, flags: int):
+        nl = self.index.n_loci
+        base = self.small.data_ptr()
+        native.check(self.lib.mmlst_consensus_indirect_dev(native.ptr(self.counts), native.ptr(self.db_ascii_d), native.ptr(self.db_start_d),
+                                                           base + 4 * self.o_col, nl, base + 4 * self.o_hdr, self.mincov, native.ptr(self.cons),
+                                                           base + 4 * self.o_holes, base + 4 * self.o_snps, flags, self._stream()))
+
+    def _pileup_call(self):
         s = self.s
-        self.counts.zero_()
-        def k1():
-            native.check(self.lib.mmlst_pileup_indirect_dev(native.ptr(s.p_recs), native.ptr(s.planes), native.ptr(self.chunks_d), base + 4 * self.o_hdr,
-                                                            int(s.max_row_words), self.minscore, self.max_xM, native.ptr(self.counts), self.impl,
-                                                            self._stream()))
-        self._timed("pileup", k1)
+        native.check(self.lib.mmlst_pileup_indirect_dev(native.ptr(s.p_recs), native.ptr(s.planes), native.ptr(self.chunks_d),
+                                                        self.small.data_ptr() + 4 * self.o_hdr, int(s.max_row_words), self.minscore, self.max_xM,
+                                                        native.ptr(self.counts), self.impl, self._stream()))
+
+    def _enqueue(self):
+        """Everything of one pass on the current stream, no host synchronisation and no memset: score -> [all-reduce] ->
+        select -> pileup -> [all-reduce] -> consensus -> ONE D2H into a pinned buffer.  Selection and consensus reset
+        what they read, so the pass starts from and ends in the empty-table state."""
+        if not self._clean:
+            self.reset_tables()
+        self.run_score(reset=False)
+        self._timed("select", lambda: self._select_call(native.SELECT_CONSUME | native.SELECT_SCRATCH_CLEAN))
+        self.launches += 1
+        self._timed("pileup", self._pileup_call)
         self.launches += 1
         if self.dist:
-            torch.distributed.all_reduce(self.counts, op=torch.distributed.ReduceOp.SUM, group=self.group)
-        def k2():
-            native.check(self.lib.mmlst_consensus_indirect_dev(native.ptr(self.counts), native.ptr(self.db_ascii_d), native.ptr(self.db_start_d),
-                                                               base + 4 * self.o_col, nl, base + 4 * self.o_hdr, self.mincov, native.ptr(self.cons),
-                                                               base + 4 * self.o_holes, base + 4 * self.o_snps, self._stream()))
-        self._timed("consensus", k2)
+            dist.allreduce_counts(self.counts, self.group)
+        self._timed("consensus", lambda: self._consensus_call(native.CONSENSUS_CONSUME))
         self.launches += 1
-        self.small_h.copy_(sm, non_blocking=True)
-        self.cons_h.copy_(self.cons, non_blocking=True)
-        self.counters_h.copy_(self.counters, non_blocking=True)
+        self.out_h.copy_(self.out, non_blocking=True)
+        self._clean = True
+
+    def time_kernels(self, reps: int = 20) -> Dict[str, float]:
+        """Average device time (ms) of every kernel of the pass: `reps` back-to-back launches of the SAME kernel between
+        two CUDA events on the launching stream (amortises the event/launch gap a single launch would carry).  The
+        tables hold a finished pass when this is called; they are garbage afterwards (the next step resets them)."""
+        self.reset_tables()
+        self.run_score(reset=False)  # tables of a finished scoring pass (all-reduced when distributed)
+        self._select_call(native.SELECT_SCRATCH_CLEAN)
+        torch.cuda.current_stream(self.dev).synchronize()
+        out: Dict[str, float] = {}
+        saved, self.dist = self.dist, False  # kernels only: no collectives inside the loops
+        try:
+            for name in ("select", "pileup", "consensus", "score"):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                self._launch_one(name)  # warm
+                a.record()
+                for _ in range(reps):
+                    self._launch_one(name)
+                b.record()
+                b.synchronize()
+                out[name] = a.elapsed_time(b) / reps
+        finally:
+            self.dist = saved
+            self._clean = False
+        return out
+
+    def _launch_one(self, name: str):
+        s = self.s
+        if name == "score":
+            native.check(self.lib.mmlst_score_dev(native.ptr(s.tid), native.ptr(s.as0), native.ptr(s.xm3), native.ptr(s.qlen), 0,
+                                                  int(s.tid.shape[0]), self.idx_base, native.ptr(self.allow), native.ptr(self.locus_of),
+                                                  self.n_ref, self.minscore, self.max_xM, self.min_read_len, native.ptr(self.sum_as),
+                                                  native.ptr(self.n_hit), native.ptr(self.first_idx), native.ptr(self.counters),
+                                                  self._stream()))
+        elif name == "select":
+            self._select_call(native.SELECT_SCRATCH_CLEAN)  # tables left intact: every repetition does the same work
+        elif name == "pileup":
+            self._pileup_call()
+        elif name == "consensus":
+            self._consensus_call(0)
+        else:
+            raise ValueError(name)
 
     def _finish(self):
         h = self.small_h.numpy()
         n = int(h[0])
+        self.total_reads = int(h[6:8].view(np.uint64)[0])      # metamlst.py:130 totalReads
+        self.ignored_reads = int(h[8:10].view(np.uint64)[0])   # metamlst.py:129 ignoredReads
         if h[3] & 1:
             raise RuntimeError("Database is broken: a species has more detected loci than the genes table lists (metamlst.py:188)")
         if h[3] & 2:
@@ -258,8 +319,25 @@ class DevicePipeline:
         self.launches = n0
 
     def step_graph(self):
+        if not self._clean:
+            self.reset_tables()  # the captured pass contains no memset: it starts from the empty-table state it leaves behind
         self.graph.replay()
         self.launches += self.launches_per_step
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self._finish()
+
+    def enqueue_step(self):
+        """Queue one pass without waiting for it (cohort mode: passes run back to back, results are read from the pinned
+        output block after a synchronisation with `collect()`)."""
+        if getattr(self, "graph", None) is not None:
+            if not self._clean:
+                self.reset_tables()
+            self.graph.replay()
+            self.launches += self.launches_per_step
+        else:
+            self._enqueue()
+
+    def collect(self):
         torch.cuda.current_stream(self.dev).synchronize()
         return self._finish()
 
@@ -297,22 +375,24 @@ def device_select(index: api.AlleleIndex, sum_as: np.ndarray, n_hit: np.ndarray,
     gdb = np.asarray([(genes_in_db or {}).get(sp, int((sol == i).sum())) for i, sp in enumerate(names)], np.int32)
     d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     t_sum, t_n, t_f = d(sum_as.astype(np.int64)), d(n_hit.astype(np.uint32).view(np.int32)), d(first_idx.astype(np.uint32).view(np.int32))
-    t_loc, t_an = d(index.locus_of.view(np.int32)), d(np.asarray([int(a) for a in index.allele], np.int64).astype(np.uint32).view(np.int32))
+    order = np.argsort(index.locus_of, kind="stable").astype(np.uint32)
+    t_rows, t_start = d(order.view(np.int32)), d(np.searchsorted(index.locus_of[order], np.arange(nl + 1)).astype(np.int32))
+    t_an = d(np.asarray([int(a) for a in index.allele], np.int64).astype(np.uint32).view(np.int32))
     t_sol, t_gdb = d(sol), d(gdb)
     t_cs, t_rl, t_dbo = d(np.zeros(n_ref + 1, np.int64)), d(np.ones(n_ref, np.int32)), d(np.zeros(n_ref + 1, np.int64))
-    scratch = torch.zeros(nl * 24 + 64, dtype=torch.uint8, device=dev)
-    small = torch.zeros(16 + 3 * nl, dtype=torch.int32, device=dev)
+    scratch = torch.zeros(nl * 12 + 64, dtype=torch.uint8, device=dev)
+    small = torch.zeros(16 + 3 * nl + 8, dtype=torch.int32, device=dev)
     dbs = torch.zeros(nl + 1, dtype=torch.int64, device=dev)
     chunks = torch.zeros(8 * (nl + 8), dtype=torch.int32, device=dev)
     base = small.data_ptr()
-    native.check(lib.mmlst_select_dev(native.ptr(t_sum), native.ptr(t_n), native.ptr(t_f), native.ptr(t_loc), native.ptr(t_an), n_ref,
-                                      native.ptr(t_sol), native.ptr(t_gdb), nl, len(names), int(penalty), int(nloci), native.ptr(t_cs),
+    native.check(lib.mmlst_select_dev(native.ptr(t_sum), native.ptr(t_n), native.ptr(t_f), native.ptr(t_rows), native.ptr(t_start), native.ptr(t_an),
+                                      n_ref, native.ptr(t_sol), native.ptr(t_gdb), nl, len(names), int(penalty), int(nloci), native.ptr(t_cs),
                                       native.ptr(t_rl), native.ptr(t_dbo), 0, native.ptr(scratch), int(scratch.shape[0]), base,
-                                      base + 4 * 8, base + 4 * (8 + nl), base + 4 * (8 + 2 * nl), native.ptr(dbs), native.ptr(chunks), nl + 8,
-                                      torch.cuda.current_stream(dev).cuda_stream))
+                                      base + 4 * 16, base + 4 * (16 + nl), base + 4 * (16 + 2 * nl), native.ptr(dbs), native.ptr(chunks), nl + 8,
+                                      0, 0, torch.cuda.current_stream(dev).cuda_stream))
     h = small.cpu().numpy()
     n = int(h[0])
     out: Dict[str, List[int]] = {}
     for i in range(n):
-        out.setdefault(names[int(h[8 + nl + i])], []).append(int(h[8 + i]))
+        out.setdefault(names[int(h[16 + nl + i])], []).append(int(h[16 + i]))
     return list(out.items()), int(h[3])

@@ -32,7 +32,8 @@ def planes_to_counts(soa, tid, contig_len, minscore, max_xm):
     for r in range(r0, r1):
         off = int(soa.p_row_off[r]); rl = int(soa.p_reflen[r]); p = int(soa.p_pos[r])
         ok = int(soa.p_as[r]) >= minscore and int(soa.p_xm[r]) <= max_xm
-        nw = (rl + 31) // 32
+        nw = int(soa.p_recs["nw"][r])
+        assert nw == (((p & 31) + rl + 31) // 32 if rl else 0)
         row = soa.planes[off:off + 3 * nw].reshape(nw, 3)
         for j in range(nw):
             v, b1, b0 = int(row[j, 0]), int(row[j, 1]), int(row[j, 2])
@@ -40,7 +41,7 @@ def planes_to_counts(soa, tid, contig_len, minscore, max_xm):
                 vb, h, l = (v >> i) & 1, (b1 >> i) & 1, (b0 >> i) & 1
                 if not (vb | l):
                     continue
-                col = p + 32 * j + i
+                col = (p >> 5) * 32 + 32 * j + i  # rows are aligned to the contig's 32-column words
                 if 0 <= col < contig_len:
                     counts[col, (2 * h + l) if (vb and ok) else 4] += 1
     return counts

@@ -1,0 +1,115 @@
+"""N>1 host logic on CPU: world_size-2 `gloo` processes run the same reductions the GPU ranks run over NCCL
+(metamlst_b200/dist.py).  Per-rank partial tables come from the C oracle on contig-aligned shards; the reduced tables
+must equal the oracle on the whole sample, bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as td
+import torch.multiprocessing as mp
+
+from helpers import lut_from_db, small_case
+from metamlst_b200 import api, dist
+from oracle import corc
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        db, tab = small_case(seed=61, n_reads=3000, L=100, K=4, orgs=("ecoli", "saureus"), apl=5)
+        st = tab.sorted_by_coord()
+        allow, locus_of, n_loci = lut_from_db(db)
+        per_contig = np.bincount(st.tid, minlength=db.n_rows)
+        shards = dist.shard_contigs(per_contig, locus_of, world)
+        assert sorted(np.concatenate(shards).tolist()) == list(range(db.n_rows))
+        mine = st.take(np.nonzero(np.isin(st.tid, shards[rank]))[0])
+        # global record index of every local record (H5 first-record order must survive the sharding)
+        orig = np.nonzero(np.isin(st.tid, shards[rank]))[0].astype(np.uint32)
+        s, c, f, cnt = corc.score(mine, allow, locus_of, n_loci, 80, 5, 50, orig_idx=orig)
+        t_s, t_c = torch.from_numpy(s.copy()), torch.from_numpy(c.view(np.int32).copy())
+        t_f, t_cnt = torch.from_numpy(f.view(np.int32).copy()), torch.from_numpy(cnt.view(np.int64).copy())
+        dist.allreduce_score_tables(t_s, t_c, t_f, t_cnt)
+        ws, wc, wf, wcnt = corc.score(st, allow, locus_of, n_loci, 80, 5, 50)
+        assert np.array_equal(t_s.numpy(), ws) and np.array_equal(t_c.numpy().view(np.uint32), wc)
+        assert np.array_equal(t_f.numpy().view(np.uint32), wf), "first-record indices (H5) differ after MIN reduce"
+        assert np.array_equal(t_cnt.numpy().view(np.uint64), wcnt)
+        # every rank now selects the same alleles
+        index = api.AlleleIndex(tab.ref_names)
+        chosen = api.fast_select(index, t_s.numpy(), t_c.numpy().view(np.uint32), t_f.numpy().view(np.uint32), 100)
+        tids = [t for _sp, ts in chosen for t in ts]
+        # pileup counts: a rank contributes the contigs it owns (depth cap local to the contig), zeros elsewhere
+        lens = [int(st.ref_lens[t]) for t in tids]
+        col_off = np.concatenate([[0], np.cumsum(lens)])
+        counts = np.zeros((int(col_off[-1]), 5), np.int32)
+        whole = np.zeros_like(counts)
+        own = set(int(t) for t in shards[rank])
+        for i, t in enumerate(tids):
+            w, _ = corc.contig_counts(st, t, 20, 80, 5, 60)
+            whole[col_off[i]:col_off[i + 1]] = w
+            if t in own:
+                m, _ = corc.contig_counts(mine, t, 20, 80, 5, 60)
+                counts[col_off[i]:col_off[i + 1]] = m
+        t_counts = torch.from_numpy(counts)
+        dist.allreduce_counts(t_counts)
+        assert np.array_equal(t_counts.numpy(), whole)
+        # Hamming: rows sharded, best = (dist << 32 | global row) reduced with MIN
+        rng = np.random.default_rng(5)
+        rows = ["".join("ACGT"[x] for x in rng.integers(0, 4, int(n))) for n in rng.integers(40, 90, 300)]
+        rows[17] = rows[250]  # a tie between shards must resolve to the lowest global row
+        qs = [rows[250], rows[3][:50], "ACGT" * 12]
+        flat = np.frombuffer("".join(rows).encode(), np.uint8)
+        off = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+        lo, hi = dist.shard_rows(len(rows), world, rank)
+        d, a = corc.hamming_min([q.encode() for q in qs], flat, off, [(lo, hi)] * len(qs))
+        best = torch.from_numpy(((d.astype(np.uint64) << np.uint64(32)) | a.astype(np.uint64)).view(np.int64).copy())
+        if rank == 1:
+            best[2] = -1  # "nothing found on this shard" (preset ~0) must lose against any real key
+        dist.allreduce_best(best)
+        wd, wa = corc.hamming_min([q.encode() for q in qs], flat, off, [(0, len(rows))] * len(qs))
+        got = best.numpy().view(np.uint64)
+        if world == 2:
+            d0, a0 = corc.hamming_min([qs[2].encode()], flat, off, [dist.shard_rows(len(rows), world, 0)])
+            wd[2], wa[2] = d0[0], a0[0]
+        assert np.array_equal(got >> np.uint64(32), wd.astype(np.uint64)) and np.array_equal(got & np.uint64(0xffffffff), wa.astype(np.uint64))
+        assert int(got[0] & np.uint64(0xffffffff)) == 17
+        assert dist.max_over_ranks(float(rank + 1), "cpu") == float(world)
+        ret[rank] = "ok"
+    except BaseException as e:  # noqa: BLE001
+        ret[rank] = repr(e)
+        raise
+    finally:
+        td.destroy_process_group()
+
+
+def test_world_size_2_reductions_equal_the_whole_sample():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_shard_helpers():
+    rec = [100, 5, 5, 90, 1, 1, 50, 50]
+    loc = [0, 0, 1, 1, 2, 2, 3, 3]
+    sh = dist.shard_contigs(rec, loc, 2)
+    assert sorted(np.concatenate(sh).tolist()) == list(range(8))
+    for s in sh:  # whole loci stay together
+        assert all((loc[a] in {loc[b] for b in s}) for a in s)
+    loads = [sum(rec[i] for i in s) for s in sh]
+    assert abs(loads[0] - loads[1]) <= 100
+    assert dist.shard_rows(100, 4, 0) == (0, 32) and dist.shard_rows(100, 4, 3) == (96, 100)
+    assert dist.shard_rows(10, 4, 2) == (10, 10)

@@ -15,7 +15,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(l, name), name
     assert declared <= set(native.EXPORTS) | {"mmlst_hamming_min_dev2"}
-    assert l.mmlst_version() == 100
+    assert l.mmlst_version() == 101
 
 
 def test_no_device_fails_loudly():
