@@ -8,7 +8,7 @@
 
 namespace {
 
-constexpr int kRowsPerCta = 256;
+constexpr int kRowsPerCta = 128;
 constexpr int kQChunk = 64;
 constexpr int kQSplit = 2048;  // queries handled by one CTA (gridDim.z splits longer query ranges)
 
@@ -19,26 +19,48 @@ struct HamArgs {
     unsigned long long* best;
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ uint32_t prefix_mask(int bits) {  // low `bits` bits set, clamped to [0, 32]: VIMNMX + BMSK
+    uint32_t m;
+    asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(m) : "r"(static_cast<uint32_t>(max(bits, 0))));
+    return m;
+}
+
+// POPC runs on the XU pipe at 16 lanes/clk/SM (8 issue cycles per warp instruction and SM sub-partition) while a
+// LOP3 costs 2: three mismatch words are folded by one carry-save adder (2 LOP3) into ones + twos, so 3 words cost
+// 2 POPC instead of 3 and the two pipes carry about the same load (~5.3 cycles per word each).
+__device__ __forceinline__ uint32_t popc3(uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t u = a ^ b;
+    const uint32_t ones = u ^ c;
+    const uint32_t twos = (a & b) | (u & c);
+    return __popc(ones) + 2u * __popc(twos);
+}
+
 template <int W>
-__global__ void __launch_bounds__(kRowsPerCta) hamming_min_kernel(const HamArgs a) {
-    static_assert(W % 4 == 0, "W must be a multiple of 4 (128-bit query loads)");
+__global__ void __launch_bounds__(kRowsPerCta, 5) hamming_min_kernel(const HamArgs a) {
+    static_assert(W % 6 == 0 || W == 8 || W == 16 || W == 32, "W: 8, 16, 24 or 32 words per plane");
+    constexpr int U = (W % 6 == 0) ? 6 : 4;  // words per unit: plain / masked / skipped is decided per unit (CTA-uniform)
+    constexpr int NU = W / U;
     const uint32_t* blk = a.blocks + 4 * blockIdx.y;
     const uint32_t q_begin = blk[0], q_end = blk[1], r_begin = blk[2], r_end = blk[3];
-    const uint32_t row0 = (r_begin & ~31u) + blockIdx.x * kRowsPerCta;
+    // row tiles start AT the block's first row (not at a 32-row tile boundary): only the last CTA of a block is ragged
+    const uint32_t row0 = r_begin + blockIdx.x * kRowsPerCta;
     if (row0 >= r_end) return;
     const uint32_t qs = q_begin + blockIdx.z * kQSplit;
     if (qs >= q_end) return;
     const uint32_t qe = min(q_end, qs + kQSplit);
 
-    __shared__ uint4 sq_hi[kQChunk][W / 4];
-    __shared__ uint4 sq_lo[kQChunk][W / 4];
-    __shared__ uint32_t sq_len[kQChunk];
-    __shared__ uint32_t part[kRowsPerCta / 32][kQChunk];
-    __shared__ uint32_t s_minw;
+    __shared__ __align__(16) uint32_t sq_hi[2][kQChunk + 2][W];
+    __shared__ __align__(16) uint32_t sq_lo[2][kQChunk + 2][W];
+    __shared__ uint32_t sq_len[2][kQChunk + 2];
+    __shared__ uint32_t part[kRowsPerCta / 32][kQChunk + 1];
+    __shared__ uint32_t s_minl, s_maxl;
 
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t row = row0 + threadIdx.x;
-    const bool valid = (row >= r_begin) && (row < r_end) && (row < a.n_rows);
+    const bool valid = (row < r_end) && (row < a.n_rows);
     uint32_t rh[W], rl[W];
     uint32_t rlen = 0;
     {
@@ -51,52 +73,83 @@ __global__ void __launch_bounds__(kRowsPerCta) hamming_min_kernel(const HamArgs 
         }
         if (valid) rlen = a.row_len[row];
     }
-    if (threadIdx.x == 0) s_minw = 0xffffffffu;
-    __syncthreads();
-    {
-        uint32_t mw = valid ? (rlen >> 5) : 0xffffffffu;
-        mw = __reduce_min_sync(0xffffffffu, mw);
-        if (lane == 0) atomicMin(&s_minw, mw);
-    }
-    __syncthreads();
-    const uint32_t cta_minw = s_minw;
-
-    for (uint32_t qc = qs; qc < qe; qc += kQChunk) {
+    // query staging is software-pipelined with cp.async (LDGSTS, no registers): chunk c+1 travels global -> the other
+    // shared-memory buffer while chunk c is compared, and the first chunk is requested together with the row planes so
+    // that a CTA pays ONE memory round trip before computing
+    auto fetch = [&](uint32_t qc, uint32_t buf) {
         const uint32_t nq = min(uint32_t(kQChunk), qe - qc);
-        __syncthreads();
         for (uint32_t i = threadIdx.x; i < nq * (W / 4); i += kRowsPerCta) {
             const uint32_t qi = i / (W / 4), w4 = i % (W / 4);
-            sq_hi[qi][w4] = reinterpret_cast<const uint4*>(a.q_hi + static_cast<size_t>(qc + qi) * W)[w4];
-            sq_lo[qi][w4] = reinterpret_cast<const uint4*>(a.q_lo + static_cast<size_t>(qc + qi) * W)[w4];
+            cp_async16(&sq_hi[buf][qi][4 * w4], a.q_hi + static_cast<size_t>(qc + qi) * W + 4 * w4);
+            cp_async16(&sq_lo[buf][qi][4 * w4], a.q_lo + static_cast<size_t>(qc + qi) * W + 4 * w4);
         }
-        if (threadIdx.x < nq) sq_len[threadIdx.x] = a.q_len[qc + threadIdx.x];
-        __syncthreads();
-        for (uint32_t qi = 0; qi < nq; ++qi) {
-            const uint32_t qlen = sq_len[qi];
-            const uint32_t fw = min(cta_minw, qlen >> 5);     // words that are full for every pair of this CTA
-            const uint32_t minlen = min(qlen, rlen);
-            uint32_t acc = 0;
+        if (threadIdx.x < nq) sq_len[buf][threadIdx.x] = a.q_len[qc + threadIdx.x];
+        if ((nq & 1u) && threadIdx.x < W) { sq_hi[buf][nq][threadIdx.x] = 0u; sq_lo[buf][nq][threadIdx.x] = 0u; }  // phantom partner of an odd chunk
+        if ((nq & 1u) && threadIdx.x == 0) sq_len[buf][nq] = 0u;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto commit = [&]() { asm volatile("cp.async.wait_group 0;" ::: "memory"); };
+    fetch(qs, 0);
+    if (threadIdx.x == 0) { s_minl = 0xffffffffu; s_maxl = 0u; }
+    __syncthreads();
+    {
+        const uint32_t mn = __reduce_min_sync(0xffffffffu, valid ? rlen : 0xffffffffu);
+        const uint32_t mx = __reduce_max_sync(0xffffffffu, valid ? rlen : 0u);
+        if (lane == 0) { atomicMin(&s_minl, mn); atomicMax(&s_maxl, mx); }
+    }
+    commit();
+    __syncthreads();
+    const uint32_t cta_minl = s_minl, cta_maxl = s_maxl;
+
+    uint32_t buf = 0;
+    for (uint32_t qc = qs; qc < qe; qc += kQChunk, buf ^= 1u) {
+        const uint32_t nq = min(uint32_t(kQChunk), qe - qc);
+        if (qc + kQChunk < qe) fetch(qc + kQChunk, buf ^ 1u);  // in flight during the compare loop below
+        // two queries per iteration: independent accumulators double the instruction-level parallelism and share the
+        // unit classification (the union of the two queries' classes; masking a plain word is always correct)
+        for (uint32_t qi = 0; qi < nq; qi += 2) {
+            const uint32_t qlen0 = sq_len[buf][qi], qlen1 = sq_len[buf][qi + 1];
+            const bool two = qi + 1 < nq;
+            // CTA-uniform unit classes (sequences are zero-padded, H9 zip truncation):
+            //   unit <  lo_u : inside min(len_q, len_r) for every row of the CTA      -> plain XOR/OR, carry-save, POPC
+            //   unit >= hi_u : beyond max(len_q, len_r) for every row: both are zero  -> skipped
+            //   between      : every mismatch word masked to min(len_q, len_r) of the pair
+            const uint32_t qmin = two ? min(qlen0, qlen1) : qlen0, qmax = max(qlen0, qlen1);
+            const uint32_t lo_u = (min(cta_minl, qmin) >> 5) / U;
+            const uint32_t hi_u = (((max(cta_maxl, qmax) + 31u) >> 5) + U - 1) / U;
+            const int minlen0 = static_cast<int>(min(qlen0, rlen)), minlen1 = static_cast<int>(min(qlen1, rlen));
+            uint32_t acc0 = 0, acc1 = 0;
 #pragma unroll
-            for (int w4 = 0; w4 < W / 4; ++w4) {
-                const uint4 qh = sq_hi[qi][w4];
-                const uint4 ql = sq_lo[qi][w4];
-                const uint32_t qhv[4] = {qh.x, qh.y, qh.z, qh.w};
-                const uint32_t qlv[4] = {ql.x, ql.y, ql.z, ql.w};
+            for (int u = 0; u < NU; ++u) {
+                if (uint32_t(u) >= hi_u) break;  // uniform
+                uint32_t m0[U], m1[U];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int w = 4 * w4 + k;
-                    uint32_t m = (rh[w] ^ qhv[k]) | (rl[w] ^ qlv[k]);
-                    if (uint32_t(w) >= fw) {  // CTA-uniform branch: tail words are masked to min(len_q, len_r) (H9)
-                        const int vb = int(minlen) - 32 * w;
-                        const uint32_t msk = vb >= 32 ? 0xffffffffu : (vb <= 0 ? 0u : ((1u << vb) - 1u));
-                        m &= msk;
+                for (int k = 0; k < U; ++k) {
+                    const int w = U * u + k;
+                    m0[k] = (rh[w] ^ sq_hi[buf][qi][w]) | (rl[w] ^ sq_lo[buf][qi][w]);
+                    m1[k] = (rh[w] ^ sq_hi[buf][qi + 1][w]) | (rl[w] ^ sq_lo[buf][qi + 1][w]);
+                }
+                if (uint32_t(u) >= lo_u) {  // uniform
+#pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        const int w = U * u + k;
+                        m0[k] &= prefix_mask(minlen0 - 32 * w);
+                        m1[k] &= prefix_mask(minlen1 - 32 * w);
                     }
-                    acc += __popc(m);
+                }
+                if (U == 6) {
+                    acc0 += popc3(m0[0], m0[1], m0[2]) + popc3(m0[3], m0[4], m0[5]);
+                    acc1 += popc3(m1[0], m1[1], m1[2]) + popc3(m1[3], m1[4], m1[5]);
+                } else {
+                    acc0 += popc3(m0[0], m0[1], m0[2]) + __popc(m0[3]);
+                    acc1 += popc3(m1[0], m1[1], m1[2]) + __popc(m1[3]);
                 }
             }
-            uint32_t key = valid ? ((acc << 8) | threadIdx.x) : 0xffffffffu;
-            key = __reduce_min_sync(0xffffffffu, key);
-            if (lane == 0) part[wib][qi] = key;
+            uint32_t key0 = valid ? ((acc0 << 8) | threadIdx.x) : 0xffffffffu;
+            uint32_t key1 = valid ? ((acc1 << 8) | threadIdx.x) : 0xffffffffu;
+            key0 = __reduce_min_sync(0xffffffffu, key0);
+            key1 = __reduce_min_sync(0xffffffffu, key1);
+            if (lane == 0) { part[wib][qi] = key0; part[wib][qi + 1] = key1; }
         }
         __syncthreads();
         if (threadIdx.x < nq) {
@@ -109,12 +162,14 @@ __global__ void __launch_bounds__(kRowsPerCta) hamming_min_kernel(const HamArgs 
                 atomicMin(a.best + qc + threadIdx.x, v);
             }
         }
+        __syncthreads();  // everyone is done with this chunk's queries and partial minima
+        if (qc + kQChunk < qe) { commit(); __syncthreads(); }
     }
 }
 
 template <int W>
 int launch(const HamArgs& a, uint32_t max_rows, uint32_t max_q, cudaStream_t s) {
-    dim3 grid((max_rows + 31 + kRowsPerCta - 1) / kRowsPerCta + 1, a.n_blocks, (max_q + kQSplit - 1) / kQSplit);
+    dim3 grid((max_rows + kRowsPerCta - 1) / kRowsPerCta, a.n_blocks, (max_q + kQSplit - 1) / kQSplit);
     hamming_min_kernel<W><<<grid, kRowsPerCta, 0, s>>>(a);
     return mmlst_cuda_fail(cudaGetLastError(), "hamming_min_kernel");
 }
