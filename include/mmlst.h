@@ -87,6 +87,23 @@ int mmlst_score_dev(const uint32_t* tid, const int16_t* as0, const uint8_t* xm3,
                     int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, uint64_t* counters, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Stage 1, coverage column (H7).  Replaces `sequenceBank[species_gene][readCode] = len(sequence)` (metamlst.py:127) and
+ * `sum(sequenceBank[key].values())` (metamlst.py:228): per locus the sum over UNIQUE read names of len(SEQ) of the LAST
+ * passing record (file order) carrying the name.
+ *   qhash[n_rec][2] : 128-bit QNAME hash per score-stream record (two independent 64-bit hashes, mmlst_bam_unpack);
+ *                     two names are merged only if both halves collide: P(any false merge) < n^2 / 2^129
+ *   table           : device scratch of 24 * table_slots bytes, 16-byte aligned, ZEROED by the caller;
+ *                     table_slots = mmlst_coverage_table_slots(upper bound on passing records), a power of two
+ *   cov[n_loci]     : ACCUMULATED (caller zeroes); shards that hold whole loci (contig-aligned) add up
+ * Same filter as mmlst_score_dev (allow, minscore, max_xm, min_read_len).
+ * --------------------------------------------------------------------------------------------------------------- */
+uint64_t mmlst_coverage_table_slots(uint64_t n_names_upper_bound);
+int mmlst_coverage_dev(const uint32_t* tid, const int16_t* as0, const uint8_t* xm3, const uint16_t* qlen,
+                       const uint32_t* orig_idx, const uint64_t* qhash, uint64_t n_rec, uint64_t idx_base,
+                       const uint8_t* allow, const uint32_t* locus_of, uint32_t n_ref, int minscore, int max_xm,
+                       int min_read_len, void* table, uint64_t table_slots, uint64_t* cov, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Stage 2 -- pileup base counts.  Replaces cmseq/cmseq.py:527-548 (+ htslib pileup rules H1-H3 applied at unpack).
  *   chunks[c]: a run of consecutive pileup-stream records of ONE chosen contig; its columns live at
  *   counts[col_base .. col_base+contig_len); plane_delta is added (mod 2^32) to row_off of its records so that a
@@ -190,6 +207,12 @@ int mmlst_hamming_min_dev(const uint32_t* db_hi, const uint32_t* db_lo, const ui
                           uint32_t W, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
                           const uint32_t* blocks, uint32_t n_blocks, uint32_t row_index_base,
                           unsigned long long* best, void* stream);
+/* same, with the grid sized by the caller: max_block_rows / max_block_queries = largest row / query range of any block
+ * (the plain form assumes every block may span everything) */
+int mmlst_hamming_min_dev2(const uint32_t* db_hi, const uint32_t* db_lo, const uint16_t* row_len, uint32_t n_rows,
+                           uint32_t W, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
+                           const uint32_t* blocks, uint32_t n_blocks, uint32_t max_block_rows, uint32_t max_block_queries,
+                           uint32_t row_index_base, unsigned long long* best, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what the Python seams call; host<->device copies inside).
@@ -211,6 +234,12 @@ typedef struct { int minscore, max_xm, min_read_len; } mmlst_score_params;
 /* seam S1 (metamlst.py:96-151): uploads the score stream, runs the kernel, returns the integer tables. */
 int mmlst_score(mmlst_ctx* ctx, const mmlst_soa* soa, const uint8_t* allow, const uint32_t* locus_of, uint32_t n_loci,
                 const mmlst_score_params* prm, int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, uint64_t* counters);
+
+/* seam S1, coverage column (metamlst.py:127,228).  MMLST_COVERAGE_STREAM_RESIDENT: the score stream of THIS soa is still
+ * in the context from the preceding mmlst_score call (only the 16 B/record hashes are uploaded). */
+#define MMLST_COVERAGE_STREAM_RESIDENT 1u
+int mmlst_coverage(mmlst_ctx* ctx, const mmlst_soa* soa, const uint64_t* qhash, const uint8_t* allow, const uint32_t* locus_of,
+                   uint32_t n_loci, const mmlst_score_params* prm, uint32_t flags, uint64_t* cov);
 
 /* seam S2 (metaMLST_functions.py:249-281): uploads the chosen contigs' pileup records, runs pileup + consensus.
  *   chosen_tid[n_loci], dbseq/col_off as in mmlst_consensus_dev; counts may be NULL. */
@@ -236,7 +265,7 @@ int mmlst_hamming_min(mmlst_ctx* ctx, const uint32_t* q_hi, const uint32_t* q_lo
  *   minqual       : pysam min_base_quality (20 at the only call site, metaMLST_functions.py:258)
  *   max_depth     : pysam pileup max_depth (8000 default reaches cmseq unchanged); 0 = no cap
  *   assume_sorted : metamlst.py --presorted -- keep the file order, MMLST_E_UNSORTED if it is not coordinate order
- *   want_qhash    : also emit a 64-bit hash of QNAME per score-stream record (coverage column, H7)
+ *   want_qhash    : also emit the 128-bit QNAME hash (2 x u64) per score-stream record (coverage column, H7)
  * --------------------------------------------------------------------------------------------------------------- */
 typedef struct mmlst_bam mmlst_bam;
 typedef struct {
@@ -245,7 +274,7 @@ typedef struct {
 } mmlst_unpack_opts;
 typedef struct {
     mmlst_soa soa;              /* pointers into memory owned by the mmlst_bam handle, page-locked when opts.pinned */
-    const uint64_t* qhash;      /* [n_rec] or NULL */
+    const uint64_t* qhash;      /* [n_rec][2] or NULL */
     const uint32_t* ref_len;    /* [n_ref] BAM header LN */
     const char* ref_names;      /* n_ref names joined by '\n' */
     const char* header_text;

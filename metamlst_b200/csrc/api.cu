@@ -75,6 +75,10 @@ struct mmlst_ctx {
     cudaStream_t stream = nullptr;
     // score stream
     DevBuf tid, as0, xm3, qlen, oidx, allow, locus_of, sum_as, n_hit, first_idx, counters;
+    uint64_t resident_n = 0;     // records of the score stream currently in tid/as0/xm3/qlen(/oidx)
+    bool resident_oidx = false;
+    // coverage (H7)
+    DevBuf qhash, cov_table, cov;
     // pileup stream (chosen contigs only)
     DevBuf p_recs, planes, chunks, counts, dbseq, col_off, cons, holes, snps;
     // hamming
@@ -85,7 +89,7 @@ struct mmlst_ctx {
     mmlst_ctx() {
         DevBuf* l[] = {&tid, &as0, &xm3, &qlen, &oidx, &allow, &locus_of, &sum_as, &n_hit, &first_idx, &counters, &p_recs,
                        &planes, &chunks, &counts, &dbseq, &col_off, &cons, &holes, &snps, &db_hi,
-                       &db_lo, &db_len, &q_hi, &q_lo, &q_len, &blocks, &best};
+                       &db_lo, &db_len, &q_hi, &q_lo, &q_len, &blocks, &best, &qhash, &cov_table, &cov};
         for (DevBuf* b : l) all[n_all++] = b;
     }
 };
@@ -148,6 +152,7 @@ extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* al
     TRY(h2d(c->xm3, soa->xm3, n, s));
     TRY(h2d(c->qlen, soa->qlen, n, s));
     if (soa->orig_idx) TRY(h2d(c->oidx, soa->orig_idx, n, s));
+    c->resident_n = n; c->resident_oidx = soa->orig_idx != nullptr;
     TRY(h2d(c->allow, allow, nr, s));
     TRY(h2d(c->locus_of, locus_of, nr, s));
     TRY(c->sum_as.reserve(nr * 8)); TRY(c->n_hit.reserve(nr * 4)); TRY(c->first_idx.reserve(nr * 4 + 4)); TRY(c->counters.reserve(16));
@@ -164,6 +169,45 @@ extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* al
     CUDA_TRY(cudaMemcpyAsync(n_hit, c->n_hit.p, nr * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(first_idx, c->first_idx.p, nr * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(counters, c->counters.p, 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return MMLST_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int mmlst_coverage(mmlst_ctx* c, const mmlst_soa* soa, const uint64_t* qhash, const uint8_t* allow,
+                              const uint32_t* locus_of, uint32_t n_loci, const mmlst_score_params* prm, uint32_t flags,
+                              uint64_t* cov) {
+    CTX_ENTER(c);
+    if (!soa || !qhash || !allow || !locus_of || !prm || !cov) { mmlst_set_error("mmlst_coverage: null pointer"); return MMLST_E_ARG; }
+    cudaStream_t s = c->stream;
+    const size_t n = soa->n_rec, nr = soa->n_ref;
+    if (flags & MMLST_COVERAGE_STREAM_RESIDENT) {
+        if (c->resident_n != n || c->resident_oidx != (soa->orig_idx != nullptr)) {
+            mmlst_set_error("mmlst_coverage: MMLST_COVERAGE_STREAM_RESIDENT but the context holds %llu records, the stream has %llu",
+                            (unsigned long long)c->resident_n, (unsigned long long)n);
+            return MMLST_E_ARG;
+        }
+    } else {
+        TRY(h2d(c->tid, soa->tid, n, s));
+        TRY(h2d(c->as0, soa->as0, n, s));
+        TRY(h2d(c->xm3, soa->xm3, n, s));
+        TRY(h2d(c->qlen, soa->qlen, n, s));
+        if (soa->orig_idx) TRY(h2d(c->oidx, soa->orig_idx, n, s));
+        c->resident_n = n; c->resident_oidx = soa->orig_idx != nullptr;
+    }
+    TRY(h2d(c->qhash, qhash, 2 * n, s));
+    TRY(h2d(c->allow, allow, nr, s));
+    TRY(h2d(c->locus_of, locus_of, nr, s));
+    const uint64_t slots = mmlst_coverage_table_slots(n);
+    TRY(c->cov_table.reserve(slots * 24));
+    TRY(c->cov.reserve((size_t)n_loci * 8 + 8));
+    CUDA_TRY(cudaMemsetAsync(c->cov_table.p, 0, slots * 24, s));
+    CUDA_TRY(cudaMemsetAsync(c->cov.p, 0, (size_t)n_loci * 8 + 8, s));
+    TRY(mmlst_coverage_dev(c->tid.as<uint32_t>(), c->as0.as<int16_t>(), c->xm3.as<uint8_t>(), c->qlen.as<uint16_t>(),
+                           soa->orig_idx ? c->oidx.as<uint32_t>() : nullptr, c->qhash.as<uint64_t>(), n, 0, c->allow.as<uint8_t>(),
+                           c->locus_of.as<uint32_t>(), (uint32_t)nr, prm->minscore, prm->max_xm, prm->min_read_len,
+                           c->cov_table.p, slots, c->cov.as<uint64_t>(), s));
+    CUDA_TRY(cudaMemcpyAsync(cov, c->cov.p, (size_t)n_loci * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return MMLST_OK;
 }

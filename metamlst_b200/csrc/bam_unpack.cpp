@@ -138,6 +138,13 @@ inline uint64_t hash64(const uint8_t* s, size_t n) {  // FNV-1a folded through a
     h ^= h >> 30; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 27; h *= 0x94d049bb133111ebull; h ^= h >> 31;
     return h;
 }
+// second, independent 64-bit hash (different multiplier, seed and finaliser): with hash64 it forms the 128-bit name key
+inline uint64_t hash64b(const uint8_t* s, size_t n) {
+    uint64_t h = 0x9e3779b97f4a7c15ull ^ (n * 0xff51afd7ed558ccdull);
+    for (size_t i = 0; i < n; ++i) { h = (h ^ s[i]) * 0xc6a4a7935bd1e995ull; h ^= h >> 47; }
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+    return h;
+}
 
 inline uint32_t touched_words(uint32_t pos, uint32_t reflen) { return reflen ? (((pos & 31u) + reflen + 31u) >> 5) : 0u; }
 inline uint32_t row_words(uint32_t nw) {  // 3 planes, padded to an odd word count
@@ -279,7 +286,7 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
     // ---- phase 4: per-record fields (file order)
     struct Core { int32_t tid, pos; uint32_t reflen; uint16_t flag; int16_t as0, asn; uint8_t xm3, xmn; uint16_t qlen; uint8_t named_ok; };
     std::vector<Core> core(n);
-    std::vector<uint64_t> qh(o.want_qhash ? n : 0);
+    std::vector<uint64_t> qh(o.want_qhash ? 2 * n : 0);
     parallel_for(n, threads, 1 << 15, [&](size_t a, size_t e) {
         for (size_t i = a; i < e; ++i) {
             const uint8_t* r = &u[roff[i]];
@@ -302,7 +309,7 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
             }
             if (c.flag & 0x2) { err.set(MMLST_E_PAIRED, "%s: record %zu is a proper-pair mate: htslib overlap handling (H2) is not implemented -- refusing", path, i); return; }
             if (c.pos < 0) { err.set(MMLST_E_BAM, "%s: record %zu has POS 0 on a reference", path, i); return; }
-            if (o.want_qhash) qh[i] = hash64(q, l_name - 1);
+            if (o.want_qhash) { qh[2 * i] = hash64(q, l_name - 1); qh[2 * i + 1] = hash64b(q, l_name - 1); }
             uint64_t rl = 0, qlsum = 0;
             for (uint32_t k = 0; k < n_cig; ++k) {
                 const uint32_t cw = rd32(cig + 4 * k), op = cw & 15u, ln = cw >> 4;
@@ -382,7 +389,7 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
 
     // ---- score stream (coordinate order)
     if (!B->tid.alloc(n * 4, pin) || !B->as0.alloc(n * 2, pin) || !B->xm3.alloc(n, pin) || !B->qlen.alloc(n * 2, pin) ||
-        (!sorted && !B->orig_idx.alloc(n * 4, pin)) || (o.want_qhash && !B->qhash.alloc(n * 8, pin)) ||
+        (!sorted && !B->orig_idx.alloc(n * 4, pin)) || (o.want_qhash && !B->qhash.alloc(n * 16, pin)) ||
         !B->contig_start.alloc(((size_t)n_ref + 1) * 8, false)) {
         mmlst_set_error("mmlst_bam_unpack: out of host memory"); return MMLST_E_NOMEM;
     }
@@ -394,7 +401,7 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
             const size_t i = src(k);
             tid[k] = (uint32_t)core[i].tid; as0[k] = core[i].as0; xm3[k] = core[i].xm3; ql[k] = core[i].qlen;
             if (!sorted) oi[k] = (uint32_t)i;
-            if (o.want_qhash) hq[k] = qh[i];
+            if (o.want_qhash) { hq[2 * k] = qh[2 * i]; hq[2 * k + 1] = qh[2 * i + 1]; }
         }
     });
 
