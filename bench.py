@@ -123,7 +123,7 @@ def make_db(args):
     return synth.make_db(ORGS, alleles_per_locus=args.alleles, n_profiles=2048, seed=1002)
 
 
-def gen_streams(db, args, device, max_depth, locus_subset=None, seed=1002, n_reads=None, chunk=1_000_000):
+def gen_streams(db, args, device, max_depth, locus_subset=None, seed=1002, n_reads=None, chunk=1_000_000, want_qhash=False):
     from metamlst_b200 import devpack, synth
     import torch
     n_reads = n_reads or args.reads
@@ -134,7 +134,7 @@ def gen_streams(db, args, device, max_depth, locus_subset=None, seed=1002, n_rea
         # keep only what the packer needs
         cores.append({k: core[k] for k in ("L", "K", "bases", "qual", "rtype", "a_split", "rows", "start", "flag", "AS", "xm")})
         del core
-    st = devpack.pack_cores(db, cores, 20, max_depth)
+    st = devpack.pack_cores(db, cores, 20, max_depth, want_qhash=want_qhash)
     n_ops = sum(int((c["rtype"] != 0).sum()) * 2 for c in cores) * args.k  # extra CIGAR ops beyond 1 per record
     del cores
     if device != "cpu":
@@ -354,6 +354,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_extras:
         line["uncapped"] = extra_uncapped(db, args, device, index, peak)
         line["hamming"] = extra_hamming(device, peak)
+        line["coverage_column"] = extra_coverage(db, args, device, index)
         rate, dt, sample = cpu_port_run(db, args, args.cpu_sample_reads, 1)
         line["cpu_baseline"] = {"value": rate, "unit": "records/s", "cores": 1, "kind": "port", "sample": sample, "host_cpus": os.cpu_count()}
     if rank == 0:
@@ -394,6 +395,29 @@ def extra_uncapped(db, args, device, index, peak):
         del pipe
     del out["_res"]
     del st
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_coverage(db, args, device, index):
+    """Coverage column (H7): unique-QNAME dedupe of the whole score stream (hash set in HBM, 128-bit CAS).  Off the headline
+    pass: display-only in the reference (metamlst.py:230), so it is timed on its own."""
+    import torch
+    from metamlst_b200 import pipeline
+    st, _ = gen_streams(db, args, device, args.max_depth or None, want_qhash=True)
+    pipe = pipeline.DevicePipeline(st, index, db.row_seq, impl=args.pileup_impl, **PARAMS)
+    cov = pipe.run_coverage()
+    ts = []
+    for _ in range(5):
+        cov2, t = pipe.run_coverage(timed=True)
+        assert cov2 == cov
+        ts.append(t)
+    R = int(st.tid.shape[0])
+    k = float(np.median([t["kernels_ms"] for t in ts])); m = float(np.median([t["memset_ms"] for t in ts]))
+    out = {"kernels_ms": k, "table_memset_ms": m, "records_per_s": R / ((k + m) / 1e3), "table_bytes": ts[0]["table_bytes"],
+           "stream_bytes": 25 * R, "loci": len(cov), "bases_total": int(sum(cov.values())),
+           "bound": "random 32-byte sector access (hash set), not streaming"}
+    del pipe, st
     torch.cuda.empty_cache()
     return out
 

@@ -201,12 +201,22 @@ int mmlst_consensus_indirect_dev(uint32_t* counts, const uint8_t* db_ascii, cons
  *               range (locus-restricted mode = one block per locus; all-pairs = one block).
  *   best[q]   = min over rows of (distance << 32 | row) as u64 -- ties resolve to the lowest row; caller presets
  *               ~0ull; results from row shards / GPUs combine with min.
- * Sequences holding non-ACGT letters are refused by the host packer in this version (H9 exception path TODO).
+ * H9: stringDiff compares characters.  A sequence holding anything but upper-case A/C/G/T is FLAGGED with bit 15 of its
+ * length (lengths are <= 1024); its planes carry the codes of its clean columns (0 elsewhere).  Flagged sequences are
+ * skipped by mmlst_hamming_min_dev and compared exactly by mmlst_hamming_exact_dev, which needs, for the flagged rows
+ * and the flagged queries each: ids[n] ascending, x[n][W] = bit-plane of the exceptional columns, bytes[n][W*32] = the
+ * ASCII characters (zero padded).  Both calls min-merge into the same best[].
  * --------------------------------------------------------------------------------------------------------------- */
 int mmlst_hamming_min_dev(const uint32_t* db_hi, const uint32_t* db_lo, const uint16_t* row_len, uint32_t n_rows,
                           uint32_t W, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
                           const uint32_t* blocks, uint32_t n_blocks, uint32_t row_index_base,
                           unsigned long long* best, void* stream);
+int mmlst_hamming_exact_dev(const uint32_t* db_hi, const uint32_t* db_lo, const uint16_t* row_len, uint32_t n_rows, uint32_t W,
+                            const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
+                            const uint32_t* blocks, uint32_t n_blocks, uint32_t row_index_base,
+                            const uint32_t* xr_ids, const uint32_t* xr_x, const uint8_t* xr_bytes, uint32_t n_xr,
+                            const uint32_t* xq_ids, const uint32_t* xq_x, const uint8_t* xq_bytes, uint32_t n_xq,
+                            unsigned long long* best, void* stream);
 /* same, with the grid sized by the caller: max_block_rows / max_block_queries = largest row / query range of any block
  * (the plain form assumes every block may span everything) */
 int mmlst_hamming_min_dev2(const uint32_t* db_hi, const uint32_t* db_lo, const uint16_t* row_len, uint32_t n_rows,
@@ -252,6 +262,12 @@ int mmlst_db_upload(mmlst_ctx* ctx, const uint32_t* db_hi, const uint32_t* db_lo
                     uint32_t n_rows, uint32_t W);
 int mmlst_hamming_min(mmlst_ctx* ctx, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
                       const uint32_t* blocks, uint32_t n_blocks, uint32_t* min_dist, uint32_t* argmin_row);
+/* the same two calls with the flagged (non-ACGT, H9) rows / queries attached; runs the fast and the exact kernels */
+int mmlst_db_upload_x(mmlst_ctx* ctx, const uint32_t* db_hi, const uint32_t* db_lo, const uint16_t* row_len, uint32_t n_rows,
+                      uint32_t W, const uint32_t* xr_ids, const uint32_t* xr_x, const uint8_t* xr_bytes, uint32_t n_xr);
+int mmlst_hamming_min_x(mmlst_ctx* ctx, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
+                        const uint32_t* xq_ids, const uint32_t* xq_x, const uint8_t* xq_bytes, uint32_t n_xq,
+                        const uint32_t* blocks, uint32_t n_blocks, uint32_t* min_dist, uint32_t* argmin_row);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * BAM ingest (HOST, C++ threads + zlib).  Replaces the `samtools view -h -` text pipe of stage 1 (metamlst.py:96-110),

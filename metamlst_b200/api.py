@@ -106,6 +106,24 @@ def score_soa(ctx: native.Context, soa: packing.SoaHost, index: AlleleIndex, min
     return cel, total, ignored, (sum_as, n_hit, first_idx)
 
 
+def coverage_sums(ctx: native.Context, soa: packing.SoaHost, index: AlleleIndex, minscore: int = 80, max_xM: int = 5,
+                  min_read_len: int = 50, species_filter: Optional[str] = None, stream_resident: bool = False) -> Dict[str, int]:
+    """Seam S1, coverage column (H7): {'species_gene': sum over unique QNAMEs of len(SEQ) of the last passing record} ==
+    `sum(sequenceBank[key].values())` at metamlst.py:228; keys exist for loci with at least one passing record.
+    `stream_resident`: the score stream is still on the device from the score_soa call just made on this context."""
+    if soa.qhash is None:
+        raise ValueError("stream was unpacked without QNAME hashes (unpack_bam(want_qhash=True))")
+    allow = index.allow_mask(species_filter)
+    cov = np.zeros(max(index.n_loci, 1), np.uint64)
+    cs = soa.c_struct()
+    prm = native.ScoreParams(int(minscore), int(max_xM), int(min_read_len))
+    qh = np.ascontiguousarray(soa.qhash, dtype=np.uint64)
+    native.check(native.lib().mmlst_coverage(ctx.handle, C.byref(cs), native.ptr(qh), native.ptr(allow), native.ptr(index.locus_of),
+                                             index.n_loci, C.byref(prm), native.COVERAGE_STREAM_RESIDENT if stream_resident else 0,
+                                             native.ptr(cov)))
+    return {s + "_" + g: int(cov[l]) for l, (s, g) in enumerate(index.locus_names) if cov[l]}
+
+
 def select_alleles(species_cel: Dict[str, Dict[str, tuple]]) -> List[Tuple[str, str]]:
     """metamlst.py:244: per locus (dict order) the lowest-numbered allele among those whose rounded average equals
     the locus maximum."""
@@ -192,11 +210,12 @@ class HammingIndex:
             self.block[(b, g)] = (lo, i + 1)
         seqs = [r[3].encode("latin-1") for r in self.rows]
         self.W = packing._w_for(max((len(s) for s in seqs), default=1))
-        hi, lo, ln = packing.encode_2bit(seqs, self.W)
+        hi, lo, ln, xids, xx, xb = packing.encode_2bit_x(seqs, self.W)  # rows with IUPAC / N / lower case: exact path (H9)
         self._hi, self._lo = packing.tile_db(hi, lo)
         self._len = ln
-        native.check(native.lib().mmlst_db_upload(ctx.handle, native.ptr(self._hi), native.ptr(self._lo), native.ptr(self._len),
-                                                  len(self.rows), self.W))
+        self.n_flagged_rows = int(xids.size)
+        native.check(native.lib().mmlst_db_upload_x(ctx.handle, native.ptr(self._hi), native.ptr(self._lo), native.ptr(self._len),
+                                                    len(self.rows), self.W, native.ptr(xids), native.ptr(xx), native.ptr(xb), int(xids.size)))
 
     @classmethod
     def from_sqlite(cls, ctx, conn, bacterium: Optional[str] = None):
@@ -215,7 +234,10 @@ class HammingIndex:
         # group queries with identical row ranges into blocks (queries of a block must be contiguous)
         order = sorted(range(nq), key=lambda i: ranges[i])
         qs = [queries[i].encode("latin-1") for i in order]
-        hi, lo, ln = packing.encode_2bit(qs, self.W)
+        if any(len(q) > self.W * 32 for q in qs):
+            # zip truncation (H9): columns beyond the longest DB row never take part in a comparison
+            qs = [q[: self.W * 32] for q in qs]
+        hi, lo, ln, xids, xx, xb = packing.encode_2bit_x(qs, self.W)
         blocks = []
         i = 0
         while i < nq:
@@ -227,8 +249,9 @@ class HammingIndex:
         blk = np.asarray(blocks, dtype=np.uint32).reshape(-1)
         md = np.zeros(nq, np.uint32)
         am = np.zeros(nq, np.uint32)
-        native.check(native.lib().mmlst_hamming_min(self.ctx.handle, native.ptr(hi), native.ptr(lo), native.ptr(ln), nq,
-                                                    native.ptr(blk), len(blocks), native.ptr(md), native.ptr(am)))
+        native.check(native.lib().mmlst_hamming_min_x(self.ctx.handle, native.ptr(hi), native.ptr(lo), native.ptr(ln), nq,
+                                                      native.ptr(xids), native.ptr(xx), native.ptr(xb), int(xids.size),
+                                                      native.ptr(blk), len(blocks), native.ptr(md), native.ptr(am)))
         out_d = np.zeros(nq, np.uint32)
         out_a = np.zeros(nq, np.uint32)
         out_d[order] = md

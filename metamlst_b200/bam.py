@@ -70,7 +70,7 @@ def unpack_bam(path: str, minqual: int = packing.DEFAULT_MINQUAL, max_depth: Opt
         _view(s.orig_idx, n, np.uint32) if s.orig_idx else None,
         _view(s.p_recs, P, packing.PREC_DTYPE), _view(s.planes, int(s.n_plane_words), np.uint32), int(s.max_row_words),
         _view(s.contig_start, n_ref + 1, np.uint64), int(info.minqual), int(info.max_depth), int(info.n_dropped_by_cap))
-    soa.qhash = _view(info.qhash, n, np.uint64) if info.qhash else None
+    soa.qhash = _view(info.qhash, 2 * n, np.uint64).reshape(n, 2) if info.qhash else None
     soa.header_text = (info.header_text or b"").decode("latin-1")
     soa.unpack_seconds = dict(zip(("read", "inflate", "parse", "sort", "pack"), [float(x) for x in info.seconds]))
     soa._keep = (keep,)

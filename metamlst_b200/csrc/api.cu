@@ -83,13 +83,14 @@ struct mmlst_ctx {
     DevBuf p_recs, planes, chunks, counts, dbseq, col_off, cons, holes, snps;
     // hamming
     DevBuf db_hi, db_lo, db_len, q_hi, q_lo, q_len, blocks, best;
-    uint32_t db_rows = 0, db_W = 0;
-    DevBuf* all[35];
+    DevBuf xr_ids, xr_x, xr_bytes, xq_ids, xq_x, xq_bytes;  // flagged (non-ACGT) rows / queries, H9
+    uint32_t db_rows = 0, db_W = 0, db_n_xr = 0;
+    DevBuf* all[48];
     int n_all = 0;
     mmlst_ctx() {
         DevBuf* l[] = {&tid, &as0, &xm3, &qlen, &oidx, &allow, &locus_of, &sum_as, &n_hit, &first_idx, &counters, &p_recs,
                        &planes, &chunks, &counts, &dbseq, &col_off, &cons, &holes, &snps, &db_hi,
-                       &db_lo, &db_len, &q_hi, &q_lo, &q_len, &blocks, &best, &qhash, &cov_table, &cov};
+                       &db_lo, &db_len, &q_hi, &q_lo, &q_len, &blocks, &best, &qhash, &cov_table, &cov, &xr_ids, &xr_x, &xr_bytes, &xq_ids, &xq_x, &xq_bytes};
         for (DevBuf* b : l) all[n_all++] = b;
     }
 };
@@ -318,31 +319,64 @@ extern "C" int mmlst_hamming_min_dev2(const uint32_t*, const uint32_t*, const ui
                                       const uint32_t*, const uint16_t*, uint32_t, const uint32_t*, uint32_t, uint32_t, uint32_t,
                                       uint32_t, unsigned long long*, void*);
 
-extern "C" int mmlst_db_upload(mmlst_ctx* c, const uint32_t* db_hi, const uint32_t* db_lo, const uint16_t* row_len,
-                               uint32_t n_rows, uint32_t W) {
+extern "C" int mmlst_hamming_exact_dev(const uint32_t*, const uint32_t*, const uint16_t*, uint32_t, uint32_t, const uint32_t*, const uint32_t*,
+                                       const uint16_t*, uint32_t, const uint32_t*, uint32_t, uint32_t, const uint32_t*, const uint32_t*,
+                                       const uint8_t*, uint32_t, const uint32_t*, const uint32_t*, const uint8_t*, uint32_t,
+                                       unsigned long long*, void*);
+
+extern "C" int mmlst_db_upload_x(mmlst_ctx* c, const uint32_t* db_hi, const uint32_t* db_lo, const uint16_t* row_len,
+                                 uint32_t n_rows, uint32_t W, const uint32_t* xr_ids, const uint32_t* xr_x,
+                                 const uint8_t* xr_bytes, uint32_t n_xr) {
     CTX_ENTER(c);
-    if (!db_hi || !db_lo || !row_len) { mmlst_set_error("mmlst_db_upload: null pointer"); return MMLST_E_ARG; }
+    if (!db_hi || !db_lo || !row_len || (n_xr && (!xr_ids || !xr_x || !xr_bytes))) { mmlst_set_error("mmlst_db_upload: null pointer"); return MMLST_E_ARG; }
+    for (uint32_t i = 0; i < n_xr; ++i) {
+        if (xr_ids[i] >= n_rows || (i && xr_ids[i] <= xr_ids[i - 1]) || !(row_len[xr_ids[i]] & 0x8000u)) {
+            mmlst_set_error("mmlst_db_upload: flagged-row list must be ascending, in range, and every listed row flagged (bit 15 of row_len)");
+            return MMLST_E_ARG;
+        }
+    }
     const size_t words = (size_t)((n_rows + 31) / 32) * 32 * W;
     TRY(h2d(c->db_hi, db_hi, words, c->stream));
     TRY(h2d(c->db_lo, db_lo, words, c->stream));
     TRY(h2d(c->db_len, row_len, n_rows, c->stream));
+    TRY(h2d(c->xr_ids, xr_ids, n_xr, c->stream));
+    TRY(h2d(c->xr_x, xr_x, (size_t)n_xr * W, c->stream));
+    TRY(h2d(c->xr_bytes, xr_bytes, (size_t)n_xr * W * 32, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    c->db_rows = n_rows; c->db_W = W;
+    c->db_rows = n_rows; c->db_W = W; c->db_n_xr = n_xr;
     return MMLST_OK;
 }
 
-extern "C" int mmlst_hamming_min(mmlst_ctx* c, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
-                                 const uint32_t* blocks, uint32_t n_blocks, uint32_t* min_dist, uint32_t* argmin_row) {
+extern "C" int mmlst_db_upload(mmlst_ctx* c, const uint32_t* db_hi, const uint32_t* db_lo, const uint16_t* row_len,
+                               uint32_t n_rows, uint32_t W) {
+    return mmlst_db_upload_x(c, db_hi, db_lo, row_len, n_rows, W, nullptr, nullptr, nullptr, 0);
+}
+
+extern "C" int mmlst_hamming_min_x(mmlst_ctx* c, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
+                                   const uint32_t* xq_ids, const uint32_t* xq_x, const uint8_t* xq_bytes, uint32_t n_xq,
+                                   const uint32_t* blocks, uint32_t n_blocks, uint32_t* min_dist, uint32_t* argmin_row) {
     CTX_ENTER(c);
     if (!c->db_rows) { mmlst_set_error("mmlst_hamming_min: no DB uploaded"); return MMLST_E_ARG; }
-    if (!q_hi || !q_lo || !q_len || !blocks || !min_dist || !argmin_row) { mmlst_set_error("mmlst_hamming_min: null pointer"); return MMLST_E_ARG; }
+    if (!q_hi || !q_lo || !q_len || !blocks || !min_dist || !argmin_row || (n_xq && (!xq_ids || !xq_x || !xq_bytes))) {
+        mmlst_set_error("mmlst_hamming_min: null pointer");
+        return MMLST_E_ARG;
+    }
     if (n_q == 0) return MMLST_OK;
+    for (uint32_t i = 0; i < n_xq; ++i) {
+        if (xq_ids[i] >= n_q || (i && xq_ids[i] <= xq_ids[i - 1]) || !(q_len[xq_ids[i]] & 0x8000u)) {
+            mmlst_set_error("mmlst_hamming_min: flagged-query list must be ascending, in range, and every listed query flagged (bit 15 of q_len)");
+            return MMLST_E_ARG;
+        }
+    }
     cudaStream_t s = c->stream;
     const uint32_t W = c->db_W;
     TRY(h2d(c->q_hi, q_hi, (size_t)n_q * W, s));
     TRY(h2d(c->q_lo, q_lo, (size_t)n_q * W, s));
     TRY(h2d(c->q_len, q_len, n_q, s));
     TRY(h2d(c->blocks, blocks, (size_t)n_blocks * 4, s));
+    TRY(h2d(c->xq_ids, xq_ids, n_xq, s));
+    TRY(h2d(c->xq_x, xq_x, (size_t)n_xq * W, s));
+    TRY(h2d(c->xq_bytes, xq_bytes, (size_t)n_xq * W * 32, s));
     TRY(c->best.reserve((size_t)n_q * 8));
     CUDA_TRY(cudaMemsetAsync(c->best.p, 0xff, (size_t)n_q * 8, s));
     uint32_t max_rows = 0, max_q = 0;
@@ -360,6 +394,12 @@ extern "C" int mmlst_hamming_min(mmlst_ctx* c, const uint32_t* q_hi, const uint3
                                    c->q_hi.as<uint32_t>(), c->q_lo.as<uint32_t>(), c->q_len.as<uint16_t>(), n_q,
                                    c->blocks.as<uint32_t>() + 4 * (size_t)b0, nb, max_rows, max_q, 0,
                                    c->best.as<unsigned long long>(), s));
+        TRY(mmlst_hamming_exact_dev(c->db_hi.as<uint32_t>(), c->db_lo.as<uint32_t>(), c->db_len.as<uint16_t>(), c->db_rows, W,
+                                    c->q_hi.as<uint32_t>(), c->q_lo.as<uint32_t>(), c->q_len.as<uint16_t>(), n_q,
+                                    c->blocks.as<uint32_t>() + 4 * (size_t)b0, nb, 0,
+                                    c->xr_ids.as<uint32_t>(), c->xr_x.as<uint32_t>(), c->xr_bytes.as<uint8_t>(), c->db_n_xr,
+                                    c->xq_ids.as<uint32_t>(), c->xq_x.as<uint32_t>(), c->xq_bytes.as<uint8_t>(), n_xq,
+                                    c->best.as<unsigned long long>(), s));
     }
     std::vector<unsigned long long> best(n_q);
     CUDA_TRY(cudaMemcpyAsync(best.data(), c->best.p, (size_t)n_q * 8, cudaMemcpyDeviceToHost, s));
@@ -369,6 +409,11 @@ extern "C" int mmlst_hamming_min(mmlst_ctx* c, const uint32_t* q_hi, const uint3
         argmin_row[q] = (uint32_t)(best[q] & 0xffffffffu);
     }
     return MMLST_OK;
+}
+
+extern "C" int mmlst_hamming_min(mmlst_ctx* c, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
+                                 const uint32_t* blocks, uint32_t n_blocks, uint32_t* min_dist, uint32_t* argmin_row) {
+    return mmlst_hamming_min_x(c, q_hi, q_lo, q_len, n_q, nullptr, nullptr, nullptr, 0, blocks, n_blocks, min_dist, argmin_row);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

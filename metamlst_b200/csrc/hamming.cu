@@ -3,7 +3,8 @@
 // XOR + LOP3 ((qh^rh)|(ql^rl)) and one POPC.  thread = DB row (planes held in registers, loaded coalesced from
 // 32-row word-major tiles), CTA = 256 rows, queries staged in shared memory and broadcast with 128-bit LDS;
 // per query a warp-level REDUX.MIN of (distance<<8 | row-in-CTA), then one 64-bit atomicMin per (CTA, query) of
-// (distance<<32 | row) which also resolves ties to the lowest row.
+// (distance<<32 | row) which also resolves ties to the lowest row.  Sequences flagged with bit 15 of their length hold
+// non-ACGT characters and are left to the exact path (hamming_exact.cu, H9).
 #include "common.cuh"
 
 namespace {
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(kRowsPerCta, 5) hamming_min_kernel(const HamAr
 
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t row = row0 + threadIdx.x;
-    const bool valid = (row < r_end) && (row < a.n_rows);
+    bool valid = (row < r_end) && (row < a.n_rows);
     uint32_t rh[W], rl[W];
     uint32_t rlen = 0;
     {
@@ -71,7 +72,11 @@ __global__ void __launch_bounds__(kRowsPerCta, 5) hamming_min_kernel(const HamAr
             rh[w] = inb ? a.db_hi[(static_cast<size_t>(tile) * W + w) * 32 + r] : 0u;
             rl[w] = inb ? a.db_lo[(static_cast<size_t>(tile) * W + w) * 32 + r] : 0u;
         }
-        if (valid) rlen = a.row_len[row];
+        if (valid) {
+            const uint32_t raw = a.row_len[row];
+            rlen = raw & 0x7fffu;
+            valid = !(raw & 0x8000u);  // bit 15: row holds non-ACGT characters -> exact path (hamming_exact.cu, H9)
+        }
     }
     // query staging is software-pipelined with cp.async (LDGSTS, no registers): chunk c+1 travels global -> the other
     // shared-memory buffer while chunk c is compared, and the first chunk is requested together with the row planes so
@@ -108,7 +113,7 @@ __global__ void __launch_bounds__(kRowsPerCta, 5) hamming_min_kernel(const HamAr
         // two queries per iteration: independent accumulators double the instruction-level parallelism and share the
         // unit classification (the union of the two queries' classes; masking a plain word is always correct)
         for (uint32_t qi = 0; qi < nq; qi += 2) {
-            const uint32_t qlen0 = sq_len[buf][qi], qlen1 = sq_len[buf][qi + 1];
+            const uint32_t qlen0 = sq_len[buf][qi] & 0x7fffu, qlen1 = sq_len[buf][qi + 1] & 0x7fffu;
             const bool two = qi + 1 < nq;
             // CTA-uniform unit classes (sequences are zero-padded, H9 zip truncation):
             //   unit <  lo_u : inside min(len_q, len_r) for every row of the CTA      -> plain XOR/OR, carry-save, POPC
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(kRowsPerCta, 5) hamming_min_kernel(const HamAr
             uint32_t key = 0xffffffffu;
 #pragma unroll
             for (int w = 0; w < kRowsPerCta / 32; ++w) key = min(key, part[w][threadIdx.x]);
-            if (key != 0xffffffffu) {
+            if (key != 0xffffffffu && !(sq_len[buf][threadIdx.x] & 0x8000u)) {  // flagged queries: exact path only
                 const unsigned long long v = (static_cast<unsigned long long>(key >> 8) << 32) |
                                              static_cast<unsigned long long>(a.row_index_base + row0 + (key & 255u));
                 atomicMin(a.best + qc + threadIdx.x, v);

@@ -84,7 +84,8 @@ class DeviceStreams:
         return soa.pin() if pinned else soa
 
 
-def pack_cores(db, cores: List[dict], minqual: int = 20, max_depth: Optional[int] = 8000, sentinel_nodes: int = 1) -> DeviceStreams:
+def pack_cores(db, cores: List[dict], minqual: int = 20, max_depth: Optional[int] = 8000, sentinel_nodes: int = 1,
+               want_qhash: bool = False) -> DeviceStreams:
     """Streams of a coordinate-sorted ("--presorted") BAM holding the records of all `cores` (chunks of one sample)."""
     dev = cores[0]["bases"].device
     K = cores[0]["K"]
@@ -116,8 +117,10 @@ def pack_cores(db, cores: List[dict], minqual: int = 20, max_depth: Optional[int
     s.as0 = AS[order].to(torch.int16)
     s.xm3 = xm[order].clamp(0, 255).to(torch.uint8)  # synthetic records always carry XS:i => 4th aux field is XM
     s.qlen = torch.full((n,), L, dtype=torch.int16, device=dev)
-    # depth cap on the host (sequential), then compaction on the device
     rd = read_of[order]
+    if want_qhash:  # 128-bit name key per record [n][2]: the read index itself (QNAME "r<id>": injective, so exact)
+        s.qhash = torch.stack([rd, torch.full_like(rd, 0x51ED270B0B1F2A37)], dim=1).contiguous()
+    # depth cap on the host (sequential), then compaction on the device
     p_reflen_all = reflen_r[rd]
     admitted = np.ones(n, dtype=np.uint8)
     if max_depth is not None:

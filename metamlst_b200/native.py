@@ -44,6 +44,11 @@ EXPORTS = {
     "mmlst_pinned_free": (None, [C.c_void_p]),
     "mmlst_score_dev": (C.c_int, [C.c_void_p] * 5 + [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmlst_coverage_table_slots": (C.c_uint64, [C.c_uint64]),
+    "mmlst_coverage_dev": (C.c_int, [C.c_void_p] * 6 + [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int,
+                                     C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "mmlst_coverage": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(ScoreParams),
+                                 C.c_uint32, C.c_void_p]),
     "mmlst_pileup_dev": (C.c_int, [C.c_void_p] * 3 + [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_uint32,
                                    C.c_int, C.c_void_p]),
     "mmlst_consensus_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
@@ -66,6 +71,13 @@ EXPORTS = {
     "mmlst_pileup_consensus": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmlst_db_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "mmlst_db_upload_x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_uint32]),
+    "mmlst_hamming_min_x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "mmlst_hamming_exact_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "mmlst_bam_unpack": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mmlst_bam_info": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mmlst_bam_free": (None, [C.c_void_p]),
@@ -74,7 +86,7 @@ EXPORTS = {
 }
 
 _lib = None
-SELECT_CONSUME, SELECT_SCRATCH_CLEAN, CONSENSUS_CONSUME = 1, 2, 1  # include/mmlst.h flags
+SELECT_CONSUME, SELECT_SCRATCH_CLEAN, CONSENSUS_CONSUME, COVERAGE_STREAM_RESIDENT = 1, 2, 1, 1  # include/mmlst.h flags
 
 
 def lib() -> C.CDLL:

@@ -46,7 +46,7 @@ class SoaHost:
     max_depth: int = DEFAULT_MAX_DEPTH
     n_dropped_by_cap: int = 0
     _keep: tuple = ()
-    qhash: Optional[np.ndarray] = None  # u64 [n_rec] QNAME hash (coverage column, H7); None when not unpacked
+    qhash: Optional[np.ndarray] = None  # u64 [n_rec][2] 128-bit QNAME hash (coverage column, H7); None when not unpacked
     header_text: str = ""
     unpack_seconds: Optional[dict] = None
 
@@ -91,7 +91,7 @@ class SoaHost:
         import torch
 
         keep = []
-        for name in ("tid", "as0", "xm3", "qlen", "orig_idx", "p_recs", "planes"):
+        for name in ("tid", "as0", "xm3", "qlen", "orig_idx", "p_recs", "planes", "qhash"):
             arr = getattr(self, name)
             if arr is None:
                 continue
@@ -247,9 +247,20 @@ def pack_table(tab, minqual: int = DEFAULT_MINQUAL, max_depth: Optional[int] = D
     recs = np.zeros(P, dtype=PREC_DTYPE)
     recs["pos"], recs["row_off"], recs["reflen"], recs["as_named"], recs["xm_named"] = p_pos, p_row_off[:-1], p_reflen, p_as, p_xm
     recs["nw"] = p_nw
-    return SoaHost(list(tab.ref_names), np.asarray(tab.ref_lens, dtype=np.int32), tid, as0, xm3, qlen, orig_idx,
-                   recs, planes, int(rw.max()) if P else 0, contig_start,
-                   minqual, max_depth if max_depth is not None else 0, int((~adm).sum()))
+    soa = SoaHost(list(tab.ref_names), np.asarray(tab.ref_lens, dtype=np.int32), tid, as0, xm3, qlen, orig_idx,
+                  recs, planes, int(rw.max()) if P else 0, contig_start,
+                  minqual, max_depth if max_depth is not None else 0, int((~adm).sum()))
+    soa.qhash = qname_key(tab.qname_id[order])
+    return soa
+
+
+def qname_key(qname_id: np.ndarray) -> np.ndarray:
+    """128-bit name key [n][2] of a synthetic table whose QNAMEs are "r<id>": the id itself (injective, so exact -- the
+    BAM unpacker hashes the name bytes instead; only equality of keys matters to the coverage kernel)."""
+    k = np.zeros((qname_id.shape[0], 2), dtype=np.uint64)
+    k[:, 0] = qname_id.astype(np.uint64)
+    k[:, 1] = np.uint64(0x51ED270B0B1F2A37)
+    return k
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -264,33 +275,46 @@ def _w_for(max_len: int) -> int:
     raise native.MmlstError(-7, "sequence of %d bases exceeds 1024 (W > 32 words per plane)" % max_len)
 
 
-def encode_2bit(seqs: Sequence[bytes], W: int):
-    """ASCII sequences -> (hi[n, W], lo[n, W], len[n]) uint32 bit-planes of the code A=0 C=1 G=2 T=3 (upper case
-    only: stringDiff compares characters, metaMLST_functions.py:230-234).  Non-ACGT letters are refused (H9 exception
-    path not implemented in this version)."""
+def encode_2bit_x(seqs: Sequence[bytes], W: int):
+    """ASCII sequences -> (hi[n, W], lo[n, W], len[n] u16, xids[m] u32, xx[m, W] u32, xbytes[m, W*32] u8).
+    Bit-planes of the code A=0 C=1 G=2 T=3, upper case only: stringDiff compares characters
+    (metaMLST_functions.py:230-234).  A sequence holding any other character (IUPAC, 'N', lower case, H9) is FLAGGED
+    with bit 15 of its length and listed in xids with the bit-plane of its exceptional columns (xx) and its ASCII bytes
+    (xbytes): the exact kernel compares those (include/mmlst.h)."""
     n = len(seqs)
     lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=n)
-    if n and lens.max() > 65535:
-        raise native.MmlstError(-7, "sequence longer than 65535")
+    if n and lens.max() > W * 32:
+        raise native.MmlstError(-7, "sequence longer than W*32")
     lut = np.full(256, 255, dtype=np.uint8)
     for i, ch in enumerate(b"ACGT"):
         lut[ch] = i
     mat = np.zeros((n, W * 32), dtype=np.uint8)
-    valid = np.zeros((n, W * 32), dtype=bool)
+    exc = np.zeros((n, W * 32), dtype=bool)
     flat = np.frombuffer(b"".join(seqs), dtype=np.uint8)
     rows = np.repeat(np.arange(n), lens)
     cols = np.arange(flat.shape[0]) - np.repeat(np.cumsum(lens) - lens, lens)
-    if n and lens.max() > W * 32:
-        raise native.MmlstError(-7, "sequence longer than W*32")
     codes = lut[flat]
-    if np.any(codes == 255):
-        bad = int(np.argmax(codes == 255))
-        raise native.MmlstError(-7, "non-ACGT letter %r in sequence %d: exact-character path (H9) not implemented" % (chr(flat[bad]), int(rows[bad])))
-    mat[rows, cols] = codes
-    valid[rows, cols] = True
+    bad = codes == 255
+    mat[rows, cols] = np.where(bad, 0, codes)
+    exc[rows[bad], cols[bad]] = True
     hi = _pack_bits_u32((mat & 2) != 0)
     lo = _pack_bits_u32((mat & 1) != 0)
-    return np.ascontiguousarray(hi), np.ascontiguousarray(lo), lens.astype(np.uint16)
+    ln = lens.astype(np.uint16)
+    xids = np.nonzero(exc.any(axis=1))[0].astype(np.uint32)
+    ln[xids] |= np.uint16(0x8000)
+    xx = np.ascontiguousarray(_pack_bits_u32(exc[xids])) if xids.size else np.zeros((0, W), np.uint32)
+    xbytes = np.zeros((xids.size, W * 32), dtype=np.uint8)
+    for k, i in enumerate(xids):
+        xbytes[k, : lens[i]] = np.frombuffer(seqs[int(i)], dtype=np.uint8)
+    return np.ascontiguousarray(hi), np.ascontiguousarray(lo), ln, xids, xx, xbytes
+
+
+def encode_2bit(seqs: Sequence[bytes], W: int):
+    """Strict form for clean (upper-case ACGT) sequences: (hi, lo, len); refuses anything the 2-bit planes cannot hold."""
+    hi, lo, ln, xids, _xx, _xb = encode_2bit_x(seqs, W)
+    if xids.size:
+        raise native.MmlstError(-7, "non-ACGT letter in sequence %d: use encode_2bit_x (exact-character path, H9)" % int(xids[0]))
+    return hi, lo, ln
 
 
 def tile_db(hi: np.ndarray, lo: np.ndarray):

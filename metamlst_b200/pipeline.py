@@ -143,6 +143,35 @@ class DevicePipeline:
         if self.dist:
             dist.allreduce_score_tables(self.sum_as, self.n_hit, self.first_idx, self.counters, self.group)
 
+    def run_coverage(self, timed: bool = False):
+        """Coverage column (H7, metamlst.py:127,228) of the resident score stream: {'species_gene': bases}.  Needs streams
+        packed with the 128-bit QNAME keys.  Contig-aligned shards hold whole loci, so ranks just add their tables."""
+        s = self.s
+        if getattr(s, "qhash", None) is None:
+            raise ValueError("streams were packed without QNAME keys (want_qhash)")
+        n = int(s.tid.shape[0])
+        slots = int(self.lib.mmlst_coverage_table_slots(n))
+        if getattr(self, "_cov_table", None) is None or self._cov_table.shape[0] < slots * 3:
+            self._cov_table = torch.empty(slots * 3, dtype=torch.int64, device=self.dev)
+            self._cov = torch.zeros(self.index.n_loci, dtype=torch.int64, device=self.dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        self._cov_table[: slots * 3].zero_(); self._cov.zero_()
+        ev[1].record()
+        native.check(self.lib.mmlst_coverage_dev(native.ptr(s.tid), native.ptr(s.as0), native.ptr(s.xm3), native.ptr(s.qlen), 0, native.ptr(s.qhash),
+                                                 n, self.idx_base, native.ptr(self.allow), native.ptr(self.locus_of), self.n_ref, self.minscore,
+                                                 self.max_xM, self.min_read_len, native.ptr(self._cov_table), slots, native.ptr(self._cov),
+                                                 self._stream()))
+        ev[2].record()
+        self.launches += 2
+        if self.dist:
+            torch.distributed.all_reduce(self._cov, group=self.group)
+        cov = self._cov.cpu().numpy()
+        out = {sp + "_" + g: int(cov[l]) for l, (sp, g) in enumerate(self.index.locus_names) if cov[l]}
+        if timed:
+            return out, {"memset_ms": ev[0].elapsed_time(ev[1]), "kernels_ms": ev[1].elapsed_time(ev[2]), "table_bytes": slots * 24}
+        return out
+
     def select(self):
         sum_as = self.sum_as.cpu().numpy()
         n_hit = self.n_hit.cpu().numpy().view(np.uint32)

@@ -49,7 +49,9 @@ def test_unpack_synthetic_bam(tmp_path, order, maxd):
     # same QNAME <=> same hash on this sample (K records per read share a name)
     qn = tab.qname_id if got.orig_idx is None else tab.qname_id[got.orig_idx]
     _, inv = np.unique(qn, return_inverse=True)
-    _, inv2 = np.unique(got.qhash, return_inverse=True)
+    assert got.qhash.shape == (tab.n, 2)
+    _, inv2 = np.unique(got.qhash, axis=0, return_inverse=True)
+    inv2 = inv2.reshape(-1)
     assert len(set(zip(inv.tolist(), inv2.tolist()))) == len(set(inv.tolist()))
 
 

@@ -55,6 +55,73 @@ def test_score_empty_and_thresholds(ctx):
     assert cel == {} and total == 0
 
 
+# ------------------------------------------------------------------------------------------------ coverage column (H7)
+def _np_coverage(tid, as0, xm3, qlen, idx, key, allow, locus_of, minscore, max_xm, min_len):
+    """numpy statement of metamlst.py:127,228 on raw arrays: last passing record per (locus, name) wins."""
+    ok = (allow[tid] != 0) & (as0 >= minscore) & (qlen >= min_len) & (xm3 <= max_xm)
+    want = {}
+    last = {}
+    for i in np.nonzero(ok)[0][np.argsort(idx[ok], kind="stable")]:
+        last[(int(locus_of[tid[i]]), int(key[i, 0]), int(key[i, 1]))] = int(qlen[i])
+    for (l, _a, _b), v in last.items():
+        want[l] = want.get(l, 0) + v
+    return want
+
+
+def test_coverage_matches_oracle_sequence_bank(ctx):
+    # the reference's sequenceBank on real records: K alignments of a read share its QNAME (unique per locus: 1 of K counts)
+    for order in ("name", "coord"):
+        db, tab = small_case(seed=33, n_reads=2500, orgs=("ecoli", "saureus"), apl=6, sub_err=0.02)
+        if order == "coord":
+            tab = tab.sorted_by_coord()
+        soa = packing.pack_table(tab)
+        index = api.AlleleIndex(tab.ref_names)
+        for filt in (None, "saureus"):
+            h, recs = table_to_records(tab)
+            _cel, bank, _t, _i = orc.stage1(h, recs, 176, 3, 50, filt, 100)
+            want = {k: sum(v.values()) for k, v in bank.items()}
+            assert api.coverage_sums(ctx, soa, index, 176, 3, 50, filt) == want
+            # resident form: right after the scoring call on the same context
+            api.score_soa(ctx, soa, index, 176, 3, 50, filt, 100)
+            assert api.coverage_sums(ctx, soa, index, 176, 3, 50, filt, stream_resident=True) == want
+
+
+def test_coverage_last_record_wins_and_names_shared_across_loci(ctx):
+    # raw streams: few distinct names (heavy duplication, the same name on several loci), random lengths, shuffled
+    # file order through orig_idx => the LAST record in FILE order decides (dict overwrite, metamlst.py:127)
+    rng = np.random.default_rng(5)
+    names = ["o_g%d_%d" % (g, a) for g in range(5) for a in range(1, 4)]
+    index = api.AlleleIndex(names)
+    for n in (1, 31, 1000, 70001):
+        tid = np.sort(rng.integers(0, len(names), n)).astype(np.uint32)
+        as0 = rng.integers(150, 201, n).astype(np.int16)
+        xm3 = rng.integers(0, 6, n).astype(np.uint8)
+        qlen = rng.integers(40, 152, n).astype(np.uint16)
+        key = np.zeros((n, 2), np.uint64)
+        key[:, 0] = rng.integers(0, max(2, n // 5), n).astype(np.uint64)
+        key[:, 1] = rng.integers(0, 2, n).astype(np.uint64)  # {0,0} occurs: the empty-slot sentinel must not swallow it
+        for oidx in (None, rng.permutation(n).astype(np.uint32)):
+            soa = packing.SoaHost(names, np.full(len(names), 500, np.int32), tid, as0, xm3, qlen, oidx,
+                                  np.zeros(0, packing.PREC_DTYPE), np.zeros(0, np.uint32), 0, np.zeros(len(names) + 1, np.uint64))
+            soa.qhash = key
+            idx = np.arange(n) if oidx is None else oidx.astype(np.int64)
+            want = _np_coverage(tid, as0.astype(int), xm3.astype(int), qlen.astype(int), idx, key, np.ones(len(names), np.uint8), index.locus_of, 170, 3, 50)
+            got = api.coverage_sums(ctx, soa, index, 170, 3, 50)
+            assert got == {"o_g%d" % l: v for l, v in want.items()}, n
+
+
+def test_coverage_from_bam_names(ctx, tmp_path):
+    # real QNAME bytes through the unpacker's 128-bit hash, unsorted file (orig_idx path), vs the oracle on the same BAM
+    from metamlst_b200 import bam
+    for name in ("basic", "two_org", "no_xs"):
+        d = os.path.join(GOLDEN, name)
+        h, recs = bamio.read_bam(os.path.join(d, "sample.bam"))
+        _cel, bank, _t, _i = orc.stage1(h, recs, 80, 5, 50, None, 100)
+        soa = bam.unpack_bam(os.path.join(d, "sample.bam"))
+        index = api.AlleleIndex(soa.ref_names)
+        assert api.coverage_sums(ctx, soa, index, 80, 5, 50) == {k: sum(v.values()) for k, v in bank.items()}, name
+
+
 # ------------------------------------------------------------------------------------------------ stage 2
 CASES = [
     dict(seed=41, n_reads=400, L=100, K=4, maxd=8000),
@@ -196,6 +263,50 @@ def test_hamming_min_bit_exact(ctx, n_rows, lo, hi):
     assert np.array_equal(d, wd) and np.array_equal(a, wa)
 
 
+@pytest.mark.parametrize("n_rows,frac_rows,frac_q", [(40, 0.2, 0.2), (900, 0.01, 0.1), (900, 0.3, 0.0), (300, 0.0, 0.5), (64, 1.0, 1.0)])
+def test_hamming_non_acgt_characters_exact_path(ctx, n_rows, frac_rows, frac_q):
+    """H9: stringDiff compares characters -- IUPAC codes, N and lower case in DB rows and/or queries; every pair with a
+    flagged side goes through the exact kernel, the rest through the 2-bit kernel, and both merge into one min/argmin."""
+    rng = np.random.default_rng(1000 + n_rows)
+    base = _rand_rows(rng, 1, 500, 500)[0]
+    odd = list("NRYKMSWnacgt-")
+
+    def mutate(s, n_sub, p_odd):
+        s = list(s)
+        for p in rng.integers(0, len(s), size=n_sub):
+            s[int(p)] = "ACGT"[int(rng.integers(0, 4))]
+        if rng.random() < p_odd:
+            for p in rng.integers(0, len(s), size=int(rng.integers(1, 6))):
+                s[int(p)] = odd[int(rng.integers(0, len(odd)))]
+        return "".join(s)
+
+    rows = [mutate(base[: int(l)], int(rng.integers(0, 6)), frac_rows) for l in rng.integers(420, 501, size=n_rows)]
+    rows[min(7, n_rows - 1)] = rows[2]  # duplicate (possibly flagged) row: the lowest index wins
+    loci = [("org", "g%d" % (i * 2 // n_rows)) for i in range(n_rows)]
+    idx = api.HammingIndex(ctx, [(o, g, i + 1, s) for i, ((o, g), s) in enumerate(zip(loci, rows))])
+    assert (idx.n_flagged_rows > 0) == (frac_rows > 0)
+    qs, ranges = [], []
+    for k in range(60):
+        r = int(rng.integers(0, n_rows))
+        q = mutate(rows[r], int(rng.integers(0, 4)), frac_q)
+        if k % 6 == 0:
+            q = q[: max(1, len(q) - int(rng.integers(0, 60)))]
+        if k % 9 == 0:
+            q = rows[r]  # identical to a (maybe flagged) row: distance 0 even through odd characters
+        qs.append(q)
+        ranges.append(idx.block[("org", loci[r][1])] if k % 2 else (0, n_rows))
+    flat = np.frombuffer("".join(r[3] for r in idx.rows).encode(), np.uint8)
+    off = np.zeros(n_rows + 1, np.int64)
+    off[1:] = np.cumsum([len(r[3]) for r in idx.rows])
+    wd, wa = corc.hamming_min([q.encode() for q in qs], flat, off, ranges)
+    d, a = idx.search(qs, ranges)
+    assert np.array_equal(d, wd) and np.array_equal(a, wa)
+    for k in range(0, 60, 7):  # and the reference's own per-character loop
+        r0, r1 = ranges[k]
+        dist = [orc.string_diff(qs[k], idx.rows[r][3]) for r in range(r0, r1)]
+        assert (int(d[k]), int(a[k])) == (min(dist), r0 + dist.index(min(dist)))
+
+
 def test_closest_allele_seam_matches_oracle_on_golden_cohort(ctx):
     d = os.path.join(GOLDEN, "cohort")
     odb = orc.OracleDB(os.path.join(d, "db.sqlite"))
@@ -256,9 +367,15 @@ def test_device_pipeline_equals_host_selected_path_and_oracle(ctx, case):
     db = synth.make_db(orgs, alleles_per_locus=6, n_profiles=10, seed=kw["seed"])
     gk = dict(read_len=kw["L"], seed=kw["seed"], K=kw["K"], sub_err=0.02)
     core = synth.gen_core(db, kw["n_reads"], device="cuda:0", **gk)
-    st = devpack.pack_cores(db, [core], 20, 8000)
+    st = devpack.pack_cores(db, [core], 20, 8000, want_qhash=True)
     tab = synth.make_sample(db, kw["n_reads"], device="cuda:0", **gk)
     index = api.AlleleIndex(db.ref_names())
+    # coverage column of the device-resident stream (H7) vs the numpy statement on the same reads
+    ms = 2 * kw["L"] - 30
+    ok = (tab.AS >= ms) & (np.where(tab.has_xs, tab.XM, tab.XO) <= 4) & (kw["L"] >= 50)
+    pairs = np.unique(np.stack([index.locus_of[tab.tid[ok]].astype(np.int64), tab.qname_id[ok]], axis=1), axis=0)
+    want_cov = {"%s_%s" % index.locus_names[int(l)]: int(c) * kw["L"] for l, c in zip(*np.unique(pairs[:, 0], return_counts=True))}
+    assert pipeline.DevicePipeline(st, index, db.row_seq, minscore=ms, max_xM=4).run_coverage() == want_cov
     for nloci in (100, 50):
         pipe = pipeline.DevicePipeline(st, index, db.row_seq, minscore=2 * kw["L"] - 30, max_xM=4, nloci=nloci)
         a = pipe.step()

@@ -88,3 +88,9 @@ def test_hamming_encoding_roundtrip_and_refusal():
     assert th.shape[0] == 32 * 8 and int(th[(0 * 8 + 2) * 32 + 2]) == int(hi[2, 2])
     with pytest.raises(native.MmlstError):
         packing.encode_2bit([b"ACGN"], 8)
+    # H9: the tolerant form flags the sequence (bit 15 of the length) and keeps the exceptional columns + bytes
+    hi, lo, ln, xids, xx, xb = packing.encode_2bit_x([b"ACGT", b"ACNTa" + b"G" * 40, b"TTTT"], 8)
+    assert list(ln) == [4, 45 | 0x8000, 4] and list(xids) == [1]
+    assert int(xx[0, 0]) == 0b10100 and int(xx[0, 1]) == 0 and bytes(xb[0, :6]) == b"ACNTaG" and xb.shape == (1, 256)
+    assert ((int(hi[1, 0]) >> 3) & 1, (int(lo[1, 0]) >> 3) & 1) == (1, 1)  # clean columns keep their code (T)
+    assert ((int(hi[1, 0]) >> 2) & 1, (int(lo[1, 0]) >> 2) & 1) == (0, 0)  # exceptional columns are 0 in the planes
