@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay of the pass")
     ap.add_argument("--cpu-sample-reads", type=int, default=400_000)
     ap.add_argument("--only-hamming", action="store_true", help="run only the configs[4] Hamming sweep (profiling aid)")
+    ap.add_argument("--exchange", default="gather", choices=["gather", "allreduce"],
+                    help="N>1: 'gather' = owner mode, one all-gather of result blocks per pass; 'allreduce' = partial score/count tensors all-reduced")
     ap.add_argument("--max-depth", type=int, default=8000, help="htslib pileup depth cap of the main workload (0 = uncapped; profiling aid)")
     return ap.parse_args()
 
@@ -208,19 +210,40 @@ def run_reference(args):
             "cpu_baseline": {"value": rate, "unit": "records/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference itself (pure Python over pysam/samtools) cannot run on this box; this is the C port of its restatement (oracle/c), a faster stand-in"}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, world):
     return {"workload": "configs[1]: single sample, %d x %d bp reads, K=%d alignments/read (%d BAM records per GPU), coordinate-sorted; "
                         "E. coli + S. aureus + K. pneumoniae synthetic schemes, 21 loci x %d alleles" % (args.reads, args.read_len, args.k, args.reads * args.k, args.alleles),
             "mode": ("parity (htslib max_depth %d, minqual 20, minscore 80, max_xM 5)" % args.max_depth) if args.max_depth else "uncapped (no depth cap; NOT the reference's semantics)",
-            "sharding": "replica" if world == 1 else "contig-aligned: each rank owns the records of a disjoint locus set; all-reduce SUM(sum_as,n_hit,counts) MIN(first_idx)",
+            "sharding": "replica" if world == 1 else ("contig-aligned: each rank owns the records of a disjoint locus set; " + (
+                "owner mode, ONE all-gather of the per-rank result blocks per pass" if args.exchange == "gather" else
+                "all-reduce SUM(sum_as,n_hit,counters) MIN(first_idx) SUM(counts)")),
             "l2": "the 360 MB score stream exceeds the 126 MB L2 and is re-streamed every step (no flush needed)"}
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Everything any library prints to fd 1 (NCCL's version banner, ...) goes to stderr; the ONE JSON line is written to
+    the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    (_REAL_STDOUT or sys.stdout).write(json.dumps(line) + "\n")
+    (_REAL_STDOUT or sys.stdout).flush()
 
 
 def main():
     args = parse()
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -237,7 +260,7 @@ def main():
     native.lib()  # fail loudly if the CUDA library is missing
     peak, peak_src = peaks()
     if args.only_hamming:
-        print(json.dumps({"hamming": extra_hamming(device, peak)}))
+        emit({"hamming": extra_hamming(device, peak)})
         return
 
     db = make_db(args)
@@ -246,7 +269,7 @@ def main():
     subset = None if world == 1 else [l for l in range(n_loci) if l % world == rank]
     st, _ = gen_streams(db, args, device, args.max_depth or None, subset, seed=1002 + rank)
     R_local = int(st.tid.shape[0])
-    pipe = pipeline.DevicePipeline(st, index, db.row_seq, impl=args.pileup_impl, idx_base=rank * R_local, **PARAMS)
+    pipe = pipeline.DevicePipeline(st, index, db.row_seq, impl=args.pileup_impl, idx_base=rank * R_local, exchange=args.exchange, **PARAMS)
 
     def barrier():
         if world > 1:
@@ -285,7 +308,6 @@ def main():
     out = pipe.collect()
     if prof:
         torch.cuda.profiler.stop()
-    clocks = sampler.stop()
     assert out == result, "results changed between steps"
     launches = pipe.launches
     # per-kernel durations: 20 back-to-back launches of each kernel of the same pass between two CUDA events on the
@@ -317,40 +339,75 @@ def main():
     line = {"metric": "aligned reads/s (score+pileup+consensus)", "value": R_total / (ms / 1e3), "unit": "records/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32/u8 (integer bit-plane arithmetic)", "data": "synthetic",
-            "config": workload_config(args, world), "clocks": clocks, "gpu_launches": launches,
+            "config": workload_config(args, world), "clocks": None, "gpu_launches": launches,
             "roofline": dict(rooflines[dominant], kernel=dominant, peak_source=peak_src), "rooflines": rooflines,
             "kernel_ms_per_step": kms, "records_per_gpu": R_local, "cuda_graph": use_graph,
             "non_kernel_ms_per_step": ms - sum(kms.values()), "latency_ms_per_step_with_host_sync": lat_ms}
 
-    # ---- end to end through the host-buffer C-ABI (pinned host memory -> results on the host)
+    # ---- end to end through the host-buffer C-ABI (pinned host memory -> results on the host), every rank on its own shard;
+    # with N>1 the ranks' results are all-gathered inside the timed region (each rank owns whole loci)
     soa = st.to_host(pinned=True)
     ctx = native.Context(local)
+
     def e2e_step():
         cel_raw = api.score_soa_raw(ctx, soa, index, **{k: PARAMS[k] for k in ("minscore", "max_xM", "min_read_len")})
         chosen = api.fast_select(index, cel_raw[0], cel_raw[1], cel_raw[2], PARAMS["penalty"])
         ts = [t for _sp, tt in chosen for t in tt]
         seqs, holes, snps, _, _ = api.pileup_consensus(ctx, soa, ts, [db.row_seq(t) for t in ts], PARAMS["minscore"], PARAMS["max_xM"], 1, args.pileup_impl)
-        return ts, seqs, holes, snps
-    if world == 1:
-        for _ in range(2):
-            r0 = e2e_step()
-        assert [s for s in r0[1]] == [s for sp in out for (_c, s, _h, _n) in out[sp]], "e2e result differs from the device-resident result"
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        n_e2e = max(3, min(args.steps, 10))
-        for _ in range(n_e2e):
-            e2e_step()
-        dt = (time.perf_counter() - t0) / n_e2e
-        h2d = 9 * R_local + db.n_rows * 5 + int(sum((st.contig_start[t + 1] - st.contig_start[t]) * 16 for t in tids))
-        proff = soa.p_row_off
-        h2d += int(sum(int(proff[int(st.contig_start[t + 1])]) - int(proff[int(st.contig_start[t])]) for t in tids)) * 4
-        d2h = db.n_rows * 16 + 16 + sum(int(st.ref_lens[t]) for t in tids) + 8 * len(tids)
-        line["e2e"] = {"value": R_local / dt, "unit": "records/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3}
-    else:
-        line["e2e"] = None
+        mine = {index.ref_names[t]: (seqs[i], int(holes[i]), int(snps[i])) for i, t in enumerate(ts)}
+        if world > 1:
+            parts = [None] * world
+            torch.distributed.all_gather_object(parts, mine)
+            mine = {k: v for p in parts for k, v in p.items()}
+        return ts, mine
+
+    for _ in range(2):
+        ts_local, r0 = e2e_step()
+    assert r0 == {c: (s_, h_, n_) for sp in out for (c, s_, h_, n_) in out[sp]}, "e2e result differs from the device-resident result"
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(3, min(args.steps, 10))
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    dt = (time.perf_counter() - t0) / n_e2e
+    clocks = sampler.stop()
+    line["clocks"] = clocks
+    h2d = 9 * R_local + db.n_rows * 5 + int(sum((st.contig_start[t + 1] - st.contig_start[t]) * 16 for t in ts_local))
+    proff = soa.p_row_off
+    h2d += int(sum(int(proff[int(st.contig_start[t + 1])]) - int(proff[int(st.contig_start[t])]) for t in ts_local)) * 4
+    d2h = db.n_rows * 16 + 16 + sum(int(st.ref_lens[t]) for t in ts_local) + 8 * len(ts_local)
+    tt = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device=device)
+    if world > 1:
+        mx = tt.clone(); torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.SUM)
+        dt = float(mx[0].item())
+    line["e2e"] = {"value": R_total / dt, "unit": "records/s", "h2d_bytes_per_step": int(tt[1].item()), "d2h_bytes_per_step": int(tt[2].item()),
+                   "ms_per_step": dt * 1e3, "timing": "host wall clock around the synchronous C-ABI calls, barrier on both sides, max over ranks"}
     ctx.close()
     del soa
 
+    if world > 1 and not args.no_extras:
+        # the other exchange form on the same shards, and the row-sharded Hamming sweep (configs[4])
+        other = "allreduce" if args.exchange == "gather" else "gather"
+        pipe2 = pipeline.DevicePipeline(st, index, db.row_seq, impl=args.pileup_impl, idx_base=rank * R_local, exchange=other, **PARAMS)
+        for _ in range(3):
+            res2 = pipe2.step()
+        assert res2 == result, "the two exchange forms disagree"
+        pipe2.capture()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            pipe2.enqueue_step()
+        f1.record()
+        barrier()
+        assert pipe2.collect() == result
+        t2 = torch.tensor([f0.elapsed_time(f1) / args.steps], dtype=torch.float64, device=device)
+        torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
+        line["other_exchange"] = {"exchange": other, "ms_per_step": float(t2.item()), "value": R_total / (float(t2.item()) / 1e3), "unit": "records/s"}
+        del pipe2
+        line["hamming_sharded"] = extra_hamming(device, peak, world=world, rank=rank)
     if rank == 0 and world == 1 and not args.no_extras:
         line["uncapped"] = extra_uncapped(db, args, device, index, peak)
         line["hamming"] = extra_hamming(device, peak)
@@ -358,9 +415,14 @@ def main():
         rate, dt, sample = cpu_port_run(db, args, args.cpu_sample_reads, 1)
         line["cpu_baseline"] = {"value": rate, "unit": "records/s", "cores": 1, "kind": "port", "sample": sample, "host_cpus": os.cpu_count()}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # no destroy_process_group(): tearing a communicator down while CUDA graphs that captured its kernels are alive
+        # can block forever; every rank has finished its work, so leave together and let the process exit
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def extra_uncapped(db, args, device, index, peak):
@@ -422,10 +484,12 @@ def extra_coverage(db, args, device, index):
     return out
 
 
-def extra_hamming(device, peak, n_rows=1_000_000, n_q=10_000):
-    """configs[4]: 10 k reconstructed loci vs 1 M DB alleles (length 480 +- 60), all-pairs and locus-restricted."""
+def extra_hamming(device, peak, n_rows=1_000_000, n_q=10_000, world=1, rank=0):
+    """configs[4]: 10 k reconstructed loci vs 1 M DB alleles (length 480 +- 60), all-pairs and locus-restricted.
+    world > 1: the DB rows are sharded over the ranks (queries replicated), best[q] = (distance << 32 | global row) is
+    all-reduced with MIN inside the timed region (strong scaling: the same 10 k x 1 M sweep on N GPUs)."""
     import torch
-    from metamlst_b200 import devpack, native
+    from metamlst_b200 import devpack, dist, native
     g = torch.Generator(device=device); g.manual_seed(1005)
     W = 24
     lens = (480 + torch.randint(-60, 61, (n_rows,), generator=g, device=device)).to(torch.int64)
@@ -451,13 +515,15 @@ def extra_hamming(device, peak, n_rows=1_000_000, n_q=10_000):
         & torch.randint(0, 2 ** 31 - 1, (n_q, W), generator=g, device=device, dtype=torch.int32) & torch.randint(0, 2 ** 31 - 1, (n_q, W), generator=g, device=device, dtype=torch.int32)
     qvalid = devpack._pack_words(col < lens[qsrc][:, None])
     q_hi = (q_hi ^ (flip & qvalid)).contiguous()  # ~1/64 of the bases substituted
-    nt = (n_rows + 31) // 32
     def tile(x):
+        nt = (x.shape[0] + 31) // 32
         p = torch.zeros((nt * 32, W), dtype=torch.int32, device=device)
-        p[:n_rows] = x
+        p[:x.shape[0]] = x
         return p.view(nt, 32, W).transpose(1, 2).contiguous().view(-1)
-    db_hi, db_lo = tile(hi), tile(lo)
-    row_len = lens.to(torch.int16)
+    sh0, sh1 = dist.shard_rows(n_rows, world, rank) if world > 1 else (0, n_rows)
+    n_loc = sh1 - sh0
+    db_hi, db_lo = tile(hi[sh0:sh1]), tile(lo[sh0:sh1])
+    row_len = lens[sh0:sh1].to(torch.int16).contiguous()
     best = torch.empty(n_q, dtype=torch.int64, device=device)
     lib = native.lib()
     stream = torch.cuda.current_stream().cuda_stream
@@ -495,12 +561,24 @@ def extra_hamming(device, peak, n_rows=1_000_000, n_q=10_000):
         return tot
 
     for name, (blk, mr, mq) in modes.items():
-        blk_d = torch.from_numpy(blk.view(np.int32).reshape(-1)).to(device)
+        # this rank's part of every block: rows clipped to [sh0, sh1) and rebased; blocks without local rows are dropped
+        loc = blk.astype(np.int64).copy()
+        loc[:, 2] = np.clip(loc[:, 2], sh0, sh1) - sh0
+        loc[:, 3] = np.clip(loc[:, 3], sh0, sh1) - sh0
+        loc = loc[loc[:, 3] > loc[:, 2]]
+        if loc.shape[0] == 0:
+            loc = np.asarray([[0, 0, 0, 0]], np.int64)
+        mr = int((loc[:, 3] - loc[:, 2]).max())
+        blk_d = torch.from_numpy(loc.astype(np.uint32).view(np.int32).reshape(-1)).to(device)
         def run():
             best.fill_(-1)
-            native.check(lib.mmlst_hamming_min_dev2(native.ptr(db_hi), native.ptr(db_lo), native.ptr(row_len), n_rows, W, native.ptr(q_hi), native.ptr(q_lo),
-                                                    native.ptr(q_len), n_q, native.ptr(blk_d), int(blk.shape[0]), int(mr), int(mq), 0, native.ptr(best), stream))
+            native.check(lib.mmlst_hamming_min_dev2(native.ptr(db_hi), native.ptr(db_lo), native.ptr(row_len), n_loc, W, native.ptr(q_hi), native.ptr(q_lo),
+                                                    native.ptr(q_len), n_q, native.ptr(blk_d), int(loc.shape[0]), max(mr, 1), int(mq), sh0, native.ptr(best), stream))
+            if world > 1:
+                dist.allreduce_best(best)
         run(); run()
+        if world > 1:
+            torch.distributed.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 3 if name == "all_pairs" else 20
@@ -510,6 +588,10 @@ def extra_hamming(device, peak, n_rows=1_000_000, n_q=10_000):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
+        if world > 1:
+            tm = torch.tensor([ms], dtype=torch.float64, device=device)
+            torch.distributed.all_reduce(tm, op=torch.distributed.ReduceOp.MAX)
+            ms = float(tm.item())
         pairs = float(sum((int(b[1]) - int(b[0])) * (int(b[3]) - int(b[2])) for b in blk))
         nq_used = int(sum(int(b[1]) - int(b[0]) for b in blk))
         comp = n_rows * S + nq_used * S + 8 * nq_used
@@ -523,7 +605,11 @@ def extra_hamming(device, peak, n_rows=1_000_000, n_q=10_000):
                      "algorithmic_words": words, "word_ops_per_s": words / (ms / 1e3), "popc_roof_words_per_s": popc_peak,
                      "popc_frac": words / (ms / 1e3) / popc_peak,
                      "effective_GBps_labelled_effective": pairs * S / ms / 1e6,
-                     "mean_min_dist": float((res[found] >> np.uint64(32)).astype(np.float64).mean())}
+                     "mean_min_dist": float((res[found] >> np.uint64(32)).astype(np.float64).mean()),
+                     "checksum_best": int(np.bitwise_xor.reduce(res[found] * np.uint64(0x9E3779B97F4A7C15))) if found.any() else 0}
+        if world > 1:
+            out[name]["n_gpus"] = world
+            out[name]["scaling"] = "strong (rows sharded, queries replicated, all-reduce MIN of best[] inside the timed region)"
     return out
 
 

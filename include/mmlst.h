@@ -177,12 +177,15 @@ int mmlst_consensus_dev(const uint32_t* counts, const uint8_t* dbseq, const uint
  * --------------------------------------------------------------------------------------------------------------- */
 #define MMLST_SELECT_CONSUME 1u
 #define MMLST_SELECT_SCRATCH_CLEAN 2u
+#define MMLST_SELECT_LOCAL 4u  /* this GPU owns a SUBSET of the loci (contig-aligned shard): no --nloci gate here; the caller
+                                  merges the per-GPU results (chosen_first gives the H5 order keys) and applies the gate */
 int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, const uint32_t* locus_rows, const uint32_t* locus_start,
                      const uint32_t* allele_num, uint32_t n_ref, const uint32_t* species_of_locus, const uint32_t* genes_in_db,
                      uint32_t n_loci, uint32_t n_species, int penalty, int nloci_pct, const uint64_t* contig_start,
                      const uint32_t* ref_len, const uint64_t* db_off, uint32_t chunk_records, void* scratch, size_t scratch_bytes,
                      uint32_t* header, uint32_t* chosen_tid, uint32_t* chosen_species, uint32_t* col_off, uint64_t* db_start,
-                     mmlst_chunk* chunks, uint32_t max_chunks, uint32_t flags, uint64_t* counters, void* stream);
+                     mmlst_chunk* chunks, uint32_t max_chunks, uint32_t flags, uint64_t* counters,
+                     uint32_t* chosen_first /* [n_loci] first passing record per chosen locus, or NULL */, void* stream);
 int mmlst_pileup_indirect_dev(const mmlst_prec* recs, const uint32_t* planes, const mmlst_chunk* chunks, const uint32_t* header,
                               uint32_t max_row_words, int minscore, int max_xm, uint32_t* counts, int impl, void* stream);
 /* flags: MMLST_CONSENSUS_CONSUME = zero every count that was read (the next pass accumulates from zero, no memset) */

@@ -56,6 +56,7 @@ struct SelArgs {
     uint32_t* header;  // [0]=n_chosen [1]=n_chunks [2]=total_cols [3]=error flags [4]=chunk_records used [6..9]=counters
     uint32_t* chosen_tid; uint32_t* chosen_species; uint32_t* col_off; unsigned long long* db_start;
     mmlst_chunk* chunks; uint32_t max_chunks;
+    uint32_t* chosen_first;  // optional: first passing record of every chosen locus (owner-computes merge across GPUs)
 };
 
 __device__ __forceinline__ long long tenths_of(long long score, uint32_t n, uint32_t mx, int penalty) {
@@ -216,7 +217,8 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
         const uint32_t det = s_detected[sp], tot = a.genes_in_db[sp];
         uint32_t pass = 0;
         if (det) {
-            if (tot < det) atomicOr(&s_err, 1u);  // "Database is broken" (metamlst.py:188-190)
+            if (a.flags & MMLST_SELECT_LOCAL) pass = 1;  // this GPU owns a subset of the loci: the gate is applied after the merge
+            else if (tot < det) atomicOr(&s_err, 1u);  // "Database is broken" (metamlst.py:188-190)
             else pass = int((double(det) / double(tot)) * 100.0) >= a.nloci_pct;  // metamlst.py:206
         }
         s_pass[sp] = pass;
@@ -244,6 +246,7 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
         const unsigned long long nrec = a.contig_start[tid + 1] - a.contig_start[tid];
         a.chosen_tid[rank] = tid;
         a.chosen_species[rank] = a.species_of_locus[m];
+        if (a.chosen_first) a.chosen_first[rank] = s_lfirst[m];
         a.db_start[rank] = a.db_off[tid];
         s_len[rank] = a.ref_len[tid];
         s_cbase[rank] = tid;  // parked here until the chunk size is known
@@ -313,7 +316,7 @@ extern "C" int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* firs
                                 const uint64_t* db_off, uint32_t chunk_records, void* scratch, size_t scratch_bytes,
                                 uint32_t* header, uint32_t* chosen_tid, uint32_t* chosen_species, uint32_t* col_off,
                                 uint64_t* db_start, mmlst_chunk* chunks, uint32_t max_chunks, uint32_t flags,
-                                uint64_t* counters, void* stream) {
+                                uint64_t* counters, uint32_t* chosen_first, void* stream) {
     if (!sum_as || !n_hit || !first_idx || !locus_rows || !locus_start || !allele_num || !species_of_locus || !genes_in_db ||
         !contig_start || !ref_len || !db_off || !scratch || !header || !chosen_tid || !chosen_species || !col_off || !db_start || !chunks) {
         mmlst_set_error("mmlst_select_dev: null pointer");
@@ -340,6 +343,7 @@ extern "C" int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* firs
     a.slots = static_cast<uint32_t>(mmlst_num_sms()) * MMLST_CHUNKS_PER_SM;
     a.header = header; a.chosen_tid = chosen_tid; a.chosen_species = chosen_species; a.col_off = col_off;
     a.db_start = reinterpret_cast<unsigned long long*>(db_start); a.chunks = chunks; a.max_chunks = max_chunks;
+    a.chosen_first = chosen_first;
     if (!(flags & MMLST_SELECT_SCRATCH_CLEAN)) CUDA_TRY(cudaMemsetAsync(a.done, 0, 4, s));
     const size_t smem = sizeof(uint32_t) * (static_cast<size_t>(n_loci) * 7 + 1 + 3 * static_cast<size_t>(n_species)) + 16;
     static size_t configured = 48 * 1024;

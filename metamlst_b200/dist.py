@@ -6,6 +6,10 @@ the order ranks arrive in.
                all-reduce SUM / SUM / MIN / SUM                                   (metamlst.py:118-130 aggregated)
     depth cap  sequential per contig (H1) => contig-aligned shards keep it rank-local, no exchange
     pileup     per-rank partial count tensor, all-reduce SUM                        (cmseq/cmseq.py:541-548 aggregated)
+    owner mode contig-aligned shards hold WHOLE loci, so a rank can select, pile up and call its own loci with no partial
+               tensor at all; the only exchange is ONE all-gather of the per-rank result blocks (chosen contig, first
+               record, consensus, holes, SNPs), after which the --nloci gate and the H5 order are applied on the merged
+               list (merge_owner_blocks).  The all-reduce form stays for shards that cut through loci.
     Hamming    DB rows sharded, queries replicated, best[q] = (distance << 32 | global row) all-reduce MIN
                (ties -> lowest row, metamlst-merge.py:177-181 order)
 """
@@ -62,6 +66,43 @@ def allreduce_score_tables(sum_as: torch.Tensor, n_hit: torch.Tensor, first_idx:
     td.all_reduce(first_idx, op=td.ReduceOp.MIN, group=group)
     first_idx.bitwise_xor_(SIGN32)
     td.all_reduce(counters, op=td.ReduceOp.SUM, group=group)
+
+
+def allreduce_score_block(zscore: torch.Tensor, first_idx: torch.Tensor, group=None) -> None:
+    """Same exchange in two calls: `zscore` is the contiguous int64 block [sum_as | counters | n_hit pairs] (two u32 hit
+    counts per int64 word add without carrying into each other as long as every total fits u32, which n_hit is by
+    type), first_idx MIN as above."""
+    if not active(group):
+        return
+    td.all_reduce(zscore, op=td.ReduceOp.SUM, group=group)
+    first_idx.bitwise_xor_(SIGN32)
+    td.all_reduce(first_idx, op=td.ReduceOp.MIN, group=group)
+    first_idx.bitwise_xor_(SIGN32)
+
+
+def merge_owner_blocks(blocks: Sequence[dict], species_names: Sequence[str], genes_in_db: Sequence[int], nloci_pct: int):
+    """Owner mode: per-rank results -> the sample's result in the reference's order.
+
+    blocks[r] = {"tid": [...], "species": [...species id...], "first": [...first passing record of the locus...],
+                 "payload": [...anything per locus...]} for the loci rank r owns and detected.
+    metamlst.py:184-206: a species is processed iff int(detected / loci_in_db * 100) >= nloci ("Database is broken" when
+    more loci are detected than the DB lists); dict order (H5) = species by their first passing record, loci inside a
+    species by theirs.  Returns [(species name, [(tid, payload)])]."""
+    per_species = {}
+    for b in blocks:
+        for t, sp, f, pay in zip(b["tid"], b["species"], b["first"], b["payload"]):
+            per_species.setdefault(int(sp), []).append((int(f), int(t), pay))
+    out = []
+    for sp, lst in per_species.items():
+        det, tot = len(lst), int(genes_in_db[sp])
+        if tot < det:
+            raise RuntimeError("Database is broken: a species has more detected loci than the genes table lists (metamlst.py:188)")
+        if int((float(det) / float(tot)) * 100) < nloci_pct:
+            continue
+        lst.sort()
+        out.append((lst[0][0], species_names[sp], [(t, pay) for _f, t, pay in lst]))
+    out.sort(key=lambda x: x[0])
+    return [(name, lst) for _f, name, lst in out]
 
 
 def allreduce_counts(counts: torch.Tensor, group=None) -> None:

@@ -60,7 +60,7 @@ EXPORTS = {
                                          C.c_void_p, C.c_void_p]),
     "mmlst_select_dev": (C.c_int, [C.c_void_p] * 6 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t] + [C.c_void_p] * 6 +
-                         [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+                         [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmlst_pileup_indirect_dev": (C.c_int, [C.c_void_p] * 4 + [C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "mmlst_consensus_indirect_dev": (C.c_int, [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_uint32, C.c_void_p]),
@@ -86,7 +86,7 @@ EXPORTS = {
 }
 
 _lib = None
-SELECT_CONSUME, SELECT_SCRATCH_CLEAN, CONSENSUS_CONSUME, COVERAGE_STREAM_RESIDENT = 1, 2, 1, 1  # include/mmlst.h flags
+SELECT_CONSUME, SELECT_SCRATCH_CLEAN, SELECT_LOCAL, CONSENSUS_CONSUME, COVERAGE_STREAM_RESIDENT = 1, 2, 4, 1, 1  # include/mmlst.h flags
 
 
 def lib() -> C.CDLL:

@@ -30,7 +30,10 @@ class DevicePipeline:
     def __init__(self, streams, index: api.AlleleIndex, dbseq_of: Callable[[int], str], minscore: int = 80, max_xM: int = 5,
                  min_read_len: int = 50, penalty: int = 100, species_filter: Optional[str] = None, mincov: int = 1,
                  impl: int = 0, idx_base: int = 0, group=None, nloci: int = 100, genes_in_db: Optional[Dict[str, int]] = None,
-                 db_ascii: Optional[np.ndarray] = None, db_off: Optional[np.ndarray] = None):
+                 db_ascii: Optional[np.ndarray] = None, db_off: Optional[np.ndarray] = None, exchange: str = "allreduce"):
+        """exchange (only with torch.distributed, world > 1): "allreduce" = partial score / count tensors are all-reduced
+        (any record sharding whose depth cap was resolved beforehand); "gather" = owner mode for contig-aligned shards:
+        each rank finishes its own loci and ONE all-gather of the result blocks ends the pass (dist.merge_owner_blocks)."""
         self.s = streams
         self.index = index
         self.dbseq_of = dbseq_of
@@ -38,6 +41,10 @@ class DevicePipeline:
         self.mincov, self.impl, self.idx_base = int(mincov), int(impl), int(idx_base)
         self.group = group
         self.dist = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+        if exchange not in ("allreduce", "gather"):
+            raise ValueError("exchange must be 'allreduce' or 'gather'")
+        self.owner = self.dist and exchange == "gather"
+        self.world = torch.distributed.get_world_size() if self.dist else 1
         dev = streams.tid.device
         self.dev = dev
         n_ref = len(index.ref_names)
@@ -48,6 +55,7 @@ class DevicePipeline:
         self.max_cols = int(np.sort(np.asarray(streams.ref_lens))[::-1][: index.n_loci].sum())
         w_hit, w_cnt = (n_ref + 1) // 2, (self.max_cols * 5 + 8 + 1) // 2
         self.zblock = torch.zeros(n_ref + 2 + w_hit + w_cnt, dtype=torch.int64, device=dev)
+        self.zscore = self.zblock[: n_ref + 2 + w_hit]  # [sum_as | counters | n_hit]: one SUM all-reduce
         self.sum_as = self.zblock[:n_ref]
         self.counters = self.zblock[n_ref:n_ref + 2]
         self.n_hit = self.zblock[n_ref + 2:n_ref + 2 + w_hit].view(torch.int32)[:n_ref]
@@ -93,16 +101,23 @@ class DevicePipeline:
         # ONE output block => one D2H node per pass: int32 header[16] | chosen_tid[nl] | chosen_species[nl] | col_off[nl+1] |
         # holes[nl] | snps[nl] | pad, then the consensus bytes
         self.o_hdr, self.o_tid, self.o_sp, self.o_col, self.o_holes, self.o_snps = 0, 16, 16 + nl, 16 + 2 * nl, 17 + 3 * nl, 17 + 4 * nl
-        self.n_small = (17 + 5 * nl + 7) // 4 * 4
+        self.o_first = 17 + 5 * nl
+        self.n_small = (17 + 6 * nl + 7) // 4 * 4
         self.out = torch.zeros(self.n_small * 4 + self.max_cols + 16, dtype=torch.uint8, device=dev)
         self.small = self.out[: self.n_small * 4].view(torch.int32)
         self.cons = self.out[self.n_small * 4:]
         self.holes = self.small[self.o_holes:self.o_holes + nl]
         self.snps = self.small[self.o_snps:self.o_snps + nl]
         self.db_start_d = torch.zeros(nl + 1, dtype=torch.int64, device=dev)
-        self.out_h = torch.zeros(self.out.shape[0], dtype=torch.uint8).pin_memory()
+        self.out_bytes = int(self.out.shape[0])
+        if self.owner:  # every rank's block, gathered
+            self.out_all = torch.zeros(self.world * self.out_bytes, dtype=torch.uint8, device=dev)
+            self.out_h = torch.zeros(self.world * self.out_bytes, dtype=torch.uint8).pin_memory()
+        else:
+            self.out_h = torch.zeros(self.out_bytes, dtype=torch.uint8).pin_memory()
         self.small_h = self.out_h[: self.n_small * 4].view(torch.int32)
-        self.cons_h = self.out_h[self.n_small * 4:]
+        self.cons_h = self.out_h[self.n_small * 4: self.out_bytes]
+        self.genes_in_db_h = gdb
         self._clean = False  # score tables / counts / scratch hold the "nothing accumulated" state
         self.timers: Optional[Dict[str, list]] = None  # name -> [(start_event, end_event)]
         self.launches = 0
@@ -140,8 +155,8 @@ class DevicePipeline:
                                                   self._stream()))
         self._timed("score", k)
         self.launches += 1
-        if self.dist:
-            dist.allreduce_score_tables(self.sum_as, self.n_hit, self.first_idx, self.counters, self.group)
+        if self.dist and not self.owner:
+            dist.allreduce_score_block(self.zscore, self.first_idx, self.group)
 
     def run_coverage(self, timed: bool = False):
         """Coverage column (H7, metamlst.py:127,228) of the resident score stream: {'species_gene': bases}.  Needs streams
@@ -232,7 +247,8 @@ class DevicePipeline:
                                                native.ptr(self.contig_start_d), native.ptr(self.ref_len_d), native.ptr(self.db_off_d), 0,
                                                native.ptr(self.scratch), int(self.scratch.shape[0]), base + 4 * self.o_hdr, base + 4 * self.o_tid,
                                                base + 4 * self.o_sp, base + 4 * self.o_col, native.ptr(self.db_start_d), native.ptr(self.chunks_d),
-                                               self.max_chunks, flags, native.ptr(self.counters), self._stream()))
+                                               self.max_chunks, flags | (native.SELECT_LOCAL if self.owner else 0), native.ptr(self.counters),
+                                               base + 4 * self.o_first, self._stream()))
 
     def _consensus_call(self, flags: int):
         nl = self.index.n_loci
@@ -258,11 +274,15 @@ class DevicePipeline:
         self.launches += 1
         self._timed("pileup", self._pileup_call)
         self.launches += 1
-        if self.dist:
+        if self.dist and not self.owner:
             dist.allreduce_counts(self.counts, self.group)
         self._timed("consensus", lambda: self._consensus_call(native.CONSENSUS_CONSUME))
         self.launches += 1
-        self.out_h.copy_(self.out, non_blocking=True)
+        if self.owner:  # the pass's only exchange: every rank ends up with every rank's result block
+            torch.distributed.all_gather_into_tensor(self.out_all, self.out, group=self.group)
+            self.out_h.copy_(self.out_all, non_blocking=True)
+        else:
+            self.out_h.copy_(self.out, non_blocking=True)
         self._clean = True
 
     def time_kernels(self, reps: int = 20) -> Dict[str, float]:
@@ -307,7 +327,31 @@ class DevicePipeline:
         else:
             raise ValueError(name)
 
+    def _finish_owner(self):
+        nl = self.index.n_loci
+        blocks, total, ignored = [], 0, 0
+        for r in range(self.world):
+            blk = self.out_h[r * self.out_bytes:(r + 1) * self.out_bytes]
+            h = blk[: self.n_small * 4].view(torch.int32).numpy()
+            cons = blk[self.n_small * 4:].numpy()
+            n = int(h[0])
+            total += int(h[6:8].view(np.uint64)[0]); ignored += int(h[8:10].view(np.uint64)[0])
+            if h[3] & 2:
+                raise RuntimeError("chunk list overflow")
+            tids = h[self.o_tid:self.o_tid + n]
+            if self.bad_len[tids].any():
+                raise IndexError("string index out of range: BAM LN > DB sequence length (metaMLST_functions.py:267)")
+            col = h[self.o_col:self.o_col + n + 1]
+            blocks.append({"tid": tids.tolist(), "species": h[self.o_sp:self.o_sp + n].tolist(),
+                           "first": h[self.o_first:self.o_first + n].view(np.uint32).tolist(),
+                           "payload": [(cons[col[i]:col[i + 1]].tobytes().decode("latin-1"), int(h[self.o_holes + i]), int(h[self.o_snps + i])) for i in range(n)]})
+        self.total_reads, self.ignored_reads = total, ignored
+        merged = dist.merge_owner_blocks(blocks, self.species_names, self.genes_in_db_h, self.nloci)
+        return {sp: [(self.index.ref_names[t], seq, holes, snps) for t, (seq, holes, snps) in lst] for sp, lst in merged}
+
     def _finish(self):
+        if self.owner:
+            return self._finish_owner()
         h = self.small_h.numpy()
         n = int(h[0])
         self.total_reads = int(h[6:8].view(np.uint64)[0])      # metamlst.py:130 totalReads
@@ -418,7 +462,7 @@ def device_select(index: api.AlleleIndex, sum_as: np.ndarray, n_hit: np.ndarray,
                                       n_ref, native.ptr(t_sol), native.ptr(t_gdb), nl, len(names), int(penalty), int(nloci), native.ptr(t_cs),
                                       native.ptr(t_rl), native.ptr(t_dbo), 0, native.ptr(scratch), int(scratch.shape[0]), base,
                                       base + 4 * 16, base + 4 * (16 + nl), base + 4 * (16 + 2 * nl), native.ptr(dbs), native.ptr(chunks), nl + 8,
-                                      0, 0, torch.cuda.current_stream(dev).cuda_stream))
+                                      0, 0, 0, torch.cuda.current_stream(dev).cuda_stream))
     h = small.cpu().numpy()
     n = int(h[0])
     out: Dict[str, List[int]] = {}

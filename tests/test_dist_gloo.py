@@ -45,10 +45,39 @@ def _worker(rank, world, port, ret):
         assert np.array_equal(t_s.numpy(), ws) and np.array_equal(t_c.numpy().view(np.uint32), wc)
         assert np.array_equal(t_f.numpy().view(np.uint32), wf), "first-record indices (H5) differ after MIN reduce"
         assert np.array_equal(t_cnt.numpy().view(np.uint64), wcnt)
+        # the two-call form: [sum_as | counters | n_hit pairs] as ONE int64 SUM + first_idx MIN
+        n_ref = s.shape[0]
+        zb = torch.zeros(n_ref + 2 + (n_ref + 1) // 2, dtype=torch.int64)
+        zb[:n_ref] = torch.from_numpy(s.copy()); zb[n_ref:n_ref + 2] = torch.from_numpy(cnt.view(np.int64).copy())
+        zb[n_ref + 2:].view(torch.int32)[:n_ref] = torch.from_numpy(c.view(np.int32).copy())
+        f2 = torch.from_numpy(f.view(np.int32).copy())
+        dist.allreduce_score_block(zb, f2)
+        assert np.array_equal(zb[:n_ref].numpy(), ws) and np.array_equal(zb[n_ref:n_ref + 2].numpy().view(np.uint64), wcnt)
+        assert np.array_equal(zb[n_ref + 2:].view(torch.int32)[:n_ref].numpy().view(np.uint32), wc) and np.array_equal(f2.numpy().view(np.uint32), wf)
         # every rank now selects the same alleles
         index = api.AlleleIndex(tab.ref_names)
         chosen = api.fast_select(index, t_s.numpy(), t_c.numpy().view(np.uint32), t_f.numpy().view(np.uint32), 100)
         tids = [t for _sp, ts in chosen for t in ts]
+        # owner mode: each rank selects among ITS loci from ITS partial tables only; one all-gather of the per-rank results and
+        # the merge (gate + H5 order) must reproduce the whole-sample selection
+        sp_names = []
+        for sp, _g in index.locus_names:
+            if sp not in sp_names:
+                sp_names.append(sp)
+        gdb = [sum(1 for sp2, _g in index.locus_names if sp2 == sp) for sp in sp_names]
+        local = api.fast_select(index, s, c, f, 100)
+        blk = {"tid": [], "species": [], "first": [], "payload": []}
+        for sp, ts in local:
+            for t in ts:
+                l = int(index.locus_of[t])
+                rows_l = np.nonzero((index.locus_of == l) & (c > 0))[0]
+                blk["tid"].append(int(t)); blk["species"].append(sp_names.index(sp)); blk["first"].append(int(f[rows_l].min())); blk["payload"].append(int(t) * 7)
+        parts = [None] * world
+        td.all_gather_object(parts, blk)
+        for nloci in (100, 60, 0):
+            merged = dist.merge_owner_blocks(parts, sp_names, gdb, nloci)
+            want = [(sp, [(t, t * 7) for t in ts]) for sp, ts in chosen if int((float(len(ts)) / float(gdb[sp_names.index(sp)])) * 100) >= nloci]
+            assert merged == want, (nloci, merged, want)
         # pileup counts: a rank contributes the contigs it owns (depth cap local to the contig), zeros elsewhere
         lens = [int(st.ref_lens[t]) for t in tids]
         col_off = np.concatenate([[0], np.cumsum(lens)])
