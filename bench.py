@@ -220,7 +220,7 @@ def workload_config(args, world):
             "sharding": "replica" if world == 1 else ("contig-aligned: each rank owns the records of a disjoint locus set; " + (
                 "owner mode, ONE all-gather of the per-rank result blocks per pass" if args.exchange == "gather" else
                 "all-reduce SUM(sum_as,n_hit,counters) MIN(first_idx) SUM(counts)")),
-            "l2": "the 360 MB score stream exceeds the 126 MB L2 and is re-streamed every step (no flush needed)"}
+            "l2": "the %d MB score stream (run-length form, 5 B/record) exceeds the 126 MB L2 and is re-streamed every step (no flush needed)" % (args.reads * args.k * 5 // 1000000)}
 
 
 _REAL_STDOUT = None
@@ -325,11 +325,19 @@ def main():
     ms = float(t.item())
     R_total = R_local * world
     tids = [index.name_to_tid[c] for sp in out for (c, _s, _h, _n) in out[sp]]
-    score_bytes = 9.0 * R_local
+    # bytes the score kernel has to read: the run-length form stores the allele id per run (5 B / record + 8 B / run +
+    # 4 B / 256-record chunk); SURVEY.md 8d's 9 B / record assumed an explicit 4-byte id per record (kept as a fallback form)
+    if pipe.use_runs:
+        score_bytes = 5.0 * R_local + 8.0 * int(st.run_tid.shape[0]) + 4.0 * int(st.chunk_run.shape[0])
+    else:
+        score_bytes = 9.0 * R_local
     pb, precs = pileup_alg_bytes(st, [t for t in tids if st.contig_start[t + 1] > st.contig_start[t]], args.read_len)
     rooflines = {
         "score": {"bound": "hbm", "achieved": score_bytes / kms["score"] / 1e6, "peak": peak, "unit": "GB/s", "frac": score_bytes / kms["score"] / 1e6 / peak,
-                  "traffic": ncu_traffic("score") if args.reads == 10_000_000 and args.k == 4 else None, "ms": kms["score"], "algorithmic_bytes": score_bytes},
+                  "traffic": ncu_traffic("score_runs" if pipe.use_runs else "score") if args.reads == 10_000_000 and args.k == 4 else None,
+                  "ms": kms["score"], "algorithmic_bytes": score_bytes,
+                  "stream_form": "run-length: as0 i16 + xm3 u8 + qlen u16 per record, allele id per run (5 B/record; SURVEY 8d's explicit-id form is 9 B/record)"
+                  if pipe.use_runs else "explicit allele id per record (9 B/record)"},
         "pileup_parity": {"bound": "hbm", "achieved": pb / kms.get("pileup", float("inf")) / 1e6, "peak": peak, "unit": "GB/s",
                           "frac": pb / kms.get("pileup", float("inf")) / 1e6 / peak, "traffic": None, "ms": kms.get("pileup"),
                           "algorithmic_bytes": pb, "records": precs},
@@ -373,7 +381,8 @@ def main():
     dt = (time.perf_counter() - t0) / n_e2e
     clocks = sampler.stop()
     line["clocks"] = clocks
-    h2d = 9 * R_local + db.n_rows * 5 + int(sum((st.contig_start[t + 1] - st.contig_start[t]) * 16 for t in ts_local))
+    h2d = (5 * R_local + 8 * int(soa.run_tid.shape[0]) + 4 + 4 * int(soa.chunk_run.shape[0])) if soa.run_tid is not None else 9 * R_local
+    h2d += db.n_rows * 5 + int(sum((st.contig_start[t + 1] - st.contig_start[t]) * 16 for t in ts_local))
     proff = soa.p_row_off
     h2d += int(sum(int(proff[int(st.contig_start[t + 1])]) - int(proff[int(st.contig_start[t])]) for t in ts_local)) * 4
     d2h = db.n_rows * 16 + 16 + sum(int(st.ref_lens[t]) for t in ts_local) + 8 * len(ts_local)

@@ -17,6 +17,8 @@
  *                      tid u32 (BAM reference index == allele row), as0 i16 (1st aux field by POSITION),
  *                      xm3 u8 (4th aux field by POSITION, saturated at 255), qlen u16 (len(SEQ) as SAM prints it),
  *                      optional orig_idx u32 (index in file order; NULL = identity + idx_base).        9 B / record
+ *                    run-length form (coordinate-sorted streams): tid per RUN of equal tid instead of per record
+ *                      (run_tid, run_start, chunk_run -- see mmlst_score_runs_dev).                      5 B / record
  *   pileup stream  : records ADMITTED by the htslib depth cap, coordinate-sorted, CIGAR already projected on the
  *                    reference: one 16-byte mmlst_prec per record {pos i32, row_off u32 (word offset into planes),
  *                    reflen u16, as_named i16, xm_named u8 (AS, XM by NAME), nw u16} -- array-of-16-byte-structs so
@@ -40,7 +42,7 @@
 extern "C" {
 #endif
 
-#define MMLST_VERSION 101
+#define MMLST_VERSION 102
 
 enum {
     MMLST_OK = 0,
@@ -85,6 +87,25 @@ int mmlst_score_dev(const uint32_t* tid, const int16_t* as0, const uint8_t* xm3,
                     const uint8_t* allow, const uint32_t* locus_of, uint32_t n_ref,
                     int minscore, int max_xm, int min_read_len,
                     int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, uint64_t* counters, void* stream);
+
+/* The same stage over the RUN-LENGTH form of the score stream (what a coordinate-sorted BAM is shipped in: 5 B / record).
+ * The allele id is stored per RUN of equal tid, not per record:
+ *   run_tid[n_runs], run_start[n_runs+1] (run r = records run_start[r] .. run_start[r+1]; run_start[0] = 0,
+ *   run_start[n_runs] = n_rec; no empty runs), chunk_run[ceil(n_rec/256)] = run holding record 256*c.
+ * Any record order is legal (a run is just a maximal stretch of equal tid); it pays off when n_runs << n_rec.
+ * n_rec < 2^32 - 256.  Same filter, outputs and accumulation rules as mmlst_score_dev (locus_of is not needed).
+ * mmlst_build_runs (HOST) derives the three arrays from tid[]: pass run_tid = NULL to get the counts only
+ * (*n_runs = runs, return value OK); capacity of run_tid / run_start is *n_runs on entry. */
+int mmlst_build_runs(const uint32_t* tid, uint64_t n_rec, uint32_t* run_tid, uint32_t* run_start, uint32_t* chunk_run,
+                     uint32_t* n_runs);
+int mmlst_score_runs_dev(const uint32_t* run_tid, const uint32_t* run_start, uint32_t n_runs, const uint32_t* chunk_run,
+                         const int16_t* as0, const uint8_t* xm3, const uint16_t* qlen, const uint32_t* orig_idx,
+                         uint64_t n_rec, uint64_t idx_base, const uint8_t* allow, uint32_t n_ref,
+                         int minscore, int max_xm, int min_read_len,
+                         int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, uint64_t* counters, void* stream);
+/* tid[i] of every record back from the run arrays (device; the coverage kernel takes the explicit form) */
+int mmlst_expand_runs_dev(const uint32_t* run_tid, const uint32_t* run_start, uint32_t n_runs, const uint32_t* chunk_run,
+                          uint64_t n_rec, uint32_t* tid, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Stage 1, coverage column (H7).  Replaces `sequenceBank[species_gene][readCode] = len(sequence)` (metamlst.py:127) and
@@ -240,6 +261,10 @@ typedef struct {
     /* per reference (allele row) */
     const uint64_t* contig_start; /* [n_ref+1] first pileup-stream record of each contig */
     uint32_t n_ref;
+    /* run-length form of the score stream (mmlst_score_runs_dev); when run_tid != NULL the host entry points upload
+     * 5 B / record + the run arrays and never read `tid` (which may then be NULL) */
+    uint32_t n_runs;
+    const uint32_t* run_tid; const uint32_t* run_start; const uint32_t* chunk_run;
 } mmlst_soa;
 
 typedef struct { int minscore, max_xm, min_read_len; } mmlst_score_params;

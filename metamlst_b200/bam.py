@@ -70,6 +70,12 @@ def unpack_bam(path: str, minqual: int = packing.DEFAULT_MINQUAL, max_depth: Opt
         _view(s.orig_idx, n, np.uint32) if s.orig_idx else None,
         _view(s.p_recs, P, packing.PREC_DTYPE), _view(s.planes, int(s.n_plane_words), np.uint32), int(s.max_row_words),
         _view(s.contig_start, n_ref + 1, np.uint64), int(info.minqual), int(info.max_depth), int(info.n_dropped_by_cap))
+    if s.run_tid:
+        nr = int(s.n_runs)
+        soa.run_tid, soa.run_start = _view(s.run_tid, nr, np.uint32), _view(s.run_start, nr + 1, np.uint32)
+        soa.chunk_run = _view(s.chunk_run, (n + 255) // 256, np.uint32)
+        if nr > 0.125 * n:  # name-grouped input: the explicit tid form is the smaller one
+            soa.run_tid = soa.run_start = soa.chunk_run = None
     soa.qhash = _view(info.qhash, 2 * n, np.uint64).reshape(n, 2) if info.qhash else None
     soa.header_text = (info.header_text or b"").decode("latin-1")
     soa.unpack_seconds = dict(zip(("read", "inflate", "parse", "sort", "pack"), [float(x) for x in info.seconds]))

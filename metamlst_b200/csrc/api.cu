@@ -75,8 +75,11 @@ struct mmlst_ctx {
     cudaStream_t stream = nullptr;
     // score stream
     DevBuf tid, as0, xm3, qlen, oidx, allow, locus_of, sum_as, n_hit, first_idx, counters;
-    uint64_t resident_n = 0;     // records of the score stream currently in tid/as0/xm3/qlen(/oidx)
+    DevBuf run_tid, run_start, chunk_run;  // run-length form (mmlst_score_runs_dev)
+    uint64_t resident_n = 0;     // records of the score stream currently in (tid/)as0/xm3/qlen(/oidx)
     bool resident_oidx = false;
+    bool resident_tid = false;   // explicit tid[] present (false after a run-length upload until mmlst_coverage expands it)
+    uint32_t resident_runs = 0;
     // coverage (H7)
     DevBuf qhash, cov_table, cov;
     // pileup stream (chosen contigs only)
@@ -90,7 +93,8 @@ struct mmlst_ctx {
     mmlst_ctx() {
         DevBuf* l[] = {&tid, &as0, &xm3, &qlen, &oidx, &allow, &locus_of, &sum_as, &n_hit, &first_idx, &counters, &p_recs,
                        &planes, &chunks, &counts, &dbseq, &col_off, &cons, &holes, &snps, &db_hi,
-                       &db_lo, &db_len, &q_hi, &q_lo, &q_len, &blocks, &best, &qhash, &cov_table, &cov, &xr_ids, &xr_x, &xr_bytes, &xq_ids, &xq_x, &xq_bytes};
+                       &db_lo, &db_len, &q_hi, &q_lo, &q_len, &blocks, &best, &qhash, &cov_table, &cov, &xr_ids, &xr_x, &xr_bytes, &xq_ids, &xq_x, &xq_bytes,
+                       &run_tid, &run_start, &chunk_run};
         for (DevBuf* b : l) all[n_all++] = b;
     }
 };
@@ -140,6 +144,56 @@ static int h2d(DevBuf& b, const T* src, size_t n, cudaStream_t s) {
     return MMLST_OK;
 }
 
+// score stream host -> device: the run-length form (5 B / record + run arrays) when the caller provides it, else explicit tid
+static int upload_score_stream(mmlst_ctx* c, const mmlst_soa* soa) {
+    cudaStream_t s = c->stream;
+    const size_t n = soa->n_rec;
+    const bool runs = soa->run_tid != nullptr && n != 0;
+    if (runs) {
+        if (!soa->run_start || !soa->chunk_run || !soa->n_runs) { mmlst_set_error("mmlst_soa: run_tid without run_start / chunk_run / n_runs"); return MMLST_E_ARG; }
+        if (soa->run_start[0] != 0 || soa->run_start[soa->n_runs] != n) { mmlst_set_error("mmlst_soa: run_start does not span the %zu records", n); return MMLST_E_ARG; }
+        TRY(h2d(c->run_tid, soa->run_tid, (size_t)soa->n_runs, s));
+        TRY(h2d(c->run_start, soa->run_start, (size_t)soa->n_runs + 1, s));
+        TRY(h2d(c->chunk_run, soa->chunk_run, (n + 255) / 256, s));
+    } else {
+        if (n && !soa->tid) { mmlst_set_error("mmlst_soa: neither tid nor run arrays given"); return MMLST_E_ARG; }
+        TRY(h2d(c->tid, soa->tid, n, s));
+    }
+    TRY(h2d(c->as0, soa->as0, n, s));
+    TRY(h2d(c->xm3, soa->xm3, n, s));
+    TRY(h2d(c->qlen, soa->qlen, n, s));
+    if (soa->orig_idx) TRY(h2d(c->oidx, soa->orig_idx, n, s));
+    c->resident_n = n; c->resident_oidx = soa->orig_idx != nullptr;
+    c->resident_tid = !runs; c->resident_runs = runs ? soa->n_runs : 0;
+    return MMLST_OK;
+}
+
+// HOST: run arrays of a tid[] (include/mmlst.h, mmlst_score_runs_dev)
+extern "C" int mmlst_build_runs(const uint32_t* tid, uint64_t n_rec, uint32_t* run_tid, uint32_t* run_start, uint32_t* chunk_run,
+                                uint32_t* n_runs) {
+    if (!n_runs || (n_rec && !tid)) { mmlst_set_error("mmlst_build_runs: null pointer"); return MMLST_E_ARG; }
+    if (n_rec >= 0xffffff00ull) { mmlst_set_error("mmlst_build_runs: %llu records do not fit 32-bit run offsets", (unsigned long long)n_rec); return MMLST_E_RANGE; }
+    if (!run_tid) {
+        uint64_t r = n_rec ? 1 : 0;
+        for (uint64_t i = 1; i < n_rec; ++i) r += tid[i] != tid[i - 1];
+        *n_runs = (uint32_t)r;
+        return MMLST_OK;
+    }
+    if (!run_start || !chunk_run) { mmlst_set_error("mmlst_build_runs: null pointer"); return MMLST_E_ARG; }
+    const uint32_t cap = *n_runs;
+    uint32_t r = 0;
+    for (uint64_t i = 0; i < n_rec; ++i) {
+        if (i == 0 || tid[i] != tid[i - 1]) {
+            if (r >= cap) { mmlst_set_error("mmlst_build_runs: more than %u runs", cap); return MMLST_E_ARG; }
+            run_tid[r] = tid[i]; run_start[r] = (uint32_t)i; ++r;
+        }
+        if ((i & 255u) == 0) chunk_run[i >> 8] = r - 1;
+    }
+    run_start[r] = (uint32_t)n_rec;
+    *n_runs = r;
+    return MMLST_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* allow, const uint32_t* locus_of,
                            uint32_t n_loci, const mmlst_score_params* prm, int64_t* sum_as, uint32_t* n_hit,
@@ -148,12 +202,7 @@ extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* al
     if (!soa || !allow || !locus_of || !prm || !sum_as || !n_hit || !first_idx || !counters) { mmlst_set_error("mmlst_score: null pointer"); return MMLST_E_ARG; }
     cudaStream_t s = c->stream;
     const size_t n = soa->n_rec, nr = soa->n_ref;
-    TRY(h2d(c->tid, soa->tid, n, s));
-    TRY(h2d(c->as0, soa->as0, n, s));
-    TRY(h2d(c->xm3, soa->xm3, n, s));
-    TRY(h2d(c->qlen, soa->qlen, n, s));
-    if (soa->orig_idx) TRY(h2d(c->oidx, soa->orig_idx, n, s));
-    c->resident_n = n; c->resident_oidx = soa->orig_idx != nullptr;
+    TRY(upload_score_stream(c, soa));
     TRY(h2d(c->allow, allow, nr, s));
     TRY(h2d(c->locus_of, locus_of, nr, s));
     TRY(c->sum_as.reserve(nr * 8)); TRY(c->n_hit.reserve(nr * 4)); TRY(c->first_idx.reserve(nr * 4 + 4)); TRY(c->counters.reserve(16));
@@ -161,11 +210,19 @@ extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* al
     CUDA_TRY(cudaMemsetAsync(c->n_hit.p, 0, nr * 4, s));
     CUDA_TRY(cudaMemsetAsync(c->first_idx.p, 0xff, nr * 4, s));
     CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, 16, s));
-    TRY(mmlst_score_dev(c->tid.as<uint32_t>(), c->as0.as<int16_t>(), c->xm3.as<uint8_t>(), c->qlen.as<uint16_t>(),
-                        soa->orig_idx ? c->oidx.as<uint32_t>() : nullptr, n, 0, c->allow.as<uint8_t>(),
-                        c->locus_of.as<uint32_t>(), (uint32_t)nr, prm->minscore, prm->max_xm, prm->min_read_len,
-                        c->sum_as.as<int64_t>(), c->n_hit.as<uint32_t>(), c->first_idx.as<uint32_t>(),
-                        c->counters.as<uint64_t>(), s));
+    if (c->resident_runs) {
+        TRY(mmlst_score_runs_dev(c->run_tid.as<uint32_t>(), c->run_start.as<uint32_t>(), c->resident_runs, c->chunk_run.as<uint32_t>(),
+                                 c->as0.as<int16_t>(), c->xm3.as<uint8_t>(), c->qlen.as<uint16_t>(),
+                                 soa->orig_idx ? c->oidx.as<uint32_t>() : nullptr, n, 0, c->allow.as<uint8_t>(), (uint32_t)nr,
+                                 prm->minscore, prm->max_xm, prm->min_read_len, c->sum_as.as<int64_t>(), c->n_hit.as<uint32_t>(),
+                                 c->first_idx.as<uint32_t>(), c->counters.as<uint64_t>(), s));
+    } else {
+        TRY(mmlst_score_dev(c->tid.as<uint32_t>(), c->as0.as<int16_t>(), c->xm3.as<uint8_t>(), c->qlen.as<uint16_t>(),
+                            soa->orig_idx ? c->oidx.as<uint32_t>() : nullptr, n, 0, c->allow.as<uint8_t>(),
+                            c->locus_of.as<uint32_t>(), (uint32_t)nr, prm->minscore, prm->max_xm, prm->min_read_len,
+                            c->sum_as.as<int64_t>(), c->n_hit.as<uint32_t>(), c->first_idx.as<uint32_t>(),
+                            c->counters.as<uint64_t>(), s));
+    }
     CUDA_TRY(cudaMemcpyAsync(sum_as, c->sum_as.p, nr * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(n_hit, c->n_hit.p, nr * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(first_idx, c->first_idx.p, nr * 4, cudaMemcpyDeviceToHost, s));
@@ -189,12 +246,13 @@ extern "C" int mmlst_coverage(mmlst_ctx* c, const mmlst_soa* soa, const uint64_t
             return MMLST_E_ARG;
         }
     } else {
-        TRY(h2d(c->tid, soa->tid, n, s));
-        TRY(h2d(c->as0, soa->as0, n, s));
-        TRY(h2d(c->xm3, soa->xm3, n, s));
-        TRY(h2d(c->qlen, soa->qlen, n, s));
-        if (soa->orig_idx) TRY(h2d(c->oidx, soa->orig_idx, n, s));
-        c->resident_n = n; c->resident_oidx = soa->orig_idx != nullptr;
+        TRY(upload_score_stream(c, soa));
+    }
+    if (!c->resident_tid && n) {  // run-length upload: the coverage kernel wants the explicit allele id per record
+        TRY(c->tid.reserve(n * 4));
+        TRY(mmlst_expand_runs_dev(c->run_tid.as<uint32_t>(), c->run_start.as<uint32_t>(), c->resident_runs, c->chunk_run.as<uint32_t>(),
+                                  n, c->tid.as<uint32_t>(), s));
+        c->resident_tid = true;
     }
     TRY(h2d(c->qhash, qhash, 2 * n, s));
     TRY(h2d(c->allow, allow, nr, s));

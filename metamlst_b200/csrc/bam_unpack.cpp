@@ -159,14 +159,15 @@ struct mmlst_bam {
     std::vector<uint32_t> ref_len;
     std::string names_blob;  // '\n'-joined, for one-call transfer to the binding
     std::string header_text;
-    Buf tid, as0, xm3, qlen, orig_idx, qhash, p_recs, planes, contig_start;
+    Buf tid, as0, xm3, qlen, orig_idx, qhash, p_recs, planes, contig_start, run_tid, run_start, chunk_run;
+    uint32_t n_runs = 0;
     uint64_t n_rec = 0, n_prec = 0, n_plane_words = 0, n_dropped = 0, n_unmapped_flag = 0;
     uint32_t max_row_words = 0;
     int presorted = 0, minqual = 20;
     uint32_t max_depth = 0;
     double t_read = 0, t_inflate = 0, t_parse = 0, t_sort = 0, t_pack = 0;
     ~mmlst_bam() {
-        for (Buf* b : {&tid, &as0, &xm3, &qlen, &orig_idx, &qhash, &p_recs, &planes, &contig_start}) b->release();
+        for (Buf* b : {&tid, &as0, &xm3, &qlen, &orig_idx, &qhash, &p_recs, &planes, &contig_start, &run_tid, &run_start, &chunk_run}) b->release();
     }
 };
 
@@ -405,6 +406,19 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
         }
     });
 
+    // run-length form of the score stream (mmlst_score_runs_dev): tid per run of equal tid, 5 B / record cross PCIe
+    if (n && n < 0xffffff00ull) {
+        uint32_t nr = 0;
+        int rc = mmlst_build_runs(B->tid.as<uint32_t>(), n, nullptr, nullptr, nullptr, &nr);
+        if (rc != MMLST_OK) return rc;
+        if (!B->run_tid.alloc((size_t)nr * 4, pin) || !B->run_start.alloc(((size_t)nr + 1) * 4, pin) || !B->chunk_run.alloc(((n + 255) / 256) * 4, pin)) {
+            mmlst_set_error("mmlst_bam_unpack: out of host memory"); return MMLST_E_NOMEM;
+        }
+        rc = mmlst_build_runs(B->tid.as<uint32_t>(), n, B->run_tid.as<uint32_t>(), B->run_start.as<uint32_t>(), B->chunk_run.as<uint32_t>(), &nr);
+        if (rc != MMLST_OK) return rc;
+        B->n_runs = nr;
+    }
+
     // ---- phase 6: pileup candidates (mapped flag), depth cap, rows
     std::vector<uint32_t> cand;  // sorted-order indices k
     cand.reserve(n);
@@ -515,6 +529,10 @@ extern "C" int mmlst_bam_info(const mmlst_bam* b, mmlst_bam_info_t* info) {
     info->soa.p_recs = b->p_recs.as<mmlst_prec>(); info->soa.planes = b->planes.as<uint32_t>();
     info->soa.n_prec = b->n_prec; info->soa.n_plane_words = b->n_plane_words; info->soa.max_row_words = b->max_row_words;
     info->soa.contig_start = b->contig_start.as<uint64_t>(); info->soa.n_ref = (uint32_t)b->ref_names.size();
+    if (b->n_runs) {
+        info->soa.n_runs = b->n_runs; info->soa.run_tid = b->run_tid.as<uint32_t>();
+        info->soa.run_start = b->run_start.as<uint32_t>(); info->soa.chunk_run = b->chunk_run.as<uint32_t>();
+    }
     info->qhash = b->qhash.as<uint64_t>();
     info->ref_len = b->ref_len.data();
     info->ref_names = b->names_blob.c_str();

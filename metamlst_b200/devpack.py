@@ -81,7 +81,26 @@ class DeviceStreams:
         soa = packing.SoaHost(self.ref_names, self.ref_lens, h(self.tid, np.uint32), h(self.as0, np.int16), h(self.xm3, np.uint8),
                               h(self.qlen, np.uint16), None, recs, h(self.planes, np.uint32),
                               int(self.max_row_words), self.contig_start.copy(), self.minqual, self.max_depth, self.n_dropped)
+        if getattr(self, "run_tid", None) is not None:
+            soa.run_tid, soa.run_start, soa.chunk_run = h(self.run_tid, np.uint32), h(self.run_start, np.uint32), h(self.chunk_run, np.uint32)
         return soa.pin() if pinned else soa
+
+    def build_runs(self) -> "DeviceStreams":
+        """Run-length form of the score stream on the device (include/mmlst.h, mmlst_score_runs_dev): run_tid, run_start,
+        chunk_run as int32 tensors (bit patterns of the u32 arrays)."""
+        n = int(self.tid.shape[0])
+        self.run_tid = self.run_start = self.chunk_run = None
+        if n == 0:
+            return self
+        assert n < 0xffffff00
+        vals, counts = torch.unique_consecutive(self.tid, return_counts=True)
+        start = torch.zeros(vals.shape[0] + 1, dtype=torch.int64, device=self.tid.device)
+        start[1:] = torch.cumsum(counts, 0)
+        first = torch.arange(0, n, 256, dtype=torch.int64, device=self.tid.device)
+        self.chunk_run = (torch.searchsorted(start, first, right=True) - 1).to(torch.int32).contiguous()
+        self.run_tid = vals.to(torch.int32).contiguous()
+        self.run_start = start.to(torch.int32).contiguous()  # n < 2^32 - 256: the u32 bit pattern
+        return self
 
 
 def pack_cores(db, cores: List[dict], minqual: int = 20, max_depth: Optional[int] = 8000, sentinel_nodes: int = 1,
@@ -150,4 +169,5 @@ def pack_cores(db, cores: List[dict], minqual: int = 20, max_depth: Optional[int
     s.max_row_words = int(rw.max()) if sel.shape[0] else 0
     tsel = tid[sel]
     s.contig_start = torch.searchsorted(tsel.contiguous(), torch.arange(len(s.ref_names) + 1, device=dev)).cpu().numpy().astype(np.uint64)
+    s.build_runs()
     return s

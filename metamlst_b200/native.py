@@ -24,7 +24,8 @@ class Soa(C.Structure):
                 ("n_rec", C.c_uint64),
                 ("p_recs", C.c_void_p),
                 ("planes", C.c_void_p), ("n_prec", C.c_uint64), ("n_plane_words", C.c_uint64), ("max_row_words", C.c_uint32),
-                ("contig_start", C.c_void_p), ("n_ref", C.c_uint32)]
+                ("contig_start", C.c_void_p), ("n_ref", C.c_uint32),
+                ("n_runs", C.c_uint32), ("run_tid", C.c_void_p), ("run_start", C.c_void_p), ("chunk_run", C.c_void_p)]
 
 
 class ScoreParams(C.Structure):
@@ -44,6 +45,10 @@ EXPORTS = {
     "mmlst_pinned_free": (None, [C.c_void_p]),
     "mmlst_score_dev": (C.c_int, [C.c_void_p] * 5 + [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmlst_build_runs": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
+    "mmlst_score_runs_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_void_p] * 5 + [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32,
+                                       C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmlst_expand_runs_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mmlst_coverage_table_slots": (C.c_uint64, [C.c_uint64]),
     "mmlst_coverage_dev": (C.c_int, [C.c_void_p] * 6 + [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int,
                                      C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),

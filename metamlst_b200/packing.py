@@ -49,6 +49,10 @@ class SoaHost:
     qhash: Optional[np.ndarray] = None  # u64 [n_rec][2] 128-bit QNAME hash (coverage column, H7); None when not unpacked
     header_text: str = ""
     unpack_seconds: Optional[dict] = None
+    # run-length form of the score stream (include/mmlst.h, mmlst_score_runs_dev): tid per run of equal tid
+    run_tid: Optional[np.ndarray] = None
+    run_start: Optional[np.ndarray] = None
+    chunk_run: Optional[np.ndarray] = None
 
     @property
     def n_rec(self) -> int:
@@ -84,14 +88,36 @@ class SoaHost:
         s.max_row_words = int(self.max_row_words)
         s.contig_start = native.ptr(self.contig_start)
         s.n_ref = len(self.ref_names)
+        if self.run_tid is not None and self.n_rec:
+            s.n_runs = int(self.run_tid.shape[0])
+            s.run_tid, s.run_start, s.chunk_run = native.ptr(self.run_tid), native.ptr(self.run_start), native.ptr(self.chunk_run)
         return s
+
+    def build_runs(self, max_fraction: float = 0.125) -> "SoaHost":
+        """Attach the run-length form (mmlst_build_runs) when it is the smaller one: at most `max_fraction` runs per
+        record (coordinate-sorted streams; a name-grouped stream keeps the explicit tid form)."""
+        n = self.n_rec
+        self.run_tid = self.run_start = self.chunk_run = None
+        if n == 0:
+            return self
+        import ctypes as C
+        lib = native.lib()
+        nr = C.c_uint32(0)
+        tid = np.ascontiguousarray(self.tid, dtype=np.uint32)
+        native.check(lib.mmlst_build_runs(native.ptr(tid), n, None, None, None, C.byref(nr)))
+        if nr.value > max_fraction * n:
+            return self
+        run_tid = np.empty(nr.value, np.uint32); run_start = np.empty(nr.value + 1, np.uint32); chunk_run = np.empty((n + 255) // 256, np.uint32)
+        native.check(lib.mmlst_build_runs(native.ptr(tid), n, native.ptr(run_tid), native.ptr(run_start), native.ptr(chunk_run), C.byref(nr)))
+        self.run_tid, self.run_start, self.chunk_run = run_tid, run_start, chunk_run
+        return self
 
     def pin(self) -> "SoaHost":
         """Copy the streams into page-locked memory (torch pinned tensors) so uploads are asynchronous DMA."""
         import torch
 
         keep = []
-        for name in ("tid", "as0", "xm3", "qlen", "orig_idx", "p_recs", "planes", "qhash"):
+        for name in ("tid", "as0", "xm3", "qlen", "orig_idx", "p_recs", "planes", "qhash", "run_tid", "run_start", "chunk_run"):
             arr = getattr(self, name)
             if arr is None:
                 continue
@@ -146,8 +172,10 @@ def _pack_bits_u32(bits: np.ndarray) -> np.ndarray:
 
 
 def pack_table(tab, minqual: int = DEFAULT_MINQUAL, max_depth: Optional[int] = DEFAULT_MAX_DEPTH, sentinel_nodes: int = 1,
-               chunk: int = 1 << 18) -> SoaHost:
-    """AlnTable (fixed read length, ASCII seq + phred qual) -> SoaHost.  max_depth=None disables the htslib cap."""
+               chunk: int = 1 << 18, run_fraction: float = 0.125) -> SoaHost:
+    """AlnTable (fixed read length, ASCII seq + phred qual) -> SoaHost.  max_depth=None disables the htslib cap.
+    run_fraction: attach the run-length form of the score stream when runs <= run_fraction * records (0 = never,
+    1 = always)."""
     n = tab.n
     if n and np.any(tab.flag & BAM_FPROPER_PAIR):
         raise native.MmlstError(-6, "proper-pair records: htslib overlap handling (H2) is not implemented -- refusing")
@@ -251,6 +279,8 @@ def pack_table(tab, minqual: int = DEFAULT_MINQUAL, max_depth: Optional[int] = D
                   recs, planes, int(rw.max()) if P else 0, contig_start,
                   minqual, max_depth if max_depth is not None else 0, int((~adm).sum()))
     soa.qhash = qname_key(tab.qname_id[order])
+    if run_fraction > 0:
+        soa.build_runs(run_fraction)
     return soa
 
 

@@ -30,7 +30,8 @@ class DevicePipeline:
     def __init__(self, streams, index: api.AlleleIndex, dbseq_of: Callable[[int], str], minscore: int = 80, max_xM: int = 5,
                  min_read_len: int = 50, penalty: int = 100, species_filter: Optional[str] = None, mincov: int = 1,
                  impl: int = 0, idx_base: int = 0, group=None, nloci: int = 100, genes_in_db: Optional[Dict[str, int]] = None,
-                 db_ascii: Optional[np.ndarray] = None, db_off: Optional[np.ndarray] = None, exchange: str = "allreduce"):
+                 db_ascii: Optional[np.ndarray] = None, db_off: Optional[np.ndarray] = None, exchange: str = "allreduce",
+                 use_runs: Optional[bool] = None):
         """exchange (only with torch.distributed, world > 1): "allreduce" = partial score / count tensors are all-reduced
         (any record sharding whose depth cap was resolved beforehand); "gather" = owner mode for contig-aligned shards:
         each rank finishes its own loci and ONE all-gather of the result blocks ends the pass (dist.merge_owner_blocks)."""
@@ -45,8 +46,9 @@ class DevicePipeline:
             raise ValueError("exchange must be 'allreduce' or 'gather'")
         self.owner = self.dist and exchange == "gather"
         self.world = torch.distributed.get_world_size() if self.dist else 1
-        dev = streams.tid.device
+        dev = streams.as0.device
         self.dev = dev
+        self.use_runs = bool(use_runs) if use_runs is not None else getattr(streams, "run_tid", None) is not None
         n_ref = len(index.ref_names)
         self.n_ref = n_ref
         self.allow = torch.from_numpy(index.allow_mask(species_filter)).to(dev)
@@ -142,18 +144,29 @@ class DevicePipeline:
         self.zblock.zero_(); self.first_idx.fill_(-1); self.scratch.zero_()
         self._clean = True
 
+    def _score_call(self):
+        """Stage 1 over the resident score stream: the run-length form (5 B / record) when the streams carry it, else the
+        explicit-tid form (9 B / record)."""
+        s = self.s
+        n = int(s.as0.shape[0])
+        if self.use_runs:
+            native.check(self.lib.mmlst_score_runs_dev(native.ptr(s.run_tid), native.ptr(s.run_start), int(s.run_tid.shape[0]), native.ptr(s.chunk_run),
+                                                       native.ptr(s.as0), native.ptr(s.xm3), native.ptr(s.qlen), 0, n, self.idx_base,
+                                                       native.ptr(self.allow), self.n_ref, self.minscore, self.max_xM, self.min_read_len,
+                                                       native.ptr(self.sum_as), native.ptr(self.n_hit), native.ptr(self.first_idx),
+                                                       native.ptr(self.counters), self._stream()))
+        else:
+            native.check(self.lib.mmlst_score_dev(native.ptr(s.tid), native.ptr(s.as0), native.ptr(s.xm3), native.ptr(s.qlen), 0, n, self.idx_base,
+                                                  native.ptr(self.allow), native.ptr(self.locus_of), self.n_ref, self.minscore, self.max_xM,
+                                                  self.min_read_len, native.ptr(self.sum_as), native.ptr(self.n_hit), native.ptr(self.first_idx),
+                                                  native.ptr(self.counters), self._stream()))
+
     def run_score(self, reset: bool = True):
         s = self.s
         if reset:
             self.reset_tables()
         self._clean = False
-        def k():
-            native.check(self.lib.mmlst_score_dev(native.ptr(s.tid), native.ptr(s.as0), native.ptr(s.xm3), native.ptr(s.qlen), 0,
-                                                  int(s.tid.shape[0]), self.idx_base, native.ptr(self.allow), native.ptr(self.locus_of),
-                                                  self.n_ref, self.minscore, self.max_xM, self.min_read_len, native.ptr(self.sum_as),
-                                                  native.ptr(self.n_hit), native.ptr(self.first_idx), native.ptr(self.counters),
-                                                  self._stream()))
-        self._timed("score", k)
+        self._timed("score", self._score_call)
         self.launches += 1
         if self.dist and not self.owner:
             dist.allreduce_score_block(self.zscore, self.first_idx, self.group)
@@ -313,11 +326,7 @@ class DevicePipeline:
     def _launch_one(self, name: str):
         s = self.s
         if name == "score":
-            native.check(self.lib.mmlst_score_dev(native.ptr(s.tid), native.ptr(s.as0), native.ptr(s.xm3), native.ptr(s.qlen), 0,
-                                                  int(s.tid.shape[0]), self.idx_base, native.ptr(self.allow), native.ptr(self.locus_of),
-                                                  self.n_ref, self.minscore, self.max_xM, self.min_read_len, native.ptr(self.sum_as),
-                                                  native.ptr(self.n_hit), native.ptr(self.first_idx), native.ptr(self.counters),
-                                                  self._stream()))
+            self._score_call()
         elif name == "select":
             self._select_call(native.SELECT_SCRATCH_CLEAN)  # tables left intact: every repetition does the same work
         elif name == "pileup":

@@ -25,6 +25,13 @@ def assert_same(want: packing.SoaHost, got: packing.SoaHost):
     if want.orig_idx is not None:
         assert np.array_equal(want.orig_idx, got.orig_idx)
     assert list(want.ref_names) == list(got.ref_names)
+    # run-length form of the score stream: the unpacker's arrays are those of mmlst_build_runs on the same tid
+    chk = packing.SoaHost([], np.zeros(0, np.int32), got.tid, got.as0, got.xm3, got.qlen, None, np.zeros(0, packing.PREC_DTYPE),
+                          np.zeros(0, np.uint32), 0, np.zeros(1, np.uint64)).build_runs(0.125)
+    assert (chk.run_tid is None) == (got.run_tid is None)
+    if got.run_tid is not None:
+        for k in ("run_tid", "run_start", "chunk_run"):
+            assert np.array_equal(getattr(chk, k), getattr(got, k)), k
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "*", "sample.bam"))), ids=lambda p: os.path.basename(os.path.dirname(p)))

@@ -1,4 +1,5 @@
 """Parity of the CUDA path (through the C-ABI) against the oracles.  Needs a B200: `pytest -m gpu`."""
+import ctypes as C
 import json
 import os
 import sqlite3
@@ -22,14 +23,16 @@ def ctx():
 
 
 # ------------------------------------------------------------------------------------------------ stage 1
+@pytest.mark.parametrize("form", ["tid", "runs"])  # explicit allele id per record (9 B) / run-length form (5 B)
 @pytest.mark.parametrize("order", ["name", "coord"])
 @pytest.mark.parametrize("n_reads,species_filter", [(37, None), (3000, None), (3000, "saureus"), (60000, "ecoli,saureus")])
-def test_score_bit_exact(ctx, order, n_reads, species_filter):
+def test_score_bit_exact(ctx, order, n_reads, species_filter, form):
     db, tab = small_case(seed=31, n_reads=n_reads, orgs=("ecoli", "saureus"), apl=8, sub_err=0.02)
     if order == "coord":
         tab = tab.sorted_by_coord()
     tab.has_xs = (np.arange(tab.n) % 7) != 0  # H4
-    soa = packing.pack_table(tab)
+    soa = packing.pack_table(tab, run_fraction=1.0 if form == "runs" else 0.0)
+    assert (soa.run_tid is not None) == (form == "runs")
     index = api.AlleleIndex(tab.ref_names)
     cel, total, ignored, (s, c, f) = api.score_soa(ctx, soa, index, 176, 3, 50, species_filter, 100)
     allow, locus_of, n_loci = lut_from_db(db, species_filter)
@@ -41,6 +44,81 @@ def test_score_bit_exact(ctx, order, n_reads, species_filter):
         want, _bank, wt, wi = orc.stage1(h, recs, 176, 3, 50, species_filter, 100)
         assert json.dumps(cel) == json.dumps(want)
         assert "".join(orc.out_log_rows(cel)) == "".join(orc.out_log_rows(want))
+
+
+def _np_score(tid, as0, xm3, qlen, idx, allow, n_ref, minscore, max_xm, min_len):
+    al = allow[tid] != 0
+    ok = al & (as0 >= minscore) & (qlen >= min_len) & (xm3 <= max_xm)
+    s = np.zeros(n_ref, np.int64); c = np.zeros(n_ref, np.int64); f = np.full(n_ref, 0xFFFFFFFF, np.int64)
+    np.add.at(s, tid[ok], as0[ok].astype(np.int64)); np.add.at(c, tid[ok], 1); np.minimum.at(f, tid[ok], idx[ok].astype(np.int64))
+    return s, c.astype(np.uint32), f.astype(np.uint32), int(al.sum()), int((al & ~ok).sum())
+
+
+@pytest.mark.parametrize("n", [1, 255, 256, 257, 511, 513, 4096, 100003, 5_000_000])
+def test_score_run_length_form_on_raw_streams(ctx, n):
+    # run boundaries everywhere: single-record runs, runs ending exactly on 256-record chunk edges, one run spanning many
+    # chunks, filtered alleles in the middle, negative scores, with and without a file-order index, tails of every size
+    rng = np.random.default_rng(n)
+    n_ref = 300
+    names = ["o%d_g%d_%d" % (t % 3, t % 7, t) for t in range(n_ref)]
+    index = api.AlleleIndex(names)
+    for style in ("mixed", "long", "short"):
+        if style == "long":
+            lens = rng.integers(1, max(2, n // 3), 64)
+        elif style == "short":
+            lens = rng.integers(1, 4, min(n, 200000))
+        else:
+            lens = np.concatenate([rng.integers(1, 900, 4000), [256, 256, 512, 1, 1, 255, 257, 768]])
+            rng.shuffle(lens)
+        lens = lens[np.cumsum(lens) <= n]
+        if lens.sum() < n:
+            lens = np.concatenate([lens, [n - lens.sum()]])
+        rt = rng.integers(0, n_ref, lens.shape[0])
+        rt[1:][rt[1:] == rt[:-1]] += 1  # adjacent runs differ
+        rt %= n_ref
+        tid = np.repeat(rt, lens).astype(np.uint32)
+        assert tid.shape[0] == n
+        as0 = rng.integers(-50, 301, n).astype(np.int16)
+        as0[rng.integers(0, n, max(1, n // 1000))] = 32767  # large scores: the warp sums must not overflow a packed field
+        xm3 = rng.integers(0, 8, n).astype(np.uint8)
+        qlen = rng.integers(30, 160, n).astype(np.uint16)
+        allow = (rng.random(n_ref) < 0.8).astype(np.uint8)
+        for oidx in (None, rng.permutation(n).astype(np.uint32)):
+            soa = packing.SoaHost(names, np.full(n_ref, 500, np.int32), tid, as0, xm3, qlen, oidx, np.zeros(0, packing.PREC_DTYPE),
+                                  np.zeros(0, np.uint32), 0, np.zeros(n_ref + 1, np.uint64)).build_runs(max_fraction=1.0)
+            assert soa.run_tid is not None
+            sum_as = np.zeros(n_ref, np.int64); n_hit = np.zeros(n_ref, np.uint32); first = np.full(n_ref, 0xFFFFFFFF, np.uint32)
+            counters = np.zeros(2, np.uint64)
+            cs = soa.c_struct()
+            prm = native.ScoreParams(100, 5, 50)
+            native.check(native.lib().mmlst_score(ctx.handle, C.byref(cs), native.ptr(allow), native.ptr(index.locus_of), index.n_loci, C.byref(prm),
+                                                  native.ptr(sum_as), native.ptr(n_hit), native.ptr(first), native.ptr(counters)))
+            idx = np.arange(n) if oidx is None else oidx
+            ws, wc, wf, wt, wi = _np_score(tid, as0.astype(np.int64), xm3.astype(int), qlen.astype(int), idx, allow, n_ref, 100, 5, 50)
+            assert np.array_equal(sum_as, ws) and np.array_equal(n_hit, wc) and np.array_equal(first, wf), (n, style, oidx is None)
+            assert (int(counters[0]), int(counters[1])) == (wt, wi)
+            # the explicit-tid kernel on the same stream (no run arrays) agrees
+            soa.run_tid = None
+            s2 = np.zeros(n_ref, np.int64); c2 = np.zeros(n_ref, np.uint32); f2 = np.full(n_ref, 0xFFFFFFFF, np.uint32); k2 = np.zeros(2, np.uint64)
+            cs = soa.c_struct()
+            native.check(native.lib().mmlst_score(ctx.handle, C.byref(cs), native.ptr(allow), native.ptr(index.locus_of), index.n_loci, C.byref(prm),
+                                                  native.ptr(s2), native.ptr(c2), native.ptr(f2), native.ptr(k2)))
+            assert np.array_equal(s2, ws) and np.array_equal(c2, wc) and np.array_equal(f2, wf) and np.array_equal(k2, counters)
+
+
+def test_expand_runs_gives_back_tid(ctx):
+    import torch
+    rng = np.random.default_rng(9)
+    for n in (1, 256, 1000, 300001):
+        tid = np.sort(rng.integers(0, 5000, n)).astype(np.uint32)
+        soa = packing.SoaHost([], np.zeros(0, np.int32), tid, np.zeros(n, np.int16), np.zeros(n, np.uint8), np.zeros(n, np.uint16), None,
+                              np.zeros(0, packing.PREC_DTYPE), np.zeros(0, np.uint32), 0, np.zeros(1, np.uint64)).build_runs(1.0)
+        d = lambda a: torch.from_numpy(a.view(np.int32)).cuda()
+        rt, rs, cr = d(soa.run_tid), d(soa.run_start), d(soa.chunk_run)
+        out = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+        native.check(native.lib().mmlst_expand_runs_dev(native.ptr(rt), native.ptr(rs), int(rt.shape[0]), native.ptr(cr), n, native.ptr(out),
+                                                        torch.cuda.current_stream().cuda_stream))
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), tid)
 
 
 def test_score_empty_and_thresholds(ctx):

@@ -15,7 +15,59 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(l, name), name
     assert declared <= set(native.EXPORTS) | {"mmlst_hamming_min_dev2"}
-    assert l.mmlst_version() == 101
+    assert l.mmlst_version() == 102
+
+
+def test_ctypes_soa_layout_matches_the_header(tmp_path):
+    # the ctypes mirror of mmlst_soa (native.Soa) must have the C compiler's layout of include/mmlst.h
+    import ctypes as C, os, subprocess
+    inc = os.path.join(os.path.dirname(native.__file__), "..", "include")
+    fields = [n for n, _t in native.Soa._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mmlst.h"\nint main(void){printf("%zu", sizeof(mmlst_soa));' +
+                   "".join('printf(" %%zu", offsetof(mmlst_soa, %s));' % f for f in fields) + 'printf(" %zu %zu", sizeof(mmlst_prec), sizeof(mmlst_chunk));return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", inc, str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert got[0] == C.sizeof(native.Soa)
+    assert got[1:1 + len(fields)] == [getattr(native.Soa, f).offset for f in fields]
+    assert got[-2:] == [packing.PREC_DTYPE.itemsize, C.sizeof(native.Chunk)]
+
+
+@pytest.mark.parametrize("n", [0, 1, 255, 256, 257, 5000, 70001])
+def test_build_runs_is_the_run_length_form_of_tid(n):
+    import ctypes as C
+    rng = np.random.default_rng(n)
+    for style in ("sorted", "single", "alternating"):
+        if style == "sorted":
+            tid = np.sort(rng.integers(0, 40, n)).astype(np.uint32)
+        elif style == "single":
+            tid = np.full(n, 7, np.uint32)
+        else:
+            tid = (np.arange(n) % 3).astype(np.uint32)
+        soa = packing.SoaHost([], np.zeros(0, np.int32), tid, np.zeros(n, np.int16), np.zeros(n, np.uint8), np.zeros(n, np.uint16), None,
+                              np.zeros(0, packing.PREC_DTYPE), np.zeros(0, np.uint32), 0, np.zeros(1, np.uint64))
+        soa.build_runs(max_fraction=1.0)
+        if n == 0:
+            assert soa.run_tid is None
+            continue
+        starts = np.concatenate([[0], np.nonzero(tid[1:] != tid[:-1])[0] + 1])
+        assert np.array_equal(soa.run_tid, tid[starts])
+        assert np.array_equal(soa.run_start, np.concatenate([starts, [n]]))
+        assert np.array_equal(np.repeat(soa.run_tid, np.diff(soa.run_start.astype(np.int64))), tid)  # lossless
+        first = np.arange(0, n, 256)
+        assert np.array_equal(soa.chunk_run, np.searchsorted(soa.run_start, first, side="right") - 1)
+        cs = soa.c_struct()
+        assert cs.n_runs == len(starts) and cs.run_tid == soa.run_tid.ctypes.data
+        # capacity is checked, not overrun
+        nr = C.c_uint32(len(starts) - 1)
+        rt = np.zeros(len(starts) + 1, np.uint32); rs = np.zeros(len(starts) + 2, np.uint32); cr = np.zeros(len(first), np.uint32)
+        if len(starts) > 1:
+            assert native.lib().mmlst_build_runs(native.ptr(tid), n, native.ptr(rt), native.ptr(rs), native.ptr(cr), C.byref(nr)) == -1
+    # the threshold keeps the explicit form for run-poor streams
+    if n >= 256:
+        soa.build_runs(max_fraction=0.125)
+        assert soa.run_tid is None
 
 
 def test_no_device_fails_loudly():
