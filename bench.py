@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--only-hamming", action="store_true", help="run only the configs[4] Hamming sweep (profiling aid)")
     ap.add_argument("--exchange", default="gather", choices=["gather", "allreduce"],
                     help="N>1: 'gather' = owner mode, one all-gather of result blocks per pass; 'allreduce' = partial score/count tensors all-reduced")
+    ap.add_argument("--lanes", type=int, default=2, help="N=1: streams that consecutive passes alternate on (cohort mode: the tail of pass i "
+                    "overlaps the scoring kernel of pass i+1); 1 = strictly serial passes")
     ap.add_argument("--max-depth", type=int, default=8000, help="htslib pileup depth cap of the main workload (0 = uncapped; profiling aid)")
     return ap.parse_args()
 
@@ -220,6 +222,9 @@ def workload_config(args, world):
             "sharding": "replica" if world == 1 else ("contig-aligned: each rank owns the records of a disjoint locus set; " + (
                 "owner mode, ONE all-gather of the per-rank result blocks per pass" if args.exchange == "gather" else
                 "all-reduce SUM(sum_as,n_hit,counters) MIN(first_idx) SUM(counts)")),
+            "schedule": ("cohort mode: consecutive passes alternate over %d streams, so the latency-bound tail of pass i (selection, capped pileup, "
+                         "consensus) runs under the HBM-bound scoring kernel of pass i+1; every pass is complete (own tables, own D2H) inside the timed "
+                         "region; strictly serial passes: serial_ms_per_step" % args.lanes) if world == 1 and args.lanes > 1 else "serial passes on one stream",
             "l2": "the %d MB score stream (run-length form, 5 B/record) exceeds the 126 MB L2 and is re-streamed every step (no flush needed)" % (args.reads * args.k * 5 // 1000000)}
 
 
@@ -306,10 +311,33 @@ def main():
     e1.record()
     barrier()
     out = pipe.collect()
+    serial_ms = e0.elapsed_time(e1) / args.steps
+    serial_launches = pipe.launches
+    lanes = None
+    if world == 1 and args.lanes > 1:
+        # cohort mode: passes alternate over `lanes` streams, each lane with its own tables / output block / graph
+        lanes = pipeline.CohortLanes(lambda: pipeline.DevicePipeline(st, index, db.row_seq, impl=args.pileup_impl, idx_base=0, **PARAMS), args.lanes)
+        for r in lanes.warm_and_capture(graph=use_graph):
+            assert r == result, "a cohort lane disagrees with the serial pass"
+        for i in range(2 * args.lanes):  # warm the overlapped schedule itself
+            lanes.enqueue(i)
+        assert all(r == result for r in lanes.collect())
+        for p in lanes.pipes:
+            p.launches = 0
+        barrier()
+        e0.record()
+        lanes.fork(e0)
+        for i in range(args.steps):
+            lanes.enqueue(i)
+        lanes.join()
+        e1.record()
+        barrier()
+        outs = lanes.collect()
+        assert all(o == result for o in outs), "cohort-mode results differ from the serial pass"
     if prof:
         torch.cuda.profiler.stop()
     assert out == result, "results changed between steps"
-    launches = pipe.launches
+    launches = lanes.launches if lanes is not None else serial_launches
     # per-kernel durations: 20 back-to-back launches of each kernel of the same pass between two CUDA events on the
     # launching stream (events are not graph-capturable; a single launch would carry the event/launch gap)
     kms = pipe.time_kernels(20)
@@ -350,7 +378,8 @@ def main():
             "config": workload_config(args, world), "clocks": None, "gpu_launches": launches,
             "roofline": dict(rooflines[dominant], kernel=dominant, peak_source=peak_src), "rooflines": rooflines,
             "kernel_ms_per_step": kms, "records_per_gpu": R_local, "cuda_graph": use_graph,
-            "non_kernel_ms_per_step": ms - sum(kms.values()), "latency_ms_per_step_with_host_sync": lat_ms}
+            "serial_ms_per_step": serial_ms, "lanes": args.lanes if lanes is not None else 1,
+            "non_kernel_ms_per_step": serial_ms - sum(kms.values()), "latency_ms_per_step_with_host_sync": lat_ms}
 
     # ---- end to end through the host-buffer C-ABI (pinned host memory -> results on the host), every rank on its own shard;
     # with N>1 the ranks' results are all-gathered inside the timed region (each rank owns whole loci)

@@ -9,6 +9,8 @@
 // (6 fully coalesced 128/64-bit streaming loads per lane) before reducing either, and carries the running (allele, sum,
 // hits, first index) of the open run in registers -- one atomic triple per (run, warp).  A chunk that lies inside one run
 // takes the uniform path (three REDUX); a chunk crossing run boundaries is reduced segment by segment.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -79,46 +81,85 @@ __device__ __forceinline__ void close_run(const RunArgs& a, WarpRun& w, uint32_t
     if (lane == 0 && w.al) flush_run(a, w.key, w.s, w.c, w.mn);
 }
 
-// sum / count / first index of the lane's records selected by mask m (bit k = record k of the lane's 8)
+// ---- the three filters of metamlst.py:115 on packed fields, without unpacking the records (SWAR)
+// Unsigned lane-wise x >= t for lanes of any width with top bit H: d = (x | H) - (t & ~H) never borrows across lanes and
+// its top bit says x_low >= t_low; then x >= t  <=>  (x_h & ~t_h) | (~(x_h ^ t_h) & d_h).  Signed as0 is compared
+// after biasing both sides by 0x8000 (only the top bit of x changes, so the bias folds into the logic).
+struct Thr {
+    uint32_t as_T, as_TL;  // (minscore + 32768) in both halves; the same without the top bits
+    uint32_t ql_T, ql_TL;  // min_read_len in both halves
+    uint32_t xm_T, xm_TH;  // max_xm in all four bytes; the same with the top bits set
+    uint32_t h8;           // 0x80808080, or 0 when a threshold lies outside its field and nothing can pass
+};
+constexpr uint32_t H16 = 0x80008000u, H8 = 0x80808080u;
+
+__device__ __forceinline__ Thr make_thr(const RunArgs& a) {
+    Thr t;
+    const bool none = a.minscore > 32767 || a.min_read_len > 65535 || a.max_xm < 0;
+    const uint32_t ts = static_cast<uint32_t>(max(a.minscore, -32768) + 32768) & 0xffffu;
+    const uint32_t tq = static_cast<uint32_t>(min(max(a.min_read_len, 0), 65535));
+    const uint32_t tx = static_cast<uint32_t>(min(max(a.max_xm, 0), 255));
+    t.as_T = ts | (ts << 16); t.as_TL = t.as_T & ~H16;
+    t.ql_T = tq | (tq << 16); t.ql_TL = t.ql_T & ~H16;
+    t.xm_T = tx * 0x01010101u; t.xm_TH = t.xm_T | H8;
+    t.h8 = none ? 0u : H8;
+    return t;
+}
+
+// p_lo / p_hi: one byte per record (records 0-3 / 4-7 of the lane), 1 = passes all three filters
 template <bool OIDX>
-__device__ __forceinline__ void lane_sums(const Loaded<OIDX>& L, const int (&as)[8], uint32_t m, uint32_t idx0, int& s, uint32_t& c, uint32_t& mn) {
-    s = 0;
+__device__ __forceinline__ void lane_pass(const Loaded<OIDX>& L, const Thr& t, uint32_t& p_lo, uint32_t& p_hi) {
+    const uint32_t aw[4] = {L.a8.x, L.a8.y, L.a8.z, L.a8.w};
+    const uint32_t qw[4] = {L.q8.x, L.q8.y, L.q8.z, L.q8.w};
+    uint32_t m[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += (m & (1u << k)) ? as[k] : 0;
-    c = __popc(m);
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t da = (aw[w] | H16) - t.as_TL;
+        const uint32_t ga = (~aw[w] & ~t.as_T) | ((aw[w] ^ t.as_T) & da);          // as0 >= minscore (signed halves)
+        const uint32_t dq = (qw[w] | H16) - t.ql_TL;
+        const uint32_t gq = (qw[w] & ~t.ql_T) | (~(qw[w] ^ t.ql_T) & dq);         // qlen >= min_read_len
+        m[w] = ga & gq & H16;
+    }
+    const uint32_t b_lo = __byte_perm(m[0], m[1], 0x7531), b_hi = __byte_perm(m[2], m[3], 0x7531);  // top byte of every half
+    const uint32_t x0 = L.x8.x, x1 = L.x8.y;
+    const uint32_t d0 = t.xm_TH - (x0 & ~H8), d1 = t.xm_TH - (x1 & ~H8);
+    const uint32_t g0 = (t.xm_T & ~x0) | (~(t.xm_T ^ x0) & d0), g1 = (t.xm_T & ~x1) | (~(t.xm_T ^ x1) & d1);  // max_xm >= xm3
+    p_lo = (b_lo & g0 & t.h8) >> 7;
+    p_hi = (b_hi & g1 & t.h8) >> 7;
+}
+
+// sum / count / first index of the lane's records selected by the byte masks
+template <bool OIDX>
+__device__ __forceinline__ void lane_sums(const Loaded<OIDX>& L, uint32_t p_lo, uint32_t p_hi, uint32_t idx0, int& s, uint32_t& c, uint32_t& mn) {
+    s = __dp2a_lo(static_cast<int>(L.a8.x), static_cast<int>(p_lo), 0);   // as0[0] p[0] + as0[1] p[1]
+    s = __dp2a_hi(static_cast<int>(L.a8.y), static_cast<int>(p_lo), s);
+    s = __dp2a_lo(static_cast<int>(L.a8.z), static_cast<int>(p_hi), s);
+    s = __dp2a_hi(static_cast<int>(L.a8.w), static_cast<int>(p_hi), s);
+    c = __popc(p_lo | (p_hi << 1));
     if constexpr (OIDX) {
         mn = 0xffffffffu;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) mn = (m & (1u << k)) ? min(mn, rec_index<true>(L, idx0, k)) : mn;
+        for (int k = 0; k < 8; ++k) mn = (((k < 4 ? p_lo : p_hi) >> (8 * (k & 3))) & 1u) ? min(mn, rec_index<true>(L, idx0, k)) : mn;
     } else {
-        mn = m ? idx0 + static_cast<uint32_t>(__ffs(m) - 1) : 0xffffffffu;
+        const uint32_t k = p_lo ? (static_cast<uint32_t>(__ffs(p_lo)) - 1u) >> 3 : 4u + ((static_cast<uint32_t>(__ffs(p_hi)) - 1u) >> 3);
+        mn = (p_lo | p_hi) ? idx0 + k : 0xffffffffu;
     }
 }
 
 // one 256-record chunk starting at record `base` (this lane: records base + 8 lane .. + 7)
 template <bool OIDX>
-__device__ __forceinline__ void reduce_chunk(const RunArgs& a, WarpRun& w, const Loaded<OIDX>& L, uint64_t base, uint32_t lane,
+__device__ __forceinline__ void reduce_chunk(const RunArgs& a, const Thr& thr, WarpRun& w, const Loaded<OIDX>& L, uint64_t base, uint32_t lane,
                                              uint32_t& tot, uint32_t& ign) {
-    constexpr int R = 8;
-    const uint32_t aw[4] = {L.a8.x, L.a8.y, L.a8.z, L.a8.w};
-    const uint32_t qw[4] = {L.q8.x, L.q8.y, L.q8.z, L.q8.w};
-    const uint32_t xw[2] = {L.x8.x, L.x8.y};
+    constexpr uint32_t R = 8;
     const uint64_t rec0 = base + (lane << 3);
     const uint32_t idx0 = static_cast<uint32_t>(a.idx_base + rec0);
-    int as[R];
-    uint32_t pass = 0;
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-        as[k] = (k & 1) ? (static_cast<int>(aw[k >> 1]) >> 16) : static_cast<int>(static_cast<short>(aw[k >> 1] & 0xffffu));
-        const int ql = (k & 1) ? int(qw[k >> 1] >> 16) : int(qw[k >> 1] & 0xffffu);
-        const int xm = int((xw[k >> 2] >> (8 * (k & 3))) & 255u);
-        pass |= ((as[k] >= a.minscore) && (ql >= a.min_read_len) && (xm <= a.max_xm)) ? (1u << k) : 0u;
-    }
+    uint32_t p_lo, p_hi;
+    lane_pass<OIDX>(L, thr, p_lo, p_hi);
     const uint64_t chunk_end = base + 256;
     if (chunk_end <= w.end) {  // the whole chunk lies inside the open run
         if (w.al) {
             int s; uint32_t c, mn;
-            lane_sums<OIDX>(L, as, pass, idx0, s, c, mn);
+            lane_sums<OIDX>(L, p_lo, p_hi, idx0, s, c, mn);
             tot += R;
             ign += R - c;
             w.s += __reduce_add_sync(FULL, s);
@@ -132,13 +173,17 @@ __device__ __forceinline__ void reduce_chunk(const RunArgs& a, WarpRun& w, const
     while (lo < chunk_end) {  // segment [lo, hi) of the chunk belongs to the open run
         const uint64_t hi = (w.end < chunk_end) ? static_cast<uint64_t>(w.end) : chunk_end;
         if (w.al) {
-            // the lane's records inside the segment: bits [klo, khi) of its 8
+            // the lane's records inside the segment: bytes [klo, khi) of its 8
             const uint32_t klo = lo <= rec0 ? 0u : (lo - rec0 >= R ? R : static_cast<uint32_t>(lo - rec0));
             const uint32_t khi = hi <= rec0 ? 0u : (hi - rec0 >= R ? R : static_cast<uint32_t>(hi - rec0));
-            const uint32_t inm = khi > klo ? (((1u << khi) - 1u) & ~((1u << klo) - 1u)) : 0u;
+            const unsigned long long ones = 0x0101010101010101ull;
+            const unsigned long long below_hi = khi >= 8 ? ~0ull : ((1ull << (8 * khi)) - 1ull);
+            const unsigned long long below_lo = klo >= 8 ? ~0ull : ((1ull << (8 * klo)) - 1ull);
+            const unsigned long long inm = khi > klo ? (below_hi & ~below_lo & ones) : 0ull;
+            const uint32_t in_lo = static_cast<uint32_t>(inm), in_hi = static_cast<uint32_t>(inm >> 32);
             int s; uint32_t c, mn;
-            lane_sums<OIDX>(L, as, pass & inm, idx0, s, c, mn);
-            const uint32_t in = __popc(inm);
+            lane_sums<OIDX>(L, p_lo & in_lo, p_hi & in_hi, idx0, s, c, mn);
+            const uint32_t in = khi > klo ? khi - klo : 0u;
             tot += in;
             ign += in - c;
             w.s += __reduce_add_sync(FULL, s);
@@ -150,8 +195,8 @@ __device__ __forceinline__ void reduce_chunk(const RunArgs& a, WarpRun& w, const
     }
 }
 
-template <bool OIDX>
-__global__ void __launch_bounds__(kThreads, 4) score_runs_kernel(const RunArgs a) {
+template <bool OIDX, bool PIPE>
+__global__ void __launch_bounds__(kThreads, PIPE ? (OIDX ? 2 : 3) : (OIDX ? 3 : 4)) score_runs_kernel(const RunArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -160,22 +205,44 @@ __global__ void __launch_bounds__(kThreads, 4) score_runs_kernel(const RunArgs a
     const uint64_t c0 = warp * per;
     const uint64_t c1 = (c0 + per < nchunks) ? c0 + per : nchunks;
     uint32_t tot = 0, ign = 0;
+    const Thr thr = make_thr(a);
 
     if (c0 < c1) {
+        // software pipeline: the loads of the NEXT pair of chunks are issued before the current pair is reduced, so every
+        // warp keeps 2.5 KB in flight while it computes; the first pair is requested before the (dependent) run lookup
+        uint64_t ch = c0;
+        Loaded<OIDX> A0, A1;
+        bool have = ch + 1 < c1;
+        if (have) { A0 = load_chunk<OIDX>(a, (ch << 8) + (lane << 3)); A1 = load_chunk<OIDX>(a, ((ch + 1) << 8) + (lane << 3)); }
         WarpRun w;
         open_run(a, w, __ldg(a.chunk_run + c0));
-        uint64_t ch = c0;
-        for (; ch + 1 < c1; ch += 2) {  // two chunks' loads in flight before either is reduced
-            const uint64_t base = ch << 8;
-            const Loaded<OIDX> L0 = load_chunk<OIDX>(a, base + (lane << 3));
-            const Loaded<OIDX> L1 = load_chunk<OIDX>(a, base + 256 + (lane << 3));
-            reduce_chunk<OIDX>(a, w, L0, base, lane, tot, ign);
-            reduce_chunk<OIDX>(a, w, L1, base + 256, lane, tot, ign);
+        Loaded<OIDX> B0, B1;  // ping-pong register buffers: no copy between them (a copy would wait for the loads)
+        if constexpr (!PIPE) {
+            while (have) {
+                reduce_chunk<OIDX>(a, thr, w, A0, ch << 8, lane, tot, ign);
+                reduce_chunk<OIDX>(a, thr, w, A1, (ch + 1) << 8, lane, tot, ign);
+                ch += 2;
+                have = ch + 1 < c1;
+                if (have) { A0 = load_chunk<OIDX>(a, (ch << 8) + (lane << 3)); A1 = load_chunk<OIDX>(a, ((ch + 1) << 8) + (lane << 3)); }
+            }
+        }
+        while (have) {
+            const bool moreB = ch + 3 < c1;
+            if (moreB) { B0 = load_chunk<OIDX>(a, ((ch + 2) << 8) + (lane << 3)); B1 = load_chunk<OIDX>(a, ((ch + 3) << 8) + (lane << 3)); }
+            reduce_chunk<OIDX>(a, thr, w, A0, ch << 8, lane, tot, ign);
+            reduce_chunk<OIDX>(a, thr, w, A1, (ch + 1) << 8, lane, tot, ign);
+            ch += 2;
+            if (!moreB) break;
+            have = ch + 3 < c1;
+            if (have) { A0 = load_chunk<OIDX>(a, ((ch + 2) << 8) + (lane << 3)); A1 = load_chunk<OIDX>(a, ((ch + 3) << 8) + (lane << 3)); }
+            reduce_chunk<OIDX>(a, thr, w, B0, ch << 8, lane, tot, ign);
+            reduce_chunk<OIDX>(a, thr, w, B1, (ch + 1) << 8, lane, tot, ign);
+            ch += 2;
         }
         if (ch < c1) {
             const uint64_t base = ch << 8;
             const Loaded<OIDX> L0 = load_chunk<OIDX>(a, base + (lane << 3));
-            reduce_chunk<OIDX>(a, w, L0, base, lane, tot, ign);
+            reduce_chunk<OIDX>(a, thr, w, L0, base, lane, tot, ign);
         }
         close_run(a, w, lane);
     }
@@ -240,18 +307,19 @@ extern "C" int mmlst_score_runs_dev(const uint32_t* run_tid, const uint32_t* run
               min_read_len, reinterpret_cast<long long*>(sum_as), n_hit, first_idx, reinterpret_cast<unsigned long long*>(counters)};
     const uint64_t nchunks = n_rec >> 8;
     uint64_t want = (nchunks + 15) / 16;  // CTAs if every warp took two chunks
-    static int resident[2] = {0, 0};  // one wave exactly: the blocked chunk distribution has no tail
-    const int v = orig_idx ? 1 : 0;
+    static int resident[4] = {0, 0, 0, 0};  // one wave exactly: the blocked chunk distribution has no tail
+    static int pipe = -1;
+    if (pipe < 0) { const char* e = getenv("MMLST_SCORE_PIPE"); pipe = (e && e[0] == '1') ? 1 : 0; }
+    const int v = (orig_idx ? 1 : 0) + 2 * pipe;
+    void (*kern)(const RunArgs) = v == 0 ? score_runs_kernel<false, false> : v == 1 ? score_runs_kernel<true, false>
+                                  : v == 2 ? score_runs_kernel<false, true> : score_runs_kernel<true, true>;
     if (!resident[v]) {
-        const cudaError_t e = v ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident[v], score_runs_kernel<true>, kThreads, 0)
-                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident[v], score_runs_kernel<false>, kThreads, 0);
-        if (e != cudaSuccess || resident[v] < 1) resident[v] = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident[v], kern, kThreads, 0) != cudaSuccess || resident[v] < 1) resident[v] = 3;
     }
     const uint64_t cap = static_cast<uint64_t>(mmlst_num_sms()) * resident[v];
     if (want > cap) want = cap;
     if (want < 1) want = 1;
-    if (v) score_runs_kernel<true><<<static_cast<unsigned>(want), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
-    else score_runs_kernel<false><<<static_cast<unsigned>(want), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    kern<<<static_cast<unsigned>(want), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
     CUDA_TRY(cudaGetLastError());
     return MMLST_OK;
 }

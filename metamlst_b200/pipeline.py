@@ -439,6 +439,62 @@ class DevicePipeline:
         return out
 
 
+class CohortLanes:
+    """Cohort mode (BASELINE.json configs[3]): consecutive samples are independent, so pass i+1 is
+    queued on another stream than pass i -- the latency-bound tail of a pass (selection, capped pileup, consensus: small
+    grids) runs underneath the HBM-bound scoring kernel of the next one.  Every lane is a DevicePipeline with its own
+    accumulators / output block and its own CUDA graph; lanes may share the input streams (the bench re-types one sample)
+    or hold different samples (a real cohort)."""
+
+    def __init__(self, make_pipe: Callable[[], "DevicePipeline"], n_lanes: int = 2):
+        self.pipes = [make_pipe() for _ in range(n_lanes)]
+        self.dev = self.pipes[0].dev
+        self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(n_lanes)]
+        self.captured = False
+
+    def warm_and_capture(self, graph: bool = True):
+        res = []
+        for p, st in zip(self.pipes, self.streams):
+            with torch.cuda.stream(st):
+                r = p.step()
+                if graph:
+                    p.capture()
+                    assert p.step_graph() == r, "graph replay differs from the eager pass"
+                res.append(r)
+        self.captured = graph
+        torch.cuda.synchronize(self.dev)
+        return res
+
+    def enqueue(self, i: int) -> None:
+        lane = i % len(self.pipes)
+        with torch.cuda.stream(self.streams[lane]):
+            self.pipes[lane].enqueue_step()
+
+    def fork(self, event: "torch.cuda.Event") -> None:
+        """All lanes start after `event` (recorded on the timing stream)."""
+        for st in self.streams:
+            st.wait_event(event)
+
+    def join(self) -> None:
+        """The current stream waits for everything queued on the lanes."""
+        cur = torch.cuda.current_stream(self.dev)
+        for st in self.streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            cur.wait_event(ev)
+
+    def collect(self):
+        out = []
+        for p, st in zip(self.pipes, self.streams):
+            with torch.cuda.stream(st):
+                out.append(p.collect())
+        return out
+
+    @property
+    def launches(self) -> int:
+        return sum(p.launches for p in self.pipes)
+
+
 def device_select(index: api.AlleleIndex, sum_as: np.ndarray, n_hit: np.ndarray, first_idx: np.ndarray, penalty: int = 100,
                   nloci: int = 100, genes_in_db: Optional[Dict[str, int]] = None, device: str = "cuda:0"):
     """mmlst_select_dev on given score tables -> [(species, [tid per locus])] in the reference's dict order
