@@ -175,6 +175,7 @@ class SampleTyper:
             consenSeq = api.build_consensus(self.ctx, soa, chromosomeList, self.minscore, self.max_xM, self.debug)
             finWrite = 1
             if want_stdout:
+                out.append("\r")  # buildConsensus ends with print('\r', end='') (metaMLST_functions.py:278)
                 out.append("\r\n  " + "Locus".ljust(7) + "Ref.".ljust(7) + "Length".rjust(7) + "Ns".rjust(7) + "SNPs".rjust(7) + "Confidence".rjust(15) + "Notes".rjust(10) + "\n")
             for l in sorted(consenSeq, key=lambda x: x.id):  # metamlst.py:253-276
                 holes = str(l.description.split("_")[0].split("::")[1])
