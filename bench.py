@@ -223,8 +223,9 @@ def workload_config(args, world):
                 "owner mode, ONE all-gather of the per-rank result blocks per pass" if args.exchange == "gather" else
                 "all-reduce SUM(sum_as,n_hit,counters) MIN(first_idx) SUM(counts)")),
             "schedule": ("cohort mode: consecutive passes alternate over %d streams, so the latency-bound tail of pass i (selection, capped pileup, "
-                         "consensus) runs under the HBM-bound scoring kernel of pass i+1; every pass is complete (own tables, own D2H) inside the timed "
-                         "region; strictly serial passes: serial_ms_per_step" % args.lanes) if world == 1 and args.lanes > 1 else "serial passes on one stream",
+                         "consensus%s) runs under the HBM-bound scoring kernel of pass i+1; every pass is complete (own tables, own D2H) inside the timed "
+                         "region; strictly serial passes: serial_ms_per_step" % (args.lanes, ", the exchange on the lane's own communicator" if world > 1 else ""))
+            if args.lanes > 1 else "serial passes on one stream",
             "l2": "the %d MB score stream (run-length form, 5 B/record) exceeds the 126 MB L2 and is re-streamed every step (no flush needed)" % (args.reads * args.k * 5 // 1000000)}
 
 
@@ -314,9 +315,12 @@ def main():
     serial_ms = e0.elapsed_time(e1) / args.steps
     serial_launches = pipe.launches
     lanes = None
-    if world == 1 and args.lanes > 1:
-        # cohort mode: passes alternate over `lanes` streams, each lane with its own tables / output block / graph
-        lanes = pipeline.CohortLanes(lambda: pipeline.DevicePipeline(st, index, db.row_seq, impl=args.pileup_impl, idx_base=0, **PARAMS), args.lanes)
+    if args.lanes > 1:
+        # cohort mode: passes alternate over `lanes` streams, each lane with its own tables / output block / graph and, with
+        # N>1, its own NCCL communicator (collectives of different lanes may be in flight together)
+        groups = [torch.distributed.new_group(list(range(world))) if world > 1 else None for _ in range(args.lanes)]
+        lanes = pipeline.CohortLanes(lambda lane: pipeline.DevicePipeline(st, index, db.row_seq, impl=args.pileup_impl, idx_base=rank * R_local,
+                                                                          exchange=args.exchange, group=groups[lane], **PARAMS), args.lanes)
         for r in lanes.warm_and_capture(graph=use_graph):
             assert r == result, "a cohort lane disagrees with the serial pass"
         for i in range(2 * args.lanes):  # warm the overlapped schedule itself

@@ -446,8 +446,10 @@ class CohortLanes:
     accumulators / output block and its own CUDA graph; lanes may share the input streams (the bench re-types one sample)
     or hold different samples (a real cohort)."""
 
-    def __init__(self, make_pipe: Callable[[], "DevicePipeline"], n_lanes: int = 2):
-        self.pipes = [make_pipe() for _ in range(n_lanes)]
+    def __init__(self, make_pipe: Callable[[int], "DevicePipeline"], n_lanes: int = 2):
+        """make_pipe(lane) -> DevicePipeline.  With torch.distributed every lane must get its OWN process group
+        (communicator): collectives of consecutive passes overlap, and NCCL serialises nothing across communicators."""
+        self.pipes = [make_pipe(lane) for lane in range(n_lanes)]
         self.dev = self.pipes[0].dev
         self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(n_lanes)]
         self.captured = False
