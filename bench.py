@@ -45,8 +45,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay of the pass")
     ap.add_argument("--cpu-sample-reads", type=int, default=400_000)
     ap.add_argument("--only-hamming", action="store_true", help="run only the configs[4] Hamming sweep (profiling aid)")
-    ap.add_argument("--exchange", default="gather", choices=["gather", "allreduce"],
-                    help="N>1: 'gather' = owner mode, one all-gather of result blocks per pass; 'allreduce' = partial score/count tensors all-reduced")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "gather", "allreduce"],
+                    help="N>1: 'p2p' = owner mode, result blocks stored into the peers' memory over NVLink by our own kernels; 'gather' = owner mode, "
+                         "one NCCL all-gather of result blocks per pass; 'allreduce' = partial score/count tensors all-reduced with NCCL")
     ap.add_argument("--lanes", type=int, default=2, help="N=1: streams that consecutive passes alternate on (cohort mode: the tail of pass i "
                     "overlaps the scoring kernel of pass i+1); 1 = strictly serial passes")
     ap.add_argument("--max-depth", type=int, default=8000, help="htslib pileup depth cap of the main workload (0 = uncapped; profiling aid)")
@@ -220,11 +221,13 @@ def workload_config(args, world):
                         "E. coli + S. aureus + K. pneumoniae synthetic schemes, 21 loci x %d alleles" % (args.reads, args.read_len, args.k, args.reads * args.k, args.alleles),
             "mode": ("parity (htslib max_depth %d, minqual 20, minscore 80, max_xM 5)" % args.max_depth) if args.max_depth else "uncapped (no depth cap; NOT the reference's semantics)",
             "sharding": "replica" if world == 1 else ("contig-aligned: each rank owns the records of a disjoint locus set; " + (
-                "owner mode, ONE all-gather of the per-rank result blocks per pass" if args.exchange == "gather" else
+                "owner mode, result blocks stored straight into every peer's memory over NVLink (csrc/exchange.cu: publish + await kernels, no NCCL "
+                "call inside the pass)" if args.exchange == "p2p" else
+                "owner mode, ONE NCCL all-gather of the per-rank result blocks per pass" if args.exchange == "gather" else
                 "all-reduce SUM(sum_as,n_hit,counters) MIN(first_idx) SUM(counts)")),
             "schedule": ("cohort mode: consecutive passes alternate over %d streams, so the latency-bound tail of pass i (selection, capped pileup, "
                          "consensus%s) runs under the HBM-bound scoring kernel of pass i+1; every pass is complete (own tables, own D2H) inside the timed "
-                         "region; strictly serial passes: serial_ms_per_step" % (args.lanes, ", the exchange on the lane's own communicator" if world > 1 else ""))
+                         "region; strictly serial passes: serial_ms_per_step" % (args.lanes, ", the exchange" if world > 1 else ""))
             if args.lanes > 1 else "serial passes on one stream",
             "l2": "the %d MB score stream (run-length form, 5 B/record) exceeds the 126 MB L2 and is re-streamed every step (no flush needed)" % (args.reads * args.k * 5 // 1000000)}
 
@@ -275,6 +278,20 @@ def main():
     subset = None if world == 1 else [l for l in range(n_loci) if l % world == rank]
     st, _ = gen_streams(db, args, device, args.max_depth or None, subset, seed=1002 + rank)
     R_local = int(st.tid.shape[0])
+    if world > 1 and args.exchange == "p2p":
+        # peer-mapped memory needs P2P access between the GPUs of the box: probe it once, and let every rank agree
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm
+            probe = symm.empty(4096, dtype=torch.uint8, device=device)
+            symm.rendezvous(probe, torch.distributed.group.WORLD)
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write("peer-mapped memory unavailable (%r): using the NCCL all-gather form\n" % (e,))
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            args.exchange = "gather"
     pipe = pipeline.DevicePipeline(st, index, db.row_seq, impl=args.pileup_impl, idx_base=rank * R_local, exchange=args.exchange, **PARAMS)
 
     def barrier():
@@ -318,7 +335,7 @@ def main():
     if args.lanes > 1:
         # cohort mode: passes alternate over `lanes` streams, each lane with its own tables / output block / graph and, with
         # N>1, its own NCCL communicator (collectives of different lanes may be in flight together)
-        groups = [torch.distributed.new_group(list(range(world))) if world > 1 else None for _ in range(args.lanes)]
+        groups = [torch.distributed.new_group(list(range(world))) if world > 1 and args.exchange != "p2p" else None for _ in range(args.lanes)]
         lanes = pipeline.CohortLanes(lambda lane: pipeline.DevicePipeline(st, index, db.row_seq, impl=args.pileup_impl, idx_base=rank * R_local,
                                                                           exchange=args.exchange, group=groups[lane], **PARAMS), args.lanes)
         for r in lanes.warm_and_capture(graph=use_graph):
@@ -431,24 +448,26 @@ def main():
 
     if world > 1 and not args.no_extras:
         # the other exchange form on the same shards, and the row-sharded Hamming sweep (configs[4])
-        other = "allreduce" if args.exchange == "gather" else "gather"
-        pipe2 = pipeline.DevicePipeline(st, index, db.row_seq, impl=args.pileup_impl, idx_base=rank * R_local, exchange=other, **PARAMS)
-        for _ in range(3):
-            res2 = pipe2.step()
-        assert res2 == result, "the two exchange forms disagree"
-        pipe2.capture()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(args.steps):
-            pipe2.enqueue_step()
-        f1.record()
-        barrier()
-        assert pipe2.collect() == result
-        t2 = torch.tensor([f0.elapsed_time(f1) / args.steps], dtype=torch.float64, device=device)
-        torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
-        line["other_exchange"] = {"exchange": other, "ms_per_step": float(t2.item()), "value": R_total / (float(t2.item()) / 1e3), "unit": "records/s"}
-        del pipe2
+        line["other_exchange"] = []
+        for other in [x for x in ("p2p", "gather", "allreduce") if x != args.exchange]:
+            pipe2 = pipeline.DevicePipeline(st, index, db.row_seq, impl=args.pileup_impl, idx_base=rank * R_local, exchange=other, **PARAMS)
+            for _ in range(3):
+                res2 = pipe2.step()
+            assert res2 == result, "the exchange forms disagree"
+            pipe2.capture()
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(args.steps):
+                pipe2.enqueue_step()
+            f1.record()
+            barrier()
+            assert pipe2.collect() == result
+            t2 = torch.tensor([f0.elapsed_time(f1) / args.steps], dtype=torch.float64, device=device)
+            torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
+            line["other_exchange"].append({"exchange": other, "schedule": "serial passes on one stream", "ms_per_step": float(t2.item()),
+                                           "value": R_total / (float(t2.item()) / 1e3), "unit": "records/s"})
+            del pipe2
         line["hamming_sharded"] = extra_hamming(device, peak, world=world, rank=rank)
     if rank == 0 and world == 1 and not args.no_extras:
         line["uncapped"] = extra_uncapped(db, args, device, index, peak)

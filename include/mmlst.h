@@ -216,6 +216,25 @@ int mmlst_consensus_indirect_dev(uint32_t* counts, const uint8_t* db_ascii, cons
                                  uint32_t* snps, uint32_t flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Multi-GPU, owner mode: a GPU that holds whole loci (contig-aligned shard) finishes them itself and
+ * the pass ends with every GPU holding every GPU's result block.  The reference is single-process (no counterpart);
+ * this pair replaces an NCCL all-gather by direct stores into the peers' memory over NVLink.
+ *   Symmetric buffer, same layout on every GPU (allocated peer-mapped by the caller, zeroed before first use):
+ *     [half 0: world x slot_stride][half 1: world x slot_stride][flag[world] u64 at flag_off]
+ *   peer_base[p] = address of GPU p's buffer as mapped into THIS GPU's address space (p == rank: the local one).
+ *   epoch = device u64 pass counter (starts at 0), advanced by mmlst_xchg_await_dev; both calls are graph-capturable.
+ *   mmlst_xchg_publish_dev: store `block` into slot[rank] of half ((epoch+1)&1) on every GPU, then release
+ *                           flag[rank] = epoch+1 there.  Never waits.
+ *   mmlst_xchg_await_dev  : wait until every local flag >= epoch+1, copy the world slots of that half into out_all
+ *                           (world x bytes, contiguous), epoch += 1.  A wait longer than ~2 s sets bit 2 of *status
+ *                           instead of hanging.  ticket = device u32 scratch, zero.
+ * --------------------------------------------------------------------------------------------------------------- */
+int mmlst_xchg_publish_dev(const void* block, uint32_t bytes, const uint64_t* peer_base, uint32_t rank, uint32_t world,
+                           uint64_t half_stride, uint64_t slot_stride, uint64_t flag_off, const uint64_t* epoch, void* stream);
+int mmlst_xchg_await_dev(void* local_base, uint32_t bytes, uint32_t world, uint64_t half_stride, uint64_t slot_stride,
+                         uint64_t flag_off, void* out_all, uint64_t* epoch, uint32_t* ticket, uint32_t* status, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Stage 3 -- closest known allele by zip-truncated Hamming distance.  Replaces metaMLST_functions.py:230-234
  * (stringDiff) driven by metamlst-merge.py:174-181 over sequencesGetAll (:224-228).
  *   DB rows   : bit-planes hi/lo of the 2-bit code, tiles of 32 rows, word-major inside a tile:

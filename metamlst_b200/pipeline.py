@@ -34,7 +34,9 @@ class DevicePipeline:
                  use_runs: Optional[bool] = None):
         """exchange (only with torch.distributed, world > 1): "allreduce" = partial score / count tensors are all-reduced
         (any record sharding whose depth cap was resolved beforehand); "gather" = owner mode for contig-aligned shards:
-        each rank finishes its own loci and ONE all-gather of the result blocks ends the pass (dist.merge_owner_blocks)."""
+        each rank finishes its own loci and ONE all-gather of the result blocks ends the pass (dist.merge_owner_blocks);
+        "p2p" = owner mode with the all-gather done by our own kernels over NVLink peer memory (csrc/exchange.cu): the
+        block is stored straight into every peer's symmetric buffer, no NCCL call inside the pass."""
         self.s = streams
         self.index = index
         self.dbseq_of = dbseq_of
@@ -42,9 +44,10 @@ class DevicePipeline:
         self.mincov, self.impl, self.idx_base = int(mincov), int(impl), int(idx_base)
         self.group = group
         self.dist = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
-        if exchange not in ("allreduce", "gather"):
-            raise ValueError("exchange must be 'allreduce' or 'gather'")
-        self.owner = self.dist and exchange == "gather"
+        if exchange not in ("allreduce", "gather", "p2p"):
+            raise ValueError("exchange must be 'allreduce', 'gather' or 'p2p'")
+        self.owner = self.dist and exchange in ("gather", "p2p")
+        self.p2p = self.dist and exchange == "p2p"
         self.world = torch.distributed.get_world_size() if self.dist else 1
         dev = streams.as0.device
         self.dev = dev
@@ -105,16 +108,18 @@ class DevicePipeline:
         self.o_hdr, self.o_tid, self.o_sp, self.o_col, self.o_holes, self.o_snps = 0, 16, 16 + nl, 16 + 2 * nl, 17 + 3 * nl, 17 + 4 * nl
         self.o_first = 17 + 5 * nl
         self.n_small = (17 + 6 * nl + 7) // 4 * 4
-        self.out = torch.zeros(self.n_small * 4 + self.max_cols + 16, dtype=torch.uint8, device=dev)
+        self.out = torch.zeros((self.n_small * 4 + self.max_cols + 16 + 15) // 16 * 16, dtype=torch.uint8, device=dev)
         self.small = self.out[: self.n_small * 4].view(torch.int32)
         self.cons = self.out[self.n_small * 4:]
         self.holes = self.small[self.o_holes:self.o_holes + nl]
         self.snps = self.small[self.o_snps:self.o_snps + nl]
         self.db_start_d = torch.zeros(nl + 1, dtype=torch.int64, device=dev)
         self.out_bytes = int(self.out.shape[0])
-        if self.owner:  # every rank's block, gathered
-            self.out_all = torch.zeros(self.world * self.out_bytes, dtype=torch.uint8, device=dev)
-            self.out_h = torch.zeros(self.world * self.out_bytes, dtype=torch.uint8).pin_memory()
+        if self.owner:  # every rank's block, gathered (+ 16 B: status word of the peer-memory exchange)
+            self.out_all = torch.zeros(self.world * self.out_bytes + 16, dtype=torch.uint8, device=dev)
+            self.out_h = torch.zeros(self.world * self.out_bytes + 16, dtype=torch.uint8).pin_memory()
+            if self.p2p:
+                self._init_p2p()
         else:
             self.out_h = torch.zeros(self.out_bytes, dtype=torch.uint8).pin_memory()
         self.small_h = self.out_h[: self.n_small * 4].view(torch.int32)
@@ -291,8 +296,16 @@ class DevicePipeline:
             dist.allreduce_counts(self.counts, self.group)
         self._timed("consensus", lambda: self._consensus_call(native.CONSENSUS_CONSUME))
         self.launches += 1
-        if self.owner:  # the pass's only exchange: every rank ends up with every rank's result block
-            torch.distributed.all_gather_into_tensor(self.out_all, self.out, group=self.group)
+        if self.p2p:  # the pass's only exchange, by our own kernels: block -> every peer's memory, then wait for theirs
+            native.check(self.lib.mmlst_xchg_publish_dev(native.ptr(self.out), self.out_bytes, native.ptr(self.peer_base), self.rank, self.world,
+                                                         self.x_half, self.x_slot, self.x_flag_off, native.ptr(self.x_epoch), self._stream()))
+            native.check(self.lib.mmlst_xchg_await_dev(native.ptr(self.xbuf), self.out_bytes, self.world, self.x_half, self.x_slot, self.x_flag_off,
+                                                       native.ptr(self.out_all), native.ptr(self.x_epoch), native.ptr(self.x_ticket),
+                                                       self.out_all.data_ptr() + self.world * self.out_bytes, self._stream()))
+            self.launches += 2
+            self.out_h.copy_(self.out_all, non_blocking=True)
+        elif self.owner:  # the same exchange as ONE NCCL all-gather
+            torch.distributed.all_gather_into_tensor(self.out_all[: self.world * self.out_bytes], self.out, group=self.group)
             self.out_h.copy_(self.out_all, non_blocking=True)
         else:
             self.out_h.copy_(self.out, non_blocking=True)
@@ -336,9 +349,32 @@ class DevicePipeline:
         else:
             raise ValueError(name)
 
+    def _init_p2p(self):
+        """Symmetric (peer-mapped) exchange buffer of this pipeline: torch's symmetric-memory allocator provides the
+        allocation and the address exchange; the data path is csrc/exchange.cu."""
+        import torch.distributed._symmetric_memory as symm
+        grp = self.group if self.group is not None else torch.distributed.group.WORLD
+        self.rank = torch.distributed.get_rank(grp)
+        self.x_slot = (self.out_bytes + 127) // 128 * 128
+        self.x_half = self.world * self.x_slot
+        self.x_flag_off = 2 * self.x_half
+        self.xbuf = symm.empty(self.x_flag_off + 128 * ((8 * self.world + 127) // 128), dtype=torch.uint8, device=self.dev)
+        self.xbuf.zero_()
+        torch.cuda.synchronize(self.dev)
+        self.xhdl = symm.rendezvous(self.xbuf, grp)  # collective: exchanges the handles, maps every peer's buffer
+        ptrs = [int(x) for x in self.xhdl.buffer_ptrs]
+        assert len(ptrs) == self.world and ptrs[self.rank] == self.xbuf.data_ptr(), "symmetric buffer: unexpected peer table"
+        self.peer_base = torch.tensor(ptrs, dtype=torch.int64, device=self.dev)
+        self.x_epoch = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.x_ticket = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        torch.cuda.synchronize(self.dev)
+        torch.distributed.barrier(grp)  # every buffer is zeroed and mapped before anyone publishes
+
     def _finish_owner(self):
         nl = self.index.n_loci
         blocks, total, ignored = [], 0, 0
+        if self.p2p and int(self.out_h[self.world * self.out_bytes:].view(torch.int32)[0]) != 0:
+            raise RuntimeError("peer-memory exchange timed out waiting for a peer's result block")
         for r in range(self.world):
             blk = self.out_h[r * self.out_bytes:(r + 1) * self.out_bytes]
             h = blk[: self.n_small * 4].view(torch.int32).numpy()
