@@ -229,7 +229,10 @@ def workload_config(args, world):
                          "consensus%s) runs under the HBM-bound scoring kernel of pass i+1; every pass is complete (own tables, own D2H) inside the timed "
                          "region; strictly serial passes: serial_ms_per_step" % (args.lanes, ", the exchange" if world > 1 else ""))
             if args.lanes > 1 else "serial passes on one stream",
-            "l2": "the %d MB score stream (run-length form, 5 B/record) exceeds the 126 MB L2 and is re-streamed every step (no flush needed)" % (args.reads * args.k * 5 // 1000000)}
+            "l2": "consecutive passes type two different samples of this shape alternately (a cohort): their score streams together (2 x %d MB in the "
+                  "3 B/record form, 2 x %d MB in the 5 B form) exceed the 126 MB L2, so every pass streams its input from HBM; per-kernel timings: score "
+                  "alternates the two samples back to back, select/pileup/consensus are timed one launch at a time after rewriting a 256 MB buffer "
+                  "(L2 flush)" % (args.reads * args.k * 3 // 1000000, args.reads * args.k * 5 // 1000000)}
 
 
 _REAL_STDOUT = None
@@ -292,7 +295,13 @@ def main():
         torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
         if int(flag.item()) == 0:
             args.exchange = "gather"
-    pipe = pipeline.DevicePipeline(st, index, db.row_seq, impl=args.pileup_impl, idx_base=rank * R_local, exchange=args.exchange, **PARAMS)
+    # consecutive passes type DIFFERENT samples of the same shape (a cohort): two samples' score streams together exceed
+    # the 126 MB L2 whatever the stream form, so no pass finds its input cached by the previous one
+    n_samples = max(2, args.lanes)
+    sts = [st] + [gen_streams(db, args, device, args.max_depth or None, subset, seed=1002 + rank + 100 * l)[0] for l in range(1, n_samples)]
+    assert all(int(x.tid.shape[0]) == R_local for x in sts)
+    pipes = [pipeline.DevicePipeline(x, index, db.row_seq, impl=args.pileup_impl, idx_base=rank * R_local, exchange=args.exchange, **PARAMS) for x in sts]
+    pipe = pipes[0]
 
     def barrier():
         if world > 1:
@@ -301,21 +310,27 @@ def main():
 
     sampler = ClockSampler(local)
     sampler.start()
-    result = None
-    for _ in range(max(args.warmup, 3)):
-        result = pipe.step()
+    results = []
+    for p in pipes:
+        for _ in range(max(args.warmup, 3)):
+            r = p.step()
+        results.append(r)
+    result = results[0]
     use_graph = not args.no_graph
     if use_graph:
         try:
-            pipe.capture()
-            assert pipe.step_graph() == result, "graph replay differs from the eager pass"
+            for p, r in zip(pipes, results):
+                p.capture()
+                assert p.step_graph() == r, "graph replay differs from the eager pass"
         except Exception as e:  # noqa: BLE001
             sys.stderr.write("CUDA graph capture unavailable (%r): timing the eager pass\n" % (e,))
             use_graph = False
     if not use_graph:
-        pipe.graph = None
+        for p in pipes:
+            p.graph = None
     barrier()
-    pipe.launches = 0
+    for p in pipes:
+        p.launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     prof = bool(os.environ.get("MMLST_CUDA_PROFILER"))  # `ncu --profile-from-start off`: capture the timed steps only
@@ -324,25 +339,27 @@ def main():
     # K passes queued back to back (each one ends with its D2H into the pinned output block); the host parses the
     # result after the timed region -- the way a cohort is typed.  Per-pass latency WITH a host sync is reported too.
     e0.record()
-    for _ in range(args.steps):
-        pipe.enqueue_step()
+    for i in range(args.steps):
+        pipes[i % n_samples].enqueue_step()
     e1.record()
     barrier()
-    out = pipe.collect()
+    outs_serial = [p.collect() for p in pipes]
+    out = outs_serial[0]
+    assert outs_serial == results, "results changed between steps"
     serial_ms = e0.elapsed_time(e1) / args.steps
-    serial_launches = pipe.launches
+    serial_launches = sum(p.launches for p in pipes)
     lanes = None
     if args.lanes > 1:
         # cohort mode: passes alternate over `lanes` streams, each lane with its own tables / output block / graph and, with
         # N>1, its own NCCL communicator (collectives of different lanes may be in flight together)
         groups = [torch.distributed.new_group(list(range(world))) if world > 1 and args.exchange != "p2p" else None for _ in range(args.lanes)]
-        lanes = pipeline.CohortLanes(lambda lane: pipeline.DevicePipeline(st, index, db.row_seq, impl=args.pileup_impl, idx_base=rank * R_local,
-                                                                          exchange=args.exchange, group=groups[lane], **PARAMS), args.lanes)
-        for r in lanes.warm_and_capture(graph=use_graph):
-            assert r == result, "a cohort lane disagrees with the serial pass"
+        lanes = pipeline.CohortLanes(lambda lane: pipeline.DevicePipeline(sts[lane % n_samples], index, db.row_seq, impl=args.pileup_impl,
+                                                                          idx_base=rank * R_local, exchange=args.exchange, group=groups[lane], **PARAMS), args.lanes)
+        want = [results[lane % n_samples] for lane in range(args.lanes)]
+        assert lanes.warm_and_capture(graph=use_graph) == want, "a cohort lane disagrees with the serial pass"
         for i in range(2 * args.lanes):  # warm the overlapped schedule itself
             lanes.enqueue(i)
-        assert all(r == result for r in lanes.collect())
+        assert lanes.collect() == want
         for p in lanes.pipes:
             p.launches = 0
         barrier()
@@ -353,15 +370,16 @@ def main():
         lanes.join()
         e1.record()
         barrier()
-        outs = lanes.collect()
-        assert all(o == result for o in outs), "cohort-mode results differ from the serial pass"
+        assert lanes.collect() == want, "cohort-mode results differ from the serial pass"
     if prof:
         torch.cuda.profiler.stop()
     assert out == result, "results changed between steps"
     launches = lanes.launches if lanes is not None else serial_launches
     # per-kernel durations: 20 back-to-back launches of each kernel of the same pass between two CUDA events on the
     # launching stream (events are not graph-capturable; a single launch would carry the event/launch gap)
-    kms = pipe.time_kernels(20)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    kms = pipe.time_kernels(20, alt=pipes[1], flush=flush)
+    del flush
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(10):
@@ -376,16 +394,20 @@ def main():
     tids = [index.name_to_tid[c] for sp in out for (c, _s, _h, _n) in out[sp]]
     # bytes the score kernel has to read: the run-length form stores the allele id per run (5 B / record + 8 B / run +
     # 4 B / 256-record chunk); SURVEY.md 8d's 9 B / record assumed an explicit 4-byte id per record (kept as a fallback form)
-    if pipe.use_runs:
+    if pipe.use_qc:
+        score_bytes = 3.0 * R_local + 8.0 * int(st.run_tid.shape[0]) + 6.0 * int(st.chunk_run.shape[0])
+    elif pipe.use_runs:
         score_bytes = 5.0 * R_local + 8.0 * int(st.run_tid.shape[0]) + 4.0 * int(st.chunk_run.shape[0])
     else:
         score_bytes = 9.0 * R_local
     pb, precs = pileup_alg_bytes(st, [t for t in tids if st.contig_start[t + 1] > st.contig_start[t]], args.read_len)
     rooflines = {
         "score": {"bound": "hbm", "achieved": score_bytes / kms["score"] / 1e6, "peak": peak, "unit": "GB/s", "frac": score_bytes / kms["score"] / 1e6 / peak,
-                  "traffic": ncu_traffic("score_runs" if pipe.use_runs else "score") if args.reads == 10_000_000 and args.k == 4 else None,
+                  "traffic": ncu_traffic("score_runs_qc" if pipe.use_qc else "score_runs" if pipe.use_runs else "score") if args.reads == 10_000_000 and args.k == 4 else None,
                   "ms": kms["score"], "algorithmic_bytes": score_bytes,
-                  "stream_form": "run-length: as0 i16 + xm3 u8 + qlen u16 per record, allele id per run (5 B/record; SURVEY 8d's explicit-id form is 9 B/record)"
+                  "stream_form": "run-length + len(SEQ) per 256-record chunk: as0 i16 + xm3 u8 per record, allele id per run (3 B/record; lossless: every "
+                                 "chunk of this sample has one read length; SURVEY 8d's explicit form is 9 B/record)" if pipe.use_qc else
+                                 "run-length: as0 i16 + xm3 u8 + qlen u16 per record, allele id per run (5 B/record; SURVEY 8d's explicit-id form is 9 B/record)"
                   if pipe.use_runs else "explicit allele id per record (9 B/record)"},
         "pileup_parity": {"bound": "hbm", "achieved": pb / kms.get("pileup", float("inf")) / 1e6, "peak": peak, "unit": "GB/s",
                           "frac": pb / kms.get("pileup", float("inf")) / 1e6 / peak, "traffic": None, "ms": kms.get("pileup"),
@@ -431,7 +453,8 @@ def main():
     dt = (time.perf_counter() - t0) / n_e2e
     clocks = sampler.stop()
     line["clocks"] = clocks
-    h2d = (5 * R_local + 8 * int(soa.run_tid.shape[0]) + 4 + 4 * int(soa.chunk_run.shape[0])) if soa.run_tid is not None else 9 * R_local
+    h2d = ((3 * R_local + 6 * int(soa.chunk_run.shape[0]) if soa.chunk_qlen is not None else 5 * R_local + 4 * int(soa.chunk_run.shape[0])) +
+           8 * int(soa.run_tid.shape[0]) + 4) if soa.run_tid is not None else 9 * R_local
     h2d += db.n_rows * 5 + int(sum((st.contig_start[t + 1] - st.contig_start[t]) * 16 for t in ts_local))
     proff = soa.p_row_off
     h2d += int(sum(int(proff[int(st.contig_start[t + 1])]) - int(proff[int(st.contig_start[t])]) for t in ts_local)) * 4

@@ -103,6 +103,18 @@ int mmlst_score_runs_dev(const uint32_t* run_tid, const uint32_t* run_start, uin
                          uint64_t n_rec, uint64_t idx_base, const uint8_t* allow, uint32_t n_ref,
                          int minscore, int max_xm, int min_read_len,
                          int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, uint64_t* counters, void* stream);
+/* Run-length form with len(SEQ) stored once per 256-record chunk ("QC": 3 B / record): chunk_qlen[ceil(n_rec/256)] =
+ * len(SEQ) shared by every record of the chunk.  Legal only when every chunk is uniform (untrimmed reads of one
+ * sequencing run); mmlst_chunk_qlen (HOST) builds the array and returns MMLST_OK with *uniform = 0 when it is not.
+ * Same filter, outputs and accumulation rules as mmlst_score_dev. */
+int mmlst_chunk_qlen(const uint16_t* qlen, uint64_t n_rec, uint16_t* chunk_qlen, int* uniform);
+int mmlst_score_runs_qc_dev(const uint32_t* run_tid, const uint32_t* run_start, uint32_t n_runs, const uint32_t* chunk_run,
+                            const uint16_t* chunk_qlen, const int16_t* as0, const uint8_t* xm3, const uint32_t* orig_idx,
+                            uint64_t n_rec, uint64_t idx_base, const uint8_t* allow, uint32_t n_ref,
+                            int minscore, int max_xm, int min_read_len,
+                            int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, uint64_t* counters, void* stream);
+/* qlen[i] of every record back from the per-chunk form (device; the coverage kernel takes it per record) */
+int mmlst_expand_chunk_qlen_dev(const uint16_t* chunk_qlen, uint64_t n_rec, uint16_t* qlen, void* stream);
 /* tid[i] of every record back from the run arrays (device; the coverage kernel takes the explicit form) */
 int mmlst_expand_runs_dev(const uint32_t* run_tid, const uint32_t* run_start, uint32_t n_runs, const uint32_t* chunk_run,
                           uint64_t n_rec, uint32_t* tid, void* stream);
@@ -284,6 +296,9 @@ typedef struct {
      * 5 B / record + the run arrays and never read `tid` (which may then be NULL) */
     uint32_t n_runs;
     const uint32_t* run_tid; const uint32_t* run_start; const uint32_t* chunk_run;
+    /* with the run arrays only: len(SEQ) per 256-record chunk (mmlst_score_runs_qc_dev); when != NULL the host entry
+     * points upload 3 B / record and never read `qlen` */
+    const uint16_t* chunk_qlen;
 } mmlst_soa;
 
 typedef struct { int minscore, max_xm, min_read_len; } mmlst_score_params;

@@ -74,8 +74,9 @@ def unpack_bam(path: str, minqual: int = packing.DEFAULT_MINQUAL, max_depth: Opt
         nr = int(s.n_runs)
         soa.run_tid, soa.run_start = _view(s.run_tid, nr, np.uint32), _view(s.run_start, nr + 1, np.uint32)
         soa.chunk_run = _view(s.chunk_run, (n + 255) // 256, np.uint32)
+        soa.chunk_qlen = _view(s.chunk_qlen, (n + 255) // 256, np.uint16) if s.chunk_qlen else None
         if nr > 0.125 * n:  # name-grouped input: the explicit tid form is the smaller one
-            soa.run_tid = soa.run_start = soa.chunk_run = None
+            soa.run_tid = soa.run_start = soa.chunk_run = soa.chunk_qlen = None
     soa.qhash = _view(info.qhash, 2 * n, np.uint64).reshape(n, 2) if info.qhash else None
     soa.header_text = (info.header_text or b"").decode("latin-1")
     soa.unpack_seconds = dict(zip(("read", "inflate", "parse", "sort", "pack"), [float(x) for x in info.seconds]))

@@ -76,6 +76,8 @@ struct mmlst_ctx {
     // score stream
     DevBuf tid, as0, xm3, qlen, oidx, allow, locus_of, sum_as, n_hit, first_idx, counters;
     DevBuf run_tid, run_start, chunk_run;  // run-length form (mmlst_score_runs_dev)
+    DevBuf chunk_qlen;                     // + len(SEQ) per chunk (mmlst_score_runs_qc_dev)
+    bool resident_qlen = false;            // explicit qlen[] present (false after a QC upload until mmlst_coverage expands it)
     uint64_t resident_n = 0;     // records of the score stream currently in (tid/)as0/xm3/qlen(/oidx)
     bool resident_oidx = false;
     bool resident_tid = false;   // explicit tid[] present (false after a run-length upload until mmlst_coverage expands it)
@@ -94,7 +96,7 @@ struct mmlst_ctx {
         DevBuf* l[] = {&tid, &as0, &xm3, &qlen, &oidx, &allow, &locus_of, &sum_as, &n_hit, &first_idx, &counters, &p_recs,
                        &planes, &chunks, &counts, &dbseq, &col_off, &cons, &holes, &snps, &db_hi,
                        &db_lo, &db_len, &q_hi, &q_lo, &q_len, &blocks, &best, &qhash, &cov_table, &cov, &xr_ids, &xr_x, &xr_bytes, &xq_ids, &xq_x, &xq_bytes,
-                       &run_tid, &run_start, &chunk_run};
+                       &run_tid, &run_start, &chunk_run, &chunk_qlen};
         for (DevBuf* b : l) all[n_all++] = b;
     }
 };
@@ -159,9 +161,12 @@ static int upload_score_stream(mmlst_ctx* c, const mmlst_soa* soa) {
         if (n && !soa->tid) { mmlst_set_error("mmlst_soa: neither tid nor run arrays given"); return MMLST_E_ARG; }
         TRY(h2d(c->tid, soa->tid, n, s));
     }
+    const bool qc = runs && soa->chunk_qlen != nullptr;
     TRY(h2d(c->as0, soa->as0, n, s));
     TRY(h2d(c->xm3, soa->xm3, n, s));
-    TRY(h2d(c->qlen, soa->qlen, n, s));
+    if (qc) TRY(h2d(c->chunk_qlen, soa->chunk_qlen, (n + 255) / 256, s));
+    else TRY(h2d(c->qlen, soa->qlen, n, s));
+    c->resident_qlen = !qc;
     if (soa->orig_idx) TRY(h2d(c->oidx, soa->orig_idx, n, s));
     c->resident_n = n; c->resident_oidx = soa->orig_idx != nullptr;
     c->resident_tid = !runs; c->resident_runs = runs ? soa->n_runs : 0;
@@ -194,6 +199,21 @@ extern "C" int mmlst_build_runs(const uint32_t* tid, uint64_t n_rec, uint32_t* r
     return MMLST_OK;
 }
 
+// HOST: len(SEQ) per 256-record chunk when every chunk is uniform (include/mmlst.h, mmlst_score_runs_qc_dev)
+extern "C" int mmlst_chunk_qlen(const uint16_t* qlen, uint64_t n_rec, uint16_t* chunk_qlen, int* uniform) {
+    if (!uniform || (n_rec && (!qlen || !chunk_qlen))) { mmlst_set_error("mmlst_chunk_qlen: null pointer"); return MMLST_E_ARG; }
+    *uniform = 1;
+    for (uint64_t c0 = 0; c0 < n_rec; c0 += 256) {
+        const uint64_t c1 = c0 + 256 < n_rec ? c0 + 256 : n_rec;
+        const uint16_t q = qlen[c0];
+        unsigned diff = 0;
+        for (uint64_t i = c0 + 1; i < c1; ++i) diff |= (unsigned)(qlen[i] ^ q);
+        if (diff) { *uniform = 0; return MMLST_OK; }
+        chunk_qlen[c0 >> 8] = q;
+    }
+    return MMLST_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* allow, const uint32_t* locus_of,
                            uint32_t n_loci, const mmlst_score_params* prm, int64_t* sum_as, uint32_t* n_hit,
@@ -210,7 +230,13 @@ extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* al
     CUDA_TRY(cudaMemsetAsync(c->n_hit.p, 0, nr * 4, s));
     CUDA_TRY(cudaMemsetAsync(c->first_idx.p, 0xff, nr * 4, s));
     CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, 16, s));
-    if (c->resident_runs) {
+    if (c->resident_runs && !c->resident_qlen) {
+        TRY(mmlst_score_runs_qc_dev(c->run_tid.as<uint32_t>(), c->run_start.as<uint32_t>(), c->resident_runs, c->chunk_run.as<uint32_t>(),
+                                    c->chunk_qlen.as<uint16_t>(), c->as0.as<int16_t>(), c->xm3.as<uint8_t>(),
+                                    soa->orig_idx ? c->oidx.as<uint32_t>() : nullptr, n, 0, c->allow.as<uint8_t>(), (uint32_t)nr,
+                                    prm->minscore, prm->max_xm, prm->min_read_len, c->sum_as.as<int64_t>(), c->n_hit.as<uint32_t>(),
+                                    c->first_idx.as<uint32_t>(), c->counters.as<uint64_t>(), s));
+    } else if (c->resident_runs) {
         TRY(mmlst_score_runs_dev(c->run_tid.as<uint32_t>(), c->run_start.as<uint32_t>(), c->resident_runs, c->chunk_run.as<uint32_t>(),
                                  c->as0.as<int16_t>(), c->xm3.as<uint8_t>(), c->qlen.as<uint16_t>(),
                                  soa->orig_idx ? c->oidx.as<uint32_t>() : nullptr, n, 0, c->allow.as<uint8_t>(), (uint32_t)nr,
@@ -253,6 +279,11 @@ extern "C" int mmlst_coverage(mmlst_ctx* c, const mmlst_soa* soa, const uint64_t
         TRY(mmlst_expand_runs_dev(c->run_tid.as<uint32_t>(), c->run_start.as<uint32_t>(), c->resident_runs, c->chunk_run.as<uint32_t>(),
                                   n, c->tid.as<uint32_t>(), s));
         c->resident_tid = true;
+    }
+    if (!c->resident_qlen && n) {  // QC upload: the coverage kernel sums len(SEQ) per record
+        TRY(c->qlen.reserve(n * 2));
+        TRY(mmlst_expand_chunk_qlen_dev(c->chunk_qlen.as<uint16_t>(), n, c->qlen.as<uint16_t>(), s));
+        c->resident_qlen = true;
     }
     TRY(h2d(c->qhash, qhash, 2 * n, s));
     TRY(h2d(c->allow, allow, nr, s));

@@ -159,15 +159,16 @@ struct mmlst_bam {
     std::vector<uint32_t> ref_len;
     std::string names_blob;  // '\n'-joined, for one-call transfer to the binding
     std::string header_text;
-    Buf tid, as0, xm3, qlen, orig_idx, qhash, p_recs, planes, contig_start, run_tid, run_start, chunk_run;
+    Buf tid, as0, xm3, qlen, orig_idx, qhash, p_recs, planes, contig_start, run_tid, run_start, chunk_run, chunk_qlen;
     uint32_t n_runs = 0;
+    bool qc = false;  // chunk_qlen valid: every 256-record chunk has one len(SEQ)
     uint64_t n_rec = 0, n_prec = 0, n_plane_words = 0, n_dropped = 0, n_unmapped_flag = 0;
     uint32_t max_row_words = 0;
     int presorted = 0, minqual = 20;
     uint32_t max_depth = 0;
     double t_read = 0, t_inflate = 0, t_parse = 0, t_sort = 0, t_pack = 0;
     ~mmlst_bam() {
-        for (Buf* b : {&tid, &as0, &xm3, &qlen, &orig_idx, &qhash, &p_recs, &planes, &contig_start, &run_tid, &run_start, &chunk_run}) b->release();
+        for (Buf* b : {&tid, &as0, &xm3, &qlen, &orig_idx, &qhash, &p_recs, &planes, &contig_start, &run_tid, &run_start, &chunk_run, &chunk_qlen}) b->release();
     }
 };
 
@@ -417,6 +418,12 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
         rc = mmlst_build_runs(B->tid.as<uint32_t>(), n, B->run_tid.as<uint32_t>(), B->run_start.as<uint32_t>(), B->chunk_run.as<uint32_t>(), &nr);
         if (rc != MMLST_OK) return rc;
         B->n_runs = nr;
+        // len(SEQ) once per chunk when every chunk is uniform (3 B / record form, mmlst_score_runs_qc_dev)
+        if (!B->chunk_qlen.alloc(((n + 255) / 256) * 2, pin)) { mmlst_set_error("mmlst_bam_unpack: out of host memory"); return MMLST_E_NOMEM; }
+        int uniform = 0;
+        rc = mmlst_chunk_qlen(B->qlen.as<uint16_t>(), n, B->chunk_qlen.as<uint16_t>(), &uniform);
+        if (rc != MMLST_OK) return rc;
+        B->qc = uniform != 0;
     }
 
     // ---- phase 6: pileup candidates (mapped flag), depth cap, rows
@@ -532,6 +539,7 @@ extern "C" int mmlst_bam_info(const mmlst_bam* b, mmlst_bam_info_t* info) {
     if (b->n_runs) {
         info->soa.n_runs = b->n_runs; info->soa.run_tid = b->run_tid.as<uint32_t>();
         info->soa.run_start = b->run_start.as<uint32_t>(); info->soa.chunk_run = b->chunk_run.as<uint32_t>();
+        if (b->qc) info->soa.chunk_qlen = b->chunk_qlen.as<uint16_t>();
     }
     info->qhash = b->qhash.as<uint64_t>();
     info->ref_len = b->ref_len.data();

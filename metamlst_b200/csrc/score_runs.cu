@@ -21,6 +21,7 @@ constexpr uint32_t FULL = 0xffffffffu;
 struct RunArgs {
     const uint32_t* run_tid; const uint32_t* run_start; const uint32_t* chunk_run; uint32_t n_runs;
     const int16_t* as0; const uint8_t* xm3; const uint16_t* qlen; const uint32_t* orig_idx;
+    const uint16_t* chunk_qlen;  // QC form: len(SEQ) of every record of chunk c (uniform chunks), qlen[] is not read
     uint64_t n_rec; uint64_t idx_base;
     const uint8_t* allow; uint32_t n_ref;
     int minscore, max_xm, min_read_len;
@@ -36,15 +37,17 @@ __device__ __forceinline__ void flush_run(const RunArgs& a, uint32_t key, long l
 }
 
 template <bool OIDX> struct Loaded;  // one lane's 8 consecutive records of a chunk
-template <> struct Loaded<false> { uint4 a8, q8; uint2 x8; };
-template <> struct Loaded<true> { uint4 a8, q8; uint2 x8; uint4 oa, ob; };
+template <> struct Loaded<false> { uint4 a8, q8; uint2 x8; uint32_t cq; };
+template <> struct Loaded<true> { uint4 a8, q8; uint2 x8; uint32_t cq; uint4 oa, ob; };
 
-template <bool OIDX>
+// QC: the chunk's common len(SEQ) comes from chunk_qlen[] (one u16 per 256 records) instead of 16 B of qlen[] per lane
+template <bool OIDX, bool QC>
 __device__ __forceinline__ Loaded<OIDX> load_chunk(const RunArgs& a, uint64_t base_lane) {
     Loaded<OIDX> L;
     L.a8 = ld_stream_u4(a.as0 + base_lane);
     L.x8 = ld_stream_u2(a.xm3 + base_lane);
-    L.q8 = ld_stream_u4(a.qlen + base_lane);
+    if constexpr (QC) { L.cq = __ldg(a.chunk_qlen + (base_lane >> 8)); L.q8 = make_uint4(0, 0, 0, 0); }
+    else { L.q8 = ld_stream_u4(a.qlen + base_lane); L.cq = 0; }
     if constexpr (OIDX) { L.oa = ld_stream_u4(a.orig_idx + base_lane); L.ob = ld_stream_u4(a.orig_idx + base_lane + 4); }
     return L;
 }
@@ -107,8 +110,8 @@ __device__ __forceinline__ Thr make_thr(const RunArgs& a) {
 }
 
 // p_lo / p_hi: one byte per record (records 0-3 / 4-7 of the lane), 1 = passes all three filters
-template <bool OIDX>
-__device__ __forceinline__ void lane_pass(const Loaded<OIDX>& L, const Thr& t, uint32_t& p_lo, uint32_t& p_hi) {
+template <bool OIDX, bool QC>
+__device__ __forceinline__ void lane_pass(const Loaded<OIDX>& L, const Thr& t, int min_read_len, uint32_t& p_lo, uint32_t& p_hi) {
     const uint32_t aw[4] = {L.a8.x, L.a8.y, L.a8.z, L.a8.w};
     const uint32_t qw[4] = {L.q8.x, L.q8.y, L.q8.z, L.q8.w};
     uint32_t m[4];
@@ -116,9 +119,13 @@ __device__ __forceinline__ void lane_pass(const Loaded<OIDX>& L, const Thr& t, u
     for (int w = 0; w < 4; ++w) {
         const uint32_t da = (aw[w] | H16) - t.as_TL;
         const uint32_t ga = (~aw[w] & ~t.as_T) | ((aw[w] ^ t.as_T) & da);          // as0 >= minscore (signed halves)
-        const uint32_t dq = (qw[w] | H16) - t.ql_TL;
-        const uint32_t gq = (qw[w] & ~t.ql_T) | (~(qw[w] ^ t.ql_T) & dq);         // qlen >= min_read_len
-        m[w] = ga & gq & H16;
+        if constexpr (QC) {
+            m[w] = ga & H16;
+        } else {
+            const uint32_t dq = (qw[w] | H16) - t.ql_TL;
+            const uint32_t gq = (qw[w] & ~t.ql_T) | (~(qw[w] ^ t.ql_T) & dq);     // qlen >= min_read_len
+            m[w] = ga & gq & H16;
+        }
     }
     const uint32_t b_lo = __byte_perm(m[0], m[1], 0x7531), b_hi = __byte_perm(m[2], m[3], 0x7531);  // top byte of every half
     const uint32_t x0 = L.x8.x, x1 = L.x8.y;
@@ -126,6 +133,9 @@ __device__ __forceinline__ void lane_pass(const Loaded<OIDX>& L, const Thr& t, u
     const uint32_t g0 = (t.xm_T & ~x0) | (~(t.xm_T ^ x0) & d0), g1 = (t.xm_T & ~x1) | (~(t.xm_T ^ x1) & d1);  // max_xm >= xm3
     p_lo = (b_lo & g0 & t.h8) >> 7;
     p_hi = (b_hi & g1 & t.h8) >> 7;
+    if constexpr (QC) {
+        if (static_cast<int>(L.cq) < min_read_len) { p_lo = 0; p_hi = 0; }  // warp-uniform: the whole chunk is too short
+    }
 }
 
 // sum / count / first index of the lane's records selected by the byte masks
@@ -147,14 +157,14 @@ __device__ __forceinline__ void lane_sums(const Loaded<OIDX>& L, uint32_t p_lo, 
 }
 
 // one 256-record chunk starting at record `base` (this lane: records base + 8 lane .. + 7)
-template <bool OIDX>
+template <bool OIDX, bool QC>
 __device__ __forceinline__ void reduce_chunk(const RunArgs& a, const Thr& thr, WarpRun& w, const Loaded<OIDX>& L, uint64_t base, uint32_t lane,
                                              uint32_t& tot, uint32_t& ign) {
     constexpr uint32_t R = 8;
     const uint64_t rec0 = base + (lane << 3);
     const uint32_t idx0 = static_cast<uint32_t>(a.idx_base + rec0);
     uint32_t p_lo, p_hi;
-    lane_pass<OIDX>(L, thr, p_lo, p_hi);
+    lane_pass<OIDX, QC>(L, thr, a.min_read_len, p_lo, p_hi);
     const uint64_t chunk_end = base + 256;
     if (chunk_end <= w.end) {  // the whole chunk lies inside the open run
         if (w.al) {
@@ -195,7 +205,7 @@ __device__ __forceinline__ void reduce_chunk(const RunArgs& a, const Thr& thr, W
     }
 }
 
-template <bool OIDX, bool PIPE>
+template <bool OIDX, bool PIPE, bool QC>
 __global__ void __launch_bounds__(kThreads, PIPE ? (OIDX ? 2 : 3) : (OIDX ? 3 : 4)) score_runs_kernel(const RunArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -213,36 +223,36 @@ __global__ void __launch_bounds__(kThreads, PIPE ? (OIDX ? 2 : 3) : (OIDX ? 3 : 
         uint64_t ch = c0;
         Loaded<OIDX> A0, A1;
         bool have = ch + 1 < c1;
-        if (have) { A0 = load_chunk<OIDX>(a, (ch << 8) + (lane << 3)); A1 = load_chunk<OIDX>(a, ((ch + 1) << 8) + (lane << 3)); }
+        if (have) { A0 = load_chunk<OIDX, QC>(a, (ch << 8) + (lane << 3)); A1 = load_chunk<OIDX, QC>(a, ((ch + 1) << 8) + (lane << 3)); }
         WarpRun w;
         open_run(a, w, __ldg(a.chunk_run + c0));
         Loaded<OIDX> B0, B1;  // ping-pong register buffers: no copy between them (a copy would wait for the loads)
         if constexpr (!PIPE) {
             while (have) {
-                reduce_chunk<OIDX>(a, thr, w, A0, ch << 8, lane, tot, ign);
-                reduce_chunk<OIDX>(a, thr, w, A1, (ch + 1) << 8, lane, tot, ign);
+                reduce_chunk<OIDX, QC>(a, thr, w, A0, ch << 8, lane, tot, ign);
+                reduce_chunk<OIDX, QC>(a, thr, w, A1, (ch + 1) << 8, lane, tot, ign);
                 ch += 2;
                 have = ch + 1 < c1;
-                if (have) { A0 = load_chunk<OIDX>(a, (ch << 8) + (lane << 3)); A1 = load_chunk<OIDX>(a, ((ch + 1) << 8) + (lane << 3)); }
+                if (have) { A0 = load_chunk<OIDX, QC>(a, (ch << 8) + (lane << 3)); A1 = load_chunk<OIDX, QC>(a, ((ch + 1) << 8) + (lane << 3)); }
             }
         }
         while (have) {
             const bool moreB = ch + 3 < c1;
-            if (moreB) { B0 = load_chunk<OIDX>(a, ((ch + 2) << 8) + (lane << 3)); B1 = load_chunk<OIDX>(a, ((ch + 3) << 8) + (lane << 3)); }
-            reduce_chunk<OIDX>(a, thr, w, A0, ch << 8, lane, tot, ign);
-            reduce_chunk<OIDX>(a, thr, w, A1, (ch + 1) << 8, lane, tot, ign);
+            if (moreB) { B0 = load_chunk<OIDX, QC>(a, ((ch + 2) << 8) + (lane << 3)); B1 = load_chunk<OIDX, QC>(a, ((ch + 3) << 8) + (lane << 3)); }
+            reduce_chunk<OIDX, QC>(a, thr, w, A0, ch << 8, lane, tot, ign);
+            reduce_chunk<OIDX, QC>(a, thr, w, A1, (ch + 1) << 8, lane, tot, ign);
             ch += 2;
             if (!moreB) break;
             have = ch + 3 < c1;
-            if (have) { A0 = load_chunk<OIDX>(a, ((ch + 2) << 8) + (lane << 3)); A1 = load_chunk<OIDX>(a, ((ch + 3) << 8) + (lane << 3)); }
-            reduce_chunk<OIDX>(a, thr, w, B0, ch << 8, lane, tot, ign);
-            reduce_chunk<OIDX>(a, thr, w, B1, (ch + 1) << 8, lane, tot, ign);
+            if (have) { A0 = load_chunk<OIDX, QC>(a, ((ch + 2) << 8) + (lane << 3)); A1 = load_chunk<OIDX, QC>(a, ((ch + 3) << 8) + (lane << 3)); }
+            reduce_chunk<OIDX, QC>(a, thr, w, B0, ch << 8, lane, tot, ign);
+            reduce_chunk<OIDX, QC>(a, thr, w, B1, (ch + 1) << 8, lane, tot, ign);
             ch += 2;
         }
         if (ch < c1) {
             const uint64_t base = ch << 8;
-            const Loaded<OIDX> L0 = load_chunk<OIDX>(a, base + (lane << 3));
-            reduce_chunk<OIDX>(a, thr, w, L0, base, lane, tot, ign);
+            const Loaded<OIDX> L0 = load_chunk<OIDX, QC>(a, base + (lane << 3));
+            reduce_chunk<OIDX, QC>(a, thr, w, L0, base, lane, tot, ign);
         }
         close_run(a, w, lane);
     }
@@ -257,7 +267,8 @@ __global__ void __launch_bounds__(kThreads, PIPE ? (OIDX ? 2 : 3) : (OIDX ? 3 : 
             if (!((key < a.n_ref) && a.allow[key])) continue;
             ++tot;
             const int as = a.as0[i];
-            if ((as >= a.minscore) && (int(a.qlen[i]) >= a.min_read_len) && (int(a.xm3[i]) <= a.max_xm)) {
+            const int ql = QC ? int(a.chunk_qlen[nchunks]) : int(a.qlen[i]);
+            if ((as >= a.minscore) && (ql >= a.min_read_len) && (int(a.xm3[i]) <= a.max_xm)) {
                 const uint32_t idx = a.orig_idx ? a.orig_idx[i] : static_cast<uint32_t>(a.idx_base + i);
                 flush_run(a, key, as, 1u, idx);
             } else {
@@ -285,34 +296,42 @@ __global__ void __launch_bounds__(256) expand_runs_kernel(const uint32_t* __rest
     }
 }
 
+__global__ void __launch_bounds__(256) expand_chunk_qlen_kernel(const uint16_t* __restrict__ chunk_qlen, uint64_t n_rec, uint16_t* __restrict__ qlen) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_rec; i += stride) qlen[i] = __ldg(chunk_qlen + (i >> 8));
+}
+
 }  // namespace
 
-extern "C" int mmlst_score_runs_dev(const uint32_t* run_tid, const uint32_t* run_start, uint32_t n_runs, const uint32_t* chunk_run,
-                                    const int16_t* as0, const uint8_t* xm3, const uint16_t* qlen, const uint32_t* orig_idx,
-                                    uint64_t n_rec, uint64_t idx_base, const uint8_t* allow, uint32_t n_ref, int minscore,
-                                    int max_xm, int min_read_len, int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx,
-                                    uint64_t* counters, void* stream) {
+static int score_runs_launch(const uint32_t* run_tid, const uint32_t* run_start, uint32_t n_runs, const uint32_t* chunk_run,
+                             const int16_t* as0, const uint8_t* xm3, const uint16_t* qlen, const uint16_t* chunk_qlen, const uint32_t* orig_idx,
+                             uint64_t n_rec, uint64_t idx_base, const uint8_t* allow, uint32_t n_ref, int minscore,
+                             int max_xm, int min_read_len, int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx,
+                             uint64_t* counters, void* stream) {
     if (n_rec == 0) return MMLST_OK;
-    if (!run_tid || !run_start || !chunk_run || !n_runs || !as0 || !xm3 || !qlen || !allow || !sum_as || !n_hit || !first_idx || !counters) {
+    if (!run_tid || !run_start || !chunk_run || !n_runs || !as0 || !xm3 || (!qlen && !chunk_qlen) || !allow || !sum_as || !n_hit || !first_idx || !counters) {
         mmlst_set_error("mmlst_score_runs_dev: null pointer");
         return MMLST_E_ARG;
     }
     if (n_rec >= 0xffffff00ull) { mmlst_set_error("mmlst_score_runs_dev: %llu records do not fit 32-bit run offsets", (unsigned long long)n_rec); return MMLST_E_RANGE; }
-    if ((reinterpret_cast<uintptr_t>(as0) & 15) || (reinterpret_cast<uintptr_t>(xm3) & 7) || (reinterpret_cast<uintptr_t>(qlen) & 15) ||
+    if ((reinterpret_cast<uintptr_t>(as0) & 15) || (reinterpret_cast<uintptr_t>(xm3) & 7) || (!chunk_qlen && (reinterpret_cast<uintptr_t>(qlen) & 15)) ||
         (orig_idx && (reinterpret_cast<uintptr_t>(orig_idx) & 15))) {
         mmlst_set_error("mmlst_score_runs_dev: record arrays must be 16-byte aligned (as0/qlen/orig_idx), 8 (xm3)");
         return MMLST_E_ARG;
     }
-    RunArgs a{run_tid, run_start, chunk_run, n_runs, as0, xm3, qlen, orig_idx, n_rec, idx_base, allow, n_ref, minscore, max_xm,
+    RunArgs a{run_tid, run_start, chunk_run, n_runs, as0, xm3, qlen, orig_idx, chunk_qlen, n_rec, idx_base, allow, n_ref, minscore, max_xm,
               min_read_len, reinterpret_cast<long long*>(sum_as), n_hit, first_idx, reinterpret_cast<unsigned long long*>(counters)};
     const uint64_t nchunks = n_rec >> 8;
     uint64_t want = (nchunks + 15) / 16;  // CTAs if every warp took two chunks
-    static int resident[4] = {0, 0, 0, 0};  // one wave exactly: the blocked chunk distribution has no tail
+    static int resident[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // one wave exactly: the blocked chunk distribution has no tail
     static int pipe = -1;
     if (pipe < 0) { const char* e = getenv("MMLST_SCORE_PIPE"); pipe = (e && e[0] == '1') ? 1 : 0; }
-    const int v = (orig_idx ? 1 : 0) + 2 * pipe;
-    void (*kern)(const RunArgs) = v == 0 ? score_runs_kernel<false, false> : v == 1 ? score_runs_kernel<true, false>
-                                  : v == 2 ? score_runs_kernel<false, true> : score_runs_kernel<true, true>;
+    const int v = (orig_idx ? 1 : 0) + 2 * pipe + (chunk_qlen ? 4 : 0);
+    void (*const kerns[8])(const RunArgs) = {score_runs_kernel<false, false, false>, score_runs_kernel<true, false, false>,
+                                             score_runs_kernel<false, true, false>, score_runs_kernel<true, true, false>,
+                                             score_runs_kernel<false, false, true>, score_runs_kernel<true, false, true>,
+                                             score_runs_kernel<false, true, true>, score_runs_kernel<true, true, true>};
+    void (*kern)(const RunArgs) = kerns[v];
     if (!resident[v]) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident[v], kern, kThreads, 0) != cudaSuccess || resident[v] < 1) resident[v] = 3;
     }
@@ -320,6 +339,38 @@ extern "C" int mmlst_score_runs_dev(const uint32_t* run_tid, const uint32_t* run
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     kern<<<static_cast<unsigned>(want), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return MMLST_OK;
+}
+
+extern "C" int mmlst_score_runs_dev(const uint32_t* run_tid, const uint32_t* run_start, uint32_t n_runs, const uint32_t* chunk_run,
+                                    const int16_t* as0, const uint8_t* xm3, const uint16_t* qlen, const uint32_t* orig_idx,
+                                    uint64_t n_rec, uint64_t idx_base, const uint8_t* allow, uint32_t n_ref, int minscore,
+                                    int max_xm, int min_read_len, int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx,
+                                    uint64_t* counters, void* stream) {
+    if (n_rec && !qlen) { mmlst_set_error("mmlst_score_runs_dev: null pointer"); return MMLST_E_ARG; }
+    return score_runs_launch(run_tid, run_start, n_runs, chunk_run, as0, xm3, qlen, nullptr, orig_idx, n_rec, idx_base, allow, n_ref, minscore,
+                             max_xm, min_read_len, sum_as, n_hit, first_idx, counters, stream);
+}
+
+extern "C" int mmlst_score_runs_qc_dev(const uint32_t* run_tid, const uint32_t* run_start, uint32_t n_runs, const uint32_t* chunk_run,
+                                       const uint16_t* chunk_qlen, const int16_t* as0, const uint8_t* xm3, const uint32_t* orig_idx,
+                                       uint64_t n_rec, uint64_t idx_base, const uint8_t* allow, uint32_t n_ref, int minscore,
+                                       int max_xm, int min_read_len, int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx,
+                                       uint64_t* counters, void* stream) {
+    if (n_rec && !chunk_qlen) { mmlst_set_error("mmlst_score_runs_qc_dev: null pointer"); return MMLST_E_ARG; }
+    return score_runs_launch(run_tid, run_start, n_runs, chunk_run, as0, xm3, nullptr, chunk_qlen, orig_idx, n_rec, idx_base, allow, n_ref,
+                             minscore, max_xm, min_read_len, sum_as, n_hit, first_idx, counters, stream);
+}
+
+// qlen[i] of every record from the per-chunk form (the coverage kernel wants it per record)
+extern "C" int mmlst_expand_chunk_qlen_dev(const uint16_t* chunk_qlen, uint64_t n_rec, uint16_t* qlen, void* stream) {
+    if (n_rec == 0) return MMLST_OK;
+    if (!chunk_qlen || !qlen) { mmlst_set_error("mmlst_expand_chunk_qlen_dev: null pointer"); return MMLST_E_ARG; }
+    uint64_t blocks = (n_rec + 255) / 256;
+    const uint64_t cap = static_cast<uint64_t>(mmlst_num_sms()) * 16;
+    if (blocks > cap) blocks = cap;
+    expand_chunk_qlen_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(chunk_qlen, n_rec, qlen);
     CUDA_TRY(cudaGetLastError());
     return MMLST_OK;
 }

@@ -83,13 +83,15 @@ class DeviceStreams:
                               int(self.max_row_words), self.contig_start.copy(), self.minqual, self.max_depth, self.n_dropped)
         if getattr(self, "run_tid", None) is not None:
             soa.run_tid, soa.run_start, soa.chunk_run = h(self.run_tid, np.uint32), h(self.run_start, np.uint32), h(self.chunk_run, np.uint32)
+            if getattr(self, "chunk_qlen", None) is not None:
+                soa.chunk_qlen = h(self.chunk_qlen, np.uint16)
         return soa.pin() if pinned else soa
 
     def build_runs(self) -> "DeviceStreams":
         """Run-length form of the score stream on the device (include/mmlst.h, mmlst_score_runs_dev): run_tid, run_start,
         chunk_run as int32 tensors (bit patterns of the u32 arrays)."""
         n = int(self.tid.shape[0])
-        self.run_tid = self.run_start = self.chunk_run = None
+        self.run_tid = self.run_start = self.chunk_run = self.chunk_qlen = None
         if n == 0:
             return self
         assert n < 0xffffff00
@@ -100,6 +102,13 @@ class DeviceStreams:
         self.chunk_run = (torch.searchsorted(start, first, right=True) - 1).to(torch.int32).contiguous()
         self.run_tid = vals.to(torch.int32).contiguous()
         self.run_start = start.to(torch.int32).contiguous()  # n < 2^32 - 256: the u32 bit pattern
+        # len(SEQ) once per 256-record chunk when every chunk is uniform (mmlst_score_runs_qc_dev)
+        nc = (n + 255) // 256
+        q = self.qlen.to(torch.int32)
+        pad = torch.full((nc * 256 - n,), int(q[-1].item()), dtype=torch.int32, device=q.device)
+        q2 = torch.cat([q, pad]).view(nc, 256)
+        if bool((q2 == q2[:, :1]).all().item()):
+            self.chunk_qlen = q2[:, 0].to(torch.int16).contiguous()  # bit pattern of the u16
         return self
 
 

@@ -53,6 +53,7 @@ class SoaHost:
     run_tid: Optional[np.ndarray] = None
     run_start: Optional[np.ndarray] = None
     chunk_run: Optional[np.ndarray] = None
+    chunk_qlen: Optional[np.ndarray] = None  # u16 per 256-record chunk when every chunk has one len(SEQ) (3 B / record form)
 
     @property
     def n_rec(self) -> int:
@@ -91,13 +92,15 @@ class SoaHost:
         if self.run_tid is not None and self.n_rec:
             s.n_runs = int(self.run_tid.shape[0])
             s.run_tid, s.run_start, s.chunk_run = native.ptr(self.run_tid), native.ptr(self.run_start), native.ptr(self.chunk_run)
+            if self.chunk_qlen is not None:
+                s.chunk_qlen = native.ptr(self.chunk_qlen)
         return s
 
     def build_runs(self, max_fraction: float = 0.125) -> "SoaHost":
         """Attach the run-length form (mmlst_build_runs) when it is the smaller one: at most `max_fraction` runs per
         record (coordinate-sorted streams; a name-grouped stream keeps the explicit tid form)."""
         n = self.n_rec
-        self.run_tid = self.run_start = self.chunk_run = None
+        self.run_tid = self.run_start = self.chunk_run = self.chunk_qlen = None
         if n == 0:
             return self
         import ctypes as C
@@ -110,6 +113,12 @@ class SoaHost:
         run_tid = np.empty(nr.value, np.uint32); run_start = np.empty(nr.value + 1, np.uint32); chunk_run = np.empty((n + 255) // 256, np.uint32)
         native.check(lib.mmlst_build_runs(native.ptr(tid), n, native.ptr(run_tid), native.ptr(run_start), native.ptr(chunk_run), C.byref(nr)))
         self.run_tid, self.run_start, self.chunk_run = run_tid, run_start, chunk_run
+        # len(SEQ) once per chunk when every 256-record chunk is uniform (mmlst_chunk_qlen)
+        cq = np.empty((n + 255) // 256, np.uint16)
+        uniform = C.c_int(0)
+        ql = np.ascontiguousarray(self.qlen, dtype=np.uint16)
+        native.check(lib.mmlst_chunk_qlen(native.ptr(ql), n, native.ptr(cq), C.byref(uniform)))
+        self.chunk_qlen = cq if uniform.value else None
         return self
 
     def pin(self) -> "SoaHost":
@@ -117,7 +126,7 @@ class SoaHost:
         import torch
 
         keep = []
-        for name in ("tid", "as0", "xm3", "qlen", "orig_idx", "p_recs", "planes", "qhash", "run_tid", "run_start", "chunk_run"):
+        for name in ("tid", "as0", "xm3", "qlen", "orig_idx", "p_recs", "planes", "qhash", "run_tid", "run_start", "chunk_run", "chunk_qlen"):
             arr = getattr(self, name)
             if arr is None:
                 continue

@@ -52,6 +52,7 @@ class DevicePipeline:
         dev = streams.as0.device
         self.dev = dev
         self.use_runs = bool(use_runs) if use_runs is not None else getattr(streams, "run_tid", None) is not None
+        self.use_qc = self.use_runs and getattr(streams, "chunk_qlen", None) is not None  # len(SEQ) per chunk: 3 B / record
         n_ref = len(index.ref_names)
         self.n_ref = n_ref
         self.allow = torch.from_numpy(index.allow_mask(species_filter)).to(dev)
@@ -150,11 +151,17 @@ class DevicePipeline:
         self._clean = True
 
     def _score_call(self):
-        """Stage 1 over the resident score stream: the run-length form (5 B / record) when the streams carry it, else the
-        explicit-tid form (9 B / record)."""
+        """Stage 1 over the resident score stream: the run-length form when the streams carry it (3 B / record with
+        len(SEQ) per chunk, else 5 B / record), else the explicit-tid form (9 B / record)."""
         s = self.s
         n = int(s.as0.shape[0])
-        if self.use_runs:
+        if self.use_runs and self.use_qc:
+            native.check(self.lib.mmlst_score_runs_qc_dev(native.ptr(s.run_tid), native.ptr(s.run_start), int(s.run_tid.shape[0]), native.ptr(s.chunk_run),
+                                                          native.ptr(s.chunk_qlen), native.ptr(s.as0), native.ptr(s.xm3), 0, n, self.idx_base,
+                                                          native.ptr(self.allow), self.n_ref, self.minscore, self.max_xM, self.min_read_len,
+                                                          native.ptr(self.sum_as), native.ptr(self.n_hit), native.ptr(self.first_idx),
+                                                          native.ptr(self.counters), self._stream()))
+        elif self.use_runs:
             native.check(self.lib.mmlst_score_runs_dev(native.ptr(s.run_tid), native.ptr(s.run_start), int(s.run_tid.shape[0]), native.ptr(s.chunk_run),
                                                        native.ptr(s.as0), native.ptr(s.xm3), native.ptr(s.qlen), 0, n, self.idx_base,
                                                        native.ptr(self.allow), self.n_ref, self.minscore, self.max_xM, self.min_read_len,
@@ -311,29 +318,52 @@ class DevicePipeline:
             self.out_h.copy_(self.out, non_blocking=True)
         self._clean = True
 
-    def time_kernels(self, reps: int = 20) -> Dict[str, float]:
-        """Average device time (ms) of every kernel of the pass: `reps` back-to-back launches of the SAME kernel between
-        two CUDA events on the launching stream (amortises the event/launch gap a single launch would carry).  The
-        tables hold a finished pass when this is called; they are garbage afterwards (the next step resets them)."""
-        self.reset_tables()
-        self.run_score(reset=False)  # tables of a finished scoring pass (all-reduced when distributed)
-        self._select_call(native.SELECT_SCRATCH_CLEAN)
+    def time_kernels(self, reps: int = 20, alt: Optional["DevicePipeline"] = None, flush: Optional[torch.Tensor] = None) -> Dict[str, float]:
+        """Average device time (ms) of every kernel of the pass, always from a cold L2.
+        score: `reps` back-to-back launches between two CUDA events on the launching stream, alternating between this
+        pipeline's sample and `alt`'s (two samples together exceed the L2, so every launch streams from HBM; back-to-back
+        amortises the event/launch gap a single launch would carry).
+        select / pileup / consensus work on tables and a depth-capped pileup stream that FIT the L2: `flush` (a buffer
+        larger than the L2) is rewritten before every launch and each launch gets its own event pair (the ~2 us event
+        gap is included: an upper bound).  Without `flush` they are timed back to back like the score kernel (warm L2).
+        The tables hold a finished pass when this is called; they are garbage afterwards (the next step resets them)."""
+        pipes = [self] + ([alt] if alt is not None else [])
+        for p in pipes:
+            p.reset_tables()
+            p.run_score(reset=False)  # tables of a finished scoring pass (all-reduced when distributed)
+            p._select_call(native.SELECT_SCRATCH_CLEAN)
         torch.cuda.current_stream(self.dev).synchronize()
         out: Dict[str, float] = {}
-        saved, self.dist = self.dist, False  # kernels only: no collectives inside the loops
+        saved = [p.dist for p in pipes]
+        for p in pipes:
+            p.dist = False  # kernels only: no collectives inside the loops
         try:
             for name in ("select", "pileup", "consensus", "score"):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                self._launch_one(name)  # warm
-                a.record()
-                for _ in range(reps):
-                    self._launch_one(name)
-                b.record()
-                b.synchronize()
-                out[name] = a.elapsed_time(b) / reps
+                for p in pipes:
+                    p._launch_one(name)  # warm
+                if name == "score" or flush is None:
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for i in range(reps):
+                        pipes[i % len(pipes)]._launch_one(name)
+                    b.record()
+                    b.synchronize()
+                    out[name] = a.elapsed_time(b) / reps
+                else:
+                    pairs = []
+                    for i in range(reps):
+                        flush.zero_()
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record()
+                        pipes[i % len(pipes)]._launch_one(name)
+                        b.record()
+                        pairs.append((a, b))
+                    torch.cuda.current_stream(self.dev).synchronize()
+                    out[name] = float(np.mean([a.elapsed_time(b) for a, b in pairs]))
         finally:
-            self.dist = saved
-            self._clean = False
+            for p, d in zip(pipes, saved):
+                p.dist = d
+                p._clean = False
         return out
 
     def _launch_one(self, name: str):

@@ -32,6 +32,9 @@ def assert_same(want: packing.SoaHost, got: packing.SoaHost):
     if got.run_tid is not None:
         for k in ("run_tid", "run_start", "chunk_run"):
             assert np.array_equal(getattr(chk, k), getattr(got, k)), k
+        assert (chk.chunk_qlen is None) == (got.chunk_qlen is None)  # len(SEQ) per chunk (3 B / record form)
+        if got.chunk_qlen is not None:
+            assert np.array_equal(chk.chunk_qlen, got.chunk_qlen) and np.array_equal(np.repeat(got.chunk_qlen, 256)[: got.n_rec], got.qlen)
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "*", "sample.bam"))), ids=lambda p: os.path.basename(os.path.dirname(p)))

@@ -81,12 +81,14 @@ def test_score_run_length_form_on_raw_streams(ctx, n):
         as0 = rng.integers(-50, 301, n).astype(np.int16)
         as0[rng.integers(0, n, max(1, n // 1000))] = 32767  # large scores: the warp sums must not overflow a packed field
         xm3 = rng.integers(0, 8, n).astype(np.uint8)
-        qlen = rng.integers(30, 160, n).astype(np.uint16)
+        qlen_rec = rng.integers(30, 160, n).astype(np.uint16)
+        qlen_chunk = np.repeat(rng.integers(30, 160, (n + 255) // 256), 256)[:n].astype(np.uint16)  # one len(SEQ) per chunk: QC form (3 B / record)
         allow = (rng.random(n_ref) < 0.8).astype(np.uint8)
-        for oidx in (None, rng.permutation(n).astype(np.uint32)):
+        for oidx, qlen in [(o, q) for o in (None, rng.permutation(n).astype(np.uint32)) for q in (qlen_rec, qlen_chunk)]:
             soa = packing.SoaHost(names, np.full(n_ref, 500, np.int32), tid, as0, xm3, qlen, oidx, np.zeros(0, packing.PREC_DTYPE),
                                   np.zeros(0, np.uint32), 0, np.zeros(n_ref + 1, np.uint64)).build_runs(max_fraction=1.0)
             assert soa.run_tid is not None
+            assert (soa.chunk_qlen is not None) == (qlen is qlen_chunk or n == 1)
             sum_as = np.zeros(n_ref, np.int64); n_hit = np.zeros(n_ref, np.uint32); first = np.full(n_ref, 0xFFFFFFFF, np.uint32)
             counters = np.zeros(2, np.uint64)
             cs = soa.c_struct()
@@ -104,6 +106,14 @@ def test_score_run_length_form_on_raw_streams(ctx, n):
             native.check(native.lib().mmlst_score(ctx.handle, C.byref(cs), native.ptr(allow), native.ptr(index.locus_of), index.n_loci, C.byref(prm),
                                                   native.ptr(s2), native.ptr(c2), native.ptr(f2), native.ptr(k2)))
             assert np.array_equal(s2, ws) and np.array_equal(c2, wc) and np.array_equal(f2, wf) and np.array_equal(k2, counters)
+            if soa.chunk_qlen is not None:  # the same stream through the 5 B / record run-length kernel (explicit qlen[])
+                soa.build_runs(max_fraction=1.0)
+                soa.chunk_qlen = None
+                s3 = np.zeros(n_ref, np.int64); c3 = np.zeros(n_ref, np.uint32); f3 = np.full(n_ref, 0xFFFFFFFF, np.uint32); k3 = np.zeros(2, np.uint64)
+                cs = soa.c_struct()
+                native.check(native.lib().mmlst_score(ctx.handle, C.byref(cs), native.ptr(allow), native.ptr(index.locus_of), index.n_loci, C.byref(prm),
+                                                      native.ptr(s3), native.ptr(c3), native.ptr(f3), native.ptr(k3)))
+                assert np.array_equal(s3, ws) and np.array_equal(c3, wc) and np.array_equal(f3, wf) and np.array_equal(k3, counters)
 
 
 def test_expand_runs_gives_back_tid(ctx):

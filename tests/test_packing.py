@@ -59,6 +59,18 @@ def test_build_runs_is_the_run_length_form_of_tid(n):
         assert np.array_equal(soa.chunk_run, np.searchsorted(soa.run_start, first, side="right") - 1)
         cs = soa.c_struct()
         assert cs.n_runs == len(starts) and cs.run_tid == soa.run_tid.ctypes.data
+        # len(SEQ) per chunk: all-zero qlen is uniform; one odd record anywhere drops the form
+        assert soa.chunk_qlen is not None and soa.chunk_qlen.shape[0] == (n + 255) // 256 and not soa.chunk_qlen.any()
+        assert cs.chunk_qlen == soa.chunk_qlen.ctypes.data
+        if n > 1:
+            soa.qlen = np.repeat(np.arange((n + 255) // 256, dtype=np.uint16) + 90, 256)[:n].copy()
+            soa.build_runs(max_fraction=1.0)
+            assert np.array_equal(soa.chunk_qlen, np.arange((n + 255) // 256, dtype=np.uint16) + 90)
+            soa.qlen[0] += 1  # chunk 0 holds at least two records
+            soa.build_runs(max_fraction=1.0)
+            assert soa.chunk_qlen is None and soa.run_tid is not None and not soa.c_struct().chunk_qlen
+            soa.qlen[:] = 0
+            soa.build_runs(max_fraction=1.0)
         # capacity is checked, not overrun
         nr = C.c_uint32(len(starts) - 1)
         rt = np.zeros(len(starts) + 1, np.uint32); rs = np.zeros(len(starts) + 2, np.uint32); cr = np.zeros(len(first), np.uint32)
