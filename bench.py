@@ -50,6 +50,8 @@ def parse():
                          "one NCCL all-gather of result blocks per pass; 'allreduce' = partial score/count tensors all-reduced with NCCL")
     ap.add_argument("--lanes", type=int, default=2, help="N=1: streams that consecutive passes alternate on (cohort mode: the tail of pass i "
                     "overlaps the scoring kernel of pass i+1); 1 = strictly serial passes")
+    ap.add_argument("--no-qc", action="store_true", help="score stream in the 5 B/record run-length form (explicit len(SEQ) per record) even when every "
+                    "256-record chunk is uniform")
     ap.add_argument("--max-depth", type=int, default=8000, help="htslib pileup depth cap of the main workload (0 = uncapped; profiling aid)")
     return ap.parse_args()
 
@@ -300,6 +302,9 @@ def main():
     n_samples = max(2, args.lanes)
     sts = [st] + [gen_streams(db, args, device, args.max_depth or None, subset, seed=1002 + rank + 100 * l)[0] for l in range(1, n_samples)]
     assert all(int(x.tid.shape[0]) == R_local for x in sts)
+    if args.no_qc:
+        for x in sts:
+            x.chunk_qlen = None
     pipes = [pipeline.DevicePipeline(x, index, db.row_seq, impl=args.pileup_impl, idx_base=rank * R_local, exchange=args.exchange, **PARAMS) for x in sts]
     pipe = pipes[0]
 
