@@ -52,6 +52,8 @@ def parse():
                     "overlaps the scoring kernel of pass i+1); 1 = strictly serial passes")
     ap.add_argument("--no-qc", action="store_true", help="score stream in the 5 B/record run-length form (explicit len(SEQ) per record) even when every "
                     "256-record chunk is uniform")
+    ap.add_argument("--score-variant", type=int, default=-1, choices=[-1, 0, 1, 2], help="form of the run-length score kernel (mmlst_set_score_variant): "
+                    "0 registers, 1 registers + software pipeline, 2 shared-memory ring fed by TMA bulk copies; -1 = the library default")
     ap.add_argument("--max-depth", type=int, default=8000, help="htslib pileup depth cap of the main workload (0 = uncapped; profiling aid)")
     return ap.parse_args()
 
@@ -272,6 +274,9 @@ def main():
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
     native.lib()  # fail loudly if the CUDA library is missing
+    if args.score_variant >= 0:
+        native.lib().mmlst_set_score_variant(args.score_variant)
+    score_variant = native.lib().mmlst_set_score_variant(-1)
     peak, peak_src = peaks()
     if args.only_hamming:
         emit({"hamming": extra_hamming(device, peak)})
@@ -385,6 +390,11 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     kms = pipe.time_kernels(20, alt=pipes[1], flush=flush)
     del flush
+    # the other forms of the score kernel on the same two samples (same tables out, checked), for the record
+    variants_ms = {str(score_variant): kms["score"]}
+    if not args.no_extras and pipe.use_runs:
+        variants_ms = pipe.time_score_variants(20, alt=pipes[1])
+        native.lib().mmlst_set_score_variant(score_variant)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(10):
@@ -409,7 +419,7 @@ def main():
     rooflines = {
         "score": {"bound": "hbm", "achieved": score_bytes / kms["score"] / 1e6, "peak": peak, "unit": "GB/s", "frac": score_bytes / kms["score"] / 1e6 / peak,
                   "traffic": ncu_traffic("score_runs_qc" if pipe.use_qc else "score_runs" if pipe.use_runs else "score") if args.reads == 10_000_000 and args.k == 4 else None,
-                  "ms": kms["score"], "algorithmic_bytes": score_bytes,
+                  "ms": kms["score"], "algorithmic_bytes": score_bytes, "kernel_form": score_variant, "ms_by_kernel_form": variants_ms,
                   "stream_form": "run-length + len(SEQ) per 256-record chunk: as0 i16 + xm3 u8 per record, allele id per run (3 B/record; lossless: every "
                                  "chunk of this sample has one read length; SURVEY 8d's explicit form is 9 B/record)" if pipe.use_qc else
                                  "run-length: as0 i16 + xm3 u8 + qlen u16 per record, allele id per run (5 B/record; SURVEY 8d's explicit-id form is 9 B/record)"

@@ -113,6 +113,12 @@ int mmlst_score_runs_qc_dev(const uint32_t* run_tid, const uint32_t* run_start, 
                             uint64_t n_rec, uint64_t idx_base, const uint8_t* allow, uint32_t n_ref,
                             int minscore, int max_xm, int min_read_len,
                             int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, uint64_t* counters, void* stream);
+/* Kernel form used by mmlst_score_runs_dev / mmlst_score_runs_qc_dev (identical results): 0 = register-staged, 1 = register-
+ * staged and software-pipelined, 2 = per-warp shared-memory ring filled by TMA bulk copies (records without orig_idx only;
+ * other inputs take form 0).  Returns the previous value; a value outside 0..2 only queries.  The environment variable
+ * MMLST_SCORE_VARIANT presets it. */
+#define MMLST_SCORE_VARIANT_DEFAULT 0
+int mmlst_set_score_variant(int variant);
 /* qlen[i] of every record back from the per-chunk form (device; the coverage kernel takes it per record) */
 int mmlst_expand_chunk_qlen_dev(const uint16_t* chunk_qlen, uint64_t n_rec, uint16_t* qlen, void* stream);
 /* tid[i] of every record back from the run arrays (device; the coverage kernel takes the explicit form) */

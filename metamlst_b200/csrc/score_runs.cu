@@ -205,6 +205,27 @@ __device__ __forceinline__ void reduce_chunk(const RunArgs& a, const Thr& thr, W
     }
 }
 
+// tail (< 256 records): last warp of the grid, one record per lane per step; the run is found by walking from the
+// tail chunk's entry
+template <bool QC>
+__device__ __forceinline__ void score_tail(const RunArgs& a, uint64_t nchunks, uint32_t lane, uint32_t& tot, uint32_t& ign) {
+    uint32_t r = __ldg(a.chunk_run + nchunks);
+    for (uint64_t i = (nchunks << 8) + lane; i < a.n_rec; i += 32) {
+        while (r + 1 < a.n_runs && i >= a.run_start[r + 1]) ++r;
+        const uint32_t key = a.run_tid[r];
+        if (!((key < a.n_ref) && a.allow[key])) continue;
+        ++tot;
+        const int as = a.as0[i];
+        const int ql = QC ? int(a.chunk_qlen[nchunks]) : int(a.qlen[i]);
+        if ((as >= a.minscore) && (ql >= a.min_read_len) && (int(a.xm3[i]) <= a.max_xm)) {
+            const uint32_t idx = a.orig_idx ? a.orig_idx[i] : static_cast<uint32_t>(a.idx_base + i);
+            flush_run(a, key, as, 1u, idx);
+        } else {
+            ++ign;
+        }
+    }
+}
+
 template <bool OIDX, bool PIPE, bool QC>
 __global__ void __launch_bounds__(kThreads, PIPE ? (OIDX ? 2 : 3) : (OIDX ? 3 : 4)) score_runs_kernel(const RunArgs a) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -257,25 +278,98 @@ __global__ void __launch_bounds__(kThreads, PIPE ? (OIDX ? 2 : 3) : (OIDX ? 3 : 
         close_run(a, w, lane);
     }
 
-    // tail (< 256 records): last warp of the grid, one record per lane per step; the run is found by walking from the
-    // tail chunk's entry
-    if (warp == nwarps - 1 && (a.n_rec & 255u)) {
-        uint32_t r = __ldg(a.chunk_run + nchunks);
-        for (uint64_t i = (nchunks << 8) + lane; i < a.n_rec; i += 32) {
-            while (r + 1 < a.n_runs && i >= a.run_start[r + 1]) ++r;
-            const uint32_t key = a.run_tid[r];
-            if (!((key < a.n_ref) && a.allow[key])) continue;
-            ++tot;
-            const int as = a.as0[i];
-            const int ql = QC ? int(a.chunk_qlen[nchunks]) : int(a.qlen[i]);
-            if ((as >= a.minscore) && (ql >= a.min_read_len) && (int(a.xm3[i]) <= a.max_xm)) {
-                const uint32_t idx = a.orig_idx ? a.orig_idx[i] : static_cast<uint32_t>(a.idx_base + i);
-                flush_run(a, key, as, 1u, idx);
-            } else {
-                ++ign;
-            }
-        }
+    if (warp == nwarps - 1 && (a.n_rec & 255u)) score_tail<QC>(a, nchunks, lane, tot, ign);
+    tot = __reduce_add_sync(FULL, tot);
+    ign = __reduce_add_sync(FULL, ign);
+    if (lane == 0 && tot) {
+        atomicAdd(a.counters + 0, static_cast<unsigned long long>(tot));
+        atomicAdd(a.counters + 1, static_cast<unsigned long long>(ign));
     }
+}
+
+// ---- variant 2: the same reduction fed through a per-warp shared-memory ring filled by TMA bulk copies.
+// The register variants above keep at most two chunks (1.5 KB in the 3 B form) in flight per warp, and only while the
+// warp is not reducing; at 32 resident warps per SM that is under the ~35 KB per SM the HBM stream needs (Little's law
+// at ~6.4 TB/s), and ncu shows the kernel waiting on long-scoreboard stalls at 45 % DRAM throughput.  Here lane 0 of every
+// warp keeps NS stages of two chunks each requested ahead (cp.async.bulk, completion on a warp-private mbarrier), so the
+// bytes in flight (NS x 1.5 KB per warp, ~190 KB per SM) no longer depend on registers or on what the warp is doing;
+// the lanes read their 8 records from the stage with one LDS.128 + one LDS.64.  Warps still own contiguous chunk ranges,
+// so the open run stays in registers exactly as above, and no CTA-wide barrier is needed after the mbarrier set-up.
+constexpr uint32_t RING_CH = 2;  // chunks per stage
+
+template <bool QC, int NS>
+__global__ void __launch_bounds__(kThreads, QC ? 4 : 3) score_runs_ring_kernel(const RunArgs a) {
+    extern __shared__ __align__(128) uint8_t ring_raw[];
+    constexpr uint32_t AS_B = RING_CH * 512u, QL_B = QC ? 0u : RING_CH * 512u, XM_B = RING_CH * 256u;
+    constexpr uint32_t STAGE_B = AS_B + QL_B + XM_B;
+    constexpr uint32_t CH_B = STAGE_B / RING_CH;  // bytes one chunk brings
+    constexpr int NW = kThreads / 32;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint8_t* const my = ring_raw + wid * (NS * STAGE_B);
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(ring_raw + NW * NS * STAGE_B) + wid * NS;
+    if (threadIdx.x == 0) {
+        uint64_t* all = reinterpret_cast<uint64_t*>(ring_raw + NW * NS * STAGE_B);
+        for (int i = 0; i < NW * NS; ++i) mbar_init(all + i, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+    const uint64_t nchunks = a.n_rec >> 8;
+    const uint64_t per = (nchunks + nwarps - 1) / nwarps;
+    const uint64_t c0 = warp * per;
+    const uint64_t c1 = (c0 + per < nchunks) ? c0 + per : nchunks;
+    uint32_t tot = 0, ign = 0;
+    const Thr thr = make_thr(a);
+
+    if (c0 < c1) {
+        const uint32_t ngroups = static_cast<uint32_t>((c1 - c0 + RING_CH - 1) / RING_CH);
+        auto issue = [&](uint32_t g, int stage) {  // lane 0: request group g (one or two chunks) into `stage`
+            const uint64_t ch = c0 + static_cast<uint64_t>(g) * RING_CH;
+            const uint32_t nch = (c1 - ch < RING_CH) ? static_cast<uint32_t>(c1 - ch) : RING_CH;
+            uint8_t* st = my + stage * STAGE_B;
+            mbar_expect_tx(bars + stage, nch * CH_B);
+            bulk_g2s(st, a.as0 + (ch << 8), nch * 512u, bars + stage);
+            if constexpr (!QC) bulk_g2s(st + AS_B, a.qlen + (ch << 8), nch * 512u, bars + stage);
+            bulk_g2s(st + AS_B + QL_B, a.xm3 + (ch << 8), nch * 256u, bars + stage);
+        };
+        if (lane == 0) {
+            const uint32_t pre = ngroups < static_cast<uint32_t>(NS) ? ngroups : static_cast<uint32_t>(NS);
+            for (uint32_t g = 0; g < pre; ++g) issue(g, static_cast<int>(g));
+        }
+        WarpRun w;
+        open_run(a, w, __ldg(a.chunk_run + c0));  // dependent lookups run under the first copies
+        uint32_t phase = 0;
+        int stage = 0;
+        for (uint32_t g = 0; g < ngroups; ++g) {
+            const uint64_t ch = c0 + static_cast<uint64_t>(g) * RING_CH;
+            const bool two = ch + 1 < c1;
+            mbar_wait(bars + stage, (phase >> stage) & 1u);
+            phase ^= 1u << stage;
+            const uint8_t* st = my + stage * STAGE_B;
+            Loaded<false> L0, L1;
+            L0.a8 = *reinterpret_cast<const uint4*>(st + lane * 16u);
+            L0.x8 = *reinterpret_cast<const uint2*>(st + AS_B + QL_B + lane * 8u);
+            if constexpr (QC) { L0.q8 = make_uint4(0, 0, 0, 0); L0.cq = __ldg(a.chunk_qlen + ch); }
+            else { L0.q8 = *reinterpret_cast<const uint4*>(st + AS_B + lane * 16u); L0.cq = 0; }
+            L1 = L0;
+            if (two) {
+                L1.a8 = *reinterpret_cast<const uint4*>(st + 512u + lane * 16u);
+                L1.x8 = *reinterpret_cast<const uint2*>(st + AS_B + QL_B + 256u + lane * 8u);
+                if constexpr (QC) L1.cq = __ldg(a.chunk_qlen + ch + 1);
+                else L1.q8 = *reinterpret_cast<const uint4*>(st + AS_B + 512u + lane * 16u);
+            }
+            __syncwarp();  // every lane has its records in registers: the stage may be refilled
+            if (lane == 0 && g + NS < ngroups) issue(g + NS, stage);
+            reduce_chunk<false, QC>(a, thr, w, L0, ch << 8, lane, tot, ign);
+            if (two) reduce_chunk<false, QC>(a, thr, w, L1, (ch + 1) << 8, lane, tot, ign);
+            stage = (stage + 1 == NS) ? 0 : stage + 1;
+        }
+        close_run(a, w, lane);
+    }
+
+    if (warp == nwarps - 1 && (a.n_rec & 255u)) score_tail<QC>(a, nchunks, lane, tot, ign);
     tot = __reduce_add_sync(FULL, tot);
     ign = __reduce_add_sync(FULL, ign);
     if (lane == 0 && tot) {
@@ -303,6 +397,23 @@ __global__ void __launch_bounds__(256) expand_chunk_qlen_kernel(const uint16_t* 
 
 }  // namespace
 
+// Which form of the run-length kernel a launch takes: 0 = registers, two chunks in flight per warp; 1 = registers,
+// software-pipelined (the next pair is requested before the current one is reduced); 2 = per-warp shared-memory ring fed
+// by TMA bulk copies.  Same arithmetic, same results; MMLST_SCORE_VARIANT presets it, mmlst_set_score_variant changes it.
+static int g_score_variant = -1;
+static int score_variant() {
+    if (g_score_variant < 0) {
+        const char* e = getenv("MMLST_SCORE_VARIANT");
+        g_score_variant = (e && e[0] >= '0' && e[0] <= '2' && !e[1]) ? e[0] - '0' : MMLST_SCORE_VARIANT_DEFAULT;
+    }
+    return g_score_variant;
+}
+extern "C" int mmlst_set_score_variant(int v) {
+    const int prev = score_variant();
+    if (v >= 0 && v <= 2) g_score_variant = v;
+    return prev;
+}
+
 static int score_runs_launch(const uint32_t* run_tid, const uint32_t* run_start, uint32_t n_runs, const uint32_t* chunk_run,
                              const int16_t* as0, const uint8_t* xm3, const uint16_t* qlen, const uint16_t* chunk_qlen, const uint32_t* orig_idx,
                              uint64_t n_rec, uint64_t idx_base, const uint8_t* allow, uint32_t n_ref, int minscore,
@@ -323,10 +434,31 @@ static int score_runs_launch(const uint32_t* run_tid, const uint32_t* run_start,
               min_read_len, reinterpret_cast<long long*>(sum_as), n_hit, first_idx, reinterpret_cast<unsigned long long*>(counters)};
     const uint64_t nchunks = n_rec >> 8;
     uint64_t want = (nchunks + 15) / 16;  // CTAs if every warp took two chunks
+    const int variant = score_variant();
+    const cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool tma_ok = !orig_idx && !(reinterpret_cast<uintptr_t>(xm3) & 15);  // cp.async.bulk wants 16-byte aligned sources
+    if (variant == 2 && tma_ok) {
+        // one resident wave of the ring kernel: NS stages of two chunks per warp in dynamic shared memory
+        static int ring_resident[2] = {0, 0};
+        const int q = chunk_qlen ? 1 : 0;
+        void (*kern)(const RunArgs) = q ? score_runs_ring_kernel<true, 4> : score_runs_ring_kernel<false, 3>;
+        const size_t smem = (kThreads / 32) * (q ? 4 * (RING_CH * 768u) : 3 * (RING_CH * 1280u)) + (kThreads / 32) * 4 * sizeof(uint64_t);
+        if (!ring_resident[q]) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            int r = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, kern, kThreads, smem) != cudaSuccess || r < 1) r = 1;
+            ring_resident[q] = r;
+        }
+        const uint64_t cap = static_cast<uint64_t>(mmlst_num_sms()) * ring_resident[q];
+        if (want > cap) want = cap;
+        if (want < 1) want = 1;
+        kern<<<static_cast<unsigned>(want), kThreads, smem, st>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        return MMLST_OK;
+    }
     static int resident[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // one wave exactly: the blocked chunk distribution has no tail
-    static int pipe = -1;
-    if (pipe < 0) { const char* e = getenv("MMLST_SCORE_PIPE"); pipe = (e && e[0] == '1') ? 1 : 0; }
-    const int v = (orig_idx ? 1 : 0) + 2 * pipe + (chunk_qlen ? 4 : 0);
+    const int v = (orig_idx ? 1 : 0) + 2 * (variant == 1 ? 1 : 0) + (chunk_qlen ? 4 : 0);
     void (*const kerns[8])(const RunArgs) = {score_runs_kernel<false, false, false>, score_runs_kernel<true, false, false>,
                                              score_runs_kernel<false, true, false>, score_runs_kernel<true, true, false>,
                                              score_runs_kernel<false, false, true>, score_runs_kernel<true, false, true>,
@@ -338,7 +470,7 @@ static int score_runs_launch(const uint32_t* run_tid, const uint32_t* run_start,
     const uint64_t cap = static_cast<uint64_t>(mmlst_num_sms()) * resident[v];
     if (want > cap) want = cap;
     if (want < 1) want = 1;
-    kern<<<static_cast<unsigned>(want), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    kern<<<static_cast<unsigned>(want), kThreads, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return MMLST_OK;
 }

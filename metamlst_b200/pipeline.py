@@ -366,6 +366,35 @@ class DevicePipeline:
                 p._clean = False
         return out
 
+    def time_score_variants(self, reps: int = 20, alt: Optional["DevicePipeline"] = None) -> Dict[str, float]:
+        """Average device time (ms) of the run-length score kernel in each of its forms (mmlst_set_score_variant), timed like
+        time_kernels() times it (back to back, alternating two samples, cold L2); every form must leave the same tables.
+        Leaves the library on the last form tried: the caller restores its own."""
+        pipes = [self] + ([alt] if alt is not None else [])
+        out: Dict[str, float] = {}
+        want = None
+        for v in (0, 1, 2):
+            self.lib.mmlst_set_score_variant(v)
+            self.reset_tables()
+            self._score_call()
+            torch.cuda.current_stream(self.dev).synchronize()
+            got = [self.zscore.clone(), self.first_idx.clone()]
+            if want is None:
+                want = got
+            assert all(torch.equal(a, b) for a, b in zip(got, want)), "score kernel form %d disagrees with form 0" % v
+            for p in pipes:
+                p._score_call()  # warm
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(reps):
+                pipes[i % len(pipes)]._score_call()
+            b.record()
+            b.synchronize()
+            out[str(v)] = a.elapsed_time(b) / reps
+        for p in pipes:
+            p._clean = False
+        return out
+
     def _launch_one(self, name: str):
         s = self.s
         if name == "score":

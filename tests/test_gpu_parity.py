@@ -22,11 +22,23 @@ def ctx():
     c.close()
 
 
+# forms of the run-length score kernel (mmlst_set_score_variant) the stage-1 tests run under
+SCORE_VARIANTS = tuple(int(x) for x in os.environ.get("MMLST_TEST_SCORE_VARIANTS", "0").split(","))
+
+
+@pytest.fixture(params=SCORE_VARIANTS, ids=lambda v: "form%d" % v)
+def kernel_form(request):
+    prev = native.lib().mmlst_set_score_variant(request.param)
+    assert native.lib().mmlst_set_score_variant(-1) == request.param
+    yield request.param
+    native.lib().mmlst_set_score_variant(prev)
+
+
 # ------------------------------------------------------------------------------------------------ stage 1
 @pytest.mark.parametrize("form", ["tid", "runs"])  # explicit allele id per record (9 B) / run-length form (5 B)
 @pytest.mark.parametrize("order", ["name", "coord"])
 @pytest.mark.parametrize("n_reads,species_filter", [(37, None), (3000, None), (3000, "saureus"), (60000, "ecoli,saureus")])
-def test_score_bit_exact(ctx, order, n_reads, species_filter, form):
+def test_score_bit_exact(ctx, order, n_reads, species_filter, form, kernel_form):
     db, tab = small_case(seed=31, n_reads=n_reads, orgs=("ecoli", "saureus"), apl=8, sub_err=0.02)
     if order == "coord":
         tab = tab.sorted_by_coord()
@@ -55,7 +67,7 @@ def _np_score(tid, as0, xm3, qlen, idx, allow, n_ref, minscore, max_xm, min_len)
 
 
 @pytest.mark.parametrize("n", [1, 255, 256, 257, 511, 513, 4096, 100003, 5_000_000])
-def test_score_run_length_form_on_raw_streams(ctx, n):
+def test_score_run_length_form_on_raw_streams(ctx, n, kernel_form):
     # run boundaries everywhere: single-record runs, runs ending exactly on 256-record chunk edges, one run spanning many
     # chunks, filtered alleles in the middle, negative scores, with and without a file-order index, tails of every size
     rng = np.random.default_rng(n)
@@ -448,7 +460,7 @@ def test_device_selection_rounding_and_order_match_python(ctx):
 @pytest.mark.parametrize("case", [dict(seed=81, n_reads=3000, L=100, K=4, orgs=("ecoli", "saureus")),
                                   dict(seed=82, n_reads=30000, L=150, K=4, orgs=("ecoli",)),
                                   dict(seed=83, n_reads=60, L=100, K=2, orgs=("ecoli", "saureus", "kpneumoniae"))])
-def test_device_pipeline_equals_host_selected_path_and_oracle(ctx, case):
+def test_device_pipeline_equals_host_selected_path_and_oracle(ctx, case, kernel_form):
     from metamlst_b200 import devpack, pipeline, synth
     kw = dict(case)
     orgs = kw.pop("orgs")
