@@ -1,6 +1,10 @@
 // Shared helpers for libmmlst (sm_100a only).
 #pragma once
+#ifdef MMLST_HOST_EMUL
+#include "simt_host_emul.h"  // tests/simt: CUDA vocabulary for a host build, one std::thread per lane
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -30,6 +34,7 @@ __host__ __device__ inline uint32_t mmlst_chunk_tiles(unsigned long long n_rec, 
     return best_cr > 63u ? 63u : best_cr;
 }
 
+#ifndef MMLST_HOST_EMUL
 void mmlst_set_error(const char* fmt, ...);
 int mmlst_cuda_fail(cudaError_t e, const char* what);
 
@@ -87,3 +92,4 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
                      : "memory");
     } while (!done);
 }
+#endif  // MMLST_HOST_EMUL
