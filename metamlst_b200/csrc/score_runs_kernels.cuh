@@ -109,12 +109,13 @@ __device__ __forceinline__ void lane_pass(const Loaded<OIDX>& L, const Thr& t, i
     for (int w = 0; w < 4; ++w) {
         const uint32_t da = (aw[w] | H16) - t.as_TL;
         const uint32_t ga = (~aw[w] & ~t.as_T) | ((aw[w] ^ t.as_T) & da);          // as0 >= minscore (signed halves)
+        // only the top bit of every half is meaningful; the final `& t.h8` below keeps exactly those
         if constexpr (QC) {
-            m[w] = ga & H16;
+            m[w] = ga;
         } else {
             const uint32_t dq = (qw[w] | H16) - t.ql_TL;
             const uint32_t gq = (qw[w] & ~t.ql_T) | (~(qw[w] ^ t.ql_T) & dq);     // qlen >= min_read_len
-            m[w] = ga & gq & H16;
+            m[w] = ga & gq;
         }
     }
     const uint32_t b_lo = __byte_perm(m[0], m[1], 0x7531), b_hi = __byte_perm(m[2], m[3], 0x7531);  // top byte of every half
@@ -323,6 +324,19 @@ __device__ __forceinline__ void segment_masks(uint32_t klo, uint32_t khi, uint32
     in_hi = bytes_below(khi > 4u ? khi - 4u : 0u) & ~bytes_below(klo > 4u ? klo - 4u : 0u) & 0x01010101u;
 }
 
+// sum / count of the lane's records selected by the byte masks, and the index of the first selected one
+__device__ __forceinline__ void lane_sums_pf(const Loaded<false>& L, uint32_t p_lo, uint32_t p_hi, int& s, uint32_t& c) {
+    s = __dp2a_lo(static_cast<int>(L.a8.x), static_cast<int>(p_lo), 0);
+    s = __dp2a_hi(static_cast<int>(L.a8.y), static_cast<int>(p_lo), s);
+    s = __dp2a_lo(static_cast<int>(L.a8.z), static_cast<int>(p_hi), s);
+    s = __dp2a_hi(static_cast<int>(L.a8.w), static_cast<int>(p_hi), s);
+    c = __popc(p_lo | (p_hi << 1));
+}
+__device__ __forceinline__ uint32_t first_pass_index(uint32_t p_lo, uint32_t p_hi, uint32_t idx0) {
+    const uint32_t k = p_lo ? (static_cast<uint32_t>(__ffs(p_lo)) - 1u) >> 3 : 4u + ((static_cast<uint32_t>(__ffs(p_hi)) - 1u) >> 3);
+    return (p_lo | p_hi) ? idx0 + k : 0xffffffffu;
+}
+
 template <bool QC>
 __device__ __forceinline__ void reduce_chunk_pf(const RunArgs& a, const Thr& thr, WarpRunPF& w, const Loaded<false>& L, uint32_t base, uint32_t lane,
                                                 uint32_t& tot, uint32_t& ign) {
@@ -333,13 +347,15 @@ __device__ __forceinline__ void reduce_chunk_pf(const RunArgs& a, const Thr& thr
     const uint32_t chunk_end = base + 256u;  // n_rec < 2^32 - 256: no wrap
     if (chunk_end <= w.end) {  // the whole chunk lies inside the open run
         if (w.al) {
-            int s; uint32_t c, mn;
-            lane_sums<false>(L, p_lo, p_hi, idx0, s, c, mn);
+            int s; uint32_t c;
+            lane_sums_pf(L, p_lo, p_hi, s, c);
             tot += R;
             ign += R - c;
             w.s += __reduce_add_sync(FULL, s);
             w.c += __reduce_add_sync(FULL, c);
-            w.mn = min(w.mn, __reduce_min_sync(FULL, mn));
+            // record indices ascend inside a run (no file-order index here): once the run has a passing record, later
+            // chunks cannot lower its first index
+            if (w.mn == 0xffffffffu) w.mn = __reduce_min_sync(FULL, first_pass_index(p_lo, p_hi, idx0));
         }
         if (chunk_end == w.end) next_run_pf(a, w, lane);
         return;
@@ -353,14 +369,14 @@ __device__ __forceinline__ void reduce_chunk_pf(const RunArgs& a, const Thr& thr
             const uint32_t khi = static_cast<uint32_t>(min(max(static_cast<int>(hi - base) - lane0, 0), 8));
             uint32_t in_lo, in_hi;
             segment_masks(klo, khi, in_lo, in_hi);
-            int s; uint32_t c, mn;
-            lane_sums<false>(L, p_lo & in_lo, p_hi & in_hi, idx0, s, c, mn);
+            int s; uint32_t c;
+            lane_sums_pf(L, p_lo & in_lo, p_hi & in_hi, s, c);
             const uint32_t in = khi - klo;  // hi > lo, so khi >= klo
             tot += in;
             ign += in - c;
             w.s += __reduce_add_sync(FULL, s);
             w.c += __reduce_add_sync(FULL, c);
-            w.mn = min(w.mn, __reduce_min_sync(FULL, mn));
+            if (w.mn == 0xffffffffu) w.mn = __reduce_min_sync(FULL, first_pass_index(p_lo & in_lo, p_hi & in_hi, idx0));
         }
         if (hi == w.end) next_run_pf(a, w, lane);
         lo = hi;
