@@ -52,8 +52,9 @@ def parse():
                     "overlaps the scoring kernel of pass i+1); 1 = strictly serial passes")
     ap.add_argument("--no-qc", action="store_true", help="score stream in the 5 B/record run-length form (explicit len(SEQ) per record) even when every "
                     "256-record chunk is uniform")
-    ap.add_argument("--score-variant", type=int, default=-1, choices=[-1, 0, 1, 2], help="form of the run-length score kernel (mmlst_set_score_variant): "
-                    "0 registers, 1 registers + software pipeline, 2 shared-memory ring fed by TMA bulk copies; -1 = the library default")
+    ap.add_argument("--score-variant", default="default", choices=["default", "0", "1", "2", "auto"],
+                    help="form of the run-length score kernel (mmlst_set_score_variant): 0 registers, 1 registers + software pipeline, 2 shared-memory "
+                         "ring fed by TMA bulk copies; 'default' = the library's; 'auto' = time all three on the workload first and keep the fastest")
     ap.add_argument("--max-depth", type=int, default=8000, help="htslib pileup depth cap of the main workload (0 = uncapped; profiling aid)")
     return ap.parse_args()
 
@@ -274,8 +275,8 @@ def main():
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
     native.lib()  # fail loudly if the CUDA library is missing
-    if args.score_variant >= 0:
-        native.lib().mmlst_set_score_variant(args.score_variant)
+    if args.score_variant in ("0", "1", "2"):
+        native.lib().mmlst_set_score_variant(int(args.score_variant))
     score_variant = native.lib().mmlst_set_score_variant(-1)
     peak, peak_src = peaks()
     if args.only_hamming:
@@ -320,6 +321,15 @@ def main():
 
     sampler = ClockSampler(local)
     sampler.start()
+    variants_ms = None
+    if args.score_variant == "auto" and pipe.use_runs:
+        # every form on this workload (equal tables asserted), fastest kept for everything that follows; with N>1 the ranks agree on rank 0's choice
+        variants_ms = pipe.time_score_variants(20, alt=pipes[1])
+        pick = torch.tensor([int(min(variants_ms, key=variants_ms.get))], dtype=torch.int32, device=device)
+        if world > 1:
+            torch.distributed.broadcast(pick, 0)
+        score_variant = int(pick.item())
+        native.lib().mmlst_set_score_variant(score_variant)
     results = []
     for p in pipes:
         for _ in range(max(args.warmup, 3)):
@@ -391,10 +401,11 @@ def main():
     kms = pipe.time_kernels(20, alt=pipes[1], flush=flush)
     del flush
     # the other forms of the score kernel on the same two samples (same tables out, checked), for the record
-    variants_ms = {str(score_variant): kms["score"]}
-    if not args.no_extras and pipe.use_runs:
-        variants_ms = pipe.time_score_variants(20, alt=pipes[1])
-        native.lib().mmlst_set_score_variant(score_variant)
+    if variants_ms is None:
+        variants_ms = {str(score_variant): kms["score"]}
+        if not args.no_extras and pipe.use_runs:
+            variants_ms = pipe.time_score_variants(20, alt=pipes[1])
+            native.lib().mmlst_set_score_variant(score_variant)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(10):

@@ -1,4 +1,4 @@
-"""N>1 host logic on CPU: world_size-2 `gloo` processes run the same reductions the GPU ranks run over NCCL
+"""N>1 host logic on CPU: world_size-2 and -4 `gloo` processes run the same reductions the GPU ranks run over NCCL
 (metamlst_b200/dist.py).  Per-rank partial tables come from the C oracle on contig-aligned shards; the reduced tables
 must equal the oracle on the whole sample, bit for bit."""
 import os
@@ -108,9 +108,13 @@ def _worker(rank, world, port, ret):
         dist.allreduce_best(best)
         wd, wa = corc.hamming_min([q.encode() for q in qs], flat, off, [(0, len(rows))] * len(qs))
         got = best.numpy().view(np.uint64)
-        if world == 2:
-            d0, a0 = corc.hamming_min([qs[2].encode()], flat, off, [dist.shard_rows(len(rows), world, 0)])
-            wd[2], wa[2] = d0[0], a0[0]
+        # query 2: the best over every shard but rank 1's
+        keys = []
+        for r in range(world):
+            if r != 1:
+                d0, a0 = corc.hamming_min([qs[2].encode()], flat, off, [dist.shard_rows(len(rows), world, r)])
+                keys.append((int(d0[0]), int(a0[0])))
+        wd[2], wa[2] = min(keys)
         assert np.array_equal(got >> np.uint64(32), wd.astype(np.uint64)) and np.array_equal(got & np.uint64(0xffffffff), wa.astype(np.uint64))
         assert int(got[0] & np.uint64(0xffffffff)) == 17
         assert dist.max_over_ranks(float(rank + 1), "cpu") == float(world)
@@ -122,13 +126,13 @@ def _worker(rank, world, port, ret):
         td.destroy_process_group()
 
 
-def test_world_size_2_reductions_equal_the_whole_sample():
-    world = 2
+@pytest.mark.parametrize("world", [2, 4])
+def test_reductions_over_ranks_equal_the_whole_sample(world):
     port = _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
-    assert dict(ret) == {0: "ok", 1: "ok"}
+    assert dict(ret) == {r: "ok" for r in range(world)}
 
 
 def test_shard_helpers():
