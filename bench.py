@@ -52,7 +52,7 @@ def parse():
                     "overlaps the scoring kernel of pass i+1); 1 = strictly serial passes")
     ap.add_argument("--no-qc", action="store_true", help="score stream in the 5 B/record run-length form (explicit len(SEQ) per record) even when every "
                     "256-record chunk is uniform")
-    ap.add_argument("--score-variant", default="default", choices=["default", "0", "1", "2", "auto"],
+    ap.add_argument("--score-variant", default="default", choices=["default", "0", "1", "2", "3", "4", "5", "auto"],
                     help="form of the run-length score kernel (mmlst_set_score_variant): 0 registers, 1 registers + software pipeline, 2 shared-memory "
                          "ring fed by TMA bulk copies; 'default' = the library's; 'auto' = time all three on the workload first and keep the fastest")
     ap.add_argument("--max-depth", type=int, default=8000, help="htslib pileup depth cap of the main workload (0 = uncapped; profiling aid)")
@@ -275,7 +275,7 @@ def main():
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
     native.lib()  # fail loudly if the CUDA library is missing
-    if args.score_variant in ("0", "1", "2"):
+    if args.score_variant in ("0", "1", "2", "3", "4", "5"):
         native.lib().mmlst_set_score_variant(int(args.score_variant))
     score_variant = native.lib().mmlst_set_score_variant(-1)
     peak, peak_src = peaks()
@@ -325,6 +325,10 @@ def main():
     if args.score_variant == "auto" and pipe.use_runs:
         # every form on this workload (equal tables asserted), fastest kept for everything that follows; with N>1 the ranks agree on rank 0's choice
         variants_ms = pipe.time_score_variants(20, alt=pipes[1])
+        if os.environ.get("MMLST_BENCH_SCALING"):  # diagnostic: fixed cost vs streaming rate of each form
+            for v in sorted(variants_ms):
+                native.lib().mmlst_set_score_variant(int(v))
+                sys.stderr.write("score form %s, records 1/1 1/2 1/4: %r\n" % (v, pipe.time_score_half(20, alt=pipes[1])))
         pick = torch.tensor([int(min(variants_ms, key=variants_ms.get))], dtype=torch.int32, device=device)
         if world > 1:
             torch.distributed.broadcast(pick, 0)

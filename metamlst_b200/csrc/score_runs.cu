@@ -16,18 +16,18 @@
 
 // Which form of the run-length kernel a launch takes: 0 = registers, two chunks in flight per warp; 1 = registers,
 // software-pipelined (the next pair is requested before the current one is reduced); 2 = per-warp shared-memory ring fed
-// by TMA bulk copies.  Same arithmetic, same results; MMLST_SCORE_VARIANT presets it, mmlst_set_score_variant changes it.
+// by TMA bulk copies (3..5: the same with other stage sizes / depths, see ring_config).  Same arithmetic, same results; MMLST_SCORE_VARIANT presets it, mmlst_set_score_variant changes it.
 static int g_score_variant = -1;
 static int score_variant() {
     if (g_score_variant < 0) {
         const char* e = getenv("MMLST_SCORE_VARIANT");
-        g_score_variant = (e && e[0] >= '0' && e[0] <= '2' && !e[1]) ? e[0] - '0' : MMLST_SCORE_VARIANT_DEFAULT;
+        g_score_variant = (e && e[0] >= '0' && e[0] <= '5' && !e[1]) ? e[0] - '0' : MMLST_SCORE_VARIANT_DEFAULT;
     }
     return g_score_variant;
 }
 extern "C" int mmlst_set_score_variant(int v) {
     const int prev = score_variant();
-    if (v >= 0 && v <= 2) g_score_variant = v;
+    if (v >= 0 && v <= 5) g_score_variant = v;
     return prev;
 }
 
@@ -54,23 +54,23 @@ static int score_runs_launch(const uint32_t* run_tid, const uint32_t* run_start,
     const int variant = score_variant();
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool tma_ok = !orig_idx && !(reinterpret_cast<uintptr_t>(xm3) & 15);  // cp.async.bulk wants 16-byte aligned sources
-    if (variant == 2 && tma_ok) {
-        // one resident wave of the ring kernel: NS stages of two chunks per warp in dynamic shared memory
-        static int ring_resident[2] = {0, 0};
+    if (variant >= 2 && tma_ok) {
+        // one resident wave of the ring kernel: NS stages of CH chunks per warp in dynamic shared memory
+        static int ring_resident[2][8] = {{0}};
         const int q = chunk_qlen ? 1 : 0;
-        void (*kern)(const RunArgs) = q ? score_runs_ring_kernel<true, 4> : score_runs_ring_kernel<false, 3>;
-        const size_t smem = (kThreads / 32) * (q ? 4 * (RING_CH * 768u) : 3 * (RING_CH * 1280u)) + (kThreads / 32) * 4 * sizeof(uint64_t);
-        if (!ring_resident[q]) {
-            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        const RingCfg cfg = q ? ring_config<true>(variant) : ring_config<false>(variant);
+        const size_t smem = (kThreads / 32) * static_cast<size_t>(cfg.ns) * (cfg.ch * (q ? 768u : 1280u) + sizeof(uint64_t));
+        if (!ring_resident[q][variant]) {
+            CUDA_TRY(cudaFuncSetAttribute(cfg.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            CUDA_TRY(cudaFuncSetAttribute(cfg.kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             int r = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, kern, kThreads, smem) != cudaSuccess || r < 1) r = 1;
-            ring_resident[q] = r;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, cfg.kern, kThreads, smem) != cudaSuccess || r < 1) r = 1;
+            ring_resident[q][variant] = r;
         }
-        const uint64_t cap = static_cast<uint64_t>(mmlst_num_sms()) * ring_resident[q];
+        const uint64_t cap = static_cast<uint64_t>(mmlst_num_sms()) * ring_resident[q][variant];
         if (want > cap) want = cap;
         if (want < 1) want = 1;
-        kern<<<static_cast<unsigned>(want), kThreads, smem, st>>>(a);
+        cfg.kern<<<static_cast<unsigned>(want), kThreads, smem, st>>>(a);
         CUDA_TRY(cudaGetLastError());
         return MMLST_OK;
     }

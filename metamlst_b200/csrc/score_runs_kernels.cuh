@@ -383,14 +383,13 @@ __device__ __forceinline__ void reduce_chunk_pf(const RunArgs& a, const Thr& thr
     }
 }
 
-constexpr uint32_t RING_CH = 2;  // chunks per stage
-
-template <bool QC, int NS>
-__global__ void __launch_bounds__(kThreads, QC ? 4 : 3) score_runs_ring_kernel(const RunArgs a) {
+// CH chunks per stage, NS stages per warp, MINB resident CTAs per SM the register budget is set for
+template <bool QC, int NS, int CH, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) score_runs_ring_kernel(const RunArgs a) {
     extern __shared__ __align__(128) uint8_t ring_raw[];
-    constexpr uint32_t AS_B = RING_CH * 512u, QL_B = QC ? 0u : RING_CH * 512u, XM_B = RING_CH * 256u;
+    constexpr uint32_t AS_B = CH * 512u, QL_B = QC ? 0u : CH * 512u, XM_B = CH * 256u;
     constexpr uint32_t STAGE_B = AS_B + QL_B + XM_B;
-    constexpr uint32_t CH_B = STAGE_B / RING_CH;  // bytes one chunk brings
+    constexpr uint32_t CH_B = STAGE_B / CH;  // bytes one chunk brings
     constexpr int NW = kThreads / 32;
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     uint8_t* const my = ring_raw + wid * (NS * STAGE_B);
@@ -412,10 +411,10 @@ __global__ void __launch_bounds__(kThreads, QC ? 4 : 3) score_runs_ring_kernel(c
     const Thr thr = make_thr(a);
 
     if (c0 < c1) {
-        const uint32_t ngroups = static_cast<uint32_t>((c1 - c0 + RING_CH - 1) / RING_CH);
-        auto issue = [&](uint32_t g, int stage) {  // lane 0: request group g (one or two chunks) into `stage`
-            const uint64_t ch = c0 + static_cast<uint64_t>(g) * RING_CH;
-            const uint32_t nch = (c1 - ch < RING_CH) ? static_cast<uint32_t>(c1 - ch) : RING_CH;
+        const uint32_t ngroups = static_cast<uint32_t>((c1 - c0 + CH - 1) / CH);
+        auto issue = [&](uint32_t g, int stage) {  // lane 0: request group g (1..CH chunks) into `stage`
+            const uint64_t ch = c0 + static_cast<uint64_t>(g) * CH;
+            const uint32_t nch = (c1 - ch < CH) ? static_cast<uint32_t>(c1 - ch) : static_cast<uint32_t>(CH);
             uint8_t* st = my + stage * STAGE_B;
             mbar_expect_tx(bars + stage, nch * CH_B);
             bulk_g2s(st, a.as0 + (ch << 8), nch * 512u, bars + stage);
@@ -431,27 +430,26 @@ __global__ void __launch_bounds__(kThreads, QC ? 4 : 3) score_runs_ring_kernel(c
         uint32_t phase = 0;
         int stage = 0;
         for (uint32_t g = 0; g < ngroups; ++g) {
-            const uint64_t ch = c0 + static_cast<uint64_t>(g) * RING_CH;
-            const bool two = ch + 1 < c1;
+            const uint64_t ch = c0 + static_cast<uint64_t>(g) * CH;
+            const uint32_t nch = (c1 - ch < CH) ? static_cast<uint32_t>(c1 - ch) : static_cast<uint32_t>(CH);
             mbar_wait(bars + stage, (phase >> stage) & 1u);
             phase ^= 1u << stage;
             const uint8_t* st = my + stage * STAGE_B;
-            Loaded<false> L0, L1;
-            L0.a8 = *reinterpret_cast<const uint4*>(st + lane * 16u);
-            L0.x8 = *reinterpret_cast<const uint2*>(st + AS_B + QL_B + lane * 8u);
-            if constexpr (QC) { L0.q8 = make_uint4(0, 0, 0, 0); L0.cq = __ldg(a.chunk_qlen + ch); }
-            else { L0.q8 = *reinterpret_cast<const uint4*>(st + AS_B + lane * 16u); L0.cq = 0; }
-            L1 = L0;
-            if (two) {
-                L1.a8 = *reinterpret_cast<const uint4*>(st + 512u + lane * 16u);
-                L1.x8 = *reinterpret_cast<const uint2*>(st + AS_B + QL_B + 256u + lane * 8u);
-                if constexpr (QC) L1.cq = __ldg(a.chunk_qlen + ch + 1);
-                else L1.q8 = *reinterpret_cast<const uint4*>(st + AS_B + 512u + lane * 16u);
+#pragma unroll
+            for (uint32_t k = 0; k < static_cast<uint32_t>(CH); ++k) {
+                if (k < nch) {  // warp-uniform
+                    Loaded<false> L;
+                    L.a8 = *reinterpret_cast<const uint4*>(st + k * 512u + lane * 16u);
+                    L.x8 = *reinterpret_cast<const uint2*>(st + AS_B + QL_B + k * 256u + lane * 8u);
+                    if constexpr (QC) { L.q8 = make_uint4(0, 0, 0, 0); L.cq = __ldg(a.chunk_qlen + ch + k); }
+                    else { L.q8 = *reinterpret_cast<const uint4*>(st + AS_B + k * 512u + lane * 16u); L.cq = 0; }
+                    if (k + 1u == nch) {
+                        __syncwarp();  // every lane has the stage's last records in registers: the stage may be refilled
+                        if (lane == 0 && g + NS < ngroups) issue(g + NS, stage);
+                    }
+                    reduce_chunk_pf<QC>(a, thr, w, L, static_cast<uint32_t>((ch + k) << 8), lane, tot, ign);
+                }
             }
-            __syncwarp();  // every lane has its records in registers: the stage may be refilled
-            if (lane == 0 && g + NS < ngroups) issue(g + NS, stage);
-            reduce_chunk_pf<QC>(a, thr, w, L0, static_cast<uint32_t>(ch << 8), lane, tot, ign);
-            if (two) reduce_chunk_pf<QC>(a, thr, w, L1, static_cast<uint32_t>((ch + 1) << 8), lane, tot, ign);
             stage = (stage + 1 == NS) ? 0 : stage + 1;
         }
         if (lane == 0 && w.al) flush_run(a, w.key, w.s, w.c, w.mn);
@@ -463,6 +461,25 @@ __global__ void __launch_bounds__(kThreads, QC ? 4 : 3) score_runs_ring_kernel(c
     if (lane == 0 && tot) {
         atomicAdd(a.counters + 0, static_cast<unsigned long long>(tot));
         atomicAdd(a.counters + 1, static_cast<unsigned long long>(ign));
+    }
+}
+
+// the ring configurations a launch can ask for (variant 2..5): {chunks per stage, stages, CTAs per SM}
+struct RingCfg { void (*kern)(const RunArgs); uint32_t ch, ns; };
+template <bool QC>
+inline RingCfg ring_config(int variant) {
+    if constexpr (QC) {  // 768 B per chunk
+        switch (variant) {
+            case 3: return {score_runs_ring_kernel<true, 3, 4, 3>, 4, 3};   // 72 KB per CTA
+            case 4: return {score_runs_ring_kernel<true, 2, 8, 2>, 8, 2};   // 96 KB
+            case 5: return {score_runs_ring_kernel<true, 2, 4, 4>, 4, 2};   // 48 KB
+            default: return {score_runs_ring_kernel<true, 4, 2, 4>, 2, 4};  // 48 KB
+        }
+    } else {  // 1280 B per chunk
+        switch (variant) {
+            case 3: case 4: case 5: return {score_runs_ring_kernel<false, 2, 4, 2>, 4, 2};  // 80 KB
+            default: return {score_runs_ring_kernel<false, 3, 2, 3>, 2, 3};                  // 60 KB
+        }
     }
 }
 

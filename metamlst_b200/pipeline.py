@@ -373,7 +373,7 @@ class DevicePipeline:
         pipes = [self] + ([alt] if alt is not None else [])
         out: Dict[str, float] = {}
         want = None
-        for v in (0, 1, 2):
+        for v in (0, 1, 2, 3, 4, 5):
             self.lib.mmlst_set_score_variant(v)
             self.reset_tables()
             self._score_call()
@@ -393,6 +393,33 @@ class DevicePipeline:
             out[str(v)] = a.elapsed_time(b) / reps
         for p in pipes:
             p._clean = False
+        return out
+
+    def time_score_half(self, reps: int = 20, alt: Optional["DevicePipeline"] = None) -> Dict[str, float]:
+        """The score kernel over the first half / quarter of the resident stream (timing only; the tables are garbage
+        afterwards): t(n) at three sizes separates the per-launch fixed cost from the streaming rate."""
+        pipes = [self] + ([alt] if alt is not None else [])
+        out: Dict[str, float] = {}
+        full = [p.s.as0 for p in pipes]
+        n = int(self.s.as0.shape[0])
+        try:
+            for frac in (1, 2, 4):
+                m = (n // frac) & ~255
+                for p, f in zip(pipes, full):
+                    p.s.as0 = f[:m]
+                for p in pipes:
+                    p._score_call()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for i in range(reps):
+                    pipes[i % len(pipes)]._score_call()
+                b.record()
+                b.synchronize()
+                out["1/%d" % frac] = a.elapsed_time(b) / reps
+        finally:
+            for p, f in zip(pipes, full):
+                p.s.as0 = f
+                p._clean = False
         return out
 
     def _launch_one(self, name: str):

@@ -68,7 +68,7 @@ static void launch(K kern, unsigned grid, unsigned block, const RunArgs& a) {
     }
 }
 
-// form: 0 registers, 1 registers + software pipeline, 2 shared-memory ring (the product's launcher takes form 0 when a
+// form: 0 registers, 1 registers + software pipeline, 2..5 shared-memory ring configurations (the product's launcher takes form 0 when a
 // file-order index is present; here that combination is refused)
 extern "C" int simt_score_runs(int form, unsigned grid, const uint32_t* run_tid, const uint32_t* run_start, uint32_t n_runs, const uint32_t* chunk_run,
                                const int16_t* as0, const uint8_t* xm3, const uint16_t* qlen, const uint16_t* chunk_qlen, const uint32_t* orig_idx,
@@ -77,10 +77,9 @@ extern "C" int simt_score_runs(int form, unsigned grid, const uint32_t* run_tid,
     RunArgs a{run_tid, run_start, chunk_run, n_runs, as0, xm3, qlen, orig_idx, chunk_qlen, n_rec, idx_base, allow, n_ref, minscore, max_xm,
               min_read_len, reinterpret_cast<long long*>(sum_as), n_hit, first_idx, reinterpret_cast<unsigned long long*>(counters)};
     const bool qc = chunk_qlen != nullptr, oi = orig_idx != nullptr;
-    if (form == 2) {
+    if (form >= 2 && form <= 5) {
         if (oi) return -1;
-        if (qc) launch(score_runs_ring_kernel<true, 4>, grid, kThreads, a);
-        else launch(score_runs_ring_kernel<false, 3>, grid, kThreads, a);
+        launch((qc ? ring_config<true>(form) : ring_config<false>(form)).kern, grid, kThreads, a);
         return 0;
     }
     if (form != 0 && form != 1) return -1;
