@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--score-variant", default="default", choices=["default", "0", "1", "2", "3", "4", "5", "auto"],
                     help="form of the run-length score kernel (mmlst_set_score_variant): 0 registers, 1 registers + software pipeline, 2 shared-memory "
                          "ring fed by TMA bulk copies; 'default' = the library's; 'auto' = time all three on the workload first and keep the fastest")
+    ap.add_argument("--score-l2-hints", default="default", choices=["default", "0", "1"], help="ring forms of the score kernel: L2 residency hints "
+                    "(mmlst_set_score_l2_hints)")
     ap.add_argument("--max-depth", type=int, default=8000, help="htslib pileup depth cap of the main workload (0 = uncapped; profiling aid)")
     return ap.parse_args()
 
@@ -277,7 +279,10 @@ def main():
     native.lib()  # fail loudly if the CUDA library is missing
     if args.score_variant in ("0", "1", "2", "3", "4", "5"):
         native.lib().mmlst_set_score_variant(int(args.score_variant))
+    if args.score_l2_hints in ("0", "1"):
+        native.lib().mmlst_set_score_l2_hints(int(args.score_l2_hints))
     score_variant = native.lib().mmlst_set_score_variant(-1)
+    score_hints = native.lib().mmlst_set_score_l2_hints(-1)
     peak, peak_src = peaks()
     if args.only_hamming:
         emit({"hamming": extra_hamming(device, peak)})
@@ -325,15 +330,13 @@ def main():
     if args.score_variant == "auto" and pipe.use_runs:
         # every form on this workload (equal tables asserted), fastest kept for everything that follows; with N>1 the ranks agree on rank 0's choice
         variants_ms = pipe.time_score_variants(20, alt=pipes[1])
-        if os.environ.get("MMLST_BENCH_SCALING"):  # diagnostic: fixed cost vs streaming rate of each form
-            for v in sorted(variants_ms):
-                native.lib().mmlst_set_score_variant(int(v))
-                sys.stderr.write("score form %s, records 1/1 1/2 1/4: %r\n" % (v, pipe.time_score_half(20, alt=pipes[1])))
-        pick = torch.tensor([int(min(variants_ms, key=variants_ms.get))], dtype=torch.int32, device=device)
+        best = min(variants_ms, key=variants_ms.get)
+        pick = torch.tensor([int(best[0]), 1 if best.endswith("h") else 0], dtype=torch.int32, device=device)
         if world > 1:
             torch.distributed.broadcast(pick, 0)
-        score_variant = int(pick.item())
+        score_variant, score_hints = int(pick[0].item()), int(pick[1].item())
         native.lib().mmlst_set_score_variant(score_variant)
+        native.lib().mmlst_set_score_l2_hints(score_hints)
     results = []
     for p in pipes:
         for _ in range(max(args.warmup, 3)):
@@ -406,10 +409,11 @@ def main():
     del flush
     # the other forms of the score kernel on the same two samples (same tables out, checked), for the record
     if variants_ms is None:
-        variants_ms = {str(score_variant): kms["score"]}
+        variants_ms = {str(score_variant) + ("h" if score_hints and score_variant >= 2 else ""): kms["score"]}
         if not args.no_extras and pipe.use_runs:
             variants_ms = pipe.time_score_variants(20, alt=pipes[1])
             native.lib().mmlst_set_score_variant(score_variant)
+            native.lib().mmlst_set_score_l2_hints(score_hints)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(10):
@@ -434,7 +438,7 @@ def main():
     rooflines = {
         "score": {"bound": "hbm", "achieved": score_bytes / kms["score"] / 1e6, "peak": peak, "unit": "GB/s", "frac": score_bytes / kms["score"] / 1e6 / peak,
                   "traffic": ncu_traffic("score_runs_qc" if pipe.use_qc else "score_runs" if pipe.use_runs else "score") if args.reads == 10_000_000 and args.k == 4 else None,
-                  "ms": kms["score"], "algorithmic_bytes": score_bytes, "kernel_form": score_variant, "ms_by_kernel_form": variants_ms,
+                  "ms": kms["score"], "algorithmic_bytes": score_bytes, "kernel_form": score_variant, "l2_hints": score_hints, "ms_by_kernel_form": variants_ms,
                   "stream_form": "run-length + len(SEQ) per 256-record chunk: as0 i16 + xm3 u8 per record, allele id per run (3 B/record; lossless: every "
                                  "chunk of this sample has one read length; SURVEY 8d's explicit form is 9 B/record)" if pipe.use_qc else
                                  "run-length: as0 i16 + xm3 u8 + qlen u16 per record, allele id per run (5 B/record; SURVEY 8d's explicit-id form is 9 B/record)"

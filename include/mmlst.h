@@ -120,6 +120,11 @@ int mmlst_score_runs_qc_dev(const uint32_t* run_tid, const uint32_t* run_start, 
  * MMLST_SCORE_VARIANT presets it. */
 #define MMLST_SCORE_VARIANT_DEFAULT 0
 int mmlst_set_score_variant(int variant);
+/* Ring forms only: L2 residency hints (score stream evict-first; run arrays, allow[] and chunk_qlen[] evict-last, so that the
+ * small tables every warp starts from survive in the L2 from one launch to the next).  1 = on, 0 = off, other = query;
+ * returns the previous value.  MMLST_SCORE_L2_HINTS presets it.  Results do not depend on it. */
+#define MMLST_SCORE_L2_HINTS_DEFAULT 0
+int mmlst_set_score_l2_hints(int on);
 /* qlen[i] of every record back from the per-chunk form (device; the coverage kernel takes it per record) */
 int mmlst_expand_chunk_qlen_dev(const uint16_t* chunk_qlen, uint64_t n_rec, uint16_t* qlen, void* stream);
 /* tid[i] of every record back from the run arrays (device; the coverage kernel takes the explicit form) */

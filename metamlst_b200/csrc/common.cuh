@@ -67,6 +67,43 @@ __device__ __forceinline__ uint32_t ld_stream_u1(const void* p) {
     return r;
 }
 
+// ---- L2 residency hints (createpolicy + .L2::cache_hint): a stream read once should not push the small tables read by
+// every warp (run arrays, allow[]) out of the L2 between launches
+__device__ __forceinline__ uint64_t l2_policy(int kind) {  // 0 normal, 1 evict first (streams), 2 evict last (tables)
+    uint64_t p;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ld_stream_u4_hint(const void* p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_stream_u2_hint(const void* p, uint64_t pol) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_table_u32(const uint32_t* p, uint64_t pol) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_table_u16(const uint16_t* p, uint64_t pol) {
+    uint16_t r;
+    asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_table_u8(const uint8_t* p, uint64_t pol) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+
 // ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) into shared memory
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -80,6 +117,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                  : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {

@@ -31,6 +31,20 @@ extern "C" int mmlst_set_score_variant(int v) {
     return prev;
 }
 
+static int g_score_l2_hints = -1;
+static int score_l2_hints() {
+    if (g_score_l2_hints < 0) {
+        const char* e = getenv("MMLST_SCORE_L2_HINTS");
+        g_score_l2_hints = e ? (e[0] == '1') : MMLST_SCORE_L2_HINTS_DEFAULT;
+    }
+    return g_score_l2_hints;
+}
+extern "C" int mmlst_set_score_l2_hints(int on) {
+    const int prev = score_l2_hints();
+    if (on == 0 || on == 1) g_score_l2_hints = on;
+    return prev;
+}
+
 static int score_runs_launch(const uint32_t* run_tid, const uint32_t* run_start, uint32_t n_runs, const uint32_t* chunk_run,
                              const int16_t* as0, const uint8_t* xm3, const uint16_t* qlen, const uint16_t* chunk_qlen, const uint32_t* orig_idx,
                              uint64_t n_rec, uint64_t idx_base, const uint8_t* allow, uint32_t n_ref, int minscore,
@@ -48,7 +62,7 @@ static int score_runs_launch(const uint32_t* run_tid, const uint32_t* run_start,
         return MMLST_E_ARG;
     }
     RunArgs a{run_tid, run_start, chunk_run, n_runs, as0, xm3, qlen, orig_idx, chunk_qlen, n_rec, idx_base, allow, n_ref, minscore, max_xm,
-              min_read_len, reinterpret_cast<long long*>(sum_as), n_hit, first_idx, reinterpret_cast<unsigned long long*>(counters)};
+              min_read_len, reinterpret_cast<long long*>(sum_as), n_hit, first_idx, reinterpret_cast<unsigned long long*>(counters), score_l2_hints()};
     const uint64_t nchunks = n_rec >> 8;
     uint64_t want = (nchunks + 15) / 16;  // CTAs if every warp took two chunks
     const int variant = score_variant();

@@ -16,6 +16,7 @@ struct RunArgs {
     const uint8_t* allow; uint32_t n_ref;
     int minscore, max_xm, min_read_len;
     long long* sum_as; uint32_t* n_hit; uint32_t* first_idx; unsigned long long* counters;
+    int l2_hints;  // ring forms: streams evict-first, run tables / allow[] / chunk_qlen evict-last in the L2
 };
 
 __device__ __forceinline__ void flush_run(const RunArgs& a, uint32_t key, long long s, uint32_t c, uint32_t mn) {
@@ -297,23 +298,23 @@ struct WarpRunPF {
     long long s; uint32_t c, mn;
 };
 
-__device__ __forceinline__ void request_next_run(const RunArgs& a, WarpRunPF& w) {
-    if (w.r + 1u < a.n_runs) { w.nkey = __ldg(a.run_tid + w.r + 1u); w.nend = __ldg(a.run_start + w.r + 2u); }
+__device__ __forceinline__ void request_next_run(const RunArgs& a, WarpRunPF& w, uint64_t pol) {
+    if (w.r + 1u < a.n_runs) { w.nkey = ld_table_u32(a.run_tid + w.r + 1u, pol); w.nend = ld_table_u32(a.run_start + w.r + 2u, pol); }
     else { w.nkey = 0xffffffffu; w.nend = 0xffffffffu; }
 }
-__device__ __forceinline__ void open_run_pf(const RunArgs& a, WarpRunPF& w, uint32_t r) {
+__device__ __forceinline__ void open_run_pf(const RunArgs& a, WarpRunPF& w, uint32_t r, uint64_t pol) {
     w.r = r;
-    if (r < a.n_runs) { w.key = __ldg(a.run_tid + r); w.end = __ldg(a.run_start + r + 1u); }
+    if (r < a.n_runs) { w.key = ld_table_u32(a.run_tid + r, pol); w.end = ld_table_u32(a.run_start + r + 1u, pol); }
     else { w.key = 0xffffffffu; w.end = 0xffffffffu; }
-    request_next_run(a, w);
-    w.al = (w.key < a.n_ref) && a.allow[w.key];
+    request_next_run(a, w, pol);
+    w.al = (w.key < a.n_ref) && ld_table_u8(a.allow + w.key, pol);
     w.s = 0; w.c = 0; w.mn = 0xffffffffu;
 }
-__device__ __forceinline__ void next_run_pf(const RunArgs& a, WarpRunPF& w, uint32_t lane) {
+__device__ __forceinline__ void next_run_pf(const RunArgs& a, WarpRunPF& w, uint32_t lane, uint64_t pol) {
     if (lane == 0 && w.al) flush_run(a, w.key, w.s, w.c, w.mn);
     w.r += 1u; w.key = w.nkey; w.end = w.nend;  // past the last run: key = end = 0xffffffff, nothing is counted
-    request_next_run(a, w);
-    w.al = (w.key < a.n_ref) && a.allow[w.key];
+    request_next_run(a, w, pol);
+    w.al = (w.key < a.n_ref) && ld_table_u8(a.allow + w.key, pol);
     w.s = 0; w.c = 0; w.mn = 0xffffffffu;
 }
 
@@ -339,7 +340,7 @@ __device__ __forceinline__ uint32_t first_pass_index(uint32_t p_lo, uint32_t p_h
 
 template <bool QC>
 __device__ __forceinline__ void reduce_chunk_pf(const RunArgs& a, const Thr& thr, WarpRunPF& w, const Loaded<false>& L, uint32_t base, uint32_t lane,
-                                                uint32_t& tot, uint32_t& ign) {
+                                                uint32_t& tot, uint32_t& ign, uint64_t pol) {
     constexpr uint32_t R = 8;
     const uint32_t idx0 = static_cast<uint32_t>(a.idx_base) + base + (lane << 3);
     uint32_t p_lo, p_hi;
@@ -357,7 +358,7 @@ __device__ __forceinline__ void reduce_chunk_pf(const RunArgs& a, const Thr& thr
             // chunks cannot lower its first index
             if (w.mn == 0xffffffffu) w.mn = __reduce_min_sync(FULL, first_pass_index(p_lo, p_hi, idx0));
         }
-        if (chunk_end == w.end) next_run_pf(a, w, lane);
+        if (chunk_end == w.end) next_run_pf(a, w, lane, pol);
         return;
     }
     const int lane0 = static_cast<int>(lane << 3);
@@ -378,7 +379,7 @@ __device__ __forceinline__ void reduce_chunk_pf(const RunArgs& a, const Thr& thr
             w.c += __reduce_add_sync(FULL, c);
             if (w.mn == 0xffffffffu) w.mn = __reduce_min_sync(FULL, first_pass_index(p_lo & in_lo, p_hi & in_hi, idx0));
         }
-        if (hi == w.end) next_run_pf(a, w, lane);
+        if (hi == w.end) next_run_pf(a, w, lane, pol);
         lo = hi;
     }
 }
@@ -409,6 +410,7 @@ __global__ void __launch_bounds__(kThreads, MINB) score_runs_ring_kernel(const R
     const uint64_t c1 = (c0 + per < nchunks) ? c0 + per : nchunks;
     uint32_t tot = 0, ign = 0;
     const Thr thr = make_thr(a);
+    const uint64_t pol_s = l2_policy(a.l2_hints ? 1 : 0), pol_t = l2_policy(a.l2_hints ? 2 : 0);
 
     if (c0 < c1) {
         const uint32_t ngroups = static_cast<uint32_t>((c1 - c0 + CH - 1) / CH);
@@ -417,16 +419,23 @@ __global__ void __launch_bounds__(kThreads, MINB) score_runs_ring_kernel(const R
             const uint32_t nch = (c1 - ch < CH) ? static_cast<uint32_t>(c1 - ch) : static_cast<uint32_t>(CH);
             uint8_t* st = my + stage * STAGE_B;
             mbar_expect_tx(bars + stage, nch * CH_B);
-            bulk_g2s(st, a.as0 + (ch << 8), nch * 512u, bars + stage);
-            if constexpr (!QC) bulk_g2s(st + AS_B, a.qlen + (ch << 8), nch * 512u, bars + stage);
-            bulk_g2s(st + AS_B + QL_B, a.xm3 + (ch << 8), nch * 256u, bars + stage);
+            bulk_g2s_hint(st, a.as0 + (ch << 8), nch * 512u, bars + stage, pol_s);
+            if constexpr (!QC) bulk_g2s_hint(st + AS_B, a.qlen + (ch << 8), nch * 512u, bars + stage, pol_s);
+            bulk_g2s_hint(st + AS_B + QL_B, a.xm3 + (ch << 8), nch * 256u, bars + stage, pol_s);
         };
         if (lane == 0) {
             const uint32_t pre = ngroups < static_cast<uint32_t>(NS) ? ngroups : static_cast<uint32_t>(NS);
             for (uint32_t g = 0; g < pre; ++g) issue(g, static_cast<int>(g));
         }
+        // len(SEQ) of the warp's first 64 chunks in two registers per lane (one load each instead of one per chunk on the
+        // critical path of every chunk); later chunks, if any, are looked up one by one
+        uint32_t cq_a = 0, cq_b = 0;
+        if constexpr (QC) {
+            if (c0 + lane < c1) cq_a = ld_table_u16(a.chunk_qlen + c0 + lane, pol_t);
+            if (c0 + 32u + lane < c1) cq_b = ld_table_u16(a.chunk_qlen + c0 + 32u + lane, pol_t);
+        }
         WarpRunPF w;
-        open_run_pf(a, w, __ldg(a.chunk_run + c0));  // dependent lookups run under the first copies
+        open_run_pf(a, w, ld_table_u32(a.chunk_run + c0, pol_t), pol_t);  // dependent lookups run under the first copies
         uint32_t phase = 0;
         int stage = 0;
         for (uint32_t g = 0; g < ngroups; ++g) {
@@ -441,13 +450,18 @@ __global__ void __launch_bounds__(kThreads, MINB) score_runs_ring_kernel(const R
                     Loaded<false> L;
                     L.a8 = *reinterpret_cast<const uint4*>(st + k * 512u + lane * 16u);
                     L.x8 = *reinterpret_cast<const uint2*>(st + AS_B + QL_B + k * 256u + lane * 8u);
-                    if constexpr (QC) { L.q8 = make_uint4(0, 0, 0, 0); L.cq = __ldg(a.chunk_qlen + ch + k); }
-                    else { L.q8 = *reinterpret_cast<const uint4*>(st + AS_B + k * 512u + lane * 16u); L.cq = 0; }
+                    if constexpr (QC) {
+                        L.q8 = make_uint4(0, 0, 0, 0);
+                        const uint32_t j = g * static_cast<uint32_t>(CH) + k;  // chunk number inside the warp's range (warp-uniform)
+                        L.cq = j < 64u ? __shfl_sync(FULL, j < 32u ? cq_a : cq_b, j & 31u) : ld_table_u16(a.chunk_qlen + ch + k, pol_t);
+                    } else {
+                        L.q8 = *reinterpret_cast<const uint4*>(st + AS_B + k * 512u + lane * 16u); L.cq = 0;
+                    }
                     if (k + 1u == nch) {
                         __syncwarp();  // every lane has the stage's last records in registers: the stage may be refilled
                         if (lane == 0 && g + NS < ngroups) issue(g + NS, stage);
                     }
-                    reduce_chunk_pf<QC>(a, thr, w, L, static_cast<uint32_t>((ch + k) << 8), lane, tot, ign);
+                    reduce_chunk_pf<QC>(a, thr, w, L, static_cast<uint32_t>((ch + k) << 8), lane, tot, ign, pol_t);
                 }
             }
             stage = (stage + 1 == NS) ? 0 : stage + 1;

@@ -369,19 +369,21 @@ class DevicePipeline:
     def time_score_variants(self, reps: int = 20, alt: Optional["DevicePipeline"] = None) -> Dict[str, float]:
         """Average device time (ms) of the run-length score kernel in each of its forms (mmlst_set_score_variant), timed like
         time_kernels() times it (back to back, alternating two samples, cold L2); every form must leave the same tables.
-        Leaves the library on the last form tried: the caller restores its own."""
+        Keys: the form, plus 'h' when the L2 residency hints are on.  Leaves the library on the last form tried: the caller restores its own."""
         pipes = [self] + ([alt] if alt is not None else [])
         out: Dict[str, float] = {}
         want = None
-        for v in (0, 1, 2, 3, 4, 5):
+        for key in ("0", "1", "2", "3", "4", "5", "2h", "3h", "4h", "5h"):  # "h": ring form with the L2 residency hints
+            v = int(key[0])
             self.lib.mmlst_set_score_variant(v)
+            self.lib.mmlst_set_score_l2_hints(1 if key.endswith("h") else 0)
             self.reset_tables()
             self._score_call()
             torch.cuda.current_stream(self.dev).synchronize()
             got = [self.zscore.clone(), self.first_idx.clone()]
             if want is None:
                 want = got
-            assert all(torch.equal(a, b) for a, b in zip(got, want)), "score kernel form %d disagrees with form 0" % v
+            assert all(torch.equal(a, b) for a, b in zip(got, want)), "score kernel form %s disagrees with form 0" % key
             for p in pipes:
                 p._score_call()  # warm
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -390,7 +392,7 @@ class DevicePipeline:
                 pipes[i % len(pipes)]._score_call()
             b.record()
             b.synchronize()
-            out[str(v)] = a.elapsed_time(b) / reps
+            out[key] = a.elapsed_time(b) / reps
         for p in pipes:
             p._clean = False
         return out

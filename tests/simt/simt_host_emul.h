@@ -95,6 +95,21 @@ inline uint4 ld_stream_u4(const void* p) { uint4 r; memcpy(&r, p, 16); return r;
 inline uint2 ld_stream_u2(const void* p) { uint2 r; memcpy(&r, p, 8); return r; }
 inline uint32_t ld_stream_u1(const void* p) { uint32_t r; memcpy(&r, p, 4); return r; }
 
+inline uint64_t l2_policy(int kind) { return static_cast<uint64_t>(kind); }
+inline uint4 ld_stream_u4_hint(const void* p, uint64_t) { return ld_stream_u4(p); }
+inline uint2 ld_stream_u2_hint(const void* p, uint64_t) { return ld_stream_u2(p); }
+inline uint32_t ld_table_u32(const uint32_t* p, uint64_t) { return *p; }
+inline uint32_t ld_table_u16(const uint16_t* p, uint64_t) { return *p; }
+inline uint32_t ld_table_u8(const uint8_t* p, uint64_t) { return *p; }
+inline uint32_t __shfl_sync(uint32_t, uint32_t v, uint32_t src) {
+    WarpEmu* w = t_warp;
+    w->slot[threadIdx.x & 31u] = v;
+    w->rv.wait();
+    const uint32_t r = static_cast<uint32_t>(w->slot[src & 31u]);
+    w->rv.wait();
+    return r;
+}
+
 // ---- mbarrier + bulk copy.  The 64-bit barrier word holds: completed phases (low 32 bits are enough here) -- the
 // arrival count is 1 in every kernel that uses these, so a phase completes when its expected bytes have landed.
 struct MbarEmu { std::atomic<uint32_t> phases; std::atomic<int64_t> tx; std::atomic<uint32_t> arrived; uint32_t count; };
@@ -121,4 +136,5 @@ inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) 
     m->tx.fetch_sub(bytes);
     mbar_try_complete(m);
 }
+inline void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t) { bulk_g2s(dst, src, bytes, bar); }
 void mbar_wait(uint64_t* bar, uint32_t parity);  // blocks until the phase of that parity has completed; aborts on a deadlock

@@ -75,7 +75,7 @@ extern "C" int simt_score_runs(int form, unsigned grid, const uint32_t* run_tid,
                                uint64_t n_rec, uint64_t idx_base, const uint8_t* allow, uint32_t n_ref, int minscore, int max_xm, int min_read_len,
                                int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, uint64_t* counters) {
     RunArgs a{run_tid, run_start, chunk_run, n_runs, as0, xm3, qlen, orig_idx, chunk_qlen, n_rec, idx_base, allow, n_ref, minscore, max_xm,
-              min_read_len, reinterpret_cast<long long*>(sum_as), n_hit, first_idx, reinterpret_cast<unsigned long long*>(counters)};
+              min_read_len, reinterpret_cast<long long*>(sum_as), n_hit, first_idx, reinterpret_cast<unsigned long long*>(counters), 1};
     const bool qc = chunk_qlen != nullptr, oi = orig_idx != nullptr;
     if (form >= 2 && form <= 5) {
         if (oi) return -1;
