@@ -70,10 +70,12 @@ static int score_runs_launch(const uint32_t* run_tid, const uint32_t* run_start,
     const bool tma_ok = !orig_idx && !(reinterpret_cast<uintptr_t>(xm3) & 15);  // cp.async.bulk wants 16-byte aligned sources
     if (variant >= 2 && tma_ok) {
         // one resident wave of the ring kernel: NS stages of CH chunks per warp in dynamic shared memory
-        static int ring_resident[2][8] = {{0}};
-        const int q = chunk_qlen ? 1 : 0;
-        const RingCfg cfg = q ? ring_config<true>(variant) : ring_config<false>(variant);
-        const size_t smem = (kThreads / 32) * static_cast<size_t>(cfg.ns) * (cfg.ch * (q ? 768u : 1280u) + sizeof(uint64_t));
+        static int ring_resident[4][8] = {{0}};
+        const int hint = a.l2_hints ? 1 : 0;
+        const int q = (chunk_qlen ? 1 : 0) + 2 * hint;
+        const RingCfg cfg = chunk_qlen ? (hint ? ring_config<true, true>(variant) : ring_config<true, false>(variant))
+                                       : (hint ? ring_config<false, true>(variant) : ring_config<false, false>(variant));
+        const size_t smem = (kThreads / 32) * static_cast<size_t>(cfg.ns) * (cfg.ch * (chunk_qlen ? 768u : 1280u) + sizeof(uint64_t));
         if (!ring_resident[q][variant]) {
             CUDA_TRY(cudaFuncSetAttribute(cfg.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             CUDA_TRY(cudaFuncSetAttribute(cfg.kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

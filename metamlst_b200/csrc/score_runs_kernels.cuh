@@ -298,23 +298,36 @@ struct WarpRunPF {
     long long s; uint32_t c, mn;
 };
 
+// table lookups of the ring forms: HINT = through the evict-last L2 policy `pol`, else the plain read-only path
+template <bool HINT> __device__ __forceinline__ uint32_t tab_u32(const uint32_t* p, uint64_t pol) {
+    if constexpr (HINT) return ld_table_u32(p, pol); else return __ldg(p);
+}
+template <bool HINT> __device__ __forceinline__ uint32_t tab_u16(const uint16_t* p, uint64_t pol) {
+    if constexpr (HINT) return ld_table_u16(p, pol); else return __ldg(p);
+}
+template <bool HINT> __device__ __forceinline__ uint32_t tab_u8(const uint8_t* p, uint64_t pol) {
+    if constexpr (HINT) return ld_table_u8(p, pol); else return *p;
+}
+template <bool HINT>
 __device__ __forceinline__ void request_next_run(const RunArgs& a, WarpRunPF& w, uint64_t pol) {
-    if (w.r + 1u < a.n_runs) { w.nkey = ld_table_u32(a.run_tid + w.r + 1u, pol); w.nend = ld_table_u32(a.run_start + w.r + 2u, pol); }
+    if (w.r + 1u < a.n_runs) { w.nkey = tab_u32<HINT>(a.run_tid + w.r + 1u, pol); w.nend = tab_u32<HINT>(a.run_start + w.r + 2u, pol); }
     else { w.nkey = 0xffffffffu; w.nend = 0xffffffffu; }
 }
+template <bool HINT>
 __device__ __forceinline__ void open_run_pf(const RunArgs& a, WarpRunPF& w, uint32_t r, uint64_t pol) {
     w.r = r;
-    if (r < a.n_runs) { w.key = ld_table_u32(a.run_tid + r, pol); w.end = ld_table_u32(a.run_start + r + 1u, pol); }
+    if (r < a.n_runs) { w.key = tab_u32<HINT>(a.run_tid + r, pol); w.end = tab_u32<HINT>(a.run_start + r + 1u, pol); }
     else { w.key = 0xffffffffu; w.end = 0xffffffffu; }
-    request_next_run(a, w, pol);
-    w.al = (w.key < a.n_ref) && ld_table_u8(a.allow + w.key, pol);
+    request_next_run<HINT>(a, w, pol);
+    w.al = (w.key < a.n_ref) && tab_u8<HINT>(a.allow + w.key, pol);
     w.s = 0; w.c = 0; w.mn = 0xffffffffu;
 }
+template <bool HINT>
 __device__ __forceinline__ void next_run_pf(const RunArgs& a, WarpRunPF& w, uint32_t lane, uint64_t pol) {
     if (lane == 0 && w.al) flush_run(a, w.key, w.s, w.c, w.mn);
     w.r += 1u; w.key = w.nkey; w.end = w.nend;  // past the last run: key = end = 0xffffffff, nothing is counted
-    request_next_run(a, w, pol);
-    w.al = (w.key < a.n_ref) && ld_table_u8(a.allow + w.key, pol);
+    request_next_run<HINT>(a, w, pol);
+    w.al = (w.key < a.n_ref) && tab_u8<HINT>(a.allow + w.key, pol);
     w.s = 0; w.c = 0; w.mn = 0xffffffffu;
 }
 
@@ -338,7 +351,7 @@ __device__ __forceinline__ uint32_t first_pass_index(uint32_t p_lo, uint32_t p_h
     return (p_lo | p_hi) ? idx0 + k : 0xffffffffu;
 }
 
-template <bool QC>
+template <bool QC, bool HINT>
 __device__ __forceinline__ void reduce_chunk_pf(const RunArgs& a, const Thr& thr, WarpRunPF& w, const Loaded<false>& L, uint32_t base, uint32_t lane,
                                                 uint32_t& tot, uint32_t& ign, uint64_t pol) {
     constexpr uint32_t R = 8;
@@ -358,7 +371,7 @@ __device__ __forceinline__ void reduce_chunk_pf(const RunArgs& a, const Thr& thr
             // chunks cannot lower its first index
             if (w.mn == 0xffffffffu) w.mn = __reduce_min_sync(FULL, first_pass_index(p_lo, p_hi, idx0));
         }
-        if (chunk_end == w.end) next_run_pf(a, w, lane, pol);
+        if (chunk_end == w.end) next_run_pf<HINT>(a, w, lane, pol);
         return;
     }
     const int lane0 = static_cast<int>(lane << 3);
@@ -379,13 +392,13 @@ __device__ __forceinline__ void reduce_chunk_pf(const RunArgs& a, const Thr& thr
             w.c += __reduce_add_sync(FULL, c);
             if (w.mn == 0xffffffffu) w.mn = __reduce_min_sync(FULL, first_pass_index(p_lo & in_lo, p_hi & in_hi, idx0));
         }
-        if (hi == w.end) next_run_pf(a, w, lane, pol);
+        if (hi == w.end) next_run_pf<HINT>(a, w, lane, pol);
         lo = hi;
     }
 }
 
 // CH chunks per stage, NS stages per warp, MINB resident CTAs per SM the register budget is set for
-template <bool QC, int NS, int CH, int MINB>
+template <bool QC, int NS, int CH, int MINB, bool HINT>
 __global__ void __launch_bounds__(kThreads, MINB) score_runs_ring_kernel(const RunArgs a) {
     extern __shared__ __align__(128) uint8_t ring_raw[];
     constexpr uint32_t AS_B = CH * 512u, QL_B = QC ? 0u : CH * 512u, XM_B = CH * 256u;
@@ -410,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, MINB) score_runs_ring_kernel(const R
     const uint64_t c1 = (c0 + per < nchunks) ? c0 + per : nchunks;
     uint32_t tot = 0, ign = 0;
     const Thr thr = make_thr(a);
-    const uint64_t pol_s = l2_policy(a.l2_hints ? 1 : 0), pol_t = l2_policy(a.l2_hints ? 2 : 0);
+    const uint64_t pol_s = HINT ? l2_policy(1) : 0ull, pol_t = HINT ? l2_policy(2) : 0ull;  // streams evict-first, tables evict-last
 
     if (c0 < c1) {
         const uint32_t ngroups = static_cast<uint32_t>((c1 - c0 + CH - 1) / CH);
@@ -419,23 +432,22 @@ __global__ void __launch_bounds__(kThreads, MINB) score_runs_ring_kernel(const R
             const uint32_t nch = (c1 - ch < CH) ? static_cast<uint32_t>(c1 - ch) : static_cast<uint32_t>(CH);
             uint8_t* st = my + stage * STAGE_B;
             mbar_expect_tx(bars + stage, nch * CH_B);
-            bulk_g2s_hint(st, a.as0 + (ch << 8), nch * 512u, bars + stage, pol_s);
-            if constexpr (!QC) bulk_g2s_hint(st + AS_B, a.qlen + (ch << 8), nch * 512u, bars + stage, pol_s);
-            bulk_g2s_hint(st + AS_B + QL_B, a.xm3 + (ch << 8), nch * 256u, bars + stage, pol_s);
+            if constexpr (HINT) {
+                bulk_g2s_hint(st, a.as0 + (ch << 8), nch * 512u, bars + stage, pol_s);
+                if constexpr (!QC) bulk_g2s_hint(st + AS_B, a.qlen + (ch << 8), nch * 512u, bars + stage, pol_s);
+                bulk_g2s_hint(st + AS_B + QL_B, a.xm3 + (ch << 8), nch * 256u, bars + stage, pol_s);
+            } else {
+                bulk_g2s(st, a.as0 + (ch << 8), nch * 512u, bars + stage);
+                if constexpr (!QC) bulk_g2s(st + AS_B, a.qlen + (ch << 8), nch * 512u, bars + stage);
+                bulk_g2s(st + AS_B + QL_B, a.xm3 + (ch << 8), nch * 256u, bars + stage);
+            }
         };
         if (lane == 0) {
             const uint32_t pre = ngroups < static_cast<uint32_t>(NS) ? ngroups : static_cast<uint32_t>(NS);
             for (uint32_t g = 0; g < pre; ++g) issue(g, static_cast<int>(g));
         }
-        // len(SEQ) of the warp's first 64 chunks in two registers per lane (one load each instead of one per chunk on the
-        // critical path of every chunk); later chunks, if any, are looked up one by one
-        uint32_t cq_a = 0, cq_b = 0;
-        if constexpr (QC) {
-            if (c0 + lane < c1) cq_a = ld_table_u16(a.chunk_qlen + c0 + lane, pol_t);
-            if (c0 + 32u + lane < c1) cq_b = ld_table_u16(a.chunk_qlen + c0 + 32u + lane, pol_t);
-        }
         WarpRunPF w;
-        open_run_pf(a, w, ld_table_u32(a.chunk_run + c0, pol_t), pol_t);  // dependent lookups run under the first copies
+        open_run_pf<HINT>(a, w, tab_u32<HINT>(a.chunk_run + c0, pol_t), pol_t);  // dependent lookups run under the first copies
         uint32_t phase = 0;
         int stage = 0;
         for (uint32_t g = 0; g < ngroups; ++g) {
@@ -450,18 +462,13 @@ __global__ void __launch_bounds__(kThreads, MINB) score_runs_ring_kernel(const R
                     Loaded<false> L;
                     L.a8 = *reinterpret_cast<const uint4*>(st + k * 512u + lane * 16u);
                     L.x8 = *reinterpret_cast<const uint2*>(st + AS_B + QL_B + k * 256u + lane * 8u);
-                    if constexpr (QC) {
-                        L.q8 = make_uint4(0, 0, 0, 0);
-                        const uint32_t j = g * static_cast<uint32_t>(CH) + k;  // chunk number inside the warp's range (warp-uniform)
-                        L.cq = j < 64u ? __shfl_sync(FULL, j < 32u ? cq_a : cq_b, j & 31u) : ld_table_u16(a.chunk_qlen + ch + k, pol_t);
-                    } else {
-                        L.q8 = *reinterpret_cast<const uint4*>(st + AS_B + k * 512u + lane * 16u); L.cq = 0;
-                    }
+                    if constexpr (QC) { L.q8 = make_uint4(0, 0, 0, 0); L.cq = tab_u16<HINT>(a.chunk_qlen + ch + k, pol_t); }
+                    else { L.q8 = *reinterpret_cast<const uint4*>(st + AS_B + k * 512u + lane * 16u); L.cq = 0; }
                     if (k + 1u == nch) {
                         __syncwarp();  // every lane has the stage's last records in registers: the stage may be refilled
                         if (lane == 0 && g + NS < ngroups) issue(g + NS, stage);
                     }
-                    reduce_chunk_pf<QC>(a, thr, w, L, static_cast<uint32_t>((ch + k) << 8), lane, tot, ign, pol_t);
+                    reduce_chunk_pf<QC, HINT>(a, thr, w, L, static_cast<uint32_t>((ch + k) << 8), lane, tot, ign, pol_t);
                 }
             }
             stage = (stage + 1 == NS) ? 0 : stage + 1;
@@ -480,19 +487,19 @@ __global__ void __launch_bounds__(kThreads, MINB) score_runs_ring_kernel(const R
 
 // the ring configurations a launch can ask for (variant 2..5): {chunks per stage, stages, CTAs per SM}
 struct RingCfg { void (*kern)(const RunArgs); uint32_t ch, ns; };
-template <bool QC>
+template <bool QC, bool HINT>
 inline RingCfg ring_config(int variant) {
     if constexpr (QC) {  // 768 B per chunk
         switch (variant) {
-            case 3: return {score_runs_ring_kernel<true, 3, 4, 3>, 4, 3};   // 72 KB per CTA
-            case 4: return {score_runs_ring_kernel<true, 2, 8, 2>, 8, 2};   // 96 KB
-            case 5: return {score_runs_ring_kernel<true, 2, 4, 4>, 4, 2};   // 48 KB
-            default: return {score_runs_ring_kernel<true, 4, 2, 4>, 2, 4};  // 48 KB
+            case 3: return {score_runs_ring_kernel<true, 3, 4, 3, HINT>, 4, 3};   // 72 KB per CTA
+            case 4: return {score_runs_ring_kernel<true, 2, 8, 2, HINT>, 8, 2};   // 96 KB
+            case 5: return {score_runs_ring_kernel<true, 2, 4, 4, HINT>, 4, 2};   // 48 KB
+            default: return {score_runs_ring_kernel<true, 4, 2, 4, HINT>, 2, 4};  // 48 KB
         }
     } else {  // 1280 B per chunk
         switch (variant) {
-            case 3: case 4: case 5: return {score_runs_ring_kernel<false, 2, 4, 2>, 4, 2};  // 80 KB
-            default: return {score_runs_ring_kernel<false, 3, 2, 3>, 2, 3};                  // 60 KB
+            case 3: case 4: case 5: return {score_runs_ring_kernel<false, 2, 4, 2, HINT>, 4, 2};  // 80 KB
+            default: return {score_runs_ring_kernel<false, 3, 2, 3, HINT>, 2, 3};                  // 60 KB
         }
     }
 }

@@ -77,9 +77,12 @@ extern "C" int simt_score_runs(int form, unsigned grid, const uint32_t* run_tid,
     RunArgs a{run_tid, run_start, chunk_run, n_runs, as0, xm3, qlen, orig_idx, chunk_qlen, n_rec, idx_base, allow, n_ref, minscore, max_xm,
               min_read_len, reinterpret_cast<long long*>(sum_as), n_hit, first_idx, reinterpret_cast<unsigned long long*>(counters), 1};
     const bool qc = chunk_qlen != nullptr, oi = orig_idx != nullptr;
-    if (form >= 2 && form <= 5) {
+    if ((form >= 2 && form <= 5) || (form >= 12 && form <= 15)) {  // 12..15: the builds with the L2 residency hints
         if (oi) return -1;
-        launch((qc ? ring_config<true>(form) : ring_config<false>(form)).kern, grid, kThreads, a);
+        const bool hint = form >= 12;
+        const int f = hint ? form - 10 : form;
+        launch((qc ? (hint ? ring_config<true, true>(f) : ring_config<true, false>(f)) : (hint ? ring_config<false, true>(f) : ring_config<false, false>(f))).kern,
+               grid, kThreads, a);
         return 0;
     }
     if (form != 0 && form != 1) return -1;

@@ -63,7 +63,7 @@ def _streams(n, style, rng, n_ref):
     return np.repeat(rt, lens).astype(np.uint32)
 
 
-@pytest.mark.parametrize("form", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("form", [0, 1, 2, 3, 4, 5, 12, 15])  # 12, 15: ring builds with the L2 hints
 @pytest.mark.parametrize("n", [1, 255, 256, 257, 511, 513, 769, 4096, 30011])
 def test_warp_program_of_every_kernel_form_matches_numpy(simt, n, form):
     rng = np.random.default_rng(1000 * form + n)
