@@ -118,7 +118,7 @@ int mmlst_score_runs_qc_dev(const uint32_t* run_tid, const uint32_t* run_start, 
  * other inputs take form 0), 3..5 = the ring with other stage sizes / depths (4 chunks x 3 stages, 8 x 2, 4 x 2).
  * Returns the previous value; a value outside 0..5 only queries.  The environment variable
  * MMLST_SCORE_VARIANT presets it. */
-#define MMLST_SCORE_VARIANT_DEFAULT 0
+#define MMLST_SCORE_VARIANT_DEFAULT 5
 int mmlst_set_score_variant(int variant);
 /* Ring forms only: L2 residency hints (score stream evict-first; run arrays, allow[] and chunk_qlen[] evict-last, so that the
  * small tables every warp starts from survive in the L2 from one launch to the next).  1 = on, 0 = off, other = query;
