@@ -33,7 +33,7 @@ import numpy as np  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=48, help="timed passes (a pass is ~40 us: the default keeps every cohort lane busy for several passes)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU")
@@ -48,8 +48,9 @@ def parse():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "gather", "allreduce"],
                     help="N>1: 'p2p' = owner mode, result blocks stored into the peers' memory over NVLink by our own kernels; 'gather' = owner mode, "
                          "one NCCL all-gather of result blocks per pass; 'allreduce' = partial score/count tensors all-reduced with NCCL")
-    ap.add_argument("--lanes", type=int, default=2, help="N=1: streams that consecutive passes alternate on (cohort mode: the tail of pass i "
-                    "overlaps the scoring kernel of pass i+1); 1 = strictly serial passes")
+    ap.add_argument("--lanes", type=int, default=0, help="streams that consecutive passes alternate on (cohort mode: the latency-bound tail of a "
+                    "pass overlaps the scoring kernels of the next ones); 1 = strictly serial passes; 0 = default: 6 at N=1 (r1t: 4 lanes 1.05e12, "
+                    "6 lanes 1.17e12, 8 lanes 1.18e12 records/s), 2 at N>1")
     ap.add_argument("--no-qc", action="store_true", help="score stream in the 5 B/record run-length form (explicit len(SEQ) per record) even when every "
                     "256-record chunk is uniform")
     ap.add_argument("--score-variant", default="default", choices=["default", "0", "1", "2", "3", "4", "5", "auto"],
@@ -210,13 +211,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.lanes <= 0:  # same `config` text as our arm
+        args.lanes = 6 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 2
     db = make_db(args)
     threads = os.cpu_count() or 1
     rate, dt, sample = cpu_port_run(db, args, args.cpu_sample_reads, threads, steps=max(1, args.steps), warmup=min(args.warmup, 1))
     line = {"impl": "reference", "metric": "aligned reads/s (score+pileup+consensus)", "value": rate, "unit": "records/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32/u8", "data": "synthetic",
-            "config": workload_config(args, 1), "gpu_launches": 0,
+            "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))), "gpu_launches": 0,
             "cpu_baseline": {"value": rate, "unit": "records/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference itself (pure Python over pysam/samtools) cannot run on this box; this is the C port of its restatement (oracle/c), a faster stand-in"}
@@ -272,6 +275,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.lanes <= 0:
+        args.lanes = 6 if world == 1 else 2
     torch.cuda.set_device(local)
     device = "cuda:%d" % local
     if world > 1:

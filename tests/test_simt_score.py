@@ -63,8 +63,13 @@ def _streams(n, style, rng, n_ref):
     return np.repeat(rt, lens).astype(np.uint32)
 
 
-@pytest.mark.parametrize("form", [0, 1, 2, 3, 4, 5, 12, 15])  # 12, 15: ring builds with the L2 hints
-@pytest.mark.parametrize("n", [1, 255, 256, 257, 511, 513, 769, 4096, 30011])
+# forms 0 / 1: register-staged kernels; 2..5: ring configurations; 12..15: the ring builds with the L2 hints.  The library
+# default (5) and the two register forms see every size; the other ring builds the sizes that exercise refills and tails.
+_SIZES = [1, 255, 256, 257, 511, 513, 769, 4096, 30011]
+_CASES = [(n, f) for f in (0, 1, 5) for n in _SIZES] + [(n, f) for f in (2, 3, 4, 12, 15) for n in (257, 4096, 30011)]
+
+
+@pytest.mark.parametrize("n,form", _CASES)
 def test_warp_program_of_every_kernel_form_matches_numpy(simt, n, form):
     rng = np.random.default_rng(1000 * form + n)
     n_ref = 300
