@@ -49,8 +49,8 @@ def parse():
                     help="N>1: 'p2p' = owner mode, result blocks stored into the peers' memory over NVLink by our own kernels; 'gather' = owner mode, "
                          "one NCCL all-gather of result blocks per pass; 'allreduce' = partial score/count tensors all-reduced with NCCL")
     ap.add_argument("--lanes", type=int, default=0, help="streams that consecutive passes alternate on (cohort mode: the latency-bound tail of a "
-                    "pass overlaps the scoring kernels of the next ones); 1 = strictly serial passes; 0 = default: 6 at N=1 (r1t: 4 lanes 1.05e12, "
-                    "6 lanes 1.17e12, 8 lanes 1.18e12 records/s), 2 at N>1")
+                    "pass overlaps the scoring kernels of the next ones); 1 = strictly serial passes; 0 = default: 6 (r1t, N=1: 4 lanes 1.05e12, 6 lanes "
+                    "1.17e12, 8 lanes 1.18e12 records/s; r1u, N=2: 2 lanes 1.49e12, 6 lanes 2.30e12)")
     ap.add_argument("--no-qc", action="store_true", help="score stream in the 5 B/record run-length form (explicit len(SEQ) per record) even when every "
                     "256-record chunk is uniform")
     ap.add_argument("--score-variant", default="default", choices=["default", "0", "1", "2", "3", "4", "5", "auto"],
@@ -212,7 +212,7 @@ def run_reference(args):
     if rank != 0:
         return
     if args.lanes <= 0:  # same `config` text as our arm
-        args.lanes = 6 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 2
+        args.lanes = 6
     db = make_db(args)
     threads = os.cpu_count() or 1
     rate, dt, sample = cpu_port_run(db, args, args.cpu_sample_reads, threads, steps=max(1, args.steps), warmup=min(args.warmup, 1))
@@ -276,7 +276,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.lanes <= 0:
-        args.lanes = 6 if world == 1 else 2
+        args.lanes = 6
     torch.cuda.set_device(local)
     device = "cuda:%d" % local
     if world > 1:
