@@ -332,7 +332,7 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
                 const uint8_t* val = a2 + 3;
                 const size_t sz = aux_size(t, val, end);
                 if (sz == 0 || val + sz > end) { err.set(MMLST_E_BAM, "%s: record %zu: malformed aux field %d", path, i, field); return; }
-                int64_t v;
+                int64_t v = 0;
                 const bool isint = aux_int(t, val, &v);
                 if (field == 0) { ok0 = isint; v0 = v; }
                 if (field == 3) { ok3 = isint; v3 = v; }
