@@ -6,6 +6,8 @@ pileup counts per contig, with and without the tag filter, with the depth cap ac
 import numpy as np
 import pytest
 
+import json
+
 import helpers
 from metamlst_b200 import bam
 from oracle import bamio, mlst_oracle as orc
@@ -56,20 +58,38 @@ def _random_record(rng, i, tid, clen):
     return bamio.BamRecord("q%d" % (i // 3), flag, tid, pos, 42, tuple(cig), seq, qual, aux)
 
 
-@pytest.mark.parametrize("seed,max_depth", [(1, 8000), (2, 8000), (3, 40)])
-def test_ragged_lengths_and_every_cigar_op(tmp_path, seed, max_depth):
+NAMES = ["ecoli_adk_1", "ecoli_adk_2", "ecoli_fumC_7", "saureus_arcC_3"]
+LENS = [536, 536, 469, 456]
+
+
+def _ragged_bam(tmp_path, seed):
     rng = np.random.default_rng(seed)
-    names = ["ecoli_adk_1", "ecoli_adk_2", "ecoli_fumC_7", "saureus_arcC_3"]
-    lens = [536, 536, 469, 456]
     recs = []
     for i in range(1800):
-        tid = int(rng.integers(0, len(names)))
-        recs.append(_random_record(rng, i, tid, lens[tid]))
+        tid = int(rng.integers(0, len(NAMES)))
+        recs.append(_random_record(rng, i, tid, LENS[tid]))
     # pile many reads on one start so the cap (40) bites where it is asked to
-    recs += [_random_record(rng, 5000 + i, 2, lens[2])._replace(pos=100) for i in range(120)]
+    recs += [_random_record(rng, 5000 + i, 2, LENS[2])._replace(pos=100) for i in range(120)]
     p = str(tmp_path / "ragged.bam")
-    bamio.write_bam(p, names, lens, recs)
+    bamio.write_bam(p, NAMES, LENS, recs)
     _h, recs = bamio.read_bam(p)  # what the file holds (BAM stores bases as 4-bit codes: case is gone, IUPAC letters stay)
+    return p, recs, rng
+
+
+def _oracle_counts(recs, tid, tf, max_depth):
+    contig = [r for r in sorted(recs, key=lambda r: (r.tid, r.pos, (r.flag >> 4) & 1)) if r.tid == tid]
+    want = np.zeros((LENS[tid], 5), np.int64)
+    full, _ = orc.get_base_stats(contig, tid, 0, 20, tf, max_depth)  # depth 0: also the columns that hold only N
+    for pos1, d in full.items():
+        f = d["base_freq"]
+        want[pos1 - 1] = [f["A"], f["C"], f["G"], f["T"], f["N"]]
+    return want
+
+
+@pytest.mark.parametrize("seed,max_depth", [(1, 8000), (2, 8000), (3, 40)])
+def test_ragged_lengths_and_every_cigar_op(tmp_path, seed, max_depth):
+    names, lens = NAMES, LENS
+    p, recs, rng = _ragged_bam(tmp_path, seed)
     soa = bam.unpack_bam(p, minqual=20, max_depth=max_depth, pinned=False, threads=3)
     assert soa.chunk_qlen is None or len(recs) < 256  # ragged chunks: the per-chunk len(SEQ) form must not be offered
     # ---- score stream, record by record (file order through orig_idx)
@@ -97,3 +117,35 @@ def test_ragged_lengths_and_every_cigar_op(tmp_path, seed, max_depth):
             got = helpers.planes_to_counts(soa, tid, lens[tid], minscore, max_xm)
             assert np.array_equal(got, want), (seed, tid, minscore, np.nonzero((got != want).any(axis=1))[0][:10])
             assert sum(1 for d in stats.values()) == int((want[:, :4].sum(axis=1) >= 1).sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,max_depth", [(1, 8000), (3, 40)])
+def test_ragged_lengths_on_the_gpu(tmp_path, seed, max_depth):
+    """The same file through the kernels: stage-1 tables and dict order against metamlst.py's own loop (oracle stage1), pileup
+    counts of both implementations against the oracle's pileup, consensus against the majority rule."""
+    from metamlst_b200 import api, native
+    p, recs, _rng = _ragged_bam(tmp_path, seed)
+    soa = bam.unpack_bam(p, minqual=20, max_depth=max_depth)
+    ctx = native.Context(0)
+    try:
+        index = api.AlleleIndex(soa.ref_names)
+        h = bamio.BamHeader("", NAMES, LENS)
+        for minscore, max_xm, min_len in ((150, 4, 50), (80, 5, 100), (0, 8, 0)):
+            cel, total, ignored, _raw = api.score_soa(ctx, soa, index, minscore, max_xm, min_len, None, 100)
+            want, _bank, wt, wi = orc.stage1(h, recs, minscore, max_xm, min_len, None, 100)
+            assert json.dumps(cel) == json.dumps(want) and (total, ignored) == (wt, wi)
+        tids = list(range(len(NAMES)))
+        for minscore, max_xm in ((-32768, 255), (150, 4)):
+            tf = None if minscore < 0 else [("AS", "loc_gte", minscore), ("XM", "loc_lte", max_xm)]
+            want = [_oracle_counts(recs, t, tf, max_depth) for t in tids]
+            for impl in (1, 2):
+                seqs, holes, snps, counts, col_off = api.pileup_consensus(ctx, soa, tids, ["A" * n for n in LENS], minscore, max_xm, 1, impl, True)
+                for i, t in enumerate(tids):
+                    assert np.array_equal(counts[col_off[i]:col_off[i + 1]], want[t]), (impl, t, minscore)
+                    contig = [r for r in sorted(recs, key=lambda r: (r.tid, r.pos, (r.flag >> 4) & 1)) if r.tid == t]
+                    cons = orc.reference_free_consensus(contig, t, LENS[t], 1, 20, "N", tf, max_depth)
+                    filled = "".join(("a" if c == "N" else c) for c in cons)  # DB base 'A', lower-cased, fills a hole (metaMLST_functions.py:267)
+                    assert seqs[i] == filled and int(holes[i]) == cons.count("N") and int(snps[i]) == sum(1 for c in cons if c not in "AN")
+    finally:
+        ctx.close()
