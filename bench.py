@@ -335,6 +335,11 @@ def main():
     if args.score_variant == "auto" and pipe.use_runs:
         # every form on this workload (equal tables asserted), fastest kept for everything that follows; with N>1 the ranks agree on rank 0's choice
         variants_ms = pipe.time_score_variants(20, alt=pipes[1])
+        if os.environ.get("MMLST_BENCH_SCALING"):  # profiling aid (profiles/run_p.sh): launch time at 1/1, 1/2, 1/4 of the stream, per form
+            for key in sorted(variants_ms):
+                native.lib().mmlst_set_score_variant(int(key[0]))
+                native.lib().mmlst_set_score_l2_hints(1 if key.endswith("h") else 0)
+                sys.stderr.write("score form %s, records 1/1 1/2 1/4: %r\n" % (key, pipe.time_score_half(20, alt=pipes[1])))
         best = min(variants_ms, key=variants_ms.get)
         pick = torch.tensor([int(best[0]), 1 if best.endswith("h") else 0], dtype=torch.int32, device=device)
         if world > 1:
