@@ -53,7 +53,7 @@ def parse():
                     "1.17e12, 8 lanes 1.18e12 records/s; r1u, N=2: 2 lanes 1.49e12, 6 lanes 2.30e12)")
     ap.add_argument("--no-qc", action="store_true", help="score stream in the 5 B/record run-length form (explicit len(SEQ) per record) even when every "
                     "256-record chunk is uniform")
-    ap.add_argument("--score-variant", default="default", choices=["default", "0", "1", "2", "3", "4", "5", "auto"],
+    ap.add_argument("--score-variant", default="default", choices=["default", "0", "1", "2", "3", "4", "5", "6", "auto"],
                     help="form of the run-length score kernel (mmlst_set_score_variant): 0 registers, 1 registers + software pipeline, 2 shared-memory "
                          "ring fed by TMA bulk copies; 'default' = the library's; 'auto' = time all three on the workload first and keep the fastest")
     ap.add_argument("--score-l2-hints", default="default", choices=["default", "0", "1"], help="ring forms of the score kernel: L2 residency hints "
@@ -282,7 +282,7 @@ def main():
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
     native.lib()  # fail loudly if the CUDA library is missing
-    if args.score_variant in ("0", "1", "2", "3", "4", "5"):
+    if args.score_variant in ("0", "1", "2", "3", "4", "5", "6"):
         native.lib().mmlst_set_score_variant(int(args.score_variant))
     if args.score_l2_hints in ("0", "1"):
         native.lib().mmlst_set_score_l2_hints(int(args.score_l2_hints))

@@ -115,8 +115,9 @@ int mmlst_score_runs_qc_dev(const uint32_t* run_tid, const uint32_t* run_start, 
                             int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, uint64_t* counters, void* stream);
 /* Kernel form used by mmlst_score_runs_dev / mmlst_score_runs_qc_dev (identical results): 0 = register-staged, 1 = register-
  * staged and software-pipelined, 2 = per-warp shared-memory ring filled by TMA bulk copies (records without orig_idx only;
- * other inputs take form 0), 3..5 = the ring with other stage sizes / depths (4 chunks x 3 stages, 8 x 2, 4 x 2).
- * Returns the previous value; a value outside 0..5 only queries.  The environment variable
+ * other inputs take form 0), 3..5 = the ring with other stage sizes / depths (4 chunks x 3 stages, 8 x 2, 4 x 2),
+ * 6 = EXPERIMENTAL, not yet timed on hardware: form 5 with pairs of chunks reduced together (per-chunk len(SEQ) streams;
+ * others take form 5).  Returns the previous value; a value outside 0..6 only queries.  The environment variable
  * MMLST_SCORE_VARIANT presets it. */
 #define MMLST_SCORE_VARIANT_DEFAULT 5
 int mmlst_set_score_variant(int variant);

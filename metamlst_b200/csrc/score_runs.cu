@@ -21,13 +21,13 @@ static int g_score_variant = -1;
 static int score_variant() {
     if (g_score_variant < 0) {
         const char* e = getenv("MMLST_SCORE_VARIANT");
-        g_score_variant = (e && e[0] >= '0' && e[0] <= '5' && !e[1]) ? e[0] - '0' : MMLST_SCORE_VARIANT_DEFAULT;
+        g_score_variant = (e && e[0] >= '0' && e[0] <= '6' && !e[1]) ? e[0] - '0' : MMLST_SCORE_VARIANT_DEFAULT;
     }
     return g_score_variant;
 }
 extern "C" int mmlst_set_score_variant(int v) {
     const int prev = score_variant();
-    if (v >= 0 && v <= 5) g_score_variant = v;
+    if (v >= 0 && v <= 6) g_score_variant = v;
     return prev;
 }
 
@@ -68,22 +68,40 @@ static int score_runs_launch(const uint32_t* run_tid, const uint32_t* run_start,
     const int variant = score_variant();
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool tma_ok = !orig_idx && !(reinterpret_cast<uintptr_t>(xm3) & 15);  // cp.async.bulk wants 16-byte aligned sources
+    if (variant == 6 && tma_ok && chunk_qlen) {  // experimental: form 5's ring with pairs of chunks reduced together
+        static int pair_resident = 0;
+        const size_t smem = (kThreads / 32) * 2u * (4u * 768u + sizeof(uint64_t));
+        if (!pair_resident) {
+            CUDA_TRY(cudaFuncSetAttribute(score_runs_ring_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            CUDA_TRY(cudaFuncSetAttribute(score_runs_ring_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            int r = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, score_runs_ring_pair_kernel, kThreads, smem) != cudaSuccess || r < 1) r = 1;
+            pair_resident = r;
+        }
+        const uint64_t cap = static_cast<uint64_t>(mmlst_num_sms()) * pair_resident;
+        if (want > cap) want = cap;
+        if (want < 1) want = 1;
+        score_runs_ring_pair_kernel<<<static_cast<unsigned>(want), kThreads, smem, st>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        return MMLST_OK;
+    }
     if (variant >= 2 && tma_ok) {
         // one resident wave of the ring kernel: NS stages of CH chunks per warp in dynamic shared memory
         static int ring_resident[4][8] = {{0}};
         const int hint = a.l2_hints ? 1 : 0;
         const int q = (chunk_qlen ? 1 : 0) + 2 * hint;
-        const RingCfg cfg = chunk_qlen ? (hint ? ring_config<true, true>(variant) : ring_config<true, false>(variant))
-                                       : (hint ? ring_config<false, true>(variant) : ring_config<false, false>(variant));
+        const int rv = variant == 6 ? 5 : variant;  // form 6 exists for the per-chunk len(SEQ) stream only
+        const RingCfg cfg = chunk_qlen ? (hint ? ring_config<true, true>(rv) : ring_config<true, false>(rv))
+                                       : (hint ? ring_config<false, true>(rv) : ring_config<false, false>(rv));
         const size_t smem = (kThreads / 32) * static_cast<size_t>(cfg.ns) * (cfg.ch * (chunk_qlen ? 768u : 1280u) + sizeof(uint64_t));
-        if (!ring_resident[q][variant]) {
+        if (!ring_resident[q][rv]) {
             CUDA_TRY(cudaFuncSetAttribute(cfg.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             CUDA_TRY(cudaFuncSetAttribute(cfg.kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             int r = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, cfg.kern, kThreads, smem) != cudaSuccess || r < 1) r = 1;
-            ring_resident[q][variant] = r;
+            ring_resident[q][rv] = r;
         }
-        const uint64_t cap = static_cast<uint64_t>(mmlst_num_sms()) * ring_resident[q][variant];
+        const uint64_t cap = static_cast<uint64_t>(mmlst_num_sms()) * ring_resident[q][rv];
         if (want > cap) want = cap;
         if (want < 1) want = 1;
         cfg.kern<<<static_cast<unsigned>(want), kThreads, smem, st>>>(a);

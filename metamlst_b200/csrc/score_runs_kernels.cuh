@@ -485,6 +485,130 @@ __global__ void __launch_bounds__(kThreads, MINB) score_runs_ring_kernel(const R
     }
 }
 
+// ---- form 6 (experimental, QC streams): form 5's ring (4 chunks x 2 stages per warp) with the chunks reduced TWO AT A TIME.
+// r1s ncu of form 5: ~119 warp instructions per 256-record chunk of which the filter + sums are ~35; the rest is per-chunk
+// bookkeeping (REDUX x 2-3, run-boundary tests, counters, loop).  When both chunks of a pair lie inside the open run -- 5 of 6
+// pairs at config 2 -- one set of reductions and tests serves 512 records.  Same tables as every other form (tests/simt,
+// tests/test_gpu_parity.py fixture kernel_form); a separate kernel so that the measured forms' code is untouched.
+__device__ __forceinline__ void reduce_pair_pf(const RunArgs& a, const Thr& thr, WarpRunPF& w, const Loaded<false>& La, const Loaded<false>& Lb,
+                                               uint32_t base, uint32_t lane, uint32_t& tot, uint32_t& ign, uint64_t pol) {
+    if (base + 512u > w.end) {  // a run ends inside the pair: chunk by chunk
+        reduce_chunk_pf<true, false>(a, thr, w, La, base, lane, tot, ign, pol);
+        reduce_chunk_pf<true, false>(a, thr, w, Lb, base + 256u, lane, tot, ign, pol);
+        return;
+    }
+    if (w.al) {
+        uint32_t pa_lo, pa_hi, pb_lo, pb_hi;
+        lane_pass<false, true>(La, thr, a.min_read_len, pa_lo, pa_hi);
+        lane_pass<false, true>(Lb, thr, a.min_read_len, pb_lo, pb_hi);
+        int s = __dp2a_lo(static_cast<int>(La.a8.x), static_cast<int>(pa_lo), 0);
+        s = __dp2a_hi(static_cast<int>(La.a8.y), static_cast<int>(pa_lo), s);
+        s = __dp2a_lo(static_cast<int>(La.a8.z), static_cast<int>(pa_hi), s);
+        s = __dp2a_hi(static_cast<int>(La.a8.w), static_cast<int>(pa_hi), s);
+        s = __dp2a_lo(static_cast<int>(Lb.a8.x), static_cast<int>(pb_lo), s);
+        s = __dp2a_hi(static_cast<int>(Lb.a8.y), static_cast<int>(pb_lo), s);
+        s = __dp2a_lo(static_cast<int>(Lb.a8.z), static_cast<int>(pb_hi), s);
+        s = __dp2a_hi(static_cast<int>(Lb.a8.w), static_cast<int>(pb_hi), s);  // |s| <= 16 x 32768 per lane, x 32 lanes < 2^31
+        const uint32_t c = __popc(pa_lo | (pa_hi << 1) | (pb_lo << 2) | (pb_hi << 3));
+        tot += 16u;
+        ign += 16u - c;
+        w.s += __reduce_add_sync(FULL, s);
+        w.c += __reduce_add_sync(FULL, c);
+        if (w.mn == 0xffffffffu) {  // indices ascend inside a run: the first chunk's hits come first
+            const uint32_t idx0 = static_cast<uint32_t>(a.idx_base) + base + (lane << 3);
+            const uint32_t ma = first_pass_index(pa_lo, pa_hi, idx0);
+            w.mn = __reduce_min_sync(FULL, ma != 0xffffffffu ? ma : first_pass_index(pb_lo, pb_hi, idx0 + 256u));
+        }
+    }
+    if (base + 512u == w.end) next_run_pf<false>(a, w, lane, pol);
+}
+
+__global__ void __launch_bounds__(kThreads, 4) score_runs_ring_pair_kernel(const RunArgs a) {
+    extern __shared__ __align__(128) uint8_t ring_raw[];
+    constexpr int NS = 2;
+    constexpr uint32_t CH = 4, AS_B = CH * 512u, XM_B = CH * 256u, STAGE_B = AS_B + XM_B, CH_B = STAGE_B / CH;
+    constexpr int NW = kThreads / 32;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint8_t* const my = ring_raw + wid * (NS * STAGE_B);
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(ring_raw + NW * NS * STAGE_B) + wid * NS;
+    if (threadIdx.x == 0) {
+        uint64_t* all = reinterpret_cast<uint64_t*>(ring_raw + NW * NS * STAGE_B);
+        for (int i = 0; i < NW * NS; ++i) mbar_init(all + i, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+    const uint64_t nchunks = a.n_rec >> 8;
+    const uint64_t per = (nchunks + nwarps - 1) / nwarps;
+    const uint64_t c0 = warp * per;
+    const uint64_t c1 = (c0 + per < nchunks) ? c0 + per : nchunks;
+    uint32_t tot = 0, ign = 0;
+    const Thr thr = make_thr(a);
+
+    if (c0 < c1) {
+        const uint32_t ngroups = static_cast<uint32_t>((c1 - c0 + CH - 1) / CH);
+        auto issue = [&](uint32_t g, int stage) {  // lane 0: request group g (1..CH chunks) into `stage`
+            const uint64_t ch = c0 + static_cast<uint64_t>(g) * CH;
+            const uint32_t nch = (c1 - ch < CH) ? static_cast<uint32_t>(c1 - ch) : CH;
+            uint8_t* st = my + stage * STAGE_B;
+            mbar_expect_tx(bars + stage, nch * CH_B);
+            bulk_g2s(st, a.as0 + (ch << 8), nch * 512u, bars + stage);
+            bulk_g2s(st + AS_B, a.xm3 + (ch << 8), nch * 256u, bars + stage);
+        };
+        if (lane == 0) {
+            const uint32_t pre = ngroups < static_cast<uint32_t>(NS) ? ngroups : static_cast<uint32_t>(NS);
+            for (uint32_t g = 0; g < pre; ++g) issue(g, static_cast<int>(g));
+        }
+        WarpRunPF w;
+        open_run_pf<false>(a, w, __ldg(a.chunk_run + c0), 0ull);
+        uint32_t phase = 0;
+        int stage = 0;
+        auto load = [&](const uint8_t* st, uint32_t k, uint64_t ch) {
+            Loaded<false> L;
+            L.a8 = *reinterpret_cast<const uint4*>(st + k * 512u + lane * 16u);
+            L.x8 = *reinterpret_cast<const uint2*>(st + AS_B + k * 256u + lane * 8u);
+            L.q8 = make_uint4(0, 0, 0, 0);
+            L.cq = __ldg(a.chunk_qlen + ch + k);
+            return L;
+        };
+        for (uint32_t g = 0; g < ngroups; ++g) {
+            const uint64_t ch = c0 + static_cast<uint64_t>(g) * CH;
+            const uint32_t nch = (c1 - ch < CH) ? static_cast<uint32_t>(c1 - ch) : CH;
+            mbar_wait(bars + stage, (phase >> stage) & 1u);
+            phase ^= 1u << stage;
+            const uint8_t* st = my + stage * STAGE_B;
+#pragma unroll
+            for (uint32_t k = 0; k < CH; k += 2) {
+                if (k < nch) {  // warp-uniform
+                    const bool two = k + 1u < nch;
+                    const Loaded<false> La = load(st, k, ch);
+                    Loaded<false> Lb = La;
+                    if (two) Lb = load(st, k + 1u, ch);
+                    if (k + 2u >= nch) {
+                        __syncwarp();  // every lane has the stage's last records in registers: the stage may be refilled
+                        if (lane == 0 && g + NS < ngroups) issue(g + NS, stage);
+                    }
+                    const uint32_t base = static_cast<uint32_t>((ch + k) << 8);
+                    if (two) reduce_pair_pf(a, thr, w, La, Lb, base, lane, tot, ign, 0ull);
+                    else reduce_chunk_pf<true, false>(a, thr, w, La, base, lane, tot, ign, 0ull);
+                }
+            }
+            stage = (stage + 1 == NS) ? 0 : stage + 1;
+        }
+        if (lane == 0 && w.al) flush_run(a, w.key, w.s, w.c, w.mn);
+    }
+
+    if (warp == nwarps - 1 && (a.n_rec & 255u)) score_tail<true>(a, nchunks, lane, tot, ign);
+    tot = __reduce_add_sync(FULL, tot);
+    ign = __reduce_add_sync(FULL, ign);
+    if (lane == 0 && tot) {
+        atomicAdd(a.counters + 0, static_cast<unsigned long long>(tot));
+        atomicAdd(a.counters + 1, static_cast<unsigned long long>(ign));
+    }
+}
+
 // the ring configurations a launch can ask for (variant 2..5): {chunks per stage, stages, CTAs per SM}
 struct RingCfg { void (*kern)(const RunArgs); uint32_t ch, ns; };
 template <bool QC, bool HINT>

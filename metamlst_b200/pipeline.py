@@ -7,6 +7,7 @@ exactly the exchange SURVEY.md 8e names; shards must be contig-aligned so that t
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -373,7 +374,10 @@ class DevicePipeline:
         pipes = [self] + ([alt] if alt is not None else [])
         out: Dict[str, float] = {}
         want = None
-        for key in ("0", "1", "2", "3", "4", "5", "2h", "3h", "4h", "5h"):  # "h": ring form with the L2 residency hints
+        keys = ["0", "1", "2", "3", "4", "5", "2h", "3h", "4h", "5h"]  # "h": ring form with the L2 residency hints
+        if os.environ.get("MMLST_EXPERIMENTAL_FORMS") and self.use_qc:
+            keys.append("6")  # pair-fused ring: verified on the host emulation only until a GPU visit has run it
+        for key in keys:
             v = int(key[0])
             self.lib.mmlst_set_score_variant(v)
             self.lib.mmlst_set_score_l2_hints(1 if key.endswith("h") else 0)

@@ -85,6 +85,11 @@ extern "C" int simt_score_runs(int form, unsigned grid, const uint32_t* run_tid,
                grid, kThreads, a);
         return 0;
     }
+    if (form == 6) {  // pair-fused ring: per-chunk len(SEQ) streams without a file-order index only
+        if (oi || !qc) return -1;
+        launch(score_runs_ring_pair_kernel, grid, kThreads, a);
+        return 0;
+    }
     if (form != 0 && form != 1) return -1;
     const bool pipe = form == 1;
     if (!oi && !pipe && !qc) launch(score_runs_kernel<false, false, false>, grid, kThreads, a);

@@ -66,7 +66,7 @@ def _streams(n, style, rng, n_ref):
 # forms 0 / 1: register-staged kernels; 2..5: ring configurations; 12..15: the ring builds with the L2 hints.  The library
 # default (5) and the two register forms see every size; the other ring builds the sizes that exercise refills and tails.
 _SIZES = [1, 255, 256, 257, 511, 513, 769, 4096, 30011]
-_CASES = [(n, f) for f in (0, 1, 5) for n in _SIZES] + [(n, f) for f in (2, 3, 4, 12, 15) for n in (257, 4096, 30011)]
+_CASES = [(n, f) for f in (0, 1, 5, 6) for n in _SIZES] + [(n, f) for f in (2, 3, 4, 12, 15) for n in (257, 4096, 30011)]  # 6: pair-fused ring
 
 
 @pytest.mark.parametrize("n,form", _CASES)
@@ -87,6 +87,8 @@ def test_warp_program_of_every_kernel_form_matches_numpy(simt, n, form):
         for oidx, qlen in [(o, q) for o in (None, rng.permutation(n).astype(np.uint32)) for q in (qlen_rec, qlen_chunk)]:
             if form >= 2 and oidx is not None:
                 continue  # the library sends records with a file-order index to form 0
+            if form == 6 and qlen is not qlen_chunk and n != 1:
+                continue  # form 6 exists for the per-chunk len(SEQ) stream (others take form 5)
             soa = packing.SoaHost([], np.zeros(0, np.int32), tid, as0, xm3, qlen, oidx, np.zeros(0, packing.PREC_DTYPE), np.zeros(0, np.uint32), 0,
                                   np.zeros(1, np.uint64)).build_runs(max_fraction=1.0)
             assert soa.run_tid is not None and (soa.chunk_qlen is not None) == (qlen is qlen_chunk or n == 1)
