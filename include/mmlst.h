@@ -344,6 +344,12 @@ int mmlst_hamming_min_x(mmlst_ctx* ctx, const uint32_t* q_hi, const uint32_t* q_
                         const uint32_t* xq_ids, const uint32_t* xq_x, const uint8_t* xq_bytes, uint32_t n_xq,
                         const uint32_t* blocks, uint32_t n_blocks, uint32_t* min_dist, uint32_t* argmin_row);
 
+/* Raw DEFLATE (RFC 1951) of ONE complete stream, e.g. the payload of a BGZF block, into a buffer of known size: the decoder
+ * the BAM unpacker uses instead of zlib's inflate() (whole-buffer, 64-bit bit buffer, two-level tables; every access is
+ * bounds-checked).  HOST.  Returns MMLST_OK and *produced = bytes written (<= out_capacity), or MMLST_E_BAM for a corrupt /
+ * truncated stream or one that does not fit.  Exported for the tests (byte-for-byte against zlib). */
+int mmlst_inflate_raw(const uint8_t* in, size_t n, uint8_t* out, size_t out_capacity, size_t* produced);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * BAM ingest (HOST, C++ threads + zlib).  Replaces the `samtools view -h -` text pipe of stage 1 (metamlst.py:96-110),
  * pysam's record access of stage 2 (cmseq/cmseq.py:54,527-545) and `samtools sort` + `samtools index`

@@ -232,12 +232,22 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
     // ---- phase 2: parallel raw inflate
     std::vector<uint8_t> u(usize + 8);
     Err err;
+    // MMLST_INFLATE=zlib keeps zlib's inflate() for cross-checks; the default is the whole-buffer decoder of inflate_fast.cpp
+    const char* inflate_env = getenv("MMLST_INFLATE");
+    const bool use_zlib = inflate_env && strcmp(inflate_env, "zlib") == 0;
     parallel_for(blocks.size(), threads, 64, [&](size_t a, size_t e) {
         z_stream zs;
         memset(&zs, 0, sizeof(zs));
         if (inflateInit2(&zs, -15) != Z_OK) { err.set(MMLST_E_NOMEM, "inflateInit2 failed"); return; }
         for (size_t i = a; i < e && !err.code.load(std::memory_order_relaxed); ++i) {
             const Block& b = blocks[i];
+            if (!use_zlib) {
+                size_t got = 0;
+                const int rc = mmlst_inflate_raw(&raw[b.coff], b.clen, &u[b.uoff], b.isize, &got);
+                if (rc == MMLST_OK && got == b.isize &&
+                    (!o.check_crc || (uint32_t)crc32(crc32(0L, Z_NULL, 0), &u[b.uoff], b.isize) == b.crc)) continue;
+                // anything else gets zlib's verdict on the same block: a file zlib can read is never refused
+            }
             inflateReset(&zs);
             zs.next_in = const_cast<Bytef*>(&raw[b.coff]);
             zs.avail_in = b.clen;

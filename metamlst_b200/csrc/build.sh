@@ -16,7 +16,8 @@ done
 EXTRA=""
 if [ -f bam_unpack.cpp ]; then
   g++ -O3 -std=c++17 -fPIC -Wall -pthread -c bam_unpack.cpp -o bam_unpack.o
-  OBJS="$OBJS bam_unpack.o"; EXTRA="-lz -lpthread"
+  g++ -O3 -std=c++17 -fPIC -Wall -c inflate_fast.cpp -o inflate_fast.o
+  OBJS="$OBJS bam_unpack.o inflate_fast.o"; EXTRA="-lz -lpthread"
 fi
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libmmlst.so $OBJS $EXTRA
 echo "built $(cd .. && pwd)/libmmlst.so"
