@@ -46,6 +46,15 @@ int mmlst_cuda_fail(cudaError_t e, const char* what);
 
 int mmlst_num_sms();
 
+// Function attributes (dynamic shared-memory limit, carve-out) and occupancy answers belong to ONE device: caches of "already
+// configured" are indexed by the current device, so that a process driving several GPUs (sample.type_cohort) configures each.
+constexpr int MMLST_MAX_DEVICES = 64;
+inline int mmlst_current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+    return d % MMLST_MAX_DEVICES;
+}
+
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // streaming 128-bit load: read once, do not pollute L1

@@ -285,7 +285,8 @@ int launch_pileup_bitsliced(const PileupArgs& a, cudaStream_t stream) {
     const size_t smem = 2 * stage_bytes + 2 * TR * sizeof(uint4) + 2 * sizeof(uint64_t) + 16;
     if (a.max_row_words < 3 || smem > 220 * 1024) return launch_pileup_atomic(a, stream);
     const int sms = mmlst_num_sms();
-    static size_t configured = 0;
+    static size_t configured_by_device[MMLST_MAX_DEVICES] = {0};
+    size_t& configured = configured_by_device[mmlst_current_device()];
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(pileup_bitsliced_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return mmlst_cuda_fail(e, "cudaFuncSetAttribute(pileup_bitsliced_kernel)");

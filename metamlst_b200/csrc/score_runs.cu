@@ -69,7 +69,8 @@ static int score_runs_launch(const uint32_t* run_tid, const uint32_t* run_start,
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool tma_ok = !orig_idx && !(reinterpret_cast<uintptr_t>(xm3) & 15);  // cp.async.bulk wants 16-byte aligned sources
     if (variant == 6 && tma_ok && chunk_qlen) {  // experimental: form 5's ring with pairs of chunks reduced together
-        static int pair_resident = 0;
+        static int pair_resident_by_device[MMLST_MAX_DEVICES] = {0};
+        int& pair_resident = pair_resident_by_device[mmlst_current_device()];
         const size_t smem = (kThreads / 32) * 2u * (4u * 768u + sizeof(uint64_t));
         if (!pair_resident) {
             CUDA_TRY(cudaFuncSetAttribute(score_runs_ring_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -87,7 +88,8 @@ static int score_runs_launch(const uint32_t* run_tid, const uint32_t* run_start,
     }
     if (variant >= 2 && tma_ok) {
         // one resident wave of the ring kernel: NS stages of CH chunks per warp in dynamic shared memory
-        static int ring_resident[4][8] = {{0}};
+        static int ring_resident_by_device[MMLST_MAX_DEVICES][4][8] = {{{0}}};
+        int (&ring_resident)[4][8] = ring_resident_by_device[mmlst_current_device()];
         const int hint = a.l2_hints ? 1 : 0;
         const int q = (chunk_qlen ? 1 : 0) + 2 * hint;
         const int rv = variant == 6 ? 5 : variant;  // form 6 exists for the per-chunk len(SEQ) stream only

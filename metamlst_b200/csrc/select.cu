@@ -346,7 +346,9 @@ extern "C" int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* firs
     a.chosen_first = chosen_first;
     if (!(flags & MMLST_SELECT_SCRATCH_CLEAN)) CUDA_TRY(cudaMemsetAsync(a.done, 0, 4, s));
     const size_t smem = sizeof(uint32_t) * (static_cast<size_t>(n_loci) * 7 + 1 + 3 * static_cast<size_t>(n_species)) + 16;
-    static size_t configured = 48 * 1024;
+    static size_t configured_by_device[MMLST_MAX_DEVICES] = {0};  // 0 = the 48 KB every kernel starts with
+    size_t& configured = configured_by_device[mmlst_current_device()];
+    if (configured == 0) configured = 48 * 1024;
     if (smem > configured) {
         CUDA_TRY(cudaFuncSetAttribute(sel_locus, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         configured = smem;
