@@ -511,21 +511,31 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
                 return;
             }
             uint32_t x = (uint32_t)c.pos & 31u, y = 0;  // column inside the row (rows are aligned to the contig's words), query index
+            // the three planes of the 32-column word being filled stay in registers and reach the row once per word
+            uint32_t wi = x >> 5, pv = 0, p1 = 0, p0 = 0;
             for (uint32_t k = 0; k < n_cig; ++k) {
                 const uint32_t cw = rd32(cig + 4 * k), op = cw & 15u, ln = cw >> 4;
                 if (op == 0 || op == 7 || op == 8) {
                     for (uint32_t t = 0; t < ln; ++t, ++x, ++y) {
+                        if ((x >> 5) != wi) {
+                            uint32_t* w3 = row + 3 * wi;
+                            w3[0] |= pv; w3[1] |= p1; w3[2] |= p0;
+                            wi = x >> 5; pv = p1 = p0 = 0;
+                        }
                         if (y >= l_seq) continue;               // qpos beyond l_qseq: quality 0 (pysam pileup_base_qual_skip)
                         if ((int)qual[y] < minqual) continue;   // H3: not in column.pileups at all
                         const int nib = (seq[y >> 1] >> ((~y & 1u) << 2)) & 15;
                         const int cd = code2[nib];
-                        uint32_t* w3 = row + 3 * (x >> 5);
                         const uint32_t bit = 1u << (x & 31u);
-                        if (cd >= 0) { w3[0] |= bit; if (cd & 2) w3[1] |= bit; if (cd & 1) w3[2] |= bit; }
-                        else w3[2] |= bit;                      // V=0, B0=1: bin N
+                        if (cd >= 0) { pv |= bit; if (cd & 2) p1 |= bit; if (cd & 1) p0 |= bit; }
+                        else p0 |= bit;                         // V=0, B0=1: bin N
                     }
                 } else if (op == 1 || op == 4) y += ln;
                 else if (op == 2 || op == 3) x += ln;
+            }
+            if (pv | p1 | p0) {
+                uint32_t* w3 = row + 3 * wi;
+                w3[0] |= pv; w3[1] |= p1; w3[2] |= p0;
             }
         }
     });

@@ -64,16 +64,17 @@ def _streams(n, style, rng, n_ref):
 
 
 # forms 0 / 1: register-staged kernels; 2..5: ring configurations; 12..15: the ring builds with the L2 hints.  The library
-# default (5) and the two register forms see every size; the other ring builds the sizes that exercise refills and tails.
+# default (5) and the experimental form 6 see every size; the other forms the sizes that exercise boundaries, refills and tails.
 _SIZES = [1, 255, 256, 257, 511, 513, 769, 4096, 30011]
-_CASES = [(n, f) for f in (0, 1, 5, 6) for n in _SIZES] + [(n, f) for f in (2, 3, 4, 12, 15) for n in (257, 4096, 30011)]  # 6: pair-fused ring
+_CASES = ([(n, f) for f in (5, 6) for n in _SIZES] + [(n, f) for f in (0, 1) for n in (1, 256, 257, 513, 4096, 30011)] +
+          [(n, f) for f in (2, 3, 4, 12, 15) for n in (257, 30011)])  # 6: pair-fused ring
 
 
 @pytest.mark.parametrize("n,form", _CASES)
 def test_warp_program_of_every_kernel_form_matches_numpy(simt, n, form):
     rng = np.random.default_rng(1000 * form + n)
     n_ref = 300
-    for style in ("mixed", "long", "short", "config2"):
+    for style in (("mixed", "long", "short", "config2") if n < 20000 else ("mixed", "config2")):  # the emulation costs ~0.4 s per launch at 30 k records
         tid = _streams(n, style, rng, n_ref)
         as0 = rng.integers(-50, 301, n).astype(np.int16)
         as0[rng.integers(0, n, max(1, n // 1000))] = 32767
