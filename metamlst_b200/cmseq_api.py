@@ -82,23 +82,30 @@ class BamContig:
         if ns in ['all', 'nofilter']:
             self.stepper = ns
 
-    # cmseq/cmseq.py:202-209: sorted keys A,C,G,N,T and max() keeps the first maximum => ties go A > C > G > N > T (H8)
-    def majority_rule(data_array):
-        freq_array = data_array['base_freq']
-        if any([v > 0 for v in freq_array.values()]):
-            return max(sorted(freq_array), key=freq_array.get)
-        else:
-            return 'N'
+    # Consensus rules (cmseq/cmseq.py:202-224).  Upstream takes `max(sorted(freq), key=freq.get)`: the keys sort to A, C, G, N, T and
+    # max() keeps the first maximum, so ties resolve A > C > G > N > T and N competes with the bases (H8).  Written out here as
+    # the scan it amounts to.  They are plain functions in the class body, as upstream, so `consensus_rule=BamContig.majority_rule`
+    # and calling `rule(column)` both work.
+    _TIE_ORDER = ("A", "C", "G", "N", "T")
 
-    def majority_rule_polymorphicLoci(data_array):  # cmseq/cmseq.py:211-224
-        freq_array = data_array['base_freq']
-        poly_pvalue = data_array['p']
-        if poly_pvalue <= 0.05:
+    def _first_maximum(freq) -> str:
+        best, best_n = None, None
+        for base in BamContig._TIE_ORDER:
+            if base in freq and (best is None or freq[base] > best_n):
+                best, best_n = base, freq[base]
+        return best
+
+    def majority_rule(data_array):
+        freq = data_array['base_freq']
+        return BamContig._first_maximum(freq) if max(freq.values()) > 0 else 'N'
+
+    def majority_rule_polymorphicLoci(data_array):
+        if data_array['p'] <= 0.05:  # polymorphic under the binomial test: masked
             return "*"
-        elif any([v > 0 for k, v in freq_array.items() if k != 'N']):
-            return max(sorted(freq_array), key=freq_array.get)
-        else:
-            return 'N'
+        freq = data_array['base_freq']
+        if max(n for base, n in freq.items() if base != 'N') > 0:
+            return BamContig._first_maximum(freq)
+        return 'N'
 
     def _counts(self, min_base_quality: int, BAM_tagFilter=None) -> np.ndarray:
         if self.stepper != 'nofilter':
@@ -144,36 +151,34 @@ class BamContig:
 
     def reference_free_consensus(self, consensus_rule=majority_rule, mincov=CMSEQ_DEFAULTS.mincov, minqual=CMSEQ_DEFAULTS.minqual,
                                  dominant_frq_thrsh=CMSEQ_DEFAULTS.poly_dominant_frq_thrsh, noneCharacter='-', BAM_tagFilter=None, trimReads=None):
-        """cmseq/cmseq.py:226-241."""
-        consensus_positions = {}
-        for pileupcolumn, position_data in self.get_base_stats(min_read_depth=mincov, min_base_quality=minqual, dominant_frq_thrsh=dominant_frq_thrsh,
-                                                               BAM_tagFilter=BAM_tagFilter, trimReads=trimReads,
-                                                               error_rate=CMSEQ_DEFAULTS.poly_error_rate).items():
-            consensus_positions[pileupcolumn] = consensus_rule(position_data)
-        if len(consensus_positions) > 0:
-            self.consensus = ''.join([(consensus_positions[position] if position in consensus_positions else noneCharacter)
-                                      for position in range(1, self.length + 1)])
-        else:
-            self.consensus = noneCharacter * self.length
+        """cmseq/cmseq.py:226-241: the rule's call for every column that has statistics, `noneCharacter` elsewhere; the string is
+        also kept in `self.consensus`."""
+        stats = self.get_base_stats(min_read_depth=mincov, min_base_quality=minqual, dominant_frq_thrsh=dominant_frq_thrsh,
+                                    BAM_tagFilter=BAM_tagFilter, trimReads=trimReads, error_rate=CMSEQ_DEFAULTS.poly_error_rate)
+        calls = [noneCharacter] * self.length
+        for pos1, column in stats.items():
+            calls[pos1 - 1] = consensus_rule(column)
+        self.consensus = ''.join(calls)
         return self.consensus
 
     def polymorphism_rate(self, mincov=CMSEQ_DEFAULTS.mincov, minqual=CMSEQ_DEFAULTS.minqual, pvalue=CMSEQ_DEFAULTS.poly_pvalue_threshold,
                           error_rate=CMSEQ_DEFAULTS.poly_error_rate, dominant_frq_thrsh=CMSEQ_DEFAULTS.poly_dominant_frq_thrsh):
-        """cmseq/cmseq.py:430-456."""
-        base_values = self.get_base_stats(min_read_depth=mincov, min_base_quality=minqual, error_rate=error_rate, dominant_frq_thrsh=dominant_frq_thrsh)
-        rv = {}
-        rv['total_covered_bases'] = len(base_values)
-        rv['total_polymorphic_bases'] = 0
-        if len(base_values) > 0:
-            pb = sum([(1 if (info['p'] < pvalue and info['ratio_max2all'] < dominant_frq_thrsh) else 0) for pox, info in base_values.items()])
-            rv['total_polymorphic_bases'] = pb
-            rv['total_polymorphic_rate'] = float(pb) / float(len(base_values))
-            if pb > 0:
-                rv['ratios'] = [info['ratio_max2all'] for pox, info in base_values.items() if (info['p'] < pvalue and info['ratio_max2all'] < dominant_frq_thrsh)]
-                rv['dominant_allele_distr_mean'] = np.mean(rv['ratios'])
-                rv['dominant_allele_distr_sd'] = np.std(rv['ratios'])
-                for i in [10, 20, 30, 40, 50, 60, 70, 80, 90, 95, 98, 99]:
-                    rv['dominant_allele_distr_perc_' + str(i)] = np.percentile(rv['ratios'], i)
+        """cmseq/cmseq.py:430-456: a column is polymorphic when its p-value is under `pvalue` AND its dominant base is under
+        `dominant_frq_thrsh`; the distribution keys appear only when there is at least one such column (same keys, same order)."""
+        stats = self.get_base_stats(min_read_depth=mincov, min_base_quality=minqual, error_rate=error_rate, dominant_frq_thrsh=dominant_frq_thrsh)
+        n_cov = len(stats)
+        ratios = [col['ratio_max2all'] for col in stats.values() if col['p'] < pvalue and col['ratio_max2all'] < dominant_frq_thrsh]
+        rv = {'total_covered_bases': n_cov, 'total_polymorphic_bases': 0}
+        if n_cov == 0:
+            return rv
+        rv['total_polymorphic_bases'] = len(ratios)
+        rv['total_polymorphic_rate'] = float(len(ratios)) / float(n_cov)
+        if ratios:
+            rv['ratios'] = ratios
+            rv['dominant_allele_distr_mean'] = np.mean(ratios)
+            rv['dominant_allele_distr_sd'] = np.std(ratios)
+            for pct in (10, 20, 30, 40, 50, 60, 70, 80, 90, 95, 98, 99):
+                rv['dominant_allele_distr_perc_' + str(pct)] = np.percentile(ratios, pct)
         return rv
 
     def breadth_and_depth_of_coverage(self, mincov=10, minqual=30, trunc=0):
