@@ -1,0 +1,73 @@
+"""What the compiler made of the hot kernels, checked without a GPU on the objects `build()` leaves in csrc/: the ring score
+kernel and the bit-sliced pileup really move their tiles with TMA bulk copies completing on mbarriers (SASS `UBLKCP`, `SYNCS`),
+the warp reductions are single `REDUX` instructions, the Hamming kernel counts with `POPC`, and the hot kernels do not spill
+registers to local memory (ptxas -v logs; the pileup kernel is allowed the 16 bytes it parks outside its loop)."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+CSRC = os.path.join(ROOT, "metamlst_b200", "csrc")
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+
+def _sass(obj):
+    path = os.path.join(CSRC, obj)
+    if not os.path.exists(path) or not os.path.exists(CUOBJDUMP):
+        pytest.skip("needs the objects of build() and cuobjdump")
+    out = subprocess.run([CUOBJDUMP, "-sass", path], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=300).stdout.decode(errors="replace")
+    funcs = {}
+    cur = None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = []
+        elif cur is not None:
+            funcs[cur].append(line)
+    return {k: "\n".join(v) for k, v in funcs.items()}
+
+
+def test_ring_score_kernels_use_tma_and_mbarriers():
+    f = _sass("score_runs.o")
+    ring = {k: v for k, v in f.items() if "ring" in k}
+    assert len(ring) >= 9, sorted(f)
+    for name, sass in ring.items():
+        assert "UBLKCP" in sass, name          # cp.async.bulk: the stages are filled by the TMA unit
+        assert "SYNCS" in sass, name           # mbarrier arrive.expect_tx / try_wait
+        assert "REDUX" in sass, name           # warp sums as one instruction
+        assert "IDP" in sass, name             # dp2a: masked sum of two int16 per instruction
+        assert not re.search(r"\b(LDL|STL)\b", sass), name  # no local-memory traffic
+    regs = [v for k, v in f.items() if "score_runs_kernel" in k]
+    assert regs and all("UBLKCP" not in v for v in regs)  # the register forms load through LDG only
+
+
+def test_pileup_and_hamming_instruction_selection():
+    p = _sass("pileup_bitsliced.o")
+    kern = [v for k, v in p.items() if "pileup_bitsliced_kernel" in k]
+    assert kern and all("UBLKCP" in v and "SYNCS" in v and "LOP3" in v for v in kern)
+    h = _sass("hamming.o")
+    kern = [v for k, v in h.items() if "hamming_min_kernel" in k]
+    assert kern and all("POPC" in v and "LDGSTS" in v for v in kern)  # popcount distance, cp.async query staging
+
+
+def test_hot_kernels_do_not_spill():
+    bad = []
+    for log in ("score_runs", "score", "pileup_bitsliced", "hamming", "select", "consensus"):
+        path = os.path.join(CSRC, log + ".ptxas.log")
+        if not os.path.exists(path):
+            pytest.skip("needs the ptxas logs of build()")
+        text = open(path).read()
+        for m in re.finditer(r"Compiling entry function '(\S+)'.*?\n.*?\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", text):
+            name, _stack, st, ld = m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(4))
+            if "pileup_bitsliced" in name:
+                # 128 registers at 2 CTAs per SM hold 50 bit-sliced counter planes: ptxas parks a few bytes outside the tile loop
+                if st > 32 or ld > 32:
+                    bad.append((name, st, ld))
+            elif (st or ld) and ("ring" in name or "hamming_min" in name or "ILb0ELb0ELb1E" in name):
+                bad.append((name, st, ld))
+    assert not bad, bad
