@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--pileup-impl", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true", help="skip uncapped / hamming / cpu baseline extras")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay of the pass")
-    ap.add_argument("--cpu-sample-reads", type=int, default=400_000)
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the full-workload comparison with the C port of the oracle after the timed region")
     ap.add_argument("--only-hamming", action="store_true", help="run only the configs[4] Hamming sweep (profiling aid)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "gather", "allreduce"],
                     help="N>1: 'p2p' = owner mode, result blocks stored into the peers' memory over NVLink by our own kernels; 'gather' = owner mode, "
@@ -136,23 +136,42 @@ def make_db(args):
     return synth.make_db(ORGS, alleles_per_locus=args.alleles, n_profiles=2048, seed=1002)
 
 
-def gen_streams(db, args, device, max_depth, locus_subset=None, seed=1002, n_reads=None, chunk=1_000_000, want_qhash=False):
-    from metamlst_b200 import devpack, synth
-    import torch
+def gen_cores(db, args, device, locus_subset=None, seed=1002, n_reads=None, chunk=1_000_000):
+    """The reads of one synthetic sample as synth.gen_core chunks (deterministic in (seed, device kind))."""
+    from metamlst_b200 import synth
     n_reads = n_reads or args.reads
     cores = []
     for i, c0 in enumerate(range(0, n_reads, chunk)):
         core = synth.gen_core(db, min(chunk, n_reads - c0), args.read_len, seed=seed * 1000 + i, K=args.k, org_props=PROPS,
                               device=device, strain_seed=1002, locus_subset=locus_subset)
-        # keep only what the packer needs
+        # keep only what the packers need
         cores.append({k: core[k] for k in ("L", "K", "bases", "qual", "rtype", "a_split", "rows", "start", "flag", "AS", "xm")})
         del core
+    return cores
+
+
+def gen_streams(db, args, device, max_depth, locus_subset=None, seed=1002, n_reads=None, chunk=1_000_000, want_qhash=False):
+    from metamlst_b200 import devpack
+    import torch
+    cores = gen_cores(db, args, device, locus_subset, seed, n_reads, chunk)
     st = devpack.pack_cores(db, cores, 20, max_depth, want_qhash=want_qhash)
     n_ops = sum(int((c["rtype"] != 0).sum()) * 2 for c in cores) * args.k  # extra CIGAR ops beyond 1 per record
     del cores
     if device != "cpu":
         torch.cuda.empty_cache()
     return st, n_ops
+
+
+def cpu_workload(db, args, device, locus_subset=None, seed=1002, n_reads=None):
+    """The SAME sample (same generator, seeds and record order) unpacked on the host for the C port of the oracle."""
+    import torch
+    from oracle import cpu_path
+    cores = gen_cores(db, args, device, locus_subset, seed, n_reads)
+    w = cpu_path.workload_from_cores(db, cores)
+    del cores
+    if device != "cpu":
+        torch.cuda.empty_cache()
+    return w
 
 
 def pileup_alg_bytes(st, tids, L):
@@ -167,62 +186,59 @@ def event_ms(pairs):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_port_run(db, args, n_reads, threads, steps=1, warmup=0):
-    """The oracle's C port (oracle/c) on the host: score + depth-cap simulation + pileup + consensus on a sample of
-    the same workload.  Returns (records/s, description)."""
-    import torch
+def cpu_port_run(w, args, threads, steps=1, warmup=0):
+    """The oracle's C port (oracle/cpu_path.py over oracle/c) on the host cores over the WHOLE sample `w`: score of every record,
+    selection, htslib depth-cap simulation over every record of the chosen contigs, pileup of the admitted ones, consensus --
+    the regime of the GPU arm (same records, same cap).  Returns (records/s, seconds per step, last result, description)."""
     from concurrent.futures import ThreadPoolExecutor
-    from metamlst_b200 import api, synth
-    from oracle import corc
-    dev = "cuda" if torch.cuda.is_available() else "cpu"
-    tab = synth.make_sample(db, n_reads, args.read_len, seed=1002001, K=args.k, org_props=PROPS, device=dev, strain_seed=1002)
-    tab = tab.sorted_by_coord()
-    index = api.AlleleIndex(tab.ref_names)
-    allow = np.ones(db.n_rows, np.uint8)
-    locus_of = db.row_locus.astype(np.uint32)
-    n = tab.n
-    bounds = np.linspace(0, n, threads + 1).astype(np.int64)
-    parts = [tab.take(np.arange(bounds[i], bounds[i + 1])) for i in range(threads)]
-    pool = ThreadPoolExecutor(threads)
-
-    def one_step():
-        res = list(pool.map(lambda p: corc.score(p, allow, locus_of, len(db.locus_names), PARAMS["minscore"], PARAMS["max_xM"], PARAMS["min_read_len"]), parts))
-        s = sum(r[0] for r in res); c = sum(r[1].astype(np.int64) for r in res).astype(np.uint32)
-        f = np.minimum.reduce([r[2] for r in res])
-        chosen = api.fast_select(index, s, c, f, PARAMS["penalty"])
-        tids = [t for _sp, ts in chosen for t in ts]
-
-        def contig(t):
-            counts, _ = corc.contig_counts(tab, t, 20, PARAMS["minscore"], PARAMS["max_xM"], 8000)
-            return corc.consensus(counts, db.row_seq(t).encode(), 1)
-        return list(pool.map(contig, tids))
-
+    from oracle import cpu_path
+    pool = ThreadPoolExecutor(threads) if threads > 1 else None
+    kw = dict(minscore=PARAMS["minscore"], max_xM=PARAMS["max_xM"], min_read_len=PARAMS["min_read_len"], penalty=PARAMS["penalty"],
+              max_depth=args.max_depth or None, threads=threads, pool=pool)
     for _ in range(warmup):
-        one_step()
+        cpu_path.run(w, **kw)
+    phases = {}
     t0 = time.perf_counter()
     for _ in range(steps):
-        one_step()
+        res = cpu_path.run(w, **kw)
+        for k, v in res["seconds"].items():
+            phases[k] = phases.get(k, 0.0) + v / steps
     dt = (time.perf_counter() - t0) / steps
-    return n / dt, dt, "%d reads x K=%d = %d records of the same generator (1/%d of the workload), C port of the oracle, %d threads" % (
-        n_reads, args.k, n, max(1, args.reads // n_reads), threads)
+    if pool is not None:
+        pool.shutdown()
+    sample = ("the WHOLE sample of `config.workload` (%d records; %d on the chosen contigs walked by the htslib depth-cap simulation, %d of them "
+              "admitted and piled up), C port of the oracle (oracle/c/mlst_oracle.c via oracle/cpu_path.py), %d thread(s); seconds per step: "
+              "score %.4f, select %.4f, depth cap + pileup + consensus %.4f" % (
+                  w.n, res["chosen_contig_records"], res["piled_records"], threads, phases["score"], phases["select"], phases["depthcap_pileup_consensus"]))
+    return w.n / dt, dt, res, sample, phases
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference itself is pure Python over pysam / samtools /
+    Biopython, none of which exist on the box, so this arm times the C port of its restatement -- a FASTER
+    stand-in -- on all host threads over the same full sample the GPU arm types (same generator, seeds, depth cap)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if args.lanes <= 0:  # same `config` text as our arm
-        args.lanes = 6
+    import torch
     db = make_db(args)
     threads = os.cpu_count() or 1
-    rate, dt, sample = cpu_port_run(db, args, args.cpu_sample_reads, threads, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    dev = "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0")) if torch.cuda.is_available() else "cpu"
+    w = cpu_workload(db, args, dev)
+    steps = max(1, args.steps)
+    rate, dt, _res, sample, phases = cpu_port_run(w, args, threads, steps=steps, warmup=min(max(args.warmup, 0), 2))
+    cfg = workload_config(args, 1)
     line = {"impl": "reference", "metric": "aligned reads/s (score+pileup+consensus)", "value": rate, "unit": "records/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32/u8", "data": "synthetic",
-            "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))), "gpu_launches": 0,
+            "config": {"workload": cfg["workload"], "mode": cfg["mode"],
+                       "arm": "host cores only: C port of the oracle, %d threads, records unpacked in host memory (score: %d record ranges; pileup: "
+                              "one chosen contig per task)" % (threads, threads)},
+            "gpu_launches": 0, "seconds_by_phase": phases,
             "cpu_baseline": {"value": rate, "unit": "records/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "the reference itself (pure Python over pysam/samtools) cannot run on this box; this is the C port of its restatement (oracle/c), a faster stand-in"}
+            "note": "the reference itself (pure Python over pysam/samtools) cannot run on this box; this is the C port of its restatement (oracle/c), "
+                    "a faster stand-in; the Python reference measured in the build container: profiles/r1_reference_python_timing.json (4.0e3 records/s)"}
     emit(line)
 
 
@@ -513,6 +529,45 @@ def main():
     ctx.close()
     del soa
 
+    if not args.no_parity_check:
+        # the benchmarked sample against the C port of the oracle, at FULL size (every rank on its own shard): score tables, chosen alleles,
+        # consensus strings, holes, SNPs.  The same CPU pass is the `cpu_baseline` (rank 0, N=1): all host threads, and one thread.
+        w = cpu_workload(db, args, device, subset, seed=1002 + rank)
+        ncpu = os.cpu_count() or 1
+        rate, dt_cpu, ref, sample, phases = cpu_port_run(w, args, ncpu, steps=1 if world > 1 else 3, warmup=0 if world > 1 else 1)
+        pipe.reset_tables()
+        pipe._score_call()
+        torch.cuda.synchronize()
+        checked = []
+        if not (world > 1 and args.exchange == "allreduce"):
+            assert np.array_equal(pipe.sum_as.cpu().numpy(), ref["sum_as"]), "sum_as differs from the C port on the full workload"
+            assert np.array_equal(pipe.n_hit.cpu().numpy().view(np.uint32), ref["n_hit"]), "n_hit differs from the C port on the full workload"
+            hit = ref["n_hit"] > 0
+            assert np.array_equal(pipe.first_idx.cpu().numpy().view(np.uint32)[hit] - np.uint32(pipe.idx_base), ref["first_idx"][hit]), "first_idx differs"
+            assert pipe.counters.cpu().numpy().view(np.uint64).tolist() == ref["counters"].tolist(), "totalReads / ignoredReads differ"
+            checked += ["sum_as", "n_hit", "first_idx", "totalReads", "ignoredReads"]
+        pipe._clean = False
+        mine = {c: (s_, h_, n_) for sp in out for (c, s_, h_, n_) in out[sp]}
+        want = {c: (s_, h_, n_) for sp in ref["result"] for (c, s_, h_, n_) in ref["result"][sp]}
+        if world == 1:
+            assert out == ref["result"], "chosen alleles / consensus / holes / SNPs (or their dict order) differ from the C port on the full workload"
+            checked += ["species and locus order", "chosen alleles", "consensus", "holes", "snps"]
+        else:
+            assert all(mine.get(c) == v for c, v in want.items()), "this rank's loci differ from the C port on the full workload"
+            checked += ["chosen alleles", "consensus", "holes", "snps (this rank's loci inside the merged result)"]
+        ok = torch.tensor([1], dtype=torch.int32, device=device)
+        if world > 1:
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        line["parity_full_workload"] = {"ok": bool(ok.item()), "against": "oracle/c via oracle/cpu_path.py (C port of the oracle), same records", "records": w.n,
+                                        "chosen_contig_records": ref["chosen_contig_records"], "piled_records": ref["piled_records"], "checked": checked,
+                                        "ranks": world}
+        if rank == 0 and world == 1:
+            line["cpu_baseline"] = {"value": rate, "unit": "records/s", "cores": ncpu, "kind": "port", "sample": sample, "seconds_by_phase": phases,
+                                    "host_cpus": os.cpu_count()}
+            if not args.no_extras:
+                r1, dt1, _r, sample1, ph1 = cpu_port_run(w, args, 1, steps=1)
+                line["cpu_baseline"]["single_thread"] = {"value": r1, "unit": "records/s", "cores": 1, "seconds_by_phase": ph1}
+        del w
     if world > 1 and not args.no_extras:
         # the other exchange form on the same shards, and the row-sharded Hamming sweep (configs[4])
         line["other_exchange"] = []
@@ -540,8 +595,6 @@ def main():
         line["uncapped"] = extra_uncapped(db, args, device, index, peak)
         line["hamming"] = extra_hamming(device, peak)
         line["coverage_column"] = extra_coverage(db, args, device, index)
-        rate, dt, sample = cpu_port_run(db, args, args.cpu_sample_reads, 1)
-        line["cpu_baseline"] = {"value": rate, "unit": "records/s", "cores": 1, "kind": "port", "sample": sample, "host_cpus": os.cpu_count()}
     if rank == 0:
         emit(line)
     if world > 1:

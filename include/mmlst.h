@@ -116,10 +116,10 @@ int mmlst_score_runs_qc_dev(const uint32_t* run_tid, const uint32_t* run_start, 
 /* Kernel form used by mmlst_score_runs_dev / mmlst_score_runs_qc_dev (identical results): 0 = register-staged, 1 = register-
  * staged and software-pipelined, 2 = per-warp shared-memory ring filled by TMA bulk copies (records without orig_idx only;
  * other inputs take form 0), 3..5 = the ring with other stage sizes / depths (4 chunks x 3 stages, 8 x 2, 4 x 2),
- * 6 = EXPERIMENTAL, not yet timed on hardware: form 5 with pairs of chunks reduced together (per-chunk len(SEQ) streams;
- * others take form 5).  Returns the previous value; a value outside 0..6 only queries.  The environment variable
+ * 6 = form 5 with pairs of chunks reduced together (per-chunk len(SEQ) streams; others take form 5): the default since
+ * round 2 (B200, configs[1]: 26.7 us against 28.8 us for form 5, profiles/r2a_bench_auto.json).  Returns the previous value; a value outside 0..6 only queries.  The environment variable
  * MMLST_SCORE_VARIANT presets it. */
-#define MMLST_SCORE_VARIANT_DEFAULT 5
+#define MMLST_SCORE_VARIANT_DEFAULT 6
 int mmlst_set_score_variant(int variant);
 /* Ring forms only: L2 residency hints (score stream evict-first; run arrays, allow[] and chunk_qlen[] evict-last, so that the
  * small tables every warp starts from survive in the L2 from one launch to the next).  1 = on, 0 = off, other = query;

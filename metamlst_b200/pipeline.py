@@ -375,8 +375,8 @@ class DevicePipeline:
         out: Dict[str, float] = {}
         want = None
         keys = ["0", "1", "2", "3", "4", "5", "2h", "3h", "4h", "5h"]  # "h": ring form with the L2 residency hints
-        if os.environ.get("MMLST_EXPERIMENTAL_FORMS") and self.use_qc:
-            keys.append("6")  # pair-fused ring: verified on the host emulation only until a GPU visit has run it
+        if self.use_qc:
+            keys.append("6")  # pair-fused ring (per-chunk len(SEQ) streams only)
         for key in keys:
             v = int(key[0])
             self.lib.mmlst_set_score_variant(v)

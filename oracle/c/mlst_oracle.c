@@ -15,14 +15,15 @@
 /* metamlst.py:101-130 + integer half of :133-151 */
 void orc_score(uint64_t n, const int32_t* tid, const int32_t* aux0, const int32_t* aux3, const int32_t* qlen,
                const uint32_t* orig_idx, const uint8_t* allow, const uint32_t* locus_of, int minscore, int max_xm,
-               int min_read_len, int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, uint64_t* counters) {
+               int min_read_len, int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, uint64_t* counters, uint64_t idx_base) {
+    /* idx_base: file-order index of record 0 of this range when orig_idx is NULL (range-split scoring) */
     for (uint64_t i = 0; i < n; ++i) {
         const int32_t t = tid[i];
         if (!allow[t]) continue;                                   /* :114 */
         if (aux0[i] >= minscore && qlen[i] >= min_read_len && aux3[i] <= max_xm) { /* :115 */
             sum_as[t] += aux0[i];
             n_hit[t] += 1;
-            const uint32_t oi = orig_idx ? orig_idx[i] : (uint32_t)i;
+            const uint32_t oi = orig_idx ? orig_idx[i] : (uint32_t)(idx_base + i);
             if (oi < first_idx[t]) first_idx[t] = oi;
         } else {
             counters[1] += 1;                                      /* :129 */
@@ -70,32 +71,50 @@ int orc_depth_cap_sim(uint64_t n, int32_t tid, const int32_t* pos, const int32_t
     return 0;
 }
 
-/* cmseq/cmseq.py:527-548 for the admitted records of one contig: counts[len][5] bins A,C,G,T,N.
- * seq/qual: n x L row-major (ASCII / phred); cigar: BAM words at cig_off[i]..cig_off[i+1]. */
+/* cmseq/cmseq.py:527-548 for ONE admitted record: walk its CIGAR, bin every aligned base into counts[len][5] (A,C,G,T,N). */
+static void pile_one(int64_t r, const uint32_t* cig, int64_t n_cig, const uint8_t* seq, const uint8_t* qual, int L, int pass,
+                     int minqual, int32_t contig_len, uint32_t* counts) {
+    int q = 0;
+    for (int64_t c = 0; c < n_cig; ++c) {
+        const uint32_t op = cig[c] & 0xF, len = cig[c] >> 4;
+        if (op == 0 || op == 7 || op == 8) {
+            for (uint32_t k = 0; k < len; ++k, ++r, ++q) {
+                if (r < 0 || r >= contig_len) continue;
+                const int qv = (q < L) ? qual[q] : 0;  /* pysam pileup_base_qual_skip (H3) */
+                if (qv < minqual) continue;
+                uint8_t b = (q < L) ? seq[q] : 'N';
+                if (b >= 'a' && b <= 'z') b -= 32;                       /* .upper(), :537 */
+                int bin = 4;
+                if (pass) { if (b == 'A') bin = 0; else if (b == 'C') bin = 1; else if (b == 'G') bin = 2; else if (b == 'T') bin = 3; }
+                counts[r * 5 + bin] += 1;
+            }
+        } else if (op == 1 || op == 4) q += len;      /* I, S: query only */
+        else if (op == 2 || op == 3) r += len;        /* D, N: is_del / is_refskip are skipped, :535 */
+    }
+}
+
+/* the admitted records of one contig.  seq/qual: n x L row-major (ASCII / phred); cigar: BAM words at cig_off[i]..cig_off[i+1]. */
 void orc_pileup(uint64_t n, const int32_t* pos, const int64_t* cig_off, const uint32_t* cig, const uint8_t* seq,
                 const uint8_t* qual, int L, const int32_t* as_named, const int32_t* xm_named, const uint8_t* admitted,
                 int minqual, int minscore, int max_xm, int32_t contig_len, uint32_t* counts) {
     for (uint64_t i = 0; i < n; ++i) {
         if (!admitted[i]) continue;
         const int pass = (as_named[i] >= minscore) && (xm_named[i] <= max_xm);  /* metaMLST_functions.py:259 */
-        int64_t r = pos[i];
-        int q = 0;
-        for (int64_t c = cig_off[i]; c < cig_off[i + 1]; ++c) {
-            const uint32_t op = cig[c] & 0xF, len = cig[c] >> 4;
-            if (op == 0 || op == 7 || op == 8) {
-                for (uint32_t k = 0; k < len; ++k, ++r, ++q) {
-                    if (r < 0 || r >= contig_len) continue;
-                    const int qv = (q < L) ? qual[i * (uint64_t)L + q] : 0;  /* pysam pileup_base_qual_skip (H3) */
-                    if (qv < minqual) continue;
-                    uint8_t b = (q < L) ? seq[i * (uint64_t)L + q] : 'N';
-                    if (b >= 'a' && b <= 'z') b -= 32;                       /* .upper(), :537 */
-                    int bin = 4;
-                    if (pass) { if (b == 'A') bin = 0; else if (b == 'C') bin = 1; else if (b == 'G') bin = 2; else if (b == 'T') bin = 3; }
-                    counts[r * 5 + bin] += 1;
-                }
-            } else if (op == 1 || op == 4) q += len;      /* I, S: query only */
-            else if (op == 2 || op == 3) r += len;        /* D, N: is_del / is_refskip are skipped, :535 */
-        }
+        pile_one(pos[i], cig + cig_off[i], cig_off[i + 1] - cig_off[i], seq + i * (uint64_t)L, qual + i * (uint64_t)L, L, pass,
+                 minqual, contig_len, counts);
+    }
+}
+
+/* same, for a table that stores SEQ / QUAL / CIGAR once per READ and K alignment records per read (bowtie2 -k): record i
+ * belongs to read read_of[i]; cig3 holds up to 3 BAM CIGAR words per read, n_cig[read] of them used. */
+void orc_pileup_reads(uint64_t n, const int32_t* pos, const int64_t* read_of, const uint32_t* cig3, const uint8_t* n_cig,
+                      const uint8_t* seq, const uint8_t* qual, int L, const int32_t* as_named, const int32_t* xm_named,
+                      const uint8_t* admitted, int minqual, int minscore, int max_xm, int32_t contig_len, uint32_t* counts) {
+    for (uint64_t i = 0; i < n; ++i) {
+        if (!admitted[i]) continue;
+        const int pass = (as_named[i] >= minscore) && (xm_named[i] <= max_xm);
+        const uint64_t rd = (uint64_t)read_of[i];
+        pile_one(pos[i], cig3 + 3 * rd, n_cig[rd], seq + rd * (uint64_t)L, qual + rd * (uint64_t)L, L, pass, minqual, contig_len, counts);
     }
 }
 

@@ -47,7 +47,7 @@ def score(tab, allow, locus_of, n_loci, minscore=80, max_xm=5, min_read_len=50, 
     allow_a = np.ascontiguousarray(allow, np.uint8)  # keep temporaries alive across the call
     locus_a = np.ascontiguousarray(locus_of, np.uint32)
     lib().orc_score(C.c_uint64(tab.n), _p(tid), _p(aux0), _p(aux3), _p(qlen), _p(oi), _p(allow_a),
-                    _p(locus_a), minscore, max_xm, min_read_len, _p(sum_as), _p(n_hit), _p(first), _p(counters))
+                    _p(locus_a), minscore, max_xm, min_read_len, _p(sum_as), _p(n_hit), _p(first), _p(counters), C.c_uint64(0))
     return sum_as, n_hit, first, counters
 
 

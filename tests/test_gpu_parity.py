@@ -23,7 +23,7 @@ def ctx():
 
 
 # forms of the run-length score kernel (mmlst_set_score_variant) the stage-1 tests run under
-SCORE_VARIANTS = tuple(int(x) for x in os.environ.get("MMLST_TEST_SCORE_VARIANTS", "5,0,1,2").split(","))  # 5 = the library default
+SCORE_VARIANTS = tuple(int(x) for x in os.environ.get("MMLST_TEST_SCORE_VARIANTS", "6,5,0,2").split(","))  # 6 = the library default
 
 
 @pytest.fixture(params=SCORE_VARIANTS, ids=lambda v: "form%d" % v)

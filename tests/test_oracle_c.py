@@ -96,3 +96,29 @@ def test_hamming_matches_string_diff():
     for i, (q, (r0, r1)) in enumerate(zip(qs, [(0, 40), (0, 40), (5, 30)])):
         dd = [orc.string_diff(q, rows[r]) for r in range(r0, r1)]
         assert int(d[i]) == min(dd) and int(a[i]) == r0 + dd.index(min(dd))
+
+
+@pytest.mark.parametrize("threads,max_depth", [(1, 8000), (3, 8000), (2, 40), (1, None)])
+def test_cpu_path_whole_sample_matches_python_oracle(threads, max_depth):
+    """oracle/cpu_path.py (what bench.py times as the CPU baseline and checks the GPU arm against at full size): the same
+    sample as an AlnTable through the Python oracle's stage 1 / selection / build_consensus."""
+    from metamlst_b200 import synth
+    from oracle import cpu_path
+    db = synth.make_db(("ecoli", "saureus"), alleles_per_locus=6, n_profiles=8, seed=11)
+    kw = dict(read_len=100, seed=5, K=3, org_props=(0.6, 0.4))
+    tab = synth.make_sample(db, 1500, **kw).sorted_by_coord()
+    core = synth.gen_core(db, 1500, **kw)
+    w = cpu_path.workload_from_cores(db, [core])
+    assert np.array_equal(w.tid, tab.tid) and np.array_equal(w.pos, tab.pos) and np.array_equal(w.aux0, tab.AS)
+    got = cpu_path.run(w, minscore=150, max_xM=4, min_read_len=50, penalty=100, max_depth=max_depth, threads=threads)
+    h, recs = table_to_records(tab)
+    cel, _bank, total, ignored = orc.stage1(h, recs, minscore=150, max_xM=4, min_read_len=50, penalty=100)
+    assert (int(got["counters"][0]), int(got["counters"][1])) == (total, ignored)
+    assert got["cel"] == cel and [list(v) for v in got["cel"].values()] == [list(v) for v in cel.values()]  # values and dict order
+    want = {}
+    for sp, genes in cel.items():
+        chrom = {"%s_%s_%s" % (sp, g, a): db.row_seq(tab.ref_names.index("%s_%s_%s" % (sp, g, a))) for g, a in orc.select_alleles(genes)}
+        for rec in orc.build_consensus(h, recs, chrom, 150, 4, max_depth=max_depth if max_depth else 1 << 30):
+            holes, snps = rec.description.split("_")
+            want.setdefault(sp, []).append((rec.id, str(rec.seq), int(holes.split("::")[1]), int(snps.split("::")[1])))
+    assert got["result"] == want
