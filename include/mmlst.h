@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define MMLST_VERSION 102
+#define MMLST_VERSION 200
 
 enum {
     MMLST_OK = 0,
@@ -343,6 +343,47 @@ int mmlst_db_upload_x(mmlst_ctx* ctx, const uint32_t* db_hi, const uint32_t* db_
 int mmlst_hamming_min_x(mmlst_ctx* ctx, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
                         const uint32_t* xq_ids, const uint32_t* xq_x, const uint8_t* xq_bytes, uint32_t n_xq,
                         const uint32_t* blocks, uint32_t n_blocks, uint32_t* min_dist, uint32_t* argmin_row);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Exact-sequence lookup (row a10).  Replaces the un-indexed scans `SELECT .. FROM alleles WHERE sequence = ? AND bacterium = ?`
+ * + fetchone() of sequenceExists / sequenceFind / sequenceLocate (metaMLST_functions.py:168-172, 196-203, 218-222):
+ *   first_row[q] = lowest DB row (or lowest row_key[row], see mmlst_db_row_keys) inside the query's block (= the organism's row range, table order) whose sequence equals the
+ *   query character for character -- same length AND same characters, case-sensitive like SQLite's `=` (H10); 0xFFFFFFFF when
+ *   there is none (caller presets it for the _dev form).  Same DB / query layouts and `blocks` as mmlst_hamming_min_dev; the
+ *   flagged (non-ACGT, bit 15 of the length) sequences compare their stored bytes (x*_ids ascending, x*_bytes [n][W*32]).
+ *   Not "zip-Hamming distance 0": the truncating distance is also 0 against a prefix or an extension of the query.
+ * --------------------------------------------------------------------------------------------------------------- */
+int mmlst_exact_match_dev(const uint32_t* db_hi, const uint32_t* db_lo, const uint16_t* row_len, uint32_t n_rows, uint32_t W,
+                          const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
+                          const uint32_t* blocks, uint32_t n_blocks, uint32_t max_block_rows, uint32_t row_index_base,
+                          const uint32_t* row_key /* NULL: key = row + row_index_base */, const uint32_t* xr_ids, const uint8_t* xr_bytes, uint32_t n_xr,
+                          const uint32_t* xq_ids, const uint8_t* xq_bytes, uint32_t n_xq, uint32_t* first_row, void* stream);
+/* host buffers, against the DB made resident by mmlst_db_upload[_x].  mmlst_db_row_keys attaches a key per resident row (its
+ * position in table order when the rows are resident grouped by locus): first_row[q] is then the lowest KEY of an equal row,
+ * which is what fetchone() returns when several genes of the organism hold the same sequence.  NULL detaches. */
+int mmlst_db_row_keys(mmlst_ctx* ctx, const uint32_t* row_key, uint32_t n_rows);
+int mmlst_exact_match(mmlst_ctx* ctx, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
+                      const uint32_t* xq_ids, const uint8_t* xq_bytes, uint32_t n_xq,
+                      const uint32_t* blocks, uint32_t n_blocks, uint32_t* first_row);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Seam S4 -- ST assignment (row a11).  Replaces the GROUP BY / HAVING statement of defineProfile (metaMLST_functions.py:205-216):
+ * among the rows of `profiles` whose alleleCode is one of the query's allele codes, count per profileCode; answer = the
+ * profiles whose count equals the maximum, ascending by profileCode (SQLite's GROUP BY order), and that count.
+ *   prof_start[n_st+1], prof_allele[]: the `profiles` table grouped by profileCode, profiles ascending by code;
+ *                                      prof_allele = alleleCode (alleles.recID) of every row of the group
+ *   q_alleles[n_q][l_max], q_n[n_q]  : allele codes of every query (labels already resolved to recIDs; unknown labels dropped
+ *                                      by the caller, H11).  A code listed twice counts a row once (`IN` is a set test).
+ *   best[q] = the maximum count (0: no profile row matches), n_best[q] = number of profiles reaching it,
+ *   out_idx[q][max_out] = their indices into the grouped table, ascending (the first max_out of them).
+ *   count: device scratch n_q * n_st u32.  The percentage int(best / len(recs) * 100) stays on the host (Python floats, H6).
+ * --------------------------------------------------------------------------------------------------------------- */
+int mmlst_st_match_dev(const uint32_t* prof_start, const uint32_t* prof_allele, uint32_t n_st,
+                       const uint32_t* q_alleles, const uint32_t* q_n, uint32_t l_max, uint32_t n_q,
+                       uint32_t* count, uint32_t* best, uint32_t* n_best, uint32_t* out_idx, uint32_t max_out, void* stream);
+int mmlst_profiles_upload(mmlst_ctx* ctx, const uint32_t* prof_start, const uint32_t* prof_allele, uint32_t n_st);
+int mmlst_st_match(mmlst_ctx* ctx, const uint32_t* q_alleles, const uint32_t* q_n, uint32_t l_max, uint32_t n_q,
+                   uint32_t* best, uint32_t* n_best, uint32_t* out_idx, uint32_t max_out);
 
 /* Raw DEFLATE (RFC 1951) of ONE complete stream, e.g. the payload of a BGZF block, into a buffer of known size: the decoder
  * the BAM unpacker uses instead of zlib's inflate() (whole-buffer, 64-bit bit buffer, two-level tables; every access is

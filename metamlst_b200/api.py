@@ -204,6 +204,7 @@ class HammingIndex:
         self.ctx = ctx
         order = sorted(range(len(rows)), key=lambda i: (rows[i][0], rows[i][1]))  # stable: keeps table order inside a locus
         self.rows = [rows[i] for i in order]
+        self.table_pos = np.asarray(order, dtype=np.int64)  # position in table (rowid) order of every resident row
         self.block: Dict[Tuple[str, str], Tuple[int, int]] = {}
         for i, (b, g, _v, _s) in enumerate(self.rows):
             lo, hi = self.block.get((b, g), (i, i))
@@ -216,6 +217,9 @@ class HammingIndex:
         self.n_flagged_rows = int(xids.size)
         native.check(native.lib().mmlst_db_upload_x(ctx.handle, native.ptr(self._hi), native.ptr(self._lo), native.ptr(self._len),
                                                     len(self.rows), self.W, native.ptr(xids), native.ptr(xx), native.ptr(xb), int(xids.size)))
+        self._keys = self.table_pos.astype(np.uint32)
+        self._row_of_key = np.argsort(self.table_pos)
+        native.check(native.lib().mmlst_db_row_keys(ctx.handle, native.ptr(self._keys), len(self.rows)))
 
     @classmethod
     def from_sqlite(cls, ctx, conn, bacterium: Optional[str] = None):
@@ -258,6 +262,50 @@ class HammingIndex:
         out_a[order] = am
         return out_d, out_a
 
+    def organism_range(self, bacterium: str) -> Optional[Tuple[int, int]]:
+        """Row range of every allele of the organism (rows are grouped by (bacterium, gene): one contiguous range)."""
+        lo = [r[0] for (b, _g), r in self.block.items() if b == bacterium]
+        hi = [r[1] for (b, _g), r in self.block.items() if b == bacterium]
+        return (min(lo), max(hi)) if lo else None
+
+    def exact_first(self, queries: Sequence[str], ranges: Sequence[Tuple[int, int]]) -> np.ndarray:
+        """Row a10 -- for every query the lowest row of its range whose sequence EQUALS it (same length, same characters, case-
+        sensitive), or 0xFFFFFFFF: `SELECT .. WHERE sequence = ? AND bacterium = ?` + fetchone() (metaMLST_functions.py:168-172,
+        196-203, 218-222) with the range = organism_range(bacterium).  Rows are resident grouped by (bacterium, gene); the kernel
+        minimises the row's position in TABLE order (mmlst_db_row_keys), so a sequence held by several genes resolves to the
+        row fetchone() returns; the value handed back is the resident row index (`self.rows[row]`)."""
+        nq = len(queries)
+        out = np.full(nq, NO_IDX, np.uint32)
+        if nq == 0:
+            return out
+        order = sorted(range(nq), key=lambda i: ranges[i])
+        qs = [queries[i].encode("latin-1") for i in order]
+        long = [i for i, q in enumerate(qs) if len(q) > self.W * 32]  # longer than every row: cannot equal any
+        if long:
+            qs = [q if len(q) <= self.W * 32 else b"" for q in qs]
+        hi, lo, ln, xids, _xx, xb = packing.encode_2bit_x(qs, self.W)
+        blocks = []
+        i = 0
+        while i < nq:
+            j = i
+            while j < nq and ranges[order[j]] == ranges[order[i]]:
+                j += 1
+            blocks.append((i, j, ranges[order[i]][0], ranges[order[i]][1]))
+            i = j
+        blk = np.asarray(blocks, dtype=np.uint32).reshape(-1)
+        got = np.full(nq, NO_IDX, np.uint32)
+        native.check(native.lib().mmlst_exact_match(self.ctx.handle, native.ptr(hi), native.ptr(lo), native.ptr(ln), nq, native.ptr(xids),
+                                                    native.ptr(xb), int(xids.size), native.ptr(blk), len(blocks), native.ptr(got)))
+        for i in long:
+            got[i] = NO_IDX
+        for i, q in enumerate(qs):
+            if len(q) == 0:  # the empty string equals only an empty DB sequence; never asked by the reference (`geneSeq == ''` short-cuts)
+                got[i] = NO_IDX
+        hit = got != NO_IDX
+        got[hit] = self._row_of_key[got[hit]].astype(np.uint32)  # table position -> resident row
+        out[order] = got
+        return out
+
     def closest_allele(self, bacterium: str, gene: str, seq: str) -> Tuple[int, int]:
         """(min distance, alleleVariant) over the rows of (bacterium, gene); flag of metamlst-merge.py:178 = d <= z."""
         rng = self.block.get((bacterium, gene))
@@ -278,6 +326,9 @@ def define_profile(conn, geneList: Sequence[str]):
     """Seam S4 -- metaMLST_functions.py:205-216 including H11: unknown labels shrink the denominator, [(0,0)] only
     when the LAST lookup failed.  Stays SQL (ms-scale)."""
     recs = []
+    if not geneList:
+        # upstream never binds `result` when the loop body does not run and dies on `if result` (metaMLST_functions.py:216)
+        raise UnboundLocalError("cannot access local variable 'result' where it is not associated with a value (defineProfile with an empty gene list)")
     result = None
     for allele in geneList:
         result = conn.execute("SELECT recID FROM alleles WHERE bacterium||'_'||gene||'_'||alleleVariant = ?", (allele,)).fetchone()
@@ -289,6 +340,57 @@ def define_profile(conn, geneList: Sequence[str]):
     q = ("SELECT profileCode, COUNT(*) as T FROM profiles WHERE alleleCode IN (" + inl + ") GROUP BY profileCode HAVING T = "
          "(SELECT COUNT(*) FROM profiles WHERE alleleCode IN (" + inl + ") GROUP BY profileCode ORDER BY COUNT(*) DESC LIMIT 1) ORDER BY T DESC")
     return [(row[0], int((float(row[1]) / float(len(recs))) * 100)) for row in conn.execute(q)]
+
+
+class ProfileIndex:
+    """Seam S4 on the device (row a11): the `profiles` table grouped by profileCode, resident in the context; label -> recID
+    resolved through a host dict built once (first row in table order, what the reference's fetchone() returns)."""
+
+    def __init__(self, ctx: native.Context, conn):
+        self.ctx = ctx
+        self.rec_of: Dict[str, int] = {}
+        for r in conn.execute("SELECT recID, bacterium, gene, alleleVariant FROM alleles ORDER BY recID"):
+            self.rec_of.setdefault("%s_%s_%s" % (r[1], r[2], r[3]), int(r[0]))
+        groups: Dict[int, List[int]] = {}
+        for r in conn.execute("SELECT profileCode, alleleCode FROM profiles"):
+            if r[1] is not None:
+                groups.setdefault(r[0], []).append(int(r[1]))
+        self.codes = sorted(groups)  # GROUP BY profileCode emits the groups in key order
+        start = np.zeros(len(self.codes) + 1, np.uint32)
+        start[1:] = np.cumsum([len(groups[c]) for c in self.codes])
+        flat = np.asarray([a for c in self.codes for a in groups[c]], dtype=np.int64)
+        if flat.size and (flat.min() < 0 or flat.max() >= 0xFFFFFFFF):
+            raise ValueError("alleleCode outside uint32")
+        self._start, self._flat = start, flat.astype(np.uint32)
+        native.check(native.lib().mmlst_profiles_upload(ctx.handle, native.ptr(self._start), native.ptr(self._flat), len(self.codes)))
+
+    def define_profiles(self, gene_lists: Sequence[Sequence[str]], max_out: int = 64) -> List[List[Tuple[int, int]]]:
+        """defineProfile(conn, geneList) for every list, ONE device call.  H11 kept: labels the DB does not know are dropped (the
+        denominator shrinks); [(0, 0)] when the LAST label of a list is unknown (or the list is empty: the reference raises
+        NameError there -- callers never pass one)."""
+        nq = len(gene_lists)
+        if nq == 0:
+            return []
+        recs = [[self.rec_of[l] for l in gl if l in self.rec_of] for gl in gene_lists]
+        lmax = max(1, max(len(r) for r in recs))
+        qa = np.full((nq, lmax), 0xFFFFFFFF, np.uint32)
+        qn = np.zeros(nq, np.uint32)
+        for i, r in enumerate(recs):
+            qa[i, :len(r)] = r
+            qn[i] = len(r)
+        best = np.zeros(nq, np.uint32); nb = np.zeros(nq, np.uint32); out = np.zeros((nq, max_out), np.uint32)
+        native.check(native.lib().mmlst_st_match(self.ctx.handle, native.ptr(qa), native.ptr(qn), lmax, nq, native.ptr(best), native.ptr(nb),
+                                                 native.ptr(out), max_out))
+        if int(nb.max()) > max_out:  # more tied profiles than asked for: once more with room for all of them
+            return self.define_profiles(gene_lists, int(nb.max()))
+        res = []
+        for i, gl in enumerate(gene_lists):
+            if not gl or gl[-1] not in self.rec_of:
+                res.append([(0, 0)])
+                continue
+            pct = int((float(best[i]) / float(len(recs[i]))) * 100)
+            res.append([(self.codes[int(p)], pct) for p in out[i, :int(nb[i])]])
+        return res
 
 
 def fast_select(index: AlleleIndex, sum_as: np.ndarray, n_hit: np.ndarray, first_idx: np.ndarray, penalty: int = 100):

@@ -23,11 +23,11 @@ int mmlst_cuda_fail(cudaError_t e, const char* what) {
 }
 
 int mmlst_num_sms() {
-    static int n = 0;
+    static int by_device[MMLST_MAX_DEVICES] = {0};  // per device: one process may drive several GPUs (sample.type_cohort)
+    int& n = by_device[mmlst_current_device()];
     if (n == 0) {
-        int dev = 0;
-        cudaDeviceProp p;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess) n = p.multiProcessorCount;
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
         else n = MMLST_NUM_SMS_DEFAULT;
     }
     return n;
@@ -90,13 +90,18 @@ struct mmlst_ctx {
     DevBuf db_hi, db_lo, db_len, q_hi, q_lo, q_len, blocks, best;
     DevBuf xr_ids, xr_x, xr_bytes, xq_ids, xq_x, xq_bytes;  // flagged (non-ACGT) rows / queries, H9
     uint32_t db_rows = 0, db_W = 0, db_n_xr = 0;
-    DevBuf* all[48];
+    // ST assignment (defineProfile): the `profiles` table grouped by profile, resident across queries
+    DevBuf prof_start, prof_allele, st_q, st_qn, st_count, st_best, st_nbest, st_out, first_row, row_key;
+    uint32_t n_st = 0;
+    bool has_row_key = false;
+    DevBuf* all[64];
     int n_all = 0;
     mmlst_ctx() {
         DevBuf* l[] = {&tid, &as0, &xm3, &qlen, &oidx, &allow, &locus_of, &sum_as, &n_hit, &first_idx, &counters, &p_recs,
                        &planes, &chunks, &counts, &dbseq, &col_off, &cons, &holes, &snps, &db_hi,
                        &db_lo, &db_len, &q_hi, &q_lo, &q_len, &blocks, &best, &qhash, &cov_table, &cov, &xr_ids, &xr_x, &xr_bytes, &xq_ids, &xq_x, &xq_bytes,
-                       &run_tid, &run_start, &chunk_run, &chunk_qlen};
+                       &run_tid, &run_start, &chunk_run, &chunk_qlen, &prof_start, &prof_allele, &st_q, &st_qn, &st_count, &st_best, &st_nbest, &st_out,
+                       &first_row, &row_key};
         for (DevBuf* b : l) all[n_all++] = b;
     }
 };
@@ -432,7 +437,7 @@ extern "C" int mmlst_db_upload_x(mmlst_ctx* c, const uint32_t* db_hi, const uint
     TRY(h2d(c->xr_x, xr_x, (size_t)n_xr * W, c->stream));
     TRY(h2d(c->xr_bytes, xr_bytes, (size_t)n_xr * W * 32, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    c->db_rows = n_rows; c->db_W = W; c->db_n_xr = n_xr;
+    c->db_rows = n_rows; c->db_W = W; c->db_n_xr = n_xr; c->has_row_key = false;
     return MMLST_OK;
 }
 
@@ -503,6 +508,100 @@ extern "C" int mmlst_hamming_min_x(mmlst_ctx* c, const uint32_t* q_hi, const uin
 extern "C" int mmlst_hamming_min(mmlst_ctx* c, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
                                  const uint32_t* blocks, uint32_t n_blocks, uint32_t* min_dist, uint32_t* argmin_row) {
     return mmlst_hamming_min_x(c, q_hi, q_lo, q_len, n_q, nullptr, nullptr, nullptr, 0, blocks, n_blocks, min_dist, argmin_row);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Rows a10 / a11 (csrc/st_match.cu): exact-sequence lookup against the resident DB, ST assignment against the resident profiles.
+extern "C" int mmlst_exact_match_dev(const uint32_t*, const uint32_t*, const uint16_t*, uint32_t, uint32_t, const uint32_t*, const uint32_t*,
+                                     const uint16_t*, uint32_t, const uint32_t*, uint32_t, uint32_t, uint32_t, const uint32_t*, const uint32_t*,
+                                     const uint8_t*, uint32_t, const uint32_t*, const uint8_t*, uint32_t, uint32_t*, void*);
+extern "C" int mmlst_st_match_dev(const uint32_t*, const uint32_t*, uint32_t, const uint32_t*, const uint32_t*, uint32_t, uint32_t, uint32_t*,
+                                  uint32_t*, uint32_t*, uint32_t*, uint32_t, void*);
+
+extern "C" int mmlst_exact_match(mmlst_ctx* c, const uint32_t* q_hi, const uint32_t* q_lo, const uint16_t* q_len, uint32_t n_q,
+                                 const uint32_t* xq_ids, const uint8_t* xq_bytes, uint32_t n_xq,
+                                 const uint32_t* blocks, uint32_t n_blocks, uint32_t* first_row) {
+    CTX_ENTER(c);
+    if (!c->db_rows) { mmlst_set_error("mmlst_exact_match: no DB uploaded"); return MMLST_E_ARG; }
+    if (n_q == 0) return MMLST_OK;
+    if (!q_hi || !q_lo || !q_len || !blocks || !first_row || (n_xq && (!xq_ids || !xq_bytes))) { mmlst_set_error("mmlst_exact_match: null pointer"); return MMLST_E_ARG; }
+    uint32_t max_rows = 0;
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        if (blocks[4 * b + 1] < blocks[4 * b] || blocks[4 * b + 3] < blocks[4 * b + 2] || blocks[4 * b + 1] > n_q || blocks[4 * b + 3] > c->db_rows) {
+            mmlst_set_error("mmlst_exact_match: block %u out of range", b);
+            return MMLST_E_ARG;
+        }
+        max_rows = std::max(max_rows, blocks[4 * b + 3] - blocks[4 * b + 2]);
+    }
+    cudaStream_t s = c->stream;
+    const uint32_t W = c->db_W;
+    TRY(h2d(c->q_hi, q_hi, (size_t)n_q * W, s));
+    TRY(h2d(c->q_lo, q_lo, (size_t)n_q * W, s));
+    TRY(h2d(c->q_len, q_len, n_q, s));
+    TRY(h2d(c->blocks, blocks, (size_t)n_blocks * 4, s));
+    TRY(h2d(c->xq_ids, xq_ids, n_xq, s));
+    TRY(h2d(c->xq_bytes, xq_bytes, (size_t)n_xq * W * 32, s));
+    TRY(c->first_row.reserve((size_t)n_q * 4));
+    CUDA_TRY(cudaMemsetAsync(c->first_row.p, 0xff, (size_t)n_q * 4, s));
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += 65535) {
+        const uint32_t nb = std::min(65535u, n_blocks - b0);
+        TRY(mmlst_exact_match_dev(c->db_hi.as<uint32_t>(), c->db_lo.as<uint32_t>(), c->db_len.as<uint16_t>(), c->db_rows, W,
+                                  c->q_hi.as<uint32_t>(), c->q_lo.as<uint32_t>(), c->q_len.as<uint16_t>(), n_q,
+                                  c->blocks.as<uint32_t>() + 4 * (size_t)b0, nb, max_rows, 0, c->has_row_key ? c->row_key.as<uint32_t>() : nullptr,
+                                  c->xr_ids.as<uint32_t>(), c->xr_bytes.as<uint8_t>(), c->db_n_xr,
+                                  c->xq_ids.as<uint32_t>(), c->xq_bytes.as<uint8_t>(), n_xq, c->first_row.as<uint32_t>(), s));
+    }
+    CUDA_TRY(cudaMemcpyAsync(first_row, c->first_row.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return MMLST_OK;
+}
+
+extern "C" int mmlst_db_row_keys(mmlst_ctx* c, const uint32_t* row_key, uint32_t n_rows) {
+    CTX_ENTER(c);
+    if (!row_key) { c->has_row_key = false; return MMLST_OK; }
+    if (n_rows != c->db_rows) { mmlst_set_error("mmlst_db_row_keys: %u keys for %u resident rows", n_rows, c->db_rows); return MMLST_E_ARG; }
+    TRY(h2d(c->row_key, row_key, n_rows, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->has_row_key = true;
+    return MMLST_OK;
+}
+
+extern "C" int mmlst_profiles_upload(mmlst_ctx* c, const uint32_t* prof_start, const uint32_t* prof_allele, uint32_t n_st) {
+    CTX_ENTER(c);
+    if (!prof_start || (n_st && prof_start[n_st] && !prof_allele)) { mmlst_set_error("mmlst_profiles_upload: null pointer"); return MMLST_E_ARG; }
+    for (uint32_t p = 0; p < n_st; ++p)
+        if (prof_start[p + 1] < prof_start[p]) { mmlst_set_error("mmlst_profiles_upload: prof_start must be non-decreasing"); return MMLST_E_ARG; }
+    TRY(h2d(c->prof_start, prof_start, (size_t)n_st + 1, c->stream));
+    TRY(h2d(c->prof_allele, prof_allele, (size_t)prof_start[n_st], c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->n_st = n_st;
+    return MMLST_OK;
+}
+
+extern "C" int mmlst_st_match(mmlst_ctx* c, const uint32_t* q_alleles, const uint32_t* q_n, uint32_t l_max, uint32_t n_q,
+                              uint32_t* best, uint32_t* n_best, uint32_t* out_idx, uint32_t max_out) {
+    CTX_ENTER(c);
+    if (n_q == 0) return MMLST_OK;
+    if (!q_alleles || !q_n || !best || !n_best || !out_idx || max_out == 0) { mmlst_set_error("mmlst_st_match: null pointer"); return MMLST_E_ARG; }
+    if (!c->prof_start.p) { mmlst_set_error("mmlst_st_match: no profile table uploaded (mmlst_profiles_upload)"); return MMLST_E_ARG; }
+    cudaStream_t s = c->stream;
+    for (uint32_t q0 = 0; q0 < n_q; q0 += 32768) {
+        const uint32_t nq = std::min(32768u, n_q - q0);
+        TRY(h2d(c->st_q, q_alleles + (size_t)q0 * l_max, (size_t)nq * l_max, s));
+        TRY(h2d(c->st_qn, q_n + q0, nq, s));
+        TRY(c->st_count.reserve((size_t)nq * std::max(c->n_st, 1u) * 4));
+        TRY(c->st_best.reserve((size_t)nq * 4));
+        TRY(c->st_nbest.reserve((size_t)nq * 4));
+        TRY(c->st_out.reserve((size_t)nq * max_out * 4));
+        TRY(mmlst_st_match_dev(c->prof_start.as<uint32_t>(), c->prof_allele.as<uint32_t>(), c->n_st, c->st_q.as<uint32_t>(), c->st_qn.as<uint32_t>(),
+                               l_max, nq, c->st_count.as<uint32_t>(), c->st_best.as<uint32_t>(), c->st_nbest.as<uint32_t>(), c->st_out.as<uint32_t>(),
+                               max_out, s));
+        CUDA_TRY(cudaMemcpyAsync(best + q0, c->st_best.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(n_best + q0, c->st_nbest.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(out_idx + (size_t)q0 * max_out, c->st_out.p, (size_t)nq * max_out * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return MMLST_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

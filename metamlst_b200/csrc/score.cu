@@ -160,7 +160,8 @@ extern "C" int mmlst_score_dev(const uint32_t* tid, const int16_t* as0, const ui
                 reinterpret_cast<long long*>(sum_as), n_hit, first_idx, reinterpret_cast<unsigned long long*>(counters)};
     const uint64_t nchunks = n_rec >> 8;
     uint64_t want = (nchunks + 7) / 8;  // CTAs if every warp took one chunk
-    static int resident = 0;  // one wave exactly: the blocked chunk distribution has no tail
+    static int resident_by_device[MMLST_MAX_DEVICES] = {0};  // one wave exactly: the blocked chunk distribution has no tail
+    int& resident = resident_by_device[mmlst_current_device()];
     if (!resident) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, score_kernel, kThreads, 0) != cudaSuccess || resident < 1) resident = 4;
     }

@@ -110,7 +110,8 @@ static int score_runs_launch(const uint32_t* run_tid, const uint32_t* run_start,
         CUDA_TRY(cudaGetLastError());
         return MMLST_OK;
     }
-    static int resident[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // one wave exactly: the blocked chunk distribution has no tail
+    static int resident_by_device[MMLST_MAX_DEVICES][8] = {{0}};  // one wave exactly: the blocked chunk distribution has no tail
+    int (&resident)[8] = resident_by_device[mmlst_current_device()];
     const int v = (orig_idx ? 1 : 0) + 2 * (variant == 1 ? 1 : 0) + (chunk_qlen ? 4 : 0);
     void (*const kerns[8])(const RunArgs) = {score_runs_kernel<false, false, false>, score_runs_kernel<true, false, false>,
                                              score_runs_kernel<false, true, false>, score_runs_kernel<true, true, false>,

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import native, packing
+from .streams import DeviceStreams  # noqa: F401  (re-exported: the class lives with the product code)
 
 
 def _pack_words(bits: torch.Tensor) -> torch.Tensor:
@@ -64,52 +65,6 @@ def read_planes(core: dict, minqual: int = 20):
     rows[:, :3 * nwmax] = planes
     # words beyond 3*nw are zero (columns beyond the span are invalid); the pad word is zero
     return reflen, nw, rw, rows
-
-
-class DeviceStreams:
-    """Coordinate-sorted streams as torch tensors on one device (+ helpers to mirror them into a pinned SoaHost)."""
-
-    def __init__(self):
-        self.ref_names: List[str] = []
-        self.ref_lens: Optional[np.ndarray] = None
-
-    def to_host(self, pinned: bool = True) -> packing.SoaHost:
-        def h(t, dt):
-            a = t.detach().cpu().numpy()
-            return a.view(dt) if a.dtype != dt else a
-        recs = self.p_recs.detach().cpu().numpy().reshape(-1).view(packing.PREC_DTYPE)
-        soa = packing.SoaHost(self.ref_names, self.ref_lens, h(self.tid, np.uint32), h(self.as0, np.int16), h(self.xm3, np.uint8),
-                              h(self.qlen, np.uint16), None, recs, h(self.planes, np.uint32),
-                              int(self.max_row_words), self.contig_start.copy(), self.minqual, self.max_depth, self.n_dropped)
-        if getattr(self, "run_tid", None) is not None:
-            soa.run_tid, soa.run_start, soa.chunk_run = h(self.run_tid, np.uint32), h(self.run_start, np.uint32), h(self.chunk_run, np.uint32)
-            if getattr(self, "chunk_qlen", None) is not None:
-                soa.chunk_qlen = h(self.chunk_qlen, np.uint16)
-        return soa.pin() if pinned else soa
-
-    def build_runs(self) -> "DeviceStreams":
-        """Run-length form of the score stream on the device (include/mmlst.h, mmlst_score_runs_dev): run_tid, run_start,
-        chunk_run as int32 tensors (bit patterns of the u32 arrays)."""
-        n = int(self.tid.shape[0])
-        self.run_tid = self.run_start = self.chunk_run = self.chunk_qlen = None
-        if n == 0:
-            return self
-        assert n < 0xffffff00
-        vals, counts = torch.unique_consecutive(self.tid, return_counts=True)
-        start = torch.zeros(vals.shape[0] + 1, dtype=torch.int64, device=self.tid.device)
-        start[1:] = torch.cumsum(counts, 0)
-        first = torch.arange(0, n, 256, dtype=torch.int64, device=self.tid.device)
-        self.chunk_run = (torch.searchsorted(start, first, right=True) - 1).to(torch.int32).contiguous()
-        self.run_tid = vals.to(torch.int32).contiguous()
-        self.run_start = start.to(torch.int32).contiguous()  # n < 2^32 - 256: the u32 bit pattern
-        # len(SEQ) once per 256-record chunk when every chunk is uniform (mmlst_score_runs_qc_dev)
-        nc = (n + 255) // 256
-        q = self.qlen.to(torch.int32)
-        pad = torch.full((nc * 256 - n,), int(q[-1].item()), dtype=torch.int32, device=q.device)
-        q2 = torch.cat([q, pad]).view(nc, 256)
-        if bool((q2 == q2[:, :1]).all().item()):
-            self.chunk_qlen = q2[:, 0].to(torch.int16).contiguous()  # bit pattern of the u16
-        return self
 
 
 def pack_cores(db, cores: List[dict], minqual: int = 20, max_depth: Optional[int] = 8000, sentinel_nodes: int = 1,

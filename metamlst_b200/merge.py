@@ -8,15 +8,16 @@ scan for an exact match (`sequenceExists` / `sequenceLocate`, metaMLST_functions
 sequence not in the DB, a Python per-character loop against every allele of the locus (`sequencesGetAll` + `stringDiff`,
 metamlst-merge.py:174-181).  Here the cohort is handled in three phases:
 
-  1. host   : parse the folder; ONE pass over `alleles` per organism builds {sequence: first alleleVariant} -- the
-              answer of every exact-match query of that organism (SQLite `=` on TEXT is case-sensitive, H10; first row
-              in rowid order is what `fetchone()` returns);
+  1. device : parse the folder (host); every distinct reconstructed sequence of an organism goes through ONE exact-match call
+              against the organism's resident 2-bit rows (`HammingIndex.exact_first`, csrc/st_match.cu: same length + same
+              characters, case-sensitive like SQLite's `=`, H10; lowest rowid wins like `fetchone()`).  Without a GPU context
+              (CPU tests that inject the distance function) the same answers come from one pass over `alleles`;
   2. device : every DISTINCT sequence that is not in the DB goes, once, through ONE batched closest-allele search
               (`api.HammingIndex.search`: 2-bit XOR + popcount, non-ACGT letters on the exact path, H9) against the rows
               of its own locus -> min zip-Hamming distance; the reference's early-exit `any(d <= z)` is `min <= z`;
   3. host   : the sequential bookkeeping of the reference (new allele / profile numbering depends on encounter order),
-              with every lookup answered from the two tables above; ST assignment (`define_profile`, H11) memoised per
-              label tuple.
+              with every lookup answered from the two tables above; ST assignment (defineProfile, H11) for all lines made of DB
+              alleles in ONE batched device call (`api.ProfileIndex`), memoised per label tuple.
 
 Files and screen text are byte-identical to the reference's (tests/test_merge_driver.py against the golden cohort that
 the unmodified script produced).  The sequence writers behind `--outseqformat` (metamlst-merge.py:345-494: FASTA/CSV
@@ -84,6 +85,8 @@ class CohortMerger:
         self._closest = closest
         self._index: Dict[str, api.HammingIndex] = {}
         self._profile_memo: Dict[Tuple[str, ...], list] = {}
+        self._profiles: Optional[api.ProfileIndex] = None
+        self.device_lookups = ctx is not None and closest is None   # rows a10 / a11 on the GPU too (exact match, ST assignment)
 
     def close(self):
         self.conn.close()
@@ -106,6 +109,23 @@ class CohortMerger:
                 table.setdefault(str(r["sequence"]), str(r["alleleVariant"]))
         return table
 
+    def _organism_index(self, bacterium: str) -> api.HammingIndex:
+        idx = self._index.get(bacterium)
+        if idx is None:
+            idx = self._index[bacterium] = api.HammingIndex.from_sqlite(self.ctx, self.conn, bacterium)
+        return idx
+
+    def exact_lookup(self, bacterium: str, sequences: Sequence[str]) -> Dict[str, str]:
+        """{sequence: str(alleleVariant)} for those of `sequences` the organism's alleles hold -- the answers `exact_table` gives,
+        from ONE device call over the resident 2-bit DB (`api.HammingIndex.exact_first`, csrc/st_match.cu)."""
+        idx = self._organism_index(bacterium)
+        rng = idx.organism_range(bacterium)
+        seqs = list(dict.fromkeys(s for s in sequences if s != ""))
+        if rng is None or not seqs:
+            return {}
+        rows = idx.exact_first(seqs, [rng] * len(seqs))
+        return {s: str(idx.rows[int(r)][2]) for s, r in zip(seqs, rows) if int(r) != api.NO_IDX}
+
     def closest_distances(self, bacterium: str, items: Sequence[Tuple[str, str]]) -> List[int]:
         """min over the alleles of (bacterium, gene) of stringDiff(seq, allele) for every (gene, seq), one device call."""
         if not items:
@@ -114,9 +134,7 @@ class CohortMerger:
             return list(self._closest(bacterium, items))
         if self.ctx is None:
             raise RuntimeError("CohortMerger needs a native.Context (GPU) for the closest-allele search; there is no CPU fallback")
-        idx = self._index.get(bacterium)
-        if idx is None:
-            idx = self._index[bacterium] = api.HammingIndex.from_sqlite(self.ctx, self.conn, bacterium)
+        idx = self._organism_index(bacterium)
         # a locus without rows in the DB: the reference's loop body never runs and the allele stays rejected (:173-181)
         have = [i for i, (g, _s) in enumerate(items) if (bacterium, g) in idx.block]
         out = [1 << 30] * len(items)
@@ -130,8 +148,24 @@ class CohortMerger:
         key = tuple(labels)
         hit = self._profile_memo.get(key)
         if hit is None:
-            hit = self._profile_memo[key] = api.define_profile(self.conn, list(labels))
+            self.define_profiles([key])
+            hit = self._profile_memo[key]
         return hit
+
+    def define_profiles(self, label_lists: Sequence[Sequence[str]]) -> None:
+        """Memoise defineProfile for every list: ONE batched device call (`api.ProfileIndex`, csrc/st_match.cu) with a GPU context,
+        else the reference's SQL statement per list."""
+        todo = [tuple(l) for l in dict.fromkeys(tuple(l) for l in label_lists) if tuple(l) not in self._profile_memo]
+        if not todo:
+            return
+        if self.device_lookups:
+            if self._profiles is None:
+                self._profiles = api.ProfileIndex(self.ctx, self.conn)
+            for key, res in zip(todo, self._profiles.define_profiles(todo)):
+                self._profile_memo[key] = res
+        else:
+            for key in todo:
+                self._profile_memo[key] = api.define_profile(self.conn, list(key))
 
     # -- classification -----------------------------------------------------------------------------------------------
     def merge_organism(self, bacterium: str, records: list) -> OrganismMerge:
@@ -143,7 +177,14 @@ class CohortMerger:
         for r in conn.execute("SELECT profileCode,gene,alleleVariant FROM profiles,alleles WHERE alleleCode = alleles.recID AND alleles.bacterium = ?",
                               (bacterium,)):  # :138-140
             st.old_profiles.setdefault(r["profileCode"], [0, {}])[1][r["gene"]] = r["alleleVariant"]
-        known = self.exact_table(bacterium)
+        if self.device_lookups:
+            known = self.exact_lookup(bacterium, [seq for loci, _s in records for (seq, _a, _p) in loci.values()])
+            # ST assignment of every line made of DB alleles only, batched (the lines that can reach defineProfile, :199-204)
+            self.define_profiles([[bacterium + "_" + label.split("_")[1] + "_" + (known[seq] if seq != "" else label.split("_")[2])
+                                   for label, (seq, _a, _p) in loci.items()]
+                                  for loci, _s in records if all(seq == "" or seq in known for (seq, _a, _p) in loci.values())])
+        else:
+            known = self.exact_table(bacterium)
         # phase 2: every distinct sequence that is not a DB sequence, searched once (first gene it appears with: a later
         # appearance hits `genesBase` upstream and never reaches the distance test)
         accepted: Dict[str, bool] = {}

@@ -39,10 +39,12 @@ class DevicePipeline:
         "p2p" = owner mode with the all-gather done by our own kernels over NVLink peer memory (csrc/exchange.cu): the
         block is stored straight into every peer's symmetric buffer, no NCCL call inside the pass."""
         self.s = streams
+        self._use_runs_arg, self._idx_base_arg = use_runs, idx_base
         self.index = index
         self.dbseq_of = dbseq_of
         self.minscore, self.max_xM, self.min_read_len, self.penalty = int(minscore), int(max_xM), int(min_read_len), int(penalty)
-        self.mincov, self.impl, self.idx_base = int(mincov), int(impl), int(idx_base)
+        self.mincov, self.impl = int(mincov), int(impl)
+        self.idx_base = int(idx_base) if idx_base else int(getattr(streams, "idx_base", 0) or 0)
         self.group = group
         self.dist = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
         if exchange not in ("allreduce", "gather", "p2p"):
@@ -94,8 +96,10 @@ class DevicePipeline:
         self.allele_num = t32(np.asarray([int(a) for a in index.allele], dtype=np.int64).astype(np.uint32).view(np.int32))
         self.species_of_locus = t32(sol)
         self.genes_in_db = t32(gdb)
-        self.contig_start_d = t32(np.asarray(streams.contig_start, dtype=np.uint64).view(np.int64))
         self.ref_len_d = t32(np.asarray(streams.ref_lens, dtype=np.int32))
+        self.contig_start_d = torch.zeros(n_ref + 1, dtype=torch.int64, device=dev)
+        self.max_chunks = 0
+        self.rebind(streams)
         self.db_ascii_d = t32(np.concatenate([db_ascii, np.zeros(8, np.uint8)]))
         self.db_off_d = t32(np.asarray(db_off, dtype=np.int64))
         nl = index.n_loci
@@ -103,8 +107,6 @@ class DevicePipeline:
         order = np.argsort(index.locus_of, kind="stable").astype(np.uint32)  # allele rows grouped by locus
         self.locus_rows = t32(order.view(np.int32))
         self.locus_start = t32(np.searchsorted(index.locus_of[order], np.arange(nl + 1)).astype(np.int32))
-        self.max_chunks = int(streams.n_prec) // 512 + nl + 8
-        self.chunks_d = torch.zeros(self.max_chunks * 8, dtype=torch.int32, device=dev)
         # ONE output block => one D2H node per pass: int32 header[16] | chosen_tid[nl] | chosen_species[nl] | col_off[nl+1] |
         # holes[nl] | snps[nl] | pad, then the consensus bytes
         self.o_hdr, self.o_tid, self.o_sp, self.o_col, self.o_holes, self.o_snps = 0, 16, 16 + nl, 16 + 2 * nl, 17 + 3 * nl, 17 + 4 * nl
@@ -127,11 +129,30 @@ class DevicePipeline:
         self.small_h = self.out_h[: self.n_small * 4].view(torch.int32)
         self.cons_h = self.out_h[self.n_small * 4: self.out_bytes]
         self.genes_in_db_h = gdb
+        self.want_tables = False  # step() also brings (sum_as, n_hit, first_idx) to the host: tables()
+        self._tables_h = None
         self._clean = False  # score tables / counts / scratch hold the "nothing accumulated" state
         self.timers: Optional[Dict[str, list]] = None  # name -> [(start_event, end_event)]
         self.launches = 0
 
     # ------------------------------------------------------------------------------------------------------------
+    def rebind(self, streams):
+        """Point the pipeline at ANOTHER sample unpacked against the same BAM header (a cohort typed against one index: every
+        look-up table, accumulator and the output block are reused; only the record streams and their contig ranges change).
+        A captured CUDA graph is dropped (it holds the old streams' addresses)."""
+        if list(streams.ref_names) != self.index.ref_names or not np.array_equal(np.asarray(streams.ref_lens), np.asarray(self.s.ref_lens)):
+            raise ValueError("rebind: the sample was aligned against a different reference set")
+        self.s = streams
+        self.use_runs = getattr(streams, "run_tid", None) is not None if self._use_runs_arg is None else bool(self._use_runs_arg)
+        self.use_qc = self.use_runs and getattr(streams, "chunk_qlen", None) is not None
+        self.idx_base = int(self._idx_base_arg) if self._idx_base_arg else int(getattr(streams, "idx_base", 0) or 0)
+        self.contig_start_d.copy_(torch.from_numpy(np.asarray(streams.contig_start, dtype=np.uint64).view(np.int64)), non_blocking=False)
+        need = int(streams.n_prec) // 512 + self.index.n_loci + 8
+        if need > self.max_chunks:
+            self.max_chunks = need
+            self.chunks_d = torch.zeros(self.max_chunks * 8, dtype=torch.int32, device=self.dev)
+        self.graph = None
+
     def _timed(self, name: str, fn):
         if self.timers is None:
             fn()
@@ -156,20 +177,23 @@ class DevicePipeline:
         len(SEQ) per chunk, else 5 B / record), else the explicit-tid form (9 B / record)."""
         s = self.s
         n = int(s.as0.shape[0])
+        oi = native.ptr(getattr(s, "orig_idx", None))  # file-order index per record (BAM that was not coordinate-sorted, locus shards); NULL = identity + idx_base
+        if n == 0:
+            return
         if self.use_runs and self.use_qc:
             native.check(self.lib.mmlst_score_runs_qc_dev(native.ptr(s.run_tid), native.ptr(s.run_start), int(s.run_tid.shape[0]), native.ptr(s.chunk_run),
-                                                          native.ptr(s.chunk_qlen), native.ptr(s.as0), native.ptr(s.xm3), 0, n, self.idx_base,
+                                                          native.ptr(s.chunk_qlen), native.ptr(s.as0), native.ptr(s.xm3), oi, n, self.idx_base,
                                                           native.ptr(self.allow), self.n_ref, self.minscore, self.max_xM, self.min_read_len,
                                                           native.ptr(self.sum_as), native.ptr(self.n_hit), native.ptr(self.first_idx),
                                                           native.ptr(self.counters), self._stream()))
         elif self.use_runs:
             native.check(self.lib.mmlst_score_runs_dev(native.ptr(s.run_tid), native.ptr(s.run_start), int(s.run_tid.shape[0]), native.ptr(s.chunk_run),
-                                                       native.ptr(s.as0), native.ptr(s.xm3), native.ptr(s.qlen), 0, n, self.idx_base,
+                                                       native.ptr(s.as0), native.ptr(s.xm3), native.ptr(s.qlen), oi, n, self.idx_base,
                                                        native.ptr(self.allow), self.n_ref, self.minscore, self.max_xM, self.min_read_len,
                                                        native.ptr(self.sum_as), native.ptr(self.n_hit), native.ptr(self.first_idx),
                                                        native.ptr(self.counters), self._stream()))
         else:
-            native.check(self.lib.mmlst_score_dev(native.ptr(s.tid), native.ptr(s.as0), native.ptr(s.xm3), native.ptr(s.qlen), 0, n, self.idx_base,
+            native.check(self.lib.mmlst_score_dev(native.ptr(s.tid), native.ptr(s.as0), native.ptr(s.xm3), native.ptr(s.qlen), oi, n, self.idx_base,
                                                   native.ptr(self.allow), native.ptr(self.locus_of), self.n_ref, self.minscore, self.max_xM,
                                                   self.min_read_len, native.ptr(self.sum_as), native.ptr(self.n_hit), native.ptr(self.first_idx),
                                                   native.ptr(self.counters), self._stream()))
@@ -296,6 +320,8 @@ class DevicePipeline:
         if not self._clean:
             self.reset_tables()
         self.run_score(reset=False)
+        if self.want_tables:  # the score tables leave the device before the selection consumes them (`.out` log / screen table)
+            self._enqueue_tables()
         self._timed("select", lambda: self._select_call(native.SELECT_CONSUME | native.SELECT_SCRATCH_CLEAN))
         self.launches += 1
         self._timed("pileup", self._pileup_call)
@@ -507,6 +533,18 @@ class DevicePipeline:
             out.setdefault(self.species_names[int(h[self.o_sp + i])], []).append(
                 (self.index.ref_names[int(tids[i])], cons[col[i]:col[i + 1]].tobytes().decode("latin-1"), int(h[self.o_holes + i]), int(h[self.o_snps + i])))
         return out
+
+    def _enqueue_tables(self):
+        if self._tables_h is None:
+            self._tables_h = (torch.zeros(self.zscore.shape[0], dtype=torch.int64).pin_memory(), torch.zeros(self.n_ref, dtype=torch.int32).pin_memory())
+        self._tables_h[0].copy_(self.zscore, non_blocking=True)
+        self._tables_h[1].copy_(self.first_idx, non_blocking=True)
+
+    def tables(self):
+        """(sum_as int64, n_hit uint32, first_idx uint32) of the last finished pass run with `want_tables` (host numpy views)."""
+        z, f = self._tables_h
+        n = self.n_ref
+        return z[:n].numpy(), z[n + 2:].view(torch.int32)[:n].numpy().view(np.uint32), f.numpy().view(np.uint32)
 
     def step(self):
         """One pass of the hot path, no host round trip between the stages.

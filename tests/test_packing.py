@@ -15,7 +15,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(l, name), name
     assert declared <= set(native.EXPORTS) | {"mmlst_hamming_min_dev2"}
-    assert l.mmlst_version() == 102
+    assert l.mmlst_version() == 200
 
 
 def test_ctypes_soa_layout_matches_the_header(tmp_path):

@@ -100,7 +100,7 @@ def test_driver_host_logic_reproduces_reference_files(name, oracle_seams, tmp_pa
     path = os.path.join(d, "sample.bam")
     oracle_seams(path)
     p = _params(name)
-    typer = sample.SampleTyper(os.path.join(d, "db.sqlite"), ctx=_NoDevice(), **p)
+    typer = sample.SampleTyper(os.path.join(d, "db.sqlite"), ctx=_NoDevice(), engine="host", **p)
     soa = bam.unpack_bam(path, presorted=p["presorted"])  # host C++ unpacker: supplies ref_names to the driver
     res = typer.type_unpacked(soa, path, want_stdout=True)
     typer.write(res, path, str(tmp_path / "out"), timestamp=7)
@@ -115,7 +115,7 @@ def test_nfo_is_appended_one_line_per_typing_run(oracle_seams, tmp_path):
     d = os.path.join(GOLDEN, "basic")
     path = os.path.join(d, "sample.bam")
     oracle_seams(path)
-    typer = sample.SampleTyper(os.path.join(d, "db.sqlite"), ctx=_NoDevice(), **_params("basic"))
+    typer = sample.SampleTyper(os.path.join(d, "db.sqlite"), ctx=_NoDevice(), engine="host", **_params("basic"))
     soa = bam.unpack_bam(path)
     for _ in range(2):
         res = typer.type_unpacked(soa, path)
@@ -141,23 +141,47 @@ def test_broken_database_ends_the_sample(oracle_seams, tmp_path):
     dst.execute("DELETE FROM genes WHERE geneName = 'adk'")
     dst.commit(); dst.close(); src.close()
     oracle_seams(path)
-    typer = sample.SampleTyper(db2, ctx=_NoDevice(), **_params("basic"))
+    typer = sample.SampleTyper(db2, ctx=_NoDevice(), engine="host", **_params("basic"))
     res = typer.type_unpacked(bam.unpack_bam(path), path, want_stdout=True)
     assert res.broken_db and res.nfo_lines == [] and "Database is brokenecoli" in res.stdout.replace(" for", "")
 
 
 # ---------------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["device", "host"])
 @pytest.mark.parametrize("name", CASES)
-def test_sample_typer_on_gpu_reproduces_reference_files(name, tmp_path):
+def test_sample_typer_on_gpu_reproduces_reference_files(name, engine, tmp_path):
+    """engine="device": BAM -> C++ unpacker -> DeviceStreams.from_soa -> DevicePipeline (one kernel chain, device-side selection);
+    engine="host": the four seams through the host-buffer C-ABI.  Both must leave the reference's bytes."""
     d = os.path.join(GOLDEN, name)
     path = os.path.join(d, "sample.bam")
-    typer = sample.SampleTyper(os.path.join(d, "db.sqlite"), device=0, **_params(name))
+    typer = sample.SampleTyper(os.path.join(d, "db.sqlite"), device=0, engine=engine, **_params(name))
     soa = bam.unpack_bam(path, presorted=_params(name)["presorted"], want_qhash=True)
     res = typer.type_unpacked(soa, path, want_stdout=True)
     typer.write(res, path, str(tmp_path / "out"), timestamp=7)
-    typer.close()
     _check_against_golden(name, res, str(tmp_path / "out"))
+    # the quiet form (no log, no screen text: nothing but the result block leaves the device) writes the same .nfo
+    typer.log = False
+    res2 = typer.type_unpacked(soa, path)
+    typer.close()
+    assert res2.nfo_lines == res.nfo_lines and res2.stdout == "" and res2.out_log is None
+    assert (res2.total_reads, res2.ignored_reads) == (res.total_reads, res.ignored_reads)
+
+
+@pytest.mark.gpu
+def test_broken_database_on_the_device_engine(tmp_path):
+    d = os.path.join(GOLDEN, "basic")
+    path = os.path.join(d, "sample.bam")
+    db2 = str(tmp_path / "db.sqlite")
+    src = sqlite3.connect(os.path.join(d, "db.sqlite"))
+    dst = sqlite3.connect(db2)
+    src.backup(dst)
+    dst.execute("DELETE FROM genes WHERE geneName = 'adk'")
+    dst.commit(); dst.close(); src.close()
+    typer = sample.SampleTyper(db2, device=0, **_params("basic"))
+    res = typer.type_unpacked(bam.unpack_bam(path, want_qhash=True), path, want_stdout=True)
+    typer.close()
+    assert res.broken_db and res.nfo_lines == [] and "Database is brokenecoli" in res.stdout.replace(" for", "")
 
 
 @pytest.mark.gpu
