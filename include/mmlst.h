@@ -424,6 +424,37 @@ int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts /* NULL = d
 int mmlst_bam_info(const mmlst_bam* bam, mmlst_bam_info_t* info);
 void mmlst_bam_free(mmlst_bam* bam);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * BAM ingest ON THE DEVICE (csrc/ingest.cu).  Same replacement as mmlst_bam_unpack (metamlst.py:96-110, cmseq/cmseq.py:54,527-545,
+ * metaMLST_functions.py:237-247), same streams, same refusals -- but only the COMPRESSED file crosses PCIe: BGZF blocks are
+ * inflated by the hardware decompression engine (cuMemBatchDecompressAsync, DEFLATE), records are chained, parsed, put in
+ * `samtools sort` order, depth-capped and packed by kernels, and the result stays in HBM.
+ *   bam / n_bytes : the whole BAM file in HOST memory (page-locked memory from mmlst_pinned_alloc makes the copy one async DMA)
+ *   opts          : as mmlst_bam_unpack (n_threads, pinned ignored; check_crc not supported on the device: the engine verifies the
+ *                   DEFLATE stream and the ISIZE of every block, not the CRC32)
+ *   stream        : cudaStream_t the work is queued on (NULL = the default stream); the call returns after the last kernel finished
+ * Every pointer of mmlst_dev_bam_info_t except contig_start / ref_len / ref_names / header_text is a DEVICE pointer owned by the
+ * handle.  MMLST_E_CUDA when the device has no hardware DEFLATE (then use mmlst_bam_unpack).
+ * --------------------------------------------------------------------------------------------------------------- */
+typedef struct mmlst_dev_bam mmlst_dev_bam;
+typedef struct {
+    const uint32_t* tid; const int16_t* as0; const uint8_t* xm3; const uint16_t* qlen; const uint32_t* orig_idx; const uint64_t* qhash;
+    const uint32_t* run_tid; const uint32_t* run_start; const uint32_t* chunk_run; const uint16_t* chunk_qlen; uint32_t n_runs;
+    const mmlst_prec* p_recs; const uint32_t* planes;
+    uint64_t n_rec, n_prec, n_plane_words; uint32_t max_row_words;
+    const uint64_t* contig_start;   /* HOST [n_ref+1] */
+    const uint32_t* ref_len;        /* HOST [n_ref] */
+    const char* ref_names;          /* HOST, joined by '\n' */
+    const char* header_text;        /* HOST */
+    uint32_t n_ref;
+    uint64_t n_dropped_by_cap, n_unmapped_flag, n_bgzf_blocks, compressed_bytes, inflated_bytes;
+    int presorted, minqual; uint32_t max_depth; int boundary_repairs;
+    double seconds[8];              /* device time: H2D, inflate, record chain, parse, sort, score stream, depth cap + compaction, pack */
+} mmlst_dev_bam_info_t;
+int mmlst_bam_ingest(int device, const uint8_t* bam, size_t n_bytes, const mmlst_unpack_opts* opts, void* stream, mmlst_dev_bam** out);
+int mmlst_dev_bam_info(const mmlst_dev_bam* bam, mmlst_dev_bam_info_t* info);
+void mmlst_dev_bam_free(mmlst_dev_bam* bam);
+
 #ifdef __cplusplus
 }
 #endif

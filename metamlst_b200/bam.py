@@ -8,6 +8,7 @@ returned SoaHost.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -82,3 +83,106 @@ def unpack_bam(path: str, minqual: int = packing.DEFAULT_MINQUAL, max_depth: Opt
     soa.unpack_seconds = dict(zip(("read", "inflate", "parse", "sort", "pack"), [float(x) for x in info.seconds]))
     soa._keep = (keep,)
     return soa
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# device-side ingest (csrc/ingest.cu): compressed bytes in, packed streams resident in HBM out
+# ----------------------------------------------------------------------------------------------------------------
+class DevBamInfo(C.Structure):
+    _fields_ = [("tid", C.c_void_p), ("as0", C.c_void_p), ("xm3", C.c_void_p), ("qlen", C.c_void_p), ("orig_idx", C.c_void_p), ("qhash", C.c_void_p),
+                ("run_tid", C.c_void_p), ("run_start", C.c_void_p), ("chunk_run", C.c_void_p), ("chunk_qlen", C.c_void_p), ("n_runs", C.c_uint32),
+                ("p_recs", C.c_void_p), ("planes", C.c_void_p),
+                ("n_rec", C.c_uint64), ("n_prec", C.c_uint64), ("n_plane_words", C.c_uint64), ("max_row_words", C.c_uint32),
+                ("contig_start", C.c_void_p), ("ref_len", C.c_void_p), ("ref_names", C.c_char_p), ("header_text", C.c_char_p), ("n_ref", C.c_uint32),
+                ("n_dropped_by_cap", C.c_uint64), ("n_unmapped_flag", C.c_uint64), ("n_bgzf_blocks", C.c_uint64), ("compressed_bytes", C.c_uint64),
+                ("inflated_bytes", C.c_uint64), ("presorted", C.c_int), ("minqual", C.c_int), ("max_depth", C.c_uint32), ("boundary_repairs", C.c_int),
+                ("seconds", C.c_double * 8)]
+
+
+class _DevHandle:
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h:
+                native.lib().mmlst_dev_bam_free(self.h)
+                self.h = None
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class _DevArray:
+    """A device array owned by the native handle, handed to torch through the CUDA array interface (no copy)."""
+
+    def __init__(self, addr: int, n: int, typestr: str, keep):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (addr, False), "version": 2, "strides": None}
+        self._keep = keep
+
+
+def read_pinned(path: str):
+    """The file's bytes in page-locked memory (one async DMA to the device): a uint8 torch tensor."""
+    import torch
+    size = os.path.getsize(path)
+    buf = torch.empty(max(size, 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    with open(path, "rb") as fh:
+        got = fh.readinto(memoryview(buf.numpy())[:size]) if size else 0
+    if got != size:
+        raise IOError("short read on %s" % path)
+    return buf[:size]
+
+
+def ingest_bam(source, device=0, minqual: int = packing.DEFAULT_MINQUAL, max_depth: Optional[int] = packing.DEFAULT_MAX_DEPTH,
+               presorted: bool = False, want_qhash: bool = True, sentinel_nodes: int = 1):
+    """BAM -> streams.DeviceStreams WITHOUT the sample ever being unpacked on the host: the compressed file crosses PCIe, the
+    hardware decompression engine inflates the BGZF blocks, kernels chain / parse / sort / depth-cap / pack the records
+    (csrc/ingest.cu).  `source`: a path, or a uint8 torch tensor / numpy array holding the file's bytes (page-locked for an
+    asynchronous copy: `read_pinned`).  Same streams, same refusals as `unpack_bam`; raises MmlstError(MMLST_E_CUDA) on a device
+    without hardware DEFLATE."""
+    import torch
+    from . import streams
+    dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+    data = read_pinned(source) if isinstance(source, str) else source
+    addr = data.data_ptr() if hasattr(data, "data_ptr") else data.ctypes.data
+    nbytes = int(data.numel() if hasattr(data, "numel") else data.size)
+    lib = native.lib()
+    o = UnpackOpts(int(minqual), int(max_depth or 0), int(sentinel_nodes), 0, 1, 1 if presorted else 0, 1 if want_qhash else 0, 0)
+    h = C.c_void_p()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        native.check(lib.mmlst_bam_ingest(dev.index or 0, addr, nbytes, C.byref(o), stream, C.byref(h)))
+    keep = _DevHandle(h)
+    info = DevBamInfo()
+    native.check(lib.mmlst_dev_bam_info(h, C.byref(info)))
+    n, P, n_ref, nr = int(info.n_rec), int(info.n_prec), int(info.n_ref), int(info.n_runs)
+
+    def t(addr_, count, typestr, dtype):
+        if not addr_ or count == 0:
+            return torch.zeros(0, dtype=dtype, device=dev)
+        return torch.as_tensor(_DevArray(addr_, count, typestr, keep), device=dev)
+
+    s = streams.DeviceStreams()
+    s._keep = keep
+    s.ref_names = info.ref_names.decode("latin-1").split("\n") if n_ref else []
+    s.ref_lens = _view(info.ref_len, n_ref, np.uint32).astype(np.int32)
+    s.header_text = (info.header_text or b"").decode("latin-1")
+    s.minqual, s.max_depth, s.n_dropped = int(info.minqual), int(info.max_depth), int(info.n_dropped_by_cap)
+    s.idx_base = 0
+    s.tid, s.as0 = t(info.tid, n, "<i4", torch.int32), t(info.as0, n, "<i2", torch.int16)
+    s.xm3, s.qlen = t(info.xm3, n, "|u1", torch.uint8), t(info.qlen, n, "<i2", torch.int16)
+    s.orig_idx = t(info.orig_idx, n, "<i4", torch.int32) if info.orig_idx else None
+    s.qhash = t(info.qhash, 2 * n, "<i8", torch.int64).view(n, 2) if (info.qhash and want_qhash) else None
+    s.p_recs = t(info.p_recs, 4 * P, "<i4", torch.int32).view(P, 4)
+    s.planes = t(info.planes, int(info.n_plane_words), "<i4", torch.int32)
+    s.n_prec, s.max_row_words = P, int(info.max_row_words)
+    s.contig_start = _view(info.contig_start, n_ref + 1, np.uint64).copy()
+    s.run_tid = s.run_start = s.chunk_run = s.chunk_qlen = None
+    if nr and nr <= 0.125 * n:  # name-grouped streams keep the explicit tid form (as unpack_bam does)
+        s.run_tid, s.run_start = t(info.run_tid, nr, "<i4", torch.int32), t(info.run_start, nr + 1, "<i4", torch.int32)
+        s.chunk_run = t(info.chunk_run, (n + 255) // 256, "<i4", torch.int32)
+        s.chunk_qlen = t(info.chunk_qlen, (n + 255) // 256, "<i2", torch.int16) if info.chunk_qlen else None
+    s.presorted = bool(info.presorted)
+    s.ingest_seconds = dict(zip(("h2d", "inflate", "chain", "parse", "sort", "score_stream", "cap_compact", "pack"), [float(x) for x in info.seconds]))
+    s.ingest_stats = {"bgzf_blocks": int(info.n_bgzf_blocks), "compressed_bytes": int(info.compressed_bytes), "inflated_bytes": int(info.inflated_bytes),
+                      "boundary_repairs": int(info.boundary_repairs), "unmapped_flag": int(info.n_unmapped_flag)}
+    return s

@@ -175,6 +175,8 @@ class SampleTyper:
             raise IOError("Failed to connect to the database: please check your database file!")  # metamlst.py:72-73
         if engine not in ("device", "host"):
             raise ValueError("engine must be 'device' or 'host'")
+        if ingest not in ("device", "host"):
+            raise ValueError("ingest must be 'device' (BGZF inflate + record parse on the GPU) or 'host' (C++ threads)")
         self.db_path = db_path
         self.conn = sqlite3.connect(db_path, check_same_thread=False)
         self.conn.row_factory = sqlite3.Row
@@ -237,7 +239,11 @@ class SampleTyper:
 
     def type_bam(self, bam_path: str, out_dir: str, want_stdout: bool = False, timestamp: Optional[int] = None) -> SampleResult:
         t0 = time.perf_counter()
-        soa = self.unpack(bam_path)
+        if self.ingest == "device" and self.engine == "device":
+            # the compressed file crosses PCIe; inflate / parse / sort / depth cap / packing happen on the device (csrc/ingest.cu)
+            soa = bam.ingest_bam(bam_path, self.device, presorted=self.presorted, want_qhash=want_stdout)
+        else:
+            soa = self.unpack(bam_path)
         t1 = time.perf_counter()
         res = self.type_unpacked(soa, bam_path, want_stdout=want_stdout)
         res.seconds["unpack"] = t1 - t0
@@ -262,7 +268,12 @@ class SampleTyper:
         dist_on = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(self.group) > 1
         rank = torch.distributed.get_rank(self.group) if dist_on else 0
         world = torch.distributed.get_world_size(self.group) if dist_on else 1
-        st = streams.DeviceStreams.from_soa(soa, dev, rank=rank, world=world, mode="ranges", want_qhash=want_qhash)
+        if isinstance(soa, streams.DeviceStreams):  # already resident (bam.ingest_bam)
+            if world > 1:
+                raise ValueError("a device-ingested sample is typed by one GPU; shard a host-unpacked sample (ingest='host') over several")
+            st = soa
+        else:
+            st = streams.DeviceStreams.from_soa(soa, dev, rank=rank, world=world, mode="ranges", want_qhash=want_qhash)
         key = (tuple(soa.ref_names), np.asarray(soa.ref_lens).tobytes())
         if self._pipe is None or self._pipe_key != key:
             index = api.AlleleIndex(soa.ref_names)
@@ -295,6 +306,10 @@ class SampleTyper:
                 cel = api.finish_scores(pipe.index, *pipe.tables(), self.penalty)
                 c = pipe.counters.cpu().numpy().view("uint64")
                 pipe.reset_tables()
+                if not hasattr(soa, "c_struct"):  # device-resident sample: the host-driven seams want it in host memory
+                    qh = soa.qhash
+                    soa = soa.to_host(pinned=False)
+                    soa.qhash = None if qh is None else qh.cpu().numpy().view("uint64")
                 cov = api.coverage_sums(self.ctx, soa, pipe.index, self.minscore, self.max_xM, self.min_read_len, self.species_filter) if want_cov else None
                 return self._calls_host_from_cel(soa, cel), cel, int(c[0]), int(c[1]), cov
             cel = api.finish_scores(pipe.index, *pipe.tables(), self.penalty) if want_tables else None

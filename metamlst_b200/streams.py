@@ -34,8 +34,9 @@ class DeviceStreams:
             a = t.detach().cpu().numpy()
             return a.view(dt) if a.dtype != dt else a
         recs = self.p_recs.detach().cpu().numpy().reshape(-1).view(packing.PREC_DTYPE)
+        oi = getattr(self, "orig_idx", None)
         soa = packing.SoaHost(self.ref_names, self.ref_lens, h(self.tid, np.uint32), h(self.as0, np.int16), h(self.xm3, np.uint8),
-                              h(self.qlen, np.uint16), None, recs, h(self.planes, np.uint32),
+                              h(self.qlen, np.uint16), None if oi is None else h(oi, np.uint32), recs, h(self.planes, np.uint32),
                               int(self.max_row_words), self.contig_start.copy(), self.minqual, self.max_depth, self.n_dropped)
         if getattr(self, "run_tid", None) is not None:
             soa.run_tid, soa.run_start, soa.chunk_run = h(self.run_tid, np.uint32), h(self.run_start, np.uint32), h(self.chunk_run, np.uint32)

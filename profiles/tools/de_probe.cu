@@ -17,7 +17,8 @@ typedef CUresult (*decomp_fn)(CUmemDecompressParams*, size_t, unsigned int, size
 
 int main(int argc, char** argv) {
     const int n_blocks = argc > 1 ? atoi(argv[1]) : 4096;
-    const int raw = 65280;
+    const int src_align = argc > 2 ? atoi(argv[2]) : 8;    // 1: payloads packed as in a BGZF file (26 bytes of header / trailer between them)
+    const int raw = argc > 3 ? atoi(argv[3]) : 65280;      // odd sizes make the destinations unaligned too
     cudaFree(0);
     int dev = 0;
     cudaGetDevice(&dev);
@@ -29,7 +30,7 @@ int main(int argc, char** argv) {
     CUresult r2 = attr(&maxlen, CU_DEVICE_ATTRIBUTE_MEM_DECOMPRESS_MAXIMUM_LENGTH, dev);
     decomp_fn fn = (decomp_fn)dlsym(h, "cuMemBatchDecompressAsync_ptsz");
     if (!fn) fn = (decomp_fn)dlsym(h, "cuMemBatchDecompressAsync");
-    printf("{\"attr_rc\": [%d, %d], \"algorithm_mask\": %d, \"max_length\": %d, \"have_entry_point\": %d", (int)r1, (int)r2, mask, maxlen, fn ? 1 : 0);
+    printf("{\"src_align\": %d, \"raw\": %d, \"attr_rc\": [%d, %d], \"algorithm_mask\": %d, \"max_length\": %d, \"have_entry_point\": %d", src_align, raw, (int)r1, (int)r2, mask, maxlen, fn ? 1 : 0);
     if (!fn || !(mask & 1)) { printf("}\n"); return 0; }
 
     // BAM-like payload: low-entropy structured bytes (compresses ~2.5x like a real BAM)
@@ -43,6 +44,7 @@ int main(int argc, char** argv) {
     std::vector<uint8_t> comp;
     std::vector<size_t> coff(n_blocks + 1, 0);
     std::vector<uint8_t> tmp(compressBound(raw) + 64);
+    std::vector<size_t> clen_tmp;
     for (int b = 0; b < n_blocks; ++b) {
         z_stream z; memset(&z, 0, sizeof z);
         deflateInit2(&z, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
@@ -51,12 +53,15 @@ int main(int argc, char** argv) {
         deflate(&z, Z_FINISH);
         size_t n = tmp.size() - z.avail_out;
         deflateEnd(&z);
-        size_t pad = (comp.size() + 7) & ~size_t(7);   // 8-byte aligned sources
+        size_t pad = src_align > 1 ? ((comp.size() + src_align - 1) / src_align) * src_align : comp.size() + 18;
         comp.resize(pad);
         coff[b] = pad;
         comp.insert(comp.end(), tmp.begin(), tmp.begin() + n);
+        clen_tmp.push_back(n);
+        if (src_align <= 1) comp.resize(comp.size() + 8);   // CRC32 + ISIZE trailer
         coff[b + 1] = comp.size();
     }
+    std::vector<size_t> clen(n_blocks);
     uint8_t *d_comp, *d_out; uint32_t* d_act;
     cudaMalloc(&d_comp, comp.size() + 64);
     cudaMalloc(&d_out, plain.size());
@@ -69,7 +74,7 @@ int main(int argc, char** argv) {
         const size_t end = (b + 1 < n_blocks) ? coff[b + 1] : comp.size();
         size_t real_end = end;  // exact size: the next block's padding start is >= this block's end
         (void)real_end;
-        prm[b].srcNumBytes = ((b + 1 < n_blocks) ? coff[b + 1] : comp.size()) - coff[b];
+        prm[b].srcNumBytes = clen_tmp[b];
         prm[b].dstNumBytes = raw;
         prm[b].dstActBytes = d_act + b;
         prm[b].src = d_comp + coff[b];

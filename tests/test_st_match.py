@@ -83,6 +83,7 @@ def test_define_profile_matches_sql(tmp_path):
             labels.append(labels[0])                           # a label twice: IN is a set test, len(recs) counts it twice
         lists.append(labels)
     lists.append(["saureus_%s_%d" % (g, int(v)) for (g, _l), v in zip(db.loci["saureus"], db.profiles["saureus"][0])])
+    lists.append(["ecoli_adk_%d" % int(prof[0][0])])   # one locus only: every ST carrying that allele ties at 100 %
     got = pidx.define_profiles(lists)
     for labels, g in zip(lists, got):
         assert g == api.define_profile(conn, labels), labels
