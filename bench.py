@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip uncapped / hamming / cpu baseline extras")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay of the pass")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the full-workload comparison with the C port of the oracle after the timed region")
+    ap.add_argument("--ingest-reads", type=int, default=2_000_000, help="reads of the BAM the `ingest` leg starts from (x K records; 0 = skip the leg)")
+    ap.add_argument("--only-ingest", action="store_true", help="run only the BAM ingest leg (profiling aid)")
     ap.add_argument("--only-hamming", action="store_true", help="run only the configs[4] Hamming sweep (profiling aid)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "gather", "allreduce"],
                     help="N>1: 'p2p' = owner mode, result blocks stored into the peers' memory over NVLink by our own kernels; 'gather' = owner mode, "
@@ -307,6 +309,9 @@ def main():
     peak, peak_src = peaks()
     if args.only_hamming:
         emit({"hamming": extra_hamming(device, peak)})
+        return
+    if args.only_ingest:
+        emit({"ingest": extra_ingest(make_db(args), args, device)})
         return
 
     db = make_db(args)
@@ -595,6 +600,8 @@ def main():
         line["uncapped"] = extra_uncapped(db, args, device, index, peak)
         line["hamming"] = extra_hamming(device, peak)
         line["coverage_column"] = extra_coverage(db, args, device, index)
+        if args.ingest_reads:
+            line["ingest"] = extra_ingest(db, args, device)
     if rank == 0:
         emit(line)
     if world > 1:
@@ -639,6 +646,71 @@ def extra_uncapped(db, args, device, index, peak):
     del out["_res"]
     del st
     torch.cuda.empty_cache()
+    return out
+
+
+def extra_ingest(db, args, device):
+    """From a BAM FILE to the result: the bytes of a bowtie2-ordered (name-grouped, unsorted) BAM of this workload's
+    shape sit in page-locked host memory; `bam.ingest_bam` ships the COMPRESSED bytes, inflates the BGZF blocks with the hardware
+    decompression engine, chains / parses / sorts / depth-caps / packs the records in HBM (csrc/ingest.cu).  Timed: host wall clock around the
+    synchronous call (H2D inside), 3 repetitions; per-phase device times from CUDA events.  Parity: every array of both streams equals the
+    C++ host unpacker's (mmlst_bam_unpack, all host threads, timed beside it on the same file)."""
+    import tempfile
+    import torch
+    from metamlst_b200 import api, bam, packing, pipeline, synth
+    out = {}
+    for order, reps in (("name", 3), ("coord", 2)):
+        cores = gen_cores(db, args, device, None, seed=1002, n_reads=args.ingest_reads)
+        raw = synth.write_bam_fast(db, cores, order=order, align_records=True)
+        del cores
+        torch.cuda.empty_cache()
+        pinned = torch.from_numpy(raw.copy()).pin_memory()
+        st = bam.ingest_bam(pinned, device)          # warm-up (driver entry points, allocator)
+        n = int(st.tid.shape[0])
+        del st
+        torch.cuda.synchronize()
+        times, phases = [], None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            st = bam.ingest_bam(pinned, device)
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+            phases = st.ingest_seconds
+            stats = st.ingest_stats
+            if _ + 1 < reps:
+                del st
+        dt = min(times)
+        # BAM bytes -> typed sample: ingest + one pass of the device pipeline
+        index = api.AlleleIndex(st.ref_names)
+        t0 = time.perf_counter()
+        st2 = bam.ingest_bam(pinned, device)
+        pipe = pipeline.DevicePipeline(st2, index, db.row_seq, impl=args.pileup_impl, **PARAMS)
+        t1 = time.perf_counter()
+        res = pipe.step()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        del pipe, st2
+        # parity + host baseline: the C++ unpacker on the same file
+        with tempfile.NamedTemporaryFile(suffix=".bam", dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as fh:
+            fh.write(raw.tobytes()); fh.flush()
+            t0h = time.perf_counter()
+            soa = bam.unpack_bam(fh.name, pinned=False, threads=os.cpu_count() or 1)
+            t_host = time.perf_counter() - t0h
+        h = lambda t: t.cpu().numpy()
+        same = (np.array_equal(h(st.tid).view(np.uint32), soa.tid) and np.array_equal(h(st.as0), soa.as0) and np.array_equal(h(st.xm3), soa.xm3) and
+                np.array_equal(h(st.qlen).view(np.uint16), soa.qlen) and (soa.orig_idx is None or np.array_equal(h(st.orig_idx).view(np.uint32), soa.orig_idx)) and
+                np.array_equal(h(st.p_recs).reshape(-1).view(packing.PREC_DTYPE), soa.p_recs) and np.array_equal(h(st.planes).view(np.uint32), soa.planes) and
+                np.array_equal(st.contig_start, soa.contig_start) and np.array_equal(h(st.qhash).view(np.uint64), soa.qhash))
+        assert same, "device ingest differs from the host unpacker"
+        out[order] = {"records": n, "bam_bytes": int(raw.size), "inflated_bytes": stats["inflated_bytes"], "bgzf_blocks": stats["bgzf_blocks"],
+                      "seconds": dt, "seconds_all_reps": times, "records_per_s": n / dt, "bam_GBps": raw.size / dt / 1e9, "inflated_GBps": stats["inflated_bytes"] / dt / 1e9,
+                      "device_seconds_by_phase": phases, "device_seconds_total": float(sum(phases.values())), "boundary_repairs": stats["boundary_repairs"],
+                      "bam_to_result_seconds": t2 - t0, "of_which_pipeline_pass": t2 - t1, "loci_typed": sum(len(v) for v in res.values()),
+                      "host_unpacker": {"seconds": t_host, "records_per_s": n / t_host, "threads": os.cpu_count(), "phases": soa.unpack_seconds},
+                      "speedup_vs_host_unpacker": t_host / dt, "parity": "every array of both streams equals the host unpacker's",
+                      "order": "bowtie2 output order (name-grouped; the device sorts)" if order == "name" else "coordinate-sorted (--presorted: no sort)"}
+        del st, soa, pinned
+        torch.cuda.empty_cache()
     return out
 
 

@@ -369,7 +369,8 @@ int mmlst_exact_match(mmlst_ctx* ctx, const uint32_t* q_hi, const uint32_t* q_lo
 /* ---------------------------------------------------------------------------------------------------------------
  * Seam S4 -- ST assignment (row a11).  Replaces the GROUP BY / HAVING statement of defineProfile (metaMLST_functions.py:205-216):
  * among the rows of `profiles` whose alleleCode is one of the query's allele codes, count per profileCode; answer = the
- * profiles whose count equals the maximum, ascending by profileCode (SQLite's GROUP BY order), and that count.
+ * profiles whose count equals the maximum and that count.  The device list is ascending by profileCode; SQLite emits the ties of
+ * `ORDER BY T DESC` in descending profileCode order, which the Python seam restores (api.ProfileIndex).
  *   prof_start[n_st+1], prof_allele[]: the `profiles` table grouped by profileCode, profiles ascending by code;
  *                                      prof_allele = alleleCode (alleles.recID) of every row of the group
  *   q_alleles[n_q][l_max], q_n[n_q]  : allele codes of every query (labels already resolved to recIDs; unknown labels dropped

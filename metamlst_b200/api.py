@@ -389,7 +389,9 @@ class ProfileIndex:
                 res.append([(0, 0)])
                 continue
             pct = int((float(best[i]) / float(len(recs[i]))) * 100)
-            res.append([(self.codes[int(p)], pct) for p in out[i, :int(nb[i])]])
+            # ties: `ORDER BY T DESC` over the groups leaves equal counts in DESCENDING profileCode order (SQLite 3.x reads its sorter
+            # backwards for DESC; pinned against sqlite3 itself in tests/test_st_match.py) -- the device list is ascending
+            res.append([(self.codes[int(p)], pct) for p in out[i, :int(nb[i])][::-1]])
         return res
 
 

@@ -443,3 +443,147 @@ def make_sample(db: SynthDB, n_reads: int, read_len: int = 100, seed: int = 1001
     tab.truth["strain_row"] = strain_row
     tab.truth["strain_seqs"] = [s.tobytes().decode() for s in strain_seqs]
     return tab
+
+
+# ----------------------------------------------------------------------------------------------
+# BAM bytes of a synthetic sample, fast (bench / test plumbing: nothing here is on a measured path)
+# ----------------------------------------------------------------------------------------------
+_BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def bam_record_bytes(db: SynthDB, cores: List[dict], order: str = "name"):
+    """The BAM records of gen_core chunks as one uint8 torch tensor + the record end offsets (int64), built with tensor ops on the
+    cores' device.  order="name": bowtie2's output order (the K alignments of a read are adjacent); "coord": `samtools sort`
+    order.  Fixed-width fields: QNAME "r%09d", aux AS:s XS:s XN:C XM:C XO:C XG:C NM:C YT:Z:UU (bowtie2's order, H4)."""
+    dev = cores[0]["bases"].device
+    K, L = cores[0]["K"], cores[0]["L"]
+    bases = torch.cat([c["bases"] for c in cores]); qual = torch.cat([c["qual"] for c in cores])
+    rtype = torch.cat([c["rtype"] for c in cores]); a = torch.cat([c["a_split"] for c in cores]); start = torch.cat([c["start"] for c in cores])
+    rows = torch.cat([c["rows"] for c in cores]); AS = torch.cat([c["AS"] for c in cores]); xm = torch.cat([c["xm"] for c in cores])
+    flag = torch.cat([c["flag"] for c in cores])
+    XS = torch.cat([c["XS"] for c in cores]) if "XS" in cores[0] else AS
+    n_reads = bases.shape[0]
+    n = n_reads * K
+    read_of = torch.arange(n, device=dev) // K
+    tid = rows.reshape(-1); pos = start[read_of]; fl = flag.reshape(-1); as_ = AS.reshape(-1); xs_ = XS.reshape(-1); xm_ = xm.reshape(-1)
+    if order == "coord":
+        key = (tid << 33) | ((pos + 1) << 1) | ((fl >> 4) & 1)
+        perm = torch.sort(key, stable=True).indices
+        read_of, tid, pos, fl, as_, xs_, xm_ = read_of[perm], tid[perm], pos[perm], fl[perm], as_[perm], xs_[perm], xm_[perm]
+    rt = rtype[read_of]
+    ncig = torch.where(rt == 0, 1, 3)
+    span = torch.full((n,), L, dtype=torch.int64, device=dev)
+    span[rt == 1] = L - 10; span[rt == 2] = L - 1; span[rt == 3] = L + 1
+    gap = ((rt == 2) | (rt == 3)).long()
+    # per-read pieces shared by the K records: 4-bit packed SEQ, QUAL, CIGAR words
+    code = torch.full_like(bases, 15)
+    for ch, v in ((65, 1), (67, 2), (71, 4), (84, 8)):
+        code[bases == ch] = v
+    if L % 2:
+        code = torch.cat([code, torch.zeros((n_reads, 1), dtype=code.dtype, device=dev)], dim=1)
+    seq4 = ((code[:, 0::2] << 4) | code[:, 1::2]).to(torch.uint8)
+    M, I, D, S = 0, 1, 2, 4
+    cig = torch.zeros((n_reads, 3), dtype=torch.int64, device=dev)
+    cig[:, 0] = (L << 4) | M
+    m1, m2, m3 = rtype == 1, rtype == 2, rtype == 3
+    cig[m1] = torch.tensor([(5 << 4) | S, ((L - 10) << 4) | M, (5 << 4) | S], device=dev)
+    cig[m2, 0] = (a[m2] << 4) | M; cig[m2, 1] = (1 << 4) | I; cig[m2, 2] = ((L - 1 - a[m2]) << 4) | M
+    cig[m3, 0] = (a[m3] << 4) | M; cig[m3, 1] = (1 << 4) | D; cig[m3, 2] = ((L - a[m3]) << 4) | M
+
+    def le(x, nbytes):  # little-endian bytes of an integer tensor -> [n, nbytes] uint8
+        x = x.to(torch.int64)
+        return torch.stack([((x >> (8 * i)) & 0xFF) for i in range(nbytes)], dim=1).to(torch.uint8)
+
+    # UCSC binning of [pos, pos + span)
+    beg, end = pos, pos + span - 1
+    binv = torch.zeros(n, dtype=torch.int64, device=dev)
+    done = torch.zeros(n, dtype=torch.bool, device=dev)
+    for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+        hit = (~done) & ((beg >> shift) == (end >> shift))
+        binv[hit] = base + (beg[hit] >> shift)
+        done |= hit
+    name = torch.zeros((n, 11), dtype=torch.uint8, device=dev)
+    name[:, 0] = ord("r")
+    rid = read_of.clone()
+    for d in range(9, 0, -1):
+        name[:, d] = (48 + rid % 10).to(torch.uint8)
+        rid = rid // 10
+    aux = torch.cat([torch.tensor(list(b"ASs"), dtype=torch.uint8, device=dev).expand(n, 3), le(as_ & 0xFFFF, 2),
+                     torch.tensor(list(b"XSs"), dtype=torch.uint8, device=dev).expand(n, 3), le(xs_ & 0xFFFF, 2),
+                     torch.tensor(list(b"XNC"), dtype=torch.uint8, device=dev).expand(n, 3), le(torch.zeros_like(xm_), 1),
+                     torch.tensor(list(b"XMC"), dtype=torch.uint8, device=dev).expand(n, 3), le(xm_.clamp(0, 255), 1),
+                     torch.tensor(list(b"XOC"), dtype=torch.uint8, device=dev).expand(n, 3), le(gap, 1),
+                     torch.tensor(list(b"XGC"), dtype=torch.uint8, device=dev).expand(n, 3), le(gap, 1),
+                     torch.tensor(list(b"NMC"), dtype=torch.uint8, device=dev).expand(n, 3), le((xm_ + gap).clamp(0, 255), 1),
+                     torch.tensor(list(b"YTZUU\0"), dtype=torch.uint8, device=dev).expand(n, 6)], dim=1)
+    nseq = (L + 1) // 2
+    fixed_tail = nseq + L + aux.shape[1]
+    size = 4 + 32 + 11 + 4 * ncig + fixed_tail  # bytes of the record including its block_size field
+    head = torch.cat([le(size - 4, 4), le(tid, 4), le(pos, 4), le(torch.full_like(tid, 11), 1), le(torch.full_like(tid, 42), 1), le(binv, 2),
+                      le(ncig, 2), le(fl, 2), le(torch.full_like(tid, L), 4), le(torch.full_like(tid, 0xFFFFFFFF), 4), le(torch.full_like(tid, 0xFFFFFFFF), 4),
+                      le(torch.zeros_like(tid), 4), name], dim=1)  # 36 + 11 bytes
+    ends = torch.cumsum(size, 0)
+    off = ends - size
+    out = torch.empty(int(ends[-1]) if n else 0, dtype=torch.uint8, device=dev)
+    chunk = 1 << 20
+    for c0 in range(0, n, chunk):
+        sl = slice(c0, min(n, c0 + chunk))
+        ro = read_of[sl]
+        for g in (1, 3):
+            sel = torch.nonzero(ncig[sl] == g)[:, 0]
+            if sel.numel() == 0:
+                continue
+            r = ro[sel]
+            rec = torch.cat([head[sl][sel], le(cig[r][:, :g].reshape(-1), 4).reshape(sel.numel(), 4 * g), seq4[r], qual[r], aux[sl][sel]], dim=1)
+            dest = off[sl][sel][:, None] + torch.arange(rec.shape[1], device=dev)[None, :]
+            out[dest.reshape(-1)] = rec.reshape(-1)
+    return out, ends
+
+
+def write_bam_fast(db: SynthDB, cores: List[dict], order: str = "name", align_records: bool = True, level: int = 1, threads: int = 0,
+                   block: int = 0xFF00, path: Optional[str] = None) -> np.ndarray:
+    """BAM file bytes (numpy uint8) of a synthetic sample: records built with tensor ops, BGZF blocks deflated by a thread pool.
+    align_records: BGZF blocks end at record boundaries (what htslib writes); False: cut every `block` bytes wherever that falls
+    (what oracle.bamio writes)."""
+    import os
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    recs, ends = bam_record_bytes(db, cores, order)
+    names, lens = db.ref_names(), db.row_len()
+    text = ("@HD\tVN:1.0\tSO:%s\n" % ("coordinate" if order == "coord" else "unsorted") + "".join("@SQ\tSN:%s\tLN:%d\n" % (n, l) for n, l in zip(names, lens)) +
+            "@PG\tID:bowtie2\tPN:bowtie2\tVN:2.4.4\n").encode()
+    head = [b"BAM\1", struct.pack("<i", len(text)), text, struct.pack("<i", len(names))]
+    for n, l in zip(names, lens):
+        nb = n.encode() + b"\0"
+        head.append(struct.pack("<i", len(nb)) + nb + struct.pack("<i", int(l)))
+    head = b"".join(head)
+    body = recs.cpu().numpy()
+    ends_h = ends.cpu().numpy()
+    cuts = [0]
+    if align_records and ends_h.size:
+        p = 0
+        while p < body.size:
+            j = int(np.searchsorted(ends_h, p + block, side="right")) - 1
+            q = int(ends_h[j]) if j >= 0 and int(ends_h[j]) > p else min(body.size, p + block)
+            cuts.append(q)
+            p = q
+    else:
+        cuts = list(range(0, body.size, block)) + [body.size]
+    pieces = [head[i:i + block] for i in range(0, len(head), block)]  # the header in its own blocks, as htslib flushes it
+    mv = memoryview(body)
+
+    def deflate(data) -> bytes:
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        comp = co.compress(data) + co.flush()
+        return (struct.pack("<BBBBIBBHBBHH", 0x1F, 0x8B, 8, 4, 0, 0, 0xFF, 6, 66, 67, 2, len(comp) + 25) + comp +
+                struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
+
+    spans = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]]
+    with ThreadPoolExecutor(threads or (os.cpu_count() or 1)) as pool:
+        blocks = list(pool.map(lambda ab: deflate(mv[ab[0]:ab[1]]), spans, chunksize=64))
+    raw = b"".join([deflate(p) for p in pieces] + blocks + [_BGZF_EOF])
+    if path:
+        with open(path, "wb") as fh:
+            fh.write(raw)
+    return np.frombuffer(raw, dtype=np.uint8)
