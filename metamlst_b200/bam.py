@@ -120,16 +120,54 @@ class _DevArray:
         self._keep = keep
 
 
-def read_pinned(path: str):
-    """The file's bytes in page-locked memory (one async DMA to the device): a uint8 torch tensor."""
+class PinnedPool:
+    """Page-locked staging buffers, reused: cudaHostAlloc costs milliseconds per call (tens for a large file), a cohort reads hundreds
+    of files.  get(n) hands out a uint8 tensor of at least n bytes, put(t) takes it back."""
+
+    def __init__(self):
+        import threading
+        self._lock = threading.Lock()
+        self._free = []
+
+    def get(self, n: int):
+        import torch
+        with self._lock:
+            best = None
+            for i, t in enumerate(self._free):
+                if t.numel() >= n and (best is None or t.numel() < self._free[best].numel()):
+                    best = i
+            if best is not None:
+                return self._free.pop(best)
+        return torch.empty(max(int(n * 1.25), 1 << 20), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+
+    def put(self, t) -> None:
+        base = getattr(t, "_pool_base", None)
+        if base is not None:
+            with self._lock:
+                if len(self._free) < 16:
+                    self._free.append(base)
+
+
+POOL = PinnedPool()
+
+
+def read_pinned(path: str, pool: Optional[PinnedPool] = None):
+    """The file's bytes in page-locked memory (one async DMA to the device): a uint8 torch tensor.  With a pool the buffer is a
+    recycled one: give it back with pool.put(tensor) once the ingest has consumed it."""
     import torch
     size = os.path.getsize(path)
-    buf = torch.empty(max(size, 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    if pool is not None:
+        base = pool.get(size)
+    else:
+        base = torch.empty(max(size, 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
     with open(path, "rb") as fh:
-        got = fh.readinto(memoryview(buf.numpy())[:size]) if size else 0
+        got = fh.readinto(memoryview(base.numpy())[:size]) if size else 0
     if got != size:
         raise IOError("short read on %s" % path)
-    return buf[:size]
+    view = base[:size]
+    if pool is not None:
+        view._pool_base = base
+    return view
 
 
 def ingest_bam(source, device=0, minqual: int = packing.DEFAULT_MINQUAL, max_depth: Optional[int] = packing.DEFAULT_MAX_DEPTH,

@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -38,22 +39,89 @@ namespace {
 
 using namespace ingest;
 
+thread_local cudaStream_t g_cur_stream = nullptr;   // stream of the mmlst_bam_ingest call running on this thread (DBuf picks it up)
+
 constexpr uint64_t kNoErr = ~0ull;
 constexpr int kT = 256;
+
+// Device workspace cache: an ingest makes ~60 allocations of up to several GB; cudaMalloc / cudaFree cost a fraction of a millisecond to
+// milliseconds each and cudaFree synchronises the device, which was a third of the wall time of a call.  Blocks are cudaMalloc'ed once
+// (plain cudaMalloc: memory the decompression engine accepts), handed out best-fit, and taken back with an event recorded on the stream
+// that used them; a block is reused by ANOTHER stream only after that event.  mmlst_ingest_trim() gives the idle blocks back.
+struct WsBlock { void* p; size_t bytes; bool used; cudaStream_t last; cudaEvent_t ev; bool has_ev; };
+struct Workspace { std::mutex m; std::vector<WsBlock> blocks; };
+Workspace g_ws[MMLST_MAX_DEVICES];
+
+int ws_get(int dev, size_t need, cudaStream_t st, void** out, size_t* got) {
+    Workspace& w = g_ws[dev % MMLST_MAX_DEVICES];
+    need = (need + 511) & ~size_t(511);
+    {
+        std::lock_guard<std::mutex> g(w.m);
+        int best = -1;
+        for (size_t i = 0; i < w.blocks.size(); ++i) {
+            const WsBlock& b = w.blocks[i];
+            if (b.used || b.bytes < need || b.bytes > 2 * need + (1u << 20)) continue;
+            if (best < 0 || b.bytes < w.blocks[best].bytes) best = static_cast<int>(i);
+        }
+        if (best >= 0) {
+            WsBlock& b = w.blocks[best];
+            b.used = true;
+            if (b.has_ev && b.last != st) cudaEventSynchronize(b.ev);
+            *out = b.p; *got = b.bytes;
+            return MMLST_OK;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e != cudaSuccess) {  // give the idle blocks back and try once more
+        cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> g(w.m);
+            for (size_t i = 0; i < w.blocks.size();) {
+                if (!w.blocks[i].used) { if (w.blocks[i].has_ev) cudaEventDestroy(w.blocks[i].ev); cudaFree(w.blocks[i].p); w.blocks.erase(w.blocks.begin() + i); } else ++i;
+            }
+        }
+        e = cudaMalloc(&p, need);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); mmlst_set_error("mmlst_bam_ingest: cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e)); return MMLST_E_NOMEM; }
+    std::lock_guard<std::mutex> g(w.m);
+    w.blocks.push_back(WsBlock{p, need, true, st, nullptr, false});
+    *out = p; *got = need;
+    return MMLST_OK;
+}
+
+void ws_put(int dev, void* p, cudaStream_t st, bool record) {
+    Workspace& w = g_ws[dev % MMLST_MAX_DEVICES];
+    std::lock_guard<std::mutex> g(w.m);
+    for (WsBlock& b : w.blocks) {
+        if (b.p != p) continue;
+        if (record) {
+            if (!b.has_ev) b.has_ev = cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming) == cudaSuccess;
+            if (b.has_ev) cudaEventRecord(b.ev, st);
+            b.last = st;
+        } else if (b.has_ev) { cudaEventDestroy(b.ev); b.has_ev = false; }
+        b.used = false;
+        return;
+    }
+}
+
+constexpr int kSlices = 8;
+struct CopyLane { std::mutex m; cudaStream_t s = nullptr; cudaEvent_t ev[kSlices + 1]; bool ready = false; };
+CopyLane g_lane[MMLST_MAX_DEVICES];
 
 struct DBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    int dev = 0;
+    cudaStream_t st = nullptr;
     int alloc(size_t n) {
         release();
         if (n == 0) n = 16;
-        const cudaError_t e = cudaMalloc(&p, n);
-        if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; mmlst_set_error("mmlst_bam_ingest: cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e)); return MMLST_E_NOMEM; }
-        bytes = n;
-        return MMLST_OK;
+        return ws_get(dev, n, st, &p, &bytes);
     }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void release() { if (p) ws_put(dev, p, st, true); p = nullptr; bytes = 0; }
     template <class T> T* as() const { return static_cast<T*>(p); }
+    DBuf() { cudaGetDevice(&dev); st = g_cur_stream; }
     ~DBuf() { release(); }
 };
 
@@ -313,18 +381,45 @@ struct PackArgs {
     const uint32_t* orig_idx; int minqual; mmlst_prec* recs; uint32_t* planes;
 };
 
-__global__ void __launch_bounds__(128) pack_kernel(const PackArgs a, unsigned long long* err) {
-    const uint64_t j = static_cast<uint64_t>(blockIdx.x) * 128 + threadIdx.x;
+// one WARP per admitted record: lane = contig column inside the 32-column word being built; every lane finds the query base aligned to
+// its column by walking the (short) CIGAR, three ballots assemble the word's planes -- no atomics, no serial walk over the read
+__global__ void __launch_bounds__(kT) pack_kernel(const PackArgs a, unsigned long long* err) {
+    const uint64_t j = (static_cast<uint64_t>(blockIdx.x) * kT + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
     if (j >= a.P) return;
     const uint32_t k = a.list[j];
     const uint32_t pos = static_cast<uint32_t>(a.s_pos[k]), rl = a.s_reflen[k];
     const uint32_t nw = touched_words(pos, rl), rw = row_words(nw);
-    mmlst_prec m;
-    m.pos = static_cast<int32_t>(pos); m.row_off = static_cast<uint32_t>(a.rowoff[j]); m.reflen = static_cast<uint16_t>(rl);
-    m.as_named = a.s_asn[k]; m.xm_named = a.s_xmn[k]; m.pad = 0; m.nw = static_cast<uint16_t>(nw);
-    a.recs[j] = m;
-    const uint32_t e = pack_record(a.u, a.s_roff[k], pos, rl, (a.s_bits[k] & 2u) != 0, a.minqual, a.planes + a.rowoff[j], rw);
-    if (e != E_NONE) report(err, a.orig_idx ? a.orig_idx[k] : k, e);
+    uint32_t* row = a.planes + a.rowoff[j];
+    if (lane == 0) {
+        mmlst_prec m;
+        m.pos = static_cast<int32_t>(pos); m.row_off = static_cast<uint32_t>(a.rowoff[j]); m.reflen = static_cast<uint16_t>(rl);
+        m.as_named = a.s_asn[k]; m.xm_named = a.s_xmn[k]; m.pad = 0; m.nw = static_cast<uint16_t>(nw);
+        a.recs[j] = m;
+    }
+    if (rl == 0) return;
+    const uint8_t* r = a.u + a.s_roff[k];
+    const uint32_t l_name = r[12], n_cig = rd16(r + 16), l_seq = rd32(r + 20);
+    const uint8_t* cig = r + 36 + l_name;
+    const uint8_t* seq = cig + 4ull * n_cig;
+    const uint8_t* qual = seq + (static_cast<uint64_t>(l_seq) + 1) / 2;
+    uint32_t e = E_NONE;
+    if (!(a.s_bits[k] & 2u)) e = E_NAMED;
+    else if (l_seq && qual[0] == 0xff) e = E_NOQUAL;
+    if (e != E_NONE) {
+        for (uint32_t w = lane; w < rw; w += 32) row[w] = 0;
+        if (lane == 0) report(err, a.orig_idx ? a.orig_idx[k] : k, e);
+        return;
+    }
+    for (uint32_t w = 0; w < nw; ++w) {
+        const uint32_t col = ((pos >> 5) + w) * 32u + lane;
+        const uint32_t cls = column_class(cig, n_cig, seq, qual, l_seq, pos, rl, col, a.minqual);
+        const uint32_t pv = __ballot_sync(0xffffffffu, cls >= 1u && cls <= 4u);
+        const uint32_t p1 = __ballot_sync(0xffffffffu, cls == 3u || cls == 4u);
+        const uint32_t p0 = __ballot_sync(0xffffffffu, cls == 2u || cls == 4u || cls == 5u);
+        if (lane == 0) { row[3 * w] = pv; row[3 * w + 1] = p1; row[3 * w + 2] = p0; }
+    }
+    if (lane == 0 && rw > 3 * nw) row[3 * nw] = 0;
 }
 
 const char* err_text(uint32_t code) {
@@ -375,7 +470,23 @@ struct mmlst_dev_bam {
 extern "C" void mmlst_dev_bam_free(mmlst_dev_bam* b) {
     if (!b) return;
     cudaSetDevice(b->device);
+    cudaDeviceSynchronize();   // whatever stream still reads the streams: the blocks go back to the cache for any stream to take
+    for (DBuf* d : {&b->tid, &b->as0, &b->xm3, &b->qlen, &b->orig_idx, &b->qhash, &b->run_tid, &b->run_start, &b->chunk_run, &b->chunk_qlen, &b->p_recs, &b->planes}) {
+        if (d->p) ws_put(d->dev, d->p, d->st, false);
+        d->p = nullptr;
+    }
     delete b;
+}
+
+extern "C" int mmlst_ingest_trim(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    Workspace& w = g_ws[device % MMLST_MAX_DEVICES];
+    std::lock_guard<std::mutex> g(w.m);
+    for (size_t i = 0; i < w.blocks.size();) {
+        if (!w.blocks[i].used) { if (w.blocks[i].has_ev) cudaEventDestroy(w.blocks[i].ev); cudaFree(w.blocks[i].p); w.blocks.erase(w.blocks.begin() + i); } else ++i;
+    }
+    return MMLST_OK;
 }
 
 extern "C" int mmlst_dev_bam_info(const mmlst_dev_bam* b, mmlst_dev_bam_info_t* o) {
@@ -417,6 +528,7 @@ extern "C" int mmlst_bam_ingest(int device, const uint8_t* bam, size_t n_bytes, 
     if (opts_in) o = *opts_in;
     CUDA_TRY(cudaSetDevice(device));
     cudaStream_t st = static_cast<cudaStream_t>(stream_in);
+    g_cur_stream = st;
     // the hardware decompression engine, through the driver entry point (libcuda is already loaded by the runtime)
     decomp_fn decompress = nullptr;
     {
@@ -492,7 +604,6 @@ extern "C" int mmlst_bam_ingest(int device, const uint8_t* bam, size_t n_bytes, 
     CUDA_TRY(cudaMemsetAsync(err, 0xff, 8, st));
     CUDA_TRY(cudaMemsetAsync(d_flags, 0, 32, st));
     mark();  // 0
-    CUDA_TRY(cudaMemcpyAsync(d_comp.p, bam, n_bytes, cudaMemcpyHostToDevice, st));
     std::vector<uint32_t> h_isize(nb);
     std::vector<uint64_t> h_uoff(nb + 1);
     for (uint32_t b = 0; b < nb; ++b) { h_isize[b] = blocks[b].isize; h_uoff[b] = blocks[b].uoff; }
@@ -510,15 +621,39 @@ extern "C" int mmlst_bam_ingest(int device, const uint8_t* bam, size_t n_bytes, 
         prm[b].dst = d_u.as<uint8_t>() + blocks[b].uoff;
         prm[b].algo = CU_MEM_DECOMPRESS_ALGORITHM_DEFLATE;
     }
-    for (uint32_t b0 = 0; b0 < nb; b0 += 1u << 16) {
-        const size_t cnt = std::min<size_t>(1u << 16, nb - b0);
-        size_t bad = static_cast<size_t>(-1);
-        const CUresult rc = decompress(prm.data() + b0, cnt, 0, &bad, reinterpret_cast<CUstream>(st));
-        if (rc != CUDA_SUCCESS) {
-            mmlst_set_error("mmlst_bam_ingest: cuMemBatchDecompressAsync failed (CUresult %d) at BGZF block %lld", static_cast<int>(rc),
-                            bad == static_cast<size_t>(-1) ? -1ll : static_cast<long long>(b0 + bad));
-            return MMLST_E_CUDA;
+    // the file goes over in slices on a copy stream while the decompression engine works on the slices that have landed: the copy
+    // engine and the decompression engine are different units, so PCIe time hides behind the inflate (or the other way round)
+    {
+        CopyLane& lane = g_lane[device % MMLST_MAX_DEVICES];
+        std::lock_guard<std::mutex> g(lane.m);
+        if (!lane.ready) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&lane.s, cudaStreamNonBlocking));
+            for (auto& e : lane.ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            lane.ready = true;
         }
+        CUDA_TRY(cudaEventRecord(lane.ev[kSlices], st));
+        CUDA_TRY(cudaStreamWaitEvent(lane.s, lane.ev[kSlices], 0));
+        const uint32_t per = (nb + kSlices - 1) / kSlices;
+        size_t lo = 0;
+        for (uint32_t c = 0, b0 = 0; b0 < nb; ++c, b0 += per) {
+            const uint32_t b1 = std::min(nb, b0 + per);
+            const size_t hi = (b1 == nb) ? n_bytes : static_cast<size_t>(blocks[b1].coff);   // up to the next slice's first payload byte
+            CUDA_TRY(cudaMemcpyAsync(d_comp.as<uint8_t>() + lo, bam + lo, hi - lo, cudaMemcpyHostToDevice, lane.s));
+            CUDA_TRY(cudaEventRecord(lane.ev[c], lane.s));
+            CUDA_TRY(cudaStreamWaitEvent(st, lane.ev[c], 0));
+            lo = hi;
+            for (uint32_t q0 = b0; q0 < b1; q0 += 1u << 16) {
+                const size_t cnt = std::min<size_t>(1u << 16, b1 - q0);
+                size_t bad = static_cast<size_t>(-1);
+                const CUresult rc = decompress(prm.data() + q0, cnt, 0, &bad, reinterpret_cast<CUstream>(st));
+                if (rc != CUDA_SUCCESS) {
+                    mmlst_set_error("mmlst_bam_ingest: cuMemBatchDecompressAsync failed (CUresult %d) at BGZF block %lld", static_cast<int>(rc),
+                                    bad == static_cast<size_t>(-1) ? -1ll : static_cast<long long>(q0 + bad));
+                    return MMLST_E_CUDA;
+                }
+            }
+        }
+        CUDA_TRY(cudaStreamSynchronize(lane.s));   // the lane (and its events) is free for the next call
     }
     check_isize_kernel<<<(nb + kT - 1) / kT, kT, 0, st>>>(d_act.as<uint32_t>(), d_isize.as<uint32_t>(), nb, err);
     CUDA_TRY(cudaGetLastError());
@@ -760,7 +895,7 @@ extern "C" int mmlst_bam_ingest(int device, const uint8_t* bam, size_t n_bytes, 
         const PackArgs pa{d_u.as<uint8_t>(), d_list.as<uint32_t>(), P, d_rowoff.as<uint64_t>(), s_pos.as<int32_t>(), s_reflen.as<uint16_t>(), s_bits.as<uint8_t>(),
                           s_asn.as<int16_t>(), s_xmn.as<uint8_t>(), s_roff.as<uint64_t>(), sorted ? nullptr : B->orig_idx.as<uint32_t>(), o.minqual,
                           B->p_recs.as<mmlst_prec>(), B->planes.as<uint32_t>()};
-        pack_kernel<<<static_cast<unsigned>((P + 127) / 128), 128, 0, st>>>(pa, err);
+        pack_kernel<<<static_cast<unsigned>((P * 32 + kT - 1) / kT), kT, 0, st>>>(pa, err);
         CUDA_TRY(cudaGetLastError());
     }
     mark();  // 8

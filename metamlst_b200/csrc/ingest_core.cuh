@@ -240,4 +240,32 @@ ING_HD uint32_t pack_record(const uint8_t* u, uint64_t off, uint32_t pos, uint32
     return E_NONE;
 }
 
+// The same row, one COLUMN at a time (the warp form of the packer: lane = column): class of contig column `col` for this record,
+// 0 = not in the column (outside the span, deletion / ref-skip, quality under minqual, beyond l_seq); 1..4 = A,C,G,T with quality
+// >= minqual; 5 = counted non-ACGT base (bin N).
+ING_HD uint32_t column_class(const uint8_t* cig, uint32_t n_cig, const uint8_t* seq, const uint8_t* qual, uint32_t l_seq, uint32_t pos, uint32_t reflen,
+                             uint32_t col, int minqual) {
+    if (col < pos || col - pos >= reflen) return 0;
+    const uint32_t rel = col - pos;
+    uint32_t rx = 0, qy = 0;
+    for (uint32_t k = 0; k < n_cig; ++k) {
+        const uint32_t cw = rd32(cig + 4 * k), op = cw & 15u, ln = cw >> 4;
+        if (op == 0 || op == 7 || op == 8) {
+            if (rel - rx < ln) {
+                const uint32_t y = qy + (rel - rx);
+                if (y >= l_seq) return 0;
+                if (static_cast<int>(qual[y]) < minqual) return 0;
+                const uint32_t nib = (seq[y >> 1] >> ((~y & 1u) << 2)) & 15u;
+                return nib == 1u ? 1u : nib == 2u ? 2u : nib == 4u ? 3u : nib == 8u ? 4u : 5u;
+            }
+            rx += ln; qy += ln;
+        } else if (op == 1 || op == 4) qy += ln;
+        else if (op == 2 || op == 3) {
+            if (rel - rx < ln) return 0;
+            rx += ln;
+        }
+    }
+    return 0;
+}
+
 }  // namespace ingest

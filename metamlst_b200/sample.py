@@ -99,6 +99,7 @@ class SampleResult:
     broken_db: bool = False                              # the reference's sys.exit(0) at metamlst.py:190
     calls: List[SpeciesCall] = field(default_factory=list)
     seconds: Dict[str, float] = field(default_factory=dict)
+    records: int = 0
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -237,13 +238,25 @@ class SampleTyper:
         """Phase 1: BAM -> packed streams.  Safe to call from another thread than type_unpacked."""
         return bam.unpack_bam(bam_path, presorted=self.presorted, threads=self.unpack_threads)
 
+    def load(self, bam_path: str):
+        """Host half of phase 1, safe on a prefetch thread: ingest="host" -> the unpacked streams (C++ threads); ingest="device" -> the
+        file's bytes in page-locked memory (the GPU does the rest: `ingest`)."""
+        if self.ingest == "device" and self.engine == "device":
+            return bam.read_pinned(bam_path, bam.POOL)
+        return self.unpack(bam_path)
+
+    def ingest_loaded(self, loaded, want_qhash: bool = False):
+        """Device half of phase 1 for ingest="device": compressed bytes cross PCIe; inflate / parse / sort / depth cap / packing happen
+        in HBM (csrc/ingest.cu).  A host-unpacked sample passes through."""
+        if hasattr(loaded, "c_struct"):
+            return loaded
+        st = bam.ingest_bam(loaded, self.device, presorted=self.presorted, want_qhash=want_qhash)
+        bam.POOL.put(loaded)  # the call is synchronous: the staging buffer has been consumed
+        return st
+
     def type_bam(self, bam_path: str, out_dir: str, want_stdout: bool = False, timestamp: Optional[int] = None) -> SampleResult:
         t0 = time.perf_counter()
-        if self.ingest == "device" and self.engine == "device":
-            # the compressed file crosses PCIe; inflate / parse / sort / depth cap / packing happen on the device (csrc/ingest.cu)
-            soa = bam.ingest_bam(bam_path, self.device, presorted=self.presorted, want_qhash=want_stdout)
-        else:
-            soa = self.unpack(bam_path)
+        soa = self.ingest_loaded(self.load(bam_path), want_qhash=want_stdout)
         t1 = time.perf_counter()
         res = self.type_unpacked(soa, bam_path, want_stdout=want_stdout)
         res.seconds["unpack"] = t1 - t0
@@ -409,10 +422,11 @@ class SampleTyper:
 
 
 def type_cohort(bam_paths: Sequence[str], db_path: str, out_dir: str, devices: Sequence[int] = (0,), prefetch: int = 2,
-                **params) -> List[SampleResult]:
+                typers: Optional[Dict[int, "SampleTyper"]] = None, **params) -> List[SampleResult]:
     """Type a cohort back to back (BASELINE.json configs[3]): per device one worker thread owning a SampleTyper (one DB
-    connection, one set of device tables for the whole cohort); an unpack thread per device runs `prefetch` samples ahead.
-    Samples are dealt round-robin to the devices; results come back in input order."""
+    connection, one set of device tables for the whole cohort); a loader thread per device runs `prefetch` samples ahead (host
+    unpack, or with ingest="device" just the file read into page-locked memory).  Samples are dealt round-robin to the devices;
+    results come back in input order.  `typers` ({device: SampleTyper}): reuse warm typers (they stay open) instead of making new ones."""
     results: List[Optional[SampleResult]] = [None] * len(bam_paths)
     errors: List[BaseException] = []
 
@@ -420,7 +434,7 @@ def type_cohort(bam_paths: Sequence[str], db_path: str, out_dir: str, devices: S
         mine = [i for i in range(len(bam_paths)) if i % len(devices) == slot]
         if not mine:
             return
-        typer = SampleTyper(db_path, device=device, **params)
+        typer = typers[device] if typers is not None else SampleTyper(db_path, device=device, **params)
         q: "queue.Queue" = queue.Queue(maxsize=max(1, prefetch))
         stop = threading.Event()
 
@@ -439,7 +453,7 @@ def type_cohort(bam_paths: Sequence[str], db_path: str, out_dir: str, devices: S
                     return
                 try:
                     t0 = time.perf_counter()
-                    soa = typer.unpack(bam_paths[i])
+                    soa = typer.load(bam_paths[i])
                     if not put((i, soa, time.perf_counter() - t0, None)):
                         return
                 except BaseException as e:  # noqa: BLE001
@@ -458,8 +472,12 @@ def type_cohort(bam_paths: Sequence[str], db_path: str, out_dir: str, devices: S
                 if err is not None:
                     raise err
                 t0 = time.perf_counter()
+                soa = typer.ingest_loaded(soa)
+                t_ing = time.perf_counter() - t0
                 res = typer.type_unpacked(soa, bam_paths[i])
-                res.seconds["unpack"] = t_unpack
+                res.seconds["load"] = t_unpack
+                res.seconds["device_ingest"] = t_ing
+                res.records = int(soa.tid.shape[0]) if hasattr(soa, "tid") else 0
                 del soa
                 typer.write(res, bam_paths[i], out_dir)
                 res.seconds["typed_and_written"] = time.perf_counter() - t0
@@ -474,7 +492,8 @@ def type_cohort(bam_paths: Sequence[str], db_path: str, out_dir: str, devices: S
                 except queue.Empty:
                     break
             th.join(timeout=5)
-            typer.close()
+            if typers is None:
+                typer.close()
 
     threads = [threading.Thread(target=worker, args=(s, d)) for s, d in enumerate(devices)]
     for t in threads:

@@ -68,6 +68,43 @@ class DeviceStreams:
             self.chunk_qlen = q2[:, 0].to(torch.int16).contiguous()  # bit pattern of the u16
         return self
 
+    def slice_ranges(self, rank: int, world: int) -> "DeviceStreams":
+        """This rank's shard of device-resident streams, mode "ranges" (module text): a contiguous range of the score stream
+        (file-order indices kept through idx_base / orig_idx) and a contiguous range of the pileup stream, rows rebased.  The
+        depth cap was resolved over the whole sample when the streams were packed."""
+        if world <= 1:
+            return self
+        dev = self.as0.device
+        n, P = int(self.tid.shape[0]), int(self.n_prec)
+        a, b = (n * rank) // world, (n * (rank + 1)) // world
+        p0, p1 = (P * rank) // world, (P * (rank + 1)) // world
+        s = DeviceStreams()
+        s.ref_names, s.ref_lens = self.ref_names, self.ref_lens
+        s.minqual, s.max_depth, s.n_dropped = self.minqual, self.max_depth, getattr(self, "n_dropped", 0)
+        s.tid, s.as0, s.xm3, s.qlen = self.tid[a:b].contiguous(), self.as0[a:b].contiguous(), self.xm3[a:b].contiguous(), self.qlen[a:b].contiguous()
+        oi = getattr(self, "orig_idx", None)
+        s.orig_idx = None if oi is None else oi[a:b].contiguous()
+        s.idx_base = (int(getattr(self, "idx_base", 0) or 0) + a) if oi is None else 0
+        qh = getattr(self, "qhash", None)
+        s.qhash = None if qh is None else qh[a:b].contiguous()
+        total_words = int(self.planes.shape[0]) - packing.PLANE_SLACK_WORDS
+        off = lambda j: (int(self.p_recs[j, 1].item()) & 0xFFFFFFFF) if j < P else total_words
+        w0, w1 = (off(p0), off(p1)) if p1 > p0 else (0, 0)
+        recs = self.p_recs[p0:p1].clone()
+        if w0 and p1 > p0:
+            recs[:, 1] = ((recs[:, 1].to(torch.int64) & 0xFFFFFFFF) - w0).to(torch.int32)
+        s.p_recs = recs
+        s.planes = torch.cat([self.planes[w0:w1], torch.zeros(packing.PLANE_SLACK_WORDS, dtype=torch.int32, device=dev)])
+        s.n_prec, s.max_row_words = p1 - p0, int(self.max_row_words)
+        cs = np.asarray(self.contig_start, dtype=np.int64)
+        s.contig_start = (np.clip(cs, p0, p1) - p0).astype(np.uint64)
+        s.run_tid = s.run_start = s.chunk_run = s.chunk_qlen = None
+        if getattr(self, "run_tid", None) is not None and b > a:
+            s.build_runs()
+            if int(s.run_tid.shape[0]) > 0.125 * (b - a):
+                s.run_tid = s.run_start = s.chunk_run = s.chunk_qlen = None
+        return s
+
     # ------------------------------------------------------------------------------------------------------------
     @classmethod
     def from_soa(cls, soa: packing.SoaHost, device, rank: int = 0, world: int = 1, mode: str = "ranges",

@@ -110,13 +110,17 @@ class SynthDB:
                 f.write("%d\t%s\n" % (st + 1, "\t".join(str(int(v)) for v in p[st])))
 
 
-def make_db(organisms: Sequence[str] = ("ecoli",), alleles_per_locus: int = 256, n_profiles: int = 2048,
+def make_db(organisms: Sequence[str] = ("ecoli",), alleles_per_locus=256, n_profiles: int = 2048,
             seed: int = 1001, subs_lambda: float = 5.0,
             schemes: Optional[Dict[str, List[Tuple[str, int]]]] = None) -> SynthDB:
-    """Each allele = the locus's random base sequence + Poisson(subs_lambda) substitutions."""
+    """Each allele = the locus's random base sequence + Poisson(subs_lambda) substitutions.  alleles_per_locus: one count for
+    every locus, or a sequence with one count per locus (organism-major order)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     schemes = schemes or SCHEMES
     loci = {o: list(schemes[o]) for o in organisms}
+    n_loci_total = sum(len(v) for v in loci.values())
+    apl = [int(alleles_per_locus)] * n_loci_total if np.isscalar(alleles_per_locus) else [int(x) for x in alleles_per_locus]
+    assert len(apl) == n_loci_total
     row_org, row_locus, row_variant, seqs, locus_names, locus_row0 = [], [], [], [], [], [0]
     li = 0
     for oi, o in enumerate(organisms):
@@ -124,7 +128,7 @@ def make_db(organisms: Sequence[str] = ("ecoli",), alleles_per_locus: int = 256,
             base = rng.integers(0, 4, size=ln, dtype=np.int64)
             seen = set()
             v = 0
-            while v < alleles_per_locus:
+            while v < apl[li]:
                 s = base.copy()
                 k = int(rng.poisson(subs_lambda)) if v > 0 else 0
                 if k:
@@ -145,9 +149,11 @@ def make_db(organisms: Sequence[str] = ("ecoli",), alleles_per_locus: int = 256,
     seq_off = np.zeros(len(seqs) + 1, dtype=np.int64)
     seq_off[1:] = np.cumsum([len(s) for s in seqs])
     profiles = {}
+    li0 = 0
     for o in organisms:
         nl = len(loci[o])
-        p = rng.integers(1, alleles_per_locus + 1, size=(n_profiles, nl)).astype(np.int32)
+        p = rng.integers(1, np.asarray(apl[li0:li0 + nl]) + 1, size=(n_profiles, nl)).astype(np.int32)
+        li0 += nl
         # distinct tuples (duplicates would make defineProfile ambiguous)
         _, idx = np.unique(p, axis=0, return_index=True)
         profiles[o] = p[np.sort(idx)]

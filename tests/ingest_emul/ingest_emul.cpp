@@ -93,4 +93,30 @@ uint64_t emul_pack(const uint8_t* u, const uint64_t* roff, const uint32_t* list,
     return 0;
 }
 
+// the warp form of pack_kernel: every 32-column word assembled from column_class of its 32 "lanes"
+uint64_t emul_pack_columns(const uint8_t* u, const uint64_t* roff, const uint32_t* list, uint64_t P, const int32_t* pos, const uint16_t* reflen, int minqual,
+                           const uint64_t* rowoff, uint32_t* planes) {
+    for (uint64_t j = 0; j < P; ++j) {
+        const uint32_t k = list[j];
+        const uint32_t p0 = static_cast<uint32_t>(pos[k]), rl = reflen[k];
+        const uint32_t nw = touched_words(p0, rl), rw = row_words(nw);
+        uint32_t* row = planes + rowoff[j];
+        for (uint32_t w = 0; w < rw; ++w) row[w] = 0;
+        if (rl == 0) continue;
+        const uint8_t* r = u + roff[k];
+        const uint32_t l_name = r[12], n_cig = rd16(r + 16), l_seq = rd32(r + 20);
+        const uint8_t* cig = r + 36 + l_name;
+        const uint8_t* seq = cig + 4ull * n_cig;
+        const uint8_t* qual = seq + (static_cast<uint64_t>(l_seq) + 1) / 2;
+        for (uint32_t w = 0; w < nw; ++w)
+            for (uint32_t lane = 0; lane < 32; ++lane) {
+                const uint32_t cls = column_class(cig, n_cig, seq, qual, l_seq, p0, rl, ((p0 >> 5) + w) * 32u + lane, minqual);
+                if (cls >= 1 && cls <= 4) row[3 * w] |= 1u << lane;
+                if (cls == 3 || cls == 4) row[3 * w + 1] |= 1u << lane;
+                if (cls == 2 || cls == 4 || cls == 5) row[3 * w + 2] |= 1u << lane;
+            }
+    }
+    return 0;
+}
+
 }  // extern "C"

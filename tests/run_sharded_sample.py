@@ -18,6 +18,7 @@ def main():
     torch.cuda.set_device(local)
     torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank = torch.distributed.get_rank()
+    os.makedirs(out_root, exist_ok=True)
     man = json.load(open(os.path.join(GOLDEN, "manifest.json")))
     cases = sorted(k for k in man if os.path.exists(os.path.join(GOLDEN, k, "sample.bam")) and not set(man[k]["args"]) - {"--log", "-a", "--presorted"})
     for name in cases:

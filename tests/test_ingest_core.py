@@ -117,6 +117,10 @@ def emulate(lib, raw: bytes, minqual=20, max_depth=8000):
     e = lib.emul_pack(ptr(u), ptr(np.ascontiguousarray(s_roff)), ptr(lst), C.c_uint64(lst.size), ptr(np.ascontiguousarray(pos)), ptr(np.ascontiguousarray(s_reflen)),
                       ptr(np.ascontiguousarray(s_bits)), minqual, ptr(rowoff), ptr(planes))
     assert e == 0, ("pack refused", e >> 8, e & 0xff)
+    planes2 = np.full_like(planes, 0xdeadbeef); planes2[int(rowoff[-1]):] = 0
+    lib.emul_pack_columns(ptr(u), ptr(np.ascontiguousarray(s_roff)), ptr(lst), C.c_uint64(lst.size), ptr(np.ascontiguousarray(pos)), ptr(np.ascontiguousarray(s_reflen)),
+                          minqual, ptr(rowoff), ptr(planes2))
+    assert np.array_equal(planes, planes2), "the column-wise (warp) form of the packer differs from the serial walk"
     return dict(names=names, n=n, repairs=rep.value, sorted=sorted_already, tid=tid, as0=as0[order], xm3=xm3[order], qlen=qlen[order], orig_idx=order.astype(np.uint32),
                 qhash=qh.reshape(n, 2)[order], p_pos=pos[lst], p_reflen=s_reflen[lst], p_as=asn[order][lst], p_xm=xmn[order][lst], p_nw=nw, p_row_off=rowoff[:-1],
                 planes=planes, contig_start=np.searchsorted(tid[lst], np.arange(n_ref + 1)))

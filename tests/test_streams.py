@@ -114,3 +114,18 @@ def test_one_real_sample_sharded_over_two_ranks(tmp_path):
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
     assert p.returncode == 0, p.stdout.decode()[-3000:]
     assert "SHARDED-OK" in p.stdout.decode()
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_slicing_resident_streams_equals_sharding_the_host_sample(world):
+    """DeviceStreams.slice_ranges (a device-resident sample cut after packing: bench_configs.py c3) == from_soa(mode="ranges")."""
+    db, tab, soa = _soa()
+    whole = streams.DeviceStreams.from_soa(soa, "cpu")
+    for r in range(world):
+        a = whole.slice_ranges(r, world)
+        b = streams.DeviceStreams.from_soa(soa, "cpu", rank=r, world=world, mode="ranges")
+        for k in ("tid", "as0", "xm3", "qlen", "p_recs", "planes"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), k
+        assert (a.orig_idx is None) == (b.orig_idx is None) and (a.orig_idx is None or torch.equal(a.orig_idx, b.orig_idx))
+        assert a.idx_base == b.idx_base and a.n_prec == b.n_prec and np.array_equal(a.contig_start, b.contig_start)
+        assert (a.run_tid is None) == (b.run_tid is None) and (a.run_tid is None or torch.equal(a.run_tid, b.run_tid))
