@@ -263,6 +263,34 @@ def workload_config(args, world):
                   "(L2 flush)" % (args.reads * args.k * 3 // 1000000, args.reads * args.k * 5 // 1000000)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank's host threads (and, by first touch, its page-locked buffers) on the NUMA node the GPU hangs off: with 8 ranks pushing
+    host buffers at PCIe speed, cross-socket traffic was what held e2e scaling back in round 1.  Best effort; returns a description."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return "numa_node -1 (single node)"
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return "node %d, %d cpus" % (node, len(allowed))
+        return "node %d has no allowed cpu" % node
+    except Exception as e:  # noqa: BLE001
+        return "unbound (%r)" % (e,)
+
+
 _REAL_STDOUT = None
 
 
@@ -295,6 +323,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.lanes <= 0:
         args.lanes = 6
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "not bound (one rank)"
     torch.cuda.set_device(local)
     device = "cuda:%d" % local
     if world > 1:
@@ -494,6 +523,12 @@ def main():
     soa = st.to_host(pinned=True)
     ctx = native.Context(local)
 
+    e2e_words = 1 + 3 * n_loci + (int(np.sort(np.asarray(st.ref_lens))[::-1][:n_loci].sum()) + 3) // 4 + 4
+    if world > 1:
+        e2e_pin = torch.zeros(e2e_words * 4, dtype=torch.uint8).pin_memory()
+        e2e_dev = torch.zeros(e2e_words * 4, dtype=torch.uint8, device=device)
+        e2e_all = torch.zeros(world * e2e_words * 4, dtype=torch.uint8, device=device)
+
     def e2e_step():
         cel_raw = api.score_soa_raw(ctx, soa, index, **{k: PARAMS[k] for k in ("minscore", "max_xM", "min_read_len")})
         chosen = api.fast_select(index, cel_raw[0], cel_raw[1], cel_raw[2], PARAMS["penalty"])
@@ -501,9 +536,29 @@ def main():
         seqs, holes, snps, _, _ = api.pileup_consensus(ctx, soa, ts, [db.row_seq(t) for t in ts], PARAMS["minscore"], PARAMS["max_xM"], 1, args.pileup_impl)
         mine = {index.ref_names[t]: (seqs[i], int(holes[i]), int(snps[i])) for i, t in enumerate(ts)}
         if world > 1:
-            parts = [None] * world
-            torch.distributed.all_gather_object(parts, mine)
-            mine = {k: v for p in parts for k, v in p.items()}
+            # every rank's result block to every rank: ONE fixed-size all-gather (NCCL) of [n | tid, holes, snps per locus | consensus bytes]
+            blk = np.zeros(e2e_words * 4, np.uint8)
+            w32 = blk.view(np.int32)
+            w32[0] = len(ts)
+            w32[1:1 + len(ts)] = ts
+            w32[1 + n_loci:1 + n_loci + len(ts)] = holes[:len(ts)]
+            w32[1 + 2 * n_loci:1 + 2 * n_loci + len(ts)] = snps[:len(ts)]
+            cat = "".join(seqs).encode("latin-1")
+            blk[(1 + 3 * n_loci) * 4:(1 + 3 * n_loci) * 4 + len(cat)] = np.frombuffer(cat, np.uint8)
+            e2e_pin.numpy()[:] = blk
+            e2e_dev.copy_(e2e_pin, non_blocking=True)
+            torch.distributed.all_gather_into_tensor(e2e_all, e2e_dev)
+            allb = e2e_all.cpu().numpy().reshape(world, -1)
+            mine = {}
+            for r in range(world):
+                v32 = allb[r].view(np.int32)
+                n = int(v32[0])
+                off = (1 + 3 * n_loci) * 4
+                for i in range(n):
+                    t = int(v32[1 + i])
+                    ln = int(st.ref_lens[t])
+                    mine[index.ref_names[t]] = (allb[r][off:off + ln].tobytes().decode("latin-1"), int(v32[1 + n_loci + i]), int(v32[1 + 2 * n_loci + i]))
+                    off += ln
         return ts, mine
 
     for _ in range(2):
@@ -530,7 +585,8 @@ def main():
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.SUM)
         dt = float(mx[0].item())
     line["e2e"] = {"value": R_total / dt, "unit": "records/s", "h2d_bytes_per_step": int(tt[1].item()), "d2h_bytes_per_step": int(tt[2].item()),
-                   "ms_per_step": dt * 1e3, "timing": "host wall clock around the synchronous C-ABI calls, barrier on both sides, max over ranks"}
+                   "ms_per_step": dt * 1e3, "timing": "host wall clock around the synchronous C-ABI calls, barrier on both sides, max over ranks",
+                   "host_numa_binding": numa, "exchange": "one fixed-size NCCL all-gather of the per-rank result blocks" if world > 1 else "none (one rank)"}
     ctx.close()
     del soa
 
