@@ -345,6 +345,25 @@ int mmlst_hamming_min_x(mmlst_ctx* ctx, const uint32_t* q_hi, const uint32_t* q_
                         const uint32_t* blocks, uint32_t n_blocks, uint32_t* min_dist, uint32_t* argmin_row);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Stage 3 on the tensor cores (csrc/hamming_tc.cu): the all-pairs closest-allele sweep as a tcgen05 GEMM.  Same semantics, same best[]
+ * convention as mmlst_hamming_min_dev for ONE block covering every query and every row (metaMLST_functions.py:230-234 over
+ * metamlst-merge.py:174-181): distance = (3 min(len) - <f(q), f(r)>) / 4 with every base written as three signs in e4m3 and zeros
+ * beyond the end of a sequence (the zip truncation, H9); exact (integers in an FP32 accumulator).  Flagged sequences are skipped
+ * (mmlst_hamming_exact_dev covers them).
+ *   mmlst_hamming_tc_expand_dev : bit planes -> e4m3 tile image (device, 16-byte aligned, mmlst_hamming_tc_image_bytes bytes) + the
+ *                                 largest clean length of every tile; tile_rows = 128 for queries ([Q][W] row-major planes,
+ *                                 db_tiled_layout = 0), 256 for DB rows (the tiled plane layout of mmlst_hamming_min_dev,
+ *                                 db_tiled_layout = 1).  W a multiple of 4.  The DB image is made once and stays resident.
+ *   mmlst_hamming_tc_search_dev : min-merges into best[q] (caller presets ~0ull); persistent kernel, one CTA per SM.
+ * --------------------------------------------------------------------------------------------------------------- */
+size_t mmlst_hamming_tc_image_bytes(uint32_t n, uint32_t W, uint32_t tile_rows);
+int mmlst_hamming_tc_expand_dev(const uint32_t* hi, const uint32_t* lo, const uint16_t* len, uint32_t n, uint32_t W, int db_tiled_layout,
+                                uint32_t tile_rows, uint8_t* image, uint32_t* tile_maxlen, void* stream);
+int mmlst_hamming_tc_search_dev(const uint8_t* q_image, const uint32_t* q_tile_maxlen, const uint16_t* q_len, uint32_t n_q,
+                                const uint8_t* db_image, const uint32_t* db_tile_maxlen, const uint16_t* row_len, uint32_t n_rows,
+                                uint32_t W, uint32_t row_index_base, unsigned long long* best, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Exact-sequence lookup (row a10).  Replaces the un-indexed scans `SELECT .. FROM alleles WHERE sequence = ? AND bacterium = ?`
  * + fetchone() of sequenceExists / sequenceFind / sequenceLocate (metaMLST_functions.py:168-172, 196-203, 218-222):
  *   first_row[q] = lowest DB row (or lowest row_key[row], see mmlst_db_row_keys) inside the query's block (= the organism's row range, table order) whose sequence equals the
@@ -455,6 +474,9 @@ typedef struct {
 int mmlst_bam_ingest(int device, const uint8_t* bam, size_t n_bytes, const mmlst_unpack_opts* opts, void* stream, mmlst_dev_bam** out);
 int mmlst_dev_bam_info(const mmlst_dev_bam* bam, mmlst_dev_bam_info_t* info);
 void mmlst_dev_bam_free(mmlst_dev_bam* bam);
+/* the ingest keeps its device workspace (a few allocations of up to the inflated size of the largest file seen) cached between calls;
+ * this gives the idle blocks back to the driver */
+int mmlst_ingest_trim(int device);
 
 #ifdef __cplusplus
 }

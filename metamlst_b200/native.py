@@ -110,6 +110,11 @@ EXPORTS = {
     "mmlst_bam_free": (None, [C.c_void_p]),
     "mmlst_hamming_min": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                     C.c_void_p, C.c_void_p]),
+    "mmlst_hamming_tc_image_bytes": (C.c_size_t, [C.c_uint32, C.c_uint32, C.c_uint32]),
+    "mmlst_hamming_tc_expand_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmlst_hamming_tc_search_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                              C.c_uint32, C.c_void_p, C.c_void_p]),
+    "mmlst_ingest_trim": (C.c_int, [C.c_int]),
     "mmlst_bam_ingest": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mmlst_dev_bam_info": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mmlst_dev_bam_free": (None, [C.c_void_p]),

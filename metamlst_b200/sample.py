@@ -422,7 +422,7 @@ class SampleTyper:
 
 
 def type_cohort(bam_paths: Sequence[str], db_path: str, out_dir: str, devices: Sequence[int] = (0,), prefetch: int = 2,
-                typers: Optional[Dict[int, "SampleTyper"]] = None, **params) -> List[SampleResult]:
+                typers: Optional[Dict[int, "SampleTyper"]] = None, loaders: int = 2, **params) -> List[SampleResult]:
     """Type a cohort back to back (BASELINE.json configs[3]): per device one worker thread owning a SampleTyper (one DB
     connection, one set of device tables for the whole cohort); a loader thread per device runs `prefetch` samples ahead (host
     unpack, or with ingest="device" just the file read into page-locked memory).  Samples are dealt round-robin to the devices;
@@ -447,10 +447,19 @@ def type_cohort(bam_paths: Sequence[str], db_path: str, out_dir: str, devices: S
                     pass
             return False
 
+        todo: "queue.Queue" = queue.Queue()
+        for i in mine:
+            todo.put(i)
+        n_load = max(1, min(int(loaders), len(mine)))
+
         def unpacker():
-            for i in mine:
-                if stop.is_set():
-                    return
+            # `loaders` threads per device pull the next sample of this device: reading a file into page-locked memory (or unpacking it
+            # on the host) takes longer than typing it on the GPU, one thread would be the bottleneck
+            while not stop.is_set():
+                try:
+                    i = todo.get_nowait()
+                except queue.Empty:
+                    break
                 try:
                     t0 = time.perf_counter()
                     soa = typer.load(bam_paths[i])
@@ -461,13 +470,18 @@ def type_cohort(bam_paths: Sequence[str], db_path: str, out_dir: str, devices: S
                     return
             put(None)
 
-        th = threading.Thread(target=unpacker, daemon=True)
-        th.start()
+        ths = [threading.Thread(target=unpacker, daemon=True) for _ in range(n_load)]
+        for th in ths:
+            th.start()
+        finished = 0
         try:
             while True:
                 item = q.get()
                 if item is None:
-                    break
+                    finished += 1
+                    if finished == n_load:
+                        break
+                    continue
                 i, soa, t_unpack, err = item
                 if err is not None:
                     raise err
@@ -491,7 +505,8 @@ def type_cohort(bam_paths: Sequence[str], db_path: str, out_dir: str, devices: S
                     q.get_nowait()
                 except queue.Empty:
                     break
-            th.join(timeout=5)
+            for th in ths:
+                th.join(timeout=5)
             if typers is None:
                 typer.close()
 
