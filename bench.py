@@ -916,6 +916,63 @@ def extra_hamming(device, peak, n_rows=1_000_000, n_q=10_000, world=1, rank=0):
                      "effective_GBps_labelled_effective": pairs * S / ms / 1e6,
                      "mean_min_dist": float((res[found] >> np.uint64(32)).astype(np.float64).mean()),
                      "checksum_best": int(np.bitwise_xor.reduce(res[found] * np.uint64(0x9E3779B97F4A7C15))) if found.any() else 0}
+        if name == "all_pairs":
+            # the same sweep on the tensor cores (csrc/hamming_tc.cu): DB rows expanded ONCE into the e4m3 tile image (resident, like the
+            # planes), queries expanded inside the timed region; best[] must be bit-identical to the POPC kernel's
+            dimg = torch.empty(int(lib.mmlst_hamming_tc_image_bytes(n_loc, W, 256)), dtype=torch.uint8, device=device)
+            dmax = torch.zeros((n_loc + 255) // 256, dtype=torch.int32, device=device)
+            qimg = torch.empty(int(lib.mmlst_hamming_tc_image_bytes(n_q, W, 128)), dtype=torch.uint8, device=device)
+            qmax = torch.zeros((n_q + 127) // 128, dtype=torch.int32, device=device)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            native.check(lib.mmlst_hamming_tc_expand_dev(native.ptr(db_hi), native.ptr(db_lo), native.ptr(row_len), n_loc, W, 1, 256, native.ptr(dimg), native.ptr(dmax), stream))
+            f1.record()
+            best_tc = torch.empty(n_q, dtype=torch.int64, device=device)
+
+            def run_tc():
+                best_tc.fill_(-1)
+                native.check(lib.mmlst_hamming_tc_expand_dev(native.ptr(q_hi), native.ptr(q_lo), native.ptr(q_len), n_q, W, 0, 128, native.ptr(qimg), native.ptr(qmax), stream))
+                native.check(lib.mmlst_hamming_tc_search_dev(native.ptr(qimg), native.ptr(qmax), native.ptr(q_len), n_q, native.ptr(dimg), native.ptr(dmax),
+                                                             native.ptr(row_len), n_loc, W, sh0, native.ptr(best_tc), stream))
+                if world > 1:
+                    dist.allreduce_best(best_tc)
+            run_tc(); run_tc()
+            if world > 1:
+                torch.distributed.barrier()
+            torch.cuda.synchronize()
+            assert torch.equal(best_tc, best), "tensor-core sweep differs from the POPC kernel"
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(3):
+                run_tc()
+            g1.record()
+            torch.cuda.synchronize()
+            tms = g0.elapsed_time(g1) / 3
+            if world > 1:
+                tm = torch.tensor([tms], dtype=torch.float64, device=device)
+                torch.distributed.all_reduce(tm, op=torch.distributed.ReduceOp.MAX)
+                tms = float(tm.item())
+            # flops the kernel really issues: per (query tile, row tile) pair 2 * 128 * 256 * 128 per K-block, K-blocks = 3 planes x the 128-base
+            # blocks the pair can reach (min of the two tiles' longest clean sequences)
+            qm, dm = qmax.cpu().numpy().astype(np.int64), dmax.cpu().numpy().astype(np.int64)
+            kb_pairs = 3.0 * float(np.ceil(np.minimum.outer(qm, dm) / 128.0).clip(max=W // 4).sum())
+            flops = 2.0 * 128 * 256 * 128 * kb_pairs
+            bf16_peak = 1613.0
+            try:
+                bf16_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+            except Exception:  # noqa: BLE001
+                pass
+            out["all_pairs_tensor_core"] = {"ms": tms, "pairs": pairs, "pairs_per_s": pairs / (tms / 1e3), "speedup_vs_popc_kernel": ms / tms,
+                                            "identical_best": True, "checksum_best": out[name]["checksum_best"],
+                                            "issued_flops": flops, "dense_flops_full_K": 2.0 * pairs * 3 * 32 * W, "TFLOPs": flops / (tms / 1e3) / 1e12,
+                                            "roofline": {"bound": "tensor", "achieved": flops / (tms / 1e3) / 1e12, "peak": 2 * bf16_peak, "unit": "TFLOP/s",
+                                                         "frac": flops / (tms / 1e3) / 1e12 / (2 * bf16_peak), "traffic": None,
+                                                         "peak_source": "2 x the measured dense bf16 rate of MEASURED_PEAKS.json (8-bit operands run at twice the 16-bit rate)"},
+                                            "db_image_bytes": int(dimg.numel()), "db_expand_ms_once": f0.elapsed_time(f1), "query_image_bytes": int(qimg.numel()),
+                                            "how": "tcgen05.mma cta_group::1 kind::f8f6f4 (e4m3 signs, FP32 accumulate in TMEM), M=128 N=256 K=32, TMA bulk copies into a "
+                                                   "4-stage ring, persistent CTA per SM; query expansion inside the timed region, DB image resident; K loop stops at the "
+                                                   "last 128-base block a tile pair can reach"}
+            del dimg, qimg
         if world > 1:
             out[name]["n_gpus"] = world
             out[name]["scaling"] = "strong (rows sharded, queries replicated, all-reduce MIN of best[] inside the timed region)"

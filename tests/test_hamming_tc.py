@@ -41,7 +41,7 @@ def _tc_search(q_hi, q_lo, q_len, d_hi_t, d_lo_t, d_len, n_q, n_rows, W, base=0)
     return best.cpu().numpy().view(np.uint64), want.cpu().numpy().view(np.uint64)
 
 
-@pytest.mark.parametrize("n_rows,n_q,W,seed", [(700, 150, 8, 1), (5000, 300, 24, 2), (256, 128, 4, 3), (1025, 129, 16, 4), (40, 3, 24, 5)])
+@pytest.mark.parametrize("n_rows,n_q,W,seed", [(700, 150, 8, 1), (5000, 300, 24, 2), (256, 128, 8, 3), (1025, 129, 16, 4), (40, 3, 24, 5)])
 def test_tensor_core_sweep_equals_the_popc_kernel_and_the_oracle(n_rows, n_q, W, seed):
     rng = np.random.default_rng(seed)
     L = 32 * W
