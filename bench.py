@@ -659,6 +659,10 @@ def main():
         if args.ingest_reads:
             line["ingest"] = extra_ingest(db, args, device)
     if rank == 0:
+        hs = line.get("hamming_sharded") or line.get("hamming")
+        if hs:  # LAST key of the line on purpose: the driver keeps the tail of the output
+            line["hamming_scaling"] = {"n": world, "all_pairs_ms": hs["all_pairs"]["ms"], "all_pairs_tensor_core_ms": hs.get("all_pairs_tensor_core", {}).get("ms"),
+                                       "locus_restricted_ms": hs["locus_restricted"]["ms"], "matvec_ms": hs["matvec_one_query_per_locus"]["ms"]}
         emit(line)
     if world > 1:
         # no destroy_process_group(): tearing a communicator down while CUDA graphs that captured its kernels are alive
@@ -829,10 +833,11 @@ def extra_hamming(device, peak, n_rows=1_000_000, n_q=10_000, world=1, rank=0):
         p = torch.zeros((nt * 32, W), dtype=torch.int32, device=device)
         p[:x.shape[0]] = x
         return p.view(nt, 32, W).transpose(1, 2).contiguous().view(-1)
-    sh0, sh1 = dist.shard_rows(n_rows, world, rank) if world > 1 else (0, n_rows)
-    n_loc = sh1 - sh0
-    db_hi, db_lo = tile(hi[sh0:sh1]), tile(lo[sh0:sh1])
-    row_len = lens[sh0:sh1].to(torch.int16).contiguous()
+    shard = dist.shard_rows(n_rows, world, rank) if world > 1 else (0, n_rows)
+    # N > 1: the all-pairs sweep (milliseconds) is sharded by DB rows and its best[] all-reduced with MIN (strong scaling); the two searches that
+    # take tens of microseconds on ONE GPU are left whole on every rank (replicas): a collective costs more than the kernel (r1: 42 -> 73 us at N=8)
+    db_sharded = (tile(hi[shard[0]:shard[1]]), tile(lo[shard[0]:shard[1]]), lens[shard[0]:shard[1]].to(torch.int16).contiguous())
+    db_whole = db_sharded if world == 1 else (tile(hi), tile(lo), lens.to(torch.int16).contiguous())
     best = torch.empty(n_q, dtype=torch.int64, device=device)
     lib = native.lib()
     stream = torch.cuda.current_stream().cuda_stream
@@ -870,6 +875,9 @@ def extra_hamming(device, peak, n_rows=1_000_000, n_q=10_000, world=1, rank=0):
         return tot
 
     for name, (blk, mr, mq) in modes.items():
+        sharded = world > 1 and name == "all_pairs"
+        (sh0, sh1), (db_hi, db_lo, row_len) = (shard, db_sharded) if sharded else ((0, n_rows), db_whole)
+        n_loc = sh1 - sh0
         # this rank's part of every block: rows clipped to [sh0, sh1) and rebased; blocks without local rows are dropped
         loc = blk.astype(np.int64).copy()
         loc[:, 2] = np.clip(loc[:, 2], sh0, sh1) - sh0
@@ -883,7 +891,7 @@ def extra_hamming(device, peak, n_rows=1_000_000, n_q=10_000, world=1, rank=0):
             best.fill_(-1)
             native.check(lib.mmlst_hamming_min_dev2(native.ptr(db_hi), native.ptr(db_lo), native.ptr(row_len), n_loc, W, native.ptr(q_hi), native.ptr(q_lo),
                                                     native.ptr(q_len), n_q, native.ptr(blk_d), int(loc.shape[0]), max(mr, 1), int(mq), sh0, native.ptr(best), stream))
-            if world > 1:
+            if sharded:
                 dist.allreduce_best(best)
         run(); run()
         if world > 1:
@@ -934,7 +942,7 @@ def extra_hamming(device, peak, n_rows=1_000_000, n_q=10_000, world=1, rank=0):
                 native.check(lib.mmlst_hamming_tc_expand_dev(native.ptr(q_hi), native.ptr(q_lo), native.ptr(q_len), n_q, W, 0, 128, native.ptr(qimg), native.ptr(qmax), stream))
                 native.check(lib.mmlst_hamming_tc_search_dev(native.ptr(qimg), native.ptr(qmax), native.ptr(q_len), n_q, native.ptr(dimg), native.ptr(dmax),
                                                              native.ptr(row_len), n_loc, W, sh0, native.ptr(best_tc), stream))
-                if world > 1:
+                if sharded:
                     dist.allreduce_best(best_tc)
             run_tc(); run_tc()
             if world > 1:
@@ -975,7 +983,8 @@ def extra_hamming(device, peak, n_rows=1_000_000, n_q=10_000, world=1, rank=0):
             del dimg, qimg
         if world > 1:
             out[name]["n_gpus"] = world
-            out[name]["scaling"] = "strong (rows sharded, queries replicated, all-reduce MIN of best[] inside the timed region)"
+            out[name]["scaling"] = ("strong (rows sharded, queries replicated, all-reduce MIN of best[] inside the timed region)" if sharded else
+                                    "replicas (every rank searches the whole DB: the kernel is shorter than a collective)")
     return out
 
 

@@ -232,6 +232,11 @@ int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, cons
                      uint32_t* header, uint32_t* chosen_tid, uint32_t* chosen_species, uint32_t* col_off, uint64_t* db_start,
                      mmlst_chunk* chunks, uint32_t max_chunks, uint32_t flags, uint64_t* counters,
                      uint32_t* chosen_first /* [n_loci] first passing record per chosen locus, or NULL */, void* stream);
+/* The device-driven kernels of a pass (mmlst_select_dev, mmlst_pileup_indirect_dev, mmlst_consensus_indirect_dev) are launched with programmatic
+ * stream serialization: each becomes resident while its predecessor still runs and waits (griddepcontrol.wait) for it to complete before touching
+ * its data, which takes the launch latency of three dependent links off a pass.  1 = on (default), 0 = off, other = query; returns the previous value.
+ * MMLST_PDL=0 presets it.  Results do not depend on it. */
+int mmlst_set_pdl(int on);
 int mmlst_pileup_indirect_dev(const mmlst_prec* recs, const uint32_t* planes, const mmlst_chunk* chunks, const uint32_t* header,
                               uint32_t max_row_words, int minscore, int max_xm, uint32_t* counts, int impl, void* stream);
 /* flags: MMLST_CONSENSUS_CONSUME = zero every count that was read (the next pass accumulates from zero, no memset) */

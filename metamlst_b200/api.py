@@ -19,6 +19,15 @@ import numpy as np
 from . import native, packing
 
 NO_IDX = 0xFFFFFFFF
+XM_SATURATION = 255  # the packed XM fields are 8 bits and saturate here: a threshold at or above it could let a larger XM through
+
+
+def check_max_xm(max_xM: int) -> int:
+    """--max_xM against the 8-bit XM fields of the streams: up to 254 is exact; anything above is refused, never silently different
+    (the lower-level pileup_consensus takes 255 as "no XM filter at all", which is exact too: cmseq with BAM_tagFilter=None)."""
+    if int(max_xM) >= XM_SATURATION:
+        raise ValueError("max_xM must be at most %d (XM is carried as 8 bits, saturated at %d)" % (XM_SATURATION - 1, XM_SATURATION))
+    return int(max_xM)
 
 
 class AlleleIndex:
@@ -85,6 +94,7 @@ def score_soa_raw(ctx: native.Context, soa: packing.SoaHost, index: AlleleIndex,
                   min_read_len: int = 50, species_filter: Optional[str] = None):
     """Seam S1, integer half: (sum_as, n_hit, first_idx, totalReads, ignoredReads) straight from mmlst_score."""
     n_ref = len(index.ref_names)
+    check_max_xm(max_xM)
     allow = index.allow_mask(species_filter)
     sum_as = np.zeros(n_ref, np.int64)
     n_hit = np.zeros(n_ref, np.uint32)
@@ -180,6 +190,7 @@ def build_consensus(ctx: native.Context, soa: packing.SoaHost, chromosomeList: D
     its unpacked SoaHost (consensus rule hard-wired upstream: dominant 0.4 (output-dead), mincov 1, minqual 20)."""
     if soa.minqual != 20:
         raise ValueError("buildConsensus needs a stream unpacked with minqual=20 (metaMLST_functions.py:258)")
+    check_max_xm(max_xM)
     name2tid = {n: i for i, n in enumerate(soa.ref_names)}
     contigs = list(chromosomeList.keys())
     for c in contigs:

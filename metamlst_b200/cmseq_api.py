@@ -187,21 +187,16 @@ class BamContig:
         not count; no tag filter."""
         if mincov < 1:
             raise ValueError("mincov must be >= 1")
-        if self.length > trunc * 2:
-            consid_r = range(int(trunc), int(self.length - trunc))
-        else:
-            consid_r = range(0, int(self.length))
+        # window of the contig that counts: `trunc` columns dropped at both ends when the contig is long enough for that
+        lo, hi = (int(trunc), int(self.length - trunc)) if self.length > trunc * 2 else (0, int(self.length))
         counts = self._counts(max(PYSAM_DEFAULT_MIN_BASE_QUALITY, int(minqual)))
-        depth = counts[:, :4].astype(np.int64).sum(axis=1)
-        coverage_positions = {}
-        for pos in range(consid_r.start, consid_r.stop):
-            if depth[pos] >= mincov:
-                coverage_positions[pos] = int(depth[pos])
-        if len(coverage_positions) > 0:
-            breadth = float(len(coverage_positions.keys())) / len(consid_r)
-            vals = list(coverage_positions.values())
-            return (breadth, np.mean(vals), np.median(vals), coverage_positions.values())
-        return (np.nan, np.nan, np.nan, [np.nan])
+        window = counts[lo:hi, :4].astype(np.int64).sum(axis=1)
+        hit = np.nonzero(window >= mincov)[0]
+        if hit.size == 0:
+            return (np.nan, np.nan, np.nan, [np.nan])
+        depth_at = dict(zip((hit + lo).tolist(), window[hit].tolist()))   # {0-based column: depth}, ascending like upstream's dict
+        vals = list(depth_at.values())
+        return (float(hit.size) / (hi - lo), np.mean(vals), np.median(vals), depth_at.values())
 
     def depth_of_coverage(self, mincov=10, minqual=30):
         return self.breadth_and_depth_of_coverage(mincov, minqual)[1]
@@ -213,6 +208,20 @@ class BamContig:
         """cmseq/cmseq.py:572-578."""
         base_stats = self.get_base_stats(*f_args, **f_kwargs)
         return [base_stats[k].get(stats_value, 'NaN') for k in base_stats]
+
+
+def _wanted_contigs(spec):
+    """cmseq/cmseq.py:58-66: `filterInputList` is a list of contig names, the path of a FASTA file (its record ids: first word of every
+    '>' line), or a comma-separated string.  None = no filter."""
+    if spec is None:
+        return None
+    if isinstance(spec, list):
+        return set(spec)
+    if os.path.isfile(spec):
+        with open(spec, "r") as fh:
+            heads = (ln[1:].split() for ln in fh if ln.startswith(">"))
+            return {h[0] if h else "" for h in heads}
+    return set(spec.split(","))
 
 
 class BamFile:
@@ -235,19 +244,7 @@ class BamFile:
         self.references = tuple(first.ref_names)
         self.lengths = tuple(int(x) for x in first.ref_lens)
         self._tid = {r: i for i, r in enumerate(self.references)}
-        toList = None
-        if filterInputList is not None:
-            if isinstance(filterInputList, list):
-                toList = filterInputList
-            elif os.path.isfile(filterInputList):
-                toList = []
-                with open(filterInputList, "r") as infile:  # ids of a FASTA file: first word after '>'
-                    for line in infile:
-                        if line.startswith(">"):
-                            toList.append(line[1:].split()[0] if line[1:].split() else "")
-            else:
-                toList = [element for element in filterInputList.split(',')]
-        keep = set(toList) if toList is not None else None  # upstream scans the list per reference (O(n_ref x n)), same result
+        keep = _wanted_contigs(filterInputList)  # upstream scans a list per reference (O(n_ref x n)); a set gives the same answer
         n_on = np.bincount(np.asarray(first.tid, dtype=np.int64), minlength=len(self.references)) if minimumReadsAligning else None
         self.contigs = dict((r, BamContig(self, r, l, stepper)) for i, (r, l) in enumerate(zip(self.references, self.lengths))
                             if l > minlen and (keep is None or r in keep) and (not minimumReadsAligning or int(n_on[i]) >= minimumReadsAligning))

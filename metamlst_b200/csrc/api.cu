@@ -33,6 +33,13 @@ int mmlst_num_sms() {
     return n;
 }
 
+static int g_pdl = -1;
+int mmlst_pdl_enabled() {
+    if (g_pdl < 0) { const char* e = getenv("MMLST_PDL"); g_pdl = (e && e[0] == '0') ? 0 : 1; }
+    return g_pdl;
+}
+extern "C" int mmlst_set_pdl(int on) { const int prev = mmlst_pdl_enabled(); if (on == 0 || on == 1) g_pdl = on; return prev; }
+
 extern "C" const char* mmlst_last_error(void) { return g_err; }
 extern "C" int mmlst_version(void) { return MMLST_VERSION; }
 extern "C" int mmlst_device_count(void) {

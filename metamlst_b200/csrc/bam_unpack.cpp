@@ -331,6 +331,7 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
             if (rl > 65535) { err.set(MMLST_E_RANGE, "%s: record %zu spans %llu reference bases (> 65535)", path, i, (unsigned long long)rl); return; }
             if (n_cig && l_seq && qlsum != l_seq) { err.set(MMLST_E_BAM, "%s: record %zu: CIGAR query length %llu != l_seq %u", path, i, (unsigned long long)qlsum, l_seq); return; }
             c.reflen = (uint32_t)rl;
+            if (l_seq > 65535u) { err.set(MMLST_E_RANGE, "%s: record %zu: read of %u bases (len(SEQ) is carried as 16 bits)", path, i, l_seq); return; }
             const uint32_t ql = l_seq ? l_seq : 1u;  // SAM prints SEQ '*' when l_seq == 0: len() == 1 (metamlst.py:111,115)
             c.qlen = (uint16_t)std::min<uint32_t>(ql, 65535u);
             // aux walk: 1st and 4th field by POSITION (metamlst.py:109-110), AS / XM by NAME (cmseq/cmseq.py:545)

@@ -143,4 +143,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
                      : "memory");
     } while (!done);
 }
+// ---- programmatic dependent launch (PDL): the kernels of one pass form a chain (score -> select -> pileup -> consensus) whose links are short;
+// a dependent kernel launched with the programmatic-serialization attribute becomes resident as soon as every CTA of its predecessor has
+// called pdl_launch_dependents() and then blocks in pdl_wait() until the predecessor has COMPLETED (memory visible): the launch latency and
+// the ramp of each link run under the previous kernel.  Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+int mmlst_pdl_enabled();
+
+template <class... KArgs, class... Args>
+inline cudaError_t mmlst_launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = mmlst_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#else
+inline void pdl_wait() {}
+inline void pdl_launch_dependents() {}
 #endif  // MMLST_HOST_EMUL

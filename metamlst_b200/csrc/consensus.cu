@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(CONS_THREADS) consensus_kernel(uint32_t* __res
                                                         uint32_t mincov, uint8_t* __restrict__ cons,
                                                         uint32_t* __restrict__ holes, uint32_t* __restrict__ snps) {
     const uint32_t locus = blockIdx.x;
+    pdl_wait();                  // counts (pileup) and the selection header are complete and visible
     if (n_loci_dev && locus >= *n_loci_dev) return;
     const uint32_t c0 = col_off[locus], c1 = col_off[locus + 1];
     // DB sequence of the chosen allele: either pre-concatenated (column-aligned) or addressed through db_start[locus]
@@ -66,8 +67,7 @@ extern "C" int mmlst_consensus_indirect_dev(uint32_t* counts, const uint8_t* db_
     if (!counts || !db_ascii || !db_start || !col_off || !header || !cons || !holes || !snps) { mmlst_set_error("mmlst_consensus_indirect_dev: null pointer"); return MMLST_E_ARG; }
     const unsigned long long* dbs = reinterpret_cast<const unsigned long long*>(db_start);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (flags & MMLST_CONSENSUS_CONSUME) consensus_kernel<true><<<max_loci, CONS_THREADS, 0, s>>>(counts, db_ascii, dbs, col_off, header, mincov, cons, holes, snps);
-    else consensus_kernel<false><<<max_loci, CONS_THREADS, 0, s>>>(counts, db_ascii, dbs, col_off, header, mincov, cons, holes, snps);
-    CUDA_TRY(cudaGetLastError());
+    if (flags & MMLST_CONSENSUS_CONSUME) CUDA_TRY(mmlst_launch_dependent(consensus_kernel<true>, dim3(max_loci), dim3(CONS_THREADS), 0, s, counts, db_ascii, dbs, col_off, header, mincov, cons, holes, snps));
+    else CUDA_TRY(mmlst_launch_dependent(consensus_kernel<false>, dim3(max_loci), dim3(CONS_THREADS), 0, s, counts, db_ascii, dbs, col_off, header, mincov, cons, holes, snps));
     return MMLST_OK;
 }

@@ -172,6 +172,37 @@ __global__ void __launch_bounds__(kRowsPerCta, 5) hamming_min_kernel(const HamAr
     }
 }
 
+// Any plane width (rows longer than 1024 bases, or widths the tiled kernel has no instance for): thread = DB row, queries of the
+// block in turn, word by word from global memory.  Same best[] contract; an order of magnitude slower -- MLST loci are 400-550 bp, this
+// is here so that no input is refused.
+__global__ void __launch_bounds__(kRowsPerCta) hamming_min_wide_kernel(const HamArgs a, uint32_t W) {
+    const uint32_t* blk = a.blocks + 4 * blockIdx.y;
+    const uint32_t q_begin = blk[0], q_end = blk[1], r_begin = blk[2], r_end = blk[3];
+    const uint32_t row = r_begin + blockIdx.x * kRowsPerCta + threadIdx.x;
+    const bool live = row < r_end && row < a.n_rows;
+    const uint32_t rl_raw = live ? a.row_len[row] : 0x8000u;
+    const size_t tb = static_cast<size_t>(row >> 5) * W * 32 + (row & 31u);
+    for (uint32_t q = q_begin; q < q_end; ++q) {
+        const uint32_t ql_raw = a.q_len[q];
+        unsigned long long key = ~0ull;
+        if (live && !(rl_raw & 0x8000u) && !(ql_raw & 0x8000u)) {
+            const uint32_t m = min(rl_raw, ql_raw);
+            uint32_t d = 0;
+            for (uint32_t w = 0; 32 * w < m; ++w) {
+                uint32_t x = (a.db_hi[tb + static_cast<size_t>(w) * 32] ^ a.q_hi[static_cast<size_t>(q) * W + w]) |
+                             (a.db_lo[tb + static_cast<size_t>(w) * 32] ^ a.q_lo[static_cast<size_t>(q) * W + w]);
+                const uint32_t left = m - 32 * w;
+                if (left < 32) x &= (1u << left) - 1u;
+                d += __popc(x);
+            }
+            key = (static_cast<unsigned long long>(d) << 32) | (row + a.row_index_base);
+        }
+        // warp minimum, one atomic per (warp, query)
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, key, o); key = x < key ? x : key; }
+        if ((threadIdx.x & 31) == 0 && key != ~0ull) atomicMin(a.best + q, key);
+    }
+}
+
 template <int W>
 int launch(const HamArgs& a, uint32_t max_rows, uint32_t max_q, cudaStream_t s) {
     dim3 grid((max_rows + kRowsPerCta - 1) / kRowsPerCta, a.n_blocks, (max_q + kQSplit - 1) / kQSplit);
@@ -196,18 +227,26 @@ extern "C" int mmlst_hamming_min_dev2(const uint32_t* db_hi, const uint32_t* db_
         mmlst_set_error("mmlst_hamming_min_dev: query planes must be 16-byte aligned");
         return MMLST_E_ARG;
     }
-    if (n_blocks > 65535) { mmlst_set_error("mmlst_hamming_min_dev: more than 65535 blocks per launch"); return MMLST_E_ARG; }
-    HamArgs a{db_hi, db_lo, row_len, n_rows, q_hi, q_lo, q_len, n_q, blocks, n_blocks, row_index_base, best};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    switch (W) {
-        case 8: return launch<8>(a, max_block_rows, max_block_queries, s);
-        case 16: return launch<16>(a, max_block_rows, max_block_queries, s);
-        case 24: return launch<24>(a, max_block_rows, max_block_queries, s);
-        case 32: return launch<32>(a, max_block_rows, max_block_queries, s);
-        default:
-            mmlst_set_error("mmlst_hamming_min_dev: W=%u unsupported (8, 16, 24 or 32 words per plane; rows up to 1024 bases)", W);
-            return MMLST_E_ARG;
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += 65535u) {   // gridDim.y holds 65535 blocks: more go out in slices
+        const uint32_t nb = n_blocks - b0 < 65535u ? n_blocks - b0 : 65535u;
+        HamArgs a{db_hi, db_lo, row_len, n_rows, q_hi, q_lo, q_len, n_q, blocks + 4 * static_cast<size_t>(b0), nb, row_index_base, best};
+        int rc;
+        switch (W) {
+            case 8: rc = launch<8>(a, max_block_rows, max_block_queries, s); break;
+            case 16: rc = launch<16>(a, max_block_rows, max_block_queries, s); break;
+            case 24: rc = launch<24>(a, max_block_rows, max_block_queries, s); break;
+            case 32: rc = launch<32>(a, max_block_rows, max_block_queries, s); break;
+            default: {
+                if (W == 0) { mmlst_set_error("mmlst_hamming_min_dev: W = 0"); return MMLST_E_ARG; }
+                const uint32_t mr = max_block_rows ? max_block_rows : n_rows;
+                hamming_min_wide_kernel<<<dim3((mr + kRowsPerCta - 1) / kRowsPerCta, nb), kRowsPerCta, 0, s>>>(a, W);
+                rc = mmlst_cuda_fail(cudaGetLastError(), "hamming_min_wide_kernel");
+            }
+        }
+        if (rc != MMLST_OK) return rc;
     }
+    return MMLST_OK;
 }
 
 extern "C" int mmlst_hamming_min_dev(const uint32_t* db_hi, const uint32_t* db_lo, const uint16_t* row_len, uint32_t n_rows,

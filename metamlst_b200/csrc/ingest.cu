@@ -437,13 +437,14 @@ const char* err_text(uint32_t code) {
         case E_XM3: return "negative 4th aux field";
         case E_NAMED: return "record enters the pileup without integer AS:i / XM:i tags (pysam get_tag KeyError, cmseq/cmseq.py:545)";
         case E_NOQUAL: return "record has no base qualities: query_qualities is None (TypeError at cmseq/cmseq.py:538)";
+        case E_QLEN: return "read longer than 65535 bases (len(SEQ) is carried as 16 bits)";
         default: return "hardware decompression produced a block of the wrong size / record chain broken";
     }
 }
 int err_class(uint32_t code) {
     switch (code) {
         case E_PAIRED: return MMLST_E_PAIRED;
-        case E_REFSPAN: case E_AS0: case E_XM3: return MMLST_E_RANGE;
+        case E_REFSPAN: case E_AS0: case E_XM3: case E_QLEN: return MMLST_E_RANGE;
         default: return MMLST_E_BAM;
     }
 }

@@ -32,7 +32,8 @@ enum Err : uint32_t {
     E_XM3 = 11,         // negative 4th aux field
     E_NAMED = 12,       // record enters the pileup without integer AS:i / XM:i (cmseq/cmseq.py:545)
     E_NOQUAL = 13,      // record enters the pileup without base qualities (cmseq/cmseq.py:538)
-    E_CHAIN = 14        // record chain could not be established (internal)
+    E_CHAIN = 14,       // record chain could not be established (internal)
+    E_QLEN = 15         // read longer than 65535 bases (len(SEQ) is carried as 16 bits)
 };
 
 ING_HD uint32_t rd16(const uint8_t* p) { return static_cast<uint32_t>(p[0]) | (static_cast<uint32_t>(p[1]) << 8); }
@@ -159,6 +160,7 @@ ING_HD uint32_t parse_record(const uint8_t* u, uint64_t off, int32_t n_ref, Core
     Core c;
     c.key = (static_cast<uint64_t>(static_cast<uint32_t>(tid)) << 33) | ((static_cast<uint64_t>(static_cast<uint32_t>(pos)) + 1ull) << 1) | ((flag >> 4) & 1u);
     c.reflen = static_cast<uint32_t>(rl);
+    if (l_seq > 65535u) return E_QLEN;
     const uint32_t ql = l_seq ? l_seq : 1u;  // SAM prints SEQ '*' when l_seq == 0: len() == 1 (metamlst.py:111,115)
     c.qlen = static_cast<uint16_t>(ql < 65535u ? ql : 65535u);
     int field = 0;

@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
         fence_mbar_init();
     }
     __syncthreads();
+    pdl_wait();                 // barriers are set up; now the predecessor (selection: chunk list, header) must be complete and visible
+    pdl_launch_dependents();    // the consensus CTAs may become resident; they wait for this grid before reading the counts
     uint32_t phase_bits = 0;  // parity per stage
     const int max_nw = int(a.max_row_words / 3u);  // upper bound of the contig words any record touches
 
@@ -294,6 +296,8 @@ int launch_pileup_bitsliced(const PileupArgs& a, cudaStream_t stream) {
     }
     const int per_sm = smem <= 113 * 1024 ? int(MMLST_CHUNKS_PER_SM) : 1;  // 227 KB per SM, 1 KB reserved per CTA
     const uint32_t grid = a.n_chunks_dev ? uint32_t(sms * per_sm) : min(a.n_chunks, uint32_t(sms * per_sm));
+    // a device-driven launch (chunk list written by the selection kernel just before) is a link of the pass's chain: programmatic dependent launch
+    if (a.n_chunks_dev) return mmlst_cuda_fail(mmlst_launch_dependent(pileup_bitsliced_kernel<2>, dim3(grid), dim3(NTHREADS), smem, stream, a, stage_words), "pileup_bitsliced_kernel");
     pileup_bitsliced_kernel<2><<<grid, NTHREADS, smem, stream>>>(a, stage_words);
     return mmlst_cuda_fail(cudaGetLastError(), "pileup_bitsliced_kernel");
 }

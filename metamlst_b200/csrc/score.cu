@@ -30,6 +30,7 @@ __device__ __forceinline__ void flush_run(const ScoreArgs& a, uint32_t key, long
 // R = 8 records per lane: 2 x LDG.128 (tid) + LDG.128 (as0) + LDG.64 (xm3) + LDG.128 (qlen) in flight per lane,
 // 256-record warp chunks.
 __global__ void __launch_bounds__(kThreads) score_kernel(const ScoreArgs a) {
+    pdl_launch_dependents();
     constexpr int R = 8;
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;

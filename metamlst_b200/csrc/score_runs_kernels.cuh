@@ -220,6 +220,7 @@ __device__ __forceinline__ void score_tail(const RunArgs& a, uint64_t nchunks, u
 
 template <bool OIDX, bool PIPE, bool QC>
 __global__ void __launch_bounds__(kThreads, PIPE ? (OIDX ? 2 : 3) : (OIDX ? 3 : 4)) score_runs_kernel(const RunArgs a) {
+    pdl_launch_dependents();  // the selection kernel may take its (few) CTAs now; it waits for this grid to finish before it reads the tables
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -400,6 +401,7 @@ __device__ __forceinline__ void reduce_chunk_pf(const RunArgs& a, const Thr& thr
 // CH chunks per stage, NS stages per warp, MINB resident CTAs per SM the register budget is set for
 template <bool QC, int NS, int CH, int MINB, bool HINT>
 __global__ void __launch_bounds__(kThreads, MINB) score_runs_ring_kernel(const RunArgs a) {
+    pdl_launch_dependents();  // the selection kernel may take its (few) CTAs now; it waits for this grid to finish before it reads the tables
     extern __shared__ __align__(128) uint8_t ring_raw[];
     constexpr uint32_t AS_B = CH * 512u, QL_B = QC ? 0u : CH * 512u, XM_B = CH * 256u;
     constexpr uint32_t STAGE_B = AS_B + QL_B + XM_B;
@@ -524,6 +526,7 @@ __device__ __forceinline__ void reduce_pair_pf(const RunArgs& a, const Thr& thr,
 }
 
 __global__ void __launch_bounds__(kThreads, 4) score_runs_ring_pair_kernel(const RunArgs a) {
+    pdl_launch_dependents();  // the selection kernel may take its (few) CTAs now; it waits for this grid to finish before it reads the tables
     extern __shared__ __align__(128) uint8_t ring_raw[];
     constexpr int NS = 2;
     constexpr uint32_t CH = 4, AS_B = CH * 512u, XM_B = CH * 256u, STAGE_B = AS_B + XM_B, CH_B = STAGE_B / CH;

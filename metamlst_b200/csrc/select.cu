@@ -103,7 +103,9 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
     __shared__ uint32_t sh32[SEL_THREADS / 32];
     __shared__ uint32_t s_last;
     const uint32_t l = blockIdx.x;
-    const uint32_t r0 = a.locus_start[l], r1 = a.locus_start[l + 1];
+    const uint32_t r0 = a.locus_start[l], r1 = a.locus_start[l + 1];   // constant table: may be read before the predecessor is done
+    pdl_wait();                  // the score tables are complete and visible
+    pdl_launch_dependents();     // the pileup CTAs may become resident (they wait for THIS grid before reading the chunk list)
     // The first SEL_R x 256 rows of the locus live in registers: ONE round of independent loads (row id, then hit count /
     // score sum / first index / allele number together), after which the three passes are register arithmetic.  Loci
     // with more rows run the same passes over the remainder from global memory.
@@ -353,7 +355,6 @@ extern "C" int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* firs
         CUDA_TRY(cudaFuncSetAttribute(sel_locus, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         configured = smem;
     }
-    sel_locus<<<n_loci, SEL_THREADS, smem, s>>>(a);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(mmlst_launch_dependent(sel_locus, dim3(n_loci), dim3(SEL_THREADS), smem, s, a));
     return MMLST_OK;
 }

@@ -311,7 +311,9 @@ def _w_for(max_len: int) -> int:
     for cand in (8, 16, 24, 32):
         if w <= cand:
             return cand
-    raise native.MmlstError(-7, "sequence of %d bases exceeds 1024 (W > 32 words per plane)" % max_len)
+    if max_len < 0x8000:  # lengths are 15 bits (bit 15 flags non-ACGT sequences); widths beyond 32 words take the any-width kernel
+        return (w + 7) // 8 * 8
+    raise native.MmlstError(-7, "sequence of %d bases exceeds 32767" % max_len)
 
 
 def encode_2bit_x(seqs: Sequence[bytes], W: int):

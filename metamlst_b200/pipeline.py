@@ -42,7 +42,7 @@ class DevicePipeline:
         self._use_runs_arg, self._idx_base_arg = use_runs, idx_base
         self.index = index
         self.dbseq_of = dbseq_of
-        self.minscore, self.max_xM, self.min_read_len, self.penalty = int(minscore), int(max_xM), int(min_read_len), int(penalty)
+        self.minscore, self.max_xM, self.min_read_len, self.penalty = int(minscore), api.check_max_xm(max_xM), int(min_read_len), int(penalty)
         self.mincov, self.impl = int(mincov), int(impl)
         self.idx_base = int(idx_base) if idx_base else int(getattr(streams, "idx_base", 0) or 0)
         self.group = group

@@ -94,3 +94,29 @@ def test_tensor_core_sweep_equals_the_popc_kernel_and_the_oracle(n_rows, n_q, W,
                 best = (d, r)
         assert (int(got[q] >> np.uint64(32)), int(got[q] & np.uint64(0xffffffff)) - 1000) == best, q
     assert int(got[0] >> np.uint64(32)) == 0 and int(got[0] & np.uint64(0xffffffff)) - 1000 == 2
+
+
+def test_rows_longer_than_1024_bases_take_the_any_width_kernel():
+    """W > 32 plane words (loci longer than 1024 bp) used to be refused: the any-width kernel answers them, same contract."""
+    from metamlst_b200 import api
+    rng = np.random.default_rng(9)
+    letters = np.frombuffer(b"ACGT", np.uint8)
+    base = rng.integers(0, 4, 1500)
+    rows = []
+    for r in range(300):
+        s = base.copy()
+        p = rng.choice(1500, size=int(rng.integers(0, 9)), replace=False)
+        s[p] = (s[p] + 1) % 4
+        rows.append(("sp", "g%d" % (r % 3), r + 1, letters[s[: int(rng.integers(1100, 1501))]].tobytes().decode()))
+    rows[7] = rows[7][:3] + (rows[7][3][:600] + "N" + rows[7][3][601:],)   # a flagged row on the exact path
+    ctx = native.Context(0)
+    idx = api.HammingIndex(ctx, rows)
+    assert idx.W > 32
+    qs = [rows[i][3][: 1200 + i] for i in (1, 5, 7, 100)] + [letters[base].tobytes().decode()]
+    genes = ["g1", "g2", "g1", "g1", "g0"]
+    d, a = idx.search(qs, [idx.block[("sp", g)] for g in genes])
+    flat = np.frombuffer("".join(r[3] for r in idx.rows).encode(), np.uint8)
+    off = np.zeros(len(idx.rows) + 1, np.int64); off[1:] = np.cumsum([len(r[3]) for r in idx.rows])
+    wd, wa = corc.hamming_min([q.encode() for q in qs], flat, off, [idx.block[("sp", g)] for g in genes])
+    assert d.tolist() == wd.tolist() and a.tolist() == wa.tolist()
+    ctx.close()
