@@ -234,8 +234,9 @@ int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, cons
                      uint32_t* chosen_first /* [n_loci] first passing record per chosen locus, or NULL */, void* stream);
 /* The device-driven kernels of a pass (mmlst_select_dev, mmlst_pileup_indirect_dev, mmlst_consensus_indirect_dev) are launched with programmatic
  * stream serialization: each becomes resident while its predecessor still runs and waits (griddepcontrol.wait) for it to complete before touching
- * its data, which takes the launch latency of three dependent links off a pass.  1 = on (default), 0 = off, other = query; returns the previous value.
- * MMLST_PDL=0 presets it.  Results do not depend on it. */
+ * its data.  1 = on, 0 = off (default), other = query; returns the previous value; MMLST_PDL=1 presets it.  Results do not depend on it.
+ * Measured on B200 (profiles/r2l_bench_pdl{0,1}.json): inside the CUDA-graph replay a pass is timed in, the links already follow each other within
+ * about a microsecond and PDL changes nothing (serial pass 75.4 us with, 74.8 us without), so it is off unless asked for (eager launches gain). */
 int mmlst_set_pdl(int on);
 int mmlst_pileup_indirect_dev(const mmlst_prec* recs, const uint32_t* planes, const mmlst_chunk* chunks, const uint32_t* header,
                               uint32_t max_row_words, int minscore, int max_xm, uint32_t* counts, int impl, void* stream);

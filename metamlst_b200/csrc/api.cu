@@ -35,7 +35,7 @@ int mmlst_num_sms() {
 
 static int g_pdl = -1;
 int mmlst_pdl_enabled() {
-    if (g_pdl < 0) { const char* e = getenv("MMLST_PDL"); g_pdl = (e && e[0] == '0') ? 0 : 1; }
+    if (g_pdl < 0) { const char* e = getenv("MMLST_PDL"); g_pdl = (e && e[0] == '1') ? 1 : 0; }
     return g_pdl;
 }
 extern "C" int mmlst_set_pdl(int on) { const int prev = mmlst_pdl_enabled(); if (on == 0 || on == 1) g_pdl = on; return prev; }
