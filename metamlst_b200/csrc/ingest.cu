@@ -33,6 +33,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "de.h"
 #include "ingest_core.cuh"
 
 namespace {
@@ -104,10 +105,6 @@ void ws_put(int dev, void* p, cudaStream_t st, bool record) {
         return;
     }
 }
-
-constexpr int kSlices = 8;
-struct CopyLane { std::mutex m; cudaStream_t s = nullptr; cudaEvent_t ev[kSlices + 1]; bool ready = false; };
-CopyLane g_lane[MMLST_MAX_DEVICES];
 
 struct DBuf {
     void* p = nullptr;
@@ -449,8 +446,6 @@ int err_class(uint32_t code) {
     }
 }
 
-typedef CUresult (*decomp_fn)(CUmemDecompressParams*, size_t, unsigned int, size_t*, CUstream);
-
 inline uint32_t h_rd16(const uint8_t* p) { return p[0] | (p[1] << 8); }
 inline uint32_t h_rd32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | (static_cast<uint32_t>(p[3]) << 24); }
 
@@ -530,29 +525,10 @@ extern "C" int mmlst_bam_ingest(int device, const uint8_t* bam, size_t n_bytes, 
     CUDA_TRY(cudaSetDevice(device));
     cudaStream_t st = static_cast<cudaStream_t>(stream_in);
     g_cur_stream = st;
-    // the hardware decompression engine, through the driver entry point (libcuda is already loaded by the runtime)
-    decomp_fn decompress = nullptr;
     {
-        int mask = 0;
-        CUdevice cudev;
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuDeviceGet", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) { cudaGetLastError(); mmlst_set_error("mmlst_bam_ingest: no driver entry points"); return MMLST_E_CUDA; }
-        reinterpret_cast<CUresult (*)(CUdevice*, int)>(fn)(&cudev, device);
-        if (cudaGetDriverEntryPoint("cuDeviceGetAttribute", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) { cudaGetLastError(); mmlst_set_error("mmlst_bam_ingest: no driver entry points"); return MMLST_E_CUDA; }
-        reinterpret_cast<CUresult (*)(int*, CUdevice_attribute, CUdevice)>(fn)(&mask, CU_DEVICE_ATTRIBUTE_MEM_DECOMPRESS_ALGORITHM_MASK, cudev);
-        if (!(mask & CU_MEM_DECOMPRESS_ALGORITHM_DEFLATE)) {
-            mmlst_set_error("mmlst_bam_ingest: this device has no hardware DEFLATE decompression (algorithm mask %d); use mmlst_bam_unpack", mask);
-            return MMLST_E_CUDA;
-        }
-        if (cudaGetDriverEntryPoint("cuMemBatchDecompressAsync", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
-            cudaGetLastError();
-            mmlst_set_error("mmlst_bam_ingest: driver has no cuMemBatchDecompressAsync");
-            return MMLST_E_CUDA;
-        }
-        decompress = reinterpret_cast<decomp_fn>(fn);
+        const int rc = mmlst_de_available(device);
+        if (rc != MMLST_OK) { mmlst_set_error("mmlst_bam_ingest: %s; use mmlst_bam_unpack", mmlst_last_error()); return rc; }
     }
-
     // ---- host: BGZF block table
     struct Blk { uint64_t coff; uint32_t clen, isize; uint64_t uoff; };
     std::vector<Blk> blocks;
@@ -625,36 +601,9 @@ extern "C" int mmlst_bam_ingest(int device, const uint8_t* bam, size_t n_bytes, 
     // the file goes over in slices on a copy stream while the decompression engine works on the slices that have landed: the copy
     // engine and the decompression engine are different units, so PCIe time hides behind the inflate (or the other way round)
     {
-        CopyLane& lane = g_lane[device % MMLST_MAX_DEVICES];
-        std::lock_guard<std::mutex> g(lane.m);
-        if (!lane.ready) {
-            CUDA_TRY(cudaStreamCreateWithFlags(&lane.s, cudaStreamNonBlocking));
-            for (auto& e : lane.ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            lane.ready = true;
-        }
-        CUDA_TRY(cudaEventRecord(lane.ev[kSlices], st));
-        CUDA_TRY(cudaStreamWaitEvent(lane.s, lane.ev[kSlices], 0));
-        const uint32_t per = (nb + kSlices - 1) / kSlices;
-        size_t lo = 0;
-        for (uint32_t c = 0, b0 = 0; b0 < nb; ++c, b0 += per) {
-            const uint32_t b1 = std::min(nb, b0 + per);
-            const size_t hi = (b1 == nb) ? n_bytes : static_cast<size_t>(blocks[b1].coff);   // up to the next slice's first payload byte
-            CUDA_TRY(cudaMemcpyAsync(d_comp.as<uint8_t>() + lo, bam + lo, hi - lo, cudaMemcpyHostToDevice, lane.s));
-            CUDA_TRY(cudaEventRecord(lane.ev[c], lane.s));
-            CUDA_TRY(cudaStreamWaitEvent(st, lane.ev[c], 0));
-            lo = hi;
-            for (uint32_t q0 = b0; q0 < b1; q0 += 1u << 16) {
-                const size_t cnt = std::min<size_t>(1u << 16, b1 - q0);
-                size_t bad = static_cast<size_t>(-1);
-                const CUresult rc = decompress(prm.data() + q0, cnt, 0, &bad, reinterpret_cast<CUstream>(st));
-                if (rc != CUDA_SUCCESS) {
-                    mmlst_set_error("mmlst_bam_ingest: cuMemBatchDecompressAsync failed (CUresult %d) at BGZF block %lld", static_cast<int>(rc),
-                                    bad == static_cast<size_t>(-1) ? -1ll : static_cast<long long>(q0 + bad));
-                    return MMLST_E_CUDA;
-                }
-            }
-        }
-        CUDA_TRY(cudaStreamSynchronize(lane.s));   // the lane (and its events) is free for the next call
+        std::vector<uint64_t> src_off(nb);
+        for (uint32_t b = 0; b < nb; ++b) src_off[b] = blocks[b].coff;
+        ING_TRY(mmlst_h2d_inflate(device, st, d_comp.as<uint8_t>(), bam, n_bytes, prm, src_off));
     }
     check_isize_kernel<<<(nb + kT - 1) / kT, kT, 0, st>>>(d_act.as<uint32_t>(), d_isize.as<uint32_t>(), nb, err);
     CUDA_TRY(cudaGetLastError());
