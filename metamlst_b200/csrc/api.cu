@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "de.h"
 #include "pileup.cuh"
 
 static thread_local char g_err[512] = "";
@@ -98,6 +99,8 @@ struct mmlst_ctx {
     DevBuf xr_ids, xr_x, xr_bytes, xq_ids, xq_x, xq_bytes;  // flagged (non-ACGT) rows / queries, H9
     uint32_t db_rows = 0, db_W = 0, db_n_xr = 0;
     // ST assignment (defineProfile): the `profiles` table grouped by profile, resident across queries
+    DevBuf zbuf, zact;                     // compressed score stream + the sizes the decompression engine reports
+    std::vector<uint32_t> zlen; uint32_t z_pending = 0;
     DevBuf prof_start, prof_allele, st_q, st_qn, st_count, st_best, st_nbest, st_out, first_row, row_key;
     uint32_t n_st = 0;
     bool has_row_key = false;
@@ -108,7 +111,7 @@ struct mmlst_ctx {
                        &planes, &chunks, &counts, &dbseq, &col_off, &cons, &holes, &snps, &db_hi,
                        &db_lo, &db_len, &q_hi, &q_lo, &q_len, &blocks, &best, &qhash, &cov_table, &cov, &xr_ids, &xr_x, &xr_bytes, &xq_ids, &xq_x, &xq_bytes,
                        &run_tid, &run_start, &chunk_run, &chunk_qlen, &prof_start, &prof_allele, &st_q, &st_qn, &st_count, &st_best, &st_nbest, &st_out,
-                       &first_row, &row_key};
+                       &first_row, &row_key, &zbuf, &zact};
         for (DevBuf* b : l) all[n_all++] = b;
     }
 };
@@ -174,8 +177,36 @@ static int upload_score_stream(mmlst_ctx* c, const mmlst_soa* soa) {
         TRY(h2d(c->tid, soa->tid, n, s));
     }
     const bool qc = runs && soa->chunk_qlen != nullptr;
-    TRY(h2d(c->as0, soa->as0, n, s));
-    TRY(h2d(c->xm3, soa->xm3, n, s));
+    if (runs && soa->z && soa->z->n_blocks) {
+        // compressed form: the DEFLATE blocks cross PCIe, the hardware decompression engine writes as0[] / xm3[] in HBM (csrc/de.cu)
+        const mmlst_zstream* z = soa->z;
+        if (!z->bytes || !z->table) { mmlst_set_error("mmlst_soa.z: null pointer"); return MMLST_E_ARG; }
+        TRY(c->as0.reserve(n * 2)); TRY(c->xm3.reserve(n)); TRY(c->zbuf.reserve(z->n_bytes + 64)); TRY(c->zact.reserve((size_t)z->n_blocks * 4));
+        std::vector<CUmemDecompressParams> prm(z->n_blocks);
+        std::vector<uint64_t> src_off(z->n_blocks);
+        memset(prm.data(), 0, sizeof(CUmemDecompressParams) * z->n_blocks);
+        c->zlen.resize(z->n_blocks);
+        for (uint32_t b = 0; b < z->n_blocks; ++b) {
+            const uint64_t* t = z->table + 4 * (size_t)b;
+            const uint64_t clen = t[3] >> 32, ulen = t[3] & 0xffffffffull;
+            const size_t cap = t[0] == 0 ? n * 2 : n;
+            if (t[0] > 1 || t[1] + ulen > cap || t[2] + clen > z->n_bytes || (b && t[2] < z->table[4 * (size_t)(b - 1) + 2]) || ulen > (4u << 20)) {
+                mmlst_set_error("mmlst_soa.z: block %u out of range / out of order", b);
+                return MMLST_E_ARG;
+            }
+            prm[b].srcNumBytes = clen; prm[b].dstNumBytes = ulen; prm[b].dstActBytes = c->zact.as<cuuint32_t>() + b;
+            prm[b].src = c->zbuf.as<uint8_t>() + t[2];
+            prm[b].dst = (t[0] == 0 ? c->as0.as<uint8_t>() : c->xm3.as<uint8_t>()) + t[1];
+            prm[b].algo = CU_MEM_DECOMPRESS_ALGORITHM_DEFLATE;
+            src_off[b] = t[2];
+            c->zlen[b] = (uint32_t)ulen;
+        }
+        TRY(mmlst_h2d_inflate(c->device, s, c->zbuf.as<uint8_t>(), z->bytes, z->n_bytes, prm, src_off));
+        c->z_pending = z->n_blocks;
+    } else {
+        TRY(h2d(c->as0, soa->as0, n, s));
+        TRY(h2d(c->xm3, soa->xm3, n, s));
+    }
     if (qc) TRY(h2d(c->chunk_qlen, soa->chunk_qlen, (n + 255) / 256, s));
     else TRY(h2d(c->qlen, soa->qlen, n, s));
     c->resident_qlen = !qc;
@@ -265,7 +296,20 @@ extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* al
     CUDA_TRY(cudaMemcpyAsync(n_hit, c->n_hit.p, nr * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(first_idx, c->first_idx.p, nr * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(counters, c->counters.p, 16, cudaMemcpyDeviceToHost, s));
+    std::vector<uint32_t> zact;
+    if (c->z_pending) {
+        zact.resize(c->z_pending);
+        CUDA_TRY(cudaMemcpyAsync(zact.data(), c->zact.p, (size_t)c->z_pending * 4, cudaMemcpyDeviceToHost, s));
+    }
     CUDA_TRY(cudaStreamSynchronize(s));
+    for (uint32_t b = 0; b < c->z_pending; ++b) {
+        if (zact[b] != c->zlen[b]) {
+            c->z_pending = 0;
+            mmlst_set_error("mmlst_score: block %u of the compressed score stream inflated to %u bytes, %u expected (corrupt mmlst_soa.z)", b, zact[b], c->zlen[b]);
+            return MMLST_E_ARG;
+        }
+    }
+    c->z_pending = 0;
     return MMLST_OK;
 }
 

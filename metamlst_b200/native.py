@@ -26,7 +26,11 @@ class Soa(C.Structure):
                 ("planes", C.c_void_p), ("n_prec", C.c_uint64), ("n_plane_words", C.c_uint64), ("max_row_words", C.c_uint32),
                 ("contig_start", C.c_void_p), ("n_ref", C.c_uint32),
                 ("n_runs", C.c_uint32), ("run_tid", C.c_void_p), ("run_start", C.c_void_p), ("chunk_run", C.c_void_p),
-                ("chunk_qlen", C.c_void_p)]
+                ("chunk_qlen", C.c_void_p), ("z", C.c_void_p)]
+
+
+class ZStream(C.Structure):
+    _fields_ = [("bytes", C.c_void_p), ("n_bytes", C.c_uint64), ("table", C.c_void_p), ("n_blocks", C.c_uint32)]
 
 
 class ScoreParams(C.Structure):

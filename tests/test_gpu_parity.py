@@ -58,6 +58,33 @@ def test_score_bit_exact(ctx, order, n_reads, species_filter, form, kernel_form)
         assert "".join(orc.out_log_rows(cel)) == "".join(orc.out_log_rows(want))
 
 
+@pytest.mark.parametrize("n_reads,block", [(40, 1 << 20), (3000, 4096), (60000, 1 << 16), (400000, 1 << 20)])
+def test_score_from_the_deflated_stream(ctx, n_reads, block):
+    """mmlst_soa.z: as0[] / xm3[] shipped as DEFLATE blocks and inflated by the hardware decompression engine -- same tables, bit for bit, as
+    the plain arrays and as the C port of the oracle; a corrupt block table is refused."""
+    db, tab = small_case(seed=33, n_reads=n_reads, orgs=("ecoli", "saureus"), apl=8, sub_err=0.02)
+    tab = tab.sorted_by_coord()
+    soa = packing.pack_table(tab, run_fraction=1.0)
+    index = api.AlleleIndex(tab.ref_names)
+    plain = api.score_soa_raw(ctx, soa, index, 176, 3, 50)
+    soa.deflate(block=block, pinned=(n_reads > 3000))
+    assert soa.z_bytes is not None and soa.z_table.shape[0] >= 2 and soa.z_bytes.shape[0] < 3 * soa.n_rec
+    keep_as0, keep_xm3 = soa.as0, soa.xm3
+    soa.as0, soa.xm3 = np.zeros_like(keep_as0), np.zeros_like(keep_xm3)   # the call must not read the plain arrays
+    got = api.score_soa_raw(ctx, soa, index, 176, 3, 50)
+    for a, b in zip(plain[:3], got[:3]):
+        assert np.array_equal(a, b)
+    assert plain[3:] == got[3:]
+    allow, locus_of, n_loci = lut_from_db(db)
+    ws, wc, wf, wcnt = corc.score(tab, allow, locus_of, n_loci, 176, 3, 50)
+    assert np.array_equal(got[0], ws) and np.array_equal(got[1], wc) and np.array_equal(got[2], wf) and got[3:] == (int(wcnt[0]), int(wcnt[1]))
+    bad = soa.z_table.copy()
+    bad[0, 3] = (bad[0, 3] >> np.uint64(32) << np.uint64(32)) | np.uint64((int(bad[0, 3]) & 0xffffffff) - 1)   # wrong inflated size
+    soa.z_table = bad
+    with pytest.raises(native.MmlstError):
+        api.score_soa_raw(ctx, soa, index, 176, 3, 50)
+
+
 def _np_score(tid, as0, xm3, qlen, idx, allow, n_ref, minscore, max_xm, min_len):
     al = allow[tid] != 0
     ok = al & (as0 >= minscore) & (qlen >= min_len) & (xm3 <= max_xm)
