@@ -158,3 +158,26 @@ def test_hamming_encoding_roundtrip_and_refusal():
     assert int(xx[0, 0]) == 0b10100 and int(xx[0, 1]) == 0 and bytes(xb[0, :6]) == b"ACNTaG" and xb.shape == (1, 256)
     assert ((int(hi[1, 0]) >> 3) & 1, (int(lo[1, 0]) >> 3) & 1) == (1, 1)  # clean columns keep their code (T)
     assert ((int(hi[1, 0]) >> 2) & 1, (int(lo[1, 0]) >> 2) & 1) == (0, 0)  # exceptional columns are 0 in the planes
+
+
+def test_deflated_score_stream_inflates_back_to_the_arrays():
+    """SoaHost.deflate() (include/mmlst.h, mmlst_zstream): independent raw-DEFLATE blocks + a table ordered by source offset; zlib on the
+    host gives back as0[] / xm3[] byte for byte (on the device the hardware decompression engine does: tests/test_gpu_parity.py)."""
+    import zlib
+    from helpers import small_case
+    db, tab = small_case(seed=3, n_reads=3000)
+    soa = packing.pack_table(tab.sorted_by_coord(), run_fraction=1.0)
+    soa.deflate(block=4096, pinned=False)
+    t = soa.z_table
+    assert t.shape[1] == 4 and np.all(np.diff(t[:, 2].astype(np.int64)) > 0) and int(t[0, 2]) == 0
+    out = {0: bytearray(soa.n_rec * 2), 1: bytearray(soa.n_rec)}
+    for kind, dst, src, packed in t.tolist():
+        clen, ulen = packed >> 32, packed & 0xffffffff
+        raw = zlib.decompress(bytes(soa.z_bytes[src:src + clen]), -15)
+        assert len(raw) == ulen <= 4096
+        out[kind][dst:dst + ulen] = raw
+    assert bytes(out[0]) == np.ascontiguousarray(soa.as0).tobytes() and bytes(out[1]) == np.ascontiguousarray(soa.xm3).tobytes()
+    assert int(t[-1, 2]) + (int(t[-1, 3]) >> 32) == soa.z_bytes.shape[0]
+    cs = soa.c_struct()
+    assert cs.z  # the C struct points at the zstream
+    assert packing.pack_table(tab, run_fraction=0.0).deflate().z_bytes is None   # needs the run-length form
