@@ -266,6 +266,23 @@ int mmlst_xchg_await_dev(void* local_base, uint32_t bytes, uint32_t world, uint6
                          uint64_t flag_off, void* out_all, uint64_t* epoch, uint32_t* ticket, uint32_t* status, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Multi-GPU, all-reduce form (north_star: partial score and pileup-count tensors all-reduced with NCCL over NVLink) for callers that
+ * are not torch.distributed processes.  One communicator per GPU: rank 0 makes the 128-byte id (mmlst_comm_unique_id) and hands it to the other ranks
+ * by any means, every rank calls mmlst_comm_create (collective).  mmlst_allreduce reduces IN PLACE, on `stream`, any of (NULL / 0 = skip):
+ *   score_block[score_words] : int64 words, SUM -- the accumulator block of a pass laid out [sum_as i64 x n_ref | counters u64 x 2 | n_hit u32 x n_ref,
+ *                              padded to 8 bytes] (u32 pairs add correctly as 64-bit words below 2^32 hits per allele)
+ *   first_idx[n_ref]         : u32, MIN (H5: first passing record of every allele; caller presets 0xFFFFFFFF)
+ *   counts[n_counts]         : u32, SUM (count tensor of the chosen contigs, columns x 5)
+ * Integer reductions: N ranks give one rank's tables bit for bit.  libnccl.so.2 is resolved at run time; MMLST_E_CUDA when it is missing.
+ * --------------------------------------------------------------------------------------------------------------- */
+typedef struct mmlst_comm mmlst_comm;
+int mmlst_comm_unique_id(uint8_t* id128);
+int mmlst_comm_create(const uint8_t* id128, int rank, int world, int device, mmlst_comm** out);
+void mmlst_comm_destroy(mmlst_comm* comm);
+int mmlst_allreduce(mmlst_comm* comm, int64_t* score_block, size_t score_words, uint32_t* first_idx, size_t n_ref, uint32_t* counts, size_t n_counts,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Stage 3 -- closest known allele by zip-truncated Hamming distance.  Replaces metaMLST_functions.py:230-234
  * (stringDiff) driven by metamlst-merge.py:174-181 over sequencesGetAll (:224-228).
  *   DB rows   : bit-planes hi/lo of the 2-bit code, tiles of 32 rows, word-major inside a tile:

@@ -120,6 +120,10 @@ EXPORTS = {
     "mmlst_hamming_tc_search_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                               C.c_uint32, C.c_void_p, C.c_void_p]),
     "mmlst_ingest_trim": (C.c_int, [C.c_int]),
+    "mmlst_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "mmlst_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "mmlst_comm_destroy": (None, [C.c_void_p]),
+    "mmlst_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mmlst_bam_ingest": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mmlst_dev_bam_info": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mmlst_dev_bam_free": (None, [C.c_void_p]),

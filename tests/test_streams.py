@@ -129,3 +129,16 @@ def test_slicing_resident_streams_equals_sharding_the_host_sample(world):
         assert (a.orig_idx is None) == (b.orig_idx is None) and (a.orig_idx is None or torch.equal(a.orig_idx, b.orig_idx))
         assert a.idx_base == b.idx_base and a.n_prec == b.n_prec and np.array_equal(a.contig_start, b.contig_start)
         assert (a.run_tid is None) == (b.run_tid is None) and (a.run_tid is None or torch.equal(a.run_tid, b.run_tid))
+
+
+@pytest.mark.gpu
+def test_c_abi_allreduce_over_two_gpus(tmp_path):
+    """mmlst_comm_* / mmlst_allreduce (include/mmlst.h): two plain processes, no torch.distributed."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "run_c_allreduce.py"), str(r), "2", str(tmp_path)], env=env,
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0].decode() for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and "C-ALLREDUCE-OK rank %d" % r in o, o[-3000:]
