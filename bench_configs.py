@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--devices", type=int, default=0, help="c4: GPUs to use (0 = all visible)")
     ap.add_argument("--alleles", type=int, default=1024, help="c4: alleles per locus of the configs[1] DB")
     ap.add_argument("--ingest", default="device", choices=["device", "host"])
+    ap.add_argument("--workers", default="processes", choices=["processes", "threads"], help="c4: one process per GPU (sample.CohortPool) or one thread per GPU (sample.type_cohort)")
     ap.add_argument("--parity-loci", type=int, default=12)
     ap.add_argument("--max-depth", type=int, default=8000)
     ap.add_argument("--pileup-impl", type=int, default=0)
@@ -209,17 +210,29 @@ def run_c4(args):
             keep_cores[i] = cores
     t_gen = time.perf_counter() - t0
     params = dict(ingest=args.ingest, engine="device", **{k: bench.PARAMS[k] for k in ("minscore", "max_xM", "min_read_len", "penalty")})
-    typers = {d: sample.SampleTyper(db_path, device=d, **params) for d in range(n_dev)}
     out_warm = os.path.join(work, "warm")
-    sample.type_cohort(paths[:n_dev], db_path, out_warm, devices=list(range(n_dev)), typers=typers)   # builds every device's tables once
-    out_dir = os.path.join(work, "out")
-    for d in range(n_dev):
-        torch.cuda.synchronize(d)
-    t0 = time.perf_counter()
-    results = sample.type_cohort(paths, db_path, out_dir, devices=list(range(n_dev)), typers=typers, prefetch=3)
-    for d in range(n_dev):
-        torch.cuda.synchronize(d)
-    dt = time.perf_counter() - t0
+    runs = []
+    if args.workers == "processes":
+        pool = sample.CohortPool(db_path, list(range(n_dev)), **params)
+        pool.type(paths[:2 * n_dev], out_warm)   # builds every device's tables and workspace once
+        typers = {}
+        for rep in range(2):
+            t0 = time.perf_counter()
+            results = pool.type(paths, os.path.join(work, "out%d" % rep))
+            runs.append(time.perf_counter() - t0)
+        pool.close()
+    else:
+        typers = {d: sample.SampleTyper(db_path, device=d, **params) for d in range(n_dev)}
+        sample.type_cohort(paths[:2 * n_dev], db_path, out_warm, devices=list(range(n_dev)), typers=typers)
+        for rep in range(2):
+            for d in range(n_dev):
+                torch.cuda.synchronize(d)
+            t0 = time.perf_counter()
+            results = sample.type_cohort(paths, db_path, os.path.join(work, "out%d" % rep), devices=list(range(n_dev)), typers=typers, prefetch=3)
+            for d in range(n_dev):
+                torch.cuda.synchronize(d)
+            runs.append(time.perf_counter() - t0)
+    dt = min(runs)
     assert len(results) == args.samples
     records = sum(r.records for r in results)
     lat = np.asarray([r.seconds["device_ingest"] + r.seconds["gpu"] + r.seconds["format"] for r in results])
@@ -246,10 +259,11 @@ def run_c4(args):
             "config": {"workload": "configs[3]: %d-sample cohort, every sample %d x %d bp reads, K=%d (%d records), bowtie2-ordered BAM files (%.2f GB in total) against "
                                    "the configs[1] DB (21 loci x %d alleles); files -> `.nfo` lines" % (args.samples, n_reads, args.read_len, args.k, n_reads * args.k,
                                                                                                           bam_bytes / 1e9, args.alleles),
-                       "schedule": "sample.type_cohort: one worker thread + one loader thread per GPU, samples dealt round-robin; ingest=%s (%s), engine=device "
+                       "schedule": ("sample.CohortPool: one PROCESS per GPU (each with its loader threads)" if args.workers == "processes" else
+                                    "sample.type_cohort: one worker thread + two loader threads per GPU") + ", samples dealt round-robin; ingest=%s (%s), engine=device "
                                    "(one kernel chain per sample, device-side selection)" % (args.ingest, "compressed bytes cross PCIe, hardware DEFLATE + parse/sort/cap/pack kernels"
                                                                                              if args.ingest == "device" else "C++ host unpacker")},
-            "whole_box_seconds": dt, "samples": args.samples, "samples_per_s": args.samples / dt, "records_total": records, "nfo_lines_written": nfo,
+            "whole_box_seconds": dt, "whole_box_seconds_both_runs": runs, "workers": args.workers, "samples": args.samples, "samples_per_s": args.samples / dt, "records_total": records, "nfo_lines_written": nfo,
             "per_sample_latency_ms": {"median": float(np.median(lat) * 1e3), "p90": float(np.percentile(lat, 90) * 1e3), "max": float(lat.max() * 1e3),
                                       "what": "device ingest + kernel chain + formatting of one sample, measured by its worker thread"},
             "per_sample_phase_ms_median": {k: float(np.median([r.seconds.get(k, 0.0) for r in results]) * 1e3) for k in ("load", "device_ingest", "gpu", "format")},

@@ -197,3 +197,20 @@ def test_cohort_driver_types_every_sample_in_order(tmp_path):
         gold = _golden_text(d, "sample.nfo")
         got = open(os.path.join(out, "sample.nfo"), newline="").read() if os.path.exists(os.path.join(out, "sample.nfo")) else ""
         assert got == gold * 3, n
+
+
+@pytest.mark.gpu
+def test_cohort_pool_one_process_per_gpu(tmp_path):
+    """sample.CohortPool: persistent worker processes (spawn), one per GPU, device ingest; the files are the reference's."""
+    name = "basic"
+    d = os.path.join(GOLDEN, name)
+    pool = sample.CohortPool(os.path.join(d, "db.sqlite"), [0], ingest="device", **{k: v for k, v in _params(name).items() if k != "log"})
+    try:
+        for rep in range(2):
+            out = str(tmp_path / ("o%d" % rep))
+            res = pool.type([os.path.join(d, "sample.bam")] * 3, out)
+            assert [r.sample for r in res] == ["sample"] * 3 and all(r.records > 0 for r in res)
+            gold = _golden_text(d, "sample.nfo")
+            assert open(os.path.join(out, "sample.nfo"), newline="").read() == gold * 3
+    finally:
+        pool.close()
