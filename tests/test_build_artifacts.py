@@ -55,6 +55,30 @@ def test_pileup_and_hamming_instruction_selection():
     assert kern and all("POPC" in v and "LDGSTS" in v for v in kern)  # popcount distance, cp.async query staging
 
 
+def test_tensor_core_hamming_uses_tcgen05_tmem_and_tma():
+    """csrc/hamming_tc.cu: `tcgen05.mma` shows as UTC*MMA, `tcgen05.ld` as LDTM, `tcgen05.commit` as UTCBAR, TMEM allocation as UTCATOMSWS,
+    the stage fills as UBLKCP; nothing of the legacy tensor path (HMMA from mma.sync / wmma)."""
+    f = _sass("hamming_tc.o")
+    kern = [v for k, v in f.items() if "hamming_tc_kernel" in k]
+    assert len(kern) == 1
+    k = kern[0]
+    assert re.search(r"\bUTC[A-Z]*MMA\b", k) and "LDTM" in k and "UTCBAR" in k and "UTCATOMSWS" in k and "UBLKCP" in k and "SYNCS" in k
+    assert not re.search(r"\bHMMA\b", k) and not re.search(r"\b(LDL|STL)\b", k)
+
+
+def test_ingest_kernels_are_built_and_do_not_spill():
+    f = _sass("ingest.o")
+    names = " ".join(f)
+    for k in ("chain_guess_kernel", "chain_repair_kernel", "chain_offsets_kernel", "parse_kernel", "gather_kernel", "cap_kernel", "pack_kernel"):
+        assert k in names, k
+    pack = [v for k, v in f.items() if "pack_kernel" in k][0]
+    assert "VOTE" in pack   # the plane words are assembled by warp ballots
+    text = open(os.path.join(CSRC, "ingest.ptxas.log")).read()
+    for m in re.finditer(r"Compiling entry function '(\S+)'.*?\n.*?\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", text):
+        if any(k in m.group(1) for k in ("chain_", "parse_kernel", "gather_kernel", "cap_kernel", "pack_kernel")):
+            assert int(m.group(3)) == 0 and int(m.group(4)) == 0, m.group(1)
+
+
 def test_hot_kernels_do_not_spill():
     bad = []
     for log in ("score_runs", "score", "pileup_bitsliced", "hamming", "select", "consensus"):
