@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--alleles", type=int, default=1024, help="c4: alleles per locus of the configs[1] DB")
     ap.add_argument("--ingest", default="device", choices=["device", "host"])
     ap.add_argument("--workers", default="processes", choices=["processes", "threads"], help="c4: one process per GPU (sample.CohortPool) or one thread per GPU (sample.type_cohort)")
+    ap.add_argument("--per-gpu", type=int, default=2, help="c4, --workers processes: worker processes per GPU")
     ap.add_argument("--parity-loci", type=int, default=12)
     ap.add_argument("--max-depth", type=int, default=8000)
     ap.add_argument("--pileup-impl", type=int, default=0)
@@ -213,8 +214,8 @@ def run_c4(args):
     out_warm = os.path.join(work, "warm")
     runs = []
     if args.workers == "processes":
-        pool = sample.CohortPool(db_path, list(range(n_dev)), **params)
-        pool.type(paths[:2 * n_dev], out_warm)   # builds every device's tables and workspace once
+        pool = sample.CohortPool(db_path, [d for d in range(n_dev) for _ in range(max(1, args.per_gpu))], **params)
+        pool.type(paths[:2 * n_dev * max(1, args.per_gpu)], out_warm)   # builds every worker's tables and workspace once
         typers = {}
         for rep in range(2):
             t0 = time.perf_counter()
@@ -259,7 +260,7 @@ def run_c4(args):
             "config": {"workload": "configs[3]: %d-sample cohort, every sample %d x %d bp reads, K=%d (%d records), bowtie2-ordered BAM files (%.2f GB in total) against "
                                    "the configs[1] DB (21 loci x %d alleles); files -> `.nfo` lines" % (args.samples, n_reads, args.read_len, args.k, n_reads * args.k,
                                                                                                           bam_bytes / 1e9, args.alleles),
-                       "schedule": ("sample.CohortPool: one PROCESS per GPU (each with its loader threads)" if args.workers == "processes" else
+                       "schedule": ("sample.CohortPool: %d PROCESS(es) per GPU (each with its loader threads)" % max(1, args.per_gpu) if args.workers == "processes" else
                                     "sample.type_cohort: one worker thread + two loader threads per GPU") + ", samples dealt round-robin; ingest=%s (%s), engine=device "
                                    "(one kernel chain per sample, device-side selection)" % (args.ingest, "compressed bytes cross PCIe, hardware DEFLATE + parse/sort/cap/pack kernels"
                                                                                              if args.ingest == "device" else "C++ host unpacker")},

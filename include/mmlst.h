@@ -172,7 +172,7 @@ typedef struct {
     uint32_t rec_begin, rec_end;   /* pileup-stream record range */
     uint32_t col_base, contig_len; /* column range in the count tensor */
     uint32_t plane_delta;          /* added to row_off[] */
-    uint32_t reserved[3];
+    uint32_t reserved[3];          /* chunk lists of mmlst_select_dev: [0] = chosen locus (output order) of the chunk, [1] = chunks of that locus */
 } mmlst_chunk;
 
 /* records per chunk that fills the chip for a launch over n_rec records (multiple of 512, <= 63*512) */
@@ -240,6 +240,15 @@ int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, cons
 int mmlst_set_pdl(int on);
 int mmlst_pileup_indirect_dev(const mmlst_prec* recs, const uint32_t* planes, const mmlst_chunk* chunks, const uint32_t* header,
                               uint32_t max_row_words, int minscore, int max_xm, uint32_t* counts, int impl, void* stream);
+/* mmlst_pileup_indirect_dev + mmlst_consensus_indirect_dev as ONE launch: the CTA that finishes the last chunk of a chosen locus (the chunk list of
+ * mmlst_select_dev carries, per chunk, its locus and that locus's chunk count; a per-locus ticket counts them) calls the consensus of that locus while
+ * its counts are still in L2.  ticket: device u32[max_loci], zeroed once by the caller, left zeroed by every call.  Same results as the two calls.
+ * Measured on B200 (configs[1], profiles/r2y_bench_fused{0,1}.json): NOT faster (serial pass 76.9 us against 74.3 us) -- the last chunk of every locus
+ * ends with the grid, so the fused consensus is a one-CTA-per-locus tail; the pipeline keeps the two launches unless MMLST_FUSED_TAIL=1. */
+int mmlst_pileup_consensus_indirect_dev(const mmlst_prec* recs, const uint32_t* planes, const mmlst_chunk* chunks, const uint32_t* header,
+                                        uint32_t max_row_words, int minscore, int max_xm, uint32_t* counts, const uint8_t* db_ascii,
+                                        const uint64_t* db_start, const uint32_t* col_off, uint32_t max_loci, uint32_t mincov, uint8_t* cons,
+                                        uint32_t* holes, uint32_t* snps, uint32_t flags, uint32_t* ticket, void* stream);
 /* flags: MMLST_CONSENSUS_CONSUME = zero every count that was read (the next pass accumulates from zero, no memset) */
 #define MMLST_CONSENSUS_CONSUME 1u
 int mmlst_consensus_indirect_dev(uint32_t* counts, const uint8_t* db_ascii, const uint64_t* db_start, const uint32_t* col_off,

@@ -388,12 +388,35 @@ extern "C" int mmlst_pileup_indirect_dev(const mmlst_prec* recs, const uint32_t*
                                          int impl, void* stream) {
     if (!recs || !planes || !chunks || !header || !counts) { mmlst_set_error("mmlst_pileup_indirect_dev: null pointer"); return MMLST_E_ARG; }
     if ((reinterpret_cast<uintptr_t>(recs) & 15) || (reinterpret_cast<uintptr_t>(planes) & 15)) { mmlst_set_error("mmlst_pileup_indirect_dev: recs and planes must be 16-byte aligned"); return MMLST_E_ARG; }
-    PileupArgs a{recs, planes, chunks, 0, max_row_words, minscore, max_xm, counts, 0, header + 1};
+    PileupArgs a{recs, planes, chunks, 0, max_row_words, minscore, max_xm, counts, 0, header + 1, FusedConsensus{}};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (impl == 1) return launch_pileup_atomic(a, s);
     if (impl == 0 || impl == 2) return launch_pileup_bitsliced(a, s);
     mmlst_set_error("mmlst_pileup_indirect_dev: impl %d unknown", impl);
     return MMLST_E_ARG;
+}
+
+// pileup AND consensus of a device-driven pass in one launch (see FusedConsensus in pileup.cuh); falls back to the two launches when the rows do not
+// fit the bit-sliced kernel's shared memory.  ticket: device u32[max_loci], zeroed once by the caller (every call leaves it zeroed).
+extern "C" int mmlst_consensus_indirect_dev(uint32_t*, const uint8_t*, const uint64_t*, const uint32_t*, uint32_t, const uint32_t*, uint32_t, uint8_t*, uint32_t*,
+                                            uint32_t*, uint32_t, void*);
+extern "C" int mmlst_pileup_consensus_indirect_dev(const mmlst_prec* recs, const uint32_t* planes, const mmlst_chunk* chunks, const uint32_t* header,
+                                                   uint32_t max_row_words, int minscore, int max_xm, uint32_t* counts, const uint8_t* db_ascii,
+                                                   const uint64_t* db_start, const uint32_t* col_off, uint32_t max_loci, uint32_t mincov, uint8_t* cons,
+                                                   uint32_t* holes, uint32_t* snps, uint32_t flags, uint32_t* ticket, void* stream) {
+    if (!recs || !planes || !chunks || !header || !counts || !db_ascii || !db_start || !col_off || !cons || !holes || !snps || !ticket) {
+        mmlst_set_error("mmlst_pileup_consensus_indirect_dev: null pointer");
+        return MMLST_E_ARG;
+    }
+    if ((reinterpret_cast<uintptr_t>(recs) & 15) || (reinterpret_cast<uintptr_t>(planes) & 15)) { mmlst_set_error("mmlst_pileup_consensus_indirect_dev: recs and planes must be 16-byte aligned"); return MMLST_E_ARG; }
+    PileupArgs a{recs, planes, chunks, 0, max_row_words, minscore, max_xm, counts, 0, header + 1,
+                 FusedConsensus{ticket, db_ascii, reinterpret_cast<const unsigned long long*>(db_start), col_off, mincov, cons, holes, snps,
+                                (flags & MMLST_CONSENSUS_CONSUME) ? 1u : 0u}};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (mmlst_pileup_bitsliced_fits(max_row_words)) return launch_pileup_bitsliced(a, s);
+    a.fc = FusedConsensus{};
+    TRY(launch_pileup_atomic(a, s));
+    return mmlst_consensus_indirect_dev(counts, db_ascii, db_start, col_off, max_loci, header, mincov, cons, holes, snps, flags, stream);
 }
 
 extern "C" int mmlst_pileup_consensus(mmlst_ctx* c, const mmlst_soa* soa, const uint32_t* chosen_tid, uint32_t n_loci,

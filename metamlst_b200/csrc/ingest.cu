@@ -106,6 +106,24 @@ void ws_put(int dev, void* p, cudaStream_t st, bool record) {
     }
 }
 
+// page-locked staging buffer, one per device, grown on demand; held (mutex) for the duration of one header fetch
+struct PinnedCache { std::mutex m; uint8_t* p = nullptr; size_t bytes = 0; };
+PinnedCache g_pinned[MMLST_MAX_DEVICES];
+struct PinnedStage {
+    PinnedCache& c;
+    std::unique_lock<std::mutex> lock;
+    explicit PinnedStage(int dev) : c(g_pinned[dev % MMLST_MAX_DEVICES]), lock(c.m) {}
+    uint8_t* get(size_t n) {
+        if (n <= c.bytes) return c.p;
+        if (c.p) cudaFreeHost(c.p);
+        c.p = nullptr; c.bytes = 0;
+        const size_t want = n + n / 2 + (1u << 16);
+        if (cudaHostAlloc(reinterpret_cast<void**>(&c.p), want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); c.p = nullptr; return nullptr; }
+        c.bytes = want;
+        return c.p;
+    }
+};
+
 struct DBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -611,18 +629,26 @@ extern "C" int mmlst_bam_ingest(int device, const uint8_t* bam, size_t n_bytes, 
     // ---- header (first bytes of the inflated stream come back to the host)
     std::unique_ptr<mmlst_dev_bam> B(new mmlst_dev_bam());
     B->device = device;
-    std::vector<uint8_t> head;
+    PinnedStage stage_guard(device);   // page-locked staging for the header, cached per device (a pageable D2H of a megabyte costs a millisecond)
+    const uint8_t* head = nullptr;
     uint64_t first_record = 0;
     {
-        size_t want = std::min<uint64_t>(usize, 1u << 20);
-        for (;;) {
-            head.resize(want);
-            CUDA_TRY(cudaMemcpyAsync(head.data(), d_u.p, want, cudaMemcpyDeviceToHost, st));
+        // l_text first (16 bytes), then ONE right-sized fetch: the reference dictionary is never longer than the @SQ lines that describe it
+        size_t want = std::min<uint64_t>(usize, 16);
+        for (int round = 0;; ++round) {
+            uint8_t* hb = stage_guard.get(want);
+            if (!hb) { mmlst_set_error("mmlst_bam_ingest: cudaHostAlloc(%zu) failed", want); return MMLST_E_NOMEM; }
+            head = hb;
+            CUDA_TRY(cudaMemcpyAsync(hb, d_u.p, want, cudaMemcpyDeviceToHost, st));
             {
                 const int rc = fetch_error(err, st, "mmlst_bam_ingest (inflate)");
                 if (rc != MMLST_OK) { mmlst_set_error("mmlst_bam_ingest: a BGZF block did not inflate to its ISIZE (corrupt file?)"); return MMLST_E_BAM; }
             }
-            if (want < 12 || memcmp(head.data(), "BAM\1", 4) != 0) { mmlst_set_error("mmlst_bam_ingest: not a BAM file (magic)"); return MMLST_E_BAM; }
+            if (round == 0 && want >= 12 && want < usize && memcmp(head, "BAM\1", 4) == 0) {
+                const int32_t lt = static_cast<int32_t>(h_rd32(&head[4]));
+                if (lt >= 0) { want = std::min<uint64_t>(usize, 2ull * static_cast<uint64_t>(lt) + (64u << 10)); continue; }
+            }
+            if (want < 12 || memcmp(head, "BAM\1", 4) != 0) { mmlst_set_error("mmlst_bam_ingest: not a BAM file (magic)"); return MMLST_E_BAM; }
             size_t p = 4;
             bool more = false;
             const int32_t l_text = static_cast<int32_t>(h_rd32(&head[p])); p += 4;
@@ -649,7 +675,7 @@ extern "C" int mmlst_bam_ingest(int device, const uint8_t* bam, size_t n_bytes, 
             }
             if (!more) { B->n_ref = static_cast<uint32_t>(n_ref); first_record = p; break; }
             if (want >= usize) { mmlst_set_error("mmlst_bam_ingest: truncated BAM header"); return MMLST_E_BAM; }
-            want = std::min<uint64_t>(usize, want * 8);
+            want = std::min<uint64_t>(usize, want * 4);
         }
     }
     const int32_t n_ref = static_cast<int32_t>(B->n_ref);

@@ -195,9 +195,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
         int cur_w = INT_MIN;
         uint32_t acc_tiles = 0;  // tiles folded into acc since the last clear
 
-        if (threadIdx.x == 0) load_geo(0);
+        if (threadIdx.x == 0 && ntiles) load_geo(0);
         __syncthreads();  // every warp is done with the previous chunk's stages and loop records
-        if (threadIdx.x == 0) { issue_copy(0, 0); if (ntiles > 1) load_geo(1); }
+        if (threadIdx.x == 0 && ntiles) { issue_copy(0, 0); if (ntiles > 1) load_geo(1); }
 
         for (uint32_t t = 0; t < ntiles; ++t) {
             const int stage = t % NS;
@@ -274,10 +274,36 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
             }
         }
         if (cur_w != INT_MIN) flush_word(acc, cur_w, ck, a.counts, acc_tiles);
+        if (a.fc.ticket) {
+            // fused consensus: the CTA that completes the last chunk of a locus calls it (release / acquire around the ticket)
+            __shared__ uint32_t s_last, s_cons[2];
+            __syncthreads();
+            const uint32_t locus = ck.reserved[0];
+            if (threadIdx.x == 0) {
+                __threadfence();
+                s_last = (atomicAdd(a.fc.ticket + locus, 1u) + 1u == ck.reserved[1]) ? 1u : 0u;
+            }
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                const uint32_t c0 = a.fc.col_off[locus], c1 = a.fc.col_off[locus + 1];
+                consensus_of_locus(a.counts, a.fc.db_ascii + a.fc.db_start[locus] - c0, c0, c1, a.fc.mincov, a.fc.consume != 0, a.fc.cons,
+                                   a.fc.holes + locus, a.fc.snps + locus, s_cons);
+                if (threadIdx.x == 0) a.fc.ticket[locus] = 0;
+            }
+        }
     }
 }
 
 }  // namespace
+
+// does a stream whose largest row has max_row_words words fit the bit-sliced kernel's shared-memory stages?  (else: atomic kernel)
+bool mmlst_pileup_bitsliced_fits(uint32_t max_row_words) {
+    const uint32_t stage_words = ((TR * max_row_words + 8u) + 31u) & ~31u;
+    const size_t stage_bytes = size_t(stage_words) * 4 + TR * sizeof(mmlst_prec);
+    const size_t smem = 2 * stage_bytes + 2 * TR * sizeof(uint4) + 2 * sizeof(uint64_t) + 16;
+    return !(max_row_words < 3 || smem > 220 * 1024);
+}
 
 int launch_pileup_bitsliced(const PileupArgs& a, cudaStream_t stream) {
     // stage = TR rows of the largest row (+ alignment slack) + TR 16-byte records; rows too long for shared memory

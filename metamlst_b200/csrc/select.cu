@@ -266,7 +266,8 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
     for (uint32_t i = threadIdx.x; i < nsel; i += blockDim.x) {
         const uint32_t tid = s_cbase[i];
         const unsigned long long nrec = a.contig_start[tid + 1] - a.contig_start[tid];
-        s_nch[i] = static_cast<uint32_t>((nrec + cr - 1) / cr);
+        const uint32_t k = static_cast<uint32_t>((nrec + cr - 1) / cr);
+        s_nch[i] = k ? k : 1u;   // a chosen locus without pileup records still gets one (empty) chunk: the fused consensus hangs off the last chunk of a locus
     }
     __syncthreads();
     if (threadIdx.x == 0) {  // exclusive prefixes over shared memory (no dependent global loads)
@@ -303,7 +304,9 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
         ck.rec_begin = static_cast<uint32_t>(b);
         ck.rec_end = static_cast<uint32_t>(b + cr < q1 ? b + cr : q1);
         ck.col_base = a.col_off[lo]; ck.contig_len = s_len[lo]; ck.plane_delta = 0;
-        ck.reserved[0] = ck.reserved[1] = ck.reserved[2] = 0;
+        ck.reserved[0] = lo;                              // chosen locus (output order) the chunk belongs to
+        ck.reserved[1] = s_cbase[lo + 1] - s_cbase[lo];   // chunks of that locus
+        ck.reserved[2] = 0;
         a.chunks[c] = ck;
     }
 }

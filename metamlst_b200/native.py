@@ -82,6 +82,8 @@ EXPORTS = {
     "mmlst_pileup_indirect_dev": (C.c_int, [C.c_void_p] * 4 + [C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "mmlst_consensus_indirect_dev": (C.c_int, [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_uint32, C.c_void_p]),
+    "mmlst_pileup_consensus_indirect_dev": (C.c_int, [C.c_void_p] * 4 + [C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "mmlst_chunk_records": (C.c_uint32, [C.c_uint64]),
     "mmlst_xchg_publish_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64,
                                          C.c_void_p, C.c_void_p]),

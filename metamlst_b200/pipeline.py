@@ -129,6 +129,11 @@ class DevicePipeline:
         self.small_h = self.out_h[: self.n_small * 4].view(torch.int32)
         self.cons_h = self.out_h[self.n_small * 4: self.out_bytes]
         self.genes_in_db_h = gdb
+        self.ticket = torch.zeros(nl + 8, dtype=torch.int32, device=dev)   # fused consensus: chunks finished per chosen locus (self-resetting)
+        # pileup + consensus as ONE launch: built, parity-tested, measured on B200 (profiles/r2y_bench_fused{0,1}.json): serial pass 76.9 us fused against
+        # 74.3 us as two launches (the last chunk of every locus finishes at the end of the grid, so the fused consensus is a serial tail of one CTA per
+        # locus, and every chunk pays two CTA barriers and a ticket) -- off unless MMLST_FUSED_TAIL=1
+        self.fused_tail = os.environ.get("MMLST_FUSED_TAIL", "0") == "1"
         self.want_tables = False  # step() also brings (sum_as, n_hit, first_idx) to the host: tables()
         self._tables_h = None
         self._clean = False  # score tables / counts / scratch hold the "nothing accumulated" state
@@ -169,7 +174,7 @@ class DevicePipeline:
     def reset_tables(self):
         """Score tables, counters, count tensor and the selection ticket back to the empty state.  The device-driven
         pass (`_enqueue`) leaves them that way itself (MMLST_SELECT_CONSUME / MMLST_CONSENSUS_CONSUME)."""
-        self.zblock.zero_(); self.first_idx.fill_(-1); self.scratch.zero_()
+        self.zblock.zero_(); self.first_idx.fill_(-1); self.scratch.zero_(); self.ticket.zero_()
         self._clean = True
 
     def _score_call(self):
@@ -313,6 +318,15 @@ class DevicePipeline:
                                                         self.small.data_ptr() + 4 * self.o_hdr, int(s.max_row_words), self.minscore, self.max_xM,
                                                         native.ptr(self.counts), self.impl, self._stream()))
 
+    def _pileup_consensus_call(self, flags: int):
+        """Pileup and consensus of the pass in ONE launch (csrc/pileup.cuh FusedConsensus): the CTA finishing the last chunk of a locus calls it."""
+        s, nl = self.s, self.index.n_loci
+        base = self.small.data_ptr()
+        native.check(self.lib.mmlst_pileup_consensus_indirect_dev(
+            native.ptr(s.p_recs), native.ptr(s.planes), native.ptr(self.chunks_d), base + 4 * self.o_hdr, int(s.max_row_words), self.minscore, self.max_xM,
+            native.ptr(self.counts), native.ptr(self.db_ascii_d), native.ptr(self.db_start_d), base + 4 * self.o_col, nl, self.mincov, native.ptr(self.cons),
+            base + 4 * self.o_holes, base + 4 * self.o_snps, flags, native.ptr(self.ticket), self._stream()))
+
     def _enqueue(self):
         """Everything of one pass on the current stream, no host synchronisation and no memset: score -> [all-reduce] ->
         select -> pileup -> [all-reduce] -> consensus -> ONE D2H into a pinned buffer.  Selection and consensus reset
@@ -324,12 +338,17 @@ class DevicePipeline:
             self._enqueue_tables()
         self._timed("select", lambda: self._select_call(native.SELECT_CONSUME | native.SELECT_SCRATCH_CLEAN))
         self.launches += 1
-        self._timed("pileup", self._pileup_call)
-        self.launches += 1
-        if self.dist and not self.owner:
-            dist.allreduce_counts(self.counts, self.group)
-        self._timed("consensus", lambda: self._consensus_call(native.CONSENSUS_CONSUME))
-        self.launches += 1
+        if self.fused_tail and self.impl != 1 and not (self.dist and not self.owner):
+            # no exchange between the two: pileup + consensus as one launch
+            self._timed("pileup+consensus", lambda: self._pileup_consensus_call(native.CONSENSUS_CONSUME))
+            self.launches += 1
+        else:
+            self._timed("pileup", self._pileup_call)
+            self.launches += 1
+            if self.dist and not self.owner:
+                dist.allreduce_counts(self.counts, self.group)
+            self._timed("consensus", lambda: self._consensus_call(native.CONSENSUS_CONSUME))
+            self.launches += 1
         if self.p2p:  # the pass's only exchange, by our own kernels: block -> every peer's memory, then wait for theirs
             native.check(self.lib.mmlst_xchg_publish_dev(native.ptr(self.out), self.out_bytes, native.ptr(self.peer_base), self.rank, self.world,
                                                          self.x_half, self.x_slot, self.x_flag_off, native.ptr(self.x_epoch), self._stream()))

@@ -523,15 +523,15 @@ def type_cohort(bam_paths: Sequence[str], db_path: str, out_dir: str, devices: S
 # ----------------------------------------------------------------------------------------------------------------
 # one PROCESS per GPU (the B200 way to run a box: no interpreter lock and no driver lock shared between the devices)
 # ----------------------------------------------------------------------------------------------------------------
-def _pool_worker(device: int, db_path: str, params: dict, tasks, results):
+def _pool_worker(slot: int, device: int, db_path: str, params: dict, tasks, results):
     try:
         import torch
         torch.cuda.set_device(device)
         typer = SampleTyper(db_path, device=device, **params)
     except BaseException as e:  # noqa: BLE001
-        results.put(("error", device, repr(e)))
+        results.put(("error", slot, repr(e)))
         return
-    results.put(("ready", device, None))
+    results.put(("ready", slot, None))
     while True:
         task = tasks.get()
         if task is None:
@@ -541,16 +541,18 @@ def _pool_worker(device: int, db_path: str, params: dict, tasks, results):
             res = type_cohort(paths, db_path, out_dir, devices=(device,), typers={device: typer})
             for r in res:
                 r.cel = None  # large and rebuilt on demand; keep the reply small
-            results.put(("done", device, list(zip(ids, res))))
+            results.put(("done", slot, list(zip(ids, res))))
         except BaseException as e:  # noqa: BLE001
-            results.put(("error", device, repr(e)))
+            results.put(("error", slot, repr(e)))
     typer.close()
 
 
 class CohortPool:
-    """Persistent workers, one process per GPU, each owning a warm SampleTyper (DB connection, device tables, ingest workspace).
-    `type(bam_paths, out_dir)` deals the samples round-robin and returns the SampleResults in input order -- what a shell loop of
-    `metamlst.py` runs over a cohort (BASELINE.json configs[3]) becomes one call per cohort."""
+    """Persistent workers, one PROCESS per entry of `devices` (a device may be listed twice: two processes then share the GPU and the
+    host-side part of one sample -- file read, block table, launches -- runs under the kernels of the other), each owning a warm
+    SampleTyper (DB connection, device tables, ingest workspace).  `type(bam_paths, out_dir)` deals the samples round-robin and returns
+    the SampleResults in input order -- what a shell loop of `metamlst.py` runs over a cohort (BASELINE.json configs[3]) becomes one
+    call per cohort."""
 
     def __init__(self, db_path: str, devices: Sequence[int], **params):
         import multiprocessing as mp
@@ -558,38 +560,39 @@ class CohortPool:
         self.devices = list(devices)
         self.db_path = db_path
         self._results = ctx.Queue()
-        self._tasks = {d: ctx.Queue() for d in self.devices}
-        self._procs = [ctx.Process(target=_pool_worker, args=(d, db_path, dict(params), self._tasks[d], self._results), daemon=True) for d in self.devices]
+        self._tasks = [ctx.Queue() for _ in self.devices]
+        self._procs = [ctx.Process(target=_pool_worker, args=(i, d, db_path, dict(params), self._tasks[i], self._results), daemon=True)
+                       for i, d in enumerate(self.devices)]
         for p in self._procs:
             p.start()
         for _ in self.devices:
-            kind, dev, info = self._results.get()
+            kind, slot, info = self._results.get()
             if kind != "ready":
                 self.close()
-                raise RuntimeError("cohort worker on device %s failed to start: %s" % (dev, info))
+                raise RuntimeError("cohort worker %s (device %s) failed to start: %s" % (slot, self.devices[slot], info))
 
     def type(self, bam_paths: Sequence[str], out_dir: str) -> List[SampleResult]:
         if not os.path.isdir(out_dir):
             os.mkdir(out_dir)
-        share: Dict[int, list] = {d: [] for d in self.devices}
+        share: List[list] = [[] for _ in self.devices]
         for i, p in enumerate(bam_paths):
-            share[self.devices[i % len(self.devices)]].append((i, p))
+            share[i % len(self.devices)].append((i, p))
         busy = 0
-        for d, items in share.items():
+        for slot, items in enumerate(share):
             if items:
-                self._tasks[d].put(([i for i, _p in items], [p for _i, p in items], out_dir))
+                self._tasks[slot].put(([i for i, _p in items], [p for _i, p in items], out_dir))
                 busy += 1
         out: List[Optional[SampleResult]] = [None] * len(bam_paths)
         for _ in range(busy):
-            kind, dev, info = self._results.get()
+            kind, slot, info = self._results.get()
             if kind == "error":
-                raise RuntimeError("cohort worker on device %s: %s" % (dev, info))
+                raise RuntimeError("cohort worker %s (device %s): %s" % (slot, self.devices[slot], info))
             for i, r in info:
                 out[i] = r
         return [r for r in out if r is not None]
 
     def close(self):
-        for q in self._tasks.values():
+        for q in self._tasks:
             try:
                 q.put(None)
             except Exception:  # noqa: BLE001

@@ -513,6 +513,13 @@ def test_device_pipeline_equals_host_selected_path_and_oracle(ctx, case, kernel_
             b = {sp: v for sp, v in b.items() if int(len(v) / 7.0 * 100) >= nloci}
         assert a == b
         assert a == pipe.step()  # idempotent
+        pipe.fused_tail = True    # pileup + consensus as ONE launch (the CTA finishing a locus's last chunk calls its consensus): same results,
+        assert a == pipe.step() == pipe.step()
+        pipe.capture()
+        assert a == pipe.step_graph() == pipe.step_graph()
+        pipe.fused_tail = False   # ... in either order of use (the ticket counters are left at zero)
+        pipe.graph = None
+        assert a == pipe.step()
     # oracle: consensus of every chosen contig
     stab = tab.sorted_by_coord()
     for sp, lst in a.items():
