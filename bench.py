@@ -532,11 +532,25 @@ def main():
         e2e_dev = torch.zeros(e2e_words * 4, dtype=torch.uint8, device=device)
         e2e_all = torch.zeros(world * e2e_words * 4, dtype=torch.uint8, device=device)
 
+    sidx = api.SampleIndex(ctx, index, st.ref_lens, db.row_seq)
+    e2e_mode = {"one_call": True}
+
     def e2e_step():
-        cel_raw = api.score_soa_raw(ctx, soa, index, **{k: PARAMS[k] for k in ("minscore", "max_xM", "min_read_len")})
-        chosen = api.fast_select(index, cel_raw[0], cel_raw[1], cel_raw[2], PARAMS["penalty"])
-        ts = [t for _sp, tt in chosen for t in tt]
-        seqs, holes, snps, _, _ = api.pileup_consensus(ctx, soa, ts, [db.row_seq(t) for t in ts], PARAMS["minscore"], PARAMS["max_xM"], 1, args.pileup_impl)
+        if e2e_mode["one_call"]:
+            # ONE library call per sample (mmlst_sample): score stream up + inflate, score, selection on the device, the chosen contigs' pileup records up,
+            # pileup, consensus, results down
+            # (--nloci gate: 100 on one rank; a rank that owns a subset of the loci cannot apply it -- the owner of the merge would, as in pipeline.py)
+            r = api.type_soa(sidx, soa, PARAMS["minscore"], PARAMS["max_xM"], PARAMS["min_read_len"], PARAMS["penalty"], 100 if world == 1 else 0,
+                             impl=args.pileup_impl)
+            ts = r["tids"]
+            flat = [x for _sp, lst in r["species"] for x in lst]
+            seqs, holes, snps = [x[1] for x in flat], [x[2] for x in flat], [x[3] for x in flat]
+        else:
+            # the two seams as separate calls (mmlst_score -> host selection -> mmlst_pileup_consensus): the reference's own call structure
+            cel_raw = api.score_soa_raw(ctx, soa, index, **{k: PARAMS[k] for k in ("minscore", "max_xM", "min_read_len")})
+            chosen = api.fast_select(index, cel_raw[0], cel_raw[1], cel_raw[2], PARAMS["penalty"])
+            ts = [t for _sp, tt in chosen for t in tt]
+            seqs, holes, snps, _, _ = api.pileup_consensus(ctx, soa, ts, [db.row_seq(t) for t in ts], PARAMS["minscore"], PARAMS["max_xM"], 1, args.pileup_impl)
         mine = {index.ref_names[t]: (seqs[i], int(holes[i]), int(snps[i])) for i, t in enumerate(ts)}
         if world > 1:
             # every rank's result block to every rank: ONE fixed-size all-gather (NCCL) of [n | tid, holes, snps per locus | consensus bytes]
@@ -578,11 +592,14 @@ def main():
         barrier()
         return ts_, (time.perf_counter() - t0_) / n_e2e
 
-    # first the plain form (3 bytes per record cross PCIe), then the compressed form (the default of the host-buffer path when the sample carries it)
+    # first the plain form (3 bytes per record cross PCIe), then the two seams as separate calls, then the headline: one call, compressed stream
     zb, zt = soa.z_bytes, soa.z_table
     soa.z_bytes = soa.z_table = None
     ts_local, dt_plain = time_e2e()
     soa.z_bytes, soa.z_table = zb, zt
+    e2e_mode["one_call"] = False
+    ts_local, dt_seams = time_e2e()
+    e2e_mode["one_call"] = True
     ts_local, dt = time_e2e()
     clocks = sampler.stop()
     line["clocks"] = clocks
@@ -592,14 +609,21 @@ def main():
     h2d += db.n_rows * 5 + int(sum((st.contig_start[t + 1] - st.contig_start[t]) * 16 for t in ts_local))
     proff = soa.p_row_off
     h2d += int(sum(int(proff[int(st.contig_start[t + 1])]) - int(proff[int(st.contig_start[t])]) for t in ts_local)) * 4
-    d2h = db.n_rows * 16 + 16 + sum(int(st.ref_lens[t]) for t in ts_local) + 8 * len(ts_local)
-    tt = torch.tensor([dt, float(h2d), float(d2h), dt_plain], dtype=torch.float64, device=device)
+    d2h_seams = db.n_rows * 16 + 16 + sum(int(st.ref_lens[t]) for t in ts_local) + 8 * len(ts_local)
+    # one call: the selection block (header + chosen rows / species / column offsets), block sizes reported by the decompression engine, consensus, holes, snps
+    d2h = (16 + 3 * n_loci + 1) * 4 + 4 * int(soa.z_table.shape[0]) + sum(int(st.ref_lens[t]) for t in ts_local) + 8 * n_loci
+    h2d -= db.n_rows * 4    # locus_of[] is resident (mmlst_index_upload); allow[] still travels
+    tt = torch.tensor([dt, float(h2d), float(d2h), dt_plain, dt_seams], dtype=torch.float64, device=device)
     if world > 1:
         mx = tt.clone(); torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.SUM)
-        dt = float(mx[0].item()); dt_plain = float(mx[3].item())
+        dt = float(mx[0].item()); dt_plain = float(mx[3].item()); dt_seams = float(mx[4].item())
     line["e2e"] = {"value": R_total / dt, "unit": "records/s", "h2d_bytes_per_step": int(tt[1].item()), "d2h_bytes_per_step": int(tt[2].item()),
-                   "ms_per_step": dt * 1e3, "timing": "host wall clock around the synchronous C-ABI calls, barrier on both sides, max over ranks",
+                   "ms_per_step": dt * 1e3, "timing": "host wall clock around the synchronous C-ABI call, barrier on both sides, max over ranks",
+                   "call": "mmlst_sample (api.type_soa): one call per sample from pinned host buffers -- score stream up, score, selection on the device, pileup records "
+                           "of the chosen contigs up, pileup, consensus, results down",
+                   "two_seam_calls": {"value": R_total / dt_seams, "unit": "records/s", "ms_per_step": dt_seams * 1e3,
+                                      "what": "mmlst_score -> host selection -> mmlst_pileup_consensus, the reference's call structure, same compressed stream"},
                    "host_numa_binding": numa, "exchange": "one fixed-size NCCL all-gather of the per-rank result blocks" if world > 1 else "none (one rank)",
                    "stream_form": "as0[] / xm3[] cross PCIe as DEFLATE blocks (%.2f bytes per record instead of 3) and are inflated in HBM by the hardware decompression "
                                   "engine, slice by slice behind the copy; deflating them is part of preparing a sample (%.2f s here, host threads), like unpacking it"

@@ -332,7 +332,9 @@ int mmlst_hamming_min_dev2(const uint32_t* db_hi, const uint32_t* db_lo, const u
  * the arrays deflate 3-4x.  When mmlst_soa.z is set (and the run-length form is used) mmlst_score ships THESE bytes and inflates them on the device
  * with the hardware decompression engine, slice by slice behind the copy.  blocks: independent raw-DEFLATE streams of at most 4 MiB of output each,
  * table[b] = { destination array (0 = as0 bytes, 1 = xm3 bytes), destination byte offset, source byte offset in `bytes`,
- * (compressed size << 32) | inflated size }, ordered by source offset.  Made once per sample by metamlst_b200.packing.SoaHost.deflate(). */
+ * (compressed size << 32) | inflated size }, ordered by source offset.  The blocks of an array tile a PREFIX of it, in order; what they do not
+ * cover is copied plain from as0 / xm3 after the compressed bytes (the bus carries it while the engine, the slower of the two, drains its queue).
+ * Made once per sample by metamlst_b200.packing.SoaHost.deflate(). */
 typedef struct {
     const uint8_t* bytes; uint64_t n_bytes;
     const uint64_t* table; uint32_t n_blocks;
@@ -355,7 +357,7 @@ typedef struct {
     /* with the run arrays only: len(SEQ) per 256-record chunk (mmlst_score_runs_qc_dev); when != NULL the host entry
      * points upload 3 B / record and never read `qlen` */
     const uint16_t* chunk_qlen;
-    /* with the run arrays only: as0 / xm3 as DEFLATE blocks (see mmlst_zstream); when != NULL mmlst_score never reads `as0` / `xm3` */
+    /* with the run arrays only: as0 / xm3 as DEFLATE blocks (see mmlst_zstream); mmlst_score then reads `as0` / `xm3` only past what the blocks cover */
     const mmlst_zstream* z;
 } mmlst_soa;
 
@@ -364,6 +366,41 @@ typedef struct { int minscore, max_xm, min_read_len; } mmlst_score_params;
 /* seam S1 (metamlst.py:96-151): uploads the score stream, runs the kernel, returns the integer tables. */
 int mmlst_score(mmlst_ctx* ctx, const mmlst_soa* soa, const uint8_t* allow, const uint32_t* locus_of, uint32_t n_loci,
                 const mmlst_score_params* prm, int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, uint64_t* counters);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * One call per sample over HOST buffers: what metamlst.py:96-287 does for one BAM between reading it and writing the
+ * .nfo -- score every record (seam S1), pick the best allele per locus and order species / loci (metamlst.py:133-220,
+ * on the device: mmlst_select_dev), pile up and call the consensus of the chosen contigs (seam S2, buildConsensus).
+ * Against mmlst_score + a host selection + mmlst_pileup_consensus it saves the D2H of the score tables, the host
+ * selection and two synchronisations; only the chosen contigs' pileup records cross the bus, after the selection.
+ *
+ * mmlst_index: what selection and consensus need from the allele DB and the BAM header, uploaded once per (DB, aligner index):
+ *   locus_of[n_ref] locus of every reference (allele row), allele_num[n_ref] = int(alleleVariant),
+ *   species_of_locus[n_loci], genes_in_db[n_species] = rows of `genes` per organism (metamlst.py:184),
+ *   db_ascii / db_off[n_ref+1]: the DB sequence of every row (metaMLST_functions.py:260-276 compares against it),
+ *   bam_ln[n_ref]: @SQ LN of every reference.
+ * mmlst_sample_result: caller-allocated arrays sized for n_loci entries (col_off: n_loci + 1), cons for cons_capacity bytes;
+ *   sum_as / n_hit / first_idx optional (all three or none).  Output order = the reference's dict order (H5).
+ *   error_bits & 1: "Database is broken" (metamlst.py:188-190), nothing piled up.  MMLST_E_RANGE + bad_len_tid: a chosen reference
+ *   whose BAM LN exceeds its DB sequence (the reference raises IndexError, H10).
+ * --------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const uint32_t* locus_of; const uint32_t* allele_num; uint32_t n_ref;
+    const uint32_t* species_of_locus; uint32_t n_loci;
+    const uint32_t* genes_in_db; uint32_t n_species;
+    const uint8_t* db_ascii; const uint64_t* db_off; const uint32_t* bam_ln;
+} mmlst_index;
+typedef struct { int minscore, max_xm, min_read_len, penalty, nloci_pct; uint32_t mincov; int pileup_impl; } mmlst_sample_params;
+typedef struct {
+    uint32_t n_chosen, error_bits, bad_len_tid, reserved;
+    uint64_t total_reads, ignored_reads;
+    uint32_t* chosen_tid; uint32_t* chosen_species; uint32_t* col_off;
+    uint8_t* cons; uint64_t cons_capacity;
+    uint32_t* holes; uint32_t* snps;
+    int64_t* sum_as; uint32_t* n_hit; uint32_t* first_idx;
+} mmlst_sample_result;
+int mmlst_index_upload(mmlst_ctx* ctx, const mmlst_index* index);
+int mmlst_sample(mmlst_ctx* ctx, const mmlst_soa* soa, const uint8_t* allow, const mmlst_sample_params* prm, mmlst_sample_result* res);
 
 /* seam S1, coverage column (metamlst.py:127,228).  MMLST_COVERAGE_STREAM_RESIDENT: the score stream of THIS soa is still
  * in the context from the preceding mmlst_score call (only the 16 B/record hashes are uploaded). */

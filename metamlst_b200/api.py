@@ -183,6 +183,79 @@ def pileup_consensus(ctx: native.Context, soa: packing.SoaHost, chosen_tid: Sequ
     return seqs, holes[:n].copy(), snps[:n].copy(), (counts[:total] if want_counts else None), col_off
 
 
+class SampleIndex:
+    """What `type_soa` keeps resident in a context: the allele index, the DB sequences and the BAM header lengths (include/mmlst.h, mmlst_index).
+    genes_in_db: {organism: rows of `genes`} (metamlst.py:184); default = loci of the organism among the references."""
+
+    def __init__(self, ctx: native.Context, index: AlleleIndex, ref_lens: Sequence[int], dbseq_of, genes_in_db: Optional[Dict[str, int]] = None):
+        self.ctx, self.index = ctx, index
+        n_ref = len(index.ref_names)
+        self.species_names: List[str] = []
+        sp_id: Dict[str, int] = {}
+        sol = np.zeros(index.n_loci, dtype=np.uint32)
+        for l, (sp, _g) in enumerate(index.locus_names):
+            if sp not in sp_id:
+                sp_id[sp] = len(self.species_names)
+                self.species_names.append(sp)
+            sol[l] = sp_id[sp]
+        gdb = np.asarray([(genes_in_db or {}).get(sp, int((sol == i).sum())) for i, sp in enumerate(self.species_names)], dtype=np.uint32)
+        seqs = [dbseq_of(t).encode("latin-1") for t in range(n_ref)]
+        db_off = np.zeros(n_ref + 1, dtype=np.uint64)
+        db_off[1:] = np.cumsum([len(x) for x in seqs])
+        db_ascii = np.frombuffer(b"".join(seqs) + b"\0" * 8, dtype=np.uint8)
+        allele_num = np.asarray([int(a) for a in index.allele], dtype=np.int64).astype(np.uint32)
+        self.ref_lens = np.ascontiguousarray(ref_lens, dtype=np.uint32)
+        self.n_loci = index.n_loci
+        self.max_cols = int(np.sort(self.ref_lens)[::-1][: self.n_loci].sum())
+        ix = native.Index(native.ptr(index.locus_of), native.ptr(allele_num), n_ref, native.ptr(sol), index.n_loci, native.ptr(gdb), len(self.species_names),
+                          native.ptr(db_ascii), native.ptr(db_off), native.ptr(self.ref_lens))
+        native.check(native.lib().mmlst_index_upload(ctx.handle, C.byref(ix)))
+        nl = self.n_loci
+        self._tid = np.zeros(nl, np.uint32); self._sp = np.zeros(nl, np.uint32); self._col = np.zeros(nl + 1, np.uint32)
+        self._holes = np.zeros(nl, np.uint32); self._snps = np.zeros(nl, np.uint32); self._cons = np.zeros(self.max_cols + 16, np.uint8)
+        self._allow: Dict[Optional[str], np.ndarray] = {}
+
+
+def type_soa(sidx: SampleIndex, soa: packing.SoaHost, minscore: int = 80, max_xM: int = 5, min_read_len: int = 50, penalty: int = 100, nloci: int = 100,
+             species_filter: Optional[str] = None, mincov: int = 1, impl: int = 0, want_tables: bool = False):
+    """One sample held in host buffers, ONE library call (mmlst_sample): score (seam S1, metamlst.py:96-151), selection in the reference's dict order
+    (metamlst.py:133-220, H5/H6, --nloci gate), pileup + consensus of the chosen contigs (seam S2, metaMLST_functions.py:249-281).
+    Returns {"species": [(organism, [(ref name, consensus, holes, snps)])], "totalReads", "ignoredReads", "tids", "tables"}."""
+    check_max_xm(max_xM)
+    if soa.minqual != 20:
+        raise ValueError("buildConsensus needs a stream unpacked with minqual=20 (metaMLST_functions.py:258)")
+    allow = sidx._allow.get(species_filter)
+    if allow is None:
+        allow = sidx._allow[species_filter] = sidx.index.allow_mask(species_filter)
+    res = native.SampleResult()
+    res.chosen_tid, res.chosen_species, res.col_off = native.ptr(sidx._tid), native.ptr(sidx._sp), native.ptr(sidx._col)
+    res.cons, res.cons_capacity, res.holes, res.snps = native.ptr(sidx._cons), sidx._cons.shape[0], native.ptr(sidx._holes), native.ptr(sidx._snps)
+    tables = None
+    if want_tables:
+        n_ref = len(sidx.index.ref_names)
+        tables = (np.zeros(n_ref, np.int64), np.zeros(n_ref, np.uint32), np.zeros(n_ref, np.uint32))
+        res.sum_as, res.n_hit, res.first_idx = (native.ptr(t) for t in tables)
+    prm = native.SampleParams(int(minscore), int(max_xM), int(min_read_len), int(penalty), int(nloci), int(mincov), int(impl))
+    cs = soa.c_struct()
+    rc = native.lib().mmlst_sample(sidx.ctx.handle, C.byref(cs), native.ptr(allow), C.byref(prm), C.byref(res))
+    if rc == native.E_RANGE and native.lib().mmlst_last_error().startswith(b"string index out of range"):
+        raise IndexError(native.lib().mmlst_last_error().decode())   # H10
+    native.check(rc)
+    if res.error_bits & 1:
+        raise RuntimeError("Database is broken")   # metamlst.py:188-190
+    n = int(res.n_chosen)
+    cons = sidx._cons.tobytes()
+    names = sidx.index.ref_names
+    species: List[Tuple[str, list]] = []
+    for i in range(n):
+        sp = sidx.species_names[int(sidx._sp[i])]
+        if not species or species[-1][0] != sp:
+            species.append((sp, []))
+        species[-1][1].append((names[int(sidx._tid[i])], cons[int(sidx._col[i]):int(sidx._col[i + 1])].decode("latin-1"), int(sidx._holes[i]), int(sidx._snps[i])))
+    return {"species": species, "totalReads": int(res.total_reads), "ignoredReads": int(res.ignored_reads), "tids": [int(t) for t in sidx._tid[:n]],
+            "tables": tables}
+
+
 def build_consensus(ctx: native.Context, soa: packing.SoaHost, chromosomeList: Dict[str, str], filterScore: int, max_xM: int,
                     debugMode: bool = False, impl: int = 0) -> List[ConsRecord]:
     """Seam S2 -- same contract as metaMLST_functions.buildConsensus(bamFile, chromosomeList, filterScore, max_xM,

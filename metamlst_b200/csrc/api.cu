@@ -2,6 +2,9 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -21,6 +24,25 @@ int mmlst_cuda_fail(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return MMLST_OK;
     mmlst_set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
     return MMLST_E_CUDA;
+}
+
+namespace {
+struct TraceBuf { const char* label[32]; double t[32]; int n = 0; };
+thread_local TraceBuf g_trace;
+bool trace_on() { static const bool on = [] { const char* e = getenv("MMLST_TRACE"); return e && *e && *e != '0'; }(); return on; }
+double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+void mmlst_trace_mark(const char* label) {
+    if (!trace_on() || g_trace.n >= 32) return;
+    g_trace.label[g_trace.n] = label; g_trace.t[g_trace.n++] = now_us();
+}
+void mmlst_trace_flush(const char* call) {
+    if (!trace_on()) return;
+    fprintf(stderr, "[mmlst trace] %s:", call);
+    for (int i = 1; i < g_trace.n; ++i) fprintf(stderr, " %s=%.0fus", g_trace.label[i], g_trace.t[i] - g_trace.t[i - 1]);
+    if (g_trace.n > 1) fprintf(stderr, " total=%.0fus", g_trace.t[g_trace.n - 1] - g_trace.t[0]);
+    fprintf(stderr, "\n");
+    g_trace.n = 0;
 }
 
 int mmlst_num_sms() {
@@ -104,14 +126,30 @@ struct mmlst_ctx {
     DevBuf prof_start, prof_allele, st_q, st_qn, st_count, st_best, st_nbest, st_out, first_row, row_key;
     uint32_t n_st = 0;
     bool has_row_key = false;
-    DevBuf* all[64];
+    // resident allele index + result staging of mmlst_sample (mmlst_index_upload)
+    DevBuf ix_locus_of, ix_locus_rows, ix_locus_start, ix_allele_num, ix_species_of_locus, ix_genes_in_db, ix_db_ascii, ix_db_off, ix_bam_ln, ix_zero64, ix_scratch,
+           ix_out, ix_db_start, ix_chunks;
+    uint32_t ix_n_ref = 0, ix_n_loci = 0, ix_n_species = 0;
+    std::vector<uint32_t> ix_bam_ln_h; std::vector<uint64_t> ix_db_off_h;
+    void* pin = nullptr; size_t pin_cap = 0;   // page-locked staging for the results of mmlst_sample
+    int pin_reserve(size_t bytes) {
+        if (bytes <= pin_cap) return MMLST_OK;
+        if (pin) cudaFreeHost(pin);
+        pin = nullptr; pin_cap = 0;
+        cudaError_t e = cudaHostAlloc(&pin, bytes + bytes / 8 + 256, cudaHostAllocDefault);
+        if (e != cudaSuccess) { cudaGetLastError(); mmlst_set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return MMLST_E_NOMEM; }
+        pin_cap = bytes + bytes / 8 + 256;
+        return MMLST_OK;
+    }
+    DevBuf* all[80];
     int n_all = 0;
     mmlst_ctx() {
         DevBuf* l[] = {&tid, &as0, &xm3, &qlen, &oidx, &allow, &locus_of, &sum_as, &n_hit, &first_idx, &counters, &p_recs,
                        &planes, &chunks, &counts, &dbseq, &col_off, &cons, &holes, &snps, &db_hi,
                        &db_lo, &db_len, &q_hi, &q_lo, &q_len, &blocks, &best, &qhash, &cov_table, &cov, &xr_ids, &xr_x, &xr_bytes, &xq_ids, &xq_x, &xq_bytes,
                        &run_tid, &run_start, &chunk_run, &chunk_qlen, &prof_start, &prof_allele, &st_q, &st_qn, &st_count, &st_best, &st_nbest, &st_out,
-                       &first_row, &row_key, &zbuf, &zact};
+                       &first_row, &row_key, &zbuf, &zact, &ix_locus_of, &ix_locus_rows, &ix_locus_start, &ix_allele_num, &ix_species_of_locus, &ix_genes_in_db, &ix_db_ascii,
+                       &ix_db_off, &ix_bam_ln, &ix_zero64, &ix_scratch, &ix_out, &ix_db_start, &ix_chunks};
         for (DevBuf* b : l) all[n_all++] = b;
     }
 };
@@ -144,6 +182,7 @@ extern "C" void mmlst_destroy(mmlst_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (int i = 0; i < c->n_all; ++i) c->all[i]->release();
+    if (c->pin) cudaFreeHost(c->pin);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -186,14 +225,16 @@ static int upload_score_stream(mmlst_ctx* c, const mmlst_soa* soa) {
         std::vector<uint64_t> src_off(z->n_blocks);
         memset(prm.data(), 0, sizeof(CUmemDecompressParams) * z->n_blocks);
         c->zlen.resize(z->n_blocks);
+        uint64_t covered[2] = {0, 0};   // the blocks of an array tile a PREFIX of it, in order; the rest of the array ships plain
         for (uint32_t b = 0; b < z->n_blocks; ++b) {
             const uint64_t* t = z->table + 4 * (size_t)b;
             const uint64_t clen = t[3] >> 32, ulen = t[3] & 0xffffffffull;
             const size_t cap = t[0] == 0 ? n * 2 : n;
-            if (t[0] > 1 || t[1] + ulen > cap || t[2] + clen > z->n_bytes || (b && t[2] < z->table[4 * (size_t)(b - 1) + 2]) || ulen > (4u << 20)) {
-                mmlst_set_error("mmlst_soa.z: block %u out of range / out of order", b);
+            if (t[0] > 1 || t[1] != covered[t[0] & 1] || t[1] + ulen > cap || t[2] + clen > z->n_bytes || (b && t[2] < z->table[4 * (size_t)(b - 1) + 2]) || ulen > (4u << 20)) {
+                mmlst_set_error("mmlst_soa.z: block %u out of range / out of order (the blocks of an array must tile a prefix of it)", b);
                 return MMLST_E_ARG;
             }
+            covered[t[0]] += ulen;
             prm[b].srcNumBytes = clen; prm[b].dstNumBytes = ulen; prm[b].dstActBytes = c->zact.as<cuuint32_t>() + b;
             prm[b].src = c->zbuf.as<uint8_t>() + t[2];
             prm[b].dst = (t[0] == 0 ? c->as0.as<uint8_t>() : c->xm3.as<uint8_t>()) + t[1];
@@ -201,7 +242,17 @@ static int upload_score_stream(mmlst_ctx* c, const mmlst_soa* soa) {
             src_off[b] = t[2];
             c->zlen[b] = (uint32_t)ulen;
         }
-        TRY(mmlst_h2d_inflate(c->device, s, c->zbuf.as<uint8_t>(), z->bytes, z->n_bytes, prm, src_off));
+        std::vector<MmlstPlainCopy> plain;
+        if (covered[0] < n * 2) {
+            if (!soa->as0) { mmlst_set_error("mmlst_soa.z covers %llu of %llu bytes of as0[] and as0 is NULL", (unsigned long long)covered[0], (unsigned long long)(n * 2)); return MMLST_E_ARG; }
+            plain.push_back({c->as0.as<uint8_t>() + covered[0], reinterpret_cast<const uint8_t*>(soa->as0) + covered[0], (size_t)(n * 2 - covered[0])});
+        }
+        if (covered[1] < n) {
+            if (!soa->xm3) { mmlst_set_error("mmlst_soa.z covers %llu of %llu bytes of xm3[] and xm3 is NULL", (unsigned long long)covered[1], (unsigned long long)n); return MMLST_E_ARG; }
+            plain.push_back({c->xm3.as<uint8_t>() + covered[1], soa->xm3 + covered[1], (size_t)(n - covered[1])});
+        }
+        mmlst_trace_mark("params_built");
+        TRY(mmlst_h2d_inflate(c->device, s, c->zbuf.as<uint8_t>(), z->bytes, z->n_bytes, prm, src_off, &plain, 3));
         c->z_pending = z->n_blocks;
     } else {
         TRY(h2d(c->as0, soa->as0, n, s));
@@ -257,17 +308,10 @@ extern "C" int mmlst_chunk_qlen(const uint16_t* qlen, uint64_t n_rec, uint16_t* 
     return MMLST_OK;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* allow, const uint32_t* locus_of,
-                           uint32_t n_loci, const mmlst_score_params* prm, int64_t* sum_as, uint32_t* n_hit,
-                           uint32_t* first_idx, uint64_t* counters) {
-    CTX_ENTER(c);
-    if (!soa || !allow || !locus_of || !prm || !sum_as || !n_hit || !first_idx || !counters) { mmlst_set_error("mmlst_score: null pointer"); return MMLST_E_ARG; }
+// the score kernel over the stream upload_score_stream() left in the context (the form follows what was uploaded), tables zeroed first
+static int launch_resident_score(mmlst_ctx* c, const mmlst_soa* soa, const mmlst_score_params* prm, const uint32_t* locus_of_dev) {
     cudaStream_t s = c->stream;
     const size_t n = soa->n_rec, nr = soa->n_ref;
-    TRY(upload_score_stream(c, soa));
-    TRY(h2d(c->allow, allow, nr, s));
-    TRY(h2d(c->locus_of, locus_of, nr, s));
     TRY(c->sum_as.reserve(nr * 8)); TRY(c->n_hit.reserve(nr * 4)); TRY(c->first_idx.reserve(nr * 4 + 4)); TRY(c->counters.reserve(16));
     CUDA_TRY(cudaMemsetAsync(c->sum_as.p, 0, nr * 8, s));
     CUDA_TRY(cudaMemsetAsync(c->n_hit.p, 0, nr * 4, s));
@@ -288,10 +332,27 @@ extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* al
     } else {
         TRY(mmlst_score_dev(c->tid.as<uint32_t>(), c->as0.as<int16_t>(), c->xm3.as<uint8_t>(), c->qlen.as<uint16_t>(),
                             soa->orig_idx ? c->oidx.as<uint32_t>() : nullptr, n, 0, c->allow.as<uint8_t>(),
-                            c->locus_of.as<uint32_t>(), (uint32_t)nr, prm->minscore, prm->max_xm, prm->min_read_len,
+                            locus_of_dev, (uint32_t)nr, prm->minscore, prm->max_xm, prm->min_read_len,
                             c->sum_as.as<int64_t>(), c->n_hit.as<uint32_t>(), c->first_idx.as<uint32_t>(),
                             c->counters.as<uint64_t>(), s));
     }
+    return MMLST_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* allow, const uint32_t* locus_of,
+                           uint32_t n_loci, const mmlst_score_params* prm, int64_t* sum_as, uint32_t* n_hit,
+                           uint32_t* first_idx, uint64_t* counters) {
+    CTX_ENTER(c);
+    if (!soa || !allow || !locus_of || !prm || !sum_as || !n_hit || !first_idx || !counters) { mmlst_set_error("mmlst_score: null pointer"); return MMLST_E_ARG; }
+    cudaStream_t s = c->stream;
+    const size_t n = soa->n_rec, nr = soa->n_ref;
+    mmlst_trace_mark("enter");
+    TRY(upload_score_stream(c, soa));
+    mmlst_trace_mark("upload_enqueued");
+    TRY(h2d(c->allow, allow, nr, s));
+    TRY(h2d(c->locus_of, locus_of, nr, s));
+    TRY(launch_resident_score(c, soa, prm, c->locus_of.as<uint32_t>()));
     CUDA_TRY(cudaMemcpyAsync(sum_as, c->sum_as.p, nr * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(n_hit, c->n_hit.p, nr * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(first_idx, c->first_idx.p, nr * 4, cudaMemcpyDeviceToHost, s));
@@ -301,7 +362,10 @@ extern "C" int mmlst_score(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* al
         zact.resize(c->z_pending);
         CUDA_TRY(cudaMemcpyAsync(zact.data(), c->zact.p, (size_t)c->z_pending * 4, cudaMemcpyDeviceToHost, s));
     }
+    mmlst_trace_mark("kernel_d2h_enqueued");
     CUDA_TRY(cudaStreamSynchronize(s));
+    mmlst_trace_mark("sync");
+    mmlst_trace_flush("mmlst_score");
     for (uint32_t b = 0; b < c->z_pending; ++b) {
         if (zact[b] != c->zlen[b]) {
             c->z_pending = 0;
@@ -427,6 +491,7 @@ extern "C" int mmlst_pileup_consensus(mmlst_ctx* c, const mmlst_soa* soa, const 
     if (!soa || !chosen_tid || !dbseq || !col_off || !cons || !holes || !snps) { mmlst_set_error("mmlst_pileup_consensus: null pointer"); return MMLST_E_ARG; }
     if (n_loci == 0) return MMLST_OK;
     cudaStream_t s = c->stream;
+    mmlst_trace_mark("enter");
     // gather the chosen contigs' record / plane ranges (contiguous in the coordinate-sorted stream)
     auto row_end = [&](uint64_t r) { return soa->p_recs[r].row_off + mmlst_row_words(soa->p_recs[r].nw); };
     size_t n_rec = 0, n_words = 0;
@@ -464,6 +529,7 @@ extern "C" int mmlst_pileup_consensus(mmlst_ctx* c, const mmlst_soa* soa, const 
         wbase += (size_t)(w1 - w0);
         wbase = (wbase + 3) & ~(size_t)3;
     }
+    mmlst_trace_mark("stream_h2d_enqueued");
     TRY(h2d(c->chunks, chunks.data(), chunks.size(), s));
     TRY(h2d(c->dbseq, dbseq, total_cols, s));
     TRY(h2d(c->col_off, col_off, (size_t)n_loci + 1, s));
@@ -478,7 +544,184 @@ extern "C" int mmlst_pileup_consensus(mmlst_ctx* c, const mmlst_soa* soa, const 
     CUDA_TRY(cudaMemcpyAsync(cons, c->cons.p, total_cols, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(holes, c->holes.p, n_loci * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(snps, c->snps.p, n_loci * 4, cudaMemcpyDeviceToHost, s));
+    mmlst_trace_mark("kernels_d2h_enqueued");
     CUDA_TRY(cudaStreamSynchronize(s));
+    mmlst_trace_mark("sync");
+    mmlst_trace_flush("mmlst_pileup_consensus");
+    return MMLST_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One call per sample over HOST buffers: score -> selection (on the device) -> pileup of the chosen contigs -> consensus.
+extern "C" int mmlst_index_upload(mmlst_ctx* c, const mmlst_index* ix) {
+    CTX_ENTER(c);
+    if (!ix || !ix->locus_of || !ix->allele_num || !ix->species_of_locus || !ix->genes_in_db || !ix->db_ascii || !ix->db_off || !ix->bam_ln) {
+        mmlst_set_error("mmlst_index_upload: null pointer");
+        return MMLST_E_ARG;
+    }
+    const uint32_t nr = ix->n_ref, nl = ix->n_loci, ns = ix->n_species;
+    if (nr == 0 || nl == 0 || ns == 0) { mmlst_set_error("mmlst_index_upload: empty index"); return MMLST_E_ARG; }
+    if (nl > 8192 || ns > 4096) { mmlst_set_error("mmlst_index_upload: more than 8192 loci / 4096 species"); return MMLST_E_RANGE; }
+    // allele rows grouped by locus (counting sort, stable: ascending row inside a locus)
+    std::vector<uint32_t> start(nl + 1, 0), rows(nr);
+    for (uint32_t t = 0; t < nr; ++t) {
+        if (ix->locus_of[t] >= nl) { mmlst_set_error("mmlst_index_upload: locus_of[%u]=%u out of range", t, ix->locus_of[t]); return MMLST_E_ARG; }
+        ++start[ix->locus_of[t] + 1];
+    }
+    for (uint32_t l = 0; l < nl; ++l) {
+        if (ix->species_of_locus[l] >= ns) { mmlst_set_error("mmlst_index_upload: species_of_locus[%u] out of range", l); return MMLST_E_ARG; }
+        start[l + 1] += start[l];
+    }
+    { std::vector<uint32_t> fill(start.begin(), start.end() - 1); for (uint32_t t = 0; t < nr; ++t) rows[fill[ix->locus_of[t]]++] = t; }
+    for (uint32_t t = 0; t < nr; ++t)
+        if (ix->db_off[t + 1] < ix->db_off[t]) { mmlst_set_error("mmlst_index_upload: db_off not ascending at row %u", t); return MMLST_E_ARG; }
+    cudaStream_t s = c->stream;
+    TRY(h2d(c->ix_locus_of, ix->locus_of, nr, s));
+    TRY(h2d(c->ix_locus_rows, rows.data(), nr, s));
+    TRY(h2d(c->ix_locus_start, start.data(), (size_t)nl + 1, s));
+    TRY(h2d(c->ix_allele_num, ix->allele_num, nr, s));
+    TRY(h2d(c->ix_species_of_locus, ix->species_of_locus, nl, s));
+    TRY(h2d(c->ix_genes_in_db, ix->genes_in_db, ns, s));
+    TRY(c->ix_db_ascii.reserve(ix->db_off[nr] + 16));
+    if (ix->db_off[nr]) CUDA_TRY(cudaMemcpyAsync(c->ix_db_ascii.p, ix->db_ascii, ix->db_off[nr], cudaMemcpyHostToDevice, s));
+    TRY(h2d(c->ix_db_off, ix->db_off, (size_t)nr + 1, s));
+    TRY(h2d(c->ix_bam_ln, ix->bam_ln, nr, s));
+    TRY(c->ix_zero64.reserve(((size_t)nr + 1) * 8));
+    CUDA_TRY(cudaMemsetAsync(c->ix_zero64.p, 0, ((size_t)nr + 1) * 8, s));
+    TRY(c->ix_scratch.reserve((size_t)nl * 12 + 64));
+    CUDA_TRY(cudaMemsetAsync(c->ix_scratch.p, 0, (size_t)nl * 12 + 64, s));
+    TRY(c->ix_out.reserve((16 + 5 * (size_t)nl + 8) * 4));
+    TRY(c->ix_db_start.reserve(((size_t)nl + 1) * 8));
+    TRY(c->ix_chunks.reserve(((size_t)nl + 1) * sizeof(mmlst_chunk)));
+    CUDA_TRY(cudaStreamSynchronize(s));   // `rows` / `start` are locals
+    c->ix_bam_ln_h.assign(ix->bam_ln, ix->bam_ln + nr);
+    c->ix_db_off_h.assign(ix->db_off, ix->db_off + nr + 1);
+    c->ix_n_ref = nr; c->ix_n_loci = nl; c->ix_n_species = ns;
+    return MMLST_OK;
+}
+
+extern "C" int mmlst_sample(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* allow, const mmlst_sample_params* prm, mmlst_sample_result* res) {
+    CTX_ENTER(c);
+    if (!soa || !allow || !prm || !res || !res->chosen_tid || !res->chosen_species || !res->col_off || !res->cons || !res->holes || !res->snps) {
+        mmlst_set_error("mmlst_sample: null pointer");
+        return MMLST_E_ARG;
+    }
+    if (!c->ix_n_ref) { mmlst_set_error("mmlst_sample: no index in the context (mmlst_index_upload)"); return MMLST_E_ARG; }
+    if (soa->n_ref != c->ix_n_ref) { mmlst_set_error("mmlst_sample: the stream has %u references, the index %u", soa->n_ref, c->ix_n_ref); return MMLST_E_ARG; }
+    cudaStream_t s = c->stream;
+    const size_t nr = soa->n_ref;
+    const uint32_t nl = c->ix_n_loci;
+    const bool want_tables = res->sum_as && res->n_hit && res->first_idx;
+    mmlst_trace_mark("enter");
+    // ---- stage 1: score stream up (DEFLATE blocks inflated by the hardware engine when the sample carries them), score, select
+    TRY(upload_score_stream(c, soa));
+    TRY(h2d(c->allow, allow, nr, s));
+    const mmlst_score_params sp{prm->minscore, prm->max_xm, prm->min_read_len};
+    TRY(launch_resident_score(c, soa, &sp, c->ix_locus_of.as<uint32_t>()));
+    // output block: header[16] | chosen_tid[nl] | chosen_species[nl] | col_off[nl+1] | holes[nl] | snps[nl]
+    uint32_t* out = c->ix_out.as<uint32_t>();
+    uint32_t* d_hdr = out; uint32_t* d_tid = out + 16; uint32_t* d_sp = d_tid + nl; uint32_t* d_col = d_sp + nl; uint32_t* d_holes = d_col + nl + 1; uint32_t* d_snps = d_holes + nl;
+    const size_t out_words = 16 + 5 * (size_t)nl + 1;
+    const size_t tab_bytes = want_tables ? nr * 16 : 0;
+    const size_t stage1_bytes = (out_words * 4 + tab_bytes + (size_t)c->z_pending * 4 + 63) & ~(size_t)63;
+    TRY(c->pin_reserve(stage1_bytes + res->cons_capacity + 8 * (size_t)nl + 128));   // one reservation: the staging block does not move inside the call
+    uint32_t* h_out = static_cast<uint32_t*>(c->pin);
+    uint8_t* h_tab = reinterpret_cast<uint8_t*>(h_out + out_words);
+    if (want_tables) {   // the selection below does not consume them
+        CUDA_TRY(cudaMemcpyAsync(h_tab, c->sum_as.p, nr * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(h_tab + nr * 8, c->n_hit.p, nr * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(h_tab + nr * 12, c->first_idx.p, nr * 4, cudaMemcpyDeviceToHost, s));
+    }
+    uint32_t* h_zact = reinterpret_cast<uint32_t*>(h_tab + tab_bytes);
+    if (c->z_pending) CUDA_TRY(cudaMemcpyAsync(h_zact, c->zact.p, (size_t)c->z_pending * 4, cudaMemcpyDeviceToHost, s));
+    TRY(mmlst_select_dev(c->sum_as.as<int64_t>(), c->n_hit.as<uint32_t>(), c->first_idx.as<uint32_t>(), c->ix_locus_rows.as<uint32_t>(),
+                         c->ix_locus_start.as<uint32_t>(), c->ix_allele_num.as<uint32_t>(), (uint32_t)nr, c->ix_species_of_locus.as<uint32_t>(),
+                         c->ix_genes_in_db.as<uint32_t>(), nl, c->ix_n_species, prm->penalty, prm->nloci_pct, c->ix_zero64.as<uint64_t>(),
+                         c->ix_bam_ln.as<uint32_t>(), c->ix_db_off.as<uint64_t>(), 512, c->ix_scratch.p, (size_t)nl * 12 + 64, d_hdr, d_tid, d_sp, d_col,
+                         c->ix_db_start.as<uint64_t>(), c->ix_chunks.as<mmlst_chunk>(), nl, 0, c->counters.as<uint64_t>(), nullptr, s));
+    CUDA_TRY(cudaMemcpyAsync(h_out, out, (16 + 3 * (size_t)nl + 1) * 4, cudaMemcpyDeviceToHost, s));
+    mmlst_trace_mark("stage1_enqueued");
+    CUDA_TRY(cudaStreamSynchronize(s));
+    mmlst_trace_mark("stage1_sync");
+    for (uint32_t b = 0; b < c->z_pending; ++b) {
+        if (h_zact[b] != c->zlen[b]) {
+            c->z_pending = 0;
+            mmlst_set_error("mmlst_sample: block %u of the compressed score stream inflated to %u bytes, %u expected (corrupt mmlst_soa.z)", b, h_zact[b], c->zlen[b]);
+            return MMLST_E_ARG;
+        }
+    }
+    c->z_pending = 0;
+    if (want_tables) { memcpy(res->sum_as, h_tab, nr * 8); memcpy(res->n_hit, h_tab + nr * 8, nr * 4); memcpy(res->first_idx, h_tab + nr * 12, nr * 4); }
+    const uint32_t n = h_out[0];
+    res->n_chosen = n; res->error_bits = h_out[3] & 1u;
+    res->total_reads = (uint64_t)h_out[6] | ((uint64_t)h_out[7] << 32);
+    res->ignored_reads = (uint64_t)h_out[8] | ((uint64_t)h_out[9] << 32);
+    if (n > nl) { mmlst_set_error("mmlst_sample: selection returned %u loci of %u", n, nl); return MMLST_E_CUDA; }
+    const uint32_t* h_tid = h_out + 16; const uint32_t* h_sp = h_tid + nl; const uint32_t* h_col = h_sp + nl;
+    memcpy(res->chosen_tid, h_tid, (size_t)n * 4); memcpy(res->chosen_species, h_sp, (size_t)n * 4); memcpy(res->col_off, h_col, ((size_t)n + 1) * 4);
+    if (n == 0 || res->error_bits) { mmlst_trace_flush("mmlst_sample"); return MMLST_OK; }
+    const uint32_t total_cols = h_col[n];
+    if (total_cols > res->cons_capacity) { mmlst_set_error("mmlst_sample: %u consensus bytes, capacity %llu", total_cols, (unsigned long long)res->cons_capacity); return MMLST_E_ARG; }
+    for (uint32_t l = 0; l < n; ++l) {   // H10: metaMLST_functions.py:267/269 index dbSequen[i] for i < BAM LN
+        const uint32_t t = h_tid[l];
+        if (c->ix_bam_ln_h[t] > c->ix_db_off_h[t + 1] - c->ix_db_off_h[t]) {
+            mmlst_set_error("string index out of range: BAM LN %u > DB sequence length %llu for reference %u", c->ix_bam_ln_h[t],
+                            (unsigned long long)(c->ix_db_off_h[t + 1] - c->ix_db_off_h[t]), t);
+            res->bad_len_tid = t;
+            return MMLST_E_RANGE;
+        }
+    }
+    // ---- stage 2: only the chosen contigs' records and plane rows cross the bus (contiguous ranges of the coordinate-sorted stream)
+    auto row_end = [&](uint64_t r) { return soa->p_recs[r].row_off + mmlst_row_words(soa->p_recs[r].nw); };
+    size_t n_rec = 0, n_words = 0;
+    for (uint32_t l = 0; l < n; ++l) {
+        const uint64_t r0 = soa->contig_start[h_tid[l]], r1 = soa->contig_start[h_tid[l] + 1];
+        if (r1 <= r0) continue;
+        n_rec += r1 - r0;
+        n_words += (size_t)row_end(r1 - 1) - soa->p_recs[r0].row_off + 4;
+    }
+    TRY(c->p_recs.reserve(n_rec * sizeof(mmlst_prec) + 64)); TRY(c->planes.reserve(n_words * 4 + 64));
+    std::vector<mmlst_chunk> chunks;
+    const uint32_t kChunkRecords = mmlst_chunk_records(n_rec);
+    size_t rbase = 0, wbase = 0;
+    for (uint32_t l = 0; l < n; ++l) {
+        const uint64_t r0 = soa->contig_start[h_tid[l]], r1 = soa->contig_start[h_tid[l] + 1];
+        const size_t nrc = r1 - r0;
+        if (nrc == 0) continue;
+        const uint32_t w0 = soa->p_recs[r0].row_off, w1 = row_end(r1 - 1);
+        CUDA_TRY(cudaMemcpyAsync(c->p_recs.as<mmlst_prec>() + rbase, soa->p_recs + r0, nrc * sizeof(mmlst_prec), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->planes.as<uint32_t>() + wbase, soa->planes + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, s));
+        for (size_t b = 0; b < nrc; b += kChunkRecords) {
+            mmlst_chunk ck{};
+            ck.rec_begin = (uint32_t)(rbase + b);
+            ck.rec_end = (uint32_t)(rbase + std::min(nrc, b + kChunkRecords));
+            ck.col_base = h_col[l];
+            ck.contig_len = h_col[l + 1] - h_col[l];
+            ck.plane_delta = (uint32_t)wbase - w0;
+            chunks.push_back(ck);
+        }
+        rbase += nrc;
+        wbase += (size_t)(w1 - w0);
+        wbase = (wbase + 3) & ~(size_t)3;
+    }
+    TRY(h2d(c->chunks, chunks.data(), chunks.size(), s));
+    TRY(c->counts.reserve((size_t)total_cols * 20 + 16)); TRY(c->cons.reserve(total_cols + 16));
+    CUDA_TRY(cudaMemsetAsync(c->counts.p, 0, (size_t)total_cols * 20, s));
+    TRY(mmlst_pileup_dev(c->p_recs.as<mmlst_prec>(), c->planes.as<uint32_t>(), c->chunks.as<mmlst_chunk>(), (uint32_t)chunks.size(),
+                         soa->max_row_words, prm->minscore, prm->max_xm, c->counts.as<uint32_t>(), total_cols, prm->pileup_impl, s));
+    TRY(mmlst_consensus_indirect_dev(c->counts.as<uint32_t>(), c->ix_db_ascii.as<uint8_t>(), c->ix_db_start.as<uint64_t>(), d_col, n, d_hdr, prm->mincov,
+                                     c->cons.as<uint8_t>(), d_holes, d_snps, 0, s));
+    uint8_t* h_cons = static_cast<uint8_t*>(c->pin) + stage1_bytes;
+    uint32_t* h_hs = reinterpret_cast<uint32_t*>(h_cons + (((size_t)total_cols + 15) & ~(size_t)15));
+    CUDA_TRY(cudaMemcpyAsync(h_cons, c->cons.p, total_cols, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h_hs, d_holes, 2 * (size_t)nl * 4, cudaMemcpyDeviceToHost, s));
+    mmlst_trace_mark("stage2_enqueued");
+    CUDA_TRY(cudaStreamSynchronize(s));
+    mmlst_trace_mark("stage2_sync");
+    memcpy(res->cons, h_cons, total_cols);
+    memcpy(res->holes, h_hs, (size_t)n * 4);
+    memcpy(res->snps, h_hs + nl, (size_t)n * 4);
+    mmlst_trace_flush("mmlst_sample");
     return MMLST_OK;
 }
 

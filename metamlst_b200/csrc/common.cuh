@@ -46,6 +46,10 @@ int mmlst_cuda_fail(cudaError_t e, const char* what);
 
 int mmlst_num_sms();
 
+// MMLST_TRACE=1: host wall-clock marks inside the host-buffer calls, printed to stderr when the call returns (profiles/tools/e2e_trace.py)
+void mmlst_trace_mark(const char* label);
+void mmlst_trace_flush(const char* call);
+
 // Function attributes (dynamic shared-memory limit, carve-out) and occupancy answers belong to ONE device: caches of "already
 // configured" are indexed by the current device, so that a process driving several GPUs (sample.type_cohort) configures each.
 constexpr int MMLST_MAX_DEVICES = 64;

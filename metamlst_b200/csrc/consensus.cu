@@ -14,10 +14,13 @@ __global__ void __launch_bounds__(CONS_THREADS) consensus_kernel(uint32_t* __res
                                                         uint32_t* __restrict__ holes, uint32_t* __restrict__ snps) {
     const uint32_t locus = blockIdx.x;
     pdl_wait();                  // counts (pileup) and the selection header are complete and visible
-    if (n_loci_dev && locus >= *n_loci_dev) return;
+    // the launch covers max_loci CTAs and all four words exist for every one of them: fetched together, ONE round trip instead of three
+    const uint32_t nl = n_loci_dev ? *n_loci_dev : 0xffffffffu;
     const uint32_t c0 = col_off[locus], c1 = col_off[locus + 1];
+    const unsigned long long dbs = db_start ? db_start[locus] : 0ull;
+    if (locus >= nl) return;
     // DB sequence of the chosen allele: either pre-concatenated (column-aligned) or addressed through db_start[locus]
-    const uint8_t* db_base = db_start ? dbseq + db_start[locus] - c0 : dbseq;
+    const uint8_t* db_base = db_start ? dbseq + dbs - c0 : dbseq;
     uint32_t h = 0, s = 0;
     for (uint32_t col = c0 + threadIdx.x; col < c1; col += blockDim.x) {
         uint32_t* c = counts + static_cast<size_t>(col) * 5;

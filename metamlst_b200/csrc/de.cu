@@ -2,6 +2,7 @@
 #include "de.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -9,8 +10,13 @@
 namespace {
 
 typedef CUresult (*decomp_fn)(CUmemDecompressParams*, size_t, unsigned int, size_t*, CUstream);
-constexpr int kSlices = 8;
-struct Lane { std::mutex m; cudaStream_t s = nullptr; cudaEvent_t ev[kSlices + 1]; bool ready = false; decomp_fn fn = nullptr; int state = 0; };   // state: 0 unknown, 1 ok, -1 absent
+constexpr int kSlices = 32;   // upper bound; the count used is slices_wanted()
+int slices_wanted(int asked) {   // slices a buffer is cut into; MMLST_DE_SLICES=<1..32> overrides the caller's choice (a tuning knob, read per call)
+    const char* e = getenv("MMLST_DE_SLICES");
+    const int n = e ? atoi(e) : asked;
+    return n < 1 ? 1 : (n > kSlices ? kSlices : n);
+}
+struct Lane { std::mutex m; cudaStream_t s = nullptr; cudaEvent_t ev[kSlices + 2]; bool ready = false; decomp_fn fn = nullptr; int state = 0; };   // state: 0 unknown, 1 ok, -1 absent
 Lane g_lane[MMLST_MAX_DEVICES];
 
 int resolve(int device, Lane& lane) {
@@ -49,7 +55,8 @@ int mmlst_de_available(int device) {
 }
 
 int mmlst_h2d_inflate(int device, cudaStream_t st, uint8_t* d_comp, const uint8_t* h_comp, size_t n_bytes,
-                      std::vector<CUmemDecompressParams>& prm, const std::vector<uint64_t>& src_off) {
+                      std::vector<CUmemDecompressParams>& prm, const std::vector<uint64_t>& src_off,
+                      const std::vector<MmlstPlainCopy>* plain, int slices) {
     Lane& lane = g_lane[device % MMLST_MAX_DEVICES];
     std::lock_guard<std::mutex> g(lane.m);
     if (lane.state != 1) { const int rc = resolve(device, lane); if (rc != MMLST_OK) return rc; }
@@ -59,10 +66,12 @@ int mmlst_h2d_inflate(int device, cudaStream_t st, uint8_t* d_comp, const uint8_
         lane.ready = true;
     }
     const uint32_t nb = static_cast<uint32_t>(prm.size());
-    if (nb == 0) return MMLST_OK;
+    const bool has_plain = plain && !plain->empty();
+    if (nb == 0 && !has_plain) return MMLST_OK;
     CUDA_TRY(cudaEventRecord(lane.ev[kSlices], st));
     CUDA_TRY(cudaStreamWaitEvent(lane.s, lane.ev[kSlices], 0));   // d_comp may still be in use by earlier work of `st`
-    const uint32_t per = (nb + kSlices - 1) / kSlices;
+    const uint32_t n_slices = static_cast<uint32_t>(slices_wanted(slices));
+    const uint32_t per = nb ? (nb + n_slices - 1) / n_slices : 1u;
     size_t lo = 0;
     for (uint32_t c = 0, b0 = 0; b0 < nb; ++c, b0 += per) {
         const uint32_t b1 = std::min(nb, b0 + per);
@@ -82,6 +91,14 @@ int mmlst_h2d_inflate(int device, cudaStream_t st, uint8_t* d_comp, const uint8_
             }
         }
     }
+    if (has_plain) {
+        for (const MmlstPlainCopy& pc : *plain)
+            if (pc.bytes) CUDA_TRY(cudaMemcpyAsync(pc.dst, pc.src, pc.bytes, cudaMemcpyHostToDevice, lane.s));
+        CUDA_TRY(cudaEventRecord(lane.ev[kSlices + 1], lane.s));
+        CUDA_TRY(cudaStreamWaitEvent(st, lane.ev[kSlices + 1], 0));
+    }
+    mmlst_trace_mark("slices_enqueued");
     CUDA_TRY(cudaStreamSynchronize(lane.s));   // the lane (and its events) is free for the next call; the host buffer has been read
+    mmlst_trace_mark("copies_done");
     return MMLST_OK;
 }

@@ -10,9 +10,15 @@
 // MMLST_OK when `device` has hardware DEFLATE and the driver exposes the batch call; MMLST_E_CUDA with mmlst_last_error() set otherwise.
 int mmlst_de_available(int device);
 
+struct MmlstPlainCopy { void* dst; const void* src; size_t bytes; };   // host -> device, queued on the copy lane after the compressed slices
+
 // Copy h_comp[0, n_bytes) to d_comp in slices on a per-device copy stream and queue the decompression of every slice's blocks on `st` as the
 // slice lands (copy engine and decompression engine overlap).  prm[b] (src / dst device pointers already set) must be ordered by source
 // offset; src_off[b] = byte offset of block b's payload inside the buffer.  Returns after the LAST copy has finished (the host buffer is
-// free again); the decompression itself is stream-ordered on `st`.
+// free again); the decompression itself is stream-ordered on `st`.  `plain`: further host -> device copies that follow the compressed slices on the
+// copy lane (the part of a stream shipped uncompressed: PCIe carries it while the engine is still inflating); `st` waits for them too.
+// `slices`: every slice costs the engine a ramp, every slice fewer delays its start: 8 for a BAM file (hundreds of MB), 3 for the score stream of
+// one sample (tens of MB; profiles/r2z_e2e_sweep.json).
 int mmlst_h2d_inflate(int device, cudaStream_t st, uint8_t* d_comp, const uint8_t* h_comp, size_t n_bytes,
-                      std::vector<CUmemDecompressParams>& prm, const std::vector<uint64_t>& src_off);
+                      std::vector<CUmemDecompressParams>& prm, const std::vector<uint64_t>& src_off,
+                      const std::vector<MmlstPlainCopy>* plain = nullptr, int slices = 8);

@@ -104,6 +104,13 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
     __shared__ uint32_t s_last;
     const uint32_t l = blockIdx.x;
     const uint32_t r0 = a.locus_start[l], r1 = a.locus_start[l + 1];   // constant table: may be read before the predecessor is done
+    // Any CTA may turn out to be the last one and finalize: each fetches the two small constant tables the finalization walks (species of a locus,
+    // `genes` rows of a species) into shared memory NOW, so that those loads fly under its own reduction instead of opening two dependent round
+    // trips to memory at the very end of the launch.
+    uint32_t* const s_sol = sm + 10 * a.n_loci + 1 + 3 * a.n_species;  // [n_loci] (behind the finalization arrays)
+    uint32_t* const s_gdb = s_sol + a.n_loci;                          // [n_species]
+    for (uint32_t i = threadIdx.x; i < a.n_loci; i += blockDim.x) s_sol[i] = a.species_of_locus[i];
+    for (uint32_t i = threadIdx.x; i < a.n_species; i += blockDim.x) s_gdb[i] = a.genes_in_db[i];
     pdl_wait();                  // the score tables are complete and visible
     pdl_launch_dependents();     // the pileup CTAs may become resident (they wait for THIS grid before reading the chunk list)
     // The first SEL_R x 256 rows of the locus live in registers: ONE round of independent loads (row id, then hit count /
@@ -187,18 +194,24 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
     if (!s_last) return;
     __threadfence();
 
-    // ---- last CTA: finalize
+    // ---- last CTA: finalize.  Two dependent round trips to memory: the per-locus results, then what hangs off the chosen rows
+    // (record range, BAM LN, DB offset); everything else comes from shared memory.
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(sm);   // [n_loci] order key of kept loci, 0 = not kept
     uint32_t* s_tid = sm + 2 * a.n_loci;                                     // [n_loci] chosen row of the locus
     uint32_t* s_cbase = s_tid + a.n_loci;                                    // [n_loci + 1]
     uint32_t* s_len = s_cbase + a.n_loci + 1;                                // [n_loci] BAM LN of chosen rows, output order
     uint32_t* s_nch = s_len + a.n_loci;                                      // [n_loci] chunks of chosen rows, output order
     uint32_t* s_lfirst = s_nch + a.n_loci;                                   // [n_loci]
-    uint32_t* s_detected = s_lfirst + a.n_loci;                              // [n_species]
+    uint32_t* s_q0 = s_lfirst + a.n_loci;                                    // [n_loci] first pileup record of chosen rows, output order
+    uint32_t* s_col = s_q0 + a.n_loci;                                       // [n_loci] first column of chosen rows, output order
+    uint32_t* s_nrec = s_col + a.n_loci;                                     // [n_loci] pileup records of chosen rows, output order
+    uint32_t* s_detected = s_nrec + a.n_loci;                                // [n_species]
     uint32_t* s_first = s_detected + a.n_species;                            // [n_species]
     uint32_t* s_pass = s_first + a.n_species;                                // [n_species]
-    __shared__ uint32_t s_n, s_err, s_cr, s_totch, s_col;
+    __shared__ uint32_t s_n, s_err, s_cr, s_totch;
     __shared__ unsigned long long s_totrec;
+    unsigned long long cnt0 = 0, cnt1 = 0;
+    if (threadIdx.x == 0 && a.counters) { cnt0 = __ldcg(a.counters); cnt1 = __ldcg(a.counters + 1); }   // in flight under everything below
     for (uint32_t i = threadIdx.x; i < a.n_species; i += blockDim.x) { s_detected[i] = 0; s_first[i] = 0xffffffffu; }
     if (threadIdx.x == 0) { s_n = 0; s_err = 0; s_totrec = 0; *a.done = 0; }
     __syncthreads();
@@ -209,14 +222,14 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
         s_lfirst[m] = lf;
         s_key[m] = (ck != ~0ull) ? 1ull : 0ull;  // provisional: detected
         if (ck != ~0ull) {
-            const uint32_t sp = a.species_of_locus[m];
+            const uint32_t sp = s_sol[m];
             atomicAdd(s_detected + sp, 1u);
             atomicMin(s_first + sp, lf);
         }
     }
     __syncthreads();
     for (uint32_t sp = threadIdx.x; sp < a.n_species; sp += blockDim.x) {
-        const uint32_t det = s_detected[sp], tot = a.genes_in_db[sp];
+        const uint32_t det = s_detected[sp], tot = s_gdb[sp];
         uint32_t pass = 0;
         if (det) {
             if (a.flags & MMLST_SELECT_LOCAL) pass = 1;  // this GPU owns a subset of the loci: the gate is applied after the merge
@@ -230,7 +243,7 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
     for (uint32_t m = threadIdx.x; m < a.n_loci; m += blockDim.x) {
         unsigned long long key = 0;
         if (s_key[m]) {
-            const uint32_t sp = a.species_of_locus[m];
+            const uint32_t sp = s_sol[m];
             if (s_pass[sp]) { key = ((static_cast<unsigned long long>(s_first[sp]) << 32) | s_lfirst[m]) + 1ull; atomicAdd(&s_n, 1u); }
         }
         s_key[m] = key;
@@ -239,20 +252,24 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
     for (uint32_t m = threadIdx.x; m < a.n_loci; m += blockDim.x) {
         const unsigned long long key = s_key[m];
         if (!key) continue;
+        const uint32_t tid = s_tid[m];
+        // the only loads that depend on the chosen row: issued together, before the rank is counted
+        const unsigned long long q0 = a.contig_start[tid], q1 = a.contig_start[tid + 1];
+        const uint32_t ln = a.ref_len[tid];
+        const unsigned long long dbo = a.db_off[tid];
         uint32_t rank = 0;
         for (uint32_t j = 0; j < a.n_loci; ++j) {
             const unsigned long long k2 = s_key[j];
             rank += (k2 != 0ull) && ((k2 < key) || (k2 == key && j < m));
         }
-        const uint32_t tid = s_tid[m];
-        const unsigned long long nrec = a.contig_start[tid + 1] - a.contig_start[tid];
         a.chosen_tid[rank] = tid;
-        a.chosen_species[rank] = a.species_of_locus[m];
+        a.chosen_species[rank] = s_sol[m];
         if (a.chosen_first) a.chosen_first[rank] = s_lfirst[m];
-        a.db_start[rank] = a.db_off[tid];
-        s_len[rank] = a.ref_len[tid];
-        s_cbase[rank] = tid;  // parked here until the chunk size is known
-        atomicAdd(&s_totrec, nrec);
+        a.db_start[rank] = dbo;
+        s_len[rank] = ln;
+        s_q0[rank] = static_cast<uint32_t>(q0);
+        s_nrec[rank] = static_cast<uint32_t>(q1 - q0);
+        atomicAdd(&s_totrec, q1 - q0);
     }
     __syncthreads();
     const uint32_t nsel = s_n;
@@ -264,9 +281,7 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
     __syncthreads();
     const uint32_t cr = s_cr;
     for (uint32_t i = threadIdx.x; i < nsel; i += blockDim.x) {
-        const uint32_t tid = s_cbase[i];
-        const unsigned long long nrec = a.contig_start[tid + 1] - a.contig_start[tid];
-        const uint32_t k = static_cast<uint32_t>((nrec + cr - 1) / cr);
+        const uint32_t k = (s_nrec[i] + cr - 1) / cr;
         s_nch[i] = k ? k : 1u;   // a chosen locus without pileup records still gets one (empty) chunk: the fused consensus hangs off the last chunk of a locus
     }
     __syncthreads();
@@ -274,21 +289,19 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
         uint32_t col = 0, nch = 0;
         for (uint32_t i = 0; i < nsel; ++i) {
             a.col_off[i] = col;
-            const uint32_t k = s_nch[i];
-            s_nch[i] = s_cbase[i];  // keep the row id
+            s_col[i] = col;
             s_cbase[i] = nch;
-            nch += k;
+            nch += s_nch[i];
             col += s_len[i];
         }
         a.col_off[nsel] = col;
         s_cbase[nsel] = nch;
-        s_totch = nch; s_col = col;
+        s_totch = nch;
         if (nch > a.max_chunks) s_err |= 2u;
         a.header[0] = nsel; a.header[1] = min(nch, a.max_chunks); a.header[2] = col; a.header[3] = s_err; a.header[4] = cr;
         if (a.counters) {  // totalReads / ignoredReads travel with the header; consumed like the tables
-            const unsigned long long c0 = a.counters[0], c1 = a.counters[1];
-            a.header[6] = static_cast<uint32_t>(c0); a.header[7] = static_cast<uint32_t>(c0 >> 32);
-            a.header[8] = static_cast<uint32_t>(c1); a.header[9] = static_cast<uint32_t>(c1 >> 32);
+            a.header[6] = static_cast<uint32_t>(cnt0); a.header[7] = static_cast<uint32_t>(cnt0 >> 32);
+            a.header[8] = static_cast<uint32_t>(cnt1); a.header[9] = static_cast<uint32_t>(cnt1 >> 32);
             if (a.flags & MMLST_SELECT_CONSUME) { a.counters[0] = 0; a.counters[1] = 0; }
         }
     }
@@ -297,13 +310,12 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
     for (uint32_t c = threadIdx.x; c < nch; c += blockDim.x) {
         uint32_t lo = 0, hi = nsel;  // last i with s_cbase[i] <= c
         while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_cbase[mid] <= c) lo = mid; else hi = mid; }
-        const uint32_t tid = s_nch[lo];
-        const unsigned long long q0 = a.contig_start[tid], q1 = a.contig_start[tid + 1];
+        const unsigned long long q0 = s_q0[lo], q1 = q0 + s_nrec[lo];
         const unsigned long long b = q0 + static_cast<unsigned long long>(c - s_cbase[lo]) * cr;
         mmlst_chunk ck;
         ck.rec_begin = static_cast<uint32_t>(b);
         ck.rec_end = static_cast<uint32_t>(b + cr < q1 ? b + cr : q1);
-        ck.col_base = a.col_off[lo]; ck.contig_len = s_len[lo]; ck.plane_delta = 0;
+        ck.col_base = s_col[lo]; ck.contig_len = s_len[lo]; ck.plane_delta = 0;
         ck.reserved[0] = lo;                              // chosen locus (output order) the chunk belongs to
         ck.reserved[1] = s_cbase[lo + 1] - s_cbase[lo];   // chunks of that locus
         ck.reserved[2] = 0;
@@ -350,7 +362,8 @@ extern "C" int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* firs
     a.db_start = reinterpret_cast<unsigned long long*>(db_start); a.chunks = chunks; a.max_chunks = max_chunks;
     a.chosen_first = chosen_first;
     if (!(flags & MMLST_SELECT_SCRATCH_CLEAN)) CUDA_TRY(cudaMemsetAsync(a.done, 0, 4, s));
-    const size_t smem = sizeof(uint32_t) * (static_cast<size_t>(n_loci) * 7 + 1 + 3 * static_cast<size_t>(n_species)) + 16;
+    // finalization arrays (10 n_loci + 1 + 3 n_species words, see the kernel) + the prefetched species_of_locus / genes_in_db
+    const size_t smem = sizeof(uint32_t) * (static_cast<size_t>(n_loci) * 11 + 1 + 4 * static_cast<size_t>(n_species)) + 16;
     static size_t configured_by_device[MMLST_MAX_DEVICES] = {0};  // 0 = the 48 KB every kernel starts with
     size_t& configured = configured_by_device[mmlst_current_device()];
     if (configured == 0) configured = 48 * 1024;

@@ -14,6 +14,9 @@ class MmlstError(RuntimeError):
         self.code = code
 
 
+E_ARG, E_CUDA, E_IO, E_BAM, E_UNSORTED, E_PAIRED, E_RANGE, E_NOMEM = -1, -2, -3, -4, -5, -6, -7, -8   # include/mmlst.h
+
+
 class Chunk(C.Structure):
     _fields_ = [("rec_begin", C.c_uint32), ("rec_end", C.c_uint32), ("col_base", C.c_uint32), ("contig_len", C.c_uint32),
                 ("plane_delta", C.c_uint32), ("reserved", C.c_uint32 * 3)]
@@ -35,6 +38,27 @@ class ZStream(C.Structure):
 
 class ScoreParams(C.Structure):
     _fields_ = [("minscore", C.c_int), ("max_xm", C.c_int), ("min_read_len", C.c_int)]
+
+
+class Index(C.Structure):   # mmlst_index
+    _fields_ = [("locus_of", C.c_void_p), ("allele_num", C.c_void_p), ("n_ref", C.c_uint32),
+                ("species_of_locus", C.c_void_p), ("n_loci", C.c_uint32),
+                ("genes_in_db", C.c_void_p), ("n_species", C.c_uint32),
+                ("db_ascii", C.c_void_p), ("db_off", C.c_void_p), ("bam_ln", C.c_void_p)]
+
+
+class SampleParams(C.Structure):   # mmlst_sample_params
+    _fields_ = [("minscore", C.c_int), ("max_xm", C.c_int), ("min_read_len", C.c_int), ("penalty", C.c_int), ("nloci_pct", C.c_int),
+                ("mincov", C.c_uint32), ("pileup_impl", C.c_int)]
+
+
+class SampleResult(C.Structure):   # mmlst_sample_result
+    _fields_ = [("n_chosen", C.c_uint32), ("error_bits", C.c_uint32), ("bad_len_tid", C.c_uint32), ("reserved", C.c_uint32),
+                ("total_reads", C.c_uint64), ("ignored_reads", C.c_uint64),
+                ("chosen_tid", C.c_void_p), ("chosen_species", C.c_void_p), ("col_off", C.c_void_p),
+                ("cons", C.c_void_p), ("cons_capacity", C.c_uint64),
+                ("holes", C.c_void_p), ("snps", C.c_void_p),
+                ("sum_as", C.c_void_p), ("n_hit", C.c_void_p), ("first_idx", C.c_void_p)]
 
 
 EXPORTS = {
@@ -129,6 +153,8 @@ EXPORTS = {
     "mmlst_bam_ingest": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mmlst_dev_bam_info": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mmlst_dev_bam_free": (None, [C.c_void_p]),
+    "mmlst_index_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mmlst_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -102,12 +102,15 @@ class SoaHost:
                 s.z = C.addressof(zs)
         return s
 
-    def deflate(self, level: int = 1, block: int = 1 << 16, threads: int = 0, pinned: bool = True) -> "SoaHost":
+    def deflate(self, level: int = 3, block: int = 1 << 16, threads: int = 0, pinned: bool = True, strategy: int = 0,
+                cover: float = 1.0) -> "SoaHost":
         """Attach the DEFLATE-compressed copy of as0[] / xm3[] (include/mmlst.h, mmlst_zstream): the host-buffer path then ships these
         bytes and the device inflates them with the hardware decompression engine.  Done once per sample, like the unpacking; needs the
         run-length form (coordinate-sorted streams).  block = inflated bytes per DEFLATE stream: the engine works on many streams at once,
         64 KiB blocks (a BGZF block's size) run at its full rate, 1 MiB blocks at a third of it (B200: 1.56 ms against 2.56 ms for the
-        120 MB of configs[1]; the plain arrays take 2.40 ms over PCIe; profiles/r2o_e2e_breakdown.json)."""
+        120 MB of configs[1]; the plain arrays take 2.40 ms over PCIe; profiles/r2o_e2e_breakdown.json).  strategy = zlib strategy (0 default,
+        Z_FIXED, Z_RLE, Z_HUFFMAN_ONLY).  cover < 1: only the first `cover` of each array is compressed and the rest crosses PCIe plain, so that
+        the bus keeps working while the engine (the slower of the two on this data) drains its queue."""
         import os
         import zlib
         from concurrent.futures import ThreadPoolExecutor
@@ -117,11 +120,14 @@ class SoaHost:
         jobs = []
         for kind, arr in ((0, np.ascontiguousarray(self.as0).view(np.uint8)), (1, np.ascontiguousarray(self.xm3).view(np.uint8))):
             mv = memoryview(arr)
-            for off in range(0, arr.shape[0], block):
-                jobs.append((kind, off, mv[off:off + block]))
+            stop = arr.shape[0] if cover >= 1.0 else int(arr.shape[0] * max(cover, 0.0)) // block * block
+            for off in range(0, stop, block):
+                jobs.append((kind, off, mv[off:min(off + block, stop)]))
+        if not jobs:
+            return self
 
         def one(job):
-            co = zlib.compressobj(level, zlib.DEFLATED, -15)
+            co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
             return co.compress(job[2]) + co.flush()
         with ThreadPoolExecutor(threads or (os.cpu_count() or 1)) as pool:
             comp = list(pool.map(one, jobs))

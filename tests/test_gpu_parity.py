@@ -527,3 +527,86 @@ def test_device_pipeline_equals_host_selected_path_and_oracle(ctx, case, kernel_
             t = index.name_to_tid[contig]
             want, _ = corc.contig_counts(stab, t, 20, 2 * kw["L"] - 30, 4, 8000)
             assert (seq, holes, snps) == corc.consensus(want, db.row_seq(t).encode(), 1)
+
+
+@pytest.mark.parametrize("case", [dict(seed=91, n_reads=3000, L=100, K=4, orgs=("ecoli", "saureus")),
+                                  dict(seed=92, n_reads=40000, L=150, K=4, orgs=("ecoli",)),
+                                  dict(seed=93, n_reads=60, L=100, K=2, orgs=("ecoli", "saureus", "kpneumoniae"))])
+def test_one_call_sample_over_host_buffers_equals_the_device_pipeline_and_the_two_seams(ctx, case):
+    """mmlst_sample (score -> device selection -> pileup of the chosen contigs -> consensus, host buffers in, results out) against the device-resident
+    pipeline, against mmlst_score + host selection + mmlst_pileup_consensus, and against the oracle; plain, deflated and partly deflated streams."""
+    from metamlst_b200 import devpack, pipeline, synth
+    kw = dict(case)
+    orgs = kw.pop("orgs")
+    db = synth.make_db(orgs, alleles_per_locus=6, n_profiles=10, seed=kw["seed"])
+    gk = dict(read_len=kw["L"], seed=kw["seed"], K=kw["K"], sub_err=0.02)
+    core = synth.gen_core(db, kw["n_reads"], device="cuda:0", **gk)
+    st = devpack.pack_cores(db, [core], 20, 8000)
+    index = api.AlleleIndex(db.ref_names())
+    ms = 2 * kw["L"] - 30
+    soa = st.to_host(pinned=True)
+    sidx = api.SampleIndex(ctx, index, st.ref_lens, db.row_seq)
+    raw = api.score_soa_raw(ctx, soa, index, ms, 4, 50)
+    for nloci in (100, 50):
+        want = pipeline.DevicePipeline(st, index, db.row_seq, minscore=ms, max_xM=4, nloci=nloci).step()
+        got = api.type_soa(sidx, soa, ms, 4, 50, 100, nloci, want_tables=True)
+        assert got["species"] == list(want.items())
+        assert (got["totalReads"], got["ignoredReads"]) == raw[3:]
+        for a, b in zip(got["tables"], raw[:3]):
+            assert np.array_equal(a, b)
+        assert api.type_soa(sidx, soa, ms, 4, 50, 100, nloci)["species"] == got["species"]   # idempotent, tables not asked for
+    # the two seams over the same buffers (host selection has no --nloci gate: compare at nloci=0)
+    chosen = api.fast_select(index, raw[0], raw[1], raw[2], 100)
+    ts = [t for _sp, tt in chosen for t in tt]
+    seqs, holes, snps, _, _ = api.pileup_consensus(ctx, soa, ts, [db.row_seq(t) for t in ts], ms, 4, 1, 0)
+    g0 = api.type_soa(sidx, soa, ms, 4, 50, 100, 0)
+    assert g0["tids"] == ts
+    assert [x for _sp, lst in g0["species"] for x in lst] == [(index.ref_names[t], seqs[i], int(holes[i]), int(snps[i])) for i, t in enumerate(ts)]
+    if soa.run_tid is not None:
+        for cover in (1.0, 0.5, 0.0):
+            soa.deflate(block=4096, pinned=False, cover=cover)
+            assert api.type_soa(sidx, soa, ms, 4, 50, 100, 0)["species"] == g0["species"]
+        soa.z_bytes = soa.z_table = None
+    # species filter: what is not allowed never scores, so it is never chosen
+    f = api.type_soa(sidx, soa, ms, 4, 50, 100, 0, species_filter=orgs[0])
+    assert [sp for sp, _ in f["species"]] == [sp for sp, _ in g0["species"] if sp == orgs[0]]
+    # oracle: consensus of every chosen contig
+    tab = synth.make_sample(db, kw["n_reads"], device="cuda:0", **gk).sorted_by_coord()
+    for sp, lst in g0["species"]:
+        for contig, seq, h, s in lst:
+            t = index.name_to_tid[contig]
+            wc, _ = corc.contig_counts(tab, t, 20, ms, 4, 8000)
+            assert (seq, h, s) == corc.consensus(wc, db.row_seq(t).encode(), 1)
+
+
+def test_one_call_sample_refusals(ctx):
+    from metamlst_b200 import devpack, synth
+    db = synth.make_db(("ecoli",), alleles_per_locus=4, n_profiles=5, seed=5)
+    core = synth.gen_core(db, 2000, device="cuda:0", read_len=100, seed=5, K=2, sub_err=0.01)
+    st = devpack.pack_cores(db, [core], 20, 8000)
+    index = api.AlleleIndex(db.ref_names())
+    soa = st.to_host(pinned=True)
+    other = native.Context(0)
+    try:   # no index in this context
+        bufs = [np.zeros(8192, np.uint32) for _ in range(5)]
+        cons = np.zeros(8192, np.uint8)
+        res = native.SampleResult()
+        res.chosen_tid, res.chosen_species, res.col_off, res.holes, res.snps = (native.ptr(b) for b in bufs)
+        res.cons, res.cons_capacity = native.ptr(cons), 8192
+        prm = native.SampleParams(170, 4, 50, 100, 100, 1, 0)
+        cs = soa.c_struct()
+        allow = index.allow_mask(None)
+        assert native.lib().mmlst_sample(other.handle, C.byref(cs), native.ptr(allow), C.byref(prm), C.byref(res)) == native.E_ARG
+        assert b"mmlst_index_upload" in native.lib().mmlst_last_error()
+    finally:
+        other.close()
+    # H10: a DB sequence shorter than the BAM LN of a chosen reference -> IndexError like metaMLST_functions.py:267
+    sidx = api.SampleIndex(ctx, index, st.ref_lens, lambda t: db.row_seq(t)[:-3])
+    with pytest.raises(IndexError):
+        api.type_soa(sidx, soa, 170, 4)
+    # "Database is broken": more detected loci than `genes` rows for the organism (metamlst.py:188-190)
+    sidx = api.SampleIndex(ctx, index, st.ref_lens, db.row_seq, genes_in_db={"ecoli": 3})
+    with pytest.raises(RuntimeError, match="Database is broken"):
+        api.type_soa(sidx, soa, 170, 4)
+    with pytest.raises(ValueError):
+        api.type_soa(sidx, soa, 170, 255)
