@@ -131,6 +131,16 @@ struct mmlst_ctx {
            ix_out, ix_db_start, ix_chunks;
     uint32_t ix_n_ref = 0, ix_n_loci = 0, ix_n_species = 0;
     std::vector<uint32_t> ix_bam_ln_h; std::vector<uint64_t> ix_db_off_h;
+    // copy lanes: the pileup records of the chosen contigs are ~2 ranges per contig; spread over a few streams their DMA set-up overlaps
+    static constexpr int kLanes = 3;
+    cudaStream_t lane[kLanes] = {nullptr, nullptr, nullptr};
+    cudaEvent_t lane_ev[kLanes + 1] = {nullptr, nullptr, nullptr, nullptr};
+    int lanes_init() {
+        if (lane[0]) return MMLST_OK;
+        for (int i = 0; i < kLanes; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&lane[i], cudaStreamNonBlocking));
+        for (int i = 0; i <= kLanes; ++i) CUDA_TRY(cudaEventCreateWithFlags(&lane_ev[i], cudaEventDisableTiming));
+        return MMLST_OK;
+    }
     void* pin = nullptr; size_t pin_cap = 0;   // page-locked staging for the results of mmlst_sample
     int pin_reserve(size_t bytes) {
         if (bytes <= pin_cap) return MMLST_OK;
@@ -183,6 +193,8 @@ extern "C" void mmlst_destroy(mmlst_ctx* c) {
     cudaSetDevice(c->device);
     for (int i = 0; i < c->n_all; ++i) c->all[i]->release();
     if (c->pin) cudaFreeHost(c->pin);
+    for (int i = 0; i < mmlst_ctx::kLanes; ++i) if (c->lane[i]) cudaStreamDestroy(c->lane[i]);
+    for (int i = 0; i <= mmlst_ctx::kLanes; ++i) if (c->lane_ev[i]) cudaEventDestroy(c->lane_ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -483,16 +495,11 @@ extern "C" int mmlst_pileup_consensus_indirect_dev(const mmlst_prec* recs, const
     return mmlst_consensus_indirect_dev(counts, db_ascii, db_start, col_off, max_loci, header, mincov, cons, holes, snps, flags, stream);
 }
 
-extern "C" int mmlst_pileup_consensus(mmlst_ctx* c, const mmlst_soa* soa, const uint32_t* chosen_tid, uint32_t n_loci,
-                                      const uint8_t* dbseq, const uint32_t* col_off, int minscore, int max_xm,
-                                      uint32_t mincov, int impl, uint32_t* counts, uint8_t* cons, uint32_t* holes,
-                                      uint32_t* snps) {
-    CTX_ENTER(c);
-    if (!soa || !chosen_tid || !dbseq || !col_off || !cons || !holes || !snps) { mmlst_set_error("mmlst_pileup_consensus: null pointer"); return MMLST_E_ARG; }
-    if (n_loci == 0) return MMLST_OK;
+// The pileup records and plane rows of the chosen contigs (contiguous ranges of the coordinate-sorted stream) host -> device, packed one after the
+// other, plus the chunk list over them.  The copies are dealt over the context's copy lanes; `s` continues when all of them have landed.
+static int upload_chosen_contigs(mmlst_ctx* c, const mmlst_soa* soa, const uint32_t* chosen_tid, uint32_t n_loci, const uint32_t* col_off,
+                                 std::vector<mmlst_chunk>& chunks) {
     cudaStream_t s = c->stream;
-    mmlst_trace_mark("enter");
-    // gather the chosen contigs' record / plane ranges (contiguous in the coordinate-sorted stream)
     auto row_end = [&](uint64_t r) { return soa->p_recs[r].row_off + mmlst_row_words(soa->p_recs[r].nw); };
     size_t n_rec = 0, n_words = 0;
     for (uint32_t l = 0; l < n_loci; ++l) {
@@ -503,19 +510,24 @@ extern "C" int mmlst_pileup_consensus(mmlst_ctx* c, const mmlst_soa* soa, const 
         n_rec += r1 - r0;
         n_words += (size_t)row_end(r1 - 1) - soa->p_recs[r0].row_off + 4;  // +4: every range starts 16-byte aligned on the device
     }
-    const uint32_t total_cols = col_off[n_loci];
     TRY(c->p_recs.reserve(n_rec * sizeof(mmlst_prec) + 64)); TRY(c->planes.reserve(n_words * 4 + 64));
-    std::vector<mmlst_chunk> chunks;
+    TRY(c->lanes_init());
+    CUDA_TRY(cudaEventRecord(c->lane_ev[mmlst_ctx::kLanes], s));   // the buffers may still be read by earlier work of `s`
+    for (int i = 0; i < mmlst_ctx::kLanes; ++i) CUDA_TRY(cudaStreamWaitEvent(c->lane[i], c->lane_ev[mmlst_ctx::kLanes], 0));
+    chunks.clear();
     const uint32_t kChunkRecords = mmlst_chunk_records(n_rec);
     size_t rbase = 0, wbase = 0;
+    int k = 0;
     for (uint32_t l = 0; l < n_loci; ++l) {
         const uint32_t t = chosen_tid[l];
         const uint64_t r0 = soa->contig_start[t], r1 = soa->contig_start[t + 1];
         const size_t nr = r1 - r0;
         if (nr == 0) continue;
         const uint32_t w0 = soa->p_recs[r0].row_off, w1 = row_end(r1 - 1);
-        CUDA_TRY(cudaMemcpyAsync(c->p_recs.as<mmlst_prec>() + rbase, soa->p_recs + r0, nr * sizeof(mmlst_prec), cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(c->planes.as<uint32_t>() + wbase, soa->planes + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->p_recs.as<mmlst_prec>() + rbase, soa->p_recs + r0, nr * sizeof(mmlst_prec), cudaMemcpyHostToDevice, c->lane[k]));
+        k = (k + 1) % mmlst_ctx::kLanes;
+        CUDA_TRY(cudaMemcpyAsync(c->planes.as<uint32_t>() + wbase, soa->planes + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, c->lane[k]));
+        k = (k + 1) % mmlst_ctx::kLanes;
         for (size_t b = 0; b < nr; b += kChunkRecords) {
             mmlst_chunk ck{};
             ck.rec_begin = (uint32_t)(rbase + b);
@@ -529,8 +541,27 @@ extern "C" int mmlst_pileup_consensus(mmlst_ctx* c, const mmlst_soa* soa, const 
         wbase += (size_t)(w1 - w0);
         wbase = (wbase + 3) & ~(size_t)3;
     }
-    mmlst_trace_mark("stream_h2d_enqueued");
+    for (int i = 0; i < mmlst_ctx::kLanes; ++i) {
+        CUDA_TRY(cudaEventRecord(c->lane_ev[i], c->lane[i]));
+        CUDA_TRY(cudaStreamWaitEvent(s, c->lane_ev[i], 0));
+    }
     TRY(h2d(c->chunks, chunks.data(), chunks.size(), s));
+    return MMLST_OK;
+}
+
+extern "C" int mmlst_pileup_consensus(mmlst_ctx* c, const mmlst_soa* soa, const uint32_t* chosen_tid, uint32_t n_loci,
+                                      const uint8_t* dbseq, const uint32_t* col_off, int minscore, int max_xm,
+                                      uint32_t mincov, int impl, uint32_t* counts, uint8_t* cons, uint32_t* holes,
+                                      uint32_t* snps) {
+    CTX_ENTER(c);
+    if (!soa || !chosen_tid || !dbseq || !col_off || !cons || !holes || !snps) { mmlst_set_error("mmlst_pileup_consensus: null pointer"); return MMLST_E_ARG; }
+    if (n_loci == 0) return MMLST_OK;
+    cudaStream_t s = c->stream;
+    mmlst_trace_mark("enter");
+    const uint32_t total_cols = col_off[n_loci];
+    std::vector<mmlst_chunk> chunks;
+    TRY(upload_chosen_contigs(c, soa, chosen_tid, n_loci, col_off, chunks));
+    mmlst_trace_mark("stream_h2d_enqueued");
     TRY(h2d(c->dbseq, dbseq, total_cols, s));
     TRY(h2d(c->col_off, col_off, (size_t)n_loci + 1, s));
     TRY(c->counts.reserve((size_t)total_cols * 20 + 16)); TRY(c->cons.reserve(total_cols + 16));
@@ -672,39 +703,8 @@ extern "C" int mmlst_sample(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* a
         }
     }
     // ---- stage 2: only the chosen contigs' records and plane rows cross the bus (contiguous ranges of the coordinate-sorted stream)
-    auto row_end = [&](uint64_t r) { return soa->p_recs[r].row_off + mmlst_row_words(soa->p_recs[r].nw); };
-    size_t n_rec = 0, n_words = 0;
-    for (uint32_t l = 0; l < n; ++l) {
-        const uint64_t r0 = soa->contig_start[h_tid[l]], r1 = soa->contig_start[h_tid[l] + 1];
-        if (r1 <= r0) continue;
-        n_rec += r1 - r0;
-        n_words += (size_t)row_end(r1 - 1) - soa->p_recs[r0].row_off + 4;
-    }
-    TRY(c->p_recs.reserve(n_rec * sizeof(mmlst_prec) + 64)); TRY(c->planes.reserve(n_words * 4 + 64));
     std::vector<mmlst_chunk> chunks;
-    const uint32_t kChunkRecords = mmlst_chunk_records(n_rec);
-    size_t rbase = 0, wbase = 0;
-    for (uint32_t l = 0; l < n; ++l) {
-        const uint64_t r0 = soa->contig_start[h_tid[l]], r1 = soa->contig_start[h_tid[l] + 1];
-        const size_t nrc = r1 - r0;
-        if (nrc == 0) continue;
-        const uint32_t w0 = soa->p_recs[r0].row_off, w1 = row_end(r1 - 1);
-        CUDA_TRY(cudaMemcpyAsync(c->p_recs.as<mmlst_prec>() + rbase, soa->p_recs + r0, nrc * sizeof(mmlst_prec), cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(c->planes.as<uint32_t>() + wbase, soa->planes + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, s));
-        for (size_t b = 0; b < nrc; b += kChunkRecords) {
-            mmlst_chunk ck{};
-            ck.rec_begin = (uint32_t)(rbase + b);
-            ck.rec_end = (uint32_t)(rbase + std::min(nrc, b + kChunkRecords));
-            ck.col_base = h_col[l];
-            ck.contig_len = h_col[l + 1] - h_col[l];
-            ck.plane_delta = (uint32_t)wbase - w0;
-            chunks.push_back(ck);
-        }
-        rbase += nrc;
-        wbase += (size_t)(w1 - w0);
-        wbase = (wbase + 3) & ~(size_t)3;
-    }
-    TRY(h2d(c->chunks, chunks.data(), chunks.size(), s));
+    TRY(upload_chosen_contigs(c, soa, h_tid, n, h_col, chunks));
     TRY(c->counts.reserve((size_t)total_cols * 20 + 16)); TRY(c->cons.reserve(total_cols + 16));
     CUDA_TRY(cudaMemsetAsync(c->counts.p, 0, (size_t)total_cols * 20, s));
     TRY(mmlst_pileup_dev(c->p_recs.as<mmlst_prec>(), c->planes.as<uint32_t>(), c->chunks.as<mmlst_chunk>(), (uint32_t)chunks.size(),

@@ -6,13 +6,15 @@
     type_cohort(bams, "db.sqlite", out_dir, devices=[0, 1, ...])   # the implicit `for bam in cohort: metamlst.py bam`
 
 Structure (not the reference's): a sample is first reduced to a list of `SpeciesCall`s -- one per organism of the score table, each
-holding its `LocusCall`s (contig, consensus, holes, SNPs) -- by one of two engines:
+holding its `LocusCall`s (contig, consensus, holes, SNPs) -- by one of three engines:
 
   engine="device" (default)  BAM -> unpack -> streams.DeviceStreams.from_soa -> pipeline.DevicePipeline.step(): score, selection,
                              pileup and consensus are ONE chain of kernels with a single D2H of the result block; the score tables
                              leave the device only when the `.out` log or the screen text is asked for.  With torch.distributed
                              (one process per GPU) every rank types its record range of the same sample and the integer tables are
                              all-reduced (`mode="ranges"`): the ranks end with identical results, rank 0 writes the files.
+  engine="onecall"           the sample stays in host memory: ONE library call per sample (api.type_soa -> mmlst_sample), only the chosen
+                             contigs' pileup records cross the bus
   engine="host"              the four seams one by one through the host-buffer C-ABI (api.score_soa, api.build_consensus): the
                              path a maintainer gets by rebinding the reference's names.
 
@@ -174,8 +176,8 @@ class SampleTyper:
                  ingest: str = "host"):
         if not os.path.isfile(db_path):
             raise IOError("Failed to connect to the database: please check your database file!")  # metamlst.py:72-73
-        if engine not in ("device", "host"):
-            raise ValueError("engine must be 'device' or 'host'")
+        if engine not in ("device", "host", "onecall"):
+            raise ValueError("engine must be 'device', 'host' or 'onecall'")
         if ingest not in ("device", "host"):
             raise ValueError("ingest must be 'device' (BGZF inflate + record parse on the GPU) or 'host' (C++ threads)")
         self.db_path = db_path
@@ -191,6 +193,8 @@ class SampleTyper:
         self.unpack_threads = int(unpack_threads)
         self._pipe = None          # pipeline.DevicePipeline of the last BAM header seen (a cohort shares one)
         self._pipe_key = None
+        self._sidx = None          # api.SampleIndex of the last BAM header seen (engine="onecall")
+        self._sidx_key = None
         self._alleles: Optional[Dict[str, str]] = None
 
     @property
@@ -335,6 +339,37 @@ class SampleTyper:
             calls.append(call)
         return calls, cel, pipe.total_reads, pipe.ignored_reads, coverage
 
+    def _calls_onecall(self, soa, want_tables: bool, want_cov: bool):
+        """engine="onecall": the sample stays in host memory and goes through ONE library call (api.type_soa -> mmlst_sample): score stream up, score,
+        selection on the device, only the chosen contigs' pileup records up, pileup, consensus, results down."""
+        import numpy as np
+        key = (tuple(soa.ref_names), np.asarray(soa.ref_lens).tobytes())
+        if self._sidx is None or self._sidx_key != key:
+            index = api.AlleleIndex(soa.ref_names)
+            table = self._allele_table()
+            genes_in_db = {sp: len(self._genes(sp)) for sp in dict.fromkeys(index.species)}
+            self._sidx = api.SampleIndex(self.ctx, index, soa.ref_lens, lambda t: table.get(index.ref_names[t]) or "", genes_in_db)
+            self._sidx_key = key
+        sidx = self._sidx
+        try:
+            r = api.type_soa(sidx, soa, self.minscore, self.max_xM, self.min_read_len, self.penalty, self.nloci, self.species_filter, want_tables=want_tables)
+        except RuntimeError as e:
+            if "Database is broken" not in str(e):
+                raise
+            return self._calls_host(soa, want_cov)   # rare: replayed seam by seam, the reference stops at the organism that shows it
+        per_species = dict(r["species"])
+        cel = api.finish_scores(sidx.index, *r["tables"], self.penalty) if want_tables else None
+        coverage = None
+        if want_cov and per_species:
+            coverage = api.coverage_sums(self.ctx, soa, sidx.index, self.minscore, self.max_xM, self.min_read_len, self.species_filter)
+        calls = []
+        for sp in (cel.keys() if cel is not None else per_species.keys()):
+            detected = list(cel[sp].keys()) if cel is not None else [c.split("_")[1] for (c, _s, _h, _n) in per_species[sp]]
+            call = SpeciesCall(sp, self._genes(sp), detected, passed_gate=sp in per_species)
+            call.loci = [LocusCall(c, s, int(h), int(n)) for (c, s, h, n) in per_species.get(sp, [])]
+            calls.append(call)
+        return calls, cel, r["totalReads"], r["ignoredReads"], coverage
+
     def _calls_host_from_cel(self, soa, cel) -> List[SpeciesCall]:
         """Gate, selection (metamlst.py:244) and seam S2 per organism from a finished score table."""
         calls = []
@@ -374,6 +409,8 @@ class SampleTyper:
         want_tables = bool(self.log or want_stdout)
         if self.engine == "device":
             calls, cel, res.total_reads, res.ignored_reads, coverage = self._calls_device(soa, want_tables, want_stdout)
+        elif self.engine == "onecall":
+            calls, cel, res.total_reads, res.ignored_reads, coverage = self._calls_onecall(soa, want_tables, want_stdout)
         else:
             calls, cel, res.total_reads, res.ignored_reads, coverage = self._calls_host(soa, want_stdout)
         t_gpu = time.perf_counter()

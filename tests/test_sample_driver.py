@@ -148,11 +148,11 @@ def test_broken_database_ends_the_sample(oracle_seams, tmp_path):
 
 # ---------------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
-@pytest.mark.parametrize("engine", ["device", "host"])
+@pytest.mark.parametrize("engine", ["device", "host", "onecall"])
 @pytest.mark.parametrize("name", CASES)
 def test_sample_typer_on_gpu_reproduces_reference_files(name, engine, tmp_path):
     """engine="device": BAM -> C++ unpacker -> DeviceStreams.from_soa -> DevicePipeline (one kernel chain, device-side selection);
-    engine="host": the four seams through the host-buffer C-ABI.  Both must leave the reference's bytes."""
+    engine="host": the four seams through the host-buffer C-ABI; engine="onecall": mmlst_sample.  All must leave the reference's bytes."""
     d = os.path.join(GOLDEN, name)
     path = os.path.join(d, "sample.bam")
     typer = sample.SampleTyper(os.path.join(d, "db.sqlite"), device=0, engine=engine, **_params(name))
