@@ -9,10 +9,11 @@ alleles).  A "step" is one full pass of the hot path over that sample.  For N>1 
 disjoint set of loci (contig-aligned shards, 10 M reads each: weak scaling) and the integer tables are all-reduced.
 
   value     : records/s with the packed streams already resident in HBM (CUDA events, max over ranks)
-  e2e       : the same pass through the host-buffer C-ABI (mmlst_score + mmlst_pileup_consensus) from pinned host
-              memory, host<->device copies inside the timed region
+  e2e       : the same pass through the host-buffer C-ABI (mmlst_sample: one call per sample) from pinned host memory,
+              host<->device copies inside the timed region; both streams cross PCIe as DEFLATE blocks inflated by the
+              hardware decompression engine; several samples in flight (api.SampleLanes), one at a time beside it
   roofline  : dominant kernel of the step against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline / --impl reference : the C port of the oracle on the host cores, on a bounded sample
+  cpu_baseline / --impl reference : the C port of the oracle on the host cores, on the WHOLE sample
 The headline mode is the reference's own semantics (pysam max_depth = 8000, "parity mode"); the same sample without
 the htslib depth cap (full 1.5 G-increment histogram) is reported under "uncapped".
 """
@@ -60,6 +61,10 @@ def parse():
                          "ring fed by TMA bulk copies; 'default' = the library's; 'auto' = time all three on the workload first and keep the fastest")
     ap.add_argument("--score-l2-hints", default="default", choices=["default", "0", "1"], help="ring forms of the score kernel: L2 residency hints "
                     "(mmlst_set_score_l2_hints)")
+    ap.add_argument("--e2e-cover", type=float, default=1.0, help="fraction of as0[] / xm3[] shipped as DEFLATE blocks in the `e2e` leg (the rest plain; r3e: with several "
+                    "samples in flight the whole arrays compressed is fastest -- 1.16 ms per sample at 1.0 against 1.24 at 0.95 and 1.32 at 0.9)")
+    ap.add_argument("--e2e-plain-pileup", action="store_true", help="`e2e` leg: ship the chosen contigs' pileup records plain instead of as DEFLATE blocks")
+    ap.add_argument("--e2e-lanes", type=int, default=3, help="samples in flight in the `e2e` leg (api.SampleLanes); 1, 2 and 3 are always timed and reported beside it")
     ap.add_argument("--max-depth", type=int, default=8000, help="htslib pileup depth cap of the main workload (0 = uncapped; profiling aid)")
     return ap.parse_args()
 
@@ -526,7 +531,7 @@ def main():
     t0 = time.perf_counter()
     # once per sample, like the unpacking: as0[] / xm3[] as DEFLATE blocks, inflated on the device by the hardware engine; the last tenth of each
     # array stays plain and rides the bus while the engine (the slower of the two on this data) drains its queue (profiles/r2z_e2e_sweep.json)
-    soa.deflate(cover=0.9)
+    soa.deflate(cover=args.e2e_cover, pileup=not args.e2e_plain_pileup)
     t_deflate = time.perf_counter() - t0
     ctx = native.Context(local)
 
@@ -540,22 +545,28 @@ def main():
     e2e_mode = {"one_call": True}
     sampler.period = float(os.environ.get("MMLST_BENCH_E2E_SAMPLER_PERIOD", "0.1"))
 
+    # (--nloci gate: 100 on one rank; a rank that owns a subset of the loci cannot apply it -- the owner of the merge would, as in pipeline.py)
+    one_call_kw = dict(minscore=PARAMS["minscore"], max_xM=PARAMS["max_xM"], min_read_len=PARAMS["min_read_len"], penalty=PARAMS["penalty"],
+                       nloci=100 if world == 1 else 0, impl=args.pileup_impl)
+
+    def unpack_one_call(r):
+        flat = [x for _sp, lst in r["species"] for x in lst]
+        return r["tids"], [x[1] for x in flat], [x[2] for x in flat], [x[3] for x in flat]
+
     def e2e_step():
         if e2e_mode["one_call"]:
             # ONE library call per sample (mmlst_sample): score stream up + inflate, score, selection on the device, the chosen contigs' pileup records up,
             # pileup, consensus, results down
-            # (--nloci gate: 100 on one rank; a rank that owns a subset of the loci cannot apply it -- the owner of the merge would, as in pipeline.py)
-            r = api.type_soa(sidx, soa, PARAMS["minscore"], PARAMS["max_xM"], PARAMS["min_read_len"], PARAMS["penalty"], 100 if world == 1 else 0,
-                             impl=args.pileup_impl)
-            ts = r["tids"]
-            flat = [x for _sp, lst in r["species"] for x in lst]
-            seqs, holes, snps = [x[1] for x in flat], [x[2] for x in flat], [x[3] for x in flat]
+            ts, seqs, holes, snps = unpack_one_call(api.type_soa(sidx, soa, **one_call_kw))
         else:
             # the two seams as separate calls (mmlst_score -> host selection -> mmlst_pileup_consensus): the reference's own call structure
             cel_raw = api.score_soa_raw(ctx, soa, index, **{k: PARAMS[k] for k in ("minscore", "max_xM", "min_read_len")})
             chosen = api.fast_select(index, cel_raw[0], cel_raw[1], cel_raw[2], PARAMS["penalty"])
             ts = [t for _sp, tt in chosen for t in tt]
             seqs, holes, snps, _, _ = api.pileup_consensus(ctx, soa, ts, [db.row_seq(t) for t in ts], PARAMS["minscore"], PARAMS["max_xM"], 1, args.pileup_impl)
+        return e2e_exchange(ts, seqs, holes, snps)
+
+    def e2e_exchange(ts, seqs, holes, snps):
         mine = {index.ref_names[t]: (seqs[i], int(holes[i]), int(snps[i])) for i, t in enumerate(ts)}
         if world > 1:
             # every rank's result block to every rank: ONE fixed-size all-gather (NCCL) of [n | tid, holes, snps per locus | consensus bytes]
@@ -597,15 +608,41 @@ def main():
         barrier()
         return ts_, (time.perf_counter() - t0_) / n_e2e
 
-    # first the plain form (3 bytes per record cross PCIe), then the two seams as separate calls, then the headline: one call, compressed stream
-    zb, zt = soa.z_bytes, soa.z_table
-    soa.z_bytes = soa.z_table = None
+    def time_e2e_lanes(n_lanes):
+        """The same call with `n_lanes` samples in flight (api.SampleLanes: one context + host thread per lane, the cohort form of the host-buffer path).
+        Every step still moves its own inputs up and its own results down inside the timed region; with N>1 the all-gather of every step's result
+        blocks is issued by this thread in step order while later steps are already running."""
+        sl = api.SampleLanes(local, index, st.ref_lens, db.row_seq, lanes=n_lanes)
+        try:
+            for r in sl.map([soa] * (2 * n_lanes), **one_call_kw):
+                ts_, r0 = e2e_exchange(*unpack_one_call(r))
+                assert r0 == want_e2e, "e2e (lanes) result differs from the device-resident result"
+            n = max(8, n_e2e) * n_lanes
+            barrier()
+            t0_ = time.perf_counter()
+            futs = [sl.submit(soa, **one_call_kw) for _ in range(n)]
+            for f in futs:
+                e2e_exchange(*unpack_one_call(f.result()))
+            barrier()
+            return (time.perf_counter() - t0_) / n
+        finally:
+            sl.close()
+
+    # first the plain form (3 bytes per record cross PCIe), then the two seams as separate calls, then one call per sample with the compressed stream, one
+    # sample at a time; then the headline: the same call with two samples in flight
+    zb, zt, zp3 = soa.z_bytes, soa.z_table, (soa.zp_bytes, soa.zp_table, soa.zp_contig_block)
+    soa.z_bytes = soa.z_table = soa.zp_bytes = soa.zp_table = soa.zp_contig_block = None
     ts_local, dt_plain = time_e2e()
     soa.z_bytes, soa.z_table = zb, zt
+    soa.zp_bytes, soa.zp_table, soa.zp_contig_block = zp3
     e2e_mode["one_call"] = False
     ts_local, dt_seams = time_e2e()
     e2e_mode["one_call"] = True
-    ts_local, dt = time_e2e()
+    ts_local, dt_one = time_e2e()
+    lanes_ms = {}
+    for nl_ in sorted({1, 2, 3, args.e2e_lanes}):
+        lanes_ms[nl_] = time_e2e_lanes(nl_)
+    dt = lanes_ms[args.e2e_lanes]
     clocks = sampler.stop()
     line["clocks"] = clocks
     h2d_plain_score = ((3 * R_local + 6 * int(soa.chunk_run.shape[0]) if soa.chunk_qlen is not None else 5 * R_local + 4 * int(soa.chunk_run.shape[0])) +
@@ -613,30 +650,48 @@ def main():
     z_cov = int((soa.z_table[:, 3] & np.uint64(0xffffffff)).sum())    # bytes of as0[] / xm3[] the DEFLATE blocks stand for; the rest travels plain
     h2d_score_zp = int(soa.z_bytes.shape[0]) + 3 * R_local - z_cov
     h2d = h2d_plain_score - 3 * R_local + h2d_score_zp + 32 * int(soa.z_table.shape[0]) if soa.z_bytes is not None else h2d_plain_score
-    h2d += db.n_rows * 5 + int(sum((st.contig_start[t + 1] - st.contig_start[t]) * 16 for t in ts_local))
+    h2d += db.n_rows * 5
     proff = soa.p_row_off
-    h2d += int(sum(int(proff[int(st.contig_start[t + 1])]) - int(proff[int(st.contig_start[t])]) for t in ts_local)) * 4
+    pileup_plain = int(sum((st.contig_start[t + 1] - st.contig_start[t]) * 16 for t in ts_local)) + \
+        int(sum(int(proff[int(st.contig_start[t + 1])]) - int(proff[int(st.contig_start[t])]) for t in ts_local)) * 4
+    if soa.zp_bytes is not None:   # the chosen contigs' DEFLATE blocks (compressed sizes from the block table)
+        cb, zt_ = soa.zp_contig_block, soa.zp_table
+        pileup_h2d = int(sum(int(((zt_[int(cb[t]):int(cb[t + 1]), 1] >> np.uint64(32)) & np.uint64(0x7fffffff)).sum()) for t in ts_local))
+    else:
+        pileup_h2d = pileup_plain
+    h2d_plain_total_extra = pileup_plain - pileup_h2d   # what the plain / two-seam forms move on top (they ship records and rows uncompressed)
+    h2d += pileup_h2d
     d2h_seams = db.n_rows * 16 + 16 + sum(int(st.ref_lens[t]) for t in ts_local) + 8 * len(ts_local)
     # one call: the selection block (header + chosen rows / species / column offsets), block sizes reported by the decompression engine, consensus, holes, snps
     d2h = (16 + 3 * n_loci + 1) * 4 + 4 * int(soa.z_table.shape[0]) + sum(int(st.ref_lens[t]) for t in ts_local) + 8 * n_loci
     h2d -= db.n_rows * 4    # locus_of[] is resident (mmlst_index_upload); allow[] still travels
-    tt = torch.tensor([dt, float(h2d), float(d2h), dt_plain, dt_seams], dtype=torch.float64, device=device)
+    lane_keys = sorted(lanes_ms)
+    tt = torch.tensor([dt, float(h2d), float(d2h), dt_plain, dt_seams, dt_one] + [lanes_ms[k] for k in lane_keys], dtype=torch.float64, device=device)
     if world > 1:
         mx = tt.clone(); torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.SUM)
-        dt = float(mx[0].item()); dt_plain = float(mx[3].item()); dt_seams = float(mx[4].item())
+        dt = float(mx[0].item()); dt_plain = float(mx[3].item()); dt_seams = float(mx[4].item()); dt_one = float(mx[5].item())
+        lanes_ms = {k: float(mx[6 + i].item()) for i, k in enumerate(lane_keys)}
     line["e2e"] = {"value": R_total / dt, "unit": "records/s", "h2d_bytes_per_step": int(tt[1].item()), "d2h_bytes_per_step": int(tt[2].item()),
-                   "ms_per_step": dt * 1e3, "timing": "host wall clock around the synchronous C-ABI call, barrier on both sides, max over ranks",
+                   "ms_per_step": dt * 1e3, "timing": "host wall clock around the K synchronous C-ABI calls, barrier on both sides, max over ranks",
                    "call": "mmlst_sample (api.type_soa): one call per sample from pinned host buffers -- score stream up, score, selection on the device, pileup records "
                            "of the chosen contigs up, pileup, consensus, results down",
+                   "schedule": "cohort mode, like `value`: %d samples in flight (api.SampleLanes: one context, stream and host thread per lane), so one sample's copies "
+                               "ride the bus while another waits for its selection block or runs its pileup; every step's own H2D and D2H are inside the timed "
+                               "region" % args.e2e_lanes,
+                   "lanes": args.e2e_lanes,
+                   "ms_per_step_by_lanes": {str(k): lanes_ms[k] * 1e3 for k in sorted(lanes_ms)},
+                   "one_at_a_time": {"value": R_total / dt_one, "unit": "records/s", "ms_per_step": dt_one * 1e3,
+                                     "what": "the same call, strictly one sample after another on one context (single-sample latency)"},
                    "two_seam_calls": {"value": R_total / dt_seams, "unit": "records/s", "ms_per_step": dt_seams * 1e3,
                                       "what": "mmlst_score -> host selection -> mmlst_pileup_consensus, the reference's call structure, same compressed stream"},
                    "host_numa_binding": numa, "exchange": "one fixed-size NCCL all-gather of the per-rank result blocks" if world > 1 else "none (one rank)",
-                   "stream_form": "the first 90 %% of as0[] / xm3[] crosses PCIe as DEFLATE blocks and is inflated in HBM by the hardware decompression engine, slice by "
+                   "stream_form": "the first %.0f %% of as0[] / xm3[] crosses PCIe as DEFLATE blocks and is inflated in HBM by the hardware decompression engine, slice by "
                                   "slice behind the copy, the rest plain (%.2f bytes per record in all instead of 3); deflating is part of preparing a sample "
-                                  "(%.2f s here, host threads), like unpacking it" % (h2d_score_zp / max(R_local, 1), t_deflate),
+                                  "(%.2f s here, host threads), like unpacking it; the chosen contigs' pileup records and plane rows cross as DEFLATE "
+                                  "blocks too (%.1f MB instead of %.1f MB per sample)" % (100 * min(max(args.e2e_cover, 0.0), 1.0), h2d_score_zp / max(R_local, 1), t_deflate, pileup_h2d / 1e6, pileup_plain / 1e6),
                    "uncompressed": {"value": R_total / dt_plain, "unit": "records/s", "ms_per_step": dt_plain * 1e3,
-                                    "h2d_bytes_per_step": int(tt[1].item()) + world * (3 * R_local - h2d_score_zp - 32 * int(soa.z_table.shape[0])),
+                                    "h2d_bytes_per_step": int(tt[1].item()) + world * (3 * R_local - h2d_score_zp - 32 * int(soa.z_table.shape[0]) + h2d_plain_total_extra),
                                     "what": "the same call with the plain arrays (3 bytes per record cross PCIe)"}}
     ctx.close()
     del soa

@@ -126,6 +126,11 @@ int mmlst_set_score_variant(int variant);
  * returns the previous value.  MMLST_SCORE_L2_HINTS presets it.  Results do not depend on it. */
 #define MMLST_SCORE_L2_HINTS_DEFAULT 0
 int mmlst_set_score_l2_hints(int on);
+/* Form 6 only: grid size in eighths of one resident wave (8 = exactly one wave; above 8 the surplus CTAs go to whichever SM frees a slot
+ * first, i.e. the hardware balances the tail of the launch).  1..64 sets, other = query; returns the previous value.  MMLST_SCORE_GRID presets
+ * it.  Results do not depend on it. */
+#define MMLST_SCORE_GRID_DEFAULT 8
+int mmlst_set_score_grid_scale(int eighths);
 /* qlen[i] of every record back from the per-chunk form (device; the coverage kernel takes it per record) */
 int mmlst_expand_chunk_qlen_dev(const uint16_t* chunk_qlen, uint64_t n_rec, uint16_t* qlen, void* stream);
 /* tid[i] of every record back from the run arrays (device; the coverage kernel takes the explicit form) */
@@ -340,6 +345,20 @@ typedef struct {
     const uint64_t* table; uint32_t n_blocks;
 } mmlst_zstream;
 
+/* Optional DEFLATE-compressed copy of the PILEUP stream, contig by contig, so that mmlst_sample ships only the chosen contigs' blocks and the hardware
+ * decompression engine writes their records and plane rows in HBM (stage 2 of the call is PCIe-bound too: ~90 bytes per admitted record; plane rows of
+ * reads piled on the same columns repeat each other, records differ in a few fields: they deflate about 2x and 3.5x).  Every contig t with records
+ * owns the blocks contig_block[t] .. contig_block[t+1]: independent raw-DEFLATE streams of at most 4 MiB of output, stored back to back in `bytes` in
+ * table order; table[2b] = byte offset of block b in `bytes`, table[2b+1] = kind << 63 | compressed size << 32 | inflated size, kind 0 = bytes of the
+ * contig's plane rows (planes[row_off of its first record .. row end of its last record)), kind 1 = bytes of its 16-byte records; the blocks of a
+ * kind tile the contig's range in order.  `p_recs` / `planes` stay mandatory: entry points other than mmlst_sample, and devices without the engine,
+ * read them.  Made once per sample by metamlst_b200.packing.SoaHost.deflate(pileup=True). */
+typedef struct {
+    const uint8_t* bytes; uint64_t n_bytes;
+    const uint64_t* table; uint32_t n_blocks;
+    const uint32_t* contig_block;   /* [n_ref + 1] */
+} mmlst_zpileup;
+
 typedef struct {
     /* score stream */
     const uint32_t* tid; const int16_t* as0; const uint8_t* xm3; const uint16_t* qlen; const uint32_t* orig_idx;
@@ -359,6 +378,8 @@ typedef struct {
     const uint16_t* chunk_qlen;
     /* with the run arrays only: as0 / xm3 as DEFLATE blocks (see mmlst_zstream); mmlst_score then reads `as0` / `xm3` only past what the blocks cover */
     const mmlst_zstream* z;
+    /* the pileup stream as DEFLATE blocks per contig (see mmlst_zpileup); read by mmlst_sample only */
+    const mmlst_zpileup* zp;
 } mmlst_soa;
 
 typedef struct { int minscore, max_xm, min_read_len; } mmlst_score_params;

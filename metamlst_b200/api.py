@@ -12,7 +12,9 @@ so that those are bit-identical by construction (H5, H6).
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Sequence, Tuple
+import queue
+from concurrent.futures import Future, ThreadPoolExecutor
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -254,6 +256,45 @@ def type_soa(sidx: SampleIndex, soa: packing.SoaHost, minscore: int = 80, max_xM
         species[-1][1].append((names[int(sidx._tid[i])], cons[int(sidx._col[i]):int(sidx._col[i + 1])].decode("latin-1"), int(sidx._holes[i]), int(sidx._snps[i])))
     return {"species": species, "totalReads": int(res.total_reads), "ignoredReads": int(res.ignored_reads), "tids": [int(t) for t in sidx._tid[:n]],
             "tables": tables}
+
+
+class SampleLanes:
+    """Several samples in flight through the host-buffer path (the cohort form of `type_soa`; `pipeline.CohortLanes` is the same idea for streams that
+    are already resident): `lanes` contexts on one device -- each with its own stream, device buffers, page-locked staging block and resident index
+    (mmlst_index_upload) -- and one host thread per lane inside the synchronous `mmlst_sample` call (ctypes drops the interpreter lock for its duration).
+    While one sample waits for its selection block or runs its pileup, the next one's score stream is already on the bus, so the PCIe link and the
+    decompression engine stay busy across the two synchronisation points of a call.  Results are those of `type_soa`, in submission order."""
+
+    def __init__(self, device: int, index: AlleleIndex, ref_lens: Sequence[int], dbseq_of, lanes: int = 2, genes_in_db: Optional[Dict[str, int]] = None):
+        if lanes < 1:
+            raise ValueError("lanes must be >= 1")
+        self.ctxs = [native.Context(device) for _ in range(lanes)]
+        self.sidx = [SampleIndex(c, index, ref_lens, dbseq_of, genes_in_db) for c in self.ctxs]
+        self._free: "queue.SimpleQueue[SampleIndex]" = queue.SimpleQueue()
+        for s in self.sidx:
+            self._free.put(s)
+        self._pool = ThreadPoolExecutor(max_workers=lanes, thread_name_prefix="mmlst-lane")
+
+    def _one(self, soa: packing.SoaHost, kw: dict):
+        s = self._free.get()
+        try:
+            return type_soa(s, soa, **kw)
+        finally:
+            self._free.put(s)
+
+    def submit(self, soa: packing.SoaHost, **kw) -> Future:
+        """One sample; the Future's result is `type_soa`'s.  Keyword arguments as `type_soa`."""
+        return self._pool.submit(self._one, soa, kw)
+
+    def map(self, soas: Iterable[packing.SoaHost], **kw) -> list:
+        futs = [self.submit(soa, **kw) for soa in soas]
+        return [f.result() for f in futs]
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for c in self.ctxs:
+            c.close()
+        self.ctxs, self.sidx = [], []
 
 
 def build_consensus(ctx: native.Context, soa: packing.SoaHost, chromosomeList: Dict[str, str], filterScore: int, max_xM: int,

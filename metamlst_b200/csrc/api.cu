@@ -123,6 +123,8 @@ struct mmlst_ctx {
     // ST assignment (defineProfile): the `profiles` table grouped by profile, resident across queries
     DevBuf zbuf, zact;                     // compressed score stream + the sizes the decompression engine reports
     std::vector<uint32_t> zlen; uint32_t z_pending = 0;
+    DevBuf zpbuf, zpact;                   // compressed pileup stream of the chosen contigs (mmlst_soa.zp) + the sizes the engine reports
+    std::vector<uint32_t> zplen; uint32_t zp_pending = 0;
     DevBuf prof_start, prof_allele, st_q, st_qn, st_count, st_best, st_nbest, st_out, first_row, row_key;
     uint32_t n_st = 0;
     bool has_row_key = false;
@@ -158,7 +160,7 @@ struct mmlst_ctx {
                        &planes, &chunks, &counts, &dbseq, &col_off, &cons, &holes, &snps, &db_hi,
                        &db_lo, &db_len, &q_hi, &q_lo, &q_len, &blocks, &best, &qhash, &cov_table, &cov, &xr_ids, &xr_x, &xr_bytes, &xq_ids, &xq_x, &xq_bytes,
                        &run_tid, &run_start, &chunk_run, &chunk_qlen, &prof_start, &prof_allele, &st_q, &st_qn, &st_count, &st_best, &st_nbest, &st_out,
-                       &first_row, &row_key, &zbuf, &zact, &ix_locus_of, &ix_locus_rows, &ix_locus_start, &ix_allele_num, &ix_species_of_locus, &ix_genes_in_db, &ix_db_ascii,
+                       &first_row, &row_key, &zbuf, &zact, &zpbuf, &zpact, &ix_locus_of, &ix_locus_rows, &ix_locus_start, &ix_allele_num, &ix_species_of_locus, &ix_genes_in_db, &ix_db_ascii,
                        &ix_db_off, &ix_bam_ln, &ix_zero64, &ix_scratch, &ix_out, &ix_db_start, &ix_chunks};
         for (DevBuf* b : l) all[n_all++] = b;
     }
@@ -498,7 +500,7 @@ extern "C" int mmlst_pileup_consensus_indirect_dev(const mmlst_prec* recs, const
 // The pileup records and plane rows of the chosen contigs (contiguous ranges of the coordinate-sorted stream) host -> device, packed one after the
 // other, plus the chunk list over them.  The copies are dealt over the context's copy lanes; `s` continues when all of them have landed.
 static int upload_chosen_contigs(mmlst_ctx* c, const mmlst_soa* soa, const uint32_t* chosen_tid, uint32_t n_loci, const uint32_t* col_off,
-                                 std::vector<mmlst_chunk>& chunks) {
+                                 std::vector<mmlst_chunk>& chunks, bool use_zp = false) {
     cudaStream_t s = c->stream;
     auto row_end = [&](uint64_t r) { return soa->p_recs[r].row_off + mmlst_row_words(soa->p_recs[r].nw); };
     size_t n_rec = 0, n_words = 0;
@@ -511,6 +513,82 @@ static int upload_chosen_contigs(mmlst_ctx* c, const mmlst_soa* soa, const uint3
         n_words += (size_t)row_end(r1 - 1) - soa->p_recs[r0].row_off + 4;  // +4: every range starts 16-byte aligned on the device
     }
     TRY(c->p_recs.reserve(n_rec * sizeof(mmlst_prec) + 64)); TRY(c->planes.reserve(n_words * 4 + 64));
+    c->zp_pending = 0;
+    if (use_zp && soa->zp && soa->zp->n_blocks && mmlst_de_available(c->device) == MMLST_OK) {
+        // compressed form: the chosen contigs' DEFLATE blocks cross the bus, the hardware decompression engine writes the records and plane rows in HBM
+        const mmlst_zpileup* z = soa->zp;
+        if (!z->bytes || !z->table || !z->contig_block) { mmlst_set_error("mmlst_soa.zp: null pointer"); return MMLST_E_ARG; }
+        std::vector<MmlstSegment> segs;
+        std::vector<uint32_t> first_block(1, 0u);
+        std::vector<CUmemDecompressParams> prm;
+        size_t zbytes = 0, nb = 0;
+        for (uint32_t l = 0; l < n_loci; ++l) {
+            const uint32_t t = chosen_tid[l];
+            if (soa->contig_start[t + 1] <= soa->contig_start[t]) continue;
+            const uint32_t b0 = z->contig_block[t], b1 = z->contig_block[t + 1];
+            if (b0 >= b1 || b1 > z->n_blocks) { mmlst_set_error("mmlst_soa.zp: contig %u has records but no blocks", t); return MMLST_E_ARG; }
+            const uint64_t s0 = z->table[2 * (size_t)b0], s1 = z->table[2 * (size_t)(b1 - 1)] + ((z->table[2 * (size_t)(b1 - 1) + 1] >> 32) & 0x7fffffffull);
+            if (s1 < s0 || s1 > z->n_bytes) { mmlst_set_error("mmlst_soa.zp: blocks of contig %u out of range", t); return MMLST_E_ARG; }
+            zbytes += ((s1 - s0) + 63) & ~(size_t)63;
+            nb += b1 - b0;
+        }
+        TRY(c->zpbuf.reserve(zbytes + 64)); TRY(c->zpact.reserve(nb * 4 + 4));
+        prm.resize(nb);
+        memset(prm.data(), 0, sizeof(CUmemDecompressParams) * nb);
+        c->zplen.resize(nb);
+        chunks.clear();
+        const uint32_t kChunkRecords = mmlst_chunk_records(n_rec);
+        size_t rbase = 0, wbase = 0, zoff = 0, q = 0;
+        for (uint32_t l = 0; l < n_loci; ++l) {
+            const uint32_t t = chosen_tid[l];
+            const uint64_t r0 = soa->contig_start[t], r1 = soa->contig_start[t + 1];
+            const size_t nr = r1 - r0;
+            if (nr == 0) continue;
+            const uint32_t w0 = soa->p_recs[r0].row_off, w1 = row_end(r1 - 1);
+            const uint32_t b0 = z->contig_block[t], b1 = z->contig_block[t + 1];
+            const uint64_t s0 = z->table[2 * (size_t)b0], s1 = z->table[2 * (size_t)(b1 - 1)] + ((z->table[2 * (size_t)(b1 - 1) + 1] >> 32) & 0x7fffffffull);
+            segs.push_back({c->zpbuf.as<uint8_t>() + zoff, z->bytes + s0, (size_t)(s1 - s0)});
+            size_t done[2] = {0, 0};   // inflated bytes of the contig's plane rows / records placed so far
+            for (uint32_t b = b0; b < b1; ++b, ++q) {
+                const uint64_t off = z->table[2 * (size_t)b], w = z->table[2 * (size_t)b + 1];
+                const unsigned kind = (unsigned)(w >> 63);
+                const uint64_t clen = (w >> 32) & 0x7fffffffull, ulen = w & 0xffffffffull;
+                const size_t cap = kind ? nr * sizeof(mmlst_prec) : (size_t)(w1 - w0) * 4;
+                if (off < s0 || off + clen > s1 || (b > b0 && off < z->table[2 * (size_t)(b - 1)]) || done[kind] + ulen > cap || ulen > (4u << 20)) {
+                    mmlst_set_error("mmlst_soa.zp: block %u of contig %u out of range / out of order", b, t);
+                    return MMLST_E_ARG;
+                }
+                prm[q].srcNumBytes = clen; prm[q].dstNumBytes = ulen; prm[q].dstActBytes = c->zpact.as<cuuint32_t>() + q;
+                prm[q].src = c->zpbuf.as<uint8_t>() + zoff + (off - s0);
+                prm[q].dst = kind ? reinterpret_cast<uint8_t*>(c->p_recs.as<mmlst_prec>() + rbase) + done[1] : reinterpret_cast<uint8_t*>(c->planes.as<uint32_t>() + wbase) + done[0];
+                prm[q].algo = CU_MEM_DECOMPRESS_ALGORITHM_DEFLATE;
+                c->zplen[q] = (uint32_t)ulen;
+                done[kind] += ulen;
+            }
+            if (done[0] != (size_t)(w1 - w0) * 4 || done[1] != nr * sizeof(mmlst_prec)) {
+                mmlst_set_error("mmlst_soa.zp: the blocks of contig %u inflate to %zu + %zu bytes, the stream has %zu + %zu", t, done[0], done[1], (size_t)(w1 - w0) * 4, nr * sizeof(mmlst_prec));
+                return MMLST_E_ARG;
+            }
+            first_block.push_back((uint32_t)q);
+            zoff += ((size_t)(s1 - s0) + 63) & ~(size_t)63;
+            for (size_t b = 0; b < nr; b += kChunkRecords) {
+                mmlst_chunk ck{};
+                ck.rec_begin = (uint32_t)(rbase + b);
+                ck.rec_end = (uint32_t)(rbase + std::min(nr, b + kChunkRecords));
+                ck.col_base = col_off[l];
+                ck.contig_len = col_off[l + 1] - col_off[l];
+                ck.plane_delta = (uint32_t)wbase - w0;
+                chunks.push_back(ck);
+            }
+            rbase += nr;
+            wbase += (size_t)(w1 - w0);
+            wbase = (wbase + 3) & ~(size_t)3;
+        }
+        TRY(h2d(c->chunks, chunks.data(), chunks.size(), s));   // ahead of the blocks on `s`: tiny, and `s` is idle until the first group lands
+        TRY(mmlst_h2d_inflate_segments(c->device, s, segs, prm, first_block, 6));
+        c->zp_pending = (uint32_t)nb;
+        return MMLST_OK;
+    }
     TRY(c->lanes_init());
     CUDA_TRY(cudaEventRecord(c->lane_ev[mmlst_ctx::kLanes], s));   // the buffers may still be read by earlier work of `s`
     for (int i = 0; i < mmlst_ctx::kLanes; ++i) CUDA_TRY(cudaStreamWaitEvent(c->lane[i], c->lane_ev[mmlst_ctx::kLanes], 0));
@@ -655,7 +733,7 @@ extern "C" int mmlst_sample(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* a
     const size_t out_words = 16 + 5 * (size_t)nl + 1;
     const size_t tab_bytes = want_tables ? nr * 16 : 0;
     const size_t stage1_bytes = (out_words * 4 + tab_bytes + (size_t)c->z_pending * 4 + 63) & ~(size_t)63;
-    TRY(c->pin_reserve(stage1_bytes + res->cons_capacity + 8 * (size_t)nl + 128));   // one reservation: the staging block does not move inside the call
+    TRY(c->pin_reserve(stage1_bytes + res->cons_capacity + 8 * (size_t)nl + (soa->zp ? (size_t)soa->zp->n_blocks * 4 : 0) + 256));   // one reservation: the staging block does not move inside the call
     uint32_t* h_out = static_cast<uint32_t*>(c->pin);
     uint8_t* h_tab = reinterpret_cast<uint8_t*>(h_out + out_words);
     if (want_tables) {   // the selection below does not consume them
@@ -704,20 +782,31 @@ extern "C" int mmlst_sample(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* a
     }
     // ---- stage 2: only the chosen contigs' records and plane rows cross the bus (contiguous ranges of the coordinate-sorted stream)
     std::vector<mmlst_chunk> chunks;
-    TRY(upload_chosen_contigs(c, soa, h_tid, n, h_col, chunks));
+    TRY(upload_chosen_contigs(c, soa, h_tid, n, h_col, chunks, true));
     TRY(c->counts.reserve((size_t)total_cols * 20 + 16)); TRY(c->cons.reserve(total_cols + 16));
     CUDA_TRY(cudaMemsetAsync(c->counts.p, 0, (size_t)total_cols * 20, s));
     TRY(mmlst_pileup_dev(c->p_recs.as<mmlst_prec>(), c->planes.as<uint32_t>(), c->chunks.as<mmlst_chunk>(), (uint32_t)chunks.size(),
                          soa->max_row_words, prm->minscore, prm->max_xm, c->counts.as<uint32_t>(), total_cols, prm->pileup_impl, s));
     TRY(mmlst_consensus_indirect_dev(c->counts.as<uint32_t>(), c->ix_db_ascii.as<uint8_t>(), c->ix_db_start.as<uint64_t>(), d_col, n, d_hdr, prm->mincov,
                                      c->cons.as<uint8_t>(), d_holes, d_snps, 0, s));
+    const size_t hs_off = stage1_bytes + (((size_t)total_cols + 15) & ~(size_t)15);
     uint8_t* h_cons = static_cast<uint8_t*>(c->pin) + stage1_bytes;
-    uint32_t* h_hs = reinterpret_cast<uint32_t*>(h_cons + (((size_t)total_cols + 15) & ~(size_t)15));
+    uint32_t* h_hs = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(c->pin) + hs_off);
+    uint32_t* h_zpact = h_hs + 2 * (size_t)nl;
     CUDA_TRY(cudaMemcpyAsync(h_cons, c->cons.p, total_cols, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(h_hs, d_holes, 2 * (size_t)nl * 4, cudaMemcpyDeviceToHost, s));
+    if (c->zp_pending) CUDA_TRY(cudaMemcpyAsync(h_zpact, c->zpact.p, (size_t)c->zp_pending * 4, cudaMemcpyDeviceToHost, s));
     mmlst_trace_mark("stage2_enqueued");
     CUDA_TRY(cudaStreamSynchronize(s));
     mmlst_trace_mark("stage2_sync");
+    for (uint32_t b = 0; b < c->zp_pending; ++b) {
+        if (h_zpact[b] != c->zplen[b]) {
+            c->zp_pending = 0;
+            mmlst_set_error("mmlst_sample: block %u of the compressed pileup stream inflated to %u bytes, %u expected (corrupt mmlst_soa.zp)", b, h_zpact[b], c->zplen[b]);
+            return MMLST_E_ARG;
+        }
+    }
+    c->zp_pending = 0;
     memcpy(res->cons, h_cons, total_cols);
     memcpy(res->holes, h_hs, (size_t)n * 4);
     memcpy(res->snps, h_hs + nl, (size_t)n * 4);

@@ -102,3 +102,54 @@ int mmlst_h2d_inflate(int device, cudaStream_t st, uint8_t* d_comp, const uint8_
     mmlst_trace_mark("copies_done");
     return MMLST_OK;
 }
+
+
+int mmlst_h2d_inflate_segments(int device, cudaStream_t st, const std::vector<MmlstSegment>& segs, std::vector<CUmemDecompressParams>& prm,
+                               const std::vector<uint32_t>& first_block, int groups) {
+    Lane& lane = g_lane[device % MMLST_MAX_DEVICES];
+    std::lock_guard<std::mutex> g(lane.m);
+    if (lane.state != 1) { const int rc = resolve(device, lane); if (rc != MMLST_OK) return rc; }
+    if (!lane.ready) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&lane.s, cudaStreamNonBlocking));
+        for (auto& e : lane.ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        lane.ready = true;
+    }
+    const uint32_t ns = static_cast<uint32_t>(segs.size());
+    if (ns == 0) return MMLST_OK;
+    if (first_block.size() != segs.size() + 1 || first_block.back() != prm.size()) { mmlst_set_error("mmlst_h2d_inflate_segments: block ranges do not match"); return MMLST_E_ARG; }
+    CUDA_TRY(cudaEventRecord(lane.ev[kSlices], st));
+    CUDA_TRY(cudaStreamWaitEvent(lane.s, lane.ev[kSlices], 0));   // the destination buffers may still be in use by earlier work of `st`
+    const uint32_t n_groups = static_cast<uint32_t>(std::min<int>(std::max(groups, 1), kSlices));
+    // groups of about equal compressed size, whole segments each
+    size_t total = 0;
+    for (const MmlstSegment& sg : segs) total += sg.bytes;
+    const size_t per = (total + n_groups - 1) / n_groups;
+    uint32_t i = 0, ev = 0;
+    while (i < ns) {
+        const uint32_t i0 = i;
+        size_t acc = 0;
+        while (i < ns && (acc == 0 || acc + segs[i].bytes <= per || ev + 1 == n_groups)) {
+            if (segs[i].bytes) CUDA_TRY(cudaMemcpyAsync(segs[i].d_dst, segs[i].h_src, segs[i].bytes, cudaMemcpyHostToDevice, lane.s));
+            acc += segs[i].bytes;
+            ++i;
+        }
+        CUDA_TRY(cudaEventRecord(lane.ev[ev], lane.s));
+        CUDA_TRY(cudaStreamWaitEvent(st, lane.ev[ev], 0));
+        ev = std::min(ev + 1, n_groups - 1);
+        const uint32_t b0 = first_block[i0], b1 = first_block[i];
+        for (uint32_t q0 = b0; q0 < b1; q0 += 1u << 16) {
+            const size_t cnt = std::min<size_t>(1u << 16, b1 - q0);
+            size_t bad = static_cast<size_t>(-1);
+            const CUresult rc = lane.fn(prm.data() + q0, cnt, 0, &bad, reinterpret_cast<CUstream>(st));
+            if (rc != CUDA_SUCCESS) {
+                mmlst_set_error("cuMemBatchDecompressAsync failed (CUresult %d) at block %lld", static_cast<int>(rc),
+                                bad == static_cast<size_t>(-1) ? -1ll : static_cast<long long>(q0 + bad));
+                return MMLST_E_CUDA;
+            }
+        }
+    }
+    mmlst_trace_mark("segments_enqueued");
+    CUDA_TRY(cudaStreamSynchronize(lane.s));   // the lane is free for the next call; the host buffer has been read
+    mmlst_trace_mark("segment_copies_done");
+    return MMLST_OK;
+}

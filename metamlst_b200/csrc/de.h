@@ -22,3 +22,10 @@ struct MmlstPlainCopy { void* dst; const void* src; size_t bytes; };   // host -
 int mmlst_h2d_inflate(int device, cudaStream_t st, uint8_t* d_comp, const uint8_t* h_comp, size_t n_bytes,
                       std::vector<CUmemDecompressParams>& prm, const std::vector<uint64_t>& src_off,
                       const std::vector<MmlstPlainCopy>* plain = nullptr, int slices = 8);
+
+// The same for compressed bytes that are NOT one contiguous host range (the chosen contigs of a compressed pileup stream): segment i is
+// h_src[i] .. + bytes[i] -> d_dst[i], and owns the blocks prm[first_block[i] .. first_block[i+1]) (src / dst device pointers already set).  The
+// segments are dealt over at most `groups` copy/decompress rounds; returns after the last copy has finished.
+struct MmlstSegment { uint8_t* d_dst; const uint8_t* h_src; size_t bytes; };
+int mmlst_h2d_inflate_segments(int device, cudaStream_t st, const std::vector<MmlstSegment>& segs, std::vector<CUmemDecompressParams>& prm,
+                               const std::vector<uint32_t>& first_block, int groups = 6);

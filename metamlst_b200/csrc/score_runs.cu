@@ -45,6 +45,23 @@ extern "C" int mmlst_set_score_l2_hints(int on) {
     return prev;
 }
 
+// Grid of the ring forms in eighths of one resident wave (8 = exactly one wave, the blocked distribution without a tail; more = the hardware
+// hands the extra CTAs to whichever SM finishes first).  MMLST_SCORE_GRID presets it, mmlst_set_score_grid_scale changes it.
+static int g_score_grid8 = -1;
+static int score_grid8() {
+    if (g_score_grid8 < 0) {
+        const char* e = getenv("MMLST_SCORE_GRID");
+        const int v = e ? atoi(e) : 0;
+        g_score_grid8 = (v >= 1 && v <= 64) ? v : MMLST_SCORE_GRID_DEFAULT;
+    }
+    return g_score_grid8;
+}
+extern "C" int mmlst_set_score_grid_scale(int eighths) {
+    const int prev = score_grid8();
+    if (eighths >= 1 && eighths <= 64) g_score_grid8 = eighths;
+    return prev;
+}
+
 static int score_runs_launch(const uint32_t* run_tid, const uint32_t* run_start, uint32_t n_runs, const uint32_t* chunk_run,
                              const int16_t* as0, const uint8_t* xm3, const uint16_t* qlen, const uint16_t* chunk_qlen, const uint32_t* orig_idx,
                              uint64_t n_rec, uint64_t idx_base, const uint8_t* allow, uint32_t n_ref, int minscore,
@@ -79,7 +96,7 @@ static int score_runs_launch(const uint32_t* run_tid, const uint32_t* run_start,
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, score_runs_ring_pair_kernel, kThreads, smem) != cudaSuccess || r < 1) r = 1;
             pair_resident = r;
         }
-        const uint64_t cap = static_cast<uint64_t>(mmlst_num_sms()) * pair_resident;
+        const uint64_t cap = static_cast<uint64_t>(mmlst_num_sms()) * pair_resident * score_grid8() / 8;
         if (want > cap) want = cap;
         if (want < 1) want = 1;
         score_runs_ring_pair_kernel<<<static_cast<unsigned>(want), kThreads, smem, st>>>(a);

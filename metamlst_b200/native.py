@@ -29,11 +29,15 @@ class Soa(C.Structure):
                 ("planes", C.c_void_p), ("n_prec", C.c_uint64), ("n_plane_words", C.c_uint64), ("max_row_words", C.c_uint32),
                 ("contig_start", C.c_void_p), ("n_ref", C.c_uint32),
                 ("n_runs", C.c_uint32), ("run_tid", C.c_void_p), ("run_start", C.c_void_p), ("chunk_run", C.c_void_p),
-                ("chunk_qlen", C.c_void_p), ("z", C.c_void_p)]
+                ("chunk_qlen", C.c_void_p), ("z", C.c_void_p), ("zp", C.c_void_p)]
 
 
 class ZStream(C.Structure):
     _fields_ = [("bytes", C.c_void_p), ("n_bytes", C.c_uint64), ("table", C.c_void_p), ("n_blocks", C.c_uint32)]
+
+
+class ZPileup(C.Structure):   # mmlst_zpileup
+    _fields_ = [("bytes", C.c_void_p), ("n_bytes", C.c_uint64), ("table", C.c_void_p), ("n_blocks", C.c_uint32), ("contig_block", C.c_void_p)]
 
 
 class ScoreParams(C.Structure):
@@ -84,6 +88,7 @@ EXPORTS = {
     "mmlst_inflate_raw": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "mmlst_set_score_variant": (C.c_int, [C.c_int]),
     "mmlst_set_score_l2_hints": (C.c_int, [C.c_int]),
+    "mmlst_set_score_grid_scale": (C.c_int, [C.c_int]),
     "mmlst_set_pdl": (C.c_int, [C.c_int]),
     "mmlst_expand_runs_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mmlst_coverage_table_slots": (C.c_uint64, [C.c_uint64]),

@@ -56,6 +56,9 @@ class SoaHost:
     chunk_qlen: Optional[np.ndarray] = None  # u16 per 256-record chunk when every chunk has one len(SEQ) (3 B / record form)
     z_bytes: Optional[np.ndarray] = None     # DEFLATE blocks of as0[] / xm3[] (mmlst_zstream) + their table [n_blocks][4] u64: deflate()
     z_table: Optional[np.ndarray] = None
+    zp_bytes: Optional[np.ndarray] = None    # DEFLATE blocks of the pileup stream, contig by contig (mmlst_zpileup): deflate(pileup=True)
+    zp_table: Optional[np.ndarray] = None    # [n_blocks][2] u64
+    zp_contig_block: Optional[np.ndarray] = None   # [n_ref + 1] u32
 
     @property
     def n_rec(self) -> int:
@@ -100,21 +103,31 @@ class SoaHost:
                 zs = native.ZStream(native.ptr(self.z_bytes), int(self.z_bytes.shape[0]), native.ptr(self.z_table), int(self.z_table.shape[0]))
                 s._zs = zs  # kept alive by the struct that points at it
                 s.z = C.addressof(zs)
+        if self.zp_bytes is not None:
+            zp = native.ZPileup(native.ptr(self.zp_bytes), int(self.zp_bytes.shape[0]), native.ptr(self.zp_table), int(self.zp_table.shape[0]),
+                                native.ptr(self.zp_contig_block))
+            s._zp = zp
+            s.zp = C.addressof(zp)
         return s
 
     def deflate(self, level: int = 3, block: int = 1 << 16, threads: int = 0, pinned: bool = True, strategy: int = 0,
-                cover: float = 1.0) -> "SoaHost":
+                cover: float = 1.0, pileup: bool = False) -> "SoaHost":
         """Attach the DEFLATE-compressed copy of as0[] / xm3[] (include/mmlst.h, mmlst_zstream): the host-buffer path then ships these
         bytes and the device inflates them with the hardware decompression engine.  Done once per sample, like the unpacking; needs the
         run-length form (coordinate-sorted streams).  block = inflated bytes per DEFLATE stream: the engine works on many streams at once,
         64 KiB blocks (a BGZF block's size) run at its full rate, 1 MiB blocks at a third of it (B200: 1.56 ms against 2.56 ms for the
         120 MB of configs[1]; the plain arrays take 2.40 ms over PCIe; profiles/r2o_e2e_breakdown.json).  strategy = zlib strategy (0 default,
         Z_FIXED, Z_RLE, Z_HUFFMAN_ONLY).  cover < 1: only the first `cover` of each array is compressed and the rest crosses PCIe plain, so that
-        the bus keeps working while the engine (the slower of the two on this data) drains its queue."""
+        the bus keeps working while the engine (the slower of the two on this data) drains its queue.  pileup=True additionally attaches the pileup
+        stream as DEFLATE blocks per contig (mmlst_zpileup: `mmlst_sample` then ships the chosen contigs' blocks instead of their records and
+        plane rows)."""
         import os
         import zlib
         from concurrent.futures import ThreadPoolExecutor
         self.z_bytes = self.z_table = None
+        self.zp_bytes = self.zp_table = self.zp_contig_block = None
+        if pileup and self.n_prec:
+            self._deflate_pileup(level, block, threads, pinned, strategy)
         if self.run_tid is None or self.n_rec == 0:
             return self
         jobs = []
@@ -144,6 +157,43 @@ class SoaHost:
             z = t.numpy()
         self.z_bytes, self.z_table = z, table
         return self
+
+    def _deflate_pileup(self, level: int, block: int, threads: int, pinned: bool, strategy: int) -> None:
+        import os
+        import zlib
+        from concurrent.futures import ThreadPoolExecutor
+        cs = np.asarray(self.contig_start, dtype=np.int64)
+        recs = np.ascontiguousarray(self.p_recs)
+        rec_bytes = memoryview(recs.view(np.uint8).reshape(-1))
+        plane_bytes = memoryview(np.ascontiguousarray(self.planes).view(np.uint8).reshape(-1))
+        row_off = recs["row_off"].astype(np.int64)             # first plane word of every record
+        row_end = row_off + row_words(recs["nw"]).astype(np.int64)
+        jobs = []          # (contig, kind, bytes)
+        per_contig = np.zeros(len(cs), np.int64)
+        for t in np.nonzero(cs[1:] > cs[:-1])[0]:
+            r0, r1 = int(cs[t]), int(cs[t + 1])
+            for kind, mv, lo, hi in ((0, plane_bytes, int(row_off[r0]) * 4, int(row_end[r1 - 1]) * 4), (1, rec_bytes, r0 * 16, r1 * 16)):
+                for off in range(lo, hi, block):
+                    jobs.append((int(t), kind, mv[off:min(off + block, hi)]))
+                    per_contig[t + 1] += 1
+
+        def one(job):
+            co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+            return co.compress(job[2]) + co.flush()
+        with ThreadPoolExecutor(threads or (os.cpu_count() or 1)) as pool:
+            comp = list(pool.map(one, jobs))
+        table = np.zeros((len(jobs), 2), np.uint64)
+        pos = 0
+        for i, ((_t, kind, raw), c) in enumerate(zip(jobs, comp)):
+            table[i] = (pos, (kind << 63) | (len(c) << 32) | len(raw))
+            pos += len(c)
+        z = np.frombuffer(b"".join(comp) + b"\0" * 64, np.uint8)
+        if pinned:
+            import torch
+            t = torch.from_numpy(z.copy()).pin_memory()
+            self._keep = tuple(self._keep) + (t,)
+            z = t.numpy()
+        self.zp_bytes, self.zp_table, self.zp_contig_block = z, table, np.cumsum(per_contig).astype(np.uint32)
 
     def build_runs(self, max_fraction: float = 0.125) -> "SoaHost":
         """Attach the run-length form (mmlst_build_runs) when it is the smaller one: at most `max_fraction` runs per

@@ -421,11 +421,13 @@ class DevicePipeline:
         want = None
         keys = ["0", "1", "2", "3", "4", "5", "2h", "3h", "4h", "5h"]  # "h": ring form with the L2 residency hints
         if self.use_qc:
-            keys.append("6")  # pair-fused ring (per-chunk len(SEQ) streams only)
+            keys += ["6", "6g10", "6g12", "6g16", "6g24"]  # pair-fused ring (per-chunk len(SEQ) streams only); gNN: grid of NN/8 resident waves
+        grid0 = self.lib.mmlst_set_score_grid_scale(-1)
         for key in keys:
             v = int(key[0])
             self.lib.mmlst_set_score_variant(v)
-            self.lib.mmlst_set_score_l2_hints(1 if key.endswith("h") else 0)
+            self.lib.mmlst_set_score_l2_hints(1 if key[1:2] == "h" else 0)
+            self.lib.mmlst_set_score_grid_scale(int(key.split("g")[1]) if "g" in key else grid0)
             self.reset_tables()
             self._score_call()
             torch.cuda.current_stream(self.dev).synchronize()
@@ -442,6 +444,7 @@ class DevicePipeline:
             b.record()
             b.synchronize()
             out[key] = a.elapsed_time(b) / reps
+        self.lib.mmlst_set_score_grid_scale(grid0)
         for p in pipes:
             p._clean = False
         return out

@@ -529,6 +529,38 @@ def test_device_pipeline_equals_host_selected_path_and_oracle(ctx, case, kernel_
             assert (seq, holes, snps) == corc.consensus(want, db.row_seq(t).encode(), 1)
 
 
+def test_sample_lanes_keep_several_samples_in_flight_with_type_soa_results(ctx):
+    """api.SampleLanes (one context + host thread per lane, mmlst_sample inside): different samples interleaved over 1, 2 and 3 lanes come back in
+    submission order and equal what `type_soa` returns for each of them one at a time (plain and deflated streams, a species filter, tables)."""
+    from metamlst_b200 import devpack, synth
+    db = synth.make_db(("ecoli", "saureus"), alleles_per_locus=6, n_profiles=10, seed=77)
+    index = api.AlleleIndex(db.ref_names())
+    soas, st0 = [], None
+    for i, n_reads in enumerate((2500, 9000, 400, 6000, 1200)):
+        st = devpack.pack_cores(db, [synth.gen_core(db, n_reads, device="cuda:0", read_len=100, seed=300 + i, K=4, sub_err=0.02)], 20, 8000)
+        st0 = st0 or st
+        soa = st.to_host(pinned=True)
+        if i % 2 and soa.run_tid is not None:
+            soa.deflate(block=4096, pinned=False, cover=0.7, pileup=(i == 3))
+        soas.append(soa)
+    sidx = api.SampleIndex(ctx, index, st0.ref_lens, db.row_seq)
+    kw = dict(minscore=170, max_xM=4, min_read_len=50, penalty=100, nloci=0)
+    want = [api.type_soa(sidx, soa, **kw) for soa in soas]
+    assert len({str(w["species"]) for w in want}) > 1   # the samples really differ
+    for lanes in (1, 2, 3):
+        sl = api.SampleLanes(0, index, st0.ref_lens, db.row_seq, lanes=lanes)
+        try:
+            for _rep in range(3):
+                got = sl.map(soas * 2, **kw)
+                assert [g["species"] for g in got] == [w["species"] for w in want] * 2
+                assert [(g["totalReads"], g["ignoredReads"], g["tids"]) for g in got] == [(w["totalReads"], w["ignoredReads"], w["tids"]) for w in want] * 2
+            f = sl.submit(soas[1], species_filter="ecoli", want_tables=True, **kw).result()
+            w = api.type_soa(sidx, soas[1], species_filter="ecoli", want_tables=True, **kw)
+            assert f["species"] == w["species"] and all(np.array_equal(a, b) for a, b in zip(f["tables"], w["tables"]))
+        finally:
+            sl.close()
+
+
 @pytest.mark.parametrize("case", [dict(seed=91, n_reads=3000, L=100, K=4, orgs=("ecoli", "saureus")),
                                   dict(seed=92, n_reads=40000, L=150, K=4, orgs=("ecoli",)),
                                   dict(seed=93, n_reads=60, L=100, K=2, orgs=("ecoli", "saureus", "kpneumoniae"))])
@@ -567,6 +599,22 @@ def test_one_call_sample_over_host_buffers_equals_the_device_pipeline_and_the_tw
             soa.deflate(block=4096, pinned=False, cover=cover)
             assert api.type_soa(sidx, soa, ms, 4, 50, 100, 0)["species"] == g0["species"]
         soa.z_bytes = soa.z_table = None
+    # the pileup stream as DEFLATE blocks per contig (mmlst_zpileup): only the chosen contigs' blocks cross the bus, the engine writes records and rows
+    g100 = api.type_soa(sidx, soa, ms, 4, 50, 100, 100)
+    for block in (1 << 16, 1000):
+        soa.deflate(block=block, pinned=False, cover=0.5, pileup=True)
+        assert soa.zp_bytes is not None and int(soa.zp_contig_block[-1]) == soa.zp_table.shape[0]
+        assert api.type_soa(sidx, soa, ms, 4, 50, 100, 0)["species"] == g0["species"]
+        assert api.type_soa(sidx, soa, ms, 4, 50, 100, 100)["species"] == g100["species"]
+    t_hit = g0["tids"][0]
+    b = int(soa.zp_contig_block[t_hit])
+    good = int(soa.zp_table[b, 1])
+    soa.zp_table[b, 1] = good + 1    # a block that claims one byte more than it inflates to
+    with pytest.raises(RuntimeError, match="zp"):
+        api.type_soa(sidx, soa, ms, 4, 50, 100, 0)
+    soa.zp_table[b, 1] = good
+    assert api.type_soa(sidx, soa, ms, 4, 50, 100, 0)["species"] == g0["species"]
+    soa.z_bytes = soa.z_table = soa.zp_bytes = soa.zp_table = soa.zp_contig_block = None
     # species filter: what is not allowed never scores, so it is never chosen
     f = api.type_soa(sidx, soa, ms, 4, 50, 100, 0, species_filter=orgs[0])
     assert [sp for sp, _ in f["species"]] == [sp for sp, _ in g0["species"] if sp == orgs[0]]

@@ -181,3 +181,37 @@ def test_deflated_score_stream_inflates_back_to_the_arrays():
     cs = soa.c_struct()
     assert cs.z  # the C struct points at the zstream
     assert packing.pack_table(tab, run_fraction=0.0).deflate().z_bytes is None   # needs the run-length form
+
+
+def test_deflated_pileup_stream_round_trips_contig_by_contig():
+    """SoaHost.deflate(pileup=True) (include/mmlst.h, mmlst_zpileup): the blocks of every contig, inflated with zlib in table order, give back exactly
+    its 16-byte records and its plane rows; contigs without records own no blocks; the blocks lie back to back in table order."""
+    import zlib
+    from metamlst_b200 import synth
+    db = synth.make_db(("ecoli", "saureus"), alleles_per_locus=5, n_profiles=8, seed=21)
+    soa = packing.pack_table(synth.make_sample(db, 3000, 100, seed=21, K=3)).build_runs()
+    for block in (1 << 16, 777):
+        soa.deflate(pinned=False, block=block, pileup=True)
+        cs, tab, cb = soa.contig_start, soa.zp_table, soa.zp_contig_block
+        assert cb.shape[0] == len(soa.ref_names) + 1 and cb[0] == 0 and int(cb[-1]) == tab.shape[0]
+        pos = 0
+        for t in range(len(soa.ref_names)):
+            r0, r1 = int(cs[t]), int(cs[t + 1])
+            out = [b"", b""]
+            for b in range(int(cb[t]), int(cb[t + 1])):
+                off, w = int(tab[b, 0]), int(tab[b, 1])
+                kind, clen, ulen = w >> 63, (w >> 32) & 0x7fffffff, w & 0xffffffff
+                assert off == pos and ulen <= block
+                pos += clen
+                d = zlib.decompress(soa.zp_bytes[off:off + clen].tobytes(), -15)
+                assert len(d) == ulen and (kind == 1 or not out[1])   # plane blocks first, then record blocks
+                out[kind] += d
+            if r1 == r0:
+                assert cb[t] == cb[t + 1]
+                continue
+            w0 = int(soa.p_recs["row_off"][r0])
+            w1 = int(soa.p_recs["row_off"][r1 - 1]) + int(packing.row_words(soa.p_recs["nw"][r1 - 1:r1])[0])
+            assert out[1] == soa.p_recs[r0:r1].tobytes() and out[0] == soa.planes[w0:w1].tobytes()
+        assert soa.c_struct().zp
+    soa.deflate(pinned=False)
+    assert soa.zp_bytes is None and not soa.c_struct().zp
