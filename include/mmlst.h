@@ -121,14 +121,21 @@ int mmlst_score_runs_qc_dev(const uint32_t* run_tid, const uint32_t* run_start, 
  * MMLST_SCORE_VARIANT presets it. */
 #define MMLST_SCORE_VARIANT_DEFAULT 6
 int mmlst_set_score_variant(int variant);
-/* Ring forms only: L2 residency hints (score stream evict-first; run arrays, allow[] and chunk_qlen[] evict-last, so that the
- * small tables every warp starts from survive in the L2 from one launch to the next).  1 = on, 0 = off, other = query;
- * returns the previous value.  MMLST_SCORE_L2_HINTS presets it.  Results do not depend on it. */
-#define MMLST_SCORE_L2_HINTS_DEFAULT 0
+/* Ring forms only: L2 residency hints (score stream evict-first; forms 2..5 also read run arrays, allow[] and chunk_qlen[] evict-last).  The stream
+ * is read once per pass, so marking it evict-first leaves the L2 to what the REST of the pass reads -- the selection tables, the chosen contigs'
+ * pileup records, the kernels' code.  The score kernel itself runs as fast either way (27.1 against 27.6 us); serial passes alternating between two
+ * samples go from 73.9 to 64.6 us because each sample's tail inputs survive the other sample's 121 MB stream (B200, profiles/r3j_hints{0,1}_l1.json);
+ * on since then.  1 = on, 0 = off, other = query; returns the previous value.  MMLST_SCORE_L2_HINTS presets it.  Results do not depend on it. */
+#define MMLST_SCORE_L2_HINTS_DEFAULT 1
 int mmlst_set_score_l2_hints(int on);
 /* Form 6 only: grid size in eighths of one resident wave (8 = exactly one wave; above 8 the surplus CTAs go to whichever SM frees a slot
  * first, i.e. the hardware balances the tail of the launch).  1..64 sets, other = query; returns the previous value.  MMLST_SCORE_GRID presets
  * it.  Results do not depend on it. */
+/* Profiling aid: register a DEVICE buffer of 2 x 8192 u64 (or NULL to switch it off, the normal state).  While registered, thread 0 of every CTA of the
+ * selection, bit-sliced pileup and consensus kernels stores the global timer (ns; first half) and its SM's cycle counter (second half) at a few marks:
+ * word (row * 8 + mark), rows 0.. = selection CTAs, 128.. = pileup CTAs, 896.. = consensus CTAs (profiles/tools/tail_timeline.py reads it).  Applies to
+ * launches made after the call (a captured CUDA graph keeps what was set at capture).  Results do not depend on it. */
+int mmlst_debug_timeline(uint64_t* dev_buf);
 #define MMLST_SCORE_GRID_DEFAULT 8
 int mmlst_set_score_grid_scale(int eighths);
 /* qlen[i] of every record back from the per-chunk form (device; the coverage kernel takes it per record) */

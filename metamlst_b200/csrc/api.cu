@@ -45,6 +45,17 @@ void mmlst_trace_flush(const char* call) {
     g_trace.n = 0;
 }
 
+static unsigned long long* g_timeline = nullptr;
+unsigned long long* mmlst_timeline_buffer() { return g_timeline; }
+// see include/mmlst.h
+extern "C" int mmlst_debug_timeline(uint64_t* dev_buf) { g_timeline = reinterpret_cast<unsigned long long*>(dev_buf); return MMLST_OK; }
+
+int mmlst_uniform_carveout() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MMLST_UNIFORM_CARVEOUT"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+
 int mmlst_num_sms() {
     static int by_device[MMLST_MAX_DEVICES] = {0};  // per device: one process may drive several GPUs (sample.type_cohort)
     int& n = by_device[mmlst_current_device()];

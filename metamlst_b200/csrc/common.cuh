@@ -59,6 +59,35 @@ inline int mmlst_current_device() {
     return d % MMLST_MAX_DEVICES;
 }
 
+// Every kernel of a pass asks for the SAME L1 / shared-memory split (all of it shared memory): the score and pileup kernels need it, and an SM whose
+// split differs from what the next kernel wants has to drain and reconfigure before that kernel's CTAs can start -- between the links of a pass and,
+// with several passes in flight on different streams, between kernels that could otherwise share an SM.  MMLST_UNIFORM_CARVEOUT=0 leaves the small
+// kernels on the driver's default (profiling aid).  Once per (kernel, device).
+int mmlst_uniform_carveout();
+template <class K>
+inline void mmlst_prefer_max_shared(K kernel, bool (&done)[MMLST_MAX_DEVICES]) {
+    bool& d = done[mmlst_current_device()];
+    if (d) return;
+    d = true;
+    if (mmlst_uniform_carveout()) { cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); cudaGetLastError(); }
+}
+
+// Profiling aid (mmlst_debug_timeline): when a device buffer is registered, thread 0 of every CTA of the tail kernels stores %globaltimer (ns) and the
+// SM's clock64() at a few marks -- tl[(base + blockIdx.x) * 8 + slot] and the same index + MMLST_TL_WORDS for the cycle counter.  `dep` makes the read
+// wait for a value (a load whose arrival the mark is meant to time).  nullptr (the normal state) costs one predicated branch per mark.
+constexpr uint32_t MMLST_TL_WORDS = 8192;   // u64 words per half: 1024 CTA rows of 8 marks
+constexpr uint32_t MMLST_TL_SELECT = 0, MMLST_TL_PILEUP = 128, MMLST_TL_CONSENSUS = 896;   // first row of each kernel
+unsigned long long* mmlst_timeline_buffer();
+__device__ __forceinline__ void tl_mark(unsigned long long* tl, uint32_t base, uint32_t slot, uint32_t dep = 0) {
+    if (tl && threadIdx.x == 0 && base + blockIdx.x < MMLST_TL_WORDS / 8) {
+        unsigned long long t, c;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) : "r"(dep) : "memory");
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(c) : "r"(dep) : "memory");
+        tl[(base + blockIdx.x) * 8 + slot] = t;
+        tl[MMLST_TL_WORDS + (base + blockIdx.x) * 8 + slot] = c;
+    }
+}
+
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // streaming 128-bit load: read once, do not pollute L1

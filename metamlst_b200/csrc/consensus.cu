@@ -11,13 +11,15 @@ __global__ void __launch_bounds__(CONS_THREADS) consensus_kernel(uint32_t* __res
                                                         const unsigned long long* __restrict__ db_start,
                                                         const uint32_t* __restrict__ col_off, const uint32_t* __restrict__ n_loci_dev,
                                                         uint32_t mincov, uint8_t* __restrict__ cons,
-                                                        uint32_t* __restrict__ holes, uint32_t* __restrict__ snps) {
+                                                        uint32_t* __restrict__ holes, uint32_t* __restrict__ snps, unsigned long long* tl) {
     const uint32_t locus = blockIdx.x;
+    tl_mark(tl, MMLST_TL_CONSENSUS, 0);
     pdl_wait();                  // counts (pileup) and the selection header are complete and visible
     // the launch covers max_loci CTAs and all four words exist for every one of them: fetched together, ONE round trip instead of three
     const uint32_t nl = n_loci_dev ? *n_loci_dev : 0xffffffffu;
     const uint32_t c0 = col_off[locus], c1 = col_off[locus + 1];
     const unsigned long long dbs = db_start ? db_start[locus] : 0ull;
+    tl_mark(tl, MMLST_TL_CONSENSUS, 1, c1 + nl);   // header words have arrived
     if (locus >= nl) return;
     // DB sequence of the chosen allele: either pre-concatenated (column-aligned) or addressed through db_start[locus]
     const uint8_t* db_base = db_start ? dbseq + dbs - c0 : dbseq;
@@ -49,6 +51,7 @@ __global__ void __launch_bounds__(CONS_THREADS) consensus_kernel(uint32_t* __res
     if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[0], h); atomicAdd(&sh[1], s); }
     __syncthreads();
     if (threadIdx.x == 0) { holes[locus] = sh[0]; snps[locus] = sh[1]; }
+    tl_mark(tl, MMLST_TL_CONSENSUS, 2);
 }
 
 }  // namespace
@@ -57,7 +60,9 @@ extern "C" int mmlst_consensus_dev(const uint32_t* counts, const uint8_t* dbseq,
                                    uint32_t mincov, uint8_t* cons, uint32_t* holes, uint32_t* snps, void* stream) {
     if (n_loci == 0) return MMLST_OK;
     if (!counts || !dbseq || !col_off || !cons || !holes || !snps) { mmlst_set_error("mmlst_consensus_dev: null pointer"); return MMLST_E_ARG; }
-    consensus_kernel<false><<<n_loci, CONS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(const_cast<uint32_t*>(counts), dbseq, nullptr, col_off, nullptr, mincov, cons, holes, snps);
+    static bool carve[MMLST_MAX_DEVICES] = {false};
+    mmlst_prefer_max_shared(consensus_kernel<false>, carve);
+    consensus_kernel<false><<<n_loci, CONS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(const_cast<uint32_t*>(counts), dbseq, nullptr, col_off, nullptr, mincov, cons, holes, snps, mmlst_timeline_buffer());
     CUDA_TRY(cudaGetLastError());
     return MMLST_OK;
 }
@@ -70,7 +75,10 @@ extern "C" int mmlst_consensus_indirect_dev(uint32_t* counts, const uint8_t* db_
     if (!counts || !db_ascii || !db_start || !col_off || !header || !cons || !holes || !snps) { mmlst_set_error("mmlst_consensus_indirect_dev: null pointer"); return MMLST_E_ARG; }
     const unsigned long long* dbs = reinterpret_cast<const unsigned long long*>(db_start);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (flags & MMLST_CONSENSUS_CONSUME) CUDA_TRY(mmlst_launch_dependent(consensus_kernel<true>, dim3(max_loci), dim3(CONS_THREADS), 0, s, counts, db_ascii, dbs, col_off, header, mincov, cons, holes, snps));
-    else CUDA_TRY(mmlst_launch_dependent(consensus_kernel<false>, dim3(max_loci), dim3(CONS_THREADS), 0, s, counts, db_ascii, dbs, col_off, header, mincov, cons, holes, snps));
+    static bool carve_t[MMLST_MAX_DEVICES] = {false}, carve_f[MMLST_MAX_DEVICES] = {false};
+    mmlst_prefer_max_shared(consensus_kernel<true>, carve_t);
+    mmlst_prefer_max_shared(consensus_kernel<false>, carve_f);
+    if (flags & MMLST_CONSENSUS_CONSUME) CUDA_TRY(mmlst_launch_dependent(consensus_kernel<true>, dim3(max_loci), dim3(CONS_THREADS), 0, s, counts, db_ascii, dbs, col_off, header, mincov, cons, holes, snps, mmlst_timeline_buffer()));
+    else CUDA_TRY(mmlst_launch_dependent(consensus_kernel<false>, dim3(max_loci), dim3(CONS_THREADS), 0, s, counts, db_ascii, dbs, col_off, header, mincov, cons, holes, snps, mmlst_timeline_buffer()));
     return MMLST_OK;
 }

@@ -95,6 +95,8 @@ extern "C" int mmlst_xchg_publish_dev(const void* block, uint32_t bytes, const u
         return MMLST_E_ARG;
     }
     XchgArgs a{reinterpret_cast<const unsigned long long*>(peer_base), rank, world, half_stride, slot_stride, flag_off, bytes};
+    static bool carve_p[MMLST_MAX_DEVICES] = {false};
+    mmlst_prefer_max_shared(publish_kernel, carve_p);
     publish_kernel<<<world, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, static_cast<const uint4*>(block),
                                                                               reinterpret_cast<const unsigned long long*>(epoch));
     CUDA_TRY(cudaGetLastError());
@@ -106,6 +108,8 @@ extern "C" int mmlst_xchg_await_dev(void* local_base, uint32_t bytes, uint32_t w
     if (!local_base || !out_all || !epoch || !ticket || !status || world == 0) { mmlst_set_error("mmlst_xchg_await_dev: bad argument"); return MMLST_E_ARG; }
     if ((bytes & 15u) || bytes > slot_stride) { mmlst_set_error("mmlst_xchg_await_dev: block size must be a 16-byte multiple and fit a slot"); return MMLST_E_ARG; }
     XchgArgs a{nullptr, 0, world, half_stride, slot_stride, flag_off, bytes};
+    static bool carve_a[MMLST_MAX_DEVICES] = {false};
+    mmlst_prefer_max_shared(await_kernel, carve_a);
     await_kernel<<<world, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, static_cast<char*>(local_base), static_cast<uint4*>(out_all),
                                                                             reinterpret_cast<unsigned long long*>(epoch), ticket, status);
     CUDA_TRY(cudaGetLastError());

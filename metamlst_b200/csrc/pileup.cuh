@@ -17,6 +17,7 @@ struct PileupArgs {
     int minscore, max_xm; uint32_t* counts; uint32_t total_cols;
     const uint32_t* n_chunks_dev;  // when non-null the chunk count is read on the device (written by mmlst_select_dev)
     FusedConsensus fc;
+    unsigned long long* tl = nullptr;   // profiling aid (mmlst_debug_timeline), nullptr = off
 };
 
 // majority call + comparison with the DB allele for the columns [c0, c1) of one locus, by the whole CTA (cmseq/cmseq.py:202-209,234-237,551-554,

@@ -22,6 +22,7 @@
 //   flush    : when the warp's word changes or the chunk ends: bit-sliced add across the 32 lanes (shuffle butterfly
 //              over only as many planes as the tiles accumulated so far can have set), lane i extracts column i,
 //              converts to A/C/G/T/N and issues 5 coalesced RED.ADD.
+#include <stdlib.h>
 #include "common.cuh"
 #include "pileup.cuh"
 
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + NS * stage_bytes + 2 * TR * sizeof(uint4));
 
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    tl_mark(a.tl, MMLST_TL_PILEUP, 0);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
@@ -164,9 +166,24 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
     uint32_t phase_bits = 0;  // parity per stage
     const int max_nw = int(a.max_row_words / 3u);  // upper bound of the contig words any record touches
 
-    const uint32_t n_chunks = pileup_n_chunks(a);
-    for (uint32_t ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
+    // NO LOCAL MEMORY in this kernel: a grid that has touched its stack completes late -- the dependent kernel started 6.3 us after the last CTA of
+    // this one had finished, 0.9 us once the last spilled word was gone (profiles/r3k_tail_timeline.json, profiles/tools/tail_timeline.py).  The chunk
+    // count is therefore re-read when it is needed (a cached load) instead of being kept live across the chunk, where ptxas parked it on the stack.
+    // What has to survive a whole chunk but is the same for every thread (the next chunk of this CTA, the locus of the chunk for the fused consensus)
+    // lives in shared memory, by chunk parity: thread 0 writes it before the chunk's first barrier, everybody reads it after the flush.
+    __shared__ uint32_t s_ctl[2][4];
+    if (blockIdx.x >= pileup_n_chunks(a)) return;
+    uint32_t par = 0;
+    for (uint32_t ci = blockIdx.x;; par ^= 1u) {
         const mmlst_chunk ck = a.chunks[ci];
+        const bool first = ci == blockIdx.x;
+        if (first) tl_mark(a.tl, MMLST_TL_PILEUP, 1, ck.rec_end);
+        if (threadIdx.x == 0) {   // whether another chunk follows is settled HERE, before the flush (the load flies under the chunk's first copy)
+            const uint32_t nx = ci + gridDim.x;
+            s_ctl[par][0] = nx < pileup_n_chunks(a) ? nx : 0xffffffffu;
+            s_ctl[par][1] = ck.reserved[0];
+            s_ctl[par][2] = ck.reserved[1];
+        }
         const uint32_t nrec = ck.rec_end - ck.rec_begin;
         const uint32_t ntiles = (nrec + TR - 1) / TR;
         uint4 g_first = make_uint4(0, 0, 0, 0), g_last = g_first;  // thread 0: first / last record of the next tile to copy
@@ -203,6 +220,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
             const int stage = t % NS;
             mbar_wait(bars + stage, (phase_bits >> stage) & 1u);
             phase_bits ^= 1u << stage;
+            if (first && t < 3) tl_mark(a.tl, MMLST_TL_PILEUP, 3 + t);   // tiles 0..2 landed
 
             const uint8_t* st = smem_raw + stage * stage_bytes;
             const uint4* raw = reinterpret_cast<const uint4*>(st + static_cast<size_t>(stage_words) * 4);
@@ -273,15 +291,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
                 }
             }
         }
+        if (first) tl_mark(a.tl, MMLST_TL_PILEUP, 6);   // thread 0 = warp 0 is done counting
         if (cur_w != INT_MIN) flush_word(acc, cur_w, ck, a.counts, acc_tiles);
+        if (a.tl && first) {   // profiling only: when the SLOWEST warp of the CTA is done flushing
+            tl_mark(a.tl, MMLST_TL_PILEUP, 2);   // (re-used slot: warp 0 done flushing; the descriptor mark moves to slot 1)
+            __syncthreads();
+            tl_mark(a.tl, MMLST_TL_PILEUP, 7);
+        }
         if (a.fc.ticket) {
             // fused consensus: the CTA that completes the last chunk of a locus calls it (release / acquire around the ticket)
             __shared__ uint32_t s_last, s_cons[2];
             __syncthreads();
-            const uint32_t locus = ck.reserved[0];
+            const uint32_t locus = s_ctl[par][1];
             if (threadIdx.x == 0) {
                 __threadfence();
-                s_last = (atomicAdd(a.fc.ticket + locus, 1u) + 1u == ck.reserved[1]) ? 1u : 0u;
+                s_last = (atomicAdd(a.fc.ticket + locus, 1u) + 1u == s_ctl[par][2]) ? 1u : 0u;
             }
             __syncthreads();
             if (s_last) {
@@ -292,6 +316,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) pileup_bitsliced_kernel(const Pil
                 if (threadIdx.x == 0) a.fc.ticket[locus] = 0;
             }
         }
+        ci = s_ctl[par][0];
+        if (ci == 0xffffffffu) break;
     }
 }
 
@@ -305,7 +331,9 @@ bool mmlst_pileup_bitsliced_fits(uint32_t max_row_words) {
     return !(max_row_words < 3 || smem > 220 * 1024);
 }
 
-int launch_pileup_bitsliced(const PileupArgs& a, cudaStream_t stream) {
+int launch_pileup_bitsliced(const PileupArgs& a_in, cudaStream_t stream) {
+    PileupArgs a = a_in;
+    a.tl = mmlst_timeline_buffer();
     // stage = TR rows of the largest row (+ alignment slack) + TR 16-byte records; rows too long for shared memory
     // take the atomic path
     const uint32_t stage_words = ((TR * a.max_row_words + 8u) + 31u) & ~31u;
@@ -320,6 +348,8 @@ int launch_pileup_bitsliced(const PileupArgs& a, cudaStream_t stream) {
         if (e != cudaSuccess) return mmlst_cuda_fail(e, "cudaFuncSetAttribute(pileup_bitsliced_kernel)");
         configured = smem;
     }
+    static bool carve[MMLST_MAX_DEVICES] = {false};
+    mmlst_prefer_max_shared(pileup_bitsliced_kernel<2>, carve);
     const int per_sm = smem <= 113 * 1024 ? int(MMLST_CHUNKS_PER_SM) : 1;  // 227 KB per SM, 1 KB reserved per CTA
     const uint32_t grid = a.n_chunks_dev ? uint32_t(sms * per_sm) : min(a.n_chunks, uint32_t(sms * per_sm));
     // a device-driven launch (chunk list written by the selection kernel just before) is a link of the pass's chain: programmatic dependent launch

@@ -557,8 +557,14 @@ __global__ void __launch_bounds__(kThreads, 4) score_runs_ring_pair_kernel(const
             const uint32_t nch = (c1 - ch < CH) ? static_cast<uint32_t>(c1 - ch) : CH;
             uint8_t* st = my + stage * STAGE_B;
             mbar_expect_tx(bars + stage, nch * CH_B);
-            bulk_g2s(st, a.as0 + (ch << 8), nch * 512u, bars + stage);
-            bulk_g2s(st + AS_B, a.xm3 + (ch << 8), nch * 256u, bars + stage);
+            if (a.l2_hints) {   // the stream is read once: evict-first, so that what the rest of the pass re-reads (tables, the pileup stream, kernel code) stays in the L2
+                const uint64_t pol_s = l2_policy(1);   // one instruction per stage, not a register pair held across the loop
+                bulk_g2s_hint(st, a.as0 + (ch << 8), nch * 512u, bars + stage, pol_s);
+                bulk_g2s_hint(st + AS_B, a.xm3 + (ch << 8), nch * 256u, bars + stage, pol_s);
+            } else {
+                bulk_g2s(st, a.as0 + (ch << 8), nch * 512u, bars + stage);
+                bulk_g2s(st + AS_B, a.xm3 + (ch << 8), nch * 256u, bars + stage);
+            }
         };
         if (lane == 0) {
             const uint32_t pre = ngroups < static_cast<uint32_t>(NS) ? ngroups : static_cast<uint32_t>(NS);

@@ -56,6 +56,7 @@ struct SelArgs {
     uint32_t* header;  // [0]=n_chosen [1]=n_chunks [2]=total_cols [3]=error flags [4]=chunk_records used [6..9]=counters
     uint32_t* chosen_tid; uint32_t* chosen_species; uint32_t* col_off; unsigned long long* db_start;
     mmlst_chunk* chunks; uint32_t max_chunks;
+    unsigned long long* tl;  // profiling aid (mmlst_debug_timeline), nullptr = off
     uint32_t* chosen_first;  // optional: first passing record of every chosen locus (owner-computes merge across GPUs)
 };
 
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
     __shared__ uint32_t sh32[SEL_THREADS / 32];
     __shared__ uint32_t s_last;
     const uint32_t l = blockIdx.x;
+    tl_mark(a.tl, MMLST_TL_SELECT, 0);
     const uint32_t r0 = a.locus_start[l], r1 = a.locus_start[l + 1];   // constant table: may be read before the predecessor is done
     // Any CTA may turn out to be the last one and finalize: each fetches the two small constant tables the finalization walks (species of a locus,
     // `genes` rows of a species) into shared memory NOW, so that those loads fly under its own reduction instead of opening two dependent round
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
         ff[k] = v ? a.first_idx[tt[k]] : 0xffffffffu;
         an[k] = v ? a.allele_num[tt[k]] : 0u;
     }
+    tl_mark(a.tl, MMLST_TL_SELECT, 1, nn[0] + an[SEL_R - 1]);   // the table rows have arrived
     const uint32_t rest0 = r0 + SEL_R * SEL_THREADS + threadIdx.x;  // rows beyond the register window
     // pass 1: per-locus max hit count and first passing record
     uint32_t mx = 0, fmin = 0xffffffffu;
@@ -186,11 +189,13 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
     }
     // ticket: the last CTA finalizes
     __syncthreads();
+    tl_mark(a.tl, MMLST_TL_SELECT, 2);   // the locus is reduced
     if (threadIdx.x == 0) {
         __threadfence();
         s_last = (atomicAdd(a.done, 1u) == gridDim.x - 1u);
     }
     __syncthreads();
+    tl_mark(a.tl, MMLST_TL_SELECT, 3, s_last);   // the ticket is back
     if (!s_last) return;
     __threadfence();
 
@@ -228,6 +233,7 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
         }
     }
     __syncthreads();
+    tl_mark(a.tl, MMLST_TL_SELECT, 5);   // last CTA: per-locus results read back
     for (uint32_t sp = threadIdx.x; sp < a.n_species; sp += blockDim.x) {
         const uint32_t det = s_detected[sp], tot = s_gdb[sp];
         uint32_t pass = 0;
@@ -272,6 +278,7 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
         atomicAdd(&s_totrec, q1 - q0);
     }
     __syncthreads();
+    tl_mark(a.tl, MMLST_TL_SELECT, 6);   // last CTA: what hangs off the chosen rows has arrived, loci ranked
     const uint32_t nsel = s_n;
     if (threadIdx.x == 0) {
         uint32_t cr = a.chunk_records;
@@ -306,6 +313,7 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
         }
     }
     __syncthreads();
+    tl_mark(a.tl, MMLST_TL_SELECT, 7);   // last CTA: header and column layout written
     const uint32_t nch = min(s_totch, a.max_chunks);
     for (uint32_t c = threadIdx.x; c < nch; c += blockDim.x) {
         uint32_t lo = 0, hi = nsel;  // last i with s_cbase[i] <= c
@@ -321,6 +329,7 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
         ck.reserved[2] = 0;
         a.chunks[c] = ck;
     }
+    tl_mark(a.tl, MMLST_TL_SELECT, 4);   // last CTA: finalization written
 }
 
 }  // namespace
@@ -361,6 +370,7 @@ extern "C" int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* firs
     a.header = header; a.chosen_tid = chosen_tid; a.chosen_species = chosen_species; a.col_off = col_off;
     a.db_start = reinterpret_cast<unsigned long long*>(db_start); a.chunks = chunks; a.max_chunks = max_chunks;
     a.chosen_first = chosen_first;
+    a.tl = mmlst_timeline_buffer();
     if (!(flags & MMLST_SELECT_SCRATCH_CLEAN)) CUDA_TRY(cudaMemsetAsync(a.done, 0, 4, s));
     // finalization arrays (10 n_loci + 1 + 3 n_species words, see the kernel) + the prefetched species_of_locus / genes_in_db
     const size_t smem = sizeof(uint32_t) * (static_cast<size_t>(n_loci) * 11 + 1 + 4 * static_cast<size_t>(n_species)) + 16;
@@ -371,6 +381,8 @@ extern "C" int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* firs
         CUDA_TRY(cudaFuncSetAttribute(sel_locus, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         configured = smem;
     }
+    static bool carve[MMLST_MAX_DEVICES] = {false};
+    mmlst_prefer_max_shared(sel_locus, carve);
     CUDA_TRY(mmlst_launch_dependent(sel_locus, dim3(n_loci), dim3(SEL_THREADS), smem, s, a));
     return MMLST_OK;
 }

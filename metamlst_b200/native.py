@@ -89,6 +89,7 @@ EXPORTS = {
     "mmlst_set_score_variant": (C.c_int, [C.c_int]),
     "mmlst_set_score_l2_hints": (C.c_int, [C.c_int]),
     "mmlst_set_score_grid_scale": (C.c_int, [C.c_int]),
+    "mmlst_debug_timeline": (C.c_int, [C.c_void_p]),
     "mmlst_set_pdl": (C.c_int, [C.c_int]),
     "mmlst_expand_runs_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mmlst_coverage_table_slots": (C.c_uint64, [C.c_uint64]),

@@ -299,7 +299,8 @@ class DevicePipeline:
         native.check(self.lib.mmlst_select_dev(native.ptr(self.sum_as), native.ptr(self.n_hit), native.ptr(self.first_idx), native.ptr(self.locus_rows),
                                                native.ptr(self.locus_start), native.ptr(self.allele_num), self.n_ref, native.ptr(self.species_of_locus),
                                                native.ptr(self.genes_in_db), nl, len(self.species_names), self.penalty, self.nloci,
-                                               native.ptr(self.contig_start_d), native.ptr(self.ref_len_d), native.ptr(self.db_off_d), 0,
+                                               native.ptr(self.contig_start_d), native.ptr(self.ref_len_d), native.ptr(self.db_off_d),
+                                               int(os.environ.get("MMLST_CHUNK_RECORDS", "0")),   # 0 = the library's rule (mmlst_chunk_records); profiling knob
                                                native.ptr(self.scratch), int(self.scratch.shape[0]), base + 4 * self.o_hdr, base + 4 * self.o_tid,
                                                base + 4 * self.o_sp, base + 4 * self.o_col, native.ptr(self.db_start_d), native.ptr(self.chunks_d),
                                                self.max_chunks, flags | (native.SELECT_LOCAL if self.owner else 0), native.ptr(self.counters),
@@ -421,7 +422,7 @@ class DevicePipeline:
         want = None
         keys = ["0", "1", "2", "3", "4", "5", "2h", "3h", "4h", "5h"]  # "h": ring form with the L2 residency hints
         if self.use_qc:
-            keys += ["6", "6g10", "6g12", "6g16", "6g24"]  # pair-fused ring (per-chunk len(SEQ) streams only); gNN: grid of NN/8 resident waves
+            keys += ["6", "6h", "6g10", "6g12"]  # pair-fused ring (per-chunk len(SEQ) streams only); gNN: grid of NN/8 resident waves
         grid0 = self.lib.mmlst_set_score_grid_scale(-1)
         for key in keys:
             v = int(key[0])

@@ -1,0 +1,123 @@
+// Microbenchmark: how long after the last CTA of kernel A has finished does the first CTA of a dependent kernel B start, as a function of A's
+// grid size, dynamic shared memory per CTA and block size?  (profiles/r3k_tail_timeline.json shows 6.3 us between the last pileup CTA and the
+// consensus kernel's first instruction, against 0.9 us between selection and pileup.)
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o profiles/tools/exit_gap_probe profiles/tools/exit_gap_probe.cu
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <algorithm>
+#include <vector>
+__device__ __forceinline__ unsigned long long gt() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); return t; }
+__global__ void kernA(unsigned long long* endt, int spin_ns, int touch) {
+    extern __shared__ unsigned char sm[];
+    if (touch) for (int i = threadIdx.x; i < touch; i += blockDim.x) sm[i] = (unsigned char)i;
+    __syncthreads();
+    const unsigned long long t0 = gt();
+    while (gt() - t0 < (unsigned long long)spin_ns) { }
+    __syncthreads();
+    if (threadIdx.x == 0) endt[blockIdx.x] = gt();
+}
+// the same with the CTA's work being `rounds` bulk copies (cp.async.bulk, completion on an mbarrier) of `bytes` each instead of a spin
+__device__ __forceinline__ unsigned su32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__global__ void kernT(unsigned long long* endt, const unsigned char* src, int bytes, int rounds, int inval, int stagger_ns = 0, int touch = 0, unsigned* sink = nullptr) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    __shared__ __align__(8) unsigned long long bar;
+    if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(su32(&bar))); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    unsigned phase = 0;
+    for (int r = 0; r < rounds; ++r) {
+        if (threadIdx.x == 0) {
+            size_t off = ((size_t)blockIdx.x * rounds + r) * bytes;
+            if (touch & 8) {   // geometry first: two read-only 16-byte loads whose values decide the source offset
+                const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(src + off)), g1 = __ldg(reinterpret_cast<const uint4*>(src + off + bytes - 16));
+                off += ((g0.y + g1.y) & 0u);
+            }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(su32(&bar)), "r"(bytes) : "memory");
+            if (touch & 4) {   // two copies on one barrier
+                const int b0 = bytes / 6 * 5 / 16 * 16, b1 = bytes - b0;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(su32(sm)), "l"(src + off), "r"(b0), "r"(su32(&bar)) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(su32(sm + b0)), "l"(src + off + b0), "r"(b1), "r"(su32(&bar)) : "memory");
+            } else {
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(su32(sm)), "l"(src + off), "r"(bytes), "r"(su32(&bar)) : "memory");
+            }
+        }
+        unsigned done;
+        do { asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(su32(&bar)), "r"(phase) : "memory"); } while (!done);
+        phase ^= 1;
+        if (touch & 1) {   // read what the copy brought with ordinary shared-memory loads, write a little back
+            unsigned acc = 0;
+            for (int i = threadIdx.x * 16; i + 16 <= bytes; i += blockDim.x * 16) { const uint4 v = *reinterpret_cast<const uint4*>(sm + i); acc += v.x ^ v.y ^ v.z ^ v.w; }
+            reinterpret_cast<unsigned*>(sm + 100 * 1024)[threadIdx.x] = acc;
+            if (acc == 0x12345678u && sink) sink[0] = acc;
+        }
+        __syncthreads();
+    }
+    if (stagger_ns) { const unsigned long long t0 = gt(); const unsigned long long d = (unsigned long long)(blockIdx.x % 16) * stagger_ns / 16; while (gt() - t0 < d) { } }
+    if (inval && threadIdx.x == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(su32(&bar)) : "memory");
+    if (threadIdx.x == 0) endt[blockIdx.x] = gt();
+}
+__global__ void kernB(unsigned long long* startt) { if (threadIdx.x == 0) startt[blockIdx.x] = gt(); }
+int main() {
+    unsigned long long *dA, *dB;
+    cudaMalloc(&dA, 4096 * 8); cudaMalloc(&dB, 4096 * 8);
+    cudaFuncSetAttribute(kernA, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaStream_t s; cudaStreamCreate(&s);
+    const int grids[] = {21, 148, 296, 592};
+    const int smems[] = {0, 48 * 1024, 110 * 1024, 220 * 1024};
+    for (int g : grids) for (int sm : smems) for (int touch = 0; touch < 2; ++touch) {
+        if (sm == 220 * 1024 && g > 148) continue;
+        if (sm == 110 * 1024 && g > 296) continue;
+        if (touch && sm == 0) continue;
+        std::vector<double> gaps;
+        for (int rep = 0; rep < 12; ++rep) {
+            cudaMemsetAsync(dA, 0, 4096 * 8, s); cudaMemsetAsync(dB, 0, 4096 * 8, s);
+            kernA<<<g, 256, sm, s>>>(dA, 5000, touch ? sm : 0);
+            kernB<<<21, 512, 0, s>>>(dB);
+            cudaStreamSynchronize(s);
+            std::vector<unsigned long long> a(g), b(21);
+            cudaMemcpy(a.data(), dA, g * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b.data(), dB, 21 * 8, cudaMemcpyDeviceToHost);
+            const unsigned long long ea = *std::max_element(a.begin(), a.end()), sb = *std::min_element(b.begin(), b.end());
+            if (rep >= 2) gaps.push_back((double)(sb - ea) / 1e3);
+        }
+        std::sort(gaps.begin(), gaps.end());
+        printf("grid %4d smem %6d touch %d : gap last-CTA-end -> next-kernel-entry  min %.2f median %.2f max %.2f us\n", g, sm, touch, gaps.front(), gaps[gaps.size() / 2], gaps.back());
+    }
+    {   // bulk-copy variant: 296 CTAs x 3 rounds x 47 KB (what the depth-capped pileup moves), and smaller
+        unsigned char* src; cudaMalloc(&src, (size_t)296 * 3 * 49152 + 4096); cudaMemset(src, 1, (size_t)296 * 3 * 49152);
+        unsigned char* flush; cudaMalloc(&flush, 256u << 20);
+        cudaFuncSetAttribute(kernT, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        cudaFuncSetAttribute(kernT, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        { int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernT, 256, 110 * 1024); printf("kernT resident CTAs per SM at 110 KB: %d\n", occ); }
+        cudaGraphExec_t graphs[16] = {nullptr}; int gi = -1;
+        for (int bytes : {49152}) for (int inval = 0; inval < 2; ++inval) for (int cold = 1; cold < 2; ++cold) {
+            ++gi;
+            const int stagger = 0, touch = (inval & 1) ? 13 : 0;
+            const int smem_kb = 110;   // 2 CTAs per SM (occupancy printed above)
+            std::vector<double> gaps, durs;
+            for (int rep = 0; rep < 12; ++rep) {
+                cudaMemsetAsync(dA, 0, 4096 * 8, s); cudaMemsetAsync(dB, 0, 4096 * 8, s);
+                if (cold) cudaMemsetAsync(flush, rep, 256u << 20, s);
+                if (!graphs[gi]) {   // the three launches as a CUDA graph: kernel -> kernel edges without the host launch latency that hides completion latency
+                    cudaGraph_t g;
+                    cudaStreamBeginCapture(s, cudaStreamCaptureModeGlobal);
+                    kernB<<<21, 512, 0, s>>>(dB + 1024);
+                    kernT<<<296, 256, smem_kb * 1024, s>>>(dA, src, bytes, 3, 0, stagger, touch, (unsigned*)dB + 4000);
+                    kernB<<<21, 512, 0, s>>>(dB);
+                    cudaStreamEndCapture(s, &g);
+                    cudaGraphInstantiate(&graphs[gi], g, 0);
+                }
+                cudaGraphLaunch(graphs[gi], s);
+                cudaStreamSynchronize(s);
+                std::vector<unsigned long long> a(296), b(21), b0(21);
+                cudaMemcpy(a.data(), dA, 296 * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b.data(), dB, 21 * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b0.data(), dB + 1024, 21 * 8, cudaMemcpyDeviceToHost);
+                const unsigned long long ea = *std::max_element(a.begin(), a.end()), sb = *std::min_element(b.begin(), b.end()), s0 = *std::min_element(b0.begin(), b0.end());
+                if (rep >= 2) { gaps.push_back((double)(sb - ea) / 1e3); durs.push_back((double)(ea - s0) / 1e3); }
+            }
+            std::sort(gaps.begin(), gaps.end()); std::sort(durs.begin(), durs.end());
+            printf("GRAPH smem %d KB: bulk copies 3 x %5d B per CTA, 296 CTAs, mode %d (1 = smem touched, 4 = two copies per barrier, 8 = geometry loads first), cold L2 %d : prev-kernel-entry -> last CTA end median %.2f us;  gap last-CTA-end -> next-kernel-entry  min %.2f median %.2f max %.2f us\n",
+                   smem_kb, bytes, touch, cold, durs[durs.size() / 2], gaps.front(), gaps[gaps.size() / 2], gaps.back());
+        }
+    }
+    cudaError_t e = cudaGetLastError();
+    printf("status %s\n", cudaGetErrorString(e));
+    return 0;
+}
