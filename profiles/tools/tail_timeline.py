@@ -55,6 +55,8 @@ def run(mode):
     native.check(lib.mmlst_debug_timeline(0))
     p.graph = None
     t = buf.cpu().numpy().astype(np.int64)
+    if OUT:
+        np.save(OUT.replace(".json", "_%s_raw.npy" % mode), t)   # [2][1024 rows][8 marks]: global timer (ns), then the SM cycle counter
     g = t[:TLW].reshape(-1, 8)
     t0 = g[g > 0].min()
     res = {}
