@@ -539,6 +539,12 @@ typedef struct mmlst_bam mmlst_bam;
 typedef struct {
     int minqual; uint32_t max_depth; uint32_t sentinel_nodes; int n_threads; int pinned; int assume_sorted;
     int want_qhash; int check_crc;
+    /* HOST unpacker only (mmlst_bam_ingest refuses it).  0 = MetaMLST's own crash rules: a record whose 1st / 4th aux field is missing or not an integer,
+     * or a pileup record without integer AS:i / XM:i tags, is MMLST_E_BAM.  1 = what a cmseq user without a tag filter gets from pysam: such records are
+     * kept -- positional fields read as -32768 / 255 (no stage-1 filter ever passes them; the Python side refuses to SCORE a stream unpacked this way),
+     * missing named tags read as 0 and are counted in mmlst_bam_info_t.n_untagged, so that a caller who DOES pass a tag filter can raise the reference's
+     * KeyError (cmseq/cmseq.py:545) instead of filtering on invented values.  Proper-pair mates stay refused (H2). */
+    int lenient_tags;
 } mmlst_unpack_opts;
 typedef struct {
     mmlst_soa soa;              /* pointers into memory owned by the mmlst_bam handle, page-locked when opts.pinned */
@@ -549,6 +555,7 @@ typedef struct {
     uint64_t n_dropped_by_cap, n_unmapped_flag;
     int presorted, minqual; uint32_t max_depth;
     double seconds[5];          /* read, inflate, parse, sort, pack */
+    uint64_t n_untagged;        /* lenient_tags: pileup records without integer AS:i / XM:i (0 otherwise: they are refused) */
 } mmlst_bam_info_t;
 int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts /* NULL = defaults */, mmlst_bam** out);
 int mmlst_bam_info(const mmlst_bam* bam, mmlst_bam_info_t* info);

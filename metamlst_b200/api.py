@@ -92,11 +92,19 @@ def finish_scores(index: AlleleIndex, sum_as: np.ndarray, n_hit: np.ndarray, fir
     return cel
 
 
+def refuse_lenient(soa) -> None:
+    """A stream unpacked with lenient_tags carries made-up positional fields for the records metamlst.py:109-110 would have crashed on: it is for
+    cmseq-style pileups only, the score seams refuse it."""
+    if getattr(soa, "lenient", False):
+        raise ValueError("this stream was unpacked with lenient_tags (cmseq use): metamlst.py's read loop would have crashed on such a BAM, it cannot be scored")
+
+
 def score_soa_raw(ctx: native.Context, soa: packing.SoaHost, index: AlleleIndex, minscore: int = 80, max_xM: int = 5,
                   min_read_len: int = 50, species_filter: Optional[str] = None):
     """Seam S1, integer half: (sum_as, n_hit, first_idx, totalReads, ignoredReads) straight from mmlst_score."""
     n_ref = len(index.ref_names)
     check_max_xm(max_xM)
+    refuse_lenient(soa)
     allow = index.allow_mask(species_filter)
     sum_as = np.zeros(n_ref, np.int64)
     n_hit = np.zeros(n_ref, np.uint32)
@@ -224,6 +232,7 @@ def type_soa(sidx: SampleIndex, soa: packing.SoaHost, minscore: int = 80, max_xM
     (metamlst.py:133-220, H5/H6, --nloci gate), pileup + consensus of the chosen contigs (seam S2, metaMLST_functions.py:249-281).
     Returns {"species": [(organism, [(ref name, consensus, holes, snps)])], "totalReads", "ignoredReads", "tids", "tables"}."""
     check_max_xm(max_xM)
+    refuse_lenient(soa)
     if soa.minqual != 20:
         raise ValueError("buildConsensus needs a stream unpacked with minqual=20 (metaMLST_functions.py:258)")
     allow = sidx._allow.get(species_filter)

@@ -18,13 +18,13 @@ from . import native, packing
 
 class UnpackOpts(C.Structure):
     _fields_ = [("minqual", C.c_int), ("max_depth", C.c_uint32), ("sentinel_nodes", C.c_uint32), ("n_threads", C.c_int),
-                ("pinned", C.c_int), ("assume_sorted", C.c_int), ("want_qhash", C.c_int), ("check_crc", C.c_int)]
+                ("pinned", C.c_int), ("assume_sorted", C.c_int), ("want_qhash", C.c_int), ("check_crc", C.c_int), ("lenient_tags", C.c_int)]
 
 
 class BamInfo(C.Structure):
     _fields_ = [("soa", native.Soa), ("qhash", C.c_void_p), ("ref_len", C.c_void_p), ("ref_names", C.c_char_p),
                 ("header_text", C.c_char_p), ("n_dropped_by_cap", C.c_uint64), ("n_unmapped_flag", C.c_uint64),
-                ("presorted", C.c_int), ("minqual", C.c_int), ("max_depth", C.c_uint32), ("seconds", C.c_double * 5)]
+                ("presorted", C.c_int), ("minqual", C.c_int), ("max_depth", C.c_uint32), ("seconds", C.c_double * 5), ("n_untagged", C.c_uint64)]
 
 
 class _Handle:
@@ -50,13 +50,15 @@ def _view(addr: Optional[int], n: int, dtype) -> np.ndarray:
 
 def unpack_bam(path: str, minqual: int = packing.DEFAULT_MINQUAL, max_depth: Optional[int] = packing.DEFAULT_MAX_DEPTH,
                presorted: bool = False, threads: int = 0, pinned: bool = True, want_qhash: bool = True,
-               sentinel_nodes: int = 1) -> packing.SoaHost:
+               sentinel_nodes: int = 1, lenient_tags: bool = False) -> packing.SoaHost:
     """Unpack a BAM once into the score stream + pileup stream (include/mmlst.h).  `presorted` = metamlst.py --presorted
     (file order is kept and must be coordinate order); otherwise records are put in `samtools sort` order and
-    `orig_idx` carries the file order stage 1 saw (H5).  max_depth=None disables the htslib depth cap."""
+    `orig_idx` carries the file order stage 1 saw (H5).  max_depth=None disables the htslib depth cap.  lenient_tags: keep records
+    MetaMLST itself would crash on (no integer 1st / 4th aux field, no AS:i / XM:i) -- for cmseq users without a tag filter; the stream
+    is then marked `lenient` (it cannot be scored) and `n_untagged` counts the pileup records without the two tags."""
     lib = native.lib()
     o = UnpackOpts(int(minqual), int(max_depth or 0), int(sentinel_nodes), int(threads), 1 if pinned else 0,
-                   1 if presorted else 0, 1 if want_qhash else 0, 1)
+                   1 if presorted else 0, 1 if want_qhash else 0, 1, 1 if lenient_tags else 0)
     h = C.c_void_p()
     native.check(lib.mmlst_bam_unpack(path.encode(), C.byref(o), C.byref(h)))
     keep = _Handle(h)
@@ -81,6 +83,7 @@ def unpack_bam(path: str, minqual: int = packing.DEFAULT_MINQUAL, max_depth: Opt
     soa.qhash = _view(info.qhash, 2 * n, np.uint64).reshape(n, 2) if info.qhash else None
     soa.header_text = (info.header_text or b"").decode("latin-1")
     soa.unpack_seconds = dict(zip(("read", "inflate", "parse", "sort", "pack"), [float(x) for x in info.seconds]))
+    soa.lenient, soa.n_untagged = bool(lenient_tags), int(info.n_untagged)
     soa._keep = (keep,)
     return soa
 
@@ -184,7 +187,7 @@ def ingest_bam(source, device=0, minqual: int = packing.DEFAULT_MINQUAL, max_dep
     addr = data.data_ptr() if hasattr(data, "data_ptr") else data.ctypes.data
     nbytes = int(data.numel() if hasattr(data, "numel") else data.size)
     lib = native.lib()
-    o = UnpackOpts(int(minqual), int(max_depth or 0), int(sentinel_nodes), 0, 1, 1 if presorted else 0, 1 if want_qhash else 0, 0)
+    o = UnpackOpts(int(minqual), int(max_depth or 0), int(sentinel_nodes), 0, 1, 1 if presorted else 0, 1 if want_qhash else 0, 0, 0)
     h = C.c_void_p()
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream

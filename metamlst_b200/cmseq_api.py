@@ -11,6 +11,10 @@ threshold is folded into the bit-planes, H3) and a contig's five counters per co
 kernel (`mmlst_pileup_consensus`).  Everything after the counters (ratio, binomial p-value, dict layout, the consensus
 rule) is the reference's own per-column arithmetic in Python floats, so values are identical, not merely close.
 
+Files MetaMLST itself would crash on are accepted the way pysam accepts them (`lenient_tags`): records without integer 1st / 4th aux fields
+or without AS:i / XM:i tags take part in the pileup; only a call that passes a `BAM_tagFilter` on such a file raises the reference's KeyError.
+Proper-pair mates are still refused (`MMLST_E_PAIRED`): pysam's `ignore_overlaps` handling (H2) is not implemented.
+
 Not carried over (each raises, nothing degrades silently): `trimReads` (the bit-planes carry no read coordinate),
 `BAM_tagFilter` entries other than `('AS','loc_gte',x)` / `('XM','loc_lte',y)` (the only ones MetaMLST passes,
 `metaMLST_functions.py:259`), `stepper='all'`, the GFF/codon functions (`parse_gff`, `baseline_PSR`,
@@ -113,6 +117,10 @@ class BamContig:
         minscore, max_xm = _tag_filter(BAM_tagFilter)
         h = self.bam_handle
         soa = h._soa(int(min_base_quality))
+        if BAM_tagFilter and getattr(soa, "n_untagged", 0):
+            # pysam's get_tag raises for the first read without the tag (cmseq/cmseq.py:545); the unpacker counts such reads per FILE, so this is
+            # raised for any contig of a file that holds one -- stricter than upstream, never silently different
+            raise KeyError("tag 'AS' / 'XM' not present in %d pileup records of %s: a BAM_tagFilter cannot be evaluated (cmseq/cmseq.py:545)" % (soa.n_untagged, h.bamFile))
         return np.asarray(_contig_counts(h.ctx, soa, h._tid[self.name], minscore, max_xm))
 
     def get_base_stats(self, min_read_depth=CMSEQ_DEFAULTS.mincov, min_base_quality=CMSEQ_DEFAULTS.minqual, error_rate=CMSEQ_DEFAULTS.poly_error_rate,
@@ -252,7 +260,7 @@ class BamFile:
     def _soa(self, minqual: int):
         s = self._soas.get(minqual)
         if s is None:
-            s = self._soas[minqual] = bam_mod.unpack_bam(self.bamFile, minqual=minqual, want_qhash=False)
+            s = self._soas[minqual] = bam_mod.unpack_bam(self.bamFile, minqual=minqual, want_qhash=False, lenient_tags=True)
         return s
 
     def get_contigs(self):

@@ -162,7 +162,7 @@ struct mmlst_bam {
     Buf tid, as0, xm3, qlen, orig_idx, qhash, p_recs, planes, contig_start, run_tid, run_start, chunk_run, chunk_qlen;
     uint32_t n_runs = 0;
     bool qc = false;  // chunk_qlen valid: every 256-record chunk has one len(SEQ)
-    uint64_t n_rec = 0, n_prec = 0, n_plane_words = 0, n_dropped = 0, n_unmapped_flag = 0;
+    uint64_t n_rec = 0, n_prec = 0, n_plane_words = 0, n_dropped = 0, n_unmapped_flag = 0, n_untagged = 0;
     uint32_t max_row_words = 0;
     int presorted = 0, minqual = 20;
     uint32_t max_depth = 0;
@@ -179,8 +179,9 @@ extern "C" void mmlst_bam_free(mmlst_bam* b) { delete b; }
 extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_in, mmlst_bam** out) {
     if (!path || !out) { mmlst_set_error("mmlst_bam_unpack: null argument"); return MMLST_E_ARG; }
     mmlst_unpack_opts o;
-    o.minqual = 20; o.max_depth = 8000; o.sentinel_nodes = 1; o.n_threads = 0; o.pinned = 1; o.assume_sorted = 0; o.want_qhash = 1; o.check_crc = 1;
+    o.minqual = 20; o.max_depth = 8000; o.sentinel_nodes = 1; o.n_threads = 0; o.pinned = 1; o.assume_sorted = 0; o.want_qhash = 1; o.check_crc = 1; o.lenient_tags = 0;
     if (opts_in) o = *opts_in;
+    const bool lenient = o.lenient_tags != 0;
     int threads = o.n_threads > 0 ? o.n_threads : (int)std::thread::hardware_concurrency();
     if (threads < 1) threads = 1;
     const bool pin = o.pinned != 0;
@@ -351,12 +352,16 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
                 if (isint && a2[0] == 'X' && a2[1] == 'M' && !okxm) { okxm = true; vxm = v; }
                 a2 = val + sz;
             }
-            if (field < 4 || !ok0 || !ok3) {
-                err.set(MMLST_E_BAM, "%s: record %zu: 1st / 4th aux field missing or not an integer: the reference crashes at metamlst.py:109-110", path, i);
-                return;
+            if (lenient && (field < 4 || !ok0 || !ok3 || v0 < -32768 || v0 > 32767 || v3 < 0)) {
+                v0 = -32768; v3 = 255;   // a cmseq caller never runs stage 1: values no stage-1 filter passes
+            } else {
+                if (field < 4 || !ok0 || !ok3) {
+                    err.set(MMLST_E_BAM, "%s: record %zu: 1st / 4th aux field missing or not an integer: the reference crashes at metamlst.py:109-110", path, i);
+                    return;
+                }
+                if (v0 < -32768 || v0 > 32767) { err.set(MMLST_E_RANGE, "%s: record %zu: 1st aux field %lld outside int16", path, i, (long long)v0); return; }
+                if (v3 < 0) { err.set(MMLST_E_RANGE, "%s: record %zu: negative 4th aux field", path, i); return; }
             }
-            if (v0 < -32768 || v0 > 32767) { err.set(MMLST_E_RANGE, "%s: record %zu: 1st aux field %lld outside int16", path, i, (long long)v0); return; }
-            if (v3 < 0) { err.set(MMLST_E_RANGE, "%s: record %zu: negative 4th aux field", path, i); return; }
             c.as0 = (int16_t)v0;
             c.xm3 = (uint8_t)std::min<int64_t>(v3, 255);
             c.named_ok = okas && okxm && vas >= -32768 && vas <= 32767 && vxm >= 0;
@@ -479,6 +484,7 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
     }
     memset(B->planes.as<uint32_t>() + rowoff[P], 0, kSlack * 4);
     const int minqual = o.minqual;
+    std::atomic<uint64_t> n_untagged{0};
     parallel_for(P, threads, 1 << 13, [&](size_t a, size_t e) {
         mmlst_prec* pr = B->p_recs.as<mmlst_prec>();
         uint32_t* planes = B->planes.as<uint32_t>();
@@ -503,9 +509,12 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
             for (uint32_t w = 0; w < rw; ++w) row[w] = 0;
             if (c.reflen == 0) continue;
             if (!c.named_ok) {
-                // get_tag('AS') / get_tag('XM') raise KeyError for the first ACGT base of this read (cmseq/cmseq.py:545)
-                err.set(MMLST_E_BAM, "%s: record %zu enters the pileup without integer AS:i / XM:i tags (pysam get_tag KeyError, cmseq/cmseq.py:545)", path, i);
-                return;
+                // get_tag('AS') / get_tag('XM') raise KeyError for the first ACGT base of this read (cmseq/cmseq.py:545) -- when a tag filter is given
+                if (!lenient) {
+                    err.set(MMLST_E_BAM, "%s: record %zu enters the pileup without integer AS:i / XM:i tags (pysam get_tag KeyError, cmseq/cmseq.py:545)", path, i);
+                    return;
+                }
+                n_untagged.fetch_add(1, std::memory_order_relaxed);
             }
             if (l_seq && qual[0] == 0xff) {
                 err.set(MMLST_E_BAM, "%s: record %zu has no base qualities: query_qualities is None (TypeError at cmseq/cmseq.py:538)", path, i);
@@ -543,6 +552,7 @@ extern "C" int mmlst_bam_unpack(const char* path, const mmlst_unpack_opts* opts_
     if (err.code) { mmlst_set_error("%s", err.msg); return err.code; }
     double t5 = now_s();
     B->minqual = o.minqual; B->max_depth = o.max_depth;
+    B->n_untagged = n_untagged.load();
     B->t_read = t1 - t0; B->t_inflate = t2 - t1; B->t_parse = t3 - t2; B->t_sort = t4 - t3; B->t_pack = t5 - t4;
     *out = B.release();
     return MMLST_OK;
@@ -568,6 +578,7 @@ extern "C" int mmlst_bam_info(const mmlst_bam* b, mmlst_bam_info_t* info) {
     info->header_text = b->header_text.c_str();
     info->n_dropped_by_cap = b->n_dropped; info->n_unmapped_flag = b->n_unmapped_flag;
     info->presorted = b->presorted; info->minqual = b->minqual; info->max_depth = b->max_depth;
+    info->n_untagged = b->n_untagged;
     info->seconds[0] = b->t_read; info->seconds[1] = b->t_inflate; info->seconds[2] = b->t_parse; info->seconds[3] = b->t_sort; info->seconds[4] = b->t_pack;
     return MMLST_OK;
 }

@@ -538,8 +538,9 @@ static int fetch_error(unsigned long long* d_err, cudaStream_t st, const char* w
 extern "C" int mmlst_bam_ingest(int device, const uint8_t* bam, size_t n_bytes, const mmlst_unpack_opts* opts_in, void* stream_in, mmlst_dev_bam** out) {
     if (!bam || !out) { mmlst_set_error("mmlst_bam_ingest: null argument"); return MMLST_E_ARG; }
     mmlst_unpack_opts o;
-    o.minqual = 20; o.max_depth = 8000; o.sentinel_nodes = 1; o.n_threads = 0; o.pinned = 1; o.assume_sorted = 0; o.want_qhash = 1; o.check_crc = 0;
+    o.minqual = 20; o.max_depth = 8000; o.sentinel_nodes = 1; o.n_threads = 0; o.pinned = 1; o.assume_sorted = 0; o.want_qhash = 1; o.check_crc = 0; o.lenient_tags = 0;
     if (opts_in) o = *opts_in;
+    if (o.lenient_tags) { mmlst_set_error("mmlst_bam_ingest: lenient_tags is an option of the host unpacker (mmlst_bam_unpack)"); return MMLST_E_ARG; }
     CUDA_TRY(cudaSetDevice(device));
     cudaStream_t st = static_cast<cudaStream_t>(stream_in);
     g_cur_stream = st;

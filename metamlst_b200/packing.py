@@ -59,6 +59,8 @@ class SoaHost:
     zp_bytes: Optional[np.ndarray] = None    # DEFLATE blocks of the pileup stream, contig by contig (mmlst_zpileup): deflate(pileup=True)
     zp_table: Optional[np.ndarray] = None    # [n_blocks][2] u64
     zp_contig_block: Optional[np.ndarray] = None   # [n_ref + 1] u32
+    lenient: bool = False                    # unpacked with lenient_tags (bam.unpack_bam): pileup only, the score seams refuse it
+    n_untagged: int = 0                      # ... pileup records without integer AS:i / XM:i tags
 
     @property
     def n_rec(self) -> int:

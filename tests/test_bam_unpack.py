@@ -120,3 +120,49 @@ def test_unmapped_flag_scores_but_never_piles_up_and_seq_star_has_len_one(tmp_pa
     assert s.n_rec == 3 and s.qlen.tolist() == [20, 1, 20]  # SEQ '*' -> len('*') == 1 (metamlst.py:111,115)
     assert s.n_prec == 2  # the 0x4 record is skipped by bam_plp_push; the empty one is admitted with reflen 0
     assert sorted(s.p_reflen.tolist()) == [0, 20]
+
+
+def test_lenient_tags_keep_what_pysam_keeps_and_count_the_untagged(tmp_path):
+    """`cmseq_api` unpacks with lenient_tags -- records MetaMLST itself crashes on (no integer 1st / 4th aux field, no AS:i / XM:i) stay in
+    the pileup with exactly the plane rows they have in the fully tagged file; the strict unpacker still refuses them with the reference line named;
+    the lenient stream cannot be scored; proper pairs stay refused either way."""
+    from metamlst_b200 import api
+    db, tab = helpers.small_case(seed=23, n_reads=300, L=100, K=2, orgs=("ecoli",), apl=4)
+    recs = list(bamio.table_records(tab.sorted_by_coord()))
+    names, lens = list(tab.ref_names), [int(x) for x in tab.ref_lens]
+    full = str(tmp_path / "full.bam"); bamio.write_bam(full, names, lens, recs, sort_order="coordinate")
+    want = bam.unpack_bam(full, pinned=False, presorted=True)
+    # BWA-like: AS:i and NM:i only (2 aux fields, no XM); every 5th record without any aux field at all
+    stripped = []
+    for i, r in enumerate(recs):
+        aux = [] if i % 5 == 0 else [a for a in r.aux if a[0] == "AS"] + [bamio.int_aux("NM", 1)]
+        stripped.append(r._replace(aux=aux))
+    lean = str(tmp_path / "lean.bam"); bamio.write_bam(lean, names, lens, stripped, sort_order="coordinate")
+    with pytest.raises(native.MmlstError, match="metamlst.py:109-110"):
+        bam.unpack_bam(lean, pinned=False, presorted=True)
+    got = bam.unpack_bam(lean, pinned=False, presorted=True, lenient_tags=True)
+    assert got.lenient and got.n_untagged == got.n_prec == want.n_prec > 0
+    assert np.array_equal(got.planes, want.planes) and np.array_equal(got.contig_start, want.contig_start)
+    for k in ("pos", "row_off", "reflen", "nw"):
+        assert np.array_equal(got.p_recs[k], want.p_recs[k]), k
+    assert not got.p_recs["as_named"].any() and not got.p_recs["xm_named"].any()
+    assert (got.as0 == -32768).all() and (got.xm3 == 255).all() and np.array_equal(got.qlen, want.qlen) and np.array_equal(got.tid, want.tid)
+    with pytest.raises(ValueError, match="lenient_tags"):
+        api.score_soa_raw(None, got, api.AlleleIndex(names))
+    # the fully tagged file through the lenient unpacker: nothing changes, nothing is counted
+    same = bam.unpack_bam(full, pinned=False, presorted=True, lenient_tags=True)
+    assert same.n_untagged == 0
+    assert_same(want, same)
+    # positional fields present but the NAMED tags missing (XS-less bowtie2 order is fine; here the 4 fields are NM, MD-like integers)
+    named = [r._replace(aux=[bamio.int_aux("NM", 3), bamio.int_aux("X0", 1), bamio.int_aux("X1", 0), bamio.int_aux("XO", 2)]) for r in recs]
+    nm = str(tmp_path / "named.bam"); bamio.write_bam(nm, names, lens, named, sort_order="coordinate")
+    with pytest.raises(native.MmlstError, match="cmseq/cmseq.py:545"):
+        bam.unpack_bam(nm, pinned=False, presorted=True)
+    got2 = bam.unpack_bam(nm, pinned=False, presorted=True, lenient_tags=True)
+    assert got2.n_untagged == got2.n_prec and (got2.as0 == 3).all() and (got2.xm3 == 2).all() and np.array_equal(got2.planes, want.planes)
+    # H2 stays refused
+    paired = [r._replace(flag=r.flag | 0x3) for r in recs[:10]]
+    pp = str(tmp_path / "paired.bam"); bamio.write_bam(pp, names, lens, paired, sort_order="coordinate")
+    for lenient in (False, True):
+        with pytest.raises(native.MmlstError, match="proper-pair"):
+            bam.unpack_bam(pp, pinned=False, presorted=True, lenient_tags=lenient)

@@ -107,6 +107,24 @@ def test_cmseq_seam_refuses_what_it_does_not_implement(monkeypatch):
         cmseq_api.BamFile(bam + ".missing", ctx=object())
 
 
+def test_cmseq_seam_accepts_untagged_bams_and_raises_only_under_a_tag_filter(tmp_path, monkeypatch):
+    """A BAM without XM:i (BWA-like): reference cmseq works on it as long as no BAM_tagFilter is given and dies with pysam's KeyError otherwise
+    (cmseq/cmseq.py:545).  Same here: the unfiltered statistics equal those of the fully tagged file, a tag filter raises KeyError."""
+    src = os.path.join(GOLDEN, "basic", "sample.bam")
+    h, recs = bamio.read_bam(src)
+    lean = str(tmp_path / "lean.bam")
+    bamio.write_bam(lean, h.ref_names, h.ref_lens, [r._replace(aux=[a for a in r.aux if a[0] == "AS"]) for r in recs])
+    monkeypatch.setattr(cmseq_api, "_contig_counts", _OracleCounts(src))   # the counts do not depend on the tags without a filter
+    full, bf = cmseq_api.BamFile(src, ctx=object()), cmseq_api.BamFile(lean, ctx=object())
+    assert list(bf.contigs) == list(full.contigs)
+    name = next(iter(bf.contigs))
+    assert _plain(bf.get_contig_by_label(name).get_base_stats()) == _plain(full.get_contig_by_label(name).get_base_stats())
+    assert bf.get_contig_by_label(name).reference_free_consensus() == full.get_contig_by_label(name).reference_free_consensus()
+    with pytest.raises(KeyError, match="cmseq/cmseq.py:545"):
+        bf.get_contig_by_label(name).get_base_stats(BAM_tagFilter=[("AS", "loc_gte", 50), ("XM", "loc_lte", 5)])
+    full.get_contig_by_label(name).get_base_stats(BAM_tagFilter=[("AS", "loc_gte", 50), ("XM", "loc_lte", 5)])   # tagged file: fine
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("scen", sorted(GOLD))
 def test_cmseq_seam_on_the_gpu_matches_the_reference(scen):
