@@ -678,13 +678,30 @@ def main():
     # one call: the selection block (header + chosen rows / species / column offsets), block sizes reported by the decompression engine, consensus, holes, snps
     d2h = (16 + 3 * n_loci + 1) * 4 + 4 * int(soa.z_table.shape[0]) + sum(int(st.ref_lens[t]) for t in ts_local) + 8 * n_loci
     h2d -= db.n_rows * 4    # locus_of[] is resident (mmlst_index_upload); allow[] still travels
+    # what the box gives this path: every rank pulling from page-locked memory at once (GPUs share PCIe uplinks: profiles/r3q_h2d_probe_n8.json)
+    bus_pin = torch.empty(128 << 20, dtype=torch.uint8).pin_memory()
+    bus_dev = torch.empty(128 << 20, dtype=torch.uint8, device=device)
+    for _ in range(2):
+        bus_dev.copy_(bus_pin, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    t0_ = time.perf_counter()
+    for _ in range(8):
+        bus_dev.copy_(bus_pin, non_blocking=True)
+    torch.cuda.synchronize()
+    bus_s = time.perf_counter() - t0_
+    barrier()
+    del bus_pin, bus_dev
     lane_keys = sorted(lanes_ms)
-    tt = torch.tensor([dt, float(h2d), float(d2h), dt_plain, dt_seams, dt_one] + [lanes_ms[k] for k in lane_keys], dtype=torch.float64, device=device)
+    tt = torch.tensor([dt, float(h2d), float(d2h), dt_plain, dt_seams, dt_one] + [lanes_ms[k] for k in lane_keys] + [bus_s], dtype=torch.float64, device=device)
+    h2d_rank_max = float(h2d)
     if world > 1:
         mx = tt.clone(); torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.SUM)
         dt = float(mx[0].item()); dt_plain = float(mx[3].item()); dt_seams = float(mx[4].item()); dt_one = float(mx[5].item())
         lanes_ms = {k: float(mx[6 + i].item()) for i, k in enumerate(lane_keys)}
+        bus_s = float(mx[6 + len(lane_keys)].item()); h2d_rank_max = float(mx[1].item())
+    bus_gbps = 8 * (128 << 20) / bus_s / 1e9
     line["e2e"] = {"value": R_total / dt, "unit": "records/s", "h2d_bytes_per_step": int(tt[1].item()), "d2h_bytes_per_step": int(tt[2].item()),
                    "ms_per_step": dt * 1e3, "timing": "host wall clock around the K synchronous C-ABI calls, barrier on both sides, max over ranks",
                    "call": "mmlst_sample (api.type_soa): one call per sample from pinned host buffers -- score stream up, score, selection on the device, pileup records "
@@ -693,6 +710,10 @@ def main():
                                "ride the bus while another waits for its selection block or runs its pileup; every step's own H2D and D2H are inside the timed "
                                "region" % args.e2e_lanes,
                    "lanes": args.e2e_lanes,
+                   "bus": {"h2d_GBps_per_gpu_all_ranks_copying": bus_gbps, "ms_per_step_at_that_rate": h2d_rank_max / bus_gbps / 1e6,
+                           "what": "128 MB copies from page-locked memory, every rank at once, slowest rank: the GPUs of the box share PCIe uplinks, so the per-GPU rate "
+                                   "falls as ranks are added (55 GB/s alone, 23 GB/s with 8: profiles/r3q_h2d_probe_n8.json); ms_per_step_at_that_rate = the largest "
+                                   "rank's h2d bytes of a step at that rate, the floor of a bus-bound step"},
                    "ms_per_step_by_lanes": {str(k): lanes_ms[k] * 1e3 for k in sorted(lanes_ms)},
                    "one_at_a_time": {"value": R_total / dt_one, "unit": "records/s", "ms_per_step": dt_one * 1e3,
                                      "what": "the same call, strictly one sample after another on one context (single-sample latency)"},
