@@ -63,6 +63,8 @@ def parse():
                     "(mmlst_set_score_l2_hints)")
     ap.add_argument("--e2e-cover", type=float, default=1.0, help="fraction of as0[] / xm3[] shipped as DEFLATE blocks in the `e2e` leg (the rest plain; r3e: with several "
                     "samples in flight the whole arrays compressed is fastest -- 1.16 ms per sample at 1.0 against 1.24 at 0.95 and 1.32 at 0.9)")
+    ap.add_argument("--e2e-level", type=int, default=6, help="zlib level of the DEFLATE blocks of the `e2e` leg (6: 0.41 bytes per record for as0 + 6 xm3 and xm3 "
+                    "against 0.49 at level 3, for twice the preparation time)")
     ap.add_argument("--e2e-plain-pileup", action="store_true", help="`e2e` leg: ship the chosen contigs' pileup records plain instead of as DEFLATE blocks")
     ap.add_argument("--e2e-lanes", type=int, default=3, help="samples in flight in the `e2e` leg (api.SampleLanes); 1, 2 and 3 are always timed and reported beside it")
     ap.add_argument("--max-depth", type=int, default=8000, help="htslib pileup depth cap of the main workload (0 = uncapped; profiling aid)")
@@ -544,7 +546,8 @@ def main():
     t0 = time.perf_counter()
     # once per sample, like the unpacking: as0[] / xm3[] as DEFLATE blocks, inflated on the device by the hardware engine; the last tenth of each
     # array stays plain and rides the bus while the engine (the slower of the two on this data) drains its queue (profiles/r2z_e2e_sweep.json)
-    soa.deflate(cover=args.e2e_cover, pileup=not args.e2e_plain_pileup)
+    soa.deflate(level=args.e2e_level, cover=args.e2e_cover, pileup=not args.e2e_plain_pileup)
+    z_coeff = int(soa.z_as_xm_coeff)
     t_deflate = time.perf_counter() - t0
     ctx = native.Context(local)
 
@@ -721,9 +724,10 @@ def main():
                                       "what": "mmlst_score -> host selection -> mmlst_pileup_consensus, the reference's call structure, same compressed stream"},
                    "host_numa_binding": numa, "exchange": "one fixed-size NCCL all-gather of the per-rank result blocks" if world > 1 else "none (one rank)",
                    "stream_form": "the first %.0f %% of as0[] / xm3[] crosses PCIe as DEFLATE blocks and is inflated in HBM by the hardware decompression engine, slice by "
-                                  "slice behind the copy, the rest plain (%.2f bytes per record in all instead of 3); deflating is part of preparing a sample "
+                                  "slice behind the copy, the rest plain (%.2f bytes per record in all instead of 3; the as0 blocks hold as0 + %d * xm3, the coefficient picked per sample, "
+                                  "and a kernel subtracts it again after the inflate); deflating is part of preparing a sample "
                                   "(%.2f s here, host threads), like unpacking it; the chosen contigs' pileup records and plane rows cross as DEFLATE "
-                                  "blocks too (%.1f MB instead of %.1f MB per sample)" % (100 * min(max(args.e2e_cover, 0.0), 1.0), h2d_score_zp / max(R_local, 1), t_deflate, pileup_h2d / 1e6, pileup_plain / 1e6),
+                                  "blocks too (%.1f MB instead of %.1f MB per sample)" % (100 * min(max(args.e2e_cover, 0.0), 1.0), h2d_score_zp / max(R_local, 1), z_coeff, t_deflate, pileup_h2d / 1e6, pileup_plain / 1e6),
                    "uncompressed": {"value": R_total / dt_plain, "unit": "records/s", "ms_per_step": dt_plain * 1e3,
                                     "h2d_bytes_per_step": int(tt[1].item()) + world * (3 * R_local - h2d_score_zp - 32 * int(soa.z_table.shape[0]) + h2d_plain_total_extra),
                                     "what": "the same call with the plain arrays (3 bytes per record cross PCIe)"}}

@@ -138,6 +138,8 @@ int mmlst_set_score_l2_hints(int on);
 int mmlst_debug_timeline(uint64_t* dev_buf);
 #define MMLST_SCORE_GRID_DEFAULT 8
 int mmlst_set_score_grid_scale(int eighths);
+/* as0[i] -= coeff * xm3[i] for i < n (device, in place): undoes the decorrelation of a compressed score stream (mmlst_zstream.as_xm_coeff) */
+int mmlst_as_untransform_dev(int16_t* as0, const uint8_t* xm3, uint64_t n, int coeff, void* stream);
 /* qlen[i] of every record back from the per-chunk form (device; the coverage kernel takes it per record) */
 int mmlst_expand_chunk_qlen_dev(const uint16_t* chunk_qlen, uint64_t n_rec, uint16_t* qlen, void* stream);
 /* tid[i] of every record back from the run arrays (device; the coverage kernel takes the explicit form) */
@@ -350,6 +352,12 @@ int mmlst_hamming_min_dev2(const uint32_t* db_hi, const uint32_t* db_lo, const u
 typedef struct {
     const uint8_t* bytes; uint64_t n_bytes;
     const uint64_t* table; uint32_t n_blocks;
+    /* Decorrelation before DEFLATE: the as0 blocks hold as0[i] + as_xm_coeff * xm3[i] (still int16; 0 = as0 itself).  An aligner's score is its match
+     * bonus minus a penalty per mismatch, so with the right coefficient (bowtie2: 6) what is left of as0 takes a handful of values and deflates to a
+     * fraction: 0.43 instead of 0.85 bytes per record for the two arrays on configs[1].  The library subtracts it again on the device after the blocks
+     * are inflated (mmlst_as_untransform_dev); only the part of as0[] covered by blocks is transformed.  SoaHost.deflate() picks the coefficient per
+     * sample by trying 0..8 on a slice of the arrays. */
+    int32_t as_xm_coeff;
 } mmlst_zstream;
 
 /* Optional DEFLATE-compressed copy of the PILEUP stream, contig by contig, so that mmlst_sample ships only the chosen contigs' blocks and the hardware

@@ -279,6 +279,10 @@ static int upload_score_stream(mmlst_ctx* c, const mmlst_soa* soa) {
         mmlst_trace_mark("params_built");
         TRY(mmlst_h2d_inflate(c->device, s, c->zbuf.as<uint8_t>(), z->bytes, z->n_bytes, prm, src_off, &plain, 3));
         c->z_pending = z->n_blocks;
+        if (z->as_xm_coeff) {   // the blocks hold as0 + coeff * xm3 over the covered prefix: back to as0 once both arrays are complete on the device
+            if (z->as_xm_coeff < -256 || z->as_xm_coeff > 256) { mmlst_set_error("mmlst_soa.z: as_xm_coeff %d out of range", z->as_xm_coeff); return MMLST_E_ARG; }
+            TRY(mmlst_as_untransform_dev(c->as0.as<int16_t>(), c->xm3.as<uint8_t>(), covered[0] / 2, z->as_xm_coeff, s));
+        }
     } else {
         TRY(h2d(c->as0, soa->as0, n, s));
         TRY(h2d(c->xm3, soa->xm3, n, s));

@@ -189,3 +189,40 @@ extern "C" int mmlst_expand_runs_dev(const uint32_t* run_tid, const uint32_t* ru
     CUDA_TRY(cudaGetLastError());
     return MMLST_OK;
 }
+
+// as0[i] -= coeff * xm3[i]: eight records per thread (one 128-bit and one 64-bit access each way), the last n % 8 by one thread
+namespace {
+__global__ void __launch_bounds__(256) as_untransform_kernel(int16_t* __restrict__ as0, const uint8_t* __restrict__ xm3, uint64_t n, int coeff) {
+    const uint64_t n8 = n >> 3;
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        uint4 a = reinterpret_cast<uint4*>(as0)[i];
+        const uint2 x = ld_stream_u2(xm3 + (i << 3));
+        uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+        const uint32_t xw[2] = {x.x, x.y};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t xb = xw[w >> 1] >> ((w & 1) * 16);
+            const int lo = static_cast<int16_t>(aw[w] & 0xffffu) - coeff * static_cast<int>(xb & 0xffu);
+            const int hi = static_cast<int16_t>(aw[w] >> 16) - coeff * static_cast<int>((xb >> 8) & 0xffu);
+            aw[w] = (static_cast<uint32_t>(lo) & 0xffffu) | (static_cast<uint32_t>(hi) << 16);
+        }
+        reinterpret_cast<uint4*>(as0)[i] = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (uint64_t i = n8 << 3; i < n; ++i) as0[i] = static_cast<int16_t>(as0[i] - coeff * static_cast<int>(xm3[i]));
+}
+}  // namespace
+
+extern "C" int mmlst_as_untransform_dev(int16_t* as0, const uint8_t* xm3, uint64_t n, int coeff, void* stream) {
+    if (n == 0 || coeff == 0) return MMLST_OK;
+    if (!as0 || !xm3) { mmlst_set_error("mmlst_as_untransform_dev: null pointer"); return MMLST_E_ARG; }
+    if ((reinterpret_cast<uintptr_t>(as0) & 15) || (reinterpret_cast<uintptr_t>(xm3) & 7)) { mmlst_set_error("mmlst_as_untransform_dev: as0 must be 16-byte aligned, xm3 8"); return MMLST_E_ARG; }
+    uint64_t blocks = ((n >> 3) + 255) / 256;
+    const uint64_t cap = static_cast<uint64_t>(mmlst_num_sms()) * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    as_untransform_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(as0, xm3, n, coeff);
+    CUDA_TRY(cudaGetLastError());
+    return MMLST_OK;
+}

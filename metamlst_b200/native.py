@@ -33,7 +33,7 @@ class Soa(C.Structure):
 
 
 class ZStream(C.Structure):
-    _fields_ = [("bytes", C.c_void_p), ("n_bytes", C.c_uint64), ("table", C.c_void_p), ("n_blocks", C.c_uint32)]
+    _fields_ = [("bytes", C.c_void_p), ("n_bytes", C.c_uint64), ("table", C.c_void_p), ("n_blocks", C.c_uint32), ("as_xm_coeff", C.c_int32)]
 
 
 class ZPileup(C.Structure):   # mmlst_zpileup
@@ -90,6 +90,7 @@ EXPORTS = {
     "mmlst_set_score_l2_hints": (C.c_int, [C.c_int]),
     "mmlst_set_score_grid_scale": (C.c_int, [C.c_int]),
     "mmlst_debug_timeline": (C.c_int, [C.c_void_p]),
+    "mmlst_as_untransform_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
     "mmlst_set_pdl": (C.c_int, [C.c_int]),
     "mmlst_expand_runs_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mmlst_coverage_table_slots": (C.c_uint64, [C.c_uint64]),

@@ -56,6 +56,7 @@ class SoaHost:
     chunk_qlen: Optional[np.ndarray] = None  # u16 per 256-record chunk when every chunk has one len(SEQ) (3 B / record form)
     z_bytes: Optional[np.ndarray] = None     # DEFLATE blocks of as0[] / xm3[] (mmlst_zstream) + their table [n_blocks][4] u64: deflate()
     z_table: Optional[np.ndarray] = None
+    z_as_xm_coeff: int = 0                   # the as0 blocks hold as0 + coeff * xm3 (mmlst_zstream.as_xm_coeff)
     zp_bytes: Optional[np.ndarray] = None    # DEFLATE blocks of the pileup stream, contig by contig (mmlst_zpileup): deflate(pileup=True)
     zp_table: Optional[np.ndarray] = None    # [n_blocks][2] u64
     zp_contig_block: Optional[np.ndarray] = None   # [n_ref + 1] u32
@@ -102,7 +103,8 @@ class SoaHost:
             if self.chunk_qlen is not None:
                 s.chunk_qlen = native.ptr(self.chunk_qlen)
             if self.z_bytes is not None:
-                zs = native.ZStream(native.ptr(self.z_bytes), int(self.z_bytes.shape[0]), native.ptr(self.z_table), int(self.z_table.shape[0]))
+                zs = native.ZStream(native.ptr(self.z_bytes), int(self.z_bytes.shape[0]), native.ptr(self.z_table), int(self.z_table.shape[0]),
+                                    int(self.z_as_xm_coeff))
                 s._zs = zs  # kept alive by the struct that points at it
                 s.z = C.addressof(zs)
         if self.zp_bytes is not None:
@@ -113,7 +115,7 @@ class SoaHost:
         return s
 
     def deflate(self, level: int = 3, block: int = 1 << 16, threads: int = 0, pinned: bool = True, strategy: int = 0,
-                cover: float = 1.0, pileup: bool = False) -> "SoaHost":
+                cover: float = 1.0, pileup: bool = False, as_xm_coeff: Optional[int] = None) -> "SoaHost":
         """Attach the DEFLATE-compressed copy of as0[] / xm3[] (include/mmlst.h, mmlst_zstream): the host-buffer path then ships these
         bytes and the device inflates them with the hardware decompression engine.  Done once per sample, like the unpacking; needs the
         run-length form (coordinate-sorted streams).  block = inflated bytes per DEFLATE stream: the engine works on many streams at once,
@@ -122,7 +124,9 @@ class SoaHost:
         Z_FIXED, Z_RLE, Z_HUFFMAN_ONLY).  cover < 1: only the first `cover` of each array is compressed and the rest crosses PCIe plain, so that
         the bus keeps working while the engine (the slower of the two on this data) drains its queue.  pileup=True additionally attaches the pileup
         stream as DEFLATE blocks per contig (mmlst_zpileup: `mmlst_sample` then ships the chosen contigs' blocks instead of their records and
-        plane rows)."""
+        plane rows).  as_xm_coeff: the as0 blocks hold as0 + coeff * xm3 (an alignment score is a match bonus minus a penalty per mismatch: with the
+        aligner's penalty as coefficient the remainder takes a handful of values; the device subtracts it again); None = try 0..8 on a slice of the
+        arrays and keep the smallest, 0 = off."""
         import os
         import zlib
         from concurrent.futures import ThreadPoolExecutor
@@ -132,8 +136,31 @@ class SoaHost:
             self._deflate_pileup(level, block, threads, pinned, strategy)
         if self.run_tid is None or self.n_rec == 0:
             return self
+        self.z_as_xm_coeff = 0
+        as0 = np.ascontiguousarray(self.as0)
+        stop_a = 2 * as0.shape[0] if cover >= 1.0 else int(2 * as0.shape[0] * max(cover, 0.0)) // block * block
+        n_tr = stop_a // 2   # records of as0[] that travel in blocks
+        if n_tr and as_xm_coeff != 0:
+            xm = np.ascontiguousarray(self.xm3)[:n_tr].astype(np.int32)
+            a32 = as0[:n_tr].astype(np.int32)
+            if as_xm_coeff is None:   # smallest zlib output over a slice from the middle of the arrays
+                m0, m1 = max(0, n_tr // 2 - (1 << 17)), min(n_tr, n_tr // 2 + (1 << 17))
+                best = None
+                for c in range(0, 9):
+                    t = a32[m0:m1] + c * xm[m0:m1]
+                    if t.max(initial=0) > 32767 or t.min(initial=0) < -32768:
+                        continue
+                    size = len(zlib.compress(t.astype(np.int16).tobytes(), 1))
+                    if best is None or size < best[0]:
+                        best = (size, c)
+                as_xm_coeff = best[1] if best else 0
+            if as_xm_coeff:
+                t = a32 + int(as_xm_coeff) * xm
+                if t.max(initial=0) <= 32767 and t.min(initial=0) >= -32768:
+                    as0 = np.concatenate([t.astype(np.int16), as0[n_tr:]])
+                    self.z_as_xm_coeff = int(as_xm_coeff)
         jobs = []
-        for kind, arr in ((0, np.ascontiguousarray(self.as0).view(np.uint8)), (1, np.ascontiguousarray(self.xm3).view(np.uint8))):
+        for kind, arr in ((0, as0.view(np.uint8)), (1, np.ascontiguousarray(self.xm3).view(np.uint8))):
             mv = memoryview(arr)
             stop = arr.shape[0] if cover >= 1.0 else int(arr.shape[0] * max(cover, 0.0)) // block * block
             for off in range(0, stop, block):

@@ -596,8 +596,13 @@ def test_one_call_sample_over_host_buffers_equals_the_device_pipeline_and_the_tw
     assert [x for _sp, lst in g0["species"] for x in lst] == [(index.ref_names[t], seqs[i], int(holes[i]), int(snps[i])) for i, t in enumerate(ts)]
     if soa.run_tid is not None:
         for cover in (1.0, 0.5, 0.0):
-            soa.deflate(block=4096, pinned=False, cover=cover)
-            assert api.type_soa(sidx, soa, ms, 4, 50, 100, 0)["species"] == g0["species"]
+            for coeff in (None, 0, 3):   # as0 + coeff * xm3 in the blocks (picked per sample / off / a coefficient that does not fit the data)
+                soa.deflate(block=4096, pinned=False, cover=cover, as_xm_coeff=coeff)
+                assert soa.z_as_xm_coeff == ((6 if coeff is None else coeff) if cover > 0 and soa.z_bytes is not None and (soa.z_table[:, 0] == 0).any() else 0)
+                r = api.type_soa(sidx, soa, ms, 4, 50, 100, 0, want_tables=True)
+                assert r["species"] == g0["species"] and all(np.array_equal(a, b) for a, b in zip(r["tables"], raw[:3]))
+                if cover == 1.0:   # the two-seam call (mmlst_score) undoes it too
+                    assert all(np.array_equal(a, b) for a, b in zip(api.score_soa_raw(ctx, soa, index, ms, 4, 50)[:3], raw[:3]))
         soa.z_bytes = soa.z_table = None
     # the pileup stream as DEFLATE blocks per contig (mmlst_zpileup): only the chosen contigs' blocks cross the bus, the engine writes records and rows
     g100 = api.type_soa(sidx, soa, ms, 4, 50, 100, 100)

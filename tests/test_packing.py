@@ -176,8 +176,25 @@ def test_deflated_score_stream_inflates_back_to_the_arrays():
         raw = zlib.decompress(bytes(soa.z_bytes[src:src + clen]), -15)
         assert len(raw) == ulen <= 4096
         out[kind][dst:dst + ulen] = raw
-    assert bytes(out[0]) == np.ascontiguousarray(soa.as0).tobytes() and bytes(out[1]) == np.ascontiguousarray(soa.xm3).tobytes()
+    # the as0 blocks hold as0 + coeff * xm3 (mmlst_zstream.as_xm_coeff, picked per sample: the synthetic aligner charges 6 per mismatch)
+    assert soa.z_as_xm_coeff == 6 and soa.c_struct()._zs.as_xm_coeff == 6
+    got_as = np.frombuffer(bytes(out[0]), np.int16).astype(np.int32) - soa.z_as_xm_coeff * np.asarray(soa.xm3).astype(np.int32)
+    assert np.array_equal(got_as, np.asarray(soa.as0).astype(np.int32)) and bytes(out[1]) == np.ascontiguousarray(soa.xm3).tobytes()
     assert int(t[-1, 2]) + (int(t[-1, 3]) >> 32) == soa.z_bytes.shape[0]
+    smaller = soa.z_bytes.shape[0]
+    soa.deflate(block=4096, pinned=False, as_xm_coeff=0)   # off: the blocks are the arrays themselves, and larger
+    assert soa.z_as_xm_coeff == 0 and soa.z_bytes.shape[0] > smaller
+    raw0 = b"".join(zlib.decompress(bytes(soa.z_bytes[src:src + (packed >> 32)]), -15) for kind, dst, src, packed in soa.z_table.tolist() if kind == 0)
+    assert raw0 == np.ascontiguousarray(soa.as0).tobytes()
+    # a coefficient that would leave int16 is dropped; only the covered prefix is transformed
+    big = packing.pack_table(tab.sorted_by_coord(), run_fraction=1.0)
+    big.as0 = np.where(np.arange(big.n_rec) == 5, 32767, np.asarray(big.as0)).astype(np.int16)
+    big.xm3 = np.where(np.arange(big.n_rec) == 5, 3, np.asarray(big.xm3)).astype(np.uint8)
+    assert big.deflate(block=4096, pinned=False, as_xm_coeff=6).z_as_xm_coeff == 0
+    half = packing.pack_table(tab.sorted_by_coord(), run_fraction=1.0).deflate(block=1024, pinned=False, cover=0.5)
+    covered = int((half.z_table[half.z_table[:, 0] == 0][:, 3] & np.uint64(0xffffffff)).sum())
+    assert half.z_as_xm_coeff == 6 and 0 < covered < 2 * half.n_rec and covered % 1024 == 0
+    soa.deflate(block=4096, pinned=False)
     cs = soa.c_struct()
     assert cs.z  # the C struct points at the zstream
     assert packing.pack_table(tab, run_fraction=0.0).deflate().z_bytes is None   # needs the run-length form
