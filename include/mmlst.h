@@ -223,7 +223,8 @@ int mmlst_consensus_dev(const uint32_t* counts, const uint8_t* dbseq, const uint
  * (--nloci gate), :213-220 + :244 (alleles whose rounded average equals the locus maximum, lowest int(allele)), and the
  * dict-order bookkeeping of H5 (species by first passing record, loci inside a species by first passing record).
  * ONE launch: CTA = locus (three in-CTA reductions, no global atomics), the last CTA to finish finalizes.
- *   locus_rows[n_ref] = allele rows grouped by locus, locus_start[n_loci+1] = range of each locus in locus_rows
+ *   locus_rows[n_ref] = allele rows grouped by locus, locus_start[n_loci+1] = range of each locus in locus_rows; locus_rows may be NULL when the rows
+ *   already ARE grouped by locus (locus_rows[i] == i: a DB dumped gene by gene), which saves the kernel one dependent trip to memory
  *   allele_num[tid] = int(alleleVariant); species_of_locus[locus]; genes_in_db[species] = rows of `genes` (metamlst.py:184)
  *   contig_start / ref_len / db_off: pileup-stream record range, BAM LN and DB-sequence offset of every allele row
  *   scratch: >= 12*n_loci + 16 bytes, 8-byte aligned.  flags: MMLST_SELECT_CONSUME = the call resets what it has read

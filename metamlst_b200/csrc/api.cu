@@ -143,6 +143,7 @@ struct mmlst_ctx {
     DevBuf ix_locus_of, ix_locus_rows, ix_locus_start, ix_allele_num, ix_species_of_locus, ix_genes_in_db, ix_db_ascii, ix_db_off, ix_bam_ln, ix_zero64, ix_scratch,
            ix_out, ix_db_start, ix_chunks;
     uint32_t ix_n_ref = 0, ix_n_loci = 0, ix_n_species = 0;
+    bool ix_rows_identity = false;   // allele rows already grouped by locus: mmlst_select_dev gets no row list
     std::vector<uint32_t> ix_bam_ln_h; std::vector<uint64_t> ix_db_off_h;
     // copy lanes: the pileup records of the chosen contigs are ~2 ranges per contig; spread over a few streams their DMA set-up overlaps
     static constexpr int kLanes = 3;
@@ -702,6 +703,8 @@ extern "C" int mmlst_index_upload(mmlst_ctx* c, const mmlst_index* ix) {
     cudaStream_t s = c->stream;
     TRY(h2d(c->ix_locus_of, ix->locus_of, nr, s));
     TRY(h2d(c->ix_locus_rows, rows.data(), nr, s));
+    c->ix_rows_identity = true;
+    for (uint32_t t = 0; t < nr; ++t) if (rows[t] != t) { c->ix_rows_identity = false; break; }
     TRY(h2d(c->ix_locus_start, start.data(), (size_t)nl + 1, s));
     TRY(h2d(c->ix_allele_num, ix->allele_num, nr, s));
     TRY(h2d(c->ix_species_of_locus, ix->species_of_locus, nl, s));
@@ -758,7 +761,7 @@ extern "C" int mmlst_sample(mmlst_ctx* c, const mmlst_soa* soa, const uint8_t* a
     }
     uint32_t* h_zact = reinterpret_cast<uint32_t*>(h_tab + tab_bytes);
     if (c->z_pending) CUDA_TRY(cudaMemcpyAsync(h_zact, c->zact.p, (size_t)c->z_pending * 4, cudaMemcpyDeviceToHost, s));
-    TRY(mmlst_select_dev(c->sum_as.as<int64_t>(), c->n_hit.as<uint32_t>(), c->first_idx.as<uint32_t>(), c->ix_locus_rows.as<uint32_t>(),
+    TRY(mmlst_select_dev(c->sum_as.as<int64_t>(), c->n_hit.as<uint32_t>(), c->first_idx.as<uint32_t>(), c->ix_rows_identity ? nullptr : c->ix_locus_rows.as<uint32_t>(),
                          c->ix_locus_start.as<uint32_t>(), c->ix_allele_num.as<uint32_t>(), (uint32_t)nr, c->ix_species_of_locus.as<uint32_t>(),
                          c->ix_genes_in_db.as<uint32_t>(), nl, c->ix_n_species, prm->penalty, prm->nloci_pct, c->ix_zero64.as<uint64_t>(),
                          c->ix_bam_ln.as<uint32_t>(), c->ix_db_off.as<uint64_t>(), 512, c->ix_scratch.p, (size_t)nl * 12 + 64, d_hdr, d_tid, d_sp, d_col,

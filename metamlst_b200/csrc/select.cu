@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
 #pragma unroll
     for (int k = 0; k < SEL_R; ++k) {
         const uint32_t i = r0 + k * SEL_THREADS + threadIdx.x;
-        tt[k] = (i < r1) ? a.locus_rows[i] : 0xffffffffu;
+        tt[k] = (i < r1) ? (a.locus_rows ? a.locus_rows[i] : i) : 0xffffffffu;   // no row list = allele rows already grouped by locus: one trip to memory less
     }
 #pragma unroll
     for (int k = 0; k < SEL_R; ++k) {
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
     for (int k = 0; k < SEL_R; ++k)
         if (nn[k]) { mx = max(mx, nn[k]); fmin = min(fmin, ff[k]); }
     for (uint32_t i = rest0; i < r1; i += SEL_THREADS) {
-        const uint32_t t = a.locus_rows[i];
+        const uint32_t t = a.locus_rows ? a.locus_rows[i] : i;
         const uint32_t n = a.n_hit[t];
         if (n) { mx = max(mx, n); fmin = min(fmin, a.first_idx[t]); }
     }
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
             best = tk[k] > best ? tk[k] : best;
         }
         for (uint32_t i = rest0; i < r1; i += SEL_THREADS) {
-            const uint32_t t = a.locus_rows[i];
+            const uint32_t t = a.locus_rows ? a.locus_rows[i] : i;
             const uint32_t n = a.n_hit[t];
             if (n) { const unsigned long long v = static_cast<unsigned long long>(tenths_of(a.sum_as[t], n, mx, a.penalty)) + T_BIAS; best = v > best ? v : best; }
         }
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
             if (a.flags & MMLST_SELECT_CONSUME) { a.sum_as[tt[k]] = 0; a.n_hit[tt[k]] = 0; a.first_idx[tt[k]] = 0xffffffffu; }
         }
         for (uint32_t i = rest0; i < r1; i += SEL_THREADS) {
-            const uint32_t t = a.locus_rows[i];
+            const uint32_t t = a.locus_rows ? a.locus_rows[i] : i;
             const uint32_t n = a.n_hit[t];
             if (!n) continue;
             if (static_cast<unsigned long long>(tenths_of(a.sum_as[t], n, mx, a.penalty)) + T_BIAS == best) {
@@ -183,7 +183,18 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
             if (a.flags & MMLST_SELECT_CONSUME) { a.sum_as[t] = 0; a.n_hit[t] = 0; a.first_idx[t] = 0xffffffffu; }
         }
         key = block_reduce_u64(key, sh64, false);
-        if (threadIdx.x == 0) { a.res_key[l] = key; a.res_first[l] = ~nfmax; }
+        if (threadIdx.x == 0) {
+            a.res_key[l] = key; a.res_first[l] = ~nfmax;
+            // what the finalizing CTA will read for this locus's chosen row (record range, BAM LN, DB offset) is asked into the L2 now: it arrives while
+            // the ticket travels, instead of costing the finalizer a trip to HBM on its serial path
+            const uint32_t row = static_cast<uint32_t>(key & 0xffffffffull);
+            if (key != ~0ull && row < a.n_ref) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.contig_start + row));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.contig_start + row + 1));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ref_len + row));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.db_off + row));
+            }
+        }
     } else if (threadIdx.x == 0) {
         a.res_key[l] = ~0ull; a.res_first[l] = 0xffffffffu;
     }
@@ -343,7 +354,7 @@ extern "C" int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* firs
                                 uint32_t* header, uint32_t* chosen_tid, uint32_t* chosen_species, uint32_t* col_off,
                                 uint64_t* db_start, mmlst_chunk* chunks, uint32_t max_chunks, uint32_t flags,
                                 uint64_t* counters, uint32_t* chosen_first, void* stream) {
-    if (!sum_as || !n_hit || !first_idx || !locus_rows || !locus_start || !allele_num || !species_of_locus || !genes_in_db ||
+    if (!sum_as || !n_hit || !first_idx || !locus_start || !allele_num || !species_of_locus || !genes_in_db ||
         !contig_start || !ref_len || !db_off || !scratch || !header || !chosen_tid || !chosen_species || !col_off || !db_start || !chunks) {
         mmlst_set_error("mmlst_select_dev: null pointer");
         return MMLST_E_ARG;

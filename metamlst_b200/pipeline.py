@@ -105,7 +105,8 @@ class DevicePipeline:
         nl = index.n_loci
         self.scratch = torch.zeros(nl * 12 + 64, dtype=torch.uint8, device=dev)
         order = np.argsort(index.locus_of, kind="stable").astype(np.uint32)  # allele rows grouped by locus
-        self.locus_rows = t32(order.view(np.int32))
+        # rows already grouped by locus (a DB dumped gene by gene): no row list, the selection kernel saves a dependent trip to memory
+        self.locus_rows = None if np.array_equal(order, np.arange(order.shape[0], dtype=order.dtype)) else t32(order.view(np.int32))
         self.locus_start = t32(np.searchsorted(index.locus_of[order], np.arange(nl + 1)).astype(np.int32))
         # ONE output block => one D2H node per pass: int32 header[16] | chosen_tid[nl] | chosen_species[nl] | col_off[nl+1] |
         # holes[nl] | snps[nl] | pad, then the consensus bytes
@@ -705,7 +706,8 @@ def device_select(index: api.AlleleIndex, sum_as: np.ndarray, n_hit: np.ndarray,
     d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     t_sum, t_n, t_f = d(sum_as.astype(np.int64)), d(n_hit.astype(np.uint32).view(np.int32)), d(first_idx.astype(np.uint32).view(np.int32))
     order = np.argsort(index.locus_of, kind="stable").astype(np.uint32)
-    t_rows, t_start = d(order.view(np.int32)), d(np.searchsorted(index.locus_of[order], np.arange(nl + 1)).astype(np.int32))
+    identity = np.array_equal(order, np.arange(order.shape[0], dtype=order.dtype))   # rows already grouped by locus: no row list (include/mmlst.h)
+    t_rows, t_start = (None if identity else d(order.view(np.int32))), d(np.searchsorted(index.locus_of[order], np.arange(nl + 1)).astype(np.int32))
     t_an = d(np.asarray([int(a) for a in index.allele], np.int64).astype(np.uint32).view(np.int32))
     t_sol, t_gdb = d(sol), d(gdb)
     t_cs, t_rl, t_dbo = d(np.zeros(n_ref + 1, np.int64)), d(np.ones(n_ref, np.int32)), d(np.zeros(n_ref + 1, np.int64))

@@ -460,8 +460,11 @@ def test_device_selection_rounding_and_order_match_python(ctx):
     from metamlst_b200 import pipeline
     rng = np.random.default_rng(7)
     names = ["s%d_g%d_%d" % (sp, g, a) for sp in range(3) for g in range(4) for a in (7, 3, 12, 1, 25, 2)]
-    index = api.AlleleIndex(names)
+    grouped = api.AlleleIndex(names)                                  # allele rows grouped by locus: the kernel runs without a row list
+    mixed = api.AlleleIndex([names[i] for i in rng.permutation(len(names))])   # loci interleaved: the row list is used
+    assert np.all(np.diff(grouped.locus_of.astype(np.int64)) >= 0) and np.any(np.diff(mixed.locus_of.astype(np.int64)) < 0)
     for trial in range(60):
+        index = grouped if trial % 2 == 0 else mixed
         n = rng.integers(0, 40, size=len(names)).astype(np.uint32)
         n[rng.random(len(names)) < 0.3] = 0
         # sums chosen so that many quotients land on / next to x.x5 ties
@@ -527,6 +530,23 @@ def test_device_pipeline_equals_host_selected_path_and_oracle(ctx, case, kernel_
             t = index.name_to_tid[contig]
             want, _ = corc.contig_counts(stab, t, 20, 2 * kw["L"] - 30, 4, 8000)
             assert (seq, holes, snps) == corc.consensus(want, db.row_seq(t).encode(), 1)
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 1003, 65536 + 5])
+def test_as_untransform_is_exact_for_any_length(n):
+    """mmlst_as_untransform_dev (as0[i] -= coeff * xm3[i], in place): eight records per thread plus a scalar tail, against numpy for lengths around the
+    vector width, negative and extreme values that stay inside int16 after the subtraction."""
+    import torch
+    rng = np.random.default_rng(n)
+    xm = rng.integers(0, 256, n, dtype=np.uint8)
+    for coeff in (6, -3, 0):
+        want = rng.integers(-20000, 20000, n).astype(np.int16)
+        stored = (want.astype(np.int32) + coeff * xm.astype(np.int32)).astype(np.int16)
+        a = torch.from_numpy(stored.copy()).cuda() if n else torch.zeros(0, dtype=torch.int16, device="cuda")
+        x = torch.from_numpy(xm.copy()).cuda() if n else torch.zeros(0, dtype=torch.uint8, device="cuda")
+        native.check(native.lib().mmlst_as_untransform_dev(native.ptr(a) if n else 0, native.ptr(x) if n else 0, n, coeff, torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert np.array_equal(a.cpu().numpy(), want)
 
 
 def test_sample_lanes_keep_several_samples_in_flight_with_type_soa_results(ctx):
