@@ -27,6 +27,7 @@ __global__ void kernT(unsigned long long* endt, const unsigned char* src, int by
     for (int r = 0; r < rounds; ++r) {
         if (threadIdx.x == 0) {
             size_t off = ((size_t)blockIdx.x * rounds + r) * bytes;
+            if (touch & 16) off += 16 + 16 * (blockIdx.x % 7);   // 16-byte aligned only, like a plane range that starts anywhere in the stream
             if (touch & 8) {   // geometry first: two read-only 16-byte loads whose values decide the source offset
                 const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(src + off)), g1 = __ldg(reinterpret_cast<const uint4*>(src + off + bytes - 16));
                 off += ((g0.y + g1.y) & 0u);
@@ -53,6 +54,39 @@ __global__ void kernT(unsigned long long* endt, const unsigned char* src, int by
     }
     if (stagger_ns) { const unsigned long long t0 = gt(); const unsigned long long d = (unsigned long long)(blockIdx.x % 16) * stagger_ns / 16; while (gt() - t0 < d) { } }
     if (inval && threadIdx.x == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(su32(&bar)) : "memory");
+    if (threadIdx.x == 0) endt[blockIdx.x] = gt();
+}
+// kernT with ~128 live registers per thread (two such CTAs fill the register file of an SM, like the pileup kernel's)
+__global__ void __launch_bounds__(256, 2) kernTR(unsigned long long* endt, const unsigned char* src, int bytes, int rounds, unsigned* sink) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    __shared__ __align__(8) unsigned long long bar;
+    unsigned r[96];
+#pragma unroll
+    for (int i = 0; i < 96; ++i) r[i] = threadIdx.x * 2654435761u + i;
+    if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(su32(&bar))); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    unsigned phase = 0;
+    for (int k = 0; k < rounds; ++k) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(su32(&bar)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(su32(sm)),
+                         "l"(src + ((size_t)blockIdx.x * rounds + k) * bytes), "r"(bytes), "r"(su32(&bar)) : "memory");
+        }
+        unsigned done;
+        do { asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(su32(&bar)), "r"(phase) : "memory"); } while (!done);
+        phase ^= 1;
+        // bit-sliced style work on what arrived: every register stays live across the rounds
+        for (int i = threadIdx.x * 4; i + 4 <= bytes; i += blockDim.x * 4 * 8) {
+            const unsigned v = *reinterpret_cast<const unsigned*>(sm + i);
+#pragma unroll
+            for (int j = 0; j < 96; ++j) r[j] = (r[j] ^ v) + (r[(j + 1) % 96] & v);
+        }
+        __syncthreads();
+    }
+    unsigned acc = 0;
+#pragma unroll
+    for (int i = 0; i < 96; ++i) acc ^= r[i];
+    if (acc == 0x12345678u) sink[0] = acc;
     if (threadIdx.x == 0) endt[blockIdx.x] = gt();
 }
 __global__ void kernB(unsigned long long* startt) { if (threadIdx.x == 0) startt[blockIdx.x] = gt(); }
@@ -88,9 +122,10 @@ int main() {
         cudaFuncSetAttribute(kernT, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         { int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernT, 256, 110 * 1024); printf("kernT resident CTAs per SM at 110 KB: %d\n", occ); }
         cudaGraphExec_t graphs[16] = {nullptr}; int gi = -1;
-        for (int bytes : {49152}) for (int inval = 0; inval < 2; ++inval) for (int cold = 1; cold < 2; ++cold) {
+        for (int bytes : {49152 - 208}) for (int inval = 0; inval < 2; ++inval) for (int cold = 1; cold < 2; ++cold) {
             ++gi;
-            const int stagger = 0, touch = (inval & 1) ? 13 : 0;
+            const int stagger = 0, touch = (inval & 1) ? 13 + 16 : 16;
+            if (inval & 1) bytes -= 0;
             const int smem_kb = 110;   // 2 CTAs per SM (occupancy printed above)
             std::vector<double> gaps, durs;
             for (int rep = 0; rep < 12; ++rep) {
@@ -116,6 +151,39 @@ int main() {
             printf("GRAPH smem %d KB: bulk copies 3 x %5d B per CTA, 296 CTAs, mode %d (1 = smem touched, 4 = two copies per barrier, 8 = geometry loads first), cold L2 %d : prev-kernel-entry -> last CTA end median %.2f us;  gap last-CTA-end -> next-kernel-entry  min %.2f median %.2f max %.2f us\n",
                    smem_kb, bytes, touch, cold, durs[durs.size() / 2], gaps.front(), gaps[gaps.size() / 2], gaps.back());
         }
+    }
+    {   // register-heavy variant, 2 CTAs per SM
+        unsigned char* src; cudaMalloc(&src, (size_t)296 * 3 * 49152 + 4096); cudaMemset(src, 1, (size_t)296 * 3 * 49152);
+        unsigned char* flush; cudaMalloc(&flush, 256u << 20);
+        cudaFuncSetAttribute(kernTR, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        cudaFuncSetAttribute(kernTR, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kernTR);
+        int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernTR, 256, 111 * 1024);
+        printf("kernTR: %d registers, %d resident CTAs per SM\n", fa.numRegs, occ);
+        cudaGraphExec_t ge = nullptr;
+        std::vector<double> gaps, durs;
+        for (int rep = 0; rep < 12; ++rep) {
+            cudaMemsetAsync(dA, 0, 4096 * 8, s); cudaMemsetAsync(dB, 0, 4096 * 8, s);
+            cudaMemsetAsync(flush, rep, 256u << 20, s);
+            if (!ge) {
+                cudaGraph_t g;
+                cudaStreamBeginCapture(s, cudaStreamCaptureModeGlobal);
+                kernB<<<21, 512, 0, s>>>(dB + 1024);
+                kernTR<<<296, 256, 111 * 1024, s>>>(dA, src, 49152, 3, (unsigned*)dB + 4000);
+                kernB<<<21, 512, 0, s>>>(dB);
+                cudaStreamEndCapture(s, &g);
+                cudaGraphInstantiate(&ge, g, 0);
+            }
+            cudaGraphLaunch(ge, s);
+            cudaStreamSynchronize(s);
+            std::vector<unsigned long long> a(296), b(21), b0(21);
+            cudaMemcpy(a.data(), dA, 296 * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b.data(), dB, 21 * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b0.data(), dB + 1024, 21 * 8, cudaMemcpyDeviceToHost);
+            const unsigned long long ea = *std::max_element(a.begin(), a.end()), sb = *std::min_element(b.begin(), b.end()), s0 = *std::min_element(b0.begin(), b0.end());
+            if (rep >= 2) { gaps.push_back((double)(sb - ea) / 1e3); durs.push_back((double)(ea - s0) / 1e3); }
+        }
+        std::sort(gaps.begin(), gaps.end()); std::sort(durs.begin(), durs.end());
+        printf("GRAPH register-heavy: prev-kernel-entry -> last CTA end median %.2f us;  gap last-CTA-end -> next-kernel-entry  min %.2f median %.2f max %.2f us\n",
+               durs[durs.size() / 2], gaps.front(), gaps[gaps.size() / 2], gaps.back());
     }
     cudaError_t e = cudaGetLastError();
     printf("status %s\n", cudaGetErrorString(e));
