@@ -236,6 +236,11 @@ int mmlst_consensus_dev(const uint32_t* counts, const uint8_t* dbseq, const uint
  *   given; chosen_tid / chosen_species / col_off / db_start per chosen locus in output order; chunks for
  *   mmlst_pileup_indirect_dev.  header needs 16 words.
  * --------------------------------------------------------------------------------------------------------------- */
+/* Finalization of the selection (gate, dict order, column layout, chunk list) by ONE warp with shuffles instead of the whole last CTA with barriers, when
+ * n_loci <= 32 and n_species <= 32 (larger index sets always take the CTA-wide form).  1 = on, 0 = off, other = query; returns the previous value;
+ * MMLST_SELECT_WARP presets it.  Results do not depend on it (tests/test_gpu_parity.py runs the selection tests under both). */
+#define MMLST_SELECT_WARP_DEFAULT 0
+int mmlst_set_select_warp_finalize(int on);
 #define MMLST_SELECT_CONSUME 1u
 #define MMLST_SELECT_SCRATCH_CLEAN 2u
 #define MMLST_SELECT_LOCAL 4u  /* this GPU owns a SUBSET of the loci (contig-aligned shard): no --nloci gate here; the caller

@@ -8,6 +8,8 @@
 // H6: Python's round(x, 1) is the correctly rounded decimal (ties on the exact binary value go to the even digit).
 // Two rounded values are equal iff their integer tenths T are equal, and T is computed here exactly from the bits of
 // the IEEE double x = (double)localScore / (double)n (same correctly rounded division as Python's float division).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -57,6 +59,7 @@ struct SelArgs {
     uint32_t* chosen_tid; uint32_t* chosen_species; uint32_t* col_off; unsigned long long* db_start;
     mmlst_chunk* chunks; uint32_t max_chunks;
     unsigned long long* tl;  // profiling aid (mmlst_debug_timeline), nullptr = off
+    uint32_t warp_final;     // finalize with ONE warp and no CTA barrier when n_loci, n_species <= 32 (mmlst_set_select_warp_finalize)
     uint32_t* chosen_first;  // optional: first passing record of every chosen locus (owner-computes merge across GPUs)
 };
 
@@ -92,6 +95,120 @@ __device__ __forceinline__ unsigned long long block_reduce_u64(unsigned long lon
 #pragma unroll
     for (int i = 1; i < SEL_THREADS / 32; ++i) { const unsigned long long x = sh[i]; r = want_max ? (x > r ? x : r) : (x < r ? x : r); }
     return r;
+}
+
+// Finalization by ONE warp (n_loci <= 32, n_species <= 32: every MLST scheme set a sample is typed against): lane m owns locus m, what the CTA-wide form
+// does with nine barriers and shared-memory atomics is done with shuffles, so the serial tail of the launch is two dependent reads plus warp arithmetic.
+// Same outputs as the CTA-wide form below, statement for statement (gate, H5 order keys, ranks, column layout, chunk list).
+__device__ void finalize_warp(const SelArgs& a, const uint32_t* s_sol, const uint32_t* s_gdb, uint32_t* sm) {
+    constexpr uint32_t FULLM = 0xffffffffu;
+    const uint32_t lane = threadIdx.x;   // caller: threadIdx.x < 32
+    const uint32_t nl = a.n_loci;
+    unsigned long long cnt0 = 0, cnt1 = 0;
+    if (lane == 0 && a.counters) { cnt0 = __ldcg(a.counters); cnt1 = __ldcg(a.counters + 1); }
+    if (lane == 0) *a.done = 0;
+    const bool v = lane < nl;
+    const unsigned long long ck = v ? __ldcg(a.res_key + lane) : ~0ull;
+    const uint32_t lf = v ? __ldcg(a.res_first + lane) : 0xffffffffu;
+    const bool det = v && ck != ~0ull;
+    const uint32_t tid = static_cast<uint32_t>(ck & 0xffffffffull);
+    const uint32_t sp = v ? s_sol[lane] : 0xffffffffu;
+    // what hangs off the chosen row: requested now (the per-locus CTAs asked it into the L2), used after the ranking
+    unsigned long long q0 = 0, q1 = 0, dbo = 0;
+    uint32_t ln = 0;
+    if (det) { q0 = a.contig_start[tid]; q1 = a.contig_start[tid + 1]; ln = a.ref_len[tid]; dbo = a.db_off[tid]; }
+    tl_mark(a.tl, MMLST_TL_SELECT, 5);
+    // per species: detected loci and the first passing record of the species (metamlst.py:181-206)
+    uint32_t det_cnt = 0, sp_first = 0xffffffffu;
+    for (uint32_t j = 0; j < nl; ++j) {
+        const uint32_t spj = __shfl_sync(FULLM, sp, j), lfj = __shfl_sync(FULLM, lf, j);
+        const bool dj = __shfl_sync(FULLM, det ? 1u : 0u, j) != 0u;
+        if (dj && spj == sp) { ++det_cnt; sp_first = min(sp_first, lfj); }
+    }
+    uint32_t pass = 0, broken = 0;
+    if (det) {
+        const uint32_t tot = s_gdb[sp];
+        if (a.flags & MMLST_SELECT_LOCAL) pass = 1;
+        else if (tot < det_cnt) broken = 1;   // "Database is broken" (metamlst.py:188-190)
+        else pass = int((double(det_cnt) / double(tot)) * 100.0) >= a.nloci_pct;   // metamlst.py:206
+    }
+    uint32_t err = __any_sync(FULLM, broken) ? 1u : 0u;
+    const bool kept = det && pass;
+    const unsigned long long key = kept ? ((static_cast<unsigned long long>(sp_first) << 32) | lf) + 1ull : 0ull;
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < nl; ++j) {
+        const unsigned long long k2 = __shfl_sync(FULLM, key, j);
+        rank += (k2 != 0ull) && ((k2 < key) || (k2 == key && j < lane));
+    }
+    const uint32_t nsel = __popc(__ballot_sync(FULLM, kept));
+    // output order: lane i takes the locus whose rank is i
+    uint32_t* s_inv = sm;   // [32] warp-private from here on (the other warps of the CTA have left)
+    if (kept) s_inv[rank] = lane;
+    __syncwarp();
+    const bool o = lane < nsel;
+    const uint32_t src = o ? s_inv[lane] : 0u;
+    const uint32_t o_tid = __shfl_sync(FULLM, tid, src), o_sp = __shfl_sync(FULLM, sp, src), o_lf = __shfl_sync(FULLM, lf, src), o_len = __shfl_sync(FULLM, ln, src);
+    const unsigned long long o_q0 = __shfl_sync(FULLM, q0, src), o_q1 = __shfl_sync(FULLM, q1, src), o_dbo = __shfl_sync(FULLM, dbo, src);
+    const uint32_t o_nrec = o ? static_cast<uint32_t>(o_q1 - o_q0) : 0u;
+    unsigned long long totrec = o ? (o_q1 - o_q0) : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) totrec += __shfl_xor_sync(FULLM, totrec, d);
+    tl_mark(a.tl, MMLST_TL_SELECT, 6);
+    uint32_t cr = a.chunk_records;
+    if (cr == 0) cr = 512u * mmlst_chunk_tiles(totrec, a.slots);   // same rule as mmlst_chunk_records()
+    uint32_t nch_i = 0;
+    if (o) { const uint32_t k = (o_nrec + cr - 1) / cr; nch_i = k ? k : 1u; }   // a chosen locus without pileup records still gets one (empty) chunk
+    // exclusive prefixes in output order: first column and first chunk of every chosen locus
+    uint32_t col_inc = o ? o_len : 0u, ch_inc = nch_i;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t c2 = __shfl_up_sync(FULLM, col_inc, d), h2 = __shfl_up_sync(FULLM, ch_inc, d);
+        if (lane >= static_cast<uint32_t>(d)) { col_inc += c2; ch_inc += h2; }
+    }
+    const uint32_t col_ex = col_inc - (o ? o_len : 0u), ch_ex = ch_inc - nch_i;
+    const uint32_t tot_cols = __shfl_sync(FULLM, col_inc, 31), tot_ch = __shfl_sync(FULLM, ch_inc, 31);
+    if (tot_ch > a.max_chunks) err |= 2u;
+    uint32_t* s_cbase = sm + 32;    // [33]
+    uint32_t* s_q0 = s_cbase + 33;  // [32]
+    uint32_t* s_nrec = s_q0 + 32;   // [32]
+    uint32_t* s_col = s_nrec + 32;  // [32]
+    uint32_t* s_len = s_col + 32;   // [32]
+    if (o) {
+        a.chosen_tid[lane] = o_tid;
+        a.chosen_species[lane] = o_sp;
+        if (a.chosen_first) a.chosen_first[lane] = o_lf;
+        a.db_start[lane] = o_dbo;
+        a.col_off[lane] = col_ex;
+        s_cbase[lane] = ch_ex; s_q0[lane] = static_cast<uint32_t>(o_q0); s_nrec[lane] = o_nrec; s_col[lane] = col_ex; s_len[lane] = o_len;
+    }
+    if (lane == 0) {
+        a.col_off[nsel] = tot_cols;
+        s_cbase[nsel] = tot_ch;
+        a.header[0] = nsel; a.header[1] = min(tot_ch, a.max_chunks); a.header[2] = tot_cols; a.header[3] = err; a.header[4] = cr;
+        if (a.counters) {  // totalReads / ignoredReads travel with the header; consumed like the tables
+            a.header[6] = static_cast<uint32_t>(cnt0); a.header[7] = static_cast<uint32_t>(cnt0 >> 32);
+            a.header[8] = static_cast<uint32_t>(cnt1); a.header[9] = static_cast<uint32_t>(cnt1 >> 32);
+            if (a.flags & MMLST_SELECT_CONSUME) { a.counters[0] = 0; a.counters[1] = 0; }
+        }
+    }
+    __syncwarp();
+    tl_mark(a.tl, MMLST_TL_SELECT, 7);
+    const uint32_t nch = min(tot_ch, a.max_chunks);
+    for (uint32_t c = lane; c < nch; c += 32) {
+        uint32_t lo = 0, hi = nsel;  // last i with s_cbase[i] <= c
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_cbase[mid] <= c) lo = mid; else hi = mid; }
+        const unsigned long long b0 = s_q0[lo], b1 = b0 + s_nrec[lo];
+        const unsigned long long b = b0 + static_cast<unsigned long long>(c - s_cbase[lo]) * cr;
+        mmlst_chunk ckk;
+        ckk.rec_begin = static_cast<uint32_t>(b);
+        ckk.rec_end = static_cast<uint32_t>(b + cr < b1 ? b + cr : b1);
+        ckk.col_base = s_col[lo]; ckk.contig_len = s_len[lo]; ckk.plane_delta = 0;
+        ckk.reserved[0] = lo;
+        ckk.reserved[1] = s_cbase[lo + 1] - s_cbase[lo];
+        ckk.reserved[2] = 0;
+        a.chunks[c] = ckk;
+    }
+    tl_mark(a.tl, MMLST_TL_SELECT, 4);
 }
 
 // ONE launch for the whole selection.  CTA = one locus: its allele rows (locus_rows[locus_start[l] .. locus_start[l+1]))
@@ -209,6 +326,10 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
     tl_mark(a.tl, MMLST_TL_SELECT, 3, s_last);   // the ticket is back
     if (!s_last) return;
     __threadfence();
+    if (a.warp_final && a.n_loci <= 32u && a.n_species <= 32u) {
+        if (threadIdx.x < 32) finalize_warp(a, s_sol, s_gdb, sm);
+        return;
+    }
 
     // ---- last CTA: finalize.  Two dependent round trips to memory: the per-locus results, then what hangs off the chosen rows
     // (record range, BAM LN, DB offset); everything else comes from shared memory.
@@ -345,6 +466,21 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
 
 }  // namespace
 
+static int g_select_warp = -1;
+static int select_warp() {
+    if (g_select_warp < 0) {
+        const char* e = getenv("MMLST_SELECT_WARP");
+        g_select_warp = e ? (e[0] == '1') : MMLST_SELECT_WARP_DEFAULT;
+    }
+    return g_select_warp;
+}
+// see include/mmlst.h
+extern "C" int mmlst_set_select_warp_finalize(int on) {
+    const int prev = select_warp();
+    if (on == 0 || on == 1) g_select_warp = on;
+    return prev;
+}
+
 // see include/mmlst.h
 extern "C" int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* first_idx, const uint32_t* locus_rows,
                                 const uint32_t* locus_start, const uint32_t* allele_num, uint32_t n_ref,
@@ -382,9 +518,11 @@ extern "C" int mmlst_select_dev(int64_t* sum_as, uint32_t* n_hit, uint32_t* firs
     a.db_start = reinterpret_cast<unsigned long long*>(db_start); a.chunks = chunks; a.max_chunks = max_chunks;
     a.chosen_first = chosen_first;
     a.tl = mmlst_timeline_buffer();
+    a.warp_final = select_warp() ? 1u : 0u;
     if (!(flags & MMLST_SELECT_SCRATCH_CLEAN)) CUDA_TRY(cudaMemsetAsync(a.done, 0, 4, s));
     // finalization arrays (10 n_loci + 1 + 3 n_species words, see the kernel) + the prefetched species_of_locus / genes_in_db
-    const size_t smem = sizeof(uint32_t) * (static_cast<size_t>(n_loci) * 11 + 1 + 4 * static_cast<size_t>(n_species)) + 16;
+    size_t smem = sizeof(uint32_t) * (static_cast<size_t>(n_loci) * 11 + 1 + 4 * static_cast<size_t>(n_species)) + 16;
+    if (smem < 200 * sizeof(uint32_t)) smem = 200 * sizeof(uint32_t);   // the one-warp finalizer lays out 193 words whatever n_loci is
     static size_t configured_by_device[MMLST_MAX_DEVICES] = {0};  // 0 = the 48 KB every kernel starts with
     size_t& configured = configured_by_device[mmlst_current_device()];
     if (configured == 0) configured = 48 * 1024;

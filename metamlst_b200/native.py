@@ -90,6 +90,7 @@ EXPORTS = {
     "mmlst_set_score_l2_hints": (C.c_int, [C.c_int]),
     "mmlst_set_score_grid_scale": (C.c_int, [C.c_int]),
     "mmlst_debug_timeline": (C.c_int, [C.c_void_p]),
+    "mmlst_set_select_warp_finalize": (C.c_int, [C.c_int]),
     "mmlst_as_untransform_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
     "mmlst_set_pdl": (C.c_int, [C.c_int]),
     "mmlst_expand_runs_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),

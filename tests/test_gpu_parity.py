@@ -463,8 +463,10 @@ def test_device_selection_rounding_and_order_match_python(ctx):
     grouped = api.AlleleIndex(names)                                  # allele rows grouped by locus: the kernel runs without a row list
     mixed = api.AlleleIndex([names[i] for i in rng.permutation(len(names))])   # loci interleaved: the row list is used
     assert np.all(np.diff(grouped.locus_of.astype(np.int64)) >= 0) and np.any(np.diff(mixed.locus_of.astype(np.int64)) < 0)
+    prev_warp = native.lib().mmlst_set_select_warp_finalize(-1)
     for trial in range(60):
         index = grouped if trial % 2 == 0 else mixed
+        native.lib().mmlst_set_select_warp_finalize(1 if trial % 4 < 2 else 0)   # one-warp and CTA-wide finalization, same answers
         n = rng.integers(0, 40, size=len(names)).astype(np.uint32)
         n[rng.random(len(names)) < 0.3] = 0
         # sums chosen so that many quotients land on / next to x.x5 ties
@@ -478,6 +480,7 @@ def test_device_selection_rounding_and_order_match_python(ctx):
         want = [(sp, t) for sp, t in want_all if int((float(len(t)) / 4.0) * 100) >= nloci]
         got, err = pipeline.device_select(index, s, n, f, 100, nloci)
         assert err == 0 and got == want, (trial, got, want)
+    native.lib().mmlst_set_select_warp_finalize(prev_warp)
     # hand-made ties: 2705/20 = 135.25 -> 135.2 and 2704/20 = 135.2 tie; lowest allele number (3) must win over 7
     idx2 = api.AlleleIndex(["o_g_7", "o_g_3", "o_g_5"])
     got, _ = pipeline.device_select(idx2, np.array([2705, 2704, 2690], np.int64), np.array([20, 20, 20], np.uint32), np.array([0, 1, 2], np.uint32))
