@@ -238,7 +238,8 @@ int mmlst_consensus_dev(const uint32_t* counts, const uint8_t* dbseq, const uint
  * --------------------------------------------------------------------------------------------------------------- */
 /* Finalization of the selection (gate, dict order, column layout, chunk list) by ONE warp with shuffles instead of the whole last CTA with barriers, when
  * n_loci <= 32 and n_species <= 32 (larger index sets always take the CTA-wide form).  1 = on, 0 = off, other = query; returns the previous value;
- * MMLST_SELECT_WARP presets it.  Results do not depend on it (tests/test_gpu_parity.py runs the selection tests under both). */
+ * MMLST_SELECT_WARP presets it.  Results do not depend on it (tests/test_gpu_parity.py runs the selection tests under both).  B200, configs[1]: selection
+ * 9.0 us with it, 9.9 us without (profiles/r4b_tail_timeline_warp.json); off by default. */
 #define MMLST_SELECT_WARP_DEFAULT 0
 int mmlst_set_select_warp_finalize(int on);
 #define MMLST_SELECT_CONSUME 1u

@@ -191,10 +191,20 @@ __device__ void finalize_warp(const SelArgs& a, const uint32_t* s_sol, const uin
             if (a.flags & MMLST_SELECT_CONSUME) { a.counters[0] = 0; a.counters[1] = 0; }
         }
     }
-    __syncwarp();
+    if (lane == 0) { sm[194] = nsel; sm[195] = min(tot_ch, a.max_chunks); sm[196] = cr; }   // for the chunk list, written by the whole CTA
     tl_mark(a.tl, MMLST_TL_SELECT, 7);
-    const uint32_t nch = min(tot_ch, a.max_chunks);
-    for (uint32_t c = lane; c < nch; c += 32) {
+}
+
+// chunk descriptors from what finalize_warp left in shared memory (whole CTA, after one barrier): one warp needed 3.0 us for the ~300 of a capped
+// configs[1] sample, 256 threads 0.9 us
+__device__ void chunk_list_from_warp_layout(const SelArgs& a, const uint32_t* sm) {
+    const uint32_t* s_cbase = sm + 32;
+    const uint32_t* s_q0 = s_cbase + 33;
+    const uint32_t* s_nrec = s_q0 + 32;
+    const uint32_t* s_col = s_nrec + 32;
+    const uint32_t* s_len = s_col + 32;
+    const uint32_t nsel = sm[194], nch = sm[195], cr = sm[196];
+    for (uint32_t c = threadIdx.x; c < nch; c += blockDim.x) {
         uint32_t lo = 0, hi = nsel;  // last i with s_cbase[i] <= c
         while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_cbase[mid] <= c) lo = mid; else hi = mid; }
         const unsigned long long b0 = s_q0[lo], b1 = b0 + s_nrec[lo];
@@ -328,6 +338,8 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_locus(const SelArgs a) {
     __threadfence();
     if (a.warp_final && a.n_loci <= 32u && a.n_species <= 32u) {
         if (threadIdx.x < 32) finalize_warp(a, s_sol, s_gdb, sm);
+        __syncthreads();   // the layout of the chosen loci is in shared memory
+        chunk_list_from_warp_layout(a, sm);
         return;
     }
 
