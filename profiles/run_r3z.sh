@@ -1,6 +1,6 @@
 #!/bin/bash
 # what the driver runs at round end, on one GPU: GPU suite, smoke(), both bench arms with default flags
-T=${1:-r3y}
+T=${1:-r4c}
 timeout 2400 python -m pytest tests -x -q -m gpu > gpurun_out/${T}_pytest_gpu.log 2>&1; tail -3 gpurun_out/${T}_pytest_gpu.log
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; echo smoke rc=$?; tail -2 gpurun_out/${T}_smoke.log
 SECONDS=0; timeout 900 python bench.py --impl reference > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err; echo ref rc=$? wall=${SECONDS}s; SECONDS=0; true
