@@ -90,102 +90,76 @@ __global__ void __launch_bounds__(256, 2) kernTR(unsigned long long* endt, const
     if (threadIdx.x == 0) endt[blockIdx.x] = gt();
 }
 __global__ void kernB(unsigned long long* startt) { if (threadIdx.x == 0) startt[blockIdx.x] = gt(); }
+// one measurement: [marker kernel, kernel under test, marker kernel] replayed as a CUDA graph (kernel -> kernel edges without the host launch latency that
+// hides completion latency), cold L2; prints how long the kernel's CTAs ran and how long after the last of them the next kernel's first CTA started
+template <class Launch>
+static void measure(const char* what, cudaStream_t s, unsigned long long* dA, unsigned long long* dB, unsigned char* flush, int grid, Launch launch) {
+    cudaGraphExec_t ge = nullptr;
+    std::vector<double> gaps, durs;
+    for (int rep = 0; rep < 12; ++rep) {
+        cudaMemsetAsync(dA, 0, 4096 * 8, s); cudaMemsetAsync(dB, 0, 4096 * 8, s);
+        cudaMemsetAsync(flush, rep, 256u << 20, s);
+        if (!ge) {
+            cudaGraph_t g;
+            cudaStreamBeginCapture(s, cudaStreamCaptureModeGlobal);
+            kernB<<<21, 512, 0, s>>>(dB + 1024);
+            launch();
+            kernB<<<21, 512, 0, s>>>(dB);
+            cudaStreamEndCapture(s, &g);
+            cudaGraphInstantiate(&ge, g, 0);
+        }
+        cudaGraphLaunch(ge, s);
+        cudaStreamSynchronize(s);
+        std::vector<unsigned long long> a(grid), b(21), b0(21);
+        cudaMemcpy(a.data(), dA, grid * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b.data(), dB, 21 * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b0.data(), dB + 1024, 21 * 8, cudaMemcpyDeviceToHost);
+        const unsigned long long ea = *std::max_element(a.begin(), a.end()), sb = *std::min_element(b.begin(), b.end()), s0 = *std::min_element(b0.begin(), b0.end());
+        if (rep >= 2) { gaps.push_back((double)(sb - ea) / 1e3); durs.push_back((double)(ea - s0) / 1e3); }
+    }
+    std::sort(gaps.begin(), gaps.end()); std::sort(durs.begin(), durs.end());
+    printf("%-92s previous kernel's entry -> last CTA end %6.2f us | last CTA end -> next kernel's entry  min %.2f median %.2f max %.2f us\n", what, durs[durs.size() / 2],
+           gaps.front(), gaps[gaps.size() / 2], gaps.back());
+}
+
 int main() {
     unsigned long long *dA, *dB;
     cudaMalloc(&dA, 4096 * 8); cudaMalloc(&dB, 4096 * 8);
-    cudaFuncSetAttribute(kernA, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    unsigned char *src, *flush;
+    cudaMalloc(&src, (size_t)296 * 3 * 49152 + 4096); cudaMemset(src, 1, (size_t)296 * 3 * 49152 + 4096);
+    cudaMalloc(&flush, 256u << 20);
     cudaStream_t s; cudaStreamCreate(&s);
-    const int grids[] = {21, 148, 296, 592};
-    const int smems[] = {0, 48 * 1024, 110 * 1024, 220 * 1024};
-    for (int g : grids) for (int sm : smems) for (int touch = 0; touch < 2; ++touch) {
-        if (sm == 220 * 1024 && g > 148) continue;
-        if (sm == 110 * 1024 && g > 296) continue;
-        if (touch && sm == 0) continue;
+    cudaFuncSetAttribute(kernA, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    for (auto k : {(const void*)kernT, (const void*)kernTR}) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+    int occT = 0, occR = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, kernT, 256, 110 * 1024);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occR, kernTR, 256, 111 * 1024);
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kernTR);
+    printf("resident CTAs per SM: bulk-copy kernel %d, register-heavy kernel %d (%d registers)\n", occT, occR, fa.numRegs);
+    unsigned* sink = (unsigned*)dB + 4000;
+    // eager launches first: the host launch latency (~3 us) hides everything below it
+    for (int grid : {21, 296}) for (int smem : {0, 110 * 1024}) {
         std::vector<double> gaps;
         for (int rep = 0; rep < 12; ++rep) {
             cudaMemsetAsync(dA, 0, 4096 * 8, s); cudaMemsetAsync(dB, 0, 4096 * 8, s);
-            kernA<<<g, 256, sm, s>>>(dA, 5000, touch ? sm : 0);
+            kernA<<<grid, 256, smem, s>>>(dA, 5000, smem);
             kernB<<<21, 512, 0, s>>>(dB);
             cudaStreamSynchronize(s);
-            std::vector<unsigned long long> a(g), b(21);
-            cudaMemcpy(a.data(), dA, g * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b.data(), dB, 21 * 8, cudaMemcpyDeviceToHost);
-            const unsigned long long ea = *std::max_element(a.begin(), a.end()), sb = *std::min_element(b.begin(), b.end());
-            if (rep >= 2) gaps.push_back((double)(sb - ea) / 1e3);
+            std::vector<unsigned long long> a(grid), b(21);
+            cudaMemcpy(a.data(), dA, grid * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b.data(), dB, 21 * 8, cudaMemcpyDeviceToHost);
+            if (rep >= 2) gaps.push_back((double)(*std::min_element(b.begin(), b.end()) - *std::max_element(a.begin(), a.end())) / 1e3);
         }
         std::sort(gaps.begin(), gaps.end());
-        printf("grid %4d smem %6d touch %d : gap last-CTA-end -> next-kernel-entry  min %.2f median %.2f max %.2f us\n", g, sm, touch, gaps.front(), gaps[gaps.size() / 2], gaps.back());
+        printf("EAGER 5 us spin, grid %3d, %3d KB shared memory per CTA: last CTA end -> next kernel's entry median %.2f us\n", grid, smem >> 10, gaps[gaps.size() / 2]);
     }
-    {   // bulk-copy variant: 296 CTAs x 3 rounds x 47 KB (what the depth-capped pileup moves), and smaller
-        unsigned char* src; cudaMalloc(&src, (size_t)296 * 3 * 49152 + 4096); cudaMemset(src, 1, (size_t)296 * 3 * 49152);
-        unsigned char* flush; cudaMalloc(&flush, 256u << 20);
-        cudaFuncSetAttribute(kernT, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-        cudaFuncSetAttribute(kernT, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        { int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernT, 256, 110 * 1024); printf("kernT resident CTAs per SM at 110 KB: %d\n", occ); }
-        cudaGraphExec_t graphs[16] = {nullptr}; int gi = -1;
-        for (int bytes : {49152 - 208}) for (int inval = 0; inval < 2; ++inval) for (int cold = 1; cold < 2; ++cold) {
-            ++gi;
-            const int stagger = 0, touch = (inval & 1) ? 13 + 16 : 16;
-            if (inval & 1) bytes -= 0;
-            const int smem_kb = 110;   // 2 CTAs per SM (occupancy printed above)
-            std::vector<double> gaps, durs;
-            for (int rep = 0; rep < 12; ++rep) {
-                cudaMemsetAsync(dA, 0, 4096 * 8, s); cudaMemsetAsync(dB, 0, 4096 * 8, s);
-                if (cold) cudaMemsetAsync(flush, rep, 256u << 20, s);
-                if (!graphs[gi]) {   // the three launches as a CUDA graph: kernel -> kernel edges without the host launch latency that hides completion latency
-                    cudaGraph_t g;
-                    cudaStreamBeginCapture(s, cudaStreamCaptureModeGlobal);
-                    kernB<<<21, 512, 0, s>>>(dB + 1024);
-                    kernT<<<296, 256, smem_kb * 1024, s>>>(dA, src, bytes, 3, 0, stagger, touch, (unsigned*)dB + 4000);
-                    kernB<<<21, 512, 0, s>>>(dB);
-                    cudaStreamEndCapture(s, &g);
-                    cudaGraphInstantiate(&graphs[gi], g, 0);
-                }
-                cudaGraphLaunch(graphs[gi], s);
-                cudaStreamSynchronize(s);
-                std::vector<unsigned long long> a(296), b(21), b0(21);
-                cudaMemcpy(a.data(), dA, 296 * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b.data(), dB, 21 * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b0.data(), dB + 1024, 21 * 8, cudaMemcpyDeviceToHost);
-                const unsigned long long ea = *std::max_element(a.begin(), a.end()), sb = *std::min_element(b.begin(), b.end()), s0 = *std::min_element(b0.begin(), b0.end());
-                if (rep >= 2) { gaps.push_back((double)(sb - ea) / 1e3); durs.push_back((double)(ea - s0) / 1e3); }
-            }
-            std::sort(gaps.begin(), gaps.end()); std::sort(durs.begin(), durs.end());
-            printf("GRAPH smem %d KB: bulk copies 3 x %5d B per CTA, 296 CTAs, mode %d (1 = smem touched, 4 = two copies per barrier, 8 = geometry loads first), cold L2 %d : prev-kernel-entry -> last CTA end median %.2f us;  gap last-CTA-end -> next-kernel-entry  min %.2f median %.2f max %.2f us\n",
-                   smem_kb, bytes, touch, cold, durs[durs.size() / 2], gaps.front(), gaps[gaps.size() / 2], gaps.back());
-        }
-    }
-    {   // register-heavy variant, 2 CTAs per SM
-        unsigned char* src; cudaMalloc(&src, (size_t)296 * 3 * 49152 + 4096); cudaMemset(src, 1, (size_t)296 * 3 * 49152);
-        unsigned char* flush; cudaMalloc(&flush, 256u << 20);
-        cudaFuncSetAttribute(kernTR, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        cudaFuncSetAttribute(kernTR, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kernTR);
-        int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernTR, 256, 111 * 1024);
-        printf("kernTR: %d registers, %d resident CTAs per SM\n", fa.numRegs, occ);
-        cudaGraphExec_t ge = nullptr;
-        std::vector<double> gaps, durs;
-        for (int rep = 0; rep < 12; ++rep) {
-            cudaMemsetAsync(dA, 0, 4096 * 8, s); cudaMemsetAsync(dB, 0, 4096 * 8, s);
-            cudaMemsetAsync(flush, rep, 256u << 20, s);
-            if (!ge) {
-                cudaGraph_t g;
-                cudaStreamBeginCapture(s, cudaStreamCaptureModeGlobal);
-                kernB<<<21, 512, 0, s>>>(dB + 1024);
-                kernTR<<<296, 256, 111 * 1024, s>>>(dA, src, 49152, 3, (unsigned*)dB + 4000);
-                kernB<<<21, 512, 0, s>>>(dB);
-                cudaStreamEndCapture(s, &g);
-                cudaGraphInstantiate(&ge, g, 0);
-            }
-            cudaGraphLaunch(ge, s);
-            cudaStreamSynchronize(s);
-            std::vector<unsigned long long> a(296), b(21), b0(21);
-            cudaMemcpy(a.data(), dA, 296 * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b.data(), dB, 21 * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b0.data(), dB + 1024, 21 * 8, cudaMemcpyDeviceToHost);
-            const unsigned long long ea = *std::max_element(a.begin(), a.end()), sb = *std::min_element(b.begin(), b.end()), s0 = *std::min_element(b0.begin(), b0.end());
-            if (rep >= 2) { gaps.push_back((double)(sb - ea) / 1e3); durs.push_back((double)(ea - s0) / 1e3); }
-        }
-        std::sort(gaps.begin(), gaps.end()); std::sort(durs.begin(), durs.end());
-        printf("GRAPH register-heavy: prev-kernel-entry -> last CTA end median %.2f us;  gap last-CTA-end -> next-kernel-entry  min %.2f median %.2f max %.2f us\n",
-               durs[durs.size() / 2], gaps.front(), gaps[gaps.size() / 2], gaps.back());
-    }
-    cudaError_t e = cudaGetLastError();
-    printf("status %s\n", cudaGetErrorString(e));
+    const int B = 49152;
+    measure("GRAPH 296 CTAs x 3 bulk copies of 48 KB, waited one by one", s, dA, dB, flush, 296, [&] { kernT<<<296, 256, 110 * 1024, s>>>(dA, src, B, 3, 0, 0, 0, sink); });
+    measure("GRAPH ... + the stage read with ordinary loads, two copies per barrier, geometry loads first", s, dA, dB, flush, 296, [&] { kernT<<<296, 256, 110 * 1024, s>>>(dA, src, B, 3, 0, 0, 13, sink); });
+    measure("GRAPH ... + CTAs ending up to 8 us apart", s, dA, dB, flush, 296, [&] { kernT<<<296, 256, 110 * 1024, s>>>(dA, src, B, 3, 0, 8000, 13, sink); });
+    measure("GRAPH ... + sources aligned to 16 bytes only, sizes not a multiple of 128", s, dA, dB, flush, 296, [&] { kernT<<<296, 256, 110 * 1024, s>>>(dA, src, B - 208, 3, 0, 0, 13 + 16, sink); });
+    measure("GRAPH ... + mbarrier invalidated before exit", s, dA, dB, flush, 296, [&] { kernT<<<296, 256, 110 * 1024, s>>>(dA, src, B, 3, 1, 0, 13, sink); });
+    measure("GRAPH 296 CTAs, 120 registers, 2 per SM, bit-sliced style work on what the copies bring", s, dA, dB, flush, 296, [&] { kernTR<<<296, 256, 111 * 1024, s>>>(dA, src, B, 3, sink); });
+    printf("status %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
