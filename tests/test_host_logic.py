@@ -36,3 +36,56 @@ def test_allele_index_rejects_malformed_names():
         api.AlleleIndex(["ecoli_adk_1", "ecoli_adk"])
     idx = api.AlleleIndex(["a_x_1", "b_y_2", "a_x_2"])
     assert list(idx.locus_of) == [0, 1, 0] and list(idx.allow_mask("b,c")) == [0, 1, 0] and list(idx.allow_mask(None)) == [1, 1, 1]
+
+
+def test_sample_lanes_order_errors_and_lane_reuse(monkeypatch):
+    """api.SampleLanes host logic without a GPU (contexts, index upload and the library call replaced): results come back in submission order whatever
+    order the lanes finish in, an exception of one sample reaches its caller only, and the lane that raised goes back to the pool."""
+    import time
+    from metamlst_b200 import api, native
+
+    class FakeCtx:
+        def __init__(self, device):
+            self.device, self.closed = device, False
+
+        def close(self):
+            self.closed = True
+
+    class FakeIndex:
+        def __init__(self, ctx, *a, **k):
+            self.ctx = ctx
+
+    seen = []
+
+    def fake_type_soa(sidx, soa, **kw):
+        seen.append((id(sidx), soa))
+        if soa == "boom":
+            raise RuntimeError("Database is broken")
+        time.sleep(0.05 if soa % 2 == 0 else 0.0)   # even samples finish late
+        return {"sample": soa, "kw": kw}
+
+    monkeypatch.setattr(native, "Context", FakeCtx)
+    monkeypatch.setattr(api, "SampleIndex", FakeIndex)
+    monkeypatch.setattr(api, "type_soa", fake_type_soa)
+    lanes = api.SampleLanes(0, None, [], None, lanes=3)
+    try:
+        got = lanes.map(list(range(10)), minscore=80)
+        assert [g["sample"] for g in got] == list(range(10)) and all(g["kw"] == {"minscore": 80} for g in got)
+        assert len({s for s, _ in seen}) <= 3   # three resident indexes serve all ten samples
+        futs = [lanes.submit(1), lanes.submit("boom"), lanes.submit(3)]
+        assert futs[0].result()["sample"] == 1 and futs[2].result()["sample"] == 3
+        try:
+            futs[1].result()
+            raise AssertionError("the failing sample must raise")
+        except RuntimeError as e:
+            assert "broken" in str(e)
+        assert [g["sample"] for g in lanes.map([5, 6, 7, 8])] == [5, 6, 7, 8]   # the lane that raised is back in the pool: nothing hangs
+    finally:
+        ctxs = list(lanes.ctxs)
+        lanes.close()
+    assert all(c.closed for c in ctxs) and lanes.ctxs == []
+    try:
+        api.SampleLanes(0, None, [], None, lanes=0)
+        raise AssertionError("lanes=0 must be refused")
+    except ValueError:
+        pass
