@@ -34,6 +34,32 @@ def test_ctypes_soa_layout_matches_the_header(tmp_path):
     assert got[-2:] == [packing.PREC_DTYPE.itemsize, C.sizeof(native.Chunk)]
 
 
+def test_ctypes_mirrors_of_the_other_structs_match_the_header(tmp_path):
+    """Every struct that crosses the C-ABI by pointer and is mirrored with ctypes: size and the offset of every field as the C compiler lays them out."""
+    import ctypes as C, os, subprocess
+    from metamlst_b200 import bam
+    inc = os.path.join(os.path.dirname(native.__file__), "..", "include")
+    pairs = [("mmlst_zstream", native.ZStream), ("mmlst_zpileup", native.ZPileup), ("mmlst_score_params", native.ScoreParams), ("mmlst_index", native.Index),
+             ("mmlst_sample_params", native.SampleParams), ("mmlst_sample_result", native.SampleResult), ("mmlst_unpack_opts", bam.UnpackOpts),
+             ("mmlst_bam_info_t", bam.BamInfo)]
+    body = ""
+    for cname, mirror in pairs:
+        body += 'printf(" %%zu", sizeof(%s));' % cname
+        for f, _t in mirror._fields_:
+            body += 'printf(" %%zu", offsetof(%s, %s));' % (cname, f)
+    src = tmp_path / "layout2.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mmlst.h"\nint main(void){' + body + 'return 0;}\n')
+    exe = tmp_path / "layout2"
+    subprocess.check_call(["gcc", "-I", inc, str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    i = 0
+    for cname, mirror in pairs:
+        assert got[i] == C.sizeof(mirror), cname
+        offs = [getattr(mirror, f).offset for f, _t in mirror._fields_]
+        assert got[i + 1:i + 1 + len(offs)] == offs, cname
+        i += 1 + len(offs)
+
+
 @pytest.mark.parametrize("n", [0, 1, 255, 256, 257, 5000, 70001])
 def test_build_runs_is_the_run_length_form_of_tid(n):
     import ctypes as C
