@@ -41,7 +41,7 @@ def test_ctypes_mirrors_of_the_other_structs_match_the_header(tmp_path):
     inc = os.path.join(os.path.dirname(native.__file__), "..", "include")
     pairs = [("mmlst_zstream", native.ZStream), ("mmlst_zpileup", native.ZPileup), ("mmlst_score_params", native.ScoreParams), ("mmlst_index", native.Index),
              ("mmlst_sample_params", native.SampleParams), ("mmlst_sample_result", native.SampleResult), ("mmlst_unpack_opts", bam.UnpackOpts),
-             ("mmlst_bam_info_t", bam.BamInfo)]
+             ("mmlst_bam_info_t", bam.BamInfo), ("mmlst_dev_bam_info_t", bam.DevBamInfo)]
     body = ""
     for cname, mirror in pairs:
         body += 'printf(" %%zu", sizeof(%s));' % cname
